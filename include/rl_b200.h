@@ -1,0 +1,356 @@
+/*
+ * rl_b200.h - C-ABI of the B200-native hot path for rapid-locomotion-rl.
+ *
+ * The reference (dhruvmetha/rapid-locomotion-rl) is pure Python/PyTorch and has no
+ * FFI of its own; the drop-in boundary is its Python object API.
+ * This header is the thin C boundary that the Python mirror of that API binds
+ * with ctypes.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer borrowed for the duration of the call
+ *     unless the name ends in _host; the library keeps no reference to it.
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host,
+ *     so every call is CUDA-graph capturable.
+ *   - return value: 0 = RL_OK, negative = error (rl_last_error() has the text).
+ *   - persistent env state owned by the caller is stored SoA: a `[K][N]` array
+ *     holds field k of env n at `p[k*N + n]`.  Simulator-owned tensors keep the
+ *     PhysX AoS layout (`[N,13]` root rows, `[N,12,2]` dof rows, `[N,NB,3]`
+ *     contact rows).
+ */
+#ifndef RL_B200_H
+#define RL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_OK 0
+#define RL_ERR_BAD_ARG (-1)
+#define RL_ERR_BAD_CFG (-2)
+#define RL_ERR_CUDA (-3)
+#define RL_ERR_NCCL (-4)
+#define RL_ERR_UNSUPPORTED (-5)
+
+#define RL_NUM_DOF 12
+#define RL_NUM_FEET 4
+#define RL_MAX_BODIES 24
+#define RL_MAX_TERMS 21
+#define RL_PRIV_DIM 18
+
+/* Reward term ids; formulas: legged_robot.py:1506-1646 (_reward_<name>). */
+enum RlRewardTerm {
+  RL_REW_TRACKING_LIN_VEL = 0, /* :1578 */
+  RL_REW_TRACKING_ANG_VEL = 1, /* :1614 */
+  RL_REW_LIN_VEL_Z = 2,        /* :1506 */
+  RL_REW_ANG_VEL_XY = 3,       /* :1510 */
+  RL_REW_ORIENTATION = 4,      /* :1514 */
+  RL_REW_TORQUES = 5,          /* :1523 */
+  RL_REW_DOF_ACC = 6,          /* :1539 */
+  RL_REW_BASE_HEIGHT = 7,      /* :1518 */
+  RL_REW_FEET_AIR_TIME = 8,    /* :1619 */
+  RL_REW_COLLISION = 9,        /* :1547 */
+  RL_REW_ACTION_RATE = 10,     /* :1543 */
+  RL_REW_DOF_POS_LIMITS = 11,  /* :1560 */
+  RL_REW_ENERGY = 12,          /* :1527 */
+  RL_REW_ENERGY_EXPENDITURE = 13, /* :1531 */
+  RL_REW_DOF_VEL = 14,         /* :1535 */
+  RL_REW_SURVIVAL = 15,        /* :1556 */
+  RL_REW_DOF_VEL_LIMITS = 16,  /* :1566 */
+  RL_REW_TORQUE_LIMITS = 17,   /* :1573 */
+  RL_REW_STUMBLE = 18,         /* :1633 */
+  RL_REW_STAND_STILL = 19,     /* :1638 */
+  RL_REW_FEET_CONTACT_FORCES = 20, /* :1643 */
+  RL_REW_TERMINATION = 21,     /* :1552, added after the positive clip (:330-334) */
+  RL_REW_COUNT = 22
+};
+
+/* Frozen view of the reference's `Cfg` namespace (legged_robot_config.py:6-256)
+ * plus robot constants, resolved once at env construction (legged_robot.py
+ * _parse_cfg :1417-1429, _init_buffers :935-1028, _prepare_reward_function
+ * :1074-1110, _get_noise_scale_vec :882-932).  Plain data, passed by value. */
+typedef struct RlEnvCfg {
+  int32_t num_envs;
+  int32_t num_bodies;         /* NB: 13 Mini Cheetah, 17 Go1 */
+  int32_t num_actions;        /* >= 12; only the first 12 drive joints (:665) */
+  int32_t num_obs;            /* env.num_observations */
+  int32_t num_height_points;  /* 187 when measure_heights, else 0 */
+  int32_t control_type;       /* 0 'P', 1 'V', 2 'T' (:667-685) */
+  int32_t decimation;         /* control.decimation (:116) */
+  float sim_dt;               /* float32(sim.dt) */
+  float dt;                   /* float32(decimation * sim_dt) (:1418) */
+  float action_scale;         /* control.action_scale */
+  float hip_scale_reduction;  /* control.hip_scale_reduction, dofs 0,3,6,9 (:666) */
+  float clip_actions;         /* normalization.clip_actions (:112) */
+  float clip_obs;             /* normalization.clip_observations (:133) */
+  float p_gains[RL_NUM_DOF];
+  float d_gains[RL_NUM_DOF];
+  float default_dof_pos[RL_NUM_DOF];
+  float torque_limits[RL_NUM_DOF];
+  float dof_pos_lo[RL_NUM_DOF]; /* soft limits (:512-515) */
+  float dof_pos_hi[RL_NUM_DOF];
+  float dof_vel_limits[RL_NUM_DOF];
+  int32_t feet_idx[RL_NUM_FEET];
+  int32_t n_term_bodies;
+  int32_t term_idx[RL_MAX_BODIES]; /* termination_contact_indices (:1295) */
+  int32_t n_pen_bodies;
+  int32_t pen_idx[RL_MAX_BODIES];  /* penalised_contact_indices (:1288) */
+  /* rewards: enabled terms in reward_names order; scale already multiplied by dt
+   * in double then rounded to float (:1084, :322).  Row i of episode_sums /
+   * command_sums belongs to enabled term i; when scales.termination != 0 row
+   * n_terms is "termination"; n_sum_keys = n_terms + has_termination. */
+  int32_t n_terms;
+  int32_t term_id[RL_MAX_TERMS];
+  float term_scale[RL_MAX_TERMS];
+  int32_t has_termination;         /* scales.termination != 0 (:330-334) */
+  float termination_scale;
+  int32_t n_sum_keys;              /* len(reward_scales); episode "total" row = n_sum_keys */
+  int32_t only_positive_rewards;
+  float tracking_sigma;
+  float tracking_sigma_yaw;
+  float base_height_target;
+  float soft_dof_vel_limit;
+  float soft_torque_limit;
+  float max_contact_force;
+  int32_t use_terminal_body_height;
+  float terminal_body_height;
+  int32_t global_reference;        /* commands.global_reference (:1580) */
+  /* observations (:342-417) */
+  int32_t observe_command;
+  int32_t observe_vel;
+  int32_t observe_only_ang_vel;
+  int32_t observe_only_lin_vel;
+  int32_t observe_yaw;
+  int32_t measure_heights;
+  int32_t add_noise;
+  float obs_scale_lin_vel;
+  float obs_scale_ang_vel;
+  float obs_scale_dof_pos;
+  float obs_scale_dof_vel;
+  float obs_scale_height;
+  float commands_scale[3];
+  /* privileged obs: (x - shift) * scale for friction, restitution, payload,
+   * com_displacement, motor_strength (:398-417); scale 0 when not observed */
+  float priv_scale[5];
+  float priv_shift[5];
+  /* teleport (:768-791) */
+  int32_t teleport_robots;
+  float teleport_lo_x;       /* thresh + int(x_offset * horizontal_scale)          (:776) */
+  float teleport_hi_x;       /* terrain_length * num_rows - thresh + x_offset      (:780) */
+  float teleport_shift_x;    /* terrain_length * (num_rows - 1)                    (:777) */
+  float teleport_lo_y;       /* thresh                                             (:783) */
+  float teleport_hi_y;       /* terrain_width * num_cols - thresh                  (:787) */
+  float teleport_shift_y;    /* terrain_width * (num_cols - 1)                     (:784) */
+  /* heights (:1469-1503) */
+  int32_t heights_plane;     /* mesh_type == 'plane' => zeros */
+  float border_size;
+  float horizontal_scale;
+  float vertical_scale;
+  int32_t hf_rows;
+  int32_t hf_cols;
+  /* domain randomisation re-draw inside the step (:591-593, :544-560) and push (:757-766) */
+  int32_t rand_interval;
+  int32_t randomize_motor_strength;
+  int32_t randomize_Kp_factor;
+  int32_t randomize_Kd_factor;
+  /* draws are u * span + lo with span = float32(hi - lo) evaluated in double first,
+   * exactly as the eager expression `rand * (hi - lo) + lo` rounds */
+  float motor_strength_lo_span[2];
+  float Kp_factor_lo_span[2];
+  float Kd_factor_lo_span[2];
+  int32_t push_robots;
+  int32_t push_interval;
+  float push_lo_span[2];     /* (-max_push_vel_xy, 2*max_push_vel_xy) (:764) */
+  /* upstream call order switch: 0 = as written in this fork */
+  int32_t timeout_resets;    /* 1: time_out_buf = ep_len > max_episode_length, OR into reset (:197-198) */
+  int32_t max_episode_length;
+} RlEnvCfg;
+
+/* Buffers of one vectorised env (all device pointers, caller-owned). */
+typedef struct RlEnvBuffers {
+  /* simulator-owned AoS tensors (legged_robot.py:950-971) */
+  float* root_states;           /* [N,13] in/out: teleport and push write back */
+  const float* dof_state;       /* [N,12,2] */
+  const float* contact_forces;  /* [N,NB,3] */
+  const float* actions_in;      /* [N,num_actions] raw policy output */
+  float* torques;               /* [N,12] out (fused) or in (post_physics) */
+  /* step outputs */
+  float* obs_buf;               /* [N,num_obs] */
+  float* privileged_obs_buf;    /* [N,18] */
+  float* rew_buf;               /* [N] */
+  uint8_t* reset_buf;           /* [N] bool */
+  uint8_t* time_out_buf;        /* [N] bool (only written when timeout_resets) */
+  float* measured_heights;      /* [N,P] or NULL */
+  /* persistent state, SoA [K][N] */
+  float* last_actions;          /* [12][N]; equals the clipped actions after step */
+  float* last_dof_vel;          /* [12][N] */
+  float* last_root_vel;         /* [6][N] */
+  float* joint_pos_target;      /* [12][N] */
+  float* base_lin_vel;          /* [3][N] */
+  float* base_ang_vel;          /* [3][N] */
+  float* projected_gravity;     /* [3][N] */
+  float* Kp_factors;            /* [12][N] */
+  float* Kd_factors;            /* [12][N] */
+  float* motor_strengths;       /* [12][N] */
+  const float* friction_coeffs; /* [N] */
+  const float* restitutions;    /* [N] */
+  const float* payloads;        /* [N] */
+  const float* com_displacements; /* [3][N] */
+  float* feet_air_time;         /* [4][N] */
+  uint8_t* last_contacts;       /* [N,4] bool */
+  int64_t* episode_length_buf;  /* [N] */
+  const float* commands;        /* [N,4] */
+  float* episode_sums;          /* [n_sum_keys+1][N], last row "total" */
+  float* command_sums;          /* [n_sum_keys+5][N], rows after keys: lin_vel_raw,
+                                   ang_vel_raw, lin_vel_residual, ang_vel_residual, ep_timesteps */
+  /* read-only tables */
+  const float* noise_scale_vec; /* [num_obs] (:882-932) */
+  const float* height_points;   /* [P,2] base-frame xy (:1453-1467) */
+  const int16_t* height_samples;/* [hf_rows,hf_cols] (:1141) */
+  /* optional injected uniforms in [0,1) for parity tests; NULL => Philox4x32-10
+   * keyed by (seed, env, step, stream) */
+  const float* noise_u;         /* [N,num_obs]  replaces torch.rand_like (:392) */
+  const float* dr_u;            /* [3][N] motor, Kp, Kd draws (:547-558) */
+  const float* push_u;          /* [2][N] (:764) */
+} RlEnvBuffers;
+
+const char* rl_last_error(void);
+const char* rl_version(void);
+/* sizeof(struct <name>) as compiled into the library (-1 for an unknown name): lets a
+ * binding generated from this header check its layout at load time. */
+int64_t rl_sizeof(const char* name);
+
+/* legged_robot.py:653-688 _compute_torques.  Reads actions_in, dof_state,
+ * Kp/Kd/motor factors; writes torques [N,12] and joint_pos_target.  This is the
+ * entry a real gymapi integration calls `decimation` times per step (:116-126). */
+int rl_env_torques(const RlEnvCfg* cfg_host, const RlEnvBuffers* bufs_host, void* stream);
+
+/* legged_robot.py:139-188 post_physics_step + :133-136 observation clip, with the
+ * torques taken from bufs->torques (already applied to the simulator). */
+int rl_env_post_physics(const RlEnvCfg* cfg_host, const RlEnvBuffers* bufs_host, uint64_t seed,
+                        uint64_t step, void* stream);
+
+/* legged_robot.py:106-137 step() on synthetic simulator state: torques (once;
+ * without physics the `decimation` evaluations are identical) + post-physics
+ * pipeline in ONE kernel.  The benchmark entry (SURVEY 8d metric 1). */
+int rl_env_step_fused(const RlEnvCfg* cfg_host, const RlEnvBuffers* bufs_host, uint64_t seed,
+                      uint64_t step, void* stream);
+
+/* Reset (legged_robot.py:227-290 reset_idx and the helpers it calls). */
+typedef struct RlResetCfg {
+  int32_t num_envs;
+  int32_t n_sum_keys;
+  int32_t custom_origins;           /* mesh_type in heightfield/trimesh (:1389-1404) */
+  int32_t terrain_curriculum;       /* cfg.terrain.curriculum and init_done (:800-803) */
+  int32_t max_terrain_level;        /* cfg.terrain.num_rows (:1401) */
+  int32_t num_terrain_cols;
+  float env_length_half;            /* terrain.env_length / 2 (:806) */
+  float episode_length_s_half;      /* env.episode_length_s * 0.5 (:809) */
+  float base_init_state[13];        /* :1209-1210 */
+  float x_init_range, y_init_range; /* passed as (lower, upper) - quirk (:727-729) */
+  float x_init_offset, y_init_offset;
+  float default_dof_pos[RL_NUM_DOF];
+  int32_t randomize_motor_strength, randomize_Kp_factor, randomize_Kd_factor;
+  float motor_strength_lo_span[2], Kp_factor_lo_span[2], Kd_factor_lo_span[2];
+} RlResetCfg;
+
+typedef struct RlResetBuffers {
+  const uint8_t* mask;       /* [N] nonzero = reset this env; or NULL when ids given */
+  const int64_t* ids;        /* [n_ids] env ids; or NULL when mask given */
+  int32_t n_ids;
+  float* root_states;        /* [N,13] */
+  float* dof_state;          /* [N,12,2] */
+  float* env_origins;        /* [N,3] */
+  int64_t* terrain_levels;   /* [N] */
+  const int64_t* terrain_types; /* [N] */
+  const float* terrain_origins; /* [rows, cols, 3] */
+  const float* commands;     /* [N,4] */
+  float* last_actions;       /* [12][N] */
+  float* last_dof_vel;       /* [12][N] */
+  float* feet_air_time;      /* [4][N] */
+  int64_t* episode_length_buf; /* [N] */
+  uint8_t* reset_buf;        /* [N] */
+  float* Kp_factors, *Kd_factors, *motor_strengths; /* [12][N] */
+  float* episode_sums;       /* [n_sum_keys+1][N]: summed over reset envs then zeroed */
+  double* episode_sum_out;   /* [n_sum_keys+2]: per key sum over reset envs; last = count */
+  float* obs_history;        /* [N,H] or NULL: rows zeroed (history_wrapper.py:34) */
+  int32_t obs_history_len;
+  /* injected uniforms (parity) or NULL => Philox */
+  const float* dr_u;         /* [3][N] */
+  const float* init_u;       /* [2][N] xy init draw (:727) */
+  const float* level_u;      /* [N] randint draw for solved-last-level envs (:813) */
+} RlResetBuffers;
+
+int rl_env_reset(const RlResetCfg* cfg_host, const RlResetBuffers* bufs_host, uint64_t seed,
+                 uint64_t step, void* stream);
+
+/* Grid Adaptive Curriculum (legged_robot.py:595-626 _resample_commands;
+ * curriculum.py:55-68 sample, :102-119 RewardThresholdCurriculum.update). */
+typedef struct RlGacCfg {
+  int32_t num_envs;
+  int32_t n_bins;               /* nx*ny*nz = 5202 */
+  int32_t dims[3];              /* 51, 2, 51 */
+  double bin_size[3];           /* arr[1]-arr[0] per axis (curriculum.py:30) */
+  float lin_threshold;          /* float32(forward_curriculum_threshold * scale_lin) (:606) */
+  float ang_threshold;
+  float ep_len;                 /* min(max_episode_length, int(resampling_time/dt)) (:602-603) */
+  int32_t lin_slot, ang_slot;   /* command_sums rows of tracking_lin_vel / tracking_ang_vel */
+  int32_t n_command_sums;       /* rows of command_sums, all zeroed for resampled envs (:625) */
+  int32_t num_train_envs;       /* only train envs feed the update (:612) */
+} RlGacCfg;
+
+typedef struct RlGacBuffers {
+  const uint8_t* mask;          /* [N] or NULL */
+  const int64_t* ids;           /* [n_ids] or NULL */
+  int32_t n_ids;
+  double* weights;              /* [n_bins] float64 (curriculum.py:49) */
+  const double* centers;        /* [dims0+dims1+dims2] np.linspace values per axis (curriculum.py:28) */
+  const int32_t* nbr_lo;        /* [dims0+dims1+dims2] inclusive neighbour index range per axis index, */
+  const int32_t* nbr_hi;        /*   precomputed on the host in float64 exactly as get_local_bins (:102-108) */
+  int32_t* hit_count;           /* [n_bins] workspace: neighbourhood incidence count */
+  int32_t* own_flag;            /* [n_bins] workspace: bin is the own bin of a successful env */
+  double* cdf;                  /* [n_bins] workspace: normalised inclusive prefix sum */
+  int64_t* env_command_bins;    /* [N] */
+  float* commands;              /* [N,4] */
+  float* command_sums;          /* [n_command_sums][N] */
+  const double* u_bin;          /* [N] injected uniform for the categorical draw, or NULL */
+  const double* u_cell;         /* [N,3] injected uniforms for the in-cell draw, or NULL */
+} RlGacBuffers;
+
+/* phase 1: success test + incidence scatter (int32, order independent) */
+int rl_gac_scatter(const RlGacCfg* cfg_host, const RlGacBuffers* bufs_host, void* stream);
+/* phase 2: saturating weight update (k times w<-min(1,w+0.2)), cdf, sampling, command write.
+ * Between the two phases a multi-GPU caller all-reduces hit_count/own_flag. */
+int rl_gac_update_sample(const RlGacCfg* cfg_host, const RlGacBuffers* bufs_host, uint64_t seed,
+                         uint64_t step, void* stream);
+
+/* rollout_storage.py:76-90 RolloutStorage.compute_returns.
+ *  rewards, values, returns, advantages: [T,N] fp32; dones: [T,N] uint8;
+ *  last_values: [N].  workspace: >= rl_gae_workspace_bytes(N) bytes.
+ *  Phase A scans time in reverse per env and accumulates sum / sum-of-squares of
+ *  the raw advantages in double; phase B normalises with the UNBIASED std (:90).
+ *  `stats_out` (3 doubles: sum, sumsq, count) is filled between the phases so a
+ *  multi-GPU caller can all-reduce it (call rl_gae_scan, reduce, rl_gae_normalize). */
+int64_t rl_gae_workspace_bytes(int32_t num_envs);
+int rl_gae_scan(const float* rewards, const float* values, const uint8_t* dones,
+                const float* last_values, float* returns, float* advantages, int32_t T,
+                int32_t N, float gamma, float lam, void* workspace, double* stats_out,
+                void* stream);
+int rl_gae_normalize(float* advantages, int32_t T, int32_t N, const double* stats, void* stream);
+/* both phases back to back (single GPU) */
+int rl_gae(const float* rewards, const float* values, const uint8_t* dones,
+           const float* last_values, float* returns, float* advantages, int32_t T, int32_t N,
+           float gamma, float lam, void* workspace, void* stream);
+
+/* history_wrapper.py:23 - append obs to a 2H-slot ring so that the last H steps are
+ * always one contiguous row span: hist [N, 2*H*num_obs], writes slots k and k+H. */
+int rl_history_push(float* hist, const float* obs, int32_t N, int32_t num_obs, int32_t H,
+                    int32_t slot, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL_B200_H */

@@ -1,0 +1,714 @@
+// Fused per-step env pipeline of LeggedRobot (mini_gym/envs/base/legged_robot.py).
+//
+// One launch replaces ~415 ATen ops of LeggedRobot.step (:106-137):
+//   _compute_torques :653-688, post_physics_step :139-188, _teleport_robots :768-791,
+//   _get_heights :1469-1503, _push_robots :757-766, DOF-property re-draw :591-593,
+//   check_termination :190-202, compute_reward :314-340 with every _reward_* :1506-1646,
+//   compute_observations :342-417, last_* updates :181-183, observation clip :133-136.
+//
+// Mapping to B200
+//   * one CTA = one tile of TILE=128 consecutive envs, one thread per env for the scalar
+//     pipeline; grid = ceil(N/128) (256 CTAs at 32768 envs, 2 resident per SM).
+//   * the simulator-owned tensors are AoS rows (13/24/3*NB/12 floats per env).  The CTA
+//     copies the tile's contiguous row span into shared memory with 128-bit coalesced
+//     streaming loads (or one cp.async.bulk per tensor, see stage_bulk), then each thread
+//     reads its own row from shared memory (odd row strides: conflict free).
+//   * state we own is SoA [K][N]: thread n touches p[k*N+n], i.e. every access is a fully
+//     coalesced 128 B line per warp.
+//   * outputs with AoS consumers (obs, privileged obs, torques) are assembled in shared
+//     memory and written back with coalesced 128-bit stores.
+//   * height sampling: one warp per env, lanes over the 187 points, int16 gathers served
+//     from L2 (the 9.4 MB table stays resident), warp-shuffle reduction for the mean.
+// Bound: HBM.  Algorithmic bytes per env-step: 1425 B (Mini Cheetah flat).
+//
+// Numerics: compiled with -fmad=false so every fp32 operation rounds exactly like the
+// op-by-op eager reference; integer results (cell indices, resets, counters) are exact.
+#include "rl_common.cuh"
+
+namespace rl {
+
+constexpr int TILE = 128;           // envs per CTA == threads per CTA
+constexpr int ND = RL_NUM_DOF;
+
+struct StepArgs {
+  RlEnvCfg cfg;
+  RlEnvBuffers b;
+  uint64_t seed;
+  uint64_t step;
+};
+
+// ---------------------------------------------------------------------------------------
+// cooperative tile copies
+// ---------------------------------------------------------------------------------------
+__device__ inline void stage_in(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
+  // src tile start is 16 B aligned whenever the tensor base is (TILE*row*4 is a multiple of 16)
+  if ((((uintptr_t)src) & 15) == 0) {
+    const int n4 = n_floats >> 2;
+    for (int i = threadIdx.x; i < n4; i += TILE)
+      reinterpret_cast<float4*>(dst)[i] = ldg_stream4(src + 4 * i);
+    for (int i = (n4 << 2) + threadIdx.x; i < n_floats; i += TILE) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < n_floats; i += TILE) dst[i] = __ldg(src + i);
+  }
+}
+
+__device__ inline void stage_out(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
+  if ((((uintptr_t)dst) & 15) == 0) {
+    const int n4 = n_floats >> 2;
+    for (int i = threadIdx.x; i < n4; i += TILE)
+      stg_stream4(dst + 4 * i, reinterpret_cast<const float4*>(src)[i]);
+    for (int i = (n4 << 2) + threadIdx.x; i < n_floats; i += TILE) dst[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < n_floats; i += TILE) dst[i] = src[i];
+  }
+}
+
+// rows of `width` floats in smem (dense) -> global rows with pitch `pitch`
+__device__ inline void stage_out_rows(float* __restrict__ dst, const float* __restrict__ src, int rows,
+                                      int width, int pitch) {
+  const int total = rows * width;
+  for (int i = threadIdx.x; i < total; i += TILE) {
+    const int r = i / width, c = i - r * width;
+    dst[(size_t)r * pitch + c] = src[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// small math, written in the reference's operation order
+// ---------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+
+// isaacgym.torch_utils.quat_rotate_inverse (xyzw): a - b + c with
+// a = v*(2w^2-1), b = cross(qv,v)*w*2, c = qv*dot(qv,v)*2
+__device__ inline V3 quat_rotate_inverse(float qx, float qy, float qz, float qw, V3 v) {
+  const float s = 2.0f * (qw * qw) - 1.0f;
+  V3 a = {v.x * s, v.y * s, v.z * s};
+  V3 cr = {qy * v.z - qz * v.y, qz * v.x - qx * v.z, qx * v.y - qy * v.x};
+  V3 b = {cr.x * qw * 2.0f, cr.y * qw * 2.0f, cr.z * qw * 2.0f};
+  const float d = (qx * v.x + qy * v.y) + qz * v.z;
+  V3 c = {qx * d * 2.0f, qy * d * 2.0f, qz * d * 2.0f};
+  return {a.x - b.x + c.x, a.y - b.y + c.y, a.z - b.z + c.z};
+}
+
+// isaacgym.torch_utils.quat_apply: v + w*t + cross(qv,t), t = 2*cross(qv,v)
+__device__ inline V3 quat_apply(float qx, float qy, float qz, float qw, V3 v) {
+  V3 t = {(qy * v.z - qz * v.y) * 2.0f, (qz * v.x - qx * v.z) * 2.0f, (qx * v.y - qy * v.x) * 2.0f};
+  V3 c = {qy * t.z - qz * t.y, qz * t.x - qx * t.z, qx * t.y - qy * t.x};
+  return {v.x + qw * t.x + c.x, v.y + qw * t.y + c.y, v.z + qw * t.z + c.z};
+}
+
+__device__ inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ inline float sq(float x) { return x * x; }
+
+// torch.remainder for floats (sign follows the divisor) - math_utils.py:20 `angles %= 2*pi`
+__device__ inline float py_mod(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.0f && ((b < 0.0f) != (m < 0.0f))) m += b;
+  return m;
+}
+
+// uniform for obs column c of env e: injected or Philox
+struct NoiseGen {
+  const float* inj;      // row pointer into noise_u or nullptr
+  uint64_t seed, step;
+  uint32_t env;
+  int cached_block;
+  float u[4];
+  __device__ NoiseGen(const float* inj_row, uint64_t seed_, uint64_t step_, uint32_t env_)
+      : inj(inj_row), seed(seed_), step(step_), env(env_), cached_block(-1) {}
+  __device__ inline float get(int c) {
+    if (inj) return inj[c];
+    const int blk = c >> 2;
+    if (blk != cached_block) {
+      rng4(seed, env, step, RNG_NOISE, (uint32_t)blk, u);
+      cached_block = blk;
+    }
+    return u[c & 3];
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------
+template <bool FUSE_TORQUES>
+__global__ void __launch_bounds__(TILE, 2)
+env_step_kernel(const __grid_constant__ StepArgs args) {
+  const RlEnvCfg& cfg = args.cfg;
+  const RlEnvBuffers& b = args.b;
+  const int N = cfg.num_envs;
+  const int NB = cfg.num_bodies;
+  const int tile0 = blockIdx.x * TILE;
+  const int n_valid = min(TILE, N - tile0);
+  const int tid = threadIdx.x;
+  const int e = tile0 + tid;
+  const bool valid = tid < n_valid;
+  const size_t Ns = (size_t)N;
+
+  const int P = cfg.measure_heights ? cfg.num_height_points : 0;
+  const int W = cfg.num_obs - P;  // width of the non-height part of the observation
+
+  extern __shared__ __align__(16) float smem[];
+  float* s_root = smem;                         // [TILE][13]
+  float* s_dof = s_root + TILE * 13 + 0;        // [TILE][24]   (TILE*13*4 is a multiple of 16)
+  float* s_con = s_dof + TILE * 24;             // [TILE][NB*3]
+  float* s_act = s_con + TILE * NB * 3;         // [TILE][12]
+  float* s_tq = s_act + TILE * ND;              // [TILE][12]
+  float* s_priv = s_tq + TILE * ND;             // [TILE][18]
+  float* s_obs = s_priv + TILE * RL_PRIV_DIM;   // [TILE][W]
+  float* s_hmean = s_obs + TILE * W;            // [TILE] mean(z - h)
+  __shared__ int s_root_dirty;
+
+  // ---- 1. stage the simulator-owned rows of this tile into shared memory ---------------
+  stage_in(s_root, b.root_states + (size_t)tile0 * 13, n_valid * 13);
+  stage_in(s_dof, b.dof_state + (size_t)tile0 * 24, n_valid * 24);
+  stage_in(s_con, b.contact_forces + (size_t)tile0 * NB * 3, n_valid * NB * 3);
+  stage_in(s_act, b.actions_in + (size_t)tile0 * ND, n_valid * ND);
+  if (!FUSE_TORQUES) stage_in(s_tq, b.torques + (size_t)tile0 * ND, n_valid * ND);
+  if (tid == 0) s_root_dirty = 0;
+
+  // ---- 2. issue the SoA state loads early so they overlap the staging ------------------
+  constexpr int MAXR_E = RL_MAX_TERMS + 2;   // episode rows: terms, [termination], total
+  constexpr int MAXR_C = RL_MAX_TERMS + 6;   // command rows: terms, [termination], 5 extras
+  const int n_keys = cfg.n_sum_keys;
+  float kp[ND], kd[ND], ms[ND], la[ND], ldv[ND];
+  float es[MAXR_E], cs[MAXR_C];
+  float air[RL_NUM_FEET];
+  float fr = 0.f, re = 0.f, pl = 0.f, com[3] = {0.f, 0.f, 0.f};
+  uint32_t last_contacts = 0;
+  int64_t ep_len = 0;
+  float4 cmd = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      kp[j] = b.Kp_factors[j * Ns + e];
+      kd[j] = b.Kd_factors[j * Ns + e];
+      ms[j] = b.motor_strengths[j * Ns + e];
+      la[j] = b.last_actions[j * Ns + e];
+      ldv[j] = b.last_dof_vel[j * Ns + e];
+    }
+#pragma unroll
+    for (int r = 0; r < MAXR_E; ++r) es[r] = (r <= n_keys) ? b.episode_sums[r * Ns + e] : 0.f;
+#pragma unroll
+    for (int r = 0; r < MAXR_C; ++r) cs[r] = (r < n_keys + 5) ? b.command_sums[r * Ns + e] : 0.f;
+#pragma unroll
+    for (int k = 0; k < RL_NUM_FEET; ++k) air[k] = b.feet_air_time[k * Ns + e];
+    last_contacts = *reinterpret_cast<const uint32_t*>(b.last_contacts + (size_t)e * 4);
+    fr = b.friction_coeffs[e]; re = b.restitutions[e]; pl = b.payloads[e];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) com[k] = b.com_displacements[k * Ns + e];
+    ep_len = b.episode_length_buf[e];
+    cmd = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
+  }
+  __syncthreads();
+
+  // ---- 3. counters, teleport (:152, :768-791) --------------------------------------------
+  float* root = s_root + tid * 13;
+  bool dirty = false;
+  if (valid) {
+    ep_len += 1;
+    if (cfg.teleport_robots) {
+      float x = root[0], y = root[1];
+      const float x0 = x, y0 = y;
+      if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
+      if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
+      if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
+      if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
+      if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
+    }
+  }
+  if (cfg.measure_heights) __syncthreads();  // teleported positions visible to the height warps
+
+  // ---- 4. terrain heights (:1469-1503): one warp per env, lanes over points -------------
+  if (cfg.measure_heights) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const float hscale = cfg.horizontal_scale, vscale = cfg.vertical_scale;
+    for (int le = warp; le < n_valid; le += TILE / 32) {
+      const float* r = s_root + le * 13;
+      const int ge = tile0 + le;
+      const float bx = r[0], by = r[1], bz = r[2];
+      // quat_apply_yaw (math_utils.py:12-16): zero x,y then normalize
+      float yz = r[5], yw = r[6];
+      float nrm = sqrtf(yz * yz + yw * yw);
+      nrm = fmaxf(nrm, 1e-9f);
+      yz = yz / nrm; yw = yw / nrm;
+      float acc = 0.f;
+      float* mh = b.measured_heights + (size_t)ge * P;
+      float* ob = b.obs_buf + (size_t)ge * cfg.num_obs + W;
+      const float* nu = b.noise_u ? b.noise_u + (size_t)ge * cfg.num_obs : nullptr;
+      for (int p = lane; p < P; p += 32) {
+        float h = 0.f;
+        if (!cfg.heights_plane) {
+          const float px = b.height_points[2 * p], py = b.height_points[2 * p + 1];
+          V3 w = quat_apply(0.f, 0.f, yz, yw, V3{px, py, 0.f});
+          float fx = (w.x + bx + cfg.border_size) / hscale;
+          float fy = (w.y + by + cfg.border_size) / hscale;
+          long long ix = (long long)fx, iy = (long long)fy;  // .long() truncates toward zero
+          ix = max(0ll, min(ix, (long long)cfg.hf_rows - 2));
+          iy = max(0ll, min(iy, (long long)cfg.hf_cols - 2));
+          const int16_t* H = b.height_samples;
+          const int16_t h1 = __ldg(H + ix * cfg.hf_cols + iy);
+          const int16_t h2 = __ldg(H + (ix + 1) * cfg.hf_cols + iy);
+          const int16_t h3 = __ldg(H + ix * cfg.hf_cols + iy + 1);
+          h = (float)min(min(h1, h2), h3) * vscale;
+        }
+        mh[p] = h;
+        acc += bz - h;
+        // observation suffix (:386-389) + noise (:392) + clip (:134)
+        float o = clampf(bz - 0.5f - h, -1.f, 1.f) * cfg.obs_scale_height;
+        if (cfg.add_noise) {
+          const int c = W + p;
+          float u;
+          if (nu) u = nu[c];
+          else {
+            float u4[4];
+            rng4(args.seed, (uint32_t)ge, args.step, RNG_NOISE, (uint32_t)(c >> 2), u4);
+            u = u4[c & 3];
+          }
+          o += (2.0f * u - 1.0f) * b.noise_scale_vec[c];
+        }
+        ob[p] = clampf(o, -cfg.clip_obs, cfg.clip_obs);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) s_hmean[le] = acc / (float)P;
+    }
+    __syncthreads();
+  }
+
+  // ---- 5. per-env scalar pipeline ----------------------------------------------------------
+  if (valid) {
+    const float* con = s_con + tid * NB * 3;
+    float* obs = s_obs + tid * W;
+    float* priv = s_priv + tid * RL_PRIV_DIM;
+
+    // rows of 24 / 12 floats: 128-bit shared loads (a scalar walk would be 8-way bank conflicted)
+    float dof[2 * ND], act[ND], tq[ND];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      *reinterpret_cast<float4*>(dof + 4 * k) = *reinterpret_cast<const float4*>(s_dof + tid * 24 + 4 * k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      *reinterpret_cast<float4*>(act + 4 * k) = *reinterpret_cast<const float4*>(s_act + tid * ND + 4 * k);
+    if (!FUSE_TORQUES) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<float4*>(tq + 4 * k) = *reinterpret_cast<const float4*>(s_tq + tid * ND + 4 * k);
+    }
+
+    const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+    V3 vw = {root[7], root[8], root[9]};
+    const V3 ww = {root[10], root[11], root[12]};
+    const V3 blv = quat_rotate_inverse(qx, qy, qz, qw, vw);
+    const V3 bav = quat_rotate_inverse(qx, qy, qz, qw, ww);
+    const V3 grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+
+    // push (:757-766) - after the body-frame velocity was taken (:160 precedes :588)
+    if (cfg.push_robots && (ep_len % cfg.push_interval) == 0) {
+      float u0, u1;
+      if (b.push_u) { u0 = b.push_u[e]; u1 = b.push_u[Ns + e]; }
+      else { float u4[4]; rng4(args.seed, (uint32_t)e, args.step, RNG_PUSH, 0, u4); u0 = u4[0]; u1 = u4[1]; }
+      vw.x = cfg.push_lo_span[1] * u0 + cfg.push_lo_span[0];
+      vw.y = cfg.push_lo_span[1] * u1 + cfg.push_lo_span[0];
+      root[7] = vw.x; root[8] = vw.y;
+      dirty = true;
+    }
+
+    // per-DOF sweep: torques (:653-688) and the reward partial sums
+    float sum_tq2 = 0.f, sum_acc2 = 0.f, sum_rate2 = 0.f, sum_lim = 0.f, sum_energy = 0.f,
+          sum_energy_pos = 0.f, sum_qd2 = 0.f, sum_qd_lim = 0.f, sum_tq_lim = 0.f, sum_still = 0.f;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const float q = dof[2 * j], qd = dof[2 * j + 1];
+      const float a = clampf(act[j], -cfg.clip_actions, cfg.clip_actions);  // :112-113
+      act[j] = a;
+      if (FUSE_TORQUES) {
+        float t;
+        float as = a * cfg.action_scale;
+        if (j % 3 == 0) as *= cfg.hip_scale_reduction;  // dofs 0,3,6,9 (:666)
+        if (cfg.control_type == 0) {
+          const float jpt = as + cfg.default_dof_pos[j];
+          b.joint_pos_target[j * Ns + e] = jpt;
+          t = cfg.p_gains[j] * kp[j] * (jpt - q) - cfg.d_gains[j] * kd[j] * qd;
+        } else if (cfg.control_type == 1) {
+          t = cfg.p_gains[j] * (as - qd) - cfg.d_gains[j] * (qd - ldv[j]) / cfg.sim_dt;
+        } else {
+          t = as;
+        }
+        t = t * ms[j];
+        tq[j] = clampf(t, -cfg.torque_limits[j], cfg.torque_limits[j]);
+      }
+      const float t = tq[j];
+      sum_tq2 += sq(t);
+      sum_acc2 += sq((ldv[j] - qd) / cfg.dt);
+      sum_rate2 += sq(la[j] - a);
+      {
+        float o = -fminf(q - cfg.dof_pos_lo[j], 0.f);
+        o += fmaxf(q - cfg.dof_pos_hi[j], 0.f);
+        sum_lim += o;
+      }
+      const float pw = t * qd;
+      sum_energy += pw;
+      sum_energy_pos += clampf(pw, 0.f, 1e30f);
+      sum_qd2 += sq(qd);
+      sum_qd_lim += clampf(fabsf(qd) - cfg.dof_vel_limits[j] * cfg.soft_dof_vel_limit, 0.f, 1.f);
+      sum_tq_lim += fmaxf(fabsf(t) - cfg.torque_limits[j] * cfg.soft_torque_limit, 0.f);
+      sum_still += fabsf(q - cfg.default_dof_pos[j]);
+      // last_* updates (:181-182)
+      b.last_actions[j * Ns + e] = a;
+      b.last_dof_vel[j * Ns + e] = qd;
+    }
+    if (FUSE_TORQUES) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<float4*>(s_tq + tid * ND + 4 * k) = *reinterpret_cast<float4*>(tq + 4 * k);
+    }
+
+    // DOF-property re-draw for envs whose episode clock hits the interval (:591-593,:544-560)
+    if ((ep_len % cfg.rand_interval) == 0 &&
+        (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor)) {
+      float u3[4];
+      if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[Ns + e]; u3[2] = b.dr_u[2 * Ns + e]; }
+      else rng4(args.seed, (uint32_t)e, args.step, RNG_DR, 0, u3);
+      if (cfg.randomize_motor_strength) {
+        const float v = u3[0] * cfg.motor_strength_lo_span[1] + cfg.motor_strength_lo_span[0];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) { ms[j] = v; b.motor_strengths[j * Ns + e] = v; }
+      }
+      if (cfg.randomize_Kp_factor) {
+        const float v = u3[1] * cfg.Kp_factor_lo_span[1] + cfg.Kp_factor_lo_span[0];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) b.Kp_factors[j * Ns + e] = v;
+      }
+      if (cfg.randomize_Kd_factor) {
+        const float v = u3[2] * cfg.Kd_factor_lo_span[1] + cfg.Kd_factor_lo_span[0];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) b.Kd_factors[j * Ns + e] = v;
+      }
+    }
+
+    // ---- termination (:190-202) --------------------------------------------------------------
+    const float hmean = cfg.measure_heights ? s_hmean[tid] : root[2];  // mean(z - measured_heights)
+    bool reset = false;
+    for (int k = 0; k < cfg.n_term_bodies; ++k) {
+      const float* f = con + cfg.term_idx[k] * 3;
+      const float nrm = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
+      reset |= nrm > 1.0f;
+    }
+    bool time_out = false;
+    if (cfg.timeout_resets) {
+      time_out = ep_len > (int64_t)cfg.max_episode_length;
+      reset |= time_out;
+      b.time_out_buf[e] = time_out ? 1 : 0;
+    }
+    if (cfg.use_terminal_body_height) reset |= hmean < cfg.terminal_body_height;
+    b.reset_buf[e] = reset ? 1 : 0;
+
+    // ---- reward terms (:1506-1646) -----------------------------------------------------------
+    const float cmd_xy_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y);
+    float term_val[RL_REW_COUNT];
+    {
+      const float vx = cfg.global_reference ? vw.x : blv.x, vy = cfg.global_reference ? vw.y : blv.y;
+      const float lin_err = sq(cmd.x - vx) + sq(cmd.y - vy);
+      term_val[RL_REW_TRACKING_LIN_VEL] = expf(-lin_err / cfg.tracking_sigma);
+      term_val[RL_REW_TRACKING_ANG_VEL] = expf(-sq(cmd.z - bav.z) / cfg.tracking_sigma_yaw);
+      term_val[RL_REW_LIN_VEL_Z] = sq(blv.z);
+      term_val[RL_REW_ANG_VEL_XY] = sq(bav.x) + sq(bav.y);
+      term_val[RL_REW_ORIENTATION] = sq(grav.x) + sq(grav.y);
+      term_val[RL_REW_TORQUES] = sum_tq2;
+      term_val[RL_REW_DOF_ACC] = sum_acc2;
+      term_val[RL_REW_BASE_HEIGHT] = sq(hmean - cfg.base_height_target);
+      term_val[RL_REW_ACTION_RATE] = sum_rate2;
+      term_val[RL_REW_DOF_POS_LIMITS] = sum_lim;
+      term_val[RL_REW_ENERGY] = sum_energy;
+      term_val[RL_REW_ENERGY_EXPENDITURE] = sum_energy_pos;
+      term_val[RL_REW_DOF_VEL] = sum_qd2;
+      term_val[RL_REW_DOF_VEL_LIMITS] = sum_qd_lim;
+      term_val[RL_REW_TORQUE_LIMITS] = sum_tq_lim;
+      term_val[RL_REW_STAND_STILL] = sum_still * (cmd_xy_norm < 0.1f ? 1.f : 0.f);
+      const bool term_flag = reset && !time_out;  // :1554 reset_buf * ~time_out_buf
+      term_val[RL_REW_TERMINATION] = term_flag ? 1.f : 0.f;
+      term_val[RL_REW_SURVIVAL] = term_flag ? 0.f : 1.f;
+      float coll = 0.f;
+      for (int k = 0; k < cfg.n_pen_bodies; ++k) {
+        const float* f = con + cfg.pen_idx[k] * 3;
+        const float nrm = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
+        coll += (nrm > 0.1f) ? 1.f : 0.f;
+      }
+      term_val[RL_REW_COLLISION] = coll;
+      bool stumble = false;
+      float fcf = 0.f;
+#pragma unroll
+      for (int k = 0; k < RL_NUM_FEET; ++k) {
+        const float* f = con + cfg.feet_idx[k] * 3;
+        stumble |= sqrtf(f[0] * f[0] + f[1] * f[1]) > 5.0f * fabsf(f[2]);
+        fcf += fmaxf(sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) - cfg.max_contact_force, 0.f);
+      }
+      term_val[RL_REW_STUMBLE] = stumble ? 1.f : 0.f;
+      term_val[RL_REW_FEET_CONTACT_FORCES] = fcf;
+      term_val[RL_REW_FEET_AIR_TIME] = 0.f;
+    }
+
+    // ---- compute_reward (:314-340): ordered accumulation ----------------------------------------
+    float rew = 0.f;
+    bool air_touched = false;
+#pragma unroll
+    for (int i = 0; i < RL_MAX_TERMS; ++i) {
+      if (i < cfg.n_terms) {
+        const int id = cfg.term_id[i];
+        float v = 0.f;
+        if (id == RL_REW_FEET_AIR_TIME) {
+          // stateful term (:1619-1631); its state only advances when the term is enabled
+          uint32_t nc = 0;
+          float r_air = 0.f;
+#pragma unroll
+          for (int k = 0; k < RL_NUM_FEET; ++k) {
+            const bool contact = con[cfg.feet_idx[k] * 3 + 2] > 1.0f;
+            const bool filt = contact || ((last_contacts >> (8 * k)) & 0xffu);
+            nc |= (contact ? 1u : 0u) << (8 * k);
+            const bool first = (air[k] > 0.f) && filt;
+            air[k] += cfg.dt;
+            r_air += (air[k] - 0.5f) * (first ? 1.f : 0.f);
+            air[k] *= filt ? 0.f : 1.f;
+          }
+          last_contacts = nc;
+          air_touched = true;
+          r_air *= (cmd_xy_norm > 0.1f) ? 1.f : 0.f;
+          v = r_air;
+        } else {
+#pragma unroll
+          for (int t = 0; t < RL_REW_COUNT; ++t) if (t == id) v = term_val[t];
+        }
+        const float r = v * cfg.term_scale[i];
+        rew += r;
+        es[i] += r;
+        cs[i] += r;
+      }
+    }
+    if (cfg.only_positive_rewards) rew = fmaxf(rew, 0.f);
+    // "total" row and the optional termination row sit at runtime positions; rows are
+    // walked with static indices so the accumulators stay in registers
+    const float r_term = cfg.has_termination ? term_val[RL_REW_TERMINATION] * cfg.termination_scale : 0.f;
+    const float rew_clipped = rew;
+    if (cfg.has_termination) rew += r_term;
+    b.rew_buf[e] = rew;
+    const float extras[5] = {blv.x, bav.z, sq(blv.x - cmd.x), sq(bav.z - cmd.z), 1.0f};
+#pragma unroll
+    for (int r = 0; r < MAXR_E; ++r) {
+      if (cfg.has_termination && r == cfg.n_terms) es[r] += r_term;
+      if (r == n_keys) es[r] += rew_clipped;
+      if (r <= n_keys) b.episode_sums[r * Ns + e] = es[r];
+    }
+#pragma unroll
+    for (int r = 0; r < MAXR_C; ++r) {
+      if (cfg.has_termination && r == cfg.n_terms) cs[r] += r_term;
+#pragma unroll
+      for (int x = 0; x < 5; ++x) if (r == n_keys + x) cs[r] += extras[x];
+      if (r < n_keys + 5) b.command_sums[r * Ns + e] = cs[r];
+    }
+    if (air_touched) {
+#pragma unroll
+      for (int k = 0; k < RL_NUM_FEET; ++k) b.feet_air_time[k * Ns + e] = air[k];
+      *reinterpret_cast<uint32_t*>(b.last_contacts + (size_t)e * 4) = last_contacts;
+    }
+
+    // ---- observations (:342-392), emitted in column order with noise (:392) and clip (:134) -----
+    {
+      NoiseGen ng(b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr, args.seed, args.step, (uint32_t)e);
+      int c = 0;
+      auto emit = [&](float v) {
+        if (cfg.add_noise) {
+          const float ns = b.noise_scale_vec[c];
+          if (ns != 0.f) v += (2.0f * ng.get(c) - 1.0f) * ns;
+        }
+        obs[c] = clampf(v, -cfg.clip_obs, cfg.clip_obs);
+        ++c;
+      };
+      if (cfg.observe_only_lin_vel) {
+        emit(blv.x * cfg.obs_scale_lin_vel); emit(blv.y * cfg.obs_scale_lin_vel); emit(blv.z * cfg.obs_scale_lin_vel);
+      }
+      if (cfg.observe_only_ang_vel) {
+        emit(bav.x * cfg.obs_scale_ang_vel); emit(bav.y * cfg.obs_scale_ang_vel); emit(bav.z * cfg.obs_scale_ang_vel);
+      }
+      if (cfg.observe_vel) {
+        const V3 lv = cfg.global_reference ? vw : blv;
+        emit(lv.x * cfg.obs_scale_lin_vel); emit(lv.y * cfg.obs_scale_lin_vel); emit(lv.z * cfg.obs_scale_lin_vel);
+        emit(bav.x * cfg.obs_scale_ang_vel); emit(bav.y * cfg.obs_scale_ang_vel); emit(bav.z * cfg.obs_scale_ang_vel);
+      }
+      emit(grav.x); emit(grav.y); emit(grav.z);
+      if (cfg.observe_command) {
+        emit(cmd.x * cfg.commands_scale[0]); emit(cmd.y * cfg.commands_scale[1]); emit(cmd.z * cfg.commands_scale[2]);
+      }
+#pragma unroll
+      for (int j = 0; j < ND; ++j) emit((dof[2 * j] - cfg.default_dof_pos[j]) * cfg.obs_scale_dof_pos);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) emit(dof[2 * j + 1] * cfg.obs_scale_dof_vel);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) emit(act[j]);
+      if (cfg.observe_yaw) {
+        const V3 fwd = quat_apply(qx, qy, qz, qw, V3{1.f, 0.f, 0.f});
+        float heading = atan2f(fwd.y, fwd.x);
+        const float two_pi = 6.283185307179586f;
+        heading = py_mod(heading, two_pi);
+        heading -= two_pi * (heading > 3.141592653589793f ? 1.f : 0.f);
+        emit(clampf(0.5f * heading, -1.f, 1.f));
+      }
+    }
+
+    // ---- privileged observations (:398-417) + clip (:136) ------------------------------------------
+    {
+      const float co = cfg.clip_obs;
+      float pv[RL_PRIV_DIM];
+      pv[0] = (fr - cfg.priv_shift[0]) * cfg.priv_scale[0];
+      pv[1] = (re - cfg.priv_shift[1]) * cfg.priv_scale[1];
+      pv[2] = (pl - cfg.priv_shift[2]) * cfg.priv_scale[2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pv[3 + k] = (com[k] - cfg.priv_shift[3]) * cfg.priv_scale[3];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) pv[6 + j] = (ms[j] - cfg.priv_shift[4]) * cfg.priv_scale[4];
+      // 18-float rows: 64-bit shared stores are bank-conflict free
+#pragma unroll
+      for (int k = 0; k < RL_PRIV_DIM / 2; ++k)
+        *reinterpret_cast<float2*>(priv + 2 * k) = make_float2(clampf(pv[2 * k], -co, co), clampf(pv[2 * k + 1], -co, co));
+    }
+
+    // ---- remaining state (:152, :160-162, :183) ----------------------------------------------------
+    b.episode_length_buf[e] = ep_len;
+    b.base_lin_vel[0 * Ns + e] = blv.x; b.base_lin_vel[1 * Ns + e] = blv.y; b.base_lin_vel[2 * Ns + e] = blv.z;
+    b.base_ang_vel[0 * Ns + e] = bav.x; b.base_ang_vel[1 * Ns + e] = bav.y; b.base_ang_vel[2 * Ns + e] = bav.z;
+    b.projected_gravity[0 * Ns + e] = grav.x; b.projected_gravity[1 * Ns + e] = grav.y;
+    b.projected_gravity[2 * Ns + e] = grav.z;
+    b.last_root_vel[0 * Ns + e] = vw.x; b.last_root_vel[1 * Ns + e] = vw.y; b.last_root_vel[2 * Ns + e] = vw.z;
+    b.last_root_vel[3 * Ns + e] = ww.x; b.last_root_vel[4 * Ns + e] = ww.y; b.last_root_vel[5 * Ns + e] = ww.z;
+  }
+  if (dirty) s_root_dirty = 1;
+  __syncthreads();
+
+  // ---- 6. coalesced write-back of the AoS outputs -------------------------------------------------
+  if (W == cfg.num_obs) stage_out(b.obs_buf + (size_t)tile0 * W, s_obs, n_valid * W);
+  else stage_out_rows(b.obs_buf + (size_t)tile0 * cfg.num_obs, s_obs, n_valid, W, cfg.num_obs);
+  stage_out(b.privileged_obs_buf + (size_t)tile0 * RL_PRIV_DIM, s_priv, n_valid * RL_PRIV_DIM);
+  if (FUSE_TORQUES) stage_out(b.torques + (size_t)tile0 * ND, s_tq, n_valid * ND);
+  if (s_root_dirty) stage_out(b.root_states + (size_t)tile0 * 13, s_root, n_valid * 13);
+}
+
+// standalone PD torques (:653-688) for the real-simulator path: called `decimation` times
+__global__ void __launch_bounds__(128)
+env_torques_kernel(const __grid_constant__ StepArgs args) {
+  const RlEnvCfg& cfg = args.cfg;
+  const RlEnvBuffers& b = args.b;
+  const int N = cfg.num_envs;
+  const size_t Ns = (size_t)N;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  // rows are 48 B / 96 B and 16 B aligned: 128-bit row loads (L1 merges neighbouring rows)
+  float act[ND], dof[2 * ND], out[ND];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    *reinterpret_cast<float4*>(act + 4 * k) = *reinterpret_cast<const float4*>(b.actions_in + (size_t)e * ND + 4 * k);
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    *reinterpret_cast<float4*>(dof + 4 * k) = *reinterpret_cast<const float4*>(b.dof_state + (size_t)e * 24 + 4 * k);
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    const float q = dof[2 * j], qd = dof[2 * j + 1];
+    const float a = clampf(act[j], -cfg.clip_actions, cfg.clip_actions);
+    float as = a * cfg.action_scale;
+    if (j % 3 == 0) as *= cfg.hip_scale_reduction;
+    float t;
+    if (cfg.control_type == 0) {
+      const float jpt = as + cfg.default_dof_pos[j];
+      b.joint_pos_target[j * Ns + e] = jpt;
+      t = cfg.p_gains[j] * b.Kp_factors[j * Ns + e] * (jpt - q) - cfg.d_gains[j] * b.Kd_factors[j * Ns + e] * qd;
+    } else if (cfg.control_type == 1) {
+      t = cfg.p_gains[j] * (as - qd) - cfg.d_gains[j] * (qd - b.last_dof_vel[j * Ns + e]) / cfg.sim_dt;
+    } else {
+      t = as;
+    }
+    t = t * b.motor_strengths[j * Ns + e];
+    out[j] = clampf(t, -cfg.torque_limits[j], cfg.torque_limits[j]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    *reinterpret_cast<float4*>(b.torques + (size_t)e * ND + 4 * k) = *reinterpret_cast<float4*>(out + 4 * k);
+}
+
+static size_t step_smem_bytes(const RlEnvCfg& cfg) {
+  const int P = cfg.measure_heights ? cfg.num_height_points : 0;
+  const int W = cfg.num_obs - P;
+  const size_t floats = (size_t)TILE * (13 + 24 + cfg.num_bodies * 3 + ND + ND + RL_PRIV_DIM + W + 1);
+  return floats * sizeof(float);
+}
+
+static int validate(const RlEnvCfg* cfg, const RlEnvBuffers* b, bool need_torques_in) {
+  RL_REQUIRE(cfg && b, RL_ERR_BAD_ARG, "env step: null cfg/buffers");
+  RL_REQUIRE(cfg->num_envs > 0, RL_ERR_BAD_CFG, "env step: num_envs=%d", cfg->num_envs);
+  RL_REQUIRE(cfg->num_actions == ND, RL_ERR_UNSUPPORTED, "env step: num_actions=%d (only 12 supported)", cfg->num_actions);
+  RL_REQUIRE(cfg->num_bodies > 0 && cfg->num_bodies <= RL_MAX_BODIES, RL_ERR_BAD_CFG, "env step: num_bodies=%d", cfg->num_bodies);
+  RL_REQUIRE(cfg->n_terms >= 0 && cfg->n_terms <= RL_MAX_TERMS, RL_ERR_UNSUPPORTED, "env step: n_terms=%d (max %d enabled reward terms)", cfg->n_terms, RL_MAX_TERMS);
+  RL_REQUIRE(cfg->n_sum_keys == cfg->n_terms + (cfg->has_termination ? 1 : 0), RL_ERR_BAD_CFG, "env step: n_sum_keys=%d inconsistent", cfg->n_sum_keys);
+  RL_REQUIRE(cfg->control_type >= 0 && cfg->control_type <= 2, RL_ERR_BAD_CFG, "env step: control_type=%d", cfg->control_type);
+  RL_REQUIRE(cfg->rand_interval > 0 && (!cfg->push_robots || cfg->push_interval > 0), RL_ERR_BAD_CFG, "env step: intervals must be positive");
+  const int P = cfg->measure_heights ? cfg->num_height_points : 0;
+  RL_REQUIRE(cfg->num_obs - P > 0, RL_ERR_BAD_CFG, "env step: num_obs=%d <= height points %d", cfg->num_obs, P);
+  RL_REQUIRE(b->root_states && b->dof_state && b->contact_forces && b->actions_in && b->torques &&
+             b->obs_buf && b->privileged_obs_buf && b->rew_buf && b->reset_buf && b->last_actions &&
+             b->last_dof_vel && b->last_root_vel && b->joint_pos_target && b->base_lin_vel &&
+             b->base_ang_vel && b->projected_gravity && b->Kp_factors && b->Kd_factors &&
+             b->motor_strengths && b->friction_coeffs && b->restitutions && b->payloads &&
+             b->com_displacements && b->feet_air_time && b->last_contacts && b->episode_length_buf &&
+             b->commands && b->episode_sums && b->command_sums && b->noise_scale_vec,
+             RL_ERR_BAD_ARG, "env step: a required buffer pointer is null");
+  RL_REQUIRE(((uintptr_t)b->commands & 15) == 0 && ((uintptr_t)b->last_contacts & 3) == 0, RL_ERR_BAD_ARG,
+             "env step: commands must be 16B aligned, last_contacts 4B aligned");
+  if (cfg->measure_heights) {
+    RL_REQUIRE(b->measured_heights && b->height_points, RL_ERR_BAD_ARG, "env step: heights enabled without buffers");
+    RL_REQUIRE(cfg->heights_plane || b->height_samples, RL_ERR_BAD_ARG, "env step: height_samples missing");
+  }
+  if (cfg->timeout_resets) RL_REQUIRE(b->time_out_buf, RL_ERR_BAD_ARG, "env step: time_out_buf missing");
+  (void)need_torques_in;
+  return RL_OK;
+}
+
+template <bool FUSE>
+static int launch_step(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed, uint64_t step, void* stream) {
+  int rc = validate(cfg, b, !FUSE);
+  if (rc != RL_OK) return rc;
+  const size_t smem = step_smem_bytes(*cfg);
+  RL_REQUIRE(smem <= 227 * 1024, RL_ERR_UNSUPPORTED, "env step: tile needs %zu B of shared memory", smem);
+  static size_t configured = 0;  // per template instantiation
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(env_step_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = smem;
+  }
+  StepArgs args;
+  args.cfg = *cfg; args.b = *b; args.seed = seed; args.step = step;
+  const int grid = (cfg->num_envs + TILE - 1) / TILE;
+  env_step_kernel<FUSE><<<grid, TILE, smem, (cudaStream_t)stream>>>(args);
+  return check_launch("env_step_kernel");
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" int rl_env_step_fused(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed, uint64_t step, void* stream) {
+  return launch_step<true>(cfg, b, seed, step, stream);
+}
+
+extern "C" int rl_env_post_physics(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed, uint64_t step, void* stream) {
+  return launch_step<false>(cfg, b, seed, step, stream);
+}
+
+extern "C" int rl_env_torques(const RlEnvCfg* cfg, const RlEnvBuffers* b, void* stream) {
+  RL_REQUIRE(cfg && b, RL_ERR_BAD_ARG, "rl_env_torques: null cfg/buffers");
+  RL_REQUIRE(cfg->num_actions == ND, RL_ERR_UNSUPPORTED, "rl_env_torques: num_actions=%d", cfg->num_actions);
+  RL_REQUIRE(b->actions_in && b->dof_state && b->torques && b->joint_pos_target && b->Kp_factors &&
+             b->Kd_factors && b->motor_strengths && b->last_dof_vel, RL_ERR_BAD_ARG, "rl_env_torques: null buffer");
+  RL_REQUIRE((((uintptr_t)b->actions_in | (uintptr_t)b->dof_state | (uintptr_t)b->torques) & 15) == 0,
+             RL_ERR_BAD_ARG, "rl_env_torques: actions/dof_state/torques must be 16B aligned");
+  StepArgs args;
+  args.cfg = *cfg; args.b = *b; args.seed = 0; args.step = 0;
+  const int grid = (cfg->num_envs + 127) / 128;
+  env_torques_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(args);
+  return check_launch("env_torques_kernel");
+}

@@ -1,0 +1,489 @@
+"""LeggedRobot env core on the fused sm_100a kernels.
+
+Drop-in for mini_gym/envs/base/legged_robot.py (`LeggedRobot` :21, BaseTask buffers
+base_task.py:57-63): same constructor arguments, `step(actions) -> (obs, privileged_obs, rew,
+reset, extras)` (:106-137), `reset()` (base_task.py:103-108), `reset_idx(env_ids)` (:227-290),
+`_resample_commands(env_ids)` (:595-626) and the public attributes the learner / scripts read
+(SURVEY.md 8b).  Everything between the simulator tensors and the returned buffers is one CUDA
+launch per call; there is no eager fallback - without the native library construction fails.
+
+Layout notes: state this class owns is stored SoA `[K, N]` for coalescing; attributes such as
+`last_actions`, `motor_strengths`, `base_lin_vel` are exposed as `[N, K]` transposed views of that
+storage, so indexing and in-place writes behave as in the reference.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..config import (COMMAND_SUM_EXTRAS, TerrainInfo, freeze_env_cfg, lo_span, public_vars, f32)
+from ..robots import robot_for_asset
+from ..sim import SyntheticSim
+from .curriculum import RewardThresholdCurriculum
+
+
+class LeggedRobot:
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True,
+                 eval_cfg=None, initial_dynamics_dict=None, sim=None, terrain=None, seed=0,
+                 gac_rng="philox"):
+        if eval_cfg is not None:
+            raise NotImplementedError("train/eval env split (eval_cfg) is a 'next' row (SURVEY.md 8f3)")
+        self.cfg = cfg
+        self.eval_cfg = None
+        self.sim_params = sim_params
+        self.physics_engine = physics_engine
+        self.sim_device = sim_device
+        self.headless = headless
+        self.device = torch.device(sim_device)
+        if self.device.type != "cuda":
+            raise _lib.RlError("LeggedRobot needs a CUDA device (got %r): the hot path has no CPU fallback" % (sim_device,))
+        self._lib = _lib.lib()
+        self.seed = int(seed)
+        self.gac_rng = gac_rng
+        self.initial_dynamics_dict = initial_dynamics_dict
+        self.init_done = False
+
+        # ---- _parse_cfg (:1417-1429) + asset facts + terrain ----
+        robot = robot_for_asset(cfg.asset.file)
+        if terrain is None:
+            terrain = TerrainInfo(cfg.terrain)
+        self.terrain = terrain
+        sim_dt = None if sim_params is None else getattr(sim_params, "dt", None)
+        p = self.params = freeze_env_cfg(cfg, robot, terrain, sim_dt)
+        if cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
+            cfg.terrain.curriculum = False
+        self.dt = p.dt_double
+        self.obs_scales = cfg.normalization.obs_scales
+        self.reward_scales = dict(p.reward_scales)
+        self.reward_names = list(p.reward_names)
+        self.reward_functions = [getattr(self, "_reward_" + n) for n in self.reward_names]
+        cfg.command_ranges = public_vars(cfg.commands)
+        cfg.env.max_episode_length = p.max_episode_length_f
+        self.max_episode_length = p.max_episode_length_f
+        cfg.domain_rand.push_interval = float(p.push_interval)
+        cfg.domain_rand.rand_interval = float(p.rand_interval)
+        cfg.env.num_height_points = len(p.height_points)
+
+        N = self.num_envs = p.num_envs
+        self.num_train_envs, self.num_eval_envs = N, 0
+        self.num_obs, self.num_privileged_obs, self.num_actions = p.num_obs, p.num_privileged_obs, p.num_actions
+        self.num_dof = self.num_dofs = robot.num_dof
+        self.num_bodies = robot.num_bodies
+        self.dof_names = list(robot.dof_names)
+        dev = self.device
+
+        def z(*shape, dtype=torch.float):
+            return torch.zeros(*shape, dtype=dtype, device=dev)
+
+        # ---- simulator tensors (:939-971); identity actor index tables (one actor per env) ----
+        self.sim = sim if sim is not None else SyntheticSim(robot, N, dev)
+        self.all_root_states = self.root_states = self.sim.root_states
+        self.all_dof_state = self.dof_state = self.sim.dof_state
+        self.all_contact_forces = self.sim.contact_forces
+        self.all_rigid_body_state = self.rigid_body_state = self.sim.rigid_body_state
+        self.dof_pos = self.dof_state.view(N, self.num_dof, 2)[..., 0]
+        self.dof_vel = self.dof_state.view(N, self.num_dof, 2)[..., 1]
+        self.base_quat = self.root_states[:, 3:7]
+        self.contact_forces = self.all_contact_forces.view(N, -1, 3)
+
+        # ---- BaseTask buffers (base_task.py:57-63) ----
+        self.obs_buf = z(N, self.num_obs)
+        self.privileged_obs_buf = z(N, self.num_privileged_obs)
+        self.rew_buf = z(N)
+        self._reset_u8 = torch.ones(N, dtype=torch.uint8, device=dev)
+        self.reset_buf = self._reset_u8.view(torch.bool)
+        self.episode_length_buf = z(N, dtype=torch.long)
+        self._time_out_u8 = z(N, dtype=torch.uint8)
+        self.time_out_buf = self._time_out_u8.view(torch.bool)
+        self.extras = {}
+
+        # ---- persistent state, SoA storage with [N,K] views ----
+        nd = self.num_dof
+        self._last_actions = z(nd, N); self.last_actions = self._last_actions.t()
+        self.actions = self.last_actions  # equal after every step (:181)
+        self._last_dof_vel = z(nd, N); self.last_dof_vel = self._last_dof_vel.t()
+        self._last_root_vel = z(6, N); self.last_root_vel = self._last_root_vel.t()
+        self._joint_pos_target = z(nd, N); self.joint_pos_target = self._joint_pos_target.t()
+        self._base_lin_vel = z(3, N); self.base_lin_vel = self._base_lin_vel.t()
+        self._base_ang_vel = z(3, N); self.base_ang_vel = self._base_ang_vel.t()
+        self._projected_gravity = z(3, N); self.projected_gravity = self._projected_gravity.t()
+        self._Kp = torch.ones(nd, N, device=dev); self.Kp_factors = self._Kp.t()
+        self._Kd = torch.ones(nd, N, device=dev); self.Kd_factors = self._Kd.t()
+        self._motor = torch.ones(nd, N, device=dev); self.motor_strengths = self._motor.t()
+        self.default_friction, self.default_restitution = robot.default_friction, robot.default_restitution
+        self.friction_coeffs = self.default_friction * torch.ones(N, device=dev)
+        self.restitutions = self.default_restitution * torch.ones(N, device=dev)
+        self.payloads = z(N)
+        self._com = z(3, N); self.com_displacements = self._com.t()
+        self._feet_air_time = z(4, N); self.feet_air_time = self._feet_air_time.t()
+        self._last_contacts_u8 = z(N, 4, dtype=torch.uint8)
+        self.last_contacts = self._last_contacts_u8.view(torch.bool)
+        self.torques = z(N, nd)
+        self.commands_value = z(N, cfg.commands.num_commands)
+        self.commands = torch.zeros_like(self.commands_value)
+        self.commands_scale = torch.tensor(p.commands_scale, device=dev)
+        self.measured_heights = z(N, p.num_height_points) if p.measure_heights else 0
+        self._episode_sums = z(p.n_sum_keys + 1, N)
+        self._command_sums = z(p.n_sum_keys + len(COMMAND_SUM_EXTRAS), N)
+        self.episode_sums = {n: self._episode_sums[i] for i, n in enumerate(p.sum_names + ["total"])}
+        self.command_sums = {n: self._command_sums[i] for i, n in enumerate(p.sum_names + COMMAND_SUM_EXTRAS)}
+        self._episode_sum_out = z(p.n_sum_keys + 2, dtype=torch.float64)
+        self.common_step_counter = 0
+
+        # ---- constants as tensors (callers read them) ----
+        self.p_gains = torch.tensor(p.p_gains, device=dev)
+        self.d_gains = torch.tensor(p.d_gains, device=dev)
+        self.default_dof_pos = torch.tensor(p.default_dof_pos, device=dev).unsqueeze(0)
+        self.torque_limits = torch.tensor(p.torque_limits, device=dev)
+        self.dof_vel_limits = torch.tensor(p.dof_vel_limits, device=dev)
+        self.dof_pos_limits = torch.tensor(list(zip(p.dof_pos_lo, p.dof_pos_hi)), device=dev)
+        self.feet_indices = torch.tensor(p.feet_idx, dtype=torch.long, device=dev)
+        self.termination_contact_indices = torch.tensor(p.term_idx[:p.n_term_bodies], dtype=torch.long, device=dev)
+        self.penalised_contact_indices = torch.tensor(p.pen_idx[:p.n_pen_bodies], dtype=torch.long, device=dev)
+        self.noise_scale_vec = torch.from_numpy(p.noise_scale_vec).to(dev)
+        self.add_noise = bool(p.add_noise)
+        self._height_points_xy = torch.from_numpy(p.height_points).to(dev).contiguous()
+        if p.measure_heights:
+            pts = torch.zeros(N, len(p.height_points), 3, device=dev)
+            pts[:, :, :2] = self._height_points_xy
+            self.height_points = pts
+        self.height_samples = None
+        if terrain.custom:
+            self.height_samples = torch.from_numpy(terrain.heightsamples).to(dev).contiguous()
+        self.gravity_vec = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat(N, 1)
+        self.forward_vec = torch.tensor([1.0, 0.0, 0.0], device=dev).repeat(N, 1)
+        base_init = list(cfg.init_state.pos) + list(cfg.init_state.rot) + list(cfg.init_state.lin_vel) + list(cfg.init_state.ang_vel)
+        self.base_init_state = torch.tensor(base_init, dtype=torch.float, device=dev)
+
+        # ---- env origins (:1385-1415) ----
+        self.env_origins = z(N, 3)
+        self.terrain_levels = z(N, dtype=torch.long)
+        self.terrain_types = z(N, dtype=torch.long)
+        self.terrain_origins_t = None
+        self._init_env_origins()
+
+        # ---- domain randomisation initial draw (:1231, :519-541) ----
+        if initial_dynamics_dict is not None:
+            for k, v in initial_dynamics_dict.items():
+                self._set_dynamics(k, v)
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(self.seed)
+        self._randomize_rigid_body_props(torch.arange(N, device=dev), cfg)
+
+        # ---- command curriculum (:1056-1072) ----
+        self._init_command_distribution()
+
+        self._inject = {}     # optional injected uniforms for parity tests
+        self._bufs = self._make_buffers()
+        self._cfg_struct = p.to_struct()
+        self._reset_cfg = self._make_reset_cfg()
+        self.init_done = True
+        self.record_now = self.record_eval_now = False
+
+    # ------------------------------------------------------------------------------------------
+    # construction helpers
+    # ------------------------------------------------------------------------------------------
+    def _set_dynamics(self, key, value):
+        value = value.to(self.device)
+        target = {"friction_coeffs": self.friction_coeffs, "restitutions": self.restitutions,
+                  "payloads": self.payloads, "com_displacements": self.com_displacements,
+                  "motor_strengths": self.motor_strengths, "Kp_factors": self.Kp_factors,
+                  "Kd_factors": self.Kd_factors}.get(key)
+        if target is not None:
+            target.copy_(value)
+
+    def _init_env_origins(self):
+        cfg, N, dev = self.cfg, self.num_envs, self.device
+        if self.terrain.custom:
+            self.custom_origins = True
+            t = cfg.terrain
+            max_lvl, min_lvl = t.max_init_terrain_level, t.min_init_terrain_level
+            if not t.curriculum:
+                max_lvl, min_lvl = t.num_rows - 1, 0
+            g = torch.Generator(device="cpu"); g.manual_seed(self.seed)
+            self.terrain_levels.copy_(torch.randint(min_lvl, max_lvl + 1, (N,), generator=g))
+            self.terrain_types.copy_(torch.div(torch.arange(N), (N / t.num_cols), rounding_mode="floor").to(torch.long))
+            t.max_terrain_level = t.num_rows
+            self.terrain_origins_t = torch.from_numpy(self.terrain.env_origins).to(dev).to(torch.float).contiguous()
+            t.terrain_origins = self.terrain_origins_t
+            self.env_origins[:] = self.terrain_origins_t[self.terrain_levels, self.terrain_types]
+        else:
+            self.custom_origins = False
+            num_cols = np.floor(np.sqrt(N))
+            num_rows = np.ceil(N / num_cols)
+            xx, yy = torch.meshgrid(torch.arange(num_rows), torch.arange(num_cols), indexing="ij")
+            sp = cfg.env.env_spacing
+            self.env_origins[:, 0] = (sp * xx.flatten()[:N]).to(dev)
+            self.env_origins[:, 1] = (sp * yy.flatten()[:N]).to(dev)
+
+    def _init_command_distribution(self):
+        c = self.cfg.commands
+        self.curriculum = RewardThresholdCurriculum(
+            seed=c.curriculum_seed, device=self.device,
+            x_vel=(c.limit_vel_x[0], c.limit_vel_x[1], 51), y_vel=(c.limit_vel_y[0], c.limit_vel_y[1], 2),
+            yaw_vel=(c.limit_vel_yaw[0], c.limit_vel_yaw[1], 51))
+        self._env_command_bins = torch.zeros(self.num_envs, dtype=torch.long, device=self.device)
+        low = np.array([c.lin_vel_x[0], c.lin_vel_y[0], c.ang_vel_yaw[0]])
+        high = np.array([c.lin_vel_x[1], c.lin_vel_y[1], c.ang_vel_yaw[1]])
+        self.curriculum.set_to(low=low, high=high)
+
+    @property
+    def env_command_bins(self):
+        """Device tensor [N] int64 (the reference keeps a host numpy array, :1065)."""
+        return self._env_command_bins
+
+    def _make_buffers(self):
+        b = _lib.RlEnvBuffers()
+        P = _lib.ptr
+        b.root_states = P(self.root_states); b.dof_state = P(self.dof_state)
+        b.contact_forces = P(self.all_contact_forces); b.actions_in = None
+        b.torques = P(self.torques); b.obs_buf = P(self.obs_buf)
+        b.privileged_obs_buf = P(self.privileged_obs_buf); b.rew_buf = P(self.rew_buf)
+        b.reset_buf = P(self._reset_u8); b.time_out_buf = P(self._time_out_u8)
+        b.measured_heights = P(self.measured_heights) if self.params.measure_heights else None
+        b.last_actions = P(self._last_actions); b.last_dof_vel = P(self._last_dof_vel)
+        b.last_root_vel = P(self._last_root_vel); b.joint_pos_target = P(self._joint_pos_target)
+        b.base_lin_vel = P(self._base_lin_vel); b.base_ang_vel = P(self._base_ang_vel)
+        b.projected_gravity = P(self._projected_gravity)
+        b.Kp_factors = P(self._Kp); b.Kd_factors = P(self._Kd); b.motor_strengths = P(self._motor)
+        b.friction_coeffs = P(self.friction_coeffs); b.restitutions = P(self.restitutions)
+        b.payloads = P(self.payloads); b.com_displacements = P(self._com)
+        b.feet_air_time = P(self._feet_air_time); b.last_contacts = P(self._last_contacts_u8)
+        b.episode_length_buf = P(self.episode_length_buf); b.commands = P(self.commands)
+        b.episode_sums = P(self._episode_sums); b.command_sums = P(self._command_sums)
+        b.noise_scale_vec = P(self.noise_scale_vec); b.height_points = P(self._height_points_xy)
+        b.height_samples = P(self.height_samples) if self.height_samples is not None else None
+        b.noise_u = b.dr_u = b.push_u = None
+        return b
+
+    def _make_reset_cfg(self):
+        p, cfg = self.params, self.cfg
+        r = _lib.RlResetCfg()
+        r.num_envs, r.n_sum_keys = p.num_envs, p.n_sum_keys
+        r.custom_origins = int(self.custom_origins)
+        r.terrain_curriculum = int(bool(cfg.terrain.curriculum))
+        r.max_terrain_level = int(getattr(cfg.terrain, "max_terrain_level", cfg.terrain.num_rows))
+        r.num_terrain_cols = int(cfg.terrain.num_cols)
+        r.env_length_half = f32(cfg.terrain.terrain_length / 2)
+        r.episode_length_s_half = f32(cfg.env.episode_length_s * 0.5)
+        for i, v in enumerate(self.base_init_state.tolist()):
+            r.base_init_state[i] = v
+        r.x_init_range, r.y_init_range = f32(cfg.terrain.x_init_range), f32(cfg.terrain.y_init_range)
+        r.x_init_offset, r.y_init_offset = f32(cfg.terrain.x_init_offset), f32(cfg.terrain.y_init_offset)
+        for i, v in enumerate(p.default_dof_pos):
+            r.default_dof_pos[i] = v
+        r.randomize_motor_strength, r.randomize_Kp_factor, r.randomize_Kd_factor = \
+            p.randomize_motor_strength, p.randomize_Kp_factor, p.randomize_Kd_factor
+        for name in ("motor_strength_lo_span", "Kp_factor_lo_span", "Kd_factor_lo_span"):
+            arr = getattr(r, name)
+            arr[0], arr[1] = getattr(p, name)
+        return r
+
+    # ------------------------------------------------------------------------------------------
+    # hot path
+    # ------------------------------------------------------------------------------------------
+    def step(self, actions):
+        """legged_robot.py:106-137.  One fused launch: torques + post-physics pipeline."""
+        actions = actions.to(self.device, torch.float)
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        if actions.shape != (self.num_envs, self.num_actions):
+            raise ValueError("actions must be [%d, %d], got %s" % (self.num_envs, self.num_actions, tuple(actions.shape)))
+        self._actions_in = actions
+        self.common_step_counter += 1
+        b = self._bufs
+        b.actions_in = actions.data_ptr()
+        inj = self._inject
+        b.noise_u = _lib.ptr(inj.get("noise_u")); b.dr_u = _lib.ptr(inj.get("dr_u")); b.push_u = _lib.ptr(inj.get("push_u"))
+        _lib.check(self._lib.rl_env_step_fused(C.byref(self._cfg_struct), C.byref(b), self.seed,
+                                               self.common_step_counter, _lib.current_stream()))
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _compute_torques(self, actions):
+        """legged_robot.py:653-688 as a standalone launch (the entry a real simulator loop calls
+        `decimation` times, :116-126).  Returns the [N,12] torque tensor."""
+        actions = actions.to(self.device, torch.float).contiguous()
+        b = self._bufs
+        b.actions_in = actions.data_ptr()
+        _lib.check(self._lib.rl_env_torques(C.byref(self._cfg_struct), C.byref(b), _lib.current_stream()))
+        return self.torques
+
+    def post_physics_step(self, actions=None):
+        """legged_robot.py:139-188 with the torques already in `self.torques`."""
+        if actions is not None:
+            self._actions_in = actions.to(self.device, torch.float).contiguous()
+        self.common_step_counter += 1
+        b = self._bufs
+        b.actions_in = self._actions_in.data_ptr()
+        inj = self._inject
+        b.noise_u = _lib.ptr(inj.get("noise_u")); b.dr_u = _lib.ptr(inj.get("dr_u")); b.push_u = _lib.ptr(inj.get("push_u"))
+        _lib.check(self._lib.rl_env_post_physics(C.byref(self._cfg_struct), C.byref(b), self.seed,
+                                                 self.common_step_counter, _lib.current_stream()))
+
+    def get_observations(self):
+        return self.obs_buf
+
+    def get_privileged_observations(self, horizon=0):
+        if horizon != 0:
+            raise NotImplementedError("privileged_future_horizon > 0 reads next_privileged_obs_buf, which the "
+                                      "reference never defines (base_task.py:89-97)")
+        return self.privileged_obs_buf
+
+    def reset(self):
+        """base_task.py:103-108."""
+        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        obs, privileged_obs, _, _, _ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return obs, privileged_obs
+
+    def reset_idx(self, env_ids, obs_history=None):
+        """legged_robot.py:227-290 in one launch (+ the host-side uniform command curriculum)."""
+        if len(env_ids) == 0:
+            return
+        env_ids = env_ids.to(self.device, torch.long).contiguous()
+        cfg = self.cfg
+        self._update_command_curriculum_uniform(env_ids)
+        rc = self._reset_cfg
+        rc.terrain_curriculum = int(bool(cfg.terrain.curriculum) and self.init_done)
+        b = _lib.RlResetBuffers()
+        P = _lib.ptr
+        b.mask = None; b.ids = P(env_ids); b.n_ids = int(env_ids.numel())
+        b.root_states = P(self.root_states); b.dof_state = P(self.dof_state); b.env_origins = P(self.env_origins)
+        b.terrain_levels = P(self.terrain_levels); b.terrain_types = P(self.terrain_types)
+        b.terrain_origins = P(self.terrain_origins_t); b.commands = P(self.commands)
+        b.last_actions = P(self._last_actions); b.last_dof_vel = P(self._last_dof_vel)
+        b.feet_air_time = P(self._feet_air_time); b.episode_length_buf = P(self.episode_length_buf)
+        b.reset_buf = P(self._reset_u8)
+        b.Kp_factors = P(self._Kp); b.Kd_factors = P(self._Kd); b.motor_strengths = P(self._motor)
+        b.episode_sums = P(self._episode_sums)
+        self._episode_sum_out.zero_()
+        b.episode_sum_out = P(self._episode_sum_out)
+        b.obs_history = P(obs_history); b.obs_history_len = 0 if obs_history is None else int(obs_history.shape[1])
+        inj = self._inject
+        b.dr_u = P(inj.get("reset_dr_u")); b.init_u = P(inj.get("init_u")); b.level_u = P(inj.get("level_u"))
+        _lib.check(self._lib.rl_env_reset(C.byref(rc), C.byref(b), self.seed, self.common_step_counter,
+                                          _lib.current_stream()))
+        # extras (:261-290): device-side means, no host sync
+        p = self.params
+        sums = self._episode_sum_out
+        means = (sums[:p.n_sum_keys + 1] / sums[p.n_sum_keys + 1]).to(torch.float)
+        self.extras["train/episode"] = {"rew_" + n: means[i] for i, n in enumerate(p.sum_names + ["total"])}
+        if cfg.terrain.curriculum:
+            self.extras["train/episode"]["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
+        if cfg.commands.command_curriculum:
+            self.extras["env_bins"] = self._env_command_bins[:self.num_train_envs].to(torch.float)
+            self.extras["train/episode"]["command_area"] = (self.curriculum.weights_device.sum() / len(self.curriculum))
+        if cfg.commands.yaw_command_curriculum:
+            self.extras["train/episode"]["max_command_yaw"] = cfg.command_ranges["ang_vel_yaw"][1]
+        if cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf[:self.num_train_envs]
+
+    def _update_command_curriculum_uniform(self, env_ids):
+        """legged_robot.py:851-880: rare (every max_episode_length steps) host-side range widening."""
+        cfg = self.cfg
+        if self.common_step_counter % self.max_episode_length != 0:
+            return
+        rs = self.reward_scales
+
+        def widen(key, sum_name, thr, lo_clip, hi_clip):
+            mean = torch.mean(self.episode_sums[sum_name][env_ids]) / self.max_episode_length
+            if mean > thr * rs[sum_name]:
+                r = cfg.command_ranges[key]
+                r[0] = np.clip(r[0] - 0.2, -lo_clip, 0.0)
+                r[1] = np.clip(r[1] + 0.2, 0.0, hi_clip)
+        c = cfg.commands
+        if c.command_curriculum and rs.get("tracking_lin_vel", 0) > 0:
+            widen("lin_vel_x", "tracking_lin_vel", c.forward_curriculum_threshold, c.max_reverse_curriculum,
+                  c.max_forward_curriculum)
+        if c.yaw_command_curriculum and rs.get("tracking_ang_vel", 0) > 0:
+            widen("ang_vel_yaw", "tracking_ang_vel", c.yaw_curriculum_threshold, c.max_yaw_curriculum,
+                  c.max_yaw_curriculum)
+
+    def _randomize_rigid_body_props(self, env_ids, cfg):
+        """legged_robot.py:519-541 (init-time draw; rigid-body props live in the simulator)."""
+        dr, n = cfg.domain_rand, len(env_ids)
+
+        def draw(k=None):
+            shape = (n,) if k is None else (n, k)
+            return torch.rand(*shape, device=self.device, generator=self._gen)
+        if dr.randomize_base_mass:
+            lo, hi = dr.added_mass_range
+            self.payloads[env_ids] = draw() * (hi - lo) + lo
+        if dr.randomize_com_displacement:
+            lo, hi = dr.com_displacement_range
+            self.com_displacements[env_ids, :] = draw(3) * (hi - lo) + lo
+        if dr.randomize_friction:
+            lo, hi = dr.friction_range
+            self.friction_coeffs[env_ids] = draw() * (hi - lo) + lo
+        if dr.randomize_restitution:
+            lo, hi = dr.restitution_range
+            self.restitutions[env_ids] = draw() * (hi - lo) + lo
+
+    def _resample_commands(self, env_ids):
+        """legged_robot.py:595-626 + curriculum.py:110-119,55-68 on the device."""
+        if len(env_ids) == 0:
+            return
+        env_ids = env_ids.to(self.device, torch.long).contiguous()
+        p, cur = self.params, self.curriculum
+        g = _lib.RlGacCfg()
+        g.num_envs, g.n_bins = self.num_envs, len(cur)
+        for i in range(3):
+            g.dims[i] = cur.dims[i]
+            g.bin_size[i] = float(list(cur.bin_sizes.values())[i])
+        timesteps = int(self.cfg.commands.resampling_time / self.dt)
+        g.ep_len = f32(min(self.cfg.env.max_episode_length, timesteps))
+        g.lin_threshold = f32(self.cfg.commands.forward_curriculum_threshold * self.reward_scales["tracking_lin_vel"])
+        g.ang_threshold = f32(self.cfg.commands.yaw_curriculum_threshold * self.reward_scales["tracking_ang_vel"])
+        g.lin_slot, g.ang_slot = p.sum_names.index("tracking_lin_vel"), p.sum_names.index("tracking_ang_vel")
+        g.n_command_sums = self._command_sums.shape[0]
+        g.num_train_envs = self.num_train_envs
+        nlo, nhi = cur.neighbour_ranges(0.5)
+        b = _lib.RlGacBuffers()
+        P = _lib.ptr
+        b.mask = None; b.ids = P(env_ids); b.n_ids = int(env_ids.numel())
+        b.weights = P(cur.weights_device); b.centers = P(cur.centers_device)
+        b.nbr_lo, b.nbr_hi = P(nlo), P(nhi)
+        b.hit_count, b.own_flag, b.cdf = P(cur.hit_count), P(cur.own_flag), P(cur.cdf)
+        b.env_command_bins = P(self._env_command_bins); b.commands = P(self.commands)
+        b.command_sums = P(self._command_sums)
+        u_bin = self._inject.get("gac_u_bin"); u_cell = self._inject.get("gac_u_cell")
+        if u_bin is None and self.gac_rng == "numpy":
+            # replay of the reference's host generator (curriculum.py:57,64): choice() consumes one
+            # uniform per env, then each env draws three - bit-identical command streams
+            n = int(env_ids.numel())
+            ub = cur.rng.random_sample(n)
+            uc = cur.rng.random_sample((n, 3))
+            u_bin = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+            u_cell = torch.zeros(self.num_envs, 3, dtype=torch.float64, device=self.device)
+            u_bin[env_ids] = torch.from_numpy(ub).to(self.device)
+            u_cell[env_ids] = torch.from_numpy(uc).to(self.device)
+        self._gac_keepalive = (u_bin, u_cell, env_ids)
+        b.u_bin, b.u_cell = P(u_bin), P(u_cell)
+        st = _lib.current_stream()
+        _lib.check(self._lib.rl_gac_scatter(C.byref(g), C.byref(b), st))
+        self._gac_allreduce()
+        _lib.check(self._lib.rl_gac_update_sample(C.byref(g), C.byref(b), self.seed, self.common_step_counter, st))
+
+    def _gac_allreduce(self):
+        """Multi-GPU hook: sum the int32 incidence counters over ranks so every rank applies the
+        identical saturating update."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.curriculum.hit_count)
+            dist.all_reduce(self.curriculum.own_flag)
+
+    # ---- reward plugin surface: names resolve like the reference (:1079-1093); the built-in
+    # terms are evaluated inside the fused kernel, these methods return the last per-term value ----
+    def __getattr__(self, name):
+        if name.startswith("_reward_"):
+            term = name[len("_reward_"):]
+            if term in _lib.REWARD_TERM_IDS:
+                return lambda: self._fused_term(term)
+        raise AttributeError("'%s' object has no attribute '%s'" % (type(self).__name__, name))
+
+    def _fused_term(self, term):
+        raise NotImplementedError("reward term %r is evaluated inside the fused kernel; per-term values are "
+                                  "available through episode_sums / command_sums" % term)
+
+    def close(self):
+        pass

@@ -1,0 +1,70 @@
+"""Named test configurations shared by the golden generator (reference side) and the tests
+(oracle / product side).  `case_cfg_hook(case)` mutates a Cfg tree - the reference's params_proto
+`Cfg` or ours, the attribute names are the same."""
+import numpy as np
+
+
+def case_cfg_hook(case):
+    def hook(Cfg):
+        if case == "go1_alt":
+            Cfg.env.observe_vel = True
+            Cfg.env.observe_yaw = True
+            Cfg.env.num_observations = 42 + 6 + 1
+            Cfg.commands.global_reference = False
+            Cfg.domain_rand.push_robots = True
+            Cfg.domain_rand.push_interval_s = 0.1
+            Cfg.domain_rand.randomize_Kp_factor = True
+            Cfg.domain_rand.randomize_Kd_factor = True
+            Cfg.domain_rand.rand_interval_s = 0.06
+            Cfg.rewards.only_positive_rewards = False
+            Cfg.rewards.use_terminal_body_height = True
+            Cfg.rewards.terminal_body_height = 0.29
+            Cfg.rewards.soft_dof_vel_limit = 0.1
+            Cfg.rewards.soft_torque_limit = 0.2
+            Cfg.rewards.max_contact_force = 10.0
+            s = Cfg.rewards.scales
+            s.termination = -5.0
+            s.lin_vel_z = 0.0
+            s.ang_vel_xy = 0.0
+            s.dof_acc = 0.0
+            s.energy = -0.001
+            s.energy_expenditure = -0.002
+            s.dof_vel = -0.0003
+            s.survival = 0.5
+            s.dof_vel_limits = -0.7
+            s.torque_limits = -0.02
+            s.stumble = -0.3
+            s.stand_still = -0.1
+            s.feet_contact_forces = -0.01
+        if case == "mc_rough":
+            Cfg.terrain.num_rows = 2
+            Cfg.terrain.num_cols = 2
+            Cfg.terrain.border_size = 5
+            Cfg.terrain.max_init_terrain_level = 1
+    return hook
+
+
+ENV_CASES = ["mc_flat", "go1", "go1_alt", "mc_rough"]
+
+
+def build_case(case, num_envs):
+    """(cfg, robot, terrain) for our side of a named case."""
+    from rapid_locomotion_rl_b200 import config as C
+    from rapid_locomotion_rl_b200.robots import robot_for_asset
+    from rapid_locomotion_rl_b200.sim import synthetic_heightfield
+    cfg = C.new_cfg()
+    if case.startswith("go1"):
+        C.config_go1(cfg)
+    else:
+        C.config_mini_cheetah(cfg)
+    if case == "mc_rough":
+        C.config_rough(cfg)
+    case_cfg_hook(case)(cfg)
+    cfg.env.num_envs = num_envs
+    cfg.env.record_video = False
+    hs = None
+    if case == "mc_rough":
+        probe = C.TerrainInfo(cfg.terrain)
+        hs = synthetic_heightfield(probe.tot_rows, probe.tot_cols, seed=3)
+    terrain = C.TerrainInfo(cfg.terrain, hs)
+    return cfg, robot_for_asset(cfg.asset.file), terrain

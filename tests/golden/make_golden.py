@@ -1,0 +1,313 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference) on CPU fp32 through the shims in tests/_ref_shims.
+
+    python tests/golden/make_golden.py            # all cases (one subprocess per config: the
+                                                  # reference's Cfg is a process-global class)
+    python tests/golden/make_golden.py mc_flat    # one case
+
+Randomness is injected: torch.rand / rand_like / randint_like are replaced, for the duration of a
+reference call, by a scripted queue fed from uniforms that are also written to the fixture, so the
+oracle and the CUDA kernels can be driven with exactly the numbers the reference consumed.
+tests/test_oracle_vs_golden.py then requires oracle/env_oracle.py to reproduce these tensors bit
+for bit on the CPU - this is what pins the oracle.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
+
+CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "learner"]
+N_ENVS = 48
+N_STEPS = 3
+
+
+from cases import case_cfg_hook  # noqa: E402
+
+
+def synth_inputs(rng, env_like, n, nb, default_dof_pos, feet, term, span_x, span_y, z0):
+    """Per-step simulator state (SURVEY.md 8(d) distribution, scaled to the terrain extent)."""
+    root = np.zeros((n, 13), np.float32)
+    root[:, 0] = rng.uniform(0.5, span_x - 0.5, n)
+    root[:, 1] = rng.uniform(0.5, span_y - 0.5, n)
+    root[:, 2] = z0 + rng.normal(0, 0.02, n)
+    q = np.concatenate([rng.normal(0, 0.15, (n, 3)), np.ones((n, 1))], 1)
+    root[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    root[:, 7:13] = rng.normal(0, 0.5, (n, 6))
+    dof = np.zeros((n, 12, 2), np.float32)
+    dof[:, :, 0] = default_dof_pos[None] + rng.normal(0, 0.6, (n, 12))
+    dof[:, :, 1] = rng.normal(0, 6.0, (n, 12))
+    con = rng.normal(0, 0.5, (n, nb, 3)).astype(np.float32)
+    big = rng.random((n, len(term))) < 0.1
+    for k, b in enumerate(term):
+        con[big[:, k], b] *= 20
+    for b in feet:
+        con[:, b, 2] = np.abs(rng.normal(0, 30, n)) * (rng.random(n) < 0.5)
+    actions = (rng.normal(0, 1, (n, 12)) * np.where(rng.random((n, 1)) < 0.1, 150.0, 1.0)).astype(np.float32)
+    return root, dof, con.astype(np.float32), actions
+
+
+class ScriptedRand:
+    """Replaces torch.rand / rand_like / randint_like with a scripted FIFO for one reference call."""
+
+    def __init__(self, torch, queue):
+        self.torch, self.queue = torch, list(queue)
+
+    def __enter__(self):
+        t = self.torch
+        self.saved = (t.rand, t.rand_like, t.randint_like)
+
+        def pop(shape, what):
+            assert self.queue, "reference asked for %s%s but the script is empty" % (what, tuple(shape))
+            v = self.queue.pop(0)
+            assert tuple(v.shape) == tuple(shape), "%s: scripted %s, requested %s" % (what, tuple(v.shape), tuple(shape))
+            return v.clone()
+
+        def rand(*shape, **kw):
+            if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+                shape = tuple(shape[0])
+            return pop(shape, "rand")
+
+        def rand_like(x, **kw):
+            return pop(x.shape, "rand_like")
+
+        def randint_like(x, *a, **kw):
+            return pop(x.shape, "randint_like").to(x.dtype)
+        t.rand, t.rand_like, t.randint_like = rand, rand_like, randint_like
+        return self
+
+    def __exit__(self, *exc):
+        t = self.torch
+        t.rand, t.rand_like, t.randint_like = self.saved
+        if exc[0] is None:
+            assert not self.queue, "%d scripted draws were not consumed" % len(self.queue)
+        return False
+
+
+def gen_env_case(case):
+    import torch
+    import harness
+    import statekit
+    from rapid_locomotion_rl_b200 import sim as psim
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    robot = "go1" if case.startswith("go1") else "mini_cheetah"
+    rough = case == "mc_rough"
+    hf = (lambda r, c: psim.synthetic_heightfield(r, c, seed=3)) if rough else None
+    env, Cfg = harness.make_reference_env(robot, N_ENVS, rough=rough, height_fn=hf, cfg_hook=case_cfg_hook(case))
+    e = env.env
+    N, NB = e.num_envs, e.num_bodies
+    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31) if False else {"mc_flat": 11, "go1": 12, "go1_alt": 13, "mc_rough": 14}[case])
+    t = Cfg.terrain
+    span_x, span_y = t.terrain_length * t.num_rows, t.terrain_width * t.num_cols
+    out = {}
+    if rough:
+        out["heightsamples"] = e.terrain.heightsamples
+
+    # ---- randomise the persistent state the step reads -------------------------------------------
+    def T(a, dtype=torch.float):
+        return torch.from_numpy(np.asarray(a)).to(dtype)
+    e.commands[:, :3] = T(rng.uniform(-1, 1, (N, 3)).astype(np.float32))
+    e.commands[: N // 8, :2] *= 0.05                      # some near-zero commands (air-time / stand-still gates)
+    e.last_actions[:] = T(rng.normal(0, 1, (N, 12)).astype(np.float32))
+    e.last_dof_vel[:] = T(rng.normal(0, 3, (N, 12)).astype(np.float32))
+    e.motor_strengths[:] = T(rng.uniform(0.9, 1.1, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.Kp_factors[:] = T(rng.uniform(0.8, 1.3, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.Kd_factors[:] = T(rng.uniform(0.5, 1.5, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.friction_coeffs[:] = T(rng.uniform(0.05, 4.5, N).astype(np.float32))
+    e.restitutions[:] = T(rng.uniform(0, 1, N).astype(np.float32))
+    e.payloads[:] = T(rng.uniform(-1, 3, N).astype(np.float32))
+    e.com_displacements[:] = T(rng.uniform(-0.1, 0.1, (N, 3)).astype(np.float32))
+    e.feet_air_time[:] = T((rng.uniform(0, 0.6, (N, 4)) * (rng.random((N, 4)) < 0.7)).astype(np.float32))
+    e.last_contacts = T(rng.random((N, 4)) < 0.3, torch.bool)
+    ri = int(Cfg.domain_rand.rand_interval)
+    ep = rng.integers(0, 1001, N)
+    ep[::7] = ri * rng.integers(1, 3, len(ep[::7])) - 1     # these hit the DOF-property re-draw on step 1
+    if Cfg.domain_rand.push_robots:
+        pi = int(Cfg.domain_rand.push_interval)
+        ep[1::9] = pi * rng.integers(1, 50, len(ep[1::9])) - 2   # pushed on step 2
+    e.episode_length_buf[:] = T(ep, torch.long)
+    for k in e.episode_sums:
+        e.episode_sums[k][:] = T(rng.normal(0, 1, N).astype(np.float32))
+    for k in e.command_sums:
+        e.command_sums[k][:] = T(rng.normal(0, 1, N).astype(np.float32))
+
+    feet = e.feet_indices.tolist(); term = e.termination_contact_indices.tolist()
+    z0 = 0.30 if robot == "mini_cheetah" else 0.34
+    dflt = e.default_dof_pos[0].numpy()
+    meta = dict(case=case, robot=robot, rough=rough, n_envs=N, n_steps=N_STEPS)
+    for s in range(N_STEPS):
+        root, dof, con, actions = synth_inputs(rng, e, N, NB, dflt, feet, term, span_x, span_y, z0)
+        if Cfg.terrain.teleport_robots:   # a few robots inside the teleport band on each side
+            root[0, 0] = 0.7; root[1, 0] = span_x - 1.2; root[2, 1] = 1.1; root[3, 1] = span_y - 0.3
+        e.all_root_states[:] = T(root); e.all_dof_state[:] = T(dof.reshape(-1, 2)); e.all_contact_forces[:] = T(con.reshape(-1, 3))
+        noise_u = rng.random((N, e.num_obs)).astype(np.float32)
+        dr_u = rng.random((3, N)).astype(np.float32)
+        push_u = rng.random((2, N)).astype(np.float32)
+        # canonical "before" state: what this step will read
+        before = statekit.state_from_reference(e)
+        before["root_states"], before["dof_state"], before["contact_forces"] = root, dof, con
+        # script the draws in the order the reference makes them (:588 push, :593 re-draw, :392 noise)
+        epn = e.episode_length_buf.numpy() + 1
+        queue = []
+        if Cfg.domain_rand.push_robots:
+            ids = np.nonzero(epn % int(Cfg.domain_rand.push_interval) == 0)[0]
+            queue.append(T(push_u[:, ids].T.copy()))
+        ids = np.nonzero(epn % ri == 0)[0]
+        if len(ids) > 0:
+            for k, flag in enumerate((Cfg.domain_rand.randomize_motor_strength, Cfg.domain_rand.randomize_Kp_factor,
+                                      Cfg.domain_rand.randomize_Kd_factor)):
+                if flag:
+                    queue.append(T(dr_u[k, ids].copy()))
+        if Cfg.noise.add_noise:
+            queue.append(T(noise_u))
+        with ScriptedRand(torch, queue):
+            obs, priv, rew, reset, _ = type(e).__mro__[1].step(e, T(actions))   # LeggedRobot.step, skipping the numpy extras
+        after = statekit.state_from_reference(e)
+        pre = "step%d/" % s
+        for k, v in before.items():
+            out[pre + "before/" + k] = v
+        for k, v in after.items():
+            out[pre + "after/" + k] = v
+        out[pre + "actions"] = actions; out[pre + "noise_u"] = noise_u; out[pre + "dr_u"] = dr_u; out[pre + "push_u"] = push_u
+        out[pre + "obs"] = obs.numpy().copy(); out[pre + "priv"] = priv.numpy().copy()
+        out[pre + "rew"] = rew.numpy().copy(); out[pre + "reset"] = reset.numpy().copy()
+        if rough:
+            out[pre + "measured_heights"] = e.measured_heights.numpy().copy()
+
+    # ---- reset_idx on a subset (:227-290) ------------------------------------------------------------
+    ids = np.sort(rng.choice(N, N // 3, replace=False))
+    before = statekit.state_from_reference(e)
+    if not e.custom_origins:
+        before["root_states"] = e.all_root_states.numpy().copy()
+    reset_dr_u = rng.random((3, N)).astype(np.float32)
+    init_u = rng.random((2, N)).astype(np.float32)
+    level_u = rng.random(N).astype(np.float32)
+    if Cfg.terrain.curriculum:
+        # make some robots walk far / stay put so terrain levels move both ways; some at the last level
+        e.root_states[ids[::2], :2] = e.env_origins[ids[::2], :2] + 5.0
+        e.terrain_levels[ids[1::4]] = Cfg.terrain.max_terrain_level - 1
+        e.root_states[ids[1::4], :2] = e.env_origins[ids[1::4], :2] + 6.0
+        before = statekit.state_from_reference(e)
+    queue = []
+    if Cfg.terrain.curriculum:
+        queue.append(T(np.minimum((level_u[ids] * Cfg.terrain.max_terrain_level).astype(np.int64),
+                                  Cfg.terrain.max_terrain_level - 1), torch.long))
+    for k, flag in enumerate((Cfg.domain_rand.randomize_motor_strength, Cfg.domain_rand.randomize_Kp_factor,
+                              Cfg.domain_rand.randomize_Kd_factor)):
+        if flag:
+            queue.append(T(reset_dr_u[k, ids].copy()))
+    if e.custom_origins:
+        queue.append(T(init_u[:, ids].T.copy()))
+    e.extras = {}
+    with ScriptedRand(torch, queue):
+        e.reset_idx(T(ids, torch.long))
+    after = statekit.state_from_reference(e)
+    if not e.custom_origins:
+        after["root_states"] = e.all_root_states.numpy().copy()   # plane: the reset writes the sim tensor (:733)
+    after["dof_state"] = e.all_dof_state.numpy().reshape(N, 12, 2).copy()
+    for k, v in before.items():
+        out["reset/before/" + k] = v
+    for k, v in after.items():
+        out["reset/after/" + k] = v
+    out["reset/ids"] = ids; out["reset/dr_u"] = reset_dr_u; out["reset/init_u"] = init_u; out["reset/level_u"] = level_u
+    out["reset/reset_buf"] = e.reset_buf.numpy().copy()
+    for k, v in e.extras["train/episode"].items():
+        if k.startswith("rew_"):
+            out["reset/extras/" + k] = np.float32(v)
+
+    # ---- _resample_commands (:595-626) with the reference's own MT19937 stream ------------------------
+    all_ids = T(np.arange(N), torch.long)
+    e._resample_commands(all_ids)                    # initial draw so every env owns a bin
+    lin_scale, ang_scale = e.reward_scales["tracking_lin_vel"], e.reward_scales["tracking_ang_vel"]
+    e.command_sums["tracking_lin_vel"][:] = T((rng.uniform(0.5, 1.1, N) * 500 * lin_scale).astype(np.float32))
+    e.command_sums["tracking_ang_vel"][:] = T((rng.uniform(0.2, 0.8, N) * 500 * ang_scale).astype(np.float32))
+    for rnd in range(2):
+        ids = np.sort(rng.choice(N, N // 2, replace=False))
+        pre = "resample%d/" % rnd
+        out[pre + "ids"] = ids
+        out[pre + "before/weights"] = e.curriculum.weights.copy()
+        out[pre + "before/bins"] = e.env_command_bins.copy().astype(np.int64)
+        out[pre + "before/commands"] = e.commands.numpy().copy()
+        for k, v in e.command_sums.items():
+            out[pre + "before/command_sums/" + k] = v.numpy().copy()
+        st = e.curriculum.rng.get_state()
+        e._resample_commands(T(ids, torch.long))
+        r2 = np.random.RandomState(); r2.set_state(st)
+        u_bin = np.zeros(N); u_cell = np.zeros((N, 3))
+        u_bin[ids] = r2.random_sample(len(ids))
+        u_cell[ids] = np.stack([r2.random_sample(3) for _ in ids])
+        out[pre + "u_bin"] = u_bin; out[pre + "u_cell"] = u_cell
+        out[pre + "after/weights"] = e.curriculum.weights.copy()
+        out[pre + "after/bins"] = e.env_command_bins.copy().astype(np.int64)
+        out[pre + "after/commands"] = e.commands.numpy().copy()
+        for k, v in e.command_sums.items():
+            out[pre + "after/command_sums/" + k] = v.numpy().copy()
+        e.command_sums["tracking_lin_vel"][:] = T((rng.uniform(0.5, 1.1, N) * 500 * lin_scale).astype(np.float32))
+        e.command_sums["tracking_ang_vel"][:] = T((rng.uniform(0.2, 0.8, N) * 500 * ang_scale).astype(np.float32))
+
+    # ---- constants of the frozen config: known answers for config freezing ---------------------------
+    out["const/dt"] = np.float64(e.dt); out["const/max_episode_length"] = np.float64(e.max_episode_length)
+    out["const/rand_interval"] = np.float64(Cfg.domain_rand.rand_interval)
+    out["const/push_interval"] = np.float64(Cfg.domain_rand.push_interval)
+    out["const/p_gains"] = e.p_gains.numpy(); out["const/d_gains"] = e.d_gains.numpy()
+    out["const/default_dof_pos"] = e.default_dof_pos.numpy(); out["const/torque_limits"] = e.torque_limits.numpy()
+    out["const/dof_pos_limits"] = e.dof_pos_limits.numpy(); out["const/dof_vel_limits"] = e.dof_vel_limits.numpy()
+    out["const/noise_scale_vec"] = e.noise_scale_vec.numpy()
+    out["const/feet_indices"] = e.feet_indices.numpy(); out["const/termination_contact_indices"] = e.termination_contact_indices.numpy()
+    out["const/penalised_contact_indices"] = e.penalised_contact_indices.numpy()
+    out["const/reward_names"] = np.array(e.reward_names)
+    out["const/reward_scales"] = np.array([e.reward_scales[k] for k in e.reward_scales])
+    out["const/reward_scale_keys"] = np.array(list(e.reward_scales.keys()))
+    out["const/initial_weight_sum"] = np.float64(30.0)
+    out["meta"] = np.array(repr(meta))
+    path = os.path.join(HERE, "env_%s.npz" % case)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def gen_learner_case():
+    """GAE (rollout_storage.py:76-90) and the PPO update (ppo.py:94-178) of the reference."""
+    import torch
+    import harness
+    harness.install()
+    import isaacgym  # noqa: F401  (fake)
+    from mini_gym_learn.ppo.rollout_storage import RolloutStorage
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(21)
+    out = {}
+    T_, N = 24, 50
+    st = RolloutStorage(N, T_, [42], [18], [630], [12], device="cpu")
+    rewards = rng.normal(0, 0.05, (T_, N, 1)).astype(np.float32)
+    values = rng.normal(0, 1.0, (T_, N, 1)).astype(np.float32)
+    dones = (rng.random((T_, N, 1)) < 0.05).astype(np.uint8)
+    last_values = rng.normal(0, 1.0, (N, 1)).astype(np.float32)
+    st.rewards[:] = torch.from_numpy(rewards); st.values[:] = torch.from_numpy(values)
+    st.dones[:] = torch.from_numpy(dones)
+    st.compute_returns(torch.from_numpy(last_values), 0.99, 0.95)
+    out["gae/rewards"] = rewards; out["gae/values"] = values; out["gae/dones"] = dones
+    out["gae/last_values"] = last_values
+    out["gae/returns"] = st.returns.numpy().copy(); out["gae/advantages"] = st.advantages.numpy().copy()
+    path = os.path.join(HERE, "learner.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or None
+    if which is None:
+        for c in CASES:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), c])
+    else:
+        for c in which:
+            if c == "learner":
+                gen_learner_case()
+            else:
+                gen_env_case(c)
