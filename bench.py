@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: fused env-steps/s; PPO samples/s rides along).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA kernels)
+    python bench.py --impl reference --gpus 1 --steps K ...   # reference arm: the reference's torch
+                                                              # CPU algorithm (oracle port) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, env-sharded (weak scaling)
+
+A "step" is one `LeggedRobot.step(actions)` of the fused pipeline (PD torques + terminations + all
+reward terms + observations with noise/clipping + state updates) for every env of the workload, on
+synthetic simulator state (the closed-source physics is outside the path).  Workload: Mini Cheetah
+flat, 32768 envs per GPU (BASELINE.json configs[4] = configs[1] at the scale-out size; the 4000-env
+configs[1] point and a 262144-env HBM-resident point are reported under "also").
+
+Timing hygiene: W >= 3 warm-up steps; the K timed steps are captured in ONE CUDA graph and replayed
+once between CUDA events on the launching stream; consecutive steps rotate over R independent env
+replicas whose combined footprint exceeds 2x the 126 MB L2, so no step finds its inputs cache-hot;
+multi-GPU time is the max over ranks; SM clocks / throttle reasons are sampled with NVML during the
+timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+BYTES_PER_ENV_STEP = {"mini_cheetah": 1425, "go1": 1473}   # SURVEY.md 8(d) algorithmic bytes
+L2_BYTES = 126 * 1024 * 1024
+H2D_PER_ENV = 48 + 52 + 96 + 156      # actions, root, dof_state, contact rows (Mini Cheetah)
+D2H_PER_ENV = 168 + 72 + 4 + 1        # obs, privileged obs, reward, reset flag
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """NVML SM-clock / throttle-reason sampler running while the timed region executes."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def build_replicas(case, envs, n_rep, device, seed0=0):
+    """n_rep independent env instances with synthetic simulator state."""
+    import numpy as np
+    import torch
+    from cases import build_case
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    reps = []
+    for r in range(n_rep):
+        cfg, robot, terrain = build_case(case, envs)
+        env = LeggedRobot(cfg, sim_device=device, headless=True, terrain=terrain, seed=seed0 + r)
+        p = env.params
+        st = synthetic_state(seed0 * 1000 + r, envs, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx,
+                             p.term_idx[:p.n_term_bodies])
+        env.sim.root_states.copy_(torch.from_numpy(st["root_states"]))
+        env.sim.dof_state.copy_(torch.from_numpy(st["dof_state"]).view(-1, 2))
+        env.sim.contact_forces.copy_(torch.from_numpy(st["contact_forces"]).view(-1, 3))
+        env._resample_commands(torch.arange(envs, device=device))       # commands from the GAC initial sample
+        env.episode_length_buf.copy_(torch.randint(0, 1001, (envs,), device=device))   # init_at_random_ep_len
+        actions = torch.randn(envs, 12, device=device)
+        reps.append((env, actions, st))
+    return reps
+
+
+def time_env_steps(reps, steps, warmup):
+    """W eager warm-up steps, then exactly `steps` steps captured in one CUDA graph, replayed once
+    warm and once timed.  Returns elapsed milliseconds of the timed replay."""
+    import torch
+    for i in range(max(3, warmup)):
+        env, a, _ = reps[i % len(reps)]
+        env.step(a)
+    for env, _, _ in reps:
+        env.use_device_step_counter(True)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(steps):
+            env, a, _ = reps[i % len(reps)]
+            env.step(a)
+    g.replay()      # untimed replay: graph upload, clocks up
+    torch.cuda.synchronize()
+    return g
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    pk, pk_kind = peaks()
+    bpe = BYTES_PER_ENV_STEP["mini_cheetah"]
+
+    def measure(envs, steps, warmup, sample_clocks):
+        n_rep = max(2, math.ceil(2.0 * L2_BYTES / (envs * bpe)))
+        reps = build_replicas("mc_flat", envs, n_rep, device, seed0=rank)
+        g = time_env_steps(reps, steps, warmup)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(physical_gpu_index(local)) if sample_clocks else None
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.__enter__()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.__exit__()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n_rep, reps, sampler
+
+    ms, n_rep, reps, sampler = measure(args.envs, args.steps, args.warmup, True)
+    value = args.envs * world * args.steps / (ms * 1e-3)
+    per_launch_s = ms * 1e-3 / args.steps
+    achieved = args.envs * bpe / per_launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(str(args.envs))
+
+    # ---- end to end through the public API with HOST buffers --------------------------------------
+    env, actions, st = reps[0]
+    env.use_device_step_counter(False)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_root, h_dof, h_con = pin(st["root_states"]), pin(st["dof_state"].reshape(-1, 2)), pin(st["contact_forces"].reshape(-1, 3))
+    h_act = actions.cpu().pin_memory()
+    d_act = torch.empty_like(actions)
+    h_obs = torch.empty(env.obs_buf.shape, pin_memory=True); h_priv = torch.empty(env.privileged_obs_buf.shape, pin_memory=True)
+    h_rew = torch.empty(env.rew_buf.shape, pin_memory=True); h_reset = torch.empty(env.reset_buf.shape, dtype=torch.bool, pin_memory=True)
+    k_e2e = min(args.steps, 100)
+
+    def e2e_step():
+        env.sim.root_states.copy_(h_root, non_blocking=True)
+        env.sim.dof_state.copy_(h_dof, non_blocking=True)
+        env.sim.contact_forces.copy_(h_con, non_blocking=True)
+        d_act.copy_(h_act, non_blocking=True)
+        obs, priv, rew, reset, _ = env.step(d_act)
+        h_obs.copy_(obs, non_blocking=True); h_priv.copy_(priv, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True); h_reset.copy_(reset, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = args.envs * world * k_e2e / e2e_s
+    assert float(h_obs.abs().sum()) > 0
+
+    # ---- other sizes (rank 0 only, N=1): the 4000-env configs[1] point and an HBM-resident one -----
+    also = {}
+    if world == 1 and not args.quick:
+        del reps
+        torch.cuda.empty_cache()
+        for envs in (4000, 262144):
+            k2 = min(args.steps, 1000 if envs == 4000 else 200)
+            ms2, nr2, reps2, _ = measure(envs, k2, args.warmup, False)
+            also[str(envs)] = {"value": envs * k2 / (ms2 * 1e-3), "ms_per_step": ms2 / k2, "steps": k2,
+                               "replicas": nr2, "roofline_frac": envs * bpe / (ms2 * 1e-3 / k2) / 1e9 / pk["hbm_gbs"]}
+            del reps2
+            torch.cuda.empty_cache()
+
+    out = {
+        "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "mini_cheetah_flat fused env step (PD torques + terminations + 12 reward terms + obs/noise/clip "
+                               "+ state), %d envs per GPU" % args.envs,
+                   "envs_per_gpu": args.envs, "parallelism": "env-sharded x%d, no data-path collective" % world,
+                   "cache": "steps rotate over %d env replicas (%.0f MB > 2x L2) so inputs are never L2-hot" %
+                            (n_rep, n_rep * args.envs * bpe / 1e6),
+                   "launch": "K steps captured in one CUDA graph, device-side RNG step counter"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
+                "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e,
+                "note": "host pinned buffers -> H2D -> LeggedRobot.step -> D2H of obs/priv/rew/reset, sync every step"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
+                     "kernel": "env_step_kernel<true>", "algorithmic_bytes_per_launch": args.envs * bpe},
+        "also": also,
+    }
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_baseline(sample_envs=4000, steps=10, warmup=2)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_env_arm(envs, steps, warmup, threads=None):
+    """The reference's algorithm for the path on host cores: oracle/env_oracle.py (a torch-CPU
+    restatement pinned bit-exactly to the reference; the reference itself is Python and cannot travel
+    to the GPU box).  Returns (env-steps/s, threads used, seconds)."""
+    import numpy as np
+    import torch
+    import statekit
+    from cases import build_case
+    from oracle.env_oracle import OracleEnv
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    if threads:
+        torch.set_num_threads(threads)
+    cfg, robot, terrain = build_case("mc_flat", envs)
+    o = OracleEnv(cfg, robot, terrain)
+    st = synthetic_state(0, envs, robot.num_bodies, 12, o.default_dof_pos[0].numpy(), o.feet_indices.tolist(),
+                         o.termination_contact_indices.tolist())
+    statekit.apply_to_oracle(o, st)
+    o.commands[:, :3] = torch.rand(envs, 3) * 2 - 1
+    actions = torch.randn(envs, 12)
+    for _ in range(warmup):
+        o.step(actions)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(actions)
+    dt = time.perf_counter() - t0
+    return envs * steps / dt, torch.get_num_threads(), dt
+
+
+def cpu_baseline(sample_envs, steps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    v, cores, secs = cpu_env_arm(sample_envs, steps, warmup)
+    return {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d envs x %d steps of the same Mini Cheetah flat step through oracle/env_oracle.py (torch CPU fp32, "
+                      "%.1f s)" % (sample_envs, steps, secs)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    # bounded sample per step so that K steps end within a few minutes whatever K the driver picks
+    sample = 4000
+    v1, cores, secs = cpu_env_arm(sample, 1, 1)
+    est = (args.steps + max(3, args.warmup)) * secs
+    while est > 150 and sample > 250:
+        sample //= 2
+        est /= 2
+    t0 = time.perf_counter()
+    v, cores, secs = cpu_env_arm(sample, args.steps, max(3, args.warmup))
+    out = {
+        "impl": "reference", "metric": "env_steps_per_s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "mini_cheetah_flat fused env step, reference algorithm on host cores; each step is a bounded "
+                               "sample of %d envs of the %d-env workload" % (sample, args.envs), "envs_per_gpu": args.envs},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d steps, oracle/env_oracle.py (torch CPU fp32)" % (sample, args.steps)},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=32768, help="envs per GPU")
+    ap.add_argument("--quick", action="store_true", help="skip the extra sizes")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -215,6 +215,10 @@ typedef struct RlEnvBuffers {
   const float* noise_u;         /* [N,num_obs]  replaces torch.rand_like (:392) */
   const float* dr_u;            /* [3][N] motor, Kp, Kd draws (:547-558) */
   const float* push_u;          /* [2][N] (:764) */
+  /* optional device-side step counter for CUDA-graph replay (kernel arguments are frozen in a
+   * graph): [0] is added to the `step` argument to key the RNG and is incremented once per
+   * launch by the last CTA to finish; [1] is that CTA ticket.  NULL => host `step` only. */
+  uint64_t* step_state;         /* [2] */
 } RlEnvBuffers;
 
 const char* rl_last_error(void);

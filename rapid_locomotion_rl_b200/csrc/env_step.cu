@@ -146,6 +146,8 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
 
   const int P = cfg.measure_heights ? cfg.num_height_points : 0;
   const int W = cfg.num_obs - P;  // width of the non-height part of the observation
+  // RNG step key: host argument (+ device counter when replayed from a CUDA graph)
+  const uint64_t rng_step = args.step + (b.step_state ? b.step_state[0] : 0ull);
 
   extern __shared__ __align__(16) float smem[];
   float* s_root = smem;                         // [TILE][13]
@@ -261,7 +263,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
           if (nu) u = nu[c];
           else {
             float u4[4];
-            rng4(args.seed, (uint32_t)ge, args.step, RNG_NOISE, (uint32_t)(c >> 2), u4);
+            rng4(args.seed, (uint32_t)ge, rng_step, RNG_NOISE, (uint32_t)(c >> 2), u4);
             u = u4[c & 3];
           }
           o += (2.0f * u - 1.0f) * b.noise_scale_vec[c];
@@ -305,7 +307,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
     if (cfg.push_robots && (ep_len % cfg.push_interval) == 0) {
       float u0, u1;
       if (b.push_u) { u0 = b.push_u[e]; u1 = b.push_u[Ns + e]; }
-      else { float u4[4]; rng4(args.seed, (uint32_t)e, args.step, RNG_PUSH, 0, u4); u0 = u4[0]; u1 = u4[1]; }
+      else { float u4[4]; rng4(args.seed, (uint32_t)e, rng_step, RNG_PUSH, 0, u4); u0 = u4[0]; u1 = u4[1]; }
       vw.x = cfg.push_lo_span[1] * u0 + cfg.push_lo_span[0];
       vw.y = cfg.push_lo_span[1] * u1 + cfg.push_lo_span[0];
       root[7] = vw.x; root[8] = vw.y;
@@ -367,7 +369,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
         (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor)) {
       float u3[4];
       if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[Ns + e]; u3[2] = b.dr_u[2 * Ns + e]; }
-      else rng4(args.seed, (uint32_t)e, args.step, RNG_DR, 0, u3);
+      else rng4(args.seed, (uint32_t)e, rng_step, RNG_DR, 0, u3);
       if (cfg.randomize_motor_strength) {
         const float v = u3[0] * cfg.motor_strength_lo_span[1] + cfg.motor_strength_lo_span[0];
 #pragma unroll
@@ -512,7 +514,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
 
     // ---- observations (:342-392), emitted in column order with noise (:392) and clip (:134) -----
     {
-      NoiseGen ng(b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr, args.seed, args.step, (uint32_t)e);
+      NoiseGen ng(b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr, args.seed, rng_step, (uint32_t)e);
       int c = 0;
       auto emit = [&](float v) {
         if (cfg.add_noise) {
@@ -588,6 +590,16 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   stage_out(b.privileged_obs_buf + (size_t)tile0 * RL_PRIV_DIM, s_priv, n_valid * RL_PRIV_DIM);
   if (FUSE_TORQUES) stage_out(b.torques + (size_t)tile0 * ND, s_tq, n_valid * ND);
   if (s_root_dirty) stage_out(b.root_states + (size_t)tile0 * 13, s_root, n_valid * 13);
+
+  // device step counter: every CTA read it on entry; the last one to leave advances it
+  if (b.step_state && tid == 0) {
+    __threadfence();
+    const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
+    if (done == gridDim.x - 1) {
+      b.step_state[1] = 0;
+      atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
+    }
+  }
 }
 
 // standalone PD torques (:653-688) for the real-simulator path: called `decimation` times

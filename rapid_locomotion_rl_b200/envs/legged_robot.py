@@ -255,7 +255,19 @@ class LeggedRobot:
         b.noise_scale_vec = P(self.noise_scale_vec); b.height_points = P(self._height_points_xy)
         b.height_samples = P(self.height_samples) if self.height_samples is not None else None
         b.noise_u = b.dr_u = b.push_u = None
+        b.step_state = None
         return b
+
+    def use_device_step_counter(self, enable=True):
+        """Key the in-kernel RNG with a device-resident step counter so that `step()` can be captured
+        in a CUDA graph and replayed (kernel arguments, including the host step number, are frozen
+        inside a graph).  The counter continues from `common_step_counter`."""
+        if enable:
+            self._step_state = torch.tensor([self.common_step_counter, 0], dtype=torch.int64, device=self.device)
+            self._bufs.step_state = self._step_state.data_ptr()
+        else:
+            self._bufs.step_state = None
+        self._device_steps = bool(enable)
 
     def _make_reset_cfg(self):
         p, cfg = self.params, self.cfg
@@ -296,8 +308,9 @@ class LeggedRobot:
         b.actions_in = actions.data_ptr()
         inj = self._inject
         b.noise_u = _lib.ptr(inj.get("noise_u")); b.dr_u = _lib.ptr(inj.get("dr_u")); b.push_u = _lib.ptr(inj.get("push_u"))
+        host_step = 0 if b.step_state else self.common_step_counter
         _lib.check(self._lib.rl_env_step_fused(C.byref(self._cfg_struct), C.byref(b), self.seed,
-                                               self.common_step_counter, _lib.current_stream()))
+                                               host_step, _lib.current_stream()))
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _compute_torques(self, actions):

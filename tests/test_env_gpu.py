@@ -1,0 +1,310 @@
+"""Fused env kernels (csrc/env_step.cu, env_reset.cu, gac.cu, history.cu) through the drop-in
+LeggedRobot API, against (a) the reference's golden fixtures, (b) the pinned oracle at the
+BASELINE sizes, (c) size-independent properties at 32768 envs.
+
+Tolerances (BASELINE.json north_star): resets, terminations, counters, contact flags, terrain
+levels, curriculum bins and weights bit-exact; torques / rewards / observations / accumulators
+within 1e-5 relative (atol 2e-6 covers cancellation in sums of signed terms).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import statekit
+from cases import ENV_CASES, build_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 2e-6
+DEV = "cuda:0"
+
+
+def make_env(case, n, **kw):
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    cfg, robot, terrain = build_case(case, n)
+    return LeggedRobot(cfg, sim_device=DEV, headless=True, terrain=terrain, **kw), cfg, robot, terrain
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def sub(g, prefix):
+    return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
+
+
+def load(golden_dir, case):
+    return dict(np.load(os.path.join(golden_dir, "env_%s.npz" % case), allow_pickle=False))
+
+
+def check_step(env, obs, priv, rew, reset, want_obs, want_priv, want_rew, want_reset, label):
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(obs.cpu().numpy(), want_obs, rtol=RTOL, atol=ATOL, err_msg=label + " obs")
+    np.testing.assert_allclose(priv.cpu().numpy(), want_priv, rtol=RTOL, atol=ATOL, err_msg=label + " priv")
+    np.testing.assert_allclose(rew.cpu().numpy(), want_rew, rtol=RTOL, atol=ATOL, err_msg=label + " rew")
+    assert np.array_equal(reset.cpu().numpy(), want_reset), label + " reset_buf must be bit-exact"
+
+
+@pytest.mark.parametrize("case", ENV_CASES)
+def test_step_vs_golden(golden_dir, case):
+    g = load(golden_dir, case)
+    env, cfg, robot, terrain = make_env(case, 48)
+    for s in range(3):
+        pre = "step%d/" % s
+        statekit.apply_to_product(env, sub(g, pre + "before/"))
+        env._inject = dict(noise_u=cu(g[pre + "noise_u"]), dr_u=cu(g[pre + "dr_u"]), push_u=cu(g[pre + "push_u"]))
+        obs, priv, rew, reset, _ = env.step(cu(g[pre + "actions"]))
+        check_step(env, obs, priv, rew, reset, g[pre + "obs"], g[pre + "priv"], g[pre + "rew"], g[pre + "reset"],
+                   "%s step %d" % (case, s))
+        if case == "mc_rough":
+            np.testing.assert_allclose(env.measured_heights.cpu().numpy(), g[pre + "measured_heights"], rtol=0, atol=0)
+        got = statekit.state_from_product(env)
+        statekit.assert_state_close(got, sub(g, pre + "after/"), RTOL, ATOL, skip=("contact_forces",),
+                                    label="%s step %d" % (case, s))
+
+
+def random_persistent_state(rng, n, sum_names):
+    s = dict(
+        commands=np.concatenate([rng.uniform(-1, 1, (n, 3)), np.zeros((n, 1))], 1).astype(np.float32),
+        last_actions=rng.normal(0, 1, (n, 12)).astype(np.float32),
+        last_dof_vel=rng.normal(0, 3, (n, 12)).astype(np.float32),
+        motor_strengths=np.repeat(rng.uniform(0.9, 1.1, (n, 1)), 12, 1).astype(np.float32),
+        Kp_factors=np.repeat(rng.uniform(0.8, 1.3, (n, 1)), 12, 1).astype(np.float32),
+        Kd_factors=np.repeat(rng.uniform(0.5, 1.5, (n, 1)), 12, 1).astype(np.float32),
+        friction_coeffs=rng.uniform(0.05, 4.5, n).astype(np.float32),
+        restitutions=rng.uniform(0, 1, n).astype(np.float32), payloads=rng.uniform(-1, 3, n).astype(np.float32),
+        com_displacements=rng.uniform(-0.1, 0.1, (n, 3)).astype(np.float32),
+        feet_air_time=(rng.uniform(0, 0.6, (n, 4)) * (rng.random((n, 4)) < 0.7)).astype(np.float32),
+        last_contacts=rng.random((n, 4)) < 0.3, episode_length_buf=rng.integers(0, 1001, n).astype(np.int64))
+    s["commands"][: n // 8, :2] *= 0.05
+    for k in sum_names:
+        s["episode_sums/" + k] = rng.normal(0, 1, n).astype(np.float32)
+    return s
+
+
+@pytest.mark.parametrize("case,n", [("mc_flat", 4000), ("go1", 4133), ("mc_rough", 1000), ("go1_alt", 777)])
+def test_step_vs_oracle_at_size(case, n):
+    """Same seeded inputs through the pinned oracle (CPU fp32) and the kernel, two consecutive steps."""
+    from oracle.env_oracle import OracleEnv
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    env, cfg, robot, terrain = make_env(case, n)
+    o = OracleEnv(cfg, robot, terrain)
+    rng = np.random.default_rng(n)
+    st = random_persistent_state(rng, n, list(o.episode_sums.keys()))
+    for k in o.command_sums:
+        st["command_sums/" + k] = rng.normal(0, 1, n).astype(np.float32)
+    p = env.params
+    for step in range(2):
+        sim = synthetic_state(1000 + step, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx,
+                              p.term_idx[:p.n_term_bodies], z0=0.3, teleport_band_frac=0.05)
+        if case == "mc_rough":   # keep robots over the small 2x2 test terrain
+            sim["root_states"][:, :2] = rng.uniform(0.5, 15.5, (n, 2))
+        st.update(sim)
+        statekit.apply_to_oracle(o, st)
+        statekit.apply_to_product(env, st)
+        actions = rng.normal(0, 1, (n, 12)).astype(np.float32)
+        noise_u = rng.random((n, p.num_obs)).astype(np.float32)
+        dr_u = rng.random((3, n)).astype(np.float32); push_u = rng.random((2, n)).astype(np.float32)
+        env._inject = dict(noise_u=cu(noise_u), dr_u=cu(dr_u), push_u=cu(push_u))
+        obs, priv, rew, reset, _ = env.step(cu(actions))
+        oo, op, orr, ors = o.step(torch.from_numpy(actions), noise_u=torch.from_numpy(noise_u),
+                                  dr_u=torch.from_numpy(dr_u), push_u=torch.from_numpy(push_u))
+        check_step(env, obs, priv, rew, reset, oo.numpy(), op.numpy(), orr.numpy(), ors.numpy(), "%s n=%d step %d" % (case, n, step))
+        want = statekit.state_from_oracle(o)
+        statekit.assert_state_close(statekit.state_from_product(env), want, RTOL, ATOL, label="%s n=%d" % (case, n))
+        if case == "mc_rough":
+            assert np.array_equal(env.measured_heights.cpu().numpy(), o.measured_heights.numpy()), "heights are exact"
+        st = want  # carry the state into the next step
+
+
+@pytest.mark.parametrize("case", ENV_CASES)
+def test_reset_vs_golden(golden_dir, case):
+    g = load(golden_dir, case)
+    env, cfg, robot, terrain = make_env(case, 48)
+    statekit.apply_to_product(env, sub(g, "reset/before/"))
+    env._reset_u8.copy_(cu(g["step2/reset"].astype(np.uint8)))
+    env._inject = dict(reset_dr_u=cu(g["reset/dr_u"]), init_u=cu(g["reset/init_u"]), level_u=cu(g["reset/level_u"]))
+    env.common_step_counter = 7  # not a multiple of max_episode_length: the uniform curriculum stays put
+    env.reset_idx(cu(g["reset/ids"]))
+    torch.cuda.synchronize()
+    want = sub(g, "reset/after/")
+    got = statekit.state_from_product(env)
+    statekit.assert_state_close(got, want, RTOL, ATOL,
+                                exact_keys=("root_states", "dof_state", "last_actions", "last_dof_vel", "feet_air_time",
+                                            "env_origins", "motor_strengths", "Kp_factors", "Kd_factors"),
+                                skip=("contact_forces", "torques", "base_lin_vel", "base_ang_vel", "projected_gravity",
+                                      "last_root_vel", "joint_pos_target"), label=case + " reset")
+    assert np.array_equal(env.reset_buf.cpu().numpy(), g["reset/reset_buf"])
+    for k, v in sub(g, "reset/extras/").items():
+        np.testing.assert_allclose(env.extras["train/episode"][k].item(), v, rtol=RTOL, atol=ATOL, err_msg=k)
+
+
+def test_reset_mask_and_empty():
+    """Edge cases of reset_idx: empty id list is a no-op (:238); all envs; history rows are zeroed."""
+    from rapid_locomotion_rl_b200.envs import HistoryWrapper, VelocityTrackingEasyEnv
+    cfg, robot, terrain = build_case("mc_flat", 300)
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device=DEV, headless=True, cfg=cfg, terrain=terrain))
+    env.env.episode_length_buf.fill_(5)
+    env.reset_idx(torch.zeros(0, dtype=torch.long, device=DEV))
+    assert (env.env.episode_length_buf == 5).all()
+    for _ in range(3):
+        env.step(torch.randn(300, 12, device=DEV))
+    assert env.obs_history.abs().sum() > 0
+    ids = torch.tensor([0, 17, 299], device=DEV)
+    env.reset_idx(ids)
+    torch.cuda.synchronize()
+    assert (env.obs_history[ids] == 0).all() and (env.env.episode_length_buf[ids] == 0).all()
+    assert env.obs_history[1].abs().sum() > 0 and env.env.episode_length_buf[1] == 3 + 5
+    env.reset_idx(torch.arange(300, device=DEV))
+    assert (env.env.episode_length_buf == 0).all() and (env.env.last_actions == 0).all()
+
+
+@pytest.mark.parametrize("case", ["mc_flat", "go1"])
+def test_resample_vs_golden(golden_dir, case):
+    """GAC: weights (float64) and bins bit-exact, commands bit-exact given the reference's MT19937 uniforms."""
+    g = load(golden_dir, case)
+    env, cfg, robot, terrain = make_env(case, 48)
+    assert env.curriculum.weights.sum() == 30.0
+    for rnd in range(2):
+        pre = "resample%d/" % rnd
+        env.curriculum.weights = g[pre + "before/weights"]
+        env._env_command_bins.copy_(cu(g[pre + "before/bins"]))
+        env.commands.copy_(cu(g[pre + "before/commands"]))
+        for k, row in env.command_sums.items():
+            row.copy_(cu(g[pre + "before/command_sums/" + k]))
+        env._inject = dict(gac_u_bin=cu(g[pre + "u_bin"]), gac_u_cell=cu(g[pre + "u_cell"]))
+        env._resample_commands(cu(g[pre + "ids"]))
+        torch.cuda.synchronize()
+        assert np.array_equal(env.curriculum.weights, g[pre + "after/weights"]), "weights must be bit-exact"
+        assert np.array_equal(env.env_command_bins.cpu().numpy(), g[pre + "after/bins"]), "bins must be bit-exact"
+        assert np.array_equal(env.commands.cpu().numpy(), g[pre + "after/commands"])
+        for k, row in env.command_sums.items():
+            assert np.array_equal(row.cpu().numpy(), g[pre + "after/command_sums/" + k]), k
+        assert int(env.curriculum.hit_count.abs().sum()) == 0, "workspace re-armed"
+
+
+def test_resample_numpy_replay_matches_reference_stream(golden_dir):
+    """gac_rng='numpy' replays RandomState(curriculum_seed) in the reference's draw order."""
+    g = load(golden_dir, "mc_flat")
+    env, cfg, robot, terrain = make_env("mc_flat", 48, gac_rng="numpy")
+    env._resample_commands(torch.arange(48, device=DEV))   # the initial all-env draw the fixture also made
+    pre = "resample0/"
+    env.curriculum.weights = g[pre + "before/weights"]
+    env._env_command_bins.copy_(cu(g[pre + "before/bins"]))
+    for k, row in env.command_sums.items():
+        row.copy_(cu(g[pre + "before/command_sums/" + k]))
+    env._resample_commands(cu(g[pre + "ids"]))
+    torch.cuda.synchronize()
+    assert np.array_equal(env.env_command_bins.cpu().numpy(), g[pre + "after/bins"])
+    ids = g[pre + "ids"]
+    assert np.array_equal(env.commands.cpu().numpy()[ids], g[pre + "after/commands"][ids])
+
+
+def test_resample_statistics_philox():
+    """Device RNG path: bins follow the weight distribution (chi-square) and commands fall inside their cell."""
+    env, cfg, robot, terrain = make_env("mc_flat", 32768)
+    env._resample_commands(torch.arange(32768, device=DEV))
+    torch.cuda.synchronize()
+    bins = env.env_command_bins.cpu().numpy()
+    w = env.curriculum.weights
+    live = np.nonzero(w)[0]
+    assert set(np.unique(bins)) <= set(live)
+    counts = np.bincount(bins, minlength=len(w))[live]
+    expected = 32768 / len(live)
+    chi2 = ((counts - expected) ** 2 / expected).sum()
+    assert chi2 < 2.5 * len(live), chi2     # 30 live bins: mean 29, sd 7.6
+    grid = env.curriculum.grid.T[bins]
+    half = np.array(list(env.curriculum.bin_sizes.values())) / 2
+    cmd = env.commands.cpu().numpy()
+    big = np.linalg.norm(cmd[:, :2], axis=1) > 0
+    assert (np.abs(cmd[big, :3] - grid[big]) <= half + 1e-6).all()
+    assert (np.linalg.norm(cmd[:, :2], axis=1)[big] > 0.2).all()
+
+
+def test_history_ring_matches_shift_concat():
+    from rapid_locomotion_rl_b200.envs import HistoryWrapper, VelocityTrackingEasyEnv
+    cfg, robot, terrain = build_case("mc_flat", 257)
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device=DEV, headless=True, cfg=cfg, terrain=terrain))
+    ref = torch.zeros(257, 15 * 42, device=DEV)
+    for i in range(40):
+        out, rew, done, info = env.step(torch.randn(257, 12, device=DEV))
+        ref = torch.cat((ref[:, 42:], out["obs"]), dim=-1)   # history_wrapper.py:23
+        assert torch.equal(out["obs_history"], ref), "step %d" % i
+    assert info["privileged_obs"] is out["privileged_obs"]
+    assert info["joint_pos"].shape == (257, 12)    # lazy numpy extras
+
+
+def test_philox_noise_statistics_and_determinism():
+    env, cfg, robot, terrain = make_env("mc_flat", 8192, seed=123)
+    a = torch.zeros(8192, 12, device=DEV)
+    env.common_step_counter = 10
+    o1 = env.step(a)[0].clone()
+    env.episode_length_buf.zero_(); env.common_step_counter = 10
+    o2 = env.step(a)[0].clone()
+    assert torch.equal(o1, o2), "same (seed, step) -> same noise"
+    o3 = env.step(a)[0].clone()
+    assert not torch.equal(o1, o3)
+    # gravity columns: sim state is the upright default => clean value (0,0,-1), noise U(-0.05, 0.05)
+    nz = (o1[:, :3] - torch.tensor([0.0, 0.0, -1.0], device=DEV)) / 0.05
+    assert nz.abs().max() <= 1.0 + 1e-6
+    assert abs(nz.mean().item()) < 0.02 and abs(nz.var().item() - 1.0 / 3.0) < 0.02
+    assert (o1[:, 30:42] == 0).all()   # action columns carry no noise
+
+
+def test_full_size_properties():
+    """32768 envs (BASELINE configs[4] per GPU): properties checked with plain torch on the device."""
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    n = 32768
+    env, cfg, robot, terrain = make_env("mc_flat", n)
+    p = env.params
+    st = synthetic_state(0, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx, p.term_idx[:p.n_term_bodies])
+    statekit.apply_to_product(env, st)
+    ep0 = torch.randint(0, 1001, (n,), device=DEV)
+    env.episode_length_buf.copy_(ep0)
+    actions = torch.randn(n, 12, device=DEV) * 60
+    obs, priv, rew, reset, _ = env.step(actions)
+    torch.cuda.synchronize()
+    assert torch.equal(env.episode_length_buf, ep0 + 1)
+    cf = env.contact_forces[:, env.termination_contact_indices, :]
+    assert torch.equal(reset, torch.any(torch.norm(cf, dim=-1) > 1.0, dim=1))
+    assert torch.equal(obs[:, 30:42], torch.clip(actions, -100, 100))
+    assert torch.equal(env.last_actions, torch.clip(actions, -100, 100))
+    assert torch.equal(env.last_dof_vel, env.dof_vel)
+    assert (env.torques.abs() <= env.torque_limits + 0).all()
+    assert (rew >= 0).all()                                   # only_positive_rewards
+    assert (obs.abs() <= 100).all() and (priv.abs() <= 100).all()
+    # standalone torque entry == fused torques
+    t_fused = env.torques.clone()
+    env.step(actions)  # Kp/Kd/motor unchanged unless re-drawn; compare on envs that were not re-drawn
+    keep = (env.episode_length_buf % p.rand_interval != 0) & ((env.episode_length_buf - 1) % p.rand_interval != 0)
+    t_alone = env._compute_torques(actions).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(t_alone[keep], t_fused[keep])
+
+
+def test_api_errors():
+    from rapid_locomotion_rl_b200 import _lib
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    cfg, robot, terrain = build_case("mc_flat", 16)
+    cfg.control.control_type = "X"
+    with pytest.raises(NameError):
+        LeggedRobot(cfg, sim_device=DEV, terrain=terrain)
+    cfg, robot, terrain = build_case("mc_flat", 16)
+    cfg.rewards.scales.feet_stumble = -1.0      # scale name without a _reward_ method (quirk 15)
+    with pytest.raises(AttributeError):
+        LeggedRobot(cfg, sim_device=DEV, terrain=terrain)
+    cfg, robot, terrain = build_case("go1", 16)
+    cfg.terrain.teleport_robots = True          # plane + teleport: AttributeError x_offset (quirk 5)
+    with pytest.raises(AttributeError):
+        LeggedRobot(cfg, sim_device=DEV)
+    cfg, robot, terrain = build_case("mc_flat", 16)
+    env = LeggedRobot(cfg, sim_device=DEV, terrain=terrain)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(15, 12, device=DEV))
+    with pytest.raises(_lib.RlError):
+        LeggedRobot(cfg, sim_device="cpu", terrain=terrain)
