@@ -306,9 +306,11 @@ def cpu_env_arm(envs, steps, warmup, threads=None):
     return envs * steps / dt, torch.get_num_threads(), dt
 
 
-def cpu_baseline(sample_envs, steps, warmup):
+def cpu_baseline(sample_envs, steps, warmup, target_s=12.0):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
+    _, _, probe = cpu_env_arm(sample_envs, 2, 1)
+    steps = int(min(5000, max(steps, target_s / max(probe / 2, 1e-6))))   # ~10-30 s of CPU work
     v, cores, secs = cpu_env_arm(sample_envs, steps, warmup)
     return {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
             "sample": "%d envs x %d steps of the same Mini Cheetah flat step through oracle/env_oracle.py (torch CPU fp32, "

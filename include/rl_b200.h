@@ -40,6 +40,16 @@ extern "C" {
 #define RL_MAX_BODIES 24
 #define RL_MAX_TERMS 21
 #define RL_PRIV_DIM 18
+#define RL_MAX_CORE_OBS 64                       /* observation columns before the height samples */
+/* Fixed row layout of the per-env reward accumulators (rows of unused terms are never touched):
+ *   episode_sums [RL_EPISODE_ROWS][N]: row i = enabled term i, RL_ROW_TERMINATION, RL_ROW_TOTAL
+ *   command_sums [RL_COMMAND_ROWS][N]: row i = enabled term i, RL_ROW_TERMINATION, then
+ *     RL_ROW_EXTRAS + {0 lin_vel_raw, 1 ang_vel_raw, 2 lin_vel_residual, 3 ang_vel_residual, 4 ep_timesteps} */
+#define RL_ROW_TERMINATION RL_MAX_TERMS
+#define RL_ROW_TOTAL (RL_MAX_TERMS + 1)
+#define RL_ROW_EXTRAS (RL_MAX_TERMS + 1)
+#define RL_EPISODE_ROWS (RL_MAX_TERMS + 2)
+#define RL_COMMAND_ROWS (RL_MAX_TERMS + 6)
 
 /* Reward term ids; formulas: legged_robot.py:1506-1646 (_reward_<name>). */
 enum RlRewardTerm {
@@ -100,14 +110,13 @@ typedef struct RlEnvCfg {
   int32_t pen_idx[RL_MAX_BODIES];  /* penalised_contact_indices (:1288) */
   /* rewards: enabled terms in reward_names order; scale already multiplied by dt
    * in double then rounded to float (:1084, :322).  Row i of episode_sums /
-   * command_sums belongs to enabled term i; when scales.termination != 0 row
-   * n_terms is "termination"; n_sum_keys = n_terms + has_termination. */
+   * command_sums belongs to enabled term i (fixed row layout above). */
   int32_t n_terms;
   int32_t term_id[RL_MAX_TERMS];
   float term_scale[RL_MAX_TERMS];
+  uint32_t term_mask;              /* bit id set for every enabled term */
   int32_t has_termination;         /* scales.termination != 0 (:330-334) */
   float termination_scale;
-  int32_t n_sum_keys;              /* len(reward_scales); episode "total" row = n_sum_keys */
   int32_t only_positive_rewards;
   float tracking_sigma;
   float tracking_sigma_yaw;
@@ -132,6 +141,10 @@ typedef struct RlEnvCfg {
   float obs_scale_dof_vel;
   float obs_scale_height;
   float commands_scale[3];
+  /* noise amplitude per observation column (:882-932): the non-height columns sit here so that
+   * the kernel reads them as constant-bank operands; every height column uses noise_scale_height */
+  float noise_scale_core[RL_MAX_CORE_OBS];
+  float noise_scale_height;
   /* privileged obs: (x - shift) * scale for friction, restitution, payload,
    * com_displacement, motor_strength (:398-417); scale 0 when not observed */
   float priv_scale[5];
@@ -203,11 +216,9 @@ typedef struct RlEnvBuffers {
   uint8_t* last_contacts;       /* [N,4] bool */
   int64_t* episode_length_buf;  /* [N] */
   const float* commands;        /* [N,4] */
-  float* episode_sums;          /* [n_sum_keys+1][N], last row "total" */
-  float* command_sums;          /* [n_sum_keys+5][N], rows after keys: lin_vel_raw,
-                                   ang_vel_raw, lin_vel_residual, ang_vel_residual, ep_timesteps */
+  float* episode_sums;          /* [RL_EPISODE_ROWS][N] */
+  float* command_sums;          /* [RL_COMMAND_ROWS][N] */
   /* read-only tables */
-  const float* noise_scale_vec; /* [num_obs] (:882-932) */
   const float* height_points;   /* [P,2] base-frame xy (:1453-1467) */
   const int16_t* height_samples;/* [hf_rows,hf_cols] (:1141) */
   /* optional injected uniforms in [0,1) for parity tests; NULL => Philox4x32-10
@@ -246,7 +257,8 @@ int rl_env_step_fused(const RlEnvCfg* cfg_host, const RlEnvBuffers* bufs_host, u
 /* Reset (legged_robot.py:227-290 reset_idx and the helpers it calls). */
 typedef struct RlResetCfg {
   int32_t num_envs;
-  int32_t n_sum_keys;
+  int32_t n_terms;                  /* rows 0..n_terms-1 (+ termination, total) are reduced and zeroed */
+  int32_t has_termination;
   int32_t custom_origins;           /* mesh_type in heightfield/trimesh (:1389-1404) */
   int32_t terrain_curriculum;       /* cfg.terrain.curriculum and init_done (:800-803) */
   int32_t max_terrain_level;        /* cfg.terrain.num_rows (:1401) */
@@ -278,8 +290,8 @@ typedef struct RlResetBuffers {
   int64_t* episode_length_buf; /* [N] */
   uint8_t* reset_buf;        /* [N] */
   float* Kp_factors, *Kd_factors, *motor_strengths; /* [12][N] */
-  float* episode_sums;       /* [n_sum_keys+1][N]: summed over reset envs then zeroed */
-  double* episode_sum_out;   /* [n_sum_keys+2]: per key sum over reset envs; last = count */
+  float* episode_sums;       /* [RL_EPISODE_ROWS][N]: live rows summed over the reset envs then zeroed */
+  double* episode_sum_out;   /* [RL_EPISODE_ROWS+1]: per-row sum over the reset envs; last = count */
   float* obs_history;        /* [N,H] or NULL: rows zeroed (history_wrapper.py:34) */
   int32_t obs_history_len;
   /* injected uniforms (parity) or NULL => Philox */
@@ -302,7 +314,7 @@ typedef struct RlGacCfg {
   float ang_threshold;
   float ep_len;                 /* min(max_episode_length, int(resampling_time/dt)) (:602-603) */
   int32_t lin_slot, ang_slot;   /* command_sums rows of tracking_lin_vel / tracking_ang_vel */
-  int32_t n_command_sums;       /* rows of command_sums, all zeroed for resampled envs (:625) */
+  int32_t n_command_sums;       /* rows of command_sums zeroed for resampled envs (:625): RL_COMMAND_ROWS */
   int32_t num_train_envs;       /* only train envs feed the update (:612) */
 } RlGacCfg;
 
@@ -319,7 +331,7 @@ typedef struct RlGacBuffers {
   double* cdf;                  /* [n_bins] workspace: normalised inclusive prefix sum */
   int64_t* env_command_bins;    /* [N] */
   float* commands;              /* [N,4] */
-  float* command_sums;          /* [n_command_sums][N] */
+  float* command_sums;          /* [RL_COMMAND_ROWS][N] */
   const double* u_bin;          /* [N] injected uniform for the categorical draw, or NULL */
   const double* u_cell;         /* [N,3] injected uniforms for the in-cell draw, or NULL */
 } RlGacBuffers;

@@ -13,7 +13,7 @@ from . import build as _build
 _HEADER = os.path.join(_build.INCLUDE, "rl_b200.h")
 
 _SCALARS = {
-    "int32_t": C.c_int32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "uint8_t": C.c_uint8,
+    "int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "uint8_t": C.c_uint8,
     "float": C.c_float, "double": C.c_double, "int": C.c_int,
 }
 

@@ -383,8 +383,14 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     p.term_id += [0] * (maxt - p.n_terms); p.term_scale += [0.0] * (maxt - p.n_terms)
     p.has_termination = int("termination" in reward_scales)
     p.termination_scale = f32(reward_scales.get("termination", 0.0))
-    p.sum_names = p.reward_names + (["termination"] if p.has_termination else [])
-    p.n_sum_keys = len(p.sum_names)
+    p.term_mask = 0
+    for i in p.term_id[:p.n_terms]:
+        p.term_mask |= 1 << i
+    # fixed accumulator rows (rl_b200.h): term i -> row i, termination, total / extras
+    p.sum_rows = {n: i for i, n in enumerate(p.reward_names)}
+    if p.has_termination:
+        p.sum_rows["termination"] = _lib.DEFINES["RL_MAX_TERMS"]
+    p.sum_names = list(p.sum_rows.keys())
     p.only_positive_rewards = int(bool(cfg.rewards.only_positive_rewards))
     p.tracking_sigma = f32(cfg.rewards.tracking_sigma)
     p.tracking_sigma_yaw = f32(cfg.rewards.tracking_sigma_yaw)
@@ -428,6 +434,12 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     if p.measure_heights:
         vec = np.concatenate([vec, seg(len(p.height_points), ns.height_measurements, lvl, os_.height_measurements)])
     p.noise_scale_vec = vec.astype(np.float32)
+    ncore = len(p.noise_scale_vec) - p.num_height_points
+    maxc = _lib.DEFINES["RL_MAX_CORE_OBS"]
+    if ncore > maxc:
+        raise NotImplementedError("%d non-height observation columns > %d" % (ncore, maxc))
+    p.noise_scale_core = [float(x) for x in p.noise_scale_vec[:ncore]] + [0.0] * (maxc - ncore)
+    p.noise_scale_height = float(p.noise_scale_vec[-1]) if p.measure_heights else 0.0
     # NOTE (reference quirk): observe_only_ang_vel adds 3 observation columns (:370-372) but no
     # noise entries (:882-932), so the reference itself fails to broadcast there; we require the
     # widths to agree.

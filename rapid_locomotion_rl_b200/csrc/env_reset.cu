@@ -11,7 +11,7 @@
 namespace rl {
 
 constexpr int ND_R = RL_NUM_DOF;
-constexpr int MAX_SUM_ROWS = RL_MAX_TERMS + 2;
+constexpr int MAX_SUM_ROWS = RL_EPISODE_ROWS;
 
 struct ResetArgs {
   RlResetCfg cfg;
@@ -19,6 +19,10 @@ struct ResetArgs {
   uint64_t seed;
   uint64_t step;
 };
+
+__device__ inline bool row_live(const RlResetCfg& cfg, int r) {
+  return r < cfg.n_terms || (r == RL_ROW_TERMINATION && cfg.has_termination) || r == RL_ROW_TOTAL;
+}
 
 __global__ void __launch_bounds__(128)
 env_reset_kernel(const __grid_constant__ ResetArgs args) {
@@ -115,7 +119,7 @@ env_reset_kernel(const __grid_constant__ ResetArgs args) {
     // ---- episode sums (:261-267) ----
 #pragma unroll
     for (int r = 0; r < MAX_SUM_ROWS; ++r) {
-      if (r <= cfg.n_sum_keys) {
+      if (row_live(cfg, r)) {
         ksum[r] = (double)b.episode_sums[r * Ns + e];
         b.episode_sums[r * Ns + e] = 0.f;
       }
@@ -128,12 +132,12 @@ env_reset_kernel(const __grid_constant__ ResetArgs args) {
   if (any && b.episode_sum_out) {
 #pragma unroll
     for (int r = 0; r < MAX_SUM_ROWS; ++r) {
-      if (r <= cfg.n_sum_keys) {
+      if (row_live(cfg, r)) {
         const double s = warp_sum(ksum[r]);
         if (lane == 0) atomicAdd(b.episode_sum_out + r, s);
       }
     }
-    if (lane == 0) atomicAdd(b.episode_sum_out + cfg.n_sum_keys + 1, (double)__popc(any));
+    if (lane == 0) atomicAdd(b.episode_sum_out + RL_EPISODE_ROWS, (double)__popc(any));
   }
 
   // observation-history rows (history_wrapper.py:34): the warp zeroes each active lane's row
@@ -160,8 +164,8 @@ extern "C" int rl_env_reset(const RlResetCfg* cfg, const RlResetBuffers* b, uint
   RL_REQUIRE(cfg->num_envs > 0, RL_ERR_BAD_CFG, "rl_env_reset: num_envs=%d", cfg->num_envs);
   RL_REQUIRE((b->mask != nullptr) != (b->ids != nullptr), RL_ERR_BAD_ARG,
              "rl_env_reset: exactly one of mask / ids must be given");
-  RL_REQUIRE(cfg->n_sum_keys >= 0 && cfg->n_sum_keys + 1 <= MAX_SUM_ROWS, RL_ERR_BAD_CFG,
-             "rl_env_reset: n_sum_keys=%d", cfg->n_sum_keys);
+  RL_REQUIRE(cfg->n_terms >= 0 && cfg->n_terms <= RL_MAX_TERMS, RL_ERR_BAD_CFG,
+             "rl_env_reset: n_terms=%d", cfg->n_terms);
   RL_REQUIRE(b->root_states && b->dof_state && b->env_origins && b->last_actions && b->last_dof_vel &&
              b->feet_air_time && b->episode_length_buf && b->reset_buf && b->Kp_factors && b->Kd_factors &&
              b->motor_strengths && b->episode_sums, RL_ERR_BAD_ARG, "rl_env_reset: a required buffer is null");

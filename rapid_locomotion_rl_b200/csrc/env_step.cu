@@ -23,11 +23,12 @@
 //
 // Numerics: compiled with -fmad=false so every fp32 operation rounds exactly like the
 // op-by-op eager reference; integer results (cell indices, resets, counters) are exact.
+#include <stdlib.h>
+
 #include "rl_common.cuh"
 
 namespace rl {
 
-constexpr int TILE = 128;           // envs per CTA == threads per CTA
 constexpr int ND = RL_NUM_DOF;
 
 struct StepArgs {
@@ -40,33 +41,48 @@ struct StepArgs {
 // ---------------------------------------------------------------------------------------
 // cooperative tile copies
 // ---------------------------------------------------------------------------------------
+// (fallback path for ragged tail tiles / unaligned tensors; full tiles use cp.async.bulk)
+template <int TILE>
 __device__ inline void stage_in(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
-  // src tile start is 16 B aligned whenever the tensor base is (TILE*row*4 is a multiple of 16)
   if ((((uintptr_t)src) & 15) == 0) {
     const int n4 = n_floats >> 2;
-    for (int i = threadIdx.x; i < n4; i += TILE)
-      reinterpret_cast<float4*>(dst)[i] = ldg_stream4(src + 4 * i);
+    // batches of 4 independent 128-bit loads per thread before the first store
+    for (int i = threadIdx.x; i < n4; i += 4 * TILE) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (i + k * TILE < n4) v[k] = ldg_stream4(src + 4 * (i + k * TILE));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (i + k * TILE < n4) reinterpret_cast<float4*>(dst)[i + k * TILE] = v[k];
+    }
+#pragma unroll 1
     for (int i = (n4 << 2) + threadIdx.x; i < n_floats; i += TILE) dst[i] = __ldg(src + i);
   } else {
+#pragma unroll 1
     for (int i = threadIdx.x; i < n_floats; i += TILE) dst[i] = __ldg(src + i);
   }
 }
 
+template <int TILE>
 __device__ inline void stage_out(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
   if ((((uintptr_t)dst) & 15) == 0) {
     const int n4 = n_floats >> 2;
+#pragma unroll 2
     for (int i = threadIdx.x; i < n4; i += TILE)
       stg_stream4(dst + 4 * i, reinterpret_cast<const float4*>(src)[i]);
+#pragma unroll 1
     for (int i = (n4 << 2) + threadIdx.x; i < n_floats; i += TILE) dst[i] = src[i];
   } else {
+#pragma unroll 1
     for (int i = threadIdx.x; i < n_floats; i += TILE) dst[i] = src[i];
   }
 }
 
 // rows of `width` floats in smem (dense) -> global rows with pitch `pitch`
+template <int TILE>
 __device__ inline void stage_out_rows(float* __restrict__ dst, const float* __restrict__ src, int rows,
                                       int width, int pitch) {
   const int total = rows * width;
+#pragma unroll 1
   for (int i = threadIdx.x; i < total; i += TILE) {
     const int r = i / width, c = i - r * width;
     dst[(size_t)r * pitch + c] = src[i];
@@ -107,31 +123,48 @@ __device__ inline float py_mod(float a, float b) {
   return m;
 }
 
-// uniform for obs column c of env e: injected or Philox
-struct NoiseGen {
-  const float* inj;      // row pointer into noise_u or nullptr
+// ---------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------
+// 16-bit uniform lane k (0..7) of a Philox block -> (u - 0.5) in (-0.5, 0.5), symmetric, never +-0.5
+__device__ inline float centered_u16(const uint32_t (&r)[4], int k) {
+  const uint32_t x = (r[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+  return __fmaf_rn((float)x, 1.0f / 65536.0f, 0.5f / 65536.0f - 0.5f);
+}
+
+// Observation noise (:392): obs += (2*u - 1) * scale.  Test mode reads u from the injected
+// tensor and keeps the reference's arithmetic exactly; product mode draws 8 sixteen-bit uniforms
+// per Philox4x32-10 block (counter = noisy-value index / 8).
+struct ObsNoise {
+  const float* inj;   // noise_u row or nullptr
   uint64_t seed, step;
   uint32_t env;
-  int cached_block;
-  float u[4];
-  __device__ NoiseGen(const float* inj_row, uint64_t seed_, uint64_t step_, uint32_t env_)
-      : inj(inj_row), seed(seed_), step(step_), env(env_), cached_block(-1) {}
-  __device__ inline float get(int c) {
-    if (inj) return inj[c];
-    const int blk = c >> 2;
-    if (blk != cached_block) {
-      rng4(seed, env, step, RNG_NOISE, (uint32_t)blk, u);
-      cached_block = blk;
-    }
-    return u[c & 3];
+  uint32_t r[4];
+  int have;           // Philox block currently held (-1: none)
+  __device__ ObsNoise(const float* inj_row, uint64_t s, uint64_t st, uint32_t e)
+      : inj(inj_row), seed(s), step(st), env(e), have(-1) {}
+  // k = running index over noisy values (static after unrolling), c = observation column
+  __device__ __forceinline__ float apply(float v, float scale, int k, int c) {
+    if (inj) return v + (2.0f * inj[c] - 1.0f) * scale;
+    return __fmaf_rn(2.0f * centered_u16(r, k & 7), scale, v);
+  }
+  __device__ __noinline__ void refill(int blk) {
+    Philox::gen(seed, env, (uint32_t)step, (uint32_t)(step >> 32), (RNG_NOISE << 16) | (uint32_t)blk, r);
+    have = blk;
+  }
+  __device__ __forceinline__ void need(int k) {
+    if (!inj && (k >> 3) != have) refill(k >> 3);
   }
 };
 
 // ---------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------
-template <bool FUSE_TORQUES>
-__global__ void __launch_bounds__(TILE, 2)
+// STD_OBS: the observation layout of both shipped robots (gravity 3 | commands 3 | q 12 | qd 12 |
+// actions 12, optionally followed by height samples) with every column index known at compile
+// time; the generic instantiation handles the other observe_* combinations.
+template <bool FUSE_TORQUES, int TILE, bool STD_OBS>
+__global__ void __launch_bounds__(TILE, 512 / TILE)
 env_step_kernel(const __grid_constant__ StepArgs args) {
   const RlEnvCfg& cfg = args.cfg;
   const RlEnvBuffers& b = args.b;
@@ -145,36 +178,66 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   const size_t Ns = (size_t)N;
 
   const int P = cfg.measure_heights ? cfg.num_height_points : 0;
-  const int W = cfg.num_obs - P;  // width of the non-height part of the observation
+  const int W = STD_OBS ? 42 : cfg.num_obs - P;  // width of the non-height part of the observation
   // RNG step key: host argument (+ device counter when replayed from a CUDA graph)
   const uint64_t rng_step = args.step + (b.step_state ? b.step_state[0] : 0ull);
 
+  // Shared memory: [hmean | root | union{ inputs: dof, contact, actions, (torques in) ;
+  //                                         outputs: obs, priv, torques out }].
+  // The output rows are assembled in registers and only written after a CTA barrier, when every
+  // thread is done with the input rows, so they can reuse that space (22.5 KB per 64 envs instead
+  // of 41 KB: twice the resident CTAs).
   extern __shared__ __align__(16) float smem[];
-  float* s_root = smem;                         // [TILE][13]
-  float* s_dof = s_root + TILE * 13 + 0;        // [TILE][24]   (TILE*13*4 is a multiple of 16)
+  float* s_hmean = smem;                        // [TILE] mean(z - h)
+  float* s_root = s_hmean + TILE;               // [TILE][13]
+  float* s_dof = s_root + TILE * 13;            // [TILE][24]
   float* s_con = s_dof + TILE * 24;             // [TILE][NB*3]
   float* s_act = s_con + TILE * NB * 3;         // [TILE][12]
-  float* s_tq = s_act + TILE * ND;              // [TILE][12]
-  float* s_priv = s_tq + TILE * ND;             // [TILE][18]
-  float* s_obs = s_priv + TILE * RL_PRIV_DIM;   // [TILE][W]
-  float* s_hmean = s_obs + TILE * W;            // [TILE] mean(z - h)
+  float* s_tq_in = s_act + TILE * ND;           // [TILE][12] (post_physics only)
+  float* s_obs = s_dof;                         // [TILE][W]   (aliases the inputs)
+  float* s_priv = s_obs + TILE * W;             // [TILE][18]
+  float* s_tq = s_priv + TILE * RL_PRIV_DIM;    // [TILE][12]
   __shared__ int s_root_dirty;
+  __shared__ __align__(8) uint64_t s_bar;
 
   // ---- 1. stage the simulator-owned rows of this tile into shared memory ---------------
-  stage_in(s_root, b.root_states + (size_t)tile0 * 13, n_valid * 13);
-  stage_in(s_dof, b.dof_state + (size_t)tile0 * 24, n_valid * 24);
-  stage_in(s_con, b.contact_forces + (size_t)tile0 * NB * 3, n_valid * NB * 3);
-  stage_in(s_act, b.actions_in + (size_t)tile0 * ND, n_valid * ND);
-  if (!FUSE_TORQUES) stage_in(s_tq, b.torques + (size_t)tile0 * ND, n_valid * ND);
+  // Full tiles of 16 B-aligned tensors: one elected thread issues one cp.async.bulk (TMA 1-D,
+  // SASS UBLKCP) per tensor; the bytes land asynchronously while every thread issues its SoA
+  // loads.  Ragged tail tile / unaligned views: cooperative 128-bit loads.
+  const float* g_root = b.root_states + (size_t)tile0 * 13;
+  const float* g_dof = b.dof_state + (size_t)tile0 * 24;
+  const float* g_con = b.contact_forces + (size_t)tile0 * NB * 3;
+  const float* g_act = b.actions_in + (size_t)tile0 * ND;
+  const float* g_tq = b.torques + (size_t)tile0 * ND;
+  const bool bulk_in = (n_valid == TILE) &&
+      ((((uintptr_t)g_root | (uintptr_t)g_dof | (uintptr_t)g_con | (uintptr_t)g_act | (uintptr_t)g_tq) & 15) == 0);
+  if (bulk_in) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+      const uint32_t bytes = (uint32_t)(TILE * (13 + 24 + NB * 3 + ND + (FUSE_TORQUES ? 0 : ND)) * sizeof(float));
+      mbar_expect_tx(&s_bar, bytes);
+      bulk_g2s(s_root, g_root, TILE * 13 * 4, &s_bar);
+      bulk_g2s(s_dof, g_dof, TILE * 24 * 4, &s_bar);
+      bulk_g2s(s_con, g_con, (uint32_t)(TILE * NB * 3 * 4), &s_bar);
+      bulk_g2s(s_act, g_act, TILE * ND * 4, &s_bar);
+      if (!FUSE_TORQUES) bulk_g2s(s_tq_in, g_tq, TILE * ND * 4, &s_bar);
+    }
+  } else {
+    stage_in<TILE>(s_root, g_root, n_valid * 13);
+    stage_in<TILE>(s_dof, g_dof, n_valid * 24);
+    stage_in<TILE>(s_con, g_con, n_valid * NB * 3);
+    stage_in<TILE>(s_act, g_act, n_valid * ND);
+    if (!FUSE_TORQUES) stage_in<TILE>(s_tq_in, g_tq, n_valid * ND);
+  }
   if (tid == 0) s_root_dirty = 0;
 
   // ---- 2. issue the SoA state loads early so they overlap the staging ------------------
-  constexpr int MAXR_E = RL_MAX_TERMS + 2;   // episode rows: terms, [termination], total
-  constexpr int MAXR_C = RL_MAX_TERMS + 6;   // command rows: terms, [termination], 5 extras
-  const int n_keys = cfg.n_sum_keys;
+  // (32-bit element indices: validated N * RL_COMMAND_ROWS < 2^31)
+  const uint32_t tmask = cfg.term_mask;
+  const bool air_on = (tmask >> RL_REW_FEET_AIR_TIME) & 1u;
   float kp[ND], kd[ND], ms[ND], la[ND], ldv[ND];
-  float es[MAXR_E], cs[MAXR_C];
-  float air[RL_NUM_FEET];
+  float air[RL_NUM_FEET] = {0.f, 0.f, 0.f, 0.f};
   float fr = 0.f, re = 0.f, pl = 0.f, com[3] = {0.f, 0.f, 0.f};
   uint32_t last_contacts = 0;
   int64_t ep_len = 0;
@@ -182,26 +245,26 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   if (valid) {
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
-      kp[j] = b.Kp_factors[j * Ns + e];
-      kd[j] = b.Kd_factors[j * Ns + e];
-      ms[j] = b.motor_strengths[j * Ns + e];
-      la[j] = b.last_actions[j * Ns + e];
-      ldv[j] = b.last_dof_vel[j * Ns + e];
+      const int ix = j * N + e;
+      kp[j] = b.Kp_factors[ix];
+      kd[j] = b.Kd_factors[ix];
+      ms[j] = b.motor_strengths[ix];
+      la[j] = b.last_actions[ix];
+      ldv[j] = b.last_dof_vel[ix];
     }
+    if (air_on) {
 #pragma unroll
-    for (int r = 0; r < MAXR_E; ++r) es[r] = (r <= n_keys) ? b.episode_sums[r * Ns + e] : 0.f;
-#pragma unroll
-    for (int r = 0; r < MAXR_C; ++r) cs[r] = (r < n_keys + 5) ? b.command_sums[r * Ns + e] : 0.f;
-#pragma unroll
-    for (int k = 0; k < RL_NUM_FEET; ++k) air[k] = b.feet_air_time[k * Ns + e];
-    last_contacts = *reinterpret_cast<const uint32_t*>(b.last_contacts + (size_t)e * 4);
+      for (int k = 0; k < RL_NUM_FEET; ++k) air[k] = b.feet_air_time[k * N + e];
+      last_contacts = *reinterpret_cast<const uint32_t*>(b.last_contacts + (size_t)e * 4);
+    }
     fr = b.friction_coeffs[e]; re = b.restitutions[e]; pl = b.payloads[e];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) com[k] = b.com_displacements[k * Ns + e];
+    for (int k = 0; k < 3; ++k) com[k] = b.com_displacements[k * N + e];
     ep_len = b.episode_length_buf[e];
     cmd = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
   }
-  __syncthreads();
+  __syncthreads();                      // mbarrier init / cooperative stores visible
+  if (bulk_in) mbar_wait(&s_bar, 0);    // all staged bytes have landed
 
   // ---- 3. counters, teleport (:152, :768-791) --------------------------------------------
   float* root = s_root + tid * 13;
@@ -224,6 +287,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   if (cfg.measure_heights) {
     const int warp = tid >> 5, lane = tid & 31;
     const float hscale = cfg.horizontal_scale, vscale = cfg.vertical_scale;
+#pragma unroll 1
     for (int le = warp; le < n_valid; le += TILE / 32) {
       const float* r = s_root + le * 13;
       const int ge = tile0 + le;
@@ -237,6 +301,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       float* mh = b.measured_heights + (size_t)ge * P;
       float* ob = b.obs_buf + (size_t)ge * cfg.num_obs + W;
       const float* nu = b.noise_u ? b.noise_u + (size_t)ge * cfg.num_obs : nullptr;
+#pragma unroll 1
       for (int p = lane; p < P; p += 32) {
         float h = 0.f;
         if (!cfg.heights_plane) {
@@ -258,15 +323,14 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
         // observation suffix (:386-389) + noise (:392) + clip (:134)
         float o = clampf(bz - 0.5f - h, -1.f, 1.f) * cfg.obs_scale_height;
         if (cfg.add_noise) {
-          const int c = W + p;
-          float u;
-          if (nu) u = nu[c];
-          else {
-            float u4[4];
-            rng4(args.seed, (uint32_t)ge, rng_step, RNG_NOISE, (uint32_t)(c >> 2), u4);
-            u = u4[c & 3];
+          if (nu) {
+            o += (2.0f * nu[W + p] - 1.0f) * cfg.noise_scale_height;
+          } else {
+            uint32_t r4[4];   // stream block 64+: disjoint from the core columns' blocks
+            Philox::gen(args.seed, (uint32_t)ge, (uint32_t)rng_step, (uint32_t)(rng_step >> 32),
+                        (RNG_NOISE << 16) | (uint32_t)(64 + (p >> 3)), r4);
+            o = __fmaf_rn(2.0f * centered_u16(r4, p & 7), cfg.noise_scale_height, o);
           }
-          o += (2.0f * u - 1.0f) * b.noise_scale_vec[c];
         }
         ob[p] = clampf(o, -cfg.clip_obs, cfg.clip_obs);
       }
@@ -276,14 +340,18 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
     __syncthreads();
   }
 
-  // ---- 5. per-env scalar pipeline ----------------------------------------------------------
+  // ---- 5. per-env scalar pipeline: everything lands in registers (o, pv, tq) ----------------
+  float o[STD_OBS ? 42 : 1];      // observation row (standard layout)
+  float pv[RL_PRIV_DIM];          // privileged observation row
+  float tq[ND];                   // torques
+  float dof[2 * ND], act[ND];     // this env's dof_state / action rows
+  V3 blv = {0.f, 0.f, 0.f}, bav = blv, grav = blv, vw = blv;
+  float qx = 0.f, qy = 0.f, qz = 0.f, qw = 1.f;
+  const float co = cfg.clip_obs;
   if (valid) {
     const float* con = s_con + tid * NB * 3;
-    float* obs = s_obs + tid * W;
-    float* priv = s_priv + tid * RL_PRIV_DIM;
 
     // rows of 24 / 12 floats: 128-bit shared loads (a scalar walk would be 8-way bank conflicted)
-    float dof[2 * ND], act[ND], tq[ND];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
       *reinterpret_cast<float4*>(dof + 4 * k) = *reinterpret_cast<const float4*>(s_dof + tid * 24 + 4 * k);
@@ -293,20 +361,20 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
     if (!FUSE_TORQUES) {
 #pragma unroll
       for (int k = 0; k < 3; ++k)
-        *reinterpret_cast<float4*>(tq + 4 * k) = *reinterpret_cast<const float4*>(s_tq + tid * ND + 4 * k);
+        *reinterpret_cast<float4*>(tq + 4 * k) = *reinterpret_cast<const float4*>(s_tq_in + tid * ND + 4 * k);
     }
 
-    const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
-    V3 vw = {root[7], root[8], root[9]};
+    qx = root[3]; qy = root[4]; qz = root[5]; qw = root[6];
+    vw = V3{root[7], root[8], root[9]};
     const V3 ww = {root[10], root[11], root[12]};
-    const V3 blv = quat_rotate_inverse(qx, qy, qz, qw, vw);
-    const V3 bav = quat_rotate_inverse(qx, qy, qz, qw, ww);
-    const V3 grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+    blv = quat_rotate_inverse(qx, qy, qz, qw, vw);
+    bav = quat_rotate_inverse(qx, qy, qz, qw, ww);
+    grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
 
     // push (:757-766) - after the body-frame velocity was taken (:160 precedes :588)
     if (cfg.push_robots && (ep_len % cfg.push_interval) == 0) {
       float u0, u1;
-      if (b.push_u) { u0 = b.push_u[e]; u1 = b.push_u[Ns + e]; }
+      if (b.push_u) { u0 = b.push_u[e]; u1 = b.push_u[N + e]; }
       else { float u4[4]; rng4(args.seed, (uint32_t)e, rng_step, RNG_PUSH, 0, u4); u0 = u4[0]; u1 = u4[1]; }
       vw.x = cfg.push_lo_span[1] * u0 + cfg.push_lo_span[0];
       vw.y = cfg.push_lo_span[1] * u1 + cfg.push_lo_span[0];
@@ -314,11 +382,17 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       dirty = true;
     }
 
-    // per-DOF sweep: torques (:653-688) and the reward partial sums
+    // per-DOF sweep: torques (:653-688) and the partial sums of the ENABLED reward terms
+    const bool on_energy = ((tmask >> RL_REW_ENERGY) | (tmask >> RL_REW_ENERGY_EXPENDITURE)) & 1u;
+    const bool on_qd2 = (tmask >> RL_REW_DOF_VEL) & 1u, on_qd_lim = (tmask >> RL_REW_DOF_VEL_LIMITS) & 1u;
+    const bool on_tq_lim = (tmask >> RL_REW_TORQUE_LIMITS) & 1u, on_still = (tmask >> RL_REW_STAND_STILL) & 1u;
+    const bool on_acc = (tmask >> RL_REW_DOF_ACC) & 1u, on_rate = (tmask >> RL_REW_ACTION_RATE) & 1u;
+    const bool on_lim = (tmask >> RL_REW_DOF_POS_LIMITS) & 1u;
     float sum_tq2 = 0.f, sum_acc2 = 0.f, sum_rate2 = 0.f, sum_lim = 0.f, sum_energy = 0.f,
           sum_energy_pos = 0.f, sum_qd2 = 0.f, sum_qd_lim = 0.f, sum_tq_lim = 0.f, sum_still = 0.f;
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
+      const int ix = j * N + e;
       const float q = dof[2 * j], qd = dof[2 * j + 1];
       const float a = clampf(act[j], -cfg.clip_actions, cfg.clip_actions);  // :112-113
       act[j] = a;
@@ -328,7 +402,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
         if (j % 3 == 0) as *= cfg.hip_scale_reduction;  // dofs 0,3,6,9 (:666)
         if (cfg.control_type == 0) {
           const float jpt = as + cfg.default_dof_pos[j];
-          b.joint_pos_target[j * Ns + e] = jpt;
+          b.joint_pos_target[ix] = jpt;
           t = cfg.p_gains[j] * kp[j] * (jpt - q) - cfg.d_gains[j] * kd[j] * qd;
         } else if (cfg.control_type == 1) {
           t = cfg.p_gains[j] * (as - qd) - cfg.d_gains[j] * (qd - ldv[j]) / cfg.sim_dt;
@@ -340,56 +414,63 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       }
       const float t = tq[j];
       sum_tq2 += sq(t);
-      sum_acc2 += sq((ldv[j] - qd) / cfg.dt);
-      sum_rate2 += sq(la[j] - a);
-      {
-        float o = -fminf(q - cfg.dof_pos_lo[j], 0.f);
-        o += fmaxf(q - cfg.dof_pos_hi[j], 0.f);
-        sum_lim += o;
+      if (on_acc) sum_acc2 += sq((ldv[j] - qd) / cfg.dt);
+      if (on_rate) sum_rate2 += sq(la[j] - a);
+      if (on_lim) {
+        float ov = -fminf(q - cfg.dof_pos_lo[j], 0.f);
+        ov += fmaxf(q - cfg.dof_pos_hi[j], 0.f);
+        sum_lim += ov;
       }
-      const float pw = t * qd;
-      sum_energy += pw;
-      sum_energy_pos += clampf(pw, 0.f, 1e30f);
-      sum_qd2 += sq(qd);
-      sum_qd_lim += clampf(fabsf(qd) - cfg.dof_vel_limits[j] * cfg.soft_dof_vel_limit, 0.f, 1.f);
-      sum_tq_lim += fmaxf(fabsf(t) - cfg.torque_limits[j] * cfg.soft_torque_limit, 0.f);
-      sum_still += fabsf(q - cfg.default_dof_pos[j]);
+      if (on_energy) {
+        const float pw = t * qd;
+        sum_energy += pw;
+        sum_energy_pos += clampf(pw, 0.f, 1e30f);
+      }
+      if (on_qd2) sum_qd2 += sq(qd);
+      if (on_qd_lim) sum_qd_lim += clampf(fabsf(qd) - cfg.dof_vel_limits[j] * cfg.soft_dof_vel_limit, 0.f, 1.f);
+      if (on_tq_lim) sum_tq_lim += fmaxf(fabsf(t) - cfg.torque_limits[j] * cfg.soft_torque_limit, 0.f);
+      if (on_still) sum_still += fabsf(q - cfg.default_dof_pos[j]);
       // last_* updates (:181-182)
-      b.last_actions[j * Ns + e] = a;
-      b.last_dof_vel[j * Ns + e] = qd;
-    }
-    if (FUSE_TORQUES) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        *reinterpret_cast<float4*>(s_tq + tid * ND + 4 * k) = *reinterpret_cast<float4*>(tq + 4 * k);
+      b.last_actions[ix] = a;
+      b.last_dof_vel[ix] = qd;
     }
 
     // DOF-property re-draw for envs whose episode clock hits the interval (:591-593,:544-560)
     if ((ep_len % cfg.rand_interval) == 0 &&
         (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor)) {
       float u3[4];
-      if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[Ns + e]; u3[2] = b.dr_u[2 * Ns + e]; }
+      if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[N + e]; u3[2] = b.dr_u[2 * N + e]; }
       else rng4(args.seed, (uint32_t)e, rng_step, RNG_DR, 0, u3);
       if (cfg.randomize_motor_strength) {
         const float v = u3[0] * cfg.motor_strength_lo_span[1] + cfg.motor_strength_lo_span[0];
 #pragma unroll
-        for (int j = 0; j < ND; ++j) { ms[j] = v; b.motor_strengths[j * Ns + e] = v; }
+        for (int j = 0; j < ND; ++j) { ms[j] = v; b.motor_strengths[j * N + e] = v; }
       }
       if (cfg.randomize_Kp_factor) {
         const float v = u3[1] * cfg.Kp_factor_lo_span[1] + cfg.Kp_factor_lo_span[0];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) b.Kp_factors[j * Ns + e] = v;
+#pragma unroll 1
+        for (int j = 0; j < ND; ++j) b.Kp_factors[j * N + e] = v;
       }
       if (cfg.randomize_Kd_factor) {
         const float v = u3[2] * cfg.Kd_factor_lo_span[1] + cfg.Kd_factor_lo_span[0];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) b.Kd_factors[j * Ns + e] = v;
+#pragma unroll 1
+        for (int j = 0; j < ND; ++j) b.Kd_factors[j * N + e] = v;
       }
     }
+
+    // ---- privileged observations (:398-417) + clip (:136) ------------------------------------------
+    pv[0] = clampf((fr - cfg.priv_shift[0]) * cfg.priv_scale[0], -co, co);
+    pv[1] = clampf((re - cfg.priv_shift[1]) * cfg.priv_scale[1], -co, co);
+    pv[2] = clampf((pl - cfg.priv_shift[2]) * cfg.priv_scale[2], -co, co);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pv[3 + k] = clampf((com[k] - cfg.priv_shift[3]) * cfg.priv_scale[3], -co, co);
+#pragma unroll
+    for (int j = 0; j < ND; ++j) pv[6 + j] = clampf((ms[j] - cfg.priv_shift[4]) * cfg.priv_scale[4], -co, co);
 
     // ---- termination (:190-202) --------------------------------------------------------------
     const float hmean = cfg.measure_heights ? s_hmean[tid] : root[2];  // mean(z - measured_heights)
     bool reset = false;
+#pragma unroll 1
     for (int k = 0; k < cfg.n_term_bodies; ++k) {
       const float* f = con + cfg.term_idx[k] * 3;
       const float nrm = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
@@ -430,6 +511,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       term_val[RL_REW_TERMINATION] = term_flag ? 1.f : 0.f;
       term_val[RL_REW_SURVIVAL] = term_flag ? 0.f : 1.f;
       float coll = 0.f;
+#pragma unroll 1
       for (int k = 0; k < cfg.n_pen_bodies; ++k) {
         const float* f = con + cfg.pen_idx[k] * 3;
         const float nrm = sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
@@ -438,91 +520,137 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       term_val[RL_REW_COLLISION] = coll;
       bool stumble = false;
       float fcf = 0.f;
-#pragma unroll
-      for (int k = 0; k < RL_NUM_FEET; ++k) {
-        const float* f = con + cfg.feet_idx[k] * 3;
-        stumble |= sqrtf(f[0] * f[0] + f[1] * f[1]) > 5.0f * fabsf(f[2]);
-        fcf += fmaxf(sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) - cfg.max_contact_force, 0.f);
+      if (((tmask >> RL_REW_STUMBLE) | (tmask >> RL_REW_FEET_CONTACT_FORCES)) & 1u) {
+#pragma unroll 1
+        for (int k = 0; k < RL_NUM_FEET; ++k) {
+          const float* f = con + cfg.feet_idx[k] * 3;
+          stumble |= sqrtf(f[0] * f[0] + f[1] * f[1]) > 5.0f * fabsf(f[2]);
+          fcf += fmaxf(sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) - cfg.max_contact_force, 0.f);
+        }
       }
       term_val[RL_REW_STUMBLE] = stumble ? 1.f : 0.f;
       term_val[RL_REW_FEET_CONTACT_FORCES] = fcf;
       term_val[RL_REW_FEET_AIR_TIME] = 0.f;
     }
+    // stateful feet_air_time term (:1619-1631); its state only advances when the term is enabled
+    if (air_on) {
+      uint32_t nc = 0;
+      float r_air = 0.f;
+#pragma unroll
+      for (int k = 0; k < RL_NUM_FEET; ++k) {
+        const bool contact = con[cfg.feet_idx[k] * 3 + 2] > 1.0f;
+        const bool filt = contact || ((last_contacts >> (8 * k)) & 0xffu);
+        nc |= (contact ? 1u : 0u) << (8 * k);
+        const bool first = (air[k] > 0.f) && filt;
+        air[k] += cfg.dt;
+        r_air += (air[k] - 0.5f) * (first ? 1.f : 0.f);
+        air[k] *= filt ? 0.f : 1.f;
+        b.feet_air_time[k * N + e] = air[k];
+      }
+      *reinterpret_cast<uint32_t*>(b.last_contacts + (size_t)e * 4) = nc;
+      r_air *= (cmd_xy_norm > 0.1f) ? 1.f : 0.f;
+      term_val[RL_REW_FEET_AIR_TIME] = r_air;
+    }
 
     // ---- compute_reward (:314-340): ordered accumulation ----------------------------------------
-    float rew = 0.f;
-    bool air_touched = false;
+    // Accumulator rows (fixed layout, rl_b200.h) are read here, just in time, in two batches, so
+    // that they do not occupy registers during the sweep; other resident warps cover the latency.
+    {
+      float* pe = b.episode_sums + e;
+      float* pc = b.command_sums + e;
+      float rew = 0.f;
+      constexpr int HALF = (RL_MAX_TERMS + 1) / 2;
 #pragma unroll
-    for (int i = 0; i < RL_MAX_TERMS; ++i) {
-      if (i < cfg.n_terms) {
-        const int id = cfg.term_id[i];
-        float v = 0.f;
-        if (id == RL_REW_FEET_AIR_TIME) {
-          // stateful term (:1619-1631); its state only advances when the term is enabled
-          uint32_t nc = 0;
-          float r_air = 0.f;
+      for (int h = 0; h < 2; ++h) {
+        float ev[HALF], cv[HALF];
 #pragma unroll
-          for (int k = 0; k < RL_NUM_FEET; ++k) {
-            const bool contact = con[cfg.feet_idx[k] * 3 + 2] > 1.0f;
-            const bool filt = contact || ((last_contacts >> (8 * k)) & 0xffu);
-            nc |= (contact ? 1u : 0u) << (8 * k);
-            const bool first = (air[k] > 0.f) && filt;
-            air[k] += cfg.dt;
-            r_air += (air[k] - 0.5f) * (first ? 1.f : 0.f);
-            air[k] *= filt ? 0.f : 1.f;
-          }
-          last_contacts = nc;
-          air_touched = true;
-          r_air *= (cmd_xy_norm > 0.1f) ? 1.f : 0.f;
-          v = r_air;
-        } else {
-#pragma unroll
-          for (int t = 0; t < RL_REW_COUNT; ++t) if (t == id) v = term_val[t];
+        for (int k = 0; k < HALF; ++k) {
+          const int i = h * HALF + k;
+          if (i < RL_MAX_TERMS && i < cfg.n_terms) { ev[k] = pe[i * N]; cv[k] = pc[i * N]; }
         }
-        const float r = v * cfg.term_scale[i];
-        rew += r;
-        es[i] += r;
-        cs[i] += r;
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+          const int i = h * HALF + k;
+          if (i < RL_MAX_TERMS && i < cfg.n_terms) {
+            const float r = term_val[cfg.term_id[i]] * cfg.term_scale[i];
+            rew += r;
+            pe[i * N] = ev[k] + r;
+            pc[i * N] = cv[k] + r;
+          }
+        }
       }
-    }
-    if (cfg.only_positive_rewards) rew = fmaxf(rew, 0.f);
-    // "total" row and the optional termination row sit at runtime positions; rows are
-    // walked with static indices so the accumulators stay in registers
-    const float r_term = cfg.has_termination ? term_val[RL_REW_TERMINATION] * cfg.termination_scale : 0.f;
-    const float rew_clipped = rew;
-    if (cfg.has_termination) rew += r_term;
-    b.rew_buf[e] = rew;
-    const float extras[5] = {blv.x, bav.z, sq(blv.x - cmd.x), sq(bav.z - cmd.z), 1.0f};
+      float e_tot = pe[RL_ROW_TOTAL * N], e_term = 0.f, c_term = 0.f, cx[5];
+      if (cfg.has_termination) { e_term = pe[RL_ROW_TERMINATION * N]; c_term = pc[RL_ROW_TERMINATION * N]; }
 #pragma unroll
-    for (int r = 0; r < MAXR_E; ++r) {
-      if (cfg.has_termination && r == cfg.n_terms) es[r] += r_term;
-      if (r == n_keys) es[r] += rew_clipped;
-      if (r <= n_keys) b.episode_sums[r * Ns + e] = es[r];
-    }
-#pragma unroll
-    for (int r = 0; r < MAXR_C; ++r) {
-      if (cfg.has_termination && r == cfg.n_terms) cs[r] += r_term;
-#pragma unroll
-      for (int x = 0; x < 5; ++x) if (r == n_keys + x) cs[r] += extras[x];
-      if (r < n_keys + 5) b.command_sums[r * Ns + e] = cs[r];
-    }
-    if (air_touched) {
-#pragma unroll
-      for (int k = 0; k < RL_NUM_FEET; ++k) b.feet_air_time[k * Ns + e] = air[k];
-      *reinterpret_cast<uint32_t*>(b.last_contacts + (size_t)e * 4) = last_contacts;
+      for (int x = 0; x < 5; ++x) cx[x] = pc[(RL_ROW_EXTRAS + x) * N];
+      if (cfg.only_positive_rewards) rew = fmaxf(rew, 0.f);
+      pe[RL_ROW_TOTAL * N] = e_tot + rew;
+      if (cfg.has_termination) {
+        const float r = term_val[RL_REW_TERMINATION] * cfg.termination_scale;
+        rew += r;
+        pe[RL_ROW_TERMINATION * N] = e_term + r;
+        pc[RL_ROW_TERMINATION * N] = c_term + r;
+      }
+      b.rew_buf[e] = rew;
+      pc[(RL_ROW_EXTRAS + 0) * N] = cx[0] + blv.x;               // lin_vel_raw
+      pc[(RL_ROW_EXTRAS + 1) * N] = cx[1] + bav.z;               // ang_vel_raw
+      pc[(RL_ROW_EXTRAS + 2) * N] = cx[2] + sq(blv.x - cmd.x);   // lin_vel_residual
+      pc[(RL_ROW_EXTRAS + 3) * N] = cx[3] + sq(bav.z - cmd.z);   // ang_vel_residual
+      pc[(RL_ROW_EXTRAS + 4) * N] = cx[4] + 1.0f;                // ep_timesteps
     }
 
-    // ---- observations (:342-392), emitted in column order with noise (:392) and clip (:134) -----
-    {
-      NoiseGen ng(b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr, args.seed, rng_step, (uint32_t)e);
-      int c = 0;
-      auto emit = [&](float v) {
-        if (cfg.add_noise) {
-          const float ns = b.noise_scale_vec[c];
-          if (ns != 0.f) v += (2.0f * ng.get(c) - 1.0f) * ns;
+    // ---- remaining state (:152, :160-162, :183) ----------------------------------------------------
+    b.episode_length_buf[e] = ep_len;
+    b.base_lin_vel[0 * N + e] = blv.x; b.base_lin_vel[1 * N + e] = blv.y; b.base_lin_vel[2 * N + e] = blv.z;
+    b.base_ang_vel[0 * N + e] = bav.x; b.base_ang_vel[1 * N + e] = bav.y; b.base_ang_vel[2 * N + e] = bav.z;
+    b.projected_gravity[0 * N + e] = grav.x; b.projected_gravity[1 * N + e] = grav.y;
+    b.projected_gravity[2 * N + e] = grav.z;
+    b.last_root_vel[0 * N + e] = vw.x; b.last_root_vel[1 * N + e] = vw.y; b.last_root_vel[2 * N + e] = vw.z;
+    b.last_root_vel[3 * N + e] = ww.x; b.last_root_vel[4 * N + e] = ww.y; b.last_root_vel[5 * N + e] = ww.z;
+
+    // ---- observations (:342-392) with noise (:392) and clip (:134) --------------------------------
+    if (STD_OBS) {
+      ObsNoise noise(b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr, args.seed, rng_step, (uint32_t)e);
+      // gravity 0-2 | commands 3-5 | q 6-17 | qd 18-29 | actions 30-41; noisy values are numbered
+      // 0-2 (gravity), 3-14 (q), 15-26 (qd): 4 Philox blocks of 8 sixteen-bit uniforms
+      o[0] = grav.x; o[1] = grav.y; o[2] = grav.z;
+      o[3] = cmd.x * cfg.commands_scale[0]; o[4] = cmd.y * cfg.commands_scale[1]; o[5] = cmd.z * cfg.commands_scale[2];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        o[6 + j] = (dof[2 * j] - cfg.default_dof_pos[j]) * cfg.obs_scale_dof_pos;
+        o[18 + j] = dof[2 * j + 1] * cfg.obs_scale_dof_vel;
+        o[30 + j] = act[j];
+      }
+      if (cfg.add_noise) {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          const int c = k < 3 ? k : k + 3;     // noisy value k lives in column c
+          if ((k & 7) == 0) noise.need(k);
+          o[c] = noise.apply(o[c], cfg.noise_scale_core[c], k, c);
         }
-        obs[c] = clampf(v, -cfg.clip_obs, cfg.clip_obs);
-        ++c;
+      }
+#pragma unroll
+      for (int c = 0; c < 42; ++c) o[c] = clampf(o[c], -co, co);
+    }
+  }
+  __syncthreads();   // every thread is done with the input rows: the output rows may overwrite them
+
+  if (valid) {
+    float* obs = s_obs + tid * W;
+    float* priv = s_priv + tid * RL_PRIV_DIM;
+    if (STD_OBS) {
+      // 42-float rows: 64-bit shared stores are bank-conflict free
+#pragma unroll
+      for (int c = 0; c < 42; c += 2) *reinterpret_cast<float2*>(obs + c) = make_float2(o[c], o[c + 1]);
+    } else {
+      // generic layout: [only_lin][only_ang][lin,ang][gravity][cmd][q][qd][a][yaw], runtime offsets
+      ObsNoise noise(b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr, args.seed, rng_step, (uint32_t)e);
+      const float4 cmd4 = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
+      int c = 0, k = 0;
+      auto emit = [&](float v) {
+        const float ns = cfg.add_noise ? cfg.noise_scale_core[c] : 0.f;
+        if (ns != 0.f) { noise.need(k); v = noise.apply(v, ns, k, c); ++k; }
+        obs[c++] = clampf(v, -co, co);
       };
       if (cfg.observe_only_lin_vel) {
         emit(blv.x * cfg.obs_scale_lin_vel); emit(blv.y * cfg.obs_scale_lin_vel); emit(blv.z * cfg.obs_scale_lin_vel);
@@ -537,7 +665,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       }
       emit(grav.x); emit(grav.y); emit(grav.z);
       if (cfg.observe_command) {
-        emit(cmd.x * cfg.commands_scale[0]); emit(cmd.y * cfg.commands_scale[1]); emit(cmd.z * cfg.commands_scale[2]);
+        emit(cmd4.x * cfg.commands_scale[0]); emit(cmd4.y * cfg.commands_scale[1]); emit(cmd4.z * cfg.commands_scale[2]);
       }
 #pragma unroll
       for (int j = 0; j < ND; ++j) emit((dof[2 * j] - cfg.default_dof_pos[j]) * cfg.obs_scale_dof_pos);
@@ -554,42 +682,40 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
         emit(clampf(0.5f * heading, -1.f, 1.f));
       }
     }
-
-    // ---- privileged observations (:398-417) + clip (:136) ------------------------------------------
-    {
-      const float co = cfg.clip_obs;
-      float pv[RL_PRIV_DIM];
-      pv[0] = (fr - cfg.priv_shift[0]) * cfg.priv_scale[0];
-      pv[1] = (re - cfg.priv_shift[1]) * cfg.priv_scale[1];
-      pv[2] = (pl - cfg.priv_shift[2]) * cfg.priv_scale[2];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) pv[3 + k] = (com[k] - cfg.priv_shift[3]) * cfg.priv_scale[3];
+    for (int k = 0; k < RL_PRIV_DIM / 2; ++k) *reinterpret_cast<float2*>(priv + 2 * k) = make_float2(pv[2 * k], pv[2 * k + 1]);
+    if (FUSE_TORQUES) {
 #pragma unroll
-      for (int j = 0; j < ND; ++j) pv[6 + j] = (ms[j] - cfg.priv_shift[4]) * cfg.priv_scale[4];
-      // 18-float rows: 64-bit shared stores are bank-conflict free
-#pragma unroll
-      for (int k = 0; k < RL_PRIV_DIM / 2; ++k)
-        *reinterpret_cast<float2*>(priv + 2 * k) = make_float2(clampf(pv[2 * k], -co, co), clampf(pv[2 * k + 1], -co, co));
+      for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(s_tq + tid * ND + 4 * k) = *reinterpret_cast<float4*>(tq + 4 * k);
     }
-
-    // ---- remaining state (:152, :160-162, :183) ----------------------------------------------------
-    b.episode_length_buf[e] = ep_len;
-    b.base_lin_vel[0 * Ns + e] = blv.x; b.base_lin_vel[1 * Ns + e] = blv.y; b.base_lin_vel[2 * Ns + e] = blv.z;
-    b.base_ang_vel[0 * Ns + e] = bav.x; b.base_ang_vel[1 * Ns + e] = bav.y; b.base_ang_vel[2 * Ns + e] = bav.z;
-    b.projected_gravity[0 * Ns + e] = grav.x; b.projected_gravity[1 * Ns + e] = grav.y;
-    b.projected_gravity[2 * Ns + e] = grav.z;
-    b.last_root_vel[0 * Ns + e] = vw.x; b.last_root_vel[1 * Ns + e] = vw.y; b.last_root_vel[2 * Ns + e] = vw.z;
-    b.last_root_vel[3 * Ns + e] = ww.x; b.last_root_vel[4 * Ns + e] = ww.y; b.last_root_vel[5 * Ns + e] = ww.z;
   }
   if (dirty) s_root_dirty = 1;
+  fence_async_smem();   // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
   __syncthreads();
 
-  // ---- 6. coalesced write-back of the AoS outputs -------------------------------------------------
-  if (W == cfg.num_obs) stage_out(b.obs_buf + (size_t)tile0 * W, s_obs, n_valid * W);
-  else stage_out_rows(b.obs_buf + (size_t)tile0 * cfg.num_obs, s_obs, n_valid, W, cfg.num_obs);
-  stage_out(b.privileged_obs_buf + (size_t)tile0 * RL_PRIV_DIM, s_priv, n_valid * RL_PRIV_DIM);
-  if (FUSE_TORQUES) stage_out(b.torques + (size_t)tile0 * ND, s_tq, n_valid * ND);
-  if (s_root_dirty) stage_out(b.root_states + (size_t)tile0 * 13, s_root, n_valid * 13);
+  // ---- 6. write-back of the AoS outputs: bulk stores for full aligned tiles ------------------------
+  float* o_obs = b.obs_buf + (size_t)tile0 * cfg.num_obs;
+  float* o_priv = b.privileged_obs_buf + (size_t)tile0 * RL_PRIV_DIM;
+  float* o_tq = b.torques + (size_t)tile0 * ND;
+  float* o_root = b.root_states + (size_t)tile0 * 13;
+  const bool bulk_out = (n_valid == TILE) && (W == cfg.num_obs) && ((W & 3) == 0) &&
+      ((((uintptr_t)o_obs | (uintptr_t)o_priv | (uintptr_t)o_tq | (uintptr_t)o_root) & 15) == 0);
+  if (bulk_out) {
+    if (tid == 0) {
+      bulk_s2g(o_obs, s_obs, (uint32_t)(TILE * W * 4));
+      bulk_s2g(o_priv, s_priv, TILE * RL_PRIV_DIM * 4);
+      if (FUSE_TORQUES) bulk_s2g(o_tq, s_tq, TILE * ND * 4);
+      if (s_root_dirty) bulk_s2g(o_root, s_root, TILE * 13 * 4);
+      bulk_commit();
+      bulk_wait_read0();   // shared memory must stay alive until the copy engine has read it
+    }
+  } else {
+    if (W == cfg.num_obs) stage_out<TILE>(o_obs, s_obs, n_valid * W);
+    else stage_out_rows<TILE>(o_obs, s_obs, n_valid, W, cfg.num_obs);
+    stage_out<TILE>(o_priv, s_priv, n_valid * RL_PRIV_DIM);
+    if (FUSE_TORQUES) stage_out<TILE>(o_tq, s_tq, n_valid * ND);
+    if (s_root_dirty) stage_out<TILE>(o_root, s_root, n_valid * 13);
+  }
 
   // device step counter: every CTA read it on entry; the last one to leave advances it
   if (b.step_state && tid == 0) {
@@ -643,10 +769,12 @@ env_torques_kernel(const __grid_constant__ StepArgs args) {
     *reinterpret_cast<float4*>(b.torques + (size_t)e * ND + 4 * k) = *reinterpret_cast<float4*>(out + 4 * k);
 }
 
-static size_t step_smem_bytes(const RlEnvCfg& cfg) {
+static size_t step_smem_bytes(const RlEnvCfg& cfg, int tile) {
   const int P = cfg.measure_heights ? cfg.num_height_points : 0;
   const int W = cfg.num_obs - P;
-  const size_t floats = (size_t)TILE * (13 + 24 + cfg.num_bodies * 3 + ND + ND + RL_PRIV_DIM + W + 1);
+  const size_t in_floats = 24 + cfg.num_bodies * 3 + ND + ND;       // dof, contact, actions, torques in
+  const size_t out_floats = (size_t)W + RL_PRIV_DIM + ND;            // obs, priv, torques out (alias the inputs)
+  const size_t floats = (size_t)tile * (1 + 13 + (in_floats > out_floats ? in_floats : out_floats));
   return floats * sizeof(float);
 }
 
@@ -656,7 +784,10 @@ static int validate(const RlEnvCfg* cfg, const RlEnvBuffers* b, bool need_torque
   RL_REQUIRE(cfg->num_actions == ND, RL_ERR_UNSUPPORTED, "env step: num_actions=%d (only 12 supported)", cfg->num_actions);
   RL_REQUIRE(cfg->num_bodies > 0 && cfg->num_bodies <= RL_MAX_BODIES, RL_ERR_BAD_CFG, "env step: num_bodies=%d", cfg->num_bodies);
   RL_REQUIRE(cfg->n_terms >= 0 && cfg->n_terms <= RL_MAX_TERMS, RL_ERR_UNSUPPORTED, "env step: n_terms=%d (max %d enabled reward terms)", cfg->n_terms, RL_MAX_TERMS);
-  RL_REQUIRE(cfg->n_sum_keys == cfg->n_terms + (cfg->has_termination ? 1 : 0), RL_ERR_BAD_CFG, "env step: n_sum_keys=%d inconsistent", cfg->n_sum_keys);
+  RL_REQUIRE((long long)cfg->num_envs * RL_COMMAND_ROWS < (1ll << 31), RL_ERR_UNSUPPORTED,
+             "env step: num_envs=%d too large for 32-bit element indices", cfg->num_envs);
+  RL_REQUIRE(cfg->num_obs - (cfg->measure_heights ? cfg->num_height_points : 0) <= RL_MAX_CORE_OBS, RL_ERR_UNSUPPORTED,
+             "env step: more than %d non-height observation columns", RL_MAX_CORE_OBS);
   RL_REQUIRE(cfg->control_type >= 0 && cfg->control_type <= 2, RL_ERR_BAD_CFG, "env step: control_type=%d", cfg->control_type);
   RL_REQUIRE(cfg->rand_interval > 0 && (!cfg->push_robots || cfg->push_interval > 0), RL_ERR_BAD_CFG, "env step: intervals must be positive");
   const int P = cfg->measure_heights ? cfg->num_height_points : 0;
@@ -667,7 +798,7 @@ static int validate(const RlEnvCfg* cfg, const RlEnvBuffers* b, bool need_torque
              b->base_ang_vel && b->projected_gravity && b->Kp_factors && b->Kd_factors &&
              b->motor_strengths && b->friction_coeffs && b->restitutions && b->payloads &&
              b->com_displacements && b->feet_air_time && b->last_contacts && b->episode_length_buf &&
-             b->commands && b->episode_sums && b->command_sums && b->noise_scale_vec,
+             b->commands && b->episode_sums && b->command_sums,
              RL_ERR_BAD_ARG, "env step: a required buffer pointer is null");
   RL_REQUIRE(((uintptr_t)b->commands & 15) == 0 && ((uintptr_t)b->last_contacts & 3) == 0, RL_ERR_BAD_ARG,
              "env step: commands must be 16B aligned, last_contacts 4B aligned");
@@ -680,23 +811,48 @@ static int validate(const RlEnvCfg* cfg, const RlEnvBuffers* b, bool need_torque
   return RL_OK;
 }
 
+template <bool FUSE, int TILE, bool STD>
+static int launch_inst(const StepArgs& args, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(env_step_kernel<FUSE, TILE, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = smem;
+  }
+  const int grid = (args.cfg.num_envs + TILE - 1) / TILE;
+  env_step_kernel<FUSE, TILE, STD><<<grid, TILE, smem, st>>>(args);
+  return check_launch("env_step_kernel");
+}
+
+template <bool FUSE, int TILE>
+static int launch_tile(const StepArgs& args, size_t smem, cudaStream_t st) {
+  const RlEnvCfg& c = args.cfg;
+  const int core = c.num_obs - (c.measure_heights ? c.num_height_points : 0);
+  const bool std_obs = c.observe_command && !c.observe_vel && !c.observe_only_ang_vel && !c.observe_only_lin_vel &&
+                       !c.observe_yaw && core == 42;
+  return std_obs ? launch_inst<FUSE, TILE, true>(args, smem, st) : launch_inst<FUSE, TILE, false>(args, smem, st);
+}
+
+static int env_tile() {
+  static int tile = 0;
+  if (!tile) {
+    const char* e = getenv("RL_ENV_TILE");
+    tile = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return tile;
+}
+
 template <bool FUSE>
 static int launch_step(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed, uint64_t step, void* stream) {
   int rc = validate(cfg, b, !FUSE);
   if (rc != RL_OK) return rc;
-  const size_t smem = step_smem_bytes(*cfg);
+  const int tile = env_tile();
+  const size_t smem = step_smem_bytes(*cfg, tile);
   RL_REQUIRE(smem <= 227 * 1024, RL_ERR_UNSUPPORTED, "env step: tile needs %zu B of shared memory", smem);
-  static size_t configured = 0;  // per template instantiation
-  if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(env_step_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-    configured = smem;
-  }
   StepArgs args;
   args.cfg = *cfg; args.b = *b; args.seed = seed; args.step = step;
-  const int grid = (cfg->num_envs + TILE - 1) / TILE;
-  env_step_kernel<FUSE><<<grid, TILE, smem, (cudaStream_t)stream>>>(args);
-  return check_launch("env_step_kernel");
+  if (tile == 128) return launch_tile<FUSE, 128>(args, smem, (cudaStream_t)stream);
+  return launch_tile<FUSE, 64>(args, smem, (cudaStream_t)stream);
 }
 
 }  // namespace rl

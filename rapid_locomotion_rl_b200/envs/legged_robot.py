@@ -124,11 +124,14 @@ class LeggedRobot:
         self.commands = torch.zeros_like(self.commands_value)
         self.commands_scale = torch.tensor(p.commands_scale, device=dev)
         self.measured_heights = z(N, p.num_height_points) if p.measure_heights else 0
-        self._episode_sums = z(p.n_sum_keys + 1, N)
-        self._command_sums = z(p.n_sum_keys + len(COMMAND_SUM_EXTRAS), N)
-        self.episode_sums = {n: self._episode_sums[i] for i, n in enumerate(p.sum_names + ["total"])}
-        self.command_sums = {n: self._command_sums[i] for i, n in enumerate(p.sum_names + COMMAND_SUM_EXTRAS)}
-        self._episode_sum_out = z(p.n_sum_keys + 2, dtype=torch.float64)
+        D = _lib.DEFINES
+        self._episode_sums = z(D["RL_MAX_TERMS"] + 2, N)      # fixed row layout, see rl_b200.h
+        self._command_sums = z(D["RL_MAX_TERMS"] + 6, N)
+        self._episode_rows = dict(p.sum_rows, total=D["RL_MAX_TERMS"] + 1)
+        self._command_rows = dict(p.sum_rows, **{n: D["RL_MAX_TERMS"] + 1 + i for i, n in enumerate(COMMAND_SUM_EXTRAS)})
+        self.episode_sums = {n: self._episode_sums[r] for n, r in self._episode_rows.items()}
+        self.command_sums = {n: self._command_sums[r] for n, r in self._command_rows.items()}
+        self._episode_sum_out = z(D["RL_MAX_TERMS"] + 3, dtype=torch.float64)
         self.common_step_counter = 0
 
         # ---- constants as tensors (callers read them) ----
@@ -252,7 +255,7 @@ class LeggedRobot:
         b.feet_air_time = P(self._feet_air_time); b.last_contacts = P(self._last_contacts_u8)
         b.episode_length_buf = P(self.episode_length_buf); b.commands = P(self.commands)
         b.episode_sums = P(self._episode_sums); b.command_sums = P(self._command_sums)
-        b.noise_scale_vec = P(self.noise_scale_vec); b.height_points = P(self._height_points_xy)
+        b.height_points = P(self._height_points_xy)
         b.height_samples = P(self.height_samples) if self.height_samples is not None else None
         b.noise_u = b.dr_u = b.push_u = None
         b.step_state = None
@@ -272,7 +275,7 @@ class LeggedRobot:
     def _make_reset_cfg(self):
         p, cfg = self.params, self.cfg
         r = _lib.RlResetCfg()
-        r.num_envs, r.n_sum_keys = p.num_envs, p.n_sum_keys
+        r.num_envs, r.n_terms, r.has_termination = p.num_envs, p.n_terms, p.has_termination
         r.custom_origins = int(self.custom_origins)
         r.terrain_curriculum = int(bool(cfg.terrain.curriculum))
         r.max_terrain_level = int(getattr(cfg.terrain, "max_terrain_level", cfg.terrain.num_rows))
@@ -379,8 +382,8 @@ class LeggedRobot:
         # extras (:261-290): device-side means, no host sync
         p = self.params
         sums = self._episode_sum_out
-        means = (sums[:p.n_sum_keys + 1] / sums[p.n_sum_keys + 1]).to(torch.float)
-        self.extras["train/episode"] = {"rew_" + n: means[i] for i, n in enumerate(p.sum_names + ["total"])}
+        means = (sums[:-1] / sums[-1]).to(torch.float)
+        self.extras["train/episode"] = {"rew_" + n: means[r] for n, r in self._episode_rows.items()}
         if cfg.terrain.curriculum:
             self.extras["train/episode"]["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
         if cfg.commands.command_curriculum:
@@ -447,7 +450,7 @@ class LeggedRobot:
         g.ep_len = f32(min(self.cfg.env.max_episode_length, timesteps))
         g.lin_threshold = f32(self.cfg.commands.forward_curriculum_threshold * self.reward_scales["tracking_lin_vel"])
         g.ang_threshold = f32(self.cfg.commands.yaw_curriculum_threshold * self.reward_scales["tracking_ang_vel"])
-        g.lin_slot, g.ang_slot = p.sum_names.index("tracking_lin_vel"), p.sum_names.index("tracking_ang_vel")
+        g.lin_slot, g.ang_slot = p.sum_rows["tracking_lin_vel"], p.sum_rows["tracking_ang_vel"]
         g.n_command_sums = self._command_sums.shape[0]
         g.num_train_envs = self.num_train_envs
         nlo, nhi = cur.neighbour_ranges(0.5)

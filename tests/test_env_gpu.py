@@ -98,6 +98,8 @@ def test_step_vs_oracle_at_size(case, n):
     st = random_persistent_state(rng, n, list(o.episode_sums.keys()))
     for k in o.command_sums:
         st["command_sums/" + k] = rng.normal(0, 1, n).astype(np.float32)
+    for k in ("env_origins", "terrain_levels", "terrain_types"):   # drawn at construction by the product
+        st[k] = getattr(env, k).cpu().numpy()
     p = env.params
     for step in range(2):
         sim = synthetic_state(1000 + step, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx,
