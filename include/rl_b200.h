@@ -361,6 +361,21 @@ int rl_gae(const float* rewards, const float* values, const uint8_t* dones,
            const float* last_values, float* returns, float* advantages, int32_t T, int32_t N,
            float gamma, float lam, void* workspace, void* stream);
 
+/* Dense contraction of the learner on the tcgen05 tensor cores (actor_critic.py:38-100 nn.Linear
+ * layers; forward and the autograd backward of ppo.py:102-168).  bf16 operands, fp32 accumulation
+ * in tensor memory, fused epilogue:
+ *   transposed = 0:  C[M,N] = A[M,K] * B[N,K]^T   (forward: B = weight [out,in]; dgrad: B = weight^T)
+ *   transposed = 1:  C[M,N] = A[K,M]^T * B[K,N]   (wgrad: A = dY [batch,out], B = X [batch,in])
+ * epilogue: 0 fp32 store, 1 fp32 atomic add (split_k > 1), 2 bf16 elu(acc + bias), 3 fp32 acc + bias,
+ *           4 bf16 acc * elu'(aux) with aux the bf16 ELU OUTPUT of the layer being differentiated,
+ *           5 bf16 store.
+ * db (transposed form only, may be NULL): db[m] += sum_k A[k,m], the bias gradient, from an extra
+ * ones-vector MMA.  All pitches in elements; bf16 operands need 16 B aligned bases and pitches that
+ * are multiples of 8. */
+int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const void* aux, float* db,
+                 int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ld_aux,
+                 int32_t transposed, int32_t epilogue, int32_t split_k, void* stream);
+
 /* history_wrapper.py:23 - append obs to a 2H-slot ring so that the last H steps are
  * always one contiguous row span: hist [N, 2*H*num_obs], writes slots k and k+H. */
 int rl_history_push(float* hist, const float* obs, int32_t N, int32_t num_obs, int32_t H,

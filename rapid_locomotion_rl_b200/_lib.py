@@ -96,6 +96,7 @@ SIGNATURES = {
     "rl_gae_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "rl_gae": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
     "rl_history_push": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "rl_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int32] * 10 + [_P]),
 }
 
 

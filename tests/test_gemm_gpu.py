@@ -1,0 +1,99 @@
+"""tcgen05 GEMM (csrc/gemm_tc.cu, rl_gemm_bf16) against a plain PyTorch fp32 reference of the same
+op on the same bf16-rounded operands.  Tolerance: bf16 inputs, fp32 accumulation -> the only
+difference is summation order: rtol 2e-3 of the row scale (atol = 2e-3 * sqrt(K))."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+EPI_F32, EPI_ATOMIC, EPI_BIAS_ELU_BF16, EPI_BIAS_F32, EPI_DELU_BF16, EPI_BF16 = range(6)
+
+
+def gemm(A, B, C, bias=None, aux=None, db=None, M=None, N=None, K=None, transposed=0, epilogue=0, split_k=1):
+    from rapid_locomotion_rl_b200 import _lib
+    lib = _lib.lib()
+    P = _lib.ptr
+    _lib.check(lib.rl_gemm_bf16(P(A), P(B), P(C), P(bias), P(aux), P(db), M, N, K, A.stride(0), B.stride(0),
+                                C.stride(0), 0 if aux is None else aux.stride(0), transposed, epilogue, split_k,
+                                _lib.current_stream()))
+    torch.cuda.synchronize()
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (1000, 512, 64), (24000, 256, 512),
+                                   (333, 18, 128), (4000, 12, 128), (129, 1, 128), (4096, 256, 640), (77, 32, 24)])
+def test_nt_plain(M, N, K):
+    torch.manual_seed(M + N + K)
+    A, B = rnd(M, K), rnd(N, K)
+    C = torch.full((M, N + 3), 7.0, device="cuda")[:, :N] if N % 4 else torch.empty(M, N, device="cuda")
+    ldc_ok = C.stride(0)
+    gemm(A, B, C, M=M, N=N, K=K)
+    ref = A.float() @ B.float().t()
+    torch.testing.assert_close(C, ref, rtol=2e-3, atol=2e-3 * K ** 0.5)
+    assert ldc_ok == C.stride(0)
+
+
+def test_nt_padded_pitch_and_k_tail():
+    """K not a multiple of 64 (TMA zero fill) and pitches wider than the logical extents."""
+    M, N, K = 500, 96, 60
+    A_full, B_full = rnd(M, 64), rnd(N, 64)
+    C = torch.empty(M, N, device="cuda")
+    gemm(A_full, B_full, C, M=M, N=N, K=K)
+    ref = A_full[:, :K].float() @ B_full[:, :K].float().t()
+    torch.testing.assert_close(C, ref, rtol=2e-3, atol=2e-2)
+
+
+def test_nt_bias_elu_bf16_and_bias_f32():
+    M, N, K = 3000, 512, 64
+    A, B, bias = rnd(M, K), rnd(N, K, scale=0.2), torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().t() + bias
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    gemm(A, B, C, bias=bias, M=M, N=N, K=K, epilogue=EPI_BIAS_ELU_BF16)
+    torch.testing.assert_close(C.float(), torch.nn.functional.elu(ref), rtol=1e-2, atol=2e-2)
+    C2 = torch.empty(M, N, device="cuda")
+    gemm(A, B, C2, bias=bias, M=M, N=N, K=K, epilogue=EPI_BIAS_F32)
+    torch.testing.assert_close(C2, ref, rtol=2e-3, atol=2e-2)
+
+
+def test_nt_delu_epilogue():
+    """dgrad through an ELU: dX = (dY W) * elu'(x) with elu' taken from the stored ELU output."""
+    M, N, K = 2000, 256, 128      # dX [M,N] = dY [M,K] * Wt [N,K]^T
+    dY, Wt = rnd(M, K), rnd(N, K, scale=0.2)
+    pre = torch.randn(M, N, device="cuda")
+    y = torch.nn.functional.elu(pre).to(torch.bfloat16)
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    gemm(dY, Wt, C, aux=y, M=M, N=N, K=K, epilogue=EPI_DELU_BF16)
+    yf = y.float()
+    ref = (dY.float() @ Wt.float().t()) * torch.where(yf > 0, torch.ones_like(yf), yf + 1)
+    torch.testing.assert_close(C.float(), ref, rtol=1e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("M,N,K,split", [(512, 64, 24000, 16), (256, 512, 4096, 4), (128, 256, 1000, 1),
+                                         (12, 128, 3000, 8), (18, 32, 777, 3), (1, 128, 2048, 2), (256, 640, 9000, 5)])
+def test_tn_wgrad_splitk_and_db(M, N, K, split):
+    """dW[M,N] = dY[K,M]^T X[K,N] with split-K atomics, db[m] = sum_k dY[k,m] from the ones-MMA."""
+    torch.manual_seed(K)
+    Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    dY, X = rnd(K, Mp, scale=0.1), rnd(K, Np)
+    C = torch.zeros(M, N, device="cuda")
+    db = torch.zeros(M, device="cuda")
+    gemm(dY, X, C, db=db, M=M, N=N, K=K, transposed=1, epilogue=EPI_ATOMIC if split > 1 else EPI_F32, split_k=split)
+    ref = dY[:, :M].float().t() @ X[:, :N].float()
+    torch.testing.assert_close(C, ref, rtol=3e-3, atol=3e-3 * K ** 0.5 * 0.1)
+    torch.testing.assert_close(db, dY[:, :M].float().sum(0), rtol=3e-3, atol=3e-3 * K ** 0.5 * 0.1)
+
+
+def test_bad_arguments():
+    from rapid_locomotion_rl_b200 import _lib
+    A, B = rnd(128, 64), rnd(128, 64)
+    C = torch.empty(128, 128, device="cuda")
+    with pytest.raises(_lib.RlError):
+        gemm(A, B, C, M=128, N=128, K=64, epilogue=EPI_BIAS_F32)            # bias missing
+    with pytest.raises(_lib.RlError):
+        gemm(A[:, 1:], B, C, M=128, N=128, K=63)                            # misaligned base
+    with pytest.raises(_lib.RlError):
+        gemm(A, B, C, M=128, N=128, K=64, split_k=2)                        # split-K without atomics
