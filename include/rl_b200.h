@@ -368,13 +368,64 @@ int rl_gae(const float* rewards, const float* values, const uint8_t* dones,
  *   transposed = 1:  C[M,N] = A[K,M]^T * B[K,N]   (wgrad: A = dY [batch,out], B = X [batch,in])
  * epilogue: 0 fp32 store, 1 fp32 atomic add (split_k > 1), 2 bf16 elu(acc + bias), 3 fp32 acc + bias,
  *           4 bf16 acc * elu'(aux) with aux the bf16 ELU OUTPUT of the layer being differentiated,
- *           5 bf16 store.
+ *           5 bf16 store, 6 bf16 acc + bias.
  * db (transposed form only, may be NULL): db[m] += sum_k A[k,m], the bias gradient, from an extra
  * ones-vector MMA.  All pitches in elements; bf16 operands need 16 B aligned bases and pitches that
  * are multiples of 8. */
 int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const void* aux, float* db,
                  int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ld_aux,
                  int32_t transposed, int32_t epilogue, int32_t split_k, void* stream);
+
+/* ---- PPO update support (mini_gym_learn/ppo/ppo.py:94-178) ---------------------------------- */
+
+/* rollout_storage.py:121-137: the twelve per-minibatch advanced-index gathers, fused with the bf16
+ * staging of the GEMM inputs.  Flat storage rows are [T*N, dim] fp32; idx [B] int64.
+ *   Xp  [B, ldp]  bf16: privileged obs (zero padded)          encoder input
+ *   Xac [B, ldac] bf16: obs in columns [0, obs_dim); columns [obs_dim, obs_dim+18) are left for the
+ *                       encoder latent; the rest zero          actor / critic input
+ *   Xh  [B, ldh]  bf16: observation history (may be NULL)      adaptation-module input
+ *   Lrow [B, 40] fp32: actions 12 | old mu 12 | old sigma 12 | old log-prob | advantage | return | old value */
+int rl_ppo_gather(const float* obs, const float* priv, const float* hist, const float* actions,
+                  const float* values, const float* returns, const float* logp, const float* adv,
+                  const float* mu, const float* sigma, const int64_t* idx, int32_t B, int32_t obs_dim,
+                  int32_t priv_dim, int32_t hist_dim, void* Xp, int32_t ldp, void* Xac, int32_t ldac, void* Xh,
+                  int32_t ldh, float* Lrow, void* stream);
+/* fp32 [rows, cols] -> bf16 dst[:, dst_col0 : dst_col0 + pad_to], zero padded beyond cols */
+int rl_cast_bf16(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols,
+                 int32_t dst_col0, int32_t pad_to, void* stream);
+/* ppo.py:110-144 (KL, clipped surrogate, clipped value loss, entropy) and :157-164 (adaptation MSE)
+ * with the analytic gradients w.r.t. the network outputs written as bf16 GEMM operands:
+ * dmean [B,16], dvalue [B,8], dpred [B,24]; dstd[12] and stats[4] (sum surrogate, sum value loss,
+ * sum kl, sum adaptation squared error; double) are accumulated atomically.  inv_global_B =
+ * 1 / (B * world_size). */
+int rl_ppo_loss(const float* mean, const float* value, const float* pred, const void* Xac, int32_t ldac,
+                int32_t lat_off, const float* Lrow, const float* std, int32_t B, float clip, float value_coef,
+                float entropy_coef, int32_t use_clipped_value, float inv_global_B, void* dmean, void* dvalue,
+                void* dpred, float* dstd, double* stats, void* stream);
+/* ppo.py:157-164 alone: mse(adaptation_module(hist), encoder(priv).detach()) and its gradient dpred
+ * [B,24] bf16; adds the squared error to stats[3].  Called after the policy optimiser step, as the
+ * reference computes the target with the already updated encoder. */
+int rl_adapt_loss(const float* pred, const void* Xac, int32_t ldac, int32_t lat_off, int32_t B,
+                  float inv_global_B, void* dpred, double* stats, void* stream);
+/* ppo.py:116-124 + :149: gradient 2-norm over `n` floats -> clip coefficient; kl mean -> adaptive
+ * learning rate, all on the device.  ctrl[0] = lr (in/out), ctrl[1] = clip coefficient, ctrl[2] = kl.
+ * workspace: 16 zeroed bytes. */
+int rl_grad_finalize(const float* grad, int64_t n, const double* stats, float* ctrl, void* workspace,
+                     double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, void* stream);
+/* torch.optim.Adam step (ppo.py:44-46,150,168) fused with gradient scaling and zero_grad.
+ * use_ctrl: lr = ctrl[0], grad scaled by ctrl[1]; else lr_fixed.  grad_scale: extra factor. */
+int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,
+            int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+/* bf16 shadow copies of the fp32 master weights: wb [out, ld_wb] and its transpose wbt [in, ld_wbt]
+ * (host arrays of n_layers device pointers / dims) */
+int rl_refresh_shadows(const void* const* w, void* const* wb, void* const* wbt, const int32_t* out_dim,
+                       const int32_t* in_dim, const int32_t* ld_wb, const int32_t* ld_wbt, int32_t n_layers,
+                       void* stream);
+/* actor_critic.py:137-147: a = mu + std * N(0,1) (Philox + Box-Muller, or injected normals [N,12]),
+ * summed Normal log-prob, and the mu / sigma rows PPO.act stores */
+int rl_policy_sample(const float* mean, const float* std, int32_t N, uint64_t seed, uint64_t step,
+                     const float* inj_normal, float* actions, float* logp, float* mu_out, float* sigma_out,
+                     void* stream);
 
 /* history_wrapper.py:23 - append obs to a 2H-slot ring so that the last H steps are
  * always one contiguous row span: hist [N, 2*H*num_obs], writes slots k and k+H. */

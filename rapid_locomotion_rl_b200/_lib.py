@@ -97,6 +97,16 @@ SIGNATURES = {
     "rl_gae": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
     "rl_history_push": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int32] * 10 + [_P]),
+    "rl_ppo_gather": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "rl_cast_bf16": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "rl_ppo_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
+                              C.c_int32, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "rl_adapt_loss": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
+    "rl_grad_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P]),
+    "rl_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
+                          C.c_float, _P]),
+    "rl_refresh_shadows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
+    "rl_policy_sample": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }
 
 

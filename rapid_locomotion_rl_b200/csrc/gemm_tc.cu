@@ -32,6 +32,7 @@ enum Epilogue : int {
   EPI_BIAS_F32 = 3,     // C(fp32) = acc + bias[n]             (output layer forward)
   EPI_DELU_BF16 = 4,    // C(bf16) = acc * elu'(aux[m,n])      (dgrad through the previous ELU)
   EPI_BF16 = 5,         // C(bf16) = acc
+  EPI_BIAS_BF16 = 6,    // C(bf16) = acc + bias[n]             (encoder latent into the actor/critic input)
 };
 
 struct GemmArgs {
@@ -178,7 +179,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         const int epi = args.epi;
-        if (epi == EPI_BIAS_ELU_BF16 || epi == EPI_BIAS_F32) {
+        if (epi == EPI_BIAS_ELU_BF16 || epi == EPI_BIAS_F32 || epi == EPI_BIAS_BF16) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __ldg(args.bias + nb + j);
         }
@@ -301,8 +302,8 @@ extern "C" int rl_gemm_bf16(const void* A, const void* B, void* C, const float* 
                             int32_t transposed, int32_t epilogue, int32_t split_k, void* stream) {
   RL_REQUIRE(A && B && C, RL_ERR_BAD_ARG, "rl_gemm_bf16: null operand");
   RL_REQUIRE(M > 0 && N > 0 && K > 0, RL_ERR_BAD_ARG, "rl_gemm_bf16: M=%d N=%d K=%d", M, N, K);
-  RL_REQUIRE(epilogue >= EPI_F32 && epilogue <= EPI_BF16, RL_ERR_BAD_ARG, "rl_gemm_bf16: epilogue=%d", epilogue);
-  RL_REQUIRE(!((epilogue == EPI_BIAS_ELU_BF16 || epilogue == EPI_BIAS_F32) && !bias), RL_ERR_BAD_ARG, "rl_gemm_bf16: bias missing");
+  RL_REQUIRE(epilogue >= EPI_F32 && epilogue <= EPI_BIAS_BF16, RL_ERR_BAD_ARG, "rl_gemm_bf16: epilogue=%d", epilogue);
+  RL_REQUIRE(!((epilogue == EPI_BIAS_ELU_BF16 || epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_BF16) && !bias), RL_ERR_BAD_ARG, "rl_gemm_bf16: bias missing");
   RL_REQUIRE(!(epilogue == EPI_DELU_BF16 && !aux), RL_ERR_BAD_ARG, "rl_gemm_bf16: aux missing");
   RL_REQUIRE(split_k >= 1, RL_ERR_BAD_ARG, "rl_gemm_bf16: split_k=%d", split_k);
   RL_REQUIRE(split_k == 1 || epilogue == EPI_F32_ATOMIC, RL_ERR_BAD_ARG, "rl_gemm_bf16: split-K needs the atomic epilogue");

@@ -1,0 +1,445 @@
+// PPO update support kernels around the tcgen05 GEMMs: minibatch gather + bf16 staging, the fused
+// clipped-surrogate / clipped-value / entropy / KL loss with its analytic gradients, gradient-norm
+// clipping with the KL-adaptive learning rate kept on the device, fused Adam, bf16 shadow weights,
+// and the Normal sampling of ActorCritic.act.
+// Replaces mini_gym_learn/ppo/ppo.py:94-178 (PPO.update), rollout_storage.py:100-139 (the twelve
+// advanced-index gathers per minibatch) and actor_critic.py:137-147 (Normal sample / log_prob).
+// The reference synchronises the host >= 5 times per minibatch (kl_mean compare :118-121, .item()
+// :152-153,170, slot_cache :161-162); here nothing leaves the device until update() returns.
+#include <cuda_bf16.h>
+
+#include "rl_common.cuh"
+
+namespace rl {
+
+constexpr int ACT = 12;      // num_actions
+constexpr int LAT = 18;      // latent / privileged dim
+constexpr int LROW = 40;     // per-row loss inputs: actions 12, mu_old 12, sigma_old 12, logp_old, adv, ret, v_old
+
+// ---- minibatch gather (rollout_storage.py:121-137) + bf16 staging -----------------------------------
+// one warp per minibatch row; every global access is a coalesced run along the row
+__global__ void __launch_bounds__(256)
+ppo_gather_kernel(const float* __restrict__ obs, const float* __restrict__ priv, const float* __restrict__ hist,
+                  const float* __restrict__ actions, const float* __restrict__ values, const float* __restrict__ returns,
+                  const float* __restrict__ logp, const float* __restrict__ adv, const float* __restrict__ mu,
+                  const float* __restrict__ sigma, const int64_t* __restrict__ idx, int B, int obs_dim, int priv_dim,
+                  int hist_dim, __nv_bfloat16* __restrict__ Xp, int ldp, __nv_bfloat16* __restrict__ Xac, int ldac,
+                  __nv_bfloat16* __restrict__ Xh, int ldh, float* __restrict__ Lrow) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const size_t src = (size_t)idx[warp];
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int c = lane; c < ldp; c += 32) Xp[(size_t)warp * ldp + c] = c < priv_dim ? __float2bfloat16(priv[src * priv_dim + c]) : zero;
+  for (int c = lane; c < ldac; c += 32) {
+    if (c < obs_dim) Xac[(size_t)warp * ldac + c] = __float2bfloat16(obs[src * obs_dim + c]);
+    else if (c >= obs_dim + LAT) Xac[(size_t)warp * ldac + c] = zero;   // [obs_dim, obs_dim+18) is the latent slot
+  }
+  if (Xh) for (int c = lane; c < ldh; c += 32) Xh[(size_t)warp * ldh + c] = c < hist_dim ? __float2bfloat16(hist[src * hist_dim + c]) : zero;
+  float* L = Lrow + (size_t)warp * LROW;
+  if (lane < ACT) {
+    L[lane] = actions[src * ACT + lane];
+    L[ACT + lane] = mu[src * ACT + lane];
+    L[2 * ACT + lane] = sigma[src * ACT + lane];
+  }
+  if (lane == 0) { L[36] = logp[src]; L[37] = adv[src]; L[38] = returns[src]; L[39] = values[src]; }
+}
+
+// fp32 [rows, cols] (pitch ld_src) -> bf16 [rows, ld_dst], zero padded; optional column offset into dst
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst, int rows,
+                 int cols, int dst_col0, int pad_to) {
+  const size_t total = (size_t)rows * pad_to;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / pad_to;
+    const int c = (int)(i - r * pad_to);
+    dst[r * ld_dst + dst_col0 + c] = c < cols ? __float2bfloat16(src[r * ld_src + c]) : __float2bfloat16(0.f);
+  }
+}
+
+// ---- fused PPO loss + gradients (ppo.py:110-144, 156-164) --------------------------------------------
+// stats (double): [0] sum surrogate, [1] sum value loss, [2] sum kl, [3] sum adaptation sq. error
+struct LossArgs {
+  const float* mean;      // [B,12]  actor output
+  const float* value;     // [B]     critic output
+  const float* pred;      // [B,18]  adaptation module output (or null: skip the adaptation loss)
+  const __nv_bfloat16* Xac; int ldac; int lat_off;   // latent target = Xac[:, lat_off : lat_off+18]
+  const float* Lrow;      // [B,40]
+  const float* std;       // [12]    learnable std (actor_critic.py:108)
+  int B;
+  float clip, value_coef, entropy_coef;
+  int use_clipped_value;
+  float inv_global_B;     // 1 / (B * world_size): means are taken over the global minibatch
+  __nv_bfloat16* dmean;   // [B,16]
+  __nv_bfloat16* dvalue;  // [B,8]
+  __nv_bfloat16* dpred;   // [B,24]
+  float* dstd;            // [12] gradient slot of std (atomic)
+  double* stats;          // [4]
+};
+
+__global__ void __launch_bounds__(128)
+ppo_loss_kernel(const __grid_constant__ LossArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s_surr = 0, s_val = 0, s_kl = 0, s_ad = 0;
+  float g_std[ACT];
+#pragma unroll
+  for (int d = 0; d < ACT; ++d) g_std[d] = 0.f;
+  if (i < a.B) {
+    const float* L = a.Lrow + (size_t)i * LROW;
+    const float adv = L[37], ret = L[38], v_old = L[39], logp_old = L[36];
+    float logp = 0.f, kl = 0.f;
+    float dmu[ACT], dsg[ACT];
+#pragma unroll
+    for (int d = 0; d < ACT; ++d) {
+      const float mu = a.mean[(size_t)i * ACT + d], sg = a.std[d];
+      const float act = L[d], mu_o = L[ACT + d], sg_o = L[2 * ACT + d];
+      const float diff = act - mu;
+      // Normal.log_prob (actor_critic.py:147)
+      logp += -(diff * diff) / (2.f * sg * sg) - __logf(sg) - 0.9189385332046727f;
+      // ppo.py:112-115
+      kl += __logf(sg / sg_o + 1.e-5f) + (sg_o * sg_o + (mu_o - mu) * (mu_o - mu)) / (2.f * sg * sg) - 0.5f;
+      dmu[d] = diff / (sg * sg);
+      dsg[d] = diff * diff / (sg * sg * sg) - 1.f / sg;
+    }
+    // surrogate (:127-131); torch.max routes the gradient to the larger argument, halves on ties
+    const float ratio = __expf(logp - logp_old);
+    const float lo = 1.f - a.clip, hi = 1.f + a.clip;
+    const float rc = fminf(fmaxf(ratio, lo), hi);
+    const float s1 = -adv * ratio, s2 = -adv * rc;
+    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    float g_ratio;
+    if (s1 > s2) g_ratio = -adv;
+    else if (s1 < s2) g_ratio = -adv * in_range;
+    else g_ratio = 0.5f * (-adv) + 0.5f * (-adv * in_range);
+    s_surr = fmaxf(s1, s2);
+    const float g_logp = g_ratio * ratio * a.inv_global_B;
+    // value loss (:134-142)
+    const float v = a.value[i];
+    float vl, g_v;
+    if (a.use_clipped_value) {
+      const float dv = v - v_old;
+      const float vc = v_old + fminf(fmaxf(dv, -a.clip), a.clip);
+      const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
+      const float inr = (dv >= -a.clip && dv <= a.clip) ? 1.f : 0.f;
+      vl = fmaxf(l1, l2);
+      if (l1 > l2) g_v = 2.f * (v - ret);
+      else if (l1 < l2) g_v = 2.f * (vc - ret) * inr;
+      else g_v = 0.5f * 2.f * (v - ret) + 0.5f * 2.f * (vc - ret) * inr;
+    } else {
+      vl = (ret - v) * (ret - v);
+      g_v = 2.f * (v - ret);
+    }
+    s_val = vl; s_kl = kl;
+    g_v *= a.value_coef * a.inv_global_B;
+    // gradients w.r.t. the network outputs (bf16 operands of the backward GEMMs)
+    __nv_bfloat16* dm = a.dmean + (size_t)i * 16;
+#pragma unroll
+    for (int d = 0; d < ACT; ++d) { dm[d] = __float2bfloat16(g_logp * dmu[d]); g_std[d] = g_logp * dsg[d]; }
+#pragma unroll
+    for (int d = ACT; d < 16; ++d) dm[d] = __float2bfloat16(0.f);
+    __nv_bfloat16* dvp = a.dvalue + (size_t)i * 8;
+    dvp[0] = __float2bfloat16(g_v);
+#pragma unroll
+    for (int d = 1; d < 8; ++d) dvp[d] = __float2bfloat16(0.f);
+    // adaptation regression (:157-164): mse over B x 18 elements
+    if (a.pred) {
+      const __nv_bfloat16* tgt = a.Xac + (size_t)i * a.ldac + a.lat_off;
+      __nv_bfloat16* dp = a.dpred + (size_t)i * 24;
+      const float sc = 2.f * a.inv_global_B / (float)LAT;
+      float se = 0.f;
+#pragma unroll
+      for (int d = 0; d < LAT; ++d) {
+        const float e = a.pred[(size_t)i * LAT + d] - __bfloat162float(tgt[d]);
+        se += e * e;
+        dp[d] = __float2bfloat16(sc * e);
+      }
+#pragma unroll
+      for (int d = LAT; d < 24; ++d) dp[d] = __float2bfloat16(0.f);
+      s_ad = se;
+    }
+  }
+  // block reduction -> one atomic per block
+  __shared__ double sh[4][4];
+  __shared__ float sh_std[4][ACT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s_surr = warp_sum(s_surr); s_val = warp_sum(s_val); s_kl = warp_sum(s_kl); s_ad = warp_sum(s_ad);
+#pragma unroll
+  for (int d = 0; d < ACT; ++d) g_std[d] = warp_sum(g_std[d]);
+  if (lane == 0) {
+    sh[warp][0] = s_surr; sh[warp][1] = s_val; sh[warp][2] = s_kl; sh[warp][3] = s_ad;
+#pragma unroll
+    for (int d = 0; d < ACT; ++d) sh_std[warp][d] = g_std[d];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(a.stats + threadIdx.x, sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + ACT) {
+    const int d = threadIdx.x - 32;
+    float g = sh_std[0][d] + sh_std[1][d] + sh_std[2][d] + sh_std[3][d];
+    // entropy (:144): mean over rows of sum_d (0.5 + 0.5 log 2pi + log std_d)  =>  d/dstd_d = 1/std_d, added once
+    if (blockIdx.x == 0) g += -a.entropy_coef * (1.f / a.std[d]) * (a.inv_global_B * (float)a.B);
+    atomicAdd(a.dstd + d, g);
+  }
+}
+
+// ---- adaptation-module regression (ppo.py:157-164), run AFTER the policy optimiser step so that the
+// target latent comes from the updated encoder, exactly like the reference ---------------------------------
+__global__ void __launch_bounds__(128)
+adapt_loss_kernel(const float* __restrict__ pred, const __nv_bfloat16* __restrict__ Xac, int ldac, int lat_off, int B,
+                  float inv_global_B, __nv_bfloat16* __restrict__ dpred, double* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double se = 0.0;
+  if (i < B) {
+    const __nv_bfloat16* tgt = Xac + (size_t)i * ldac + lat_off;
+    __nv_bfloat16* dp = dpred + (size_t)i * 24;
+    const float sc = 2.f * inv_global_B / (float)LAT;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < LAT; ++d) {
+      const float e = pred[(size_t)i * LAT + d] - __bfloat162float(tgt[d]);
+      acc += e * e;
+      dp[d] = __float2bfloat16(sc * e);
+    }
+#pragma unroll
+    for (int d = LAT; d < 24; ++d) dp[d] = __float2bfloat16(0.f);
+    se = acc;
+  }
+  __shared__ double sh[4];
+  se = warp_sum(se);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = se;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(stats + 3, sh[0] + sh[1] + sh[2] + sh[3]);
+}
+
+// ---- gradient norm + clip coefficient + KL-adaptive learning rate (ppo.py:116-124, 149) ---------------
+// ctrl (float): [0] learning rate (persistent), [1] clip coefficient, [2] kl mean of this minibatch
+struct FinalizeWs { double sumsq; unsigned int ticket; unsigned int pad; };
+
+__global__ void __launch_bounds__(256)
+grad_finalize_kernel(const float* __restrict__ grad, size_t n, const double* __restrict__ stats, float* ctrl,
+                     FinalizeWs* ws, double global_B, float desired_kl, float max_norm, int adaptive) {
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double g = grad[i];
+    s += g * g;
+  }
+  __shared__ double sh[8];
+  __shared__ bool last;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0;
+    for (int w = 0; w < 8; ++w) b += sh[w];
+    atomicAdd(&ws->sumsq, b);
+    __threadfence();
+    last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    const double norm = sqrt(*((volatile double*)&ws->sumsq));
+    const float coef = (float)((double)max_norm / (norm + 1e-6));       // clip_grad_norm_
+    ctrl[1] = coef < 1.f ? coef : 1.f;
+    const float kl = (float)(stats[2] / global_B);
+    ctrl[2] = kl;
+    if (adaptive) {
+      float lr = ctrl[0];
+      if (kl > desired_kl * 2.0f) lr = fmaxf(1e-5f, lr / 1.5f);
+      else if (kl < desired_kl / 2.0f && kl > 0.0f) lr = fminf(1e-2f, lr * 1.5f);
+      ctrl[0] = lr;
+    }
+    ws->sumsq = 0.0;
+    ws->ticket = 0;
+  }
+}
+
+// ---- fused Adam (torch.optim.Adam, eps 1e-8, no weight decay), gradient scaled by the clip coefficient
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+            const float* __restrict__ ctrl, float lr_fixed, int use_ctrl, float beta1, float beta2, float eps,
+            float bc1, float bc2_sqrt, float grad_scale) {
+  const float lr = use_ctrl ? ctrl[0] : lr_fixed;
+  const float coef = (use_ctrl ? ctrl[1] : 1.f) * grad_scale;
+  const float step_size = lr / bc1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+    g[i] = 0.f;      // zero_grad for the next minibatch
+  }
+}
+
+// ---- bf16 shadow weights for the tensor-core operands ------------------------------------------------
+struct ShadowLayer {
+  const float* w;          // fp32 master [out, in]
+  __nv_bfloat16* wb;       // [out, ld_wb]   forward B operand
+  __nv_bfloat16* wbt;      // [in, ld_wbt]   dgrad B operand (transpose)
+  int out, in, ld_wb, ld_wbt;
+};
+constexpr int MAX_SHADOW_LAYERS = 16;
+struct ShadowArgs { ShadowLayer L[MAX_SHADOW_LAYERS]; int n; };
+
+__global__ void __launch_bounds__(256)
+refresh_shadows_kernel(const __grid_constant__ ShadowArgs a) {
+  const ShadowLayer& L = a.L[blockIdx.y];
+  __shared__ float tile[32][33];
+  const int tiles_x = (L.in + 31) / 32, tiles_y = (L.out + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
+    const int r0 = (t / tiles_x) * 32, c0 = (t % tiles_x) * 32;
+    for (int k = ty; k < 32; k += 8) {
+      const int r = r0 + k, c = c0 + tx;
+      const float val = (r < L.out && c < L.in) ? L.w[(size_t)r * L.in + c] : 0.f;
+      tile[k][tx] = val;
+      if (r < L.out && c < L.ld_wb) L.wb[(size_t)r * L.ld_wb + c] = __float2bfloat16(val);
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      const int c = c0 + k, r = r0 + tx;     // transposed write: row = input column
+      if (c < L.in && r < L.ld_wbt) L.wbt[(size_t)c * L.ld_wbt + r] = __float2bfloat16(r < L.out ? tile[tx][k] : 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- ActorCritic.act sampling (actor_critic.py:137-147): a = mu + std * N(0,1), log_prob --------------
+__global__ void __launch_bounds__(128)
+policy_sample_kernel(const float* __restrict__ mean, const float* __restrict__ std, int N, uint64_t seed, uint64_t step,
+                     const float* __restrict__ inj_normal, float* __restrict__ actions, float* __restrict__ logp,
+                     float* __restrict__ mu_out, float* __restrict__ sigma_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float lp = 0.f;
+#pragma unroll
+  for (int b4 = 0; b4 < ACT / 4; ++b4) {
+    float z[4];
+    if (inj_normal) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) z[k] = inj_normal[(size_t)i * ACT + b4 * 4 + k];
+    } else {
+      float u[4];
+      rng4(seed, (uint32_t)i, step, RNG_POLICY, (uint32_t)b4, u);
+      // Box-Muller on two pairs
+      const float r0 = sqrtf(-2.f * __logf(fmaxf(u[0], 5.96e-8f))), r1 = sqrtf(-2.f * __logf(fmaxf(u[2], 5.96e-8f)));
+      float s0, c0, s1, c1;
+      __sincosf(6.283185307179586f * u[1], &s0, &c0);
+      __sincosf(6.283185307179586f * u[3], &s1, &c1);
+      z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int d = b4 * 4 + k;
+      const float mu = mean[(size_t)i * ACT + d], sg = std[d];
+      const float a = mu + sg * z[k];
+      actions[(size_t)i * ACT + d] = a;
+      mu_out[(size_t)i * ACT + d] = mu;
+      sigma_out[(size_t)i * ACT + d] = sg;
+      const float diff = a - mu;
+      lp += -(diff * diff) / (2.f * sg * sg) - __logf(sg) - 0.9189385332046727f;
+    }
+  }
+  logp[i] = lp;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" int rl_ppo_gather(const float* obs, const float* priv, const float* hist, const float* actions,
+                             const float* values, const float* returns, const float* logp, const float* adv,
+                             const float* mu, const float* sigma, const int64_t* idx, int32_t B, int32_t obs_dim,
+                             int32_t priv_dim, int32_t hist_dim, void* Xp, int32_t ldp, void* Xac, int32_t ldac, void* Xh,
+                             int32_t ldh, float* Lrow, void* stream) {
+  RL_REQUIRE(obs && priv && actions && values && returns && logp && adv && mu && sigma && idx && Xp && Xac && Lrow,
+             RL_ERR_BAD_ARG, "rl_ppo_gather: null pointer");
+  RL_REQUIRE(B > 0 && priv_dim <= ldp && obs_dim + LAT <= ldac && (!Xh || (hist && hist_dim <= ldh)), RL_ERR_BAD_ARG,
+             "rl_ppo_gather: bad dimensions");
+  const int blocks = (B * 32 + 255) / 256;
+  ppo_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      obs, priv, hist, actions, values, returns, logp, adv, mu, sigma, idx, B, obs_dim, priv_dim, hist_dim,
+      (__nv_bfloat16*)Xp, ldp, (__nv_bfloat16*)Xac, ldac, (__nv_bfloat16*)Xh, ldh, Lrow);
+  return check_launch("ppo_gather_kernel");
+}
+
+extern "C" int rl_cast_bf16(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols,
+                            int32_t dst_col0, int32_t pad_to, void* stream) {
+  RL_REQUIRE(src && dst && rows > 0 && cols > 0 && pad_to >= cols && dst_col0 + pad_to <= ld_dst, RL_ERR_BAD_ARG,
+             "rl_cast_bf16: bad arguments");
+  size_t total = (size_t)rows * pad_to;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, dst_col0, pad_to);
+  return check_launch("cast_bf16_kernel");
+}
+
+extern "C" int rl_ppo_loss(const float* mean, const float* value, const float* pred, const void* Xac, int32_t ldac,
+                           int32_t lat_off, const float* Lrow, const float* std, int32_t B, float clip, float value_coef,
+                           float entropy_coef, int32_t use_clipped_value, float inv_global_B, void* dmean, void* dvalue,
+                           void* dpred, float* dstd, double* stats, void* stream) {
+  RL_REQUIRE(mean && value && Lrow && std && dmean && dvalue && dstd && stats && Xac, RL_ERR_BAD_ARG, "rl_ppo_loss: null pointer");
+  RL_REQUIRE(B > 0 && (!pred || dpred), RL_ERR_BAD_ARG, "rl_ppo_loss: bad arguments");
+  LossArgs a;
+  a.mean = mean; a.value = value; a.pred = pred; a.Xac = (const __nv_bfloat16*)Xac; a.ldac = ldac; a.lat_off = lat_off;
+  a.Lrow = Lrow; a.std = std; a.B = B; a.clip = clip; a.value_coef = value_coef; a.entropy_coef = entropy_coef;
+  a.use_clipped_value = use_clipped_value; a.inv_global_B = inv_global_B;
+  a.dmean = (__nv_bfloat16*)dmean; a.dvalue = (__nv_bfloat16*)dvalue; a.dpred = (__nv_bfloat16*)dpred;
+  a.dstd = dstd; a.stats = stats;
+  ppo_loss_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("ppo_loss_kernel");
+}
+
+extern "C" int rl_adapt_loss(const float* pred, const void* Xac, int32_t ldac, int32_t lat_off, int32_t B,
+                             float inv_global_B, void* dpred, double* stats, void* stream) {
+  RL_REQUIRE(pred && Xac && dpred && stats && B > 0, RL_ERR_BAD_ARG, "rl_adapt_loss: bad arguments");
+  adapt_loss_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pred, (const __nv_bfloat16*)Xac, ldac, lat_off, B,
+                                                                     inv_global_B, (__nv_bfloat16*)dpred, stats);
+  return check_launch("adapt_loss_kernel");
+}
+
+extern "C" int rl_grad_finalize(const float* grad, int64_t n, const double* stats, float* ctrl, void* workspace,
+                                double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, void* stream) {
+  RL_REQUIRE(grad && stats && ctrl && workspace && n > 0, RL_ERR_BAD_ARG, "rl_grad_finalize: bad arguments");
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  grad_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, (size_t)n, stats, ctrl, (FinalizeWs*)workspace,
+                                                               global_B, desired_kl, max_grad_norm, adaptive);
+  return check_launch("grad_finalize_kernel");
+}
+
+extern "C" int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,
+                       int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  RL_REQUIRE(p && g && m && v && n > 0 && step >= 1 && (!use_ctrl || ctrl), RL_ERR_BAD_ARG, "rl_adam: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, ctrl, lr_fixed, use_ctrl, beta1, beta2, eps, bc1,
+                                                      bc2_sqrt, grad_scale);
+  return check_launch("adam_kernel");
+}
+
+extern "C" int rl_refresh_shadows(const void* const* w, void* const* wb, void* const* wbt, const int32_t* out_dim,
+                                  const int32_t* in_dim, const int32_t* ld_wb, const int32_t* ld_wbt, int32_t n_layers,
+                                  void* stream) {
+  RL_REQUIRE(w && wb && wbt && out_dim && in_dim && ld_wb && ld_wbt && n_layers > 0 && n_layers <= MAX_SHADOW_LAYERS,
+             RL_ERR_BAD_ARG, "rl_refresh_shadows: bad arguments");
+  ShadowArgs a;
+  a.n = n_layers;
+  for (int i = 0; i < n_layers; ++i) {
+    a.L[i].w = (const float*)w[i]; a.L[i].wb = (__nv_bfloat16*)wb[i]; a.L[i].wbt = (__nv_bfloat16*)wbt[i];
+    a.L[i].out = out_dim[i]; a.L[i].in = in_dim[i]; a.L[i].ld_wb = ld_wb[i]; a.L[i].ld_wbt = ld_wbt[i];
+    RL_REQUIRE(ld_wb[i] >= in_dim[i] && ld_wbt[i] >= out_dim[i], RL_ERR_BAD_ARG, "rl_refresh_shadows: pitch too small");
+  }
+  refresh_shadows_kernel<<<dim3(64, n_layers), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("refresh_shadows_kernel");
+}
+
+extern "C" int rl_policy_sample(const float* mean, const float* std, int32_t N, uint64_t seed, uint64_t step,
+                                const float* inj_normal, float* actions, float* logp, float* mu_out, float* sigma_out,
+                                void* stream) {
+  RL_REQUIRE(mean && std && actions && logp && mu_out && sigma_out && N > 0, RL_ERR_BAD_ARG, "rl_policy_sample: bad arguments");
+  policy_sample_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, std, N, seed, step, inj_normal, actions, logp,
+                                                                        mu_out, sigma_out);
+  return check_launch("policy_sample_kernel");
+}

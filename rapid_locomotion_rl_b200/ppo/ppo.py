@@ -1,0 +1,239 @@
+"""PPO on the fused kernels.
+
+Drop-in for mini_gym_learn/ppo/ppo.py:15-178: `PPO_Args`, `PPO(actor_critic, device)`, `init_storage`,
+`act`, `process_env_step`, `compute_returns`, `update() -> (mean_value_loss, mean_surrogate_loss,
+mean_adaptation_module_loss)`.
+
+One minibatch step = gather (1 launch) -> 14 forward GEMMs -> fused loss/gradient kernel -> 25 backward
+GEMMs (dgrad with the ELU derivative in the epilogue, split-K wgrad with the bias gradient from a
+ones-MMA) -> [NCCL all-reduce of the flat gradient when torch.distributed is initialised] -> gradient
+norm / clip / KL-adaptive learning rate on the device -> fused Adam (policy) -> fused Adam (adaptation
+module) -> bf16 shadow refresh.  No host synchronisation happens inside update(); the three returned
+means are read back once at the end (the reference syncs >= 5 times per minibatch).
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .actor_critic import (AC_Args, ActorCritic, EPI_ATOMIC, EPI_BF16, EPI_DELU_BF16)
+from .rollout_storage import RolloutStorage
+
+
+class PPO_Args:
+    """ppo.py:15-30."""
+    value_loss_coef = 1.0
+    use_clipped_value_loss = True
+    clip_param = 0.2
+    entropy_coef = 0.01
+    num_learning_epochs = 5
+    num_mini_batches = 4
+    learning_rate = 1.e-3
+    adaptation_module_learning_rate = 1.e-3
+    num_adaptation_module_substeps = 1
+    schedule = "adaptive"
+    gamma = 0.99
+    lam = 0.95
+    desired_kl = 0.01
+    max_grad_norm = 1.
+
+
+class PPO:
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RlError("PPO needs a CUDA device: the learner has no CPU fallback")
+        self._lib = _lib.lib()
+        self.actor_critic = actor_critic
+        self.storage = None
+        self.transition = RolloutStorage.Transition()
+        self.learning_rate = PPO_Args.learning_rate
+        dev = self.device
+        self._ctrl = torch.tensor([PPO_Args.learning_rate, 1.0, 0.0], device=dev)      # lr, clip coef, kl
+        self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._fin_ws = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._stats_ad = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._step_main = 0
+        self._step_adapt = 0
+        ac = actor_critic
+        self._main_layers = ac.L_enc + [ac.L_cat] + ac.L_act + ac.L_cri
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape,
+                     action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape,
+                                      obs_history_shape, action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    def act(self, obs, privileged_obs, obs_history):
+        """ppo.py:62-74."""
+        ac, t = self.actor_critic, self.transition
+        t.actions = ac.act(obs, privileged_obs).detach()
+        t.values = ac.evaluate(obs, privileged_obs).detach()
+        t.actions_log_prob = ac.get_actions_log_prob(t.actions).detach()
+        t.action_mean = ac._mu
+        t.action_sigma = ac._sigma
+        t.observations = obs
+        t.critic_observations = obs
+        t.privileged_observations = privileged_obs
+        t.observation_histories = obs_history
+        return t.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        """ppo.py:76-88."""
+        t = self.transition
+        t.rewards = rewards.clone()
+        t.dones = dones
+        t.env_bins = infos["env_bins"]
+        if "time_outs" in infos:
+            t.rewards += PPO_Args.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
+        self.storage.add_transitions(t)
+        t.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs, last_critic_privileged_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs, last_critic_privileged_obs).detach()
+        self.storage.compute_returns(last_values, PPO_Args.gamma, PPO_Args.lam)
+
+    # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _split(M, N, bn_threshold, rows):
+        tiles = ((M + 127) // 128) * ((N + (127 if N > 64 else 63)) // (128 if N > 64 else 64))
+        total_kb = (rows + 63) // 64
+        return max(1, min(total_kb, (296 + tiles - 1) // tiles))
+
+    def _wgrad(self, L, dY, dy_off, ld_dy, X, x_off, ld_x, rows):
+        """dW[out,in] += dY^T X (split-K, atomics into the flat gradient) and db from the ones-MMA."""
+        ac = self.actor_critic
+        split = self._split(L.out, L.inp, 64, rows)
+        ac._gemm(ac._p(dY, dy_off), ld_dy, ac._p(X, x_off), ld_x, L.gw.data_ptr(), L.inp, L.out, L.inp, rows,
+                 EPI_ATOMIC, transposed=1, db=L.gb.data_ptr(), split_k=split)
+
+    def _dgrad(self, L, dY, dy_off, ld_dy, dX, dx_off, ld_dx, rows, aux=None, aux_off=0, ld_aux=0, col0=0, ncols=None):
+        """dX = (dY W[:, col0:col0+ncols]) (* elu'(aux)): B operand = the transposed shadow, rows col0.."""
+        ac = self.actor_critic
+        ncols = L.inp if ncols is None else ncols
+        ac._gemm(ac._p(dY, dy_off), ld_dy, ac._p(L.wbt, col0 * L.ld_wbt), L.ld_wbt, ac._p(dX, dx_off), ld_dx, rows, ncols,
+                 L.out, EPI_DELU_BF16 if aux is not None else EPI_BF16,
+                 aux=None if aux is None else ac._p(aux, aux_off), ld_aux=ld_aux)
+
+    def minibatch_step(self, idx, world=1, allreduce=None):
+        """One PPO minibatch on the rows `idx` (int64 device tensor) of the flattened storage."""
+        ac, st, A = self.actor_critic, self.storage, PPO_Args
+        B = int(idx.numel())
+        w = ac.workspace(B, backward=True)
+        P = _lib.ptr
+        stream = _lib.current_stream()
+        ld = lambda k: w[k].shape[1]
+        flat = lambda t: t.flatten(0, 1)
+        _lib.check(self._lib.rl_ppo_gather(
+            P(flat(st.observations)), P(flat(st.privileged_observations)), P(flat(st.observation_histories)),
+            P(flat(st.actions)), P(flat(st.values)), P(flat(st.returns)), P(flat(st.actions_log_prob)),
+            P(flat(st.advantages)), P(flat(st.mu)), P(flat(st.sigma)), P(idx), B, ac.num_obs, ac.num_priv, ac.num_hist,
+            P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
+        # ---- forward ----
+        ac.forward_teacher(B)
+        # ---- loss + output gradients ----
+        self._stats.zero_()
+        inv_gb = 1.0 / (B * world)
+        _lib.check(self._lib.rl_ppo_loss(
+            P(w["mean"]), P(w["value"]), None, P(w["Xac"]), ld("Xac"), ac.num_obs, P(w["Lrow"]), P(ac.std.data), B,
+            A.clip_param, A.value_loss_coef, A.entropy_coef, int(A.use_clipped_value_loss), inv_gb, P(w["dmean"]),
+            P(w["dvalue"]), P(w["dpred"]), P(ac.std_grad), P(self._stats), stream))
+        # ---- backward: actor ----
+        H = AC_Args.actor_hidden_dims[0]
+        a, c, e, d = ac.L_act, ac.L_cri, ac.L_enc, ac.L_ada
+        self._wgrad(a[2], w["dmean"], 0, 16, w["A3"], 0, ld("A3"), B)
+        self._dgrad(a[2], w["dmean"], 0, 16, w["dA3"], 0, ld("dA3"), B, aux=w["A3"], ld_aux=ld("A3"))
+        self._wgrad(a[1], w["dA3"], 0, ld("dA3"), w["A2"], 0, ld("A2"), B)
+        self._dgrad(a[1], w["dA3"], 0, ld("dA3"), w["dA2"], 0, ld("dA2"), B, aux=w["A2"], ld_aux=ld("A2"))
+        self._wgrad(a[0], w["dA2"], 0, ld("dA2"), w["Y1"], 0, ld("Y1"), B)
+        self._dgrad(a[0], w["dA2"], 0, ld("dA2"), w["dY1"], 0, ld("dY1"), B, aux=w["Y1"], ld_aux=ld("Y1"))
+        # ---- backward: critic ----
+        self._wgrad(c[2], w["dvalue"], 0, 8, w["C3"], 0, ld("C3"), B)
+        self._dgrad(c[2], w["dvalue"], 0, 8, w["dC3"], 0, ld("dC3"), B, aux=w["C3"], ld_aux=ld("C3"))
+        self._wgrad(c[1], w["dC3"], 0, ld("dC3"), w["C2"], 0, ld("C2"), B)
+        self._dgrad(c[1], w["dC3"], 0, ld("dC3"), w["dC2"], 0, ld("dC2"), B, aux=w["C2"], ld_aux=ld("C2"))
+        self._wgrad(c[0], w["dC2"], 0, ld("dC2"), w["Y1"], H, ld("Y1"), B)
+        self._dgrad(c[0], w["dC2"], 0, ld("dC2"), w["dY1"], H, ld("dY1"), B, aux=w["Y1"], aux_off=H, ld_aux=ld("Y1"))
+        # ---- shared first layer (actor | critic) and the latent gradient ----
+        self._wgrad(ac.L_cat, w["dY1"], 0, ld("dY1"), w["Xac"], 0, ld("Xac"), B)
+        self._dgrad(ac.L_cat, w["dY1"], 0, ld("dY1"), w["dLat"], 0, ld("dLat"), B, col0=ac.num_obs, ncols=ac.latent_dim)
+        # ---- backward: encoder ----
+        self._wgrad(e[2], w["dLat"], 0, ld("dLat"), w["H2"], 0, ld("H2"), B)
+        self._dgrad(e[2], w["dLat"], 0, ld("dLat"), w["dH2"], 0, ld("dH2"), B, aux=w["H2"], ld_aux=ld("H2"))
+        self._wgrad(e[1], w["dH2"], 0, ld("dH2"), w["H1"], 0, ld("H1"), B)
+        self._dgrad(e[1], w["dH2"], 0, ld("dH2"), w["dH1"], 0, ld("dH1"), B, aux=w["H1"], ld_aux=ld("H1"))
+        self._wgrad(e[0], w["dH1"], 0, ld("dH1"), w["Xp"], 0, ld("Xp"), B)
+        # ---- data-parallel reduction of the policy gradients and loss statistics ----
+        g_main, g_adapt = ac.flat_grad[:ac.n_main], ac.flat_grad[ac.n_main:]
+        if allreduce is not None:
+            allreduce(g_main)
+            allreduce(self._stats)
+        if getattr(self, "debug_keep_grad", False):      # parity tests read the raw gradient / statistics
+            self.debug_grad = ac.flat_grad.clone()
+        # ---- clip + KL-adaptive lr + Adam, all on the device ----
+        adaptive = int(A.desired_kl is not None and A.schedule == "adaptive")
+        _lib.check(self._lib.rl_grad_finalize(P(g_main), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws),
+                                              float(B * world), float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive,
+                                              stream))
+        self._step_main += 1
+        _lib.check(self._lib.rl_adam(P(ac.flat), P(ac.flat_grad), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
+                                     0.9, 0.999, 1e-8, self._step_main, 1.0, stream))
+        ac.refresh_shadows(self._main_layers)
+        # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
+        for _ in range(A.num_adaptation_module_substeps):
+            ac.forward_encoder(B)
+            ac.forward_adaptation(B)
+            stats_ad = self._stats_ad
+            stats_ad.zero_()
+            _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(w["Xac"]), ld("Xac"), ac.num_obs, B, inv_gb, P(w["dpred"]),
+                                               P(stats_ad), stream))
+            self._wgrad(d[2], w["dpred"], 0, 24, w["D2"], 0, ld("D2"), B)
+            self._dgrad(d[2], w["dpred"], 0, 24, w["dD2"], 0, ld("dD2"), B, aux=w["D2"], ld_aux=ld("D2"))
+            self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
+            self._dgrad(d[1], w["dD2"], 0, ld("dD2"), w["dD1"], 0, ld("dD1"), B, aux=w["D1"], ld_aux=ld("D1"))
+            self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
+            if allreduce is not None:
+                allreduce(g_adapt)
+                allreduce(stats_ad)
+            if getattr(self, "debug_keep_grad", False):
+                self.debug_grad[ac.n_main:] = g_adapt
+            self._step_adapt += 1
+            n_ad = ac.n_total - ac.n_main
+            off = ac.n_main * 4
+            _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, ac.flat_grad.data_ptr() + off, ac.flat_m.data_ptr() + off,
+                                         ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
+                                         0.9, 0.999, 1e-8, self._step_adapt, 1.0, stream))
+            ac.refresh_shadows(ac.L_ada)
+            self._stats[3] += stats_ad[3]
+        if getattr(self, "debug_keep_grad", False):
+            self.debug_stats = self._stats.clone()
+        self._loss_acc += self._stats
+
+    def update(self):
+        """ppo.py:94-178."""
+        import torch.distributed as dist
+        A, st = PPO_Args, self.storage
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+        batch = st.num_envs * st.num_transitions_per_env
+        mb = batch // A.num_mini_batches
+        indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)
+        self._loss_acc.zero_()
+        for _ in range(A.num_learning_epochs):
+            for i in range(A.num_mini_batches):
+                self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
+        n_upd = A.num_learning_epochs * A.num_mini_batches
+        acc = (self._loss_acc / (mb * world)).tolist()          # the only device->host read of the update
+        self.learning_rate = float(self._ctrl[0])
+        st.clear()
+        lat = self.actor_critic.latent_dim
+        return acc[1] / n_upd, acc[0] / n_upd, acc[3] / lat / n_upd / A.num_adaptation_module_substeps

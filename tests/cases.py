@@ -68,3 +68,50 @@ def build_case(case, num_envs):
         hs = synthetic_heightfield(probe.tot_rows, probe.tot_cols, seed=3)
     terrain = C.TerrainInfo(cfg.terrain, hs)
     return cfg, robot_for_asset(cfg.asset.file), terrain
+
+
+# ---- learner fixtures: portable, seed-generated inputs (numpy), so goldens only store reference OUTPUTS ----
+LEARNER_SHAPES = {
+    "std": (12,),
+    "env_factor_encoder.0": (256, 18), "env_factor_encoder.2": (128, 256), "env_factor_encoder.4": (18, 128),
+    "adaptation_module.0": (256, 630), "adaptation_module.2": (32, 256), "adaptation_module.4": (18, 32),
+    "actor_body.0": (512, 60), "actor_body.2": (256, 512), "actor_body.4": (128, 256), "actor_body.6": (12, 128),
+    "critic_body.0": (512, 60), "critic_body.2": (256, 512), "critic_body.4": (128, 256), "critic_body.6": (1, 128),
+}
+
+
+def learner_weights(seed=7):
+    """state_dict-shaped float32 numpy weights, nn.Linear-like uniform(-1/sqrt(in), 1/sqrt(in))."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for name, shape in LEARNER_SHAPES.items():
+        if name == "std":
+            sd["std"] = np.ones(12, np.float32)
+            continue
+        bound = 1.0 / np.sqrt(shape[1])
+        sd[name + ".weight"] = rng.uniform(-bound, bound, shape).astype(np.float32)
+        sd[name + ".bias"] = rng.uniform(-bound, bound, shape[0]).astype(np.float32)
+    for k in list(sd):
+        if k.startswith("env_factor_encoder."):
+            sd["encoder." + k[len("env_factor_encoder."):]] = sd[k]
+    return sd
+
+
+def learner_rollout_inputs(n_envs, n_steps, seed=9):
+    """Per-step env outputs fed to PPO.act / process_env_step."""
+    rng = np.random.RandomState(seed)
+    steps = []
+    for _ in range(n_steps):
+        steps.append(dict(obs=rng.randn(n_envs, 42).astype(np.float32), priv=rng.uniform(-1, 1, (n_envs, 18)).astype(np.float32),
+                          hist=rng.randn(n_envs, 630).astype(np.float32), rew=(rng.randn(n_envs) * 0.05).astype(np.float32),
+                          done=rng.rand(n_envs) < 0.05))
+    last = dict(obs=rng.randn(n_envs, 42).astype(np.float32), priv=rng.uniform(-1, 1, (n_envs, 18)).astype(np.float32))
+    perm = rng.permutation(n_envs * n_steps).astype(np.int64)
+    return steps, last, perm
+
+
+def tensor_digest(a):
+    """Compact exact fingerprint of an array: float64 sum, abs-sum and 64 strided samples."""
+    a = np.asarray(a, dtype=np.float32).reshape(-1)
+    idx = np.linspace(0, a.size - 1, min(64, a.size)).astype(np.int64)
+    return np.concatenate([[a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()], a[idx].astype(np.float64)])

@@ -295,6 +295,40 @@ def gen_learner_case():
     out["gae/rewards"] = rewards; out["gae/values"] = values; out["gae/dones"] = dones
     out["gae/last_values"] = last_values
     out["gae/returns"] = st.returns.numpy().copy(); out["gae/advantages"] = st.advantages.numpy().copy()
+    # ---- PPO.update (ppo.py:94-178) on a small synthetic rollout --------------------------------------
+    # inputs (weights, env outputs, permutation) come from tests/cases.py seeds; only the tensors the
+    # reference PRODUCES are stored
+    from cases import learner_weights, learner_rollout_inputs, tensor_digest
+    from mini_gym_learn.ppo import ActorCritic
+    from mini_gym_learn.ppo.ppo import PPO
+    torch.manual_seed(1)
+    N2, T2 = 64, 8
+    ac = ActorCritic(42, 18, 630, 12)
+    ac.load_state_dict({k: torch.from_numpy(v) for k, v in learner_weights().items()})
+    ppo = PPO(ac, device="cpu")
+    ppo.init_storage(N2, T2, [42], [18], [630], [12])
+    steps, last, perm = learner_rollout_inputs(N2, T2)
+    T = torch.from_numpy
+    for sd in steps:
+        ppo.act(T(sd["obs"]), T(sd["priv"]), T(sd["hist"]))
+        ppo.process_env_step(T(sd["rew"]), T(sd["done"]), {"env_bins": torch.zeros(N2)})
+    ppo.compute_returns(T(last["obs"]), T(last["priv"]))
+    st = ppo.storage
+    flat = lambda x: x.flatten(0, 1).numpy().copy()
+    for name, tns in (("actions", st.actions), ("values", st.values), ("returns", st.returns), ("old_logp", st.actions_log_prob),
+                      ("advantages", st.advantages), ("old_mu", st.mu), ("old_sigma", st.sigma)):
+        out["ppo/storage/" + name] = flat(tns)
+    real_randperm = torch.randperm
+    torch.randperm = lambda n, **kw: T(perm).clone()
+    try:
+        res = ppo.update()
+    finally:
+        torch.randperm = real_randperm
+    out["ppo/result"] = np.array(res, dtype=np.float64)
+    out["ppo/final_lr"] = np.float64(ppo.learning_rate)
+    for k, v in ac.state_dict().items():
+        if not k.startswith("encoder."):
+            out["ppo/final_digest/" + k] = tensor_digest(v.detach().numpy())
     path = os.path.join(HERE, "learner.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
