@@ -249,6 +249,15 @@ def run_ours(args):
             del reps2
             torch.cuda.empty_cache()
 
+    ppo = None
+    if not args.quick:
+        try:
+            del reps
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        ppo = ppo_bench(args.ppo_envs, 24, device, world, pk)
+
     out = {
         "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -268,6 +277,7 @@ def run_ours(args):
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
                      "kernel": "env_step_kernel<true>", "algorithmic_bytes_per_launch": args.envs * bpe},
         "also": also,
+        "ppo": ppo,
     }
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(sample_envs=4000, steps=10, warmup=2)
@@ -276,6 +286,56 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ppo_bench(n_envs, T, device, world, pk, iters=3):
+    """BASELINE metric 2: PPO samples/s = N*T / (t_compute_returns + t_update), 5 epochs x 4 minibatches,
+    ActorCritic 512-256-128 (BASELINE.json configs[0] shape), synthetic rollout produced by the policy itself."""
+    import torch
+    import torch.distributed as dist
+    from rapid_locomotion_rl_b200.ppo import PPO, ActorCritic
+    torch.manual_seed(0)
+    ac = ActorCritic(42, 18, 630, 12, device=device)
+    ppo = PPO(ac, device=device)
+    ppo.init_storage(n_envs, T, [42], [18], [630], [12])
+    obs = torch.randn(T + 1, n_envs, 42, device=device)
+    priv = torch.rand(T + 1, n_envs, 18, device=device) * 2 - 1
+    hist = torch.randn(n_envs, 630, device=device)
+    bins = torch.zeros(n_envs, device=device)
+
+    def rollout():
+        for t in range(T):
+            ppo.act(obs[t], priv[t], hist)
+            ppo.process_env_step(torch.randn(n_envs, device=device) * 0.05, torch.rand(n_envs, device=device) < 0.01,
+                                 {"env_bins": bins})
+    times, t_gae = [], []
+    for it in range(iters + 1):
+        rollout()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        ppo.compute_returns(obs[T], priv[T])
+        e1.record()
+        res = ppo.update()
+        e2.record()
+        torch.cuda.synchronize()
+        if it > 0:       # first iteration is the warm-up
+            times.append(e0.elapsed_time(e2)); t_gae.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    samples = n_envs * T * world
+    flops = 18.02e6 * n_envs * T       # SURVEY 8(d): 3.603 MFLOP per sample-visit x 5 epochs (per GPU)
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"metric": "ppo_samples_per_s", "value": samples / (ms * 1e-3), "unit": "samples/s", "ms_per_iteration": ms,
+            "ms_gae": sum(t_gae) / len(t_gae), "envs_per_gpu": n_envs, "steps_per_env": T, "epochs": 5, "minibatches": 4,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": tf / (pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]), "traffic": None},
+            "losses": list(res), "dtype": "bf16 operands, fp32 accumulate / master weights"}
 
 
 def cpu_env_arm(envs, steps, warmup, threads=None):
@@ -353,7 +413,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=32768, help="envs per GPU")
-    ap.add_argument("--quick", action="store_true", help="skip the extra sizes")
+    ap.add_argument("--quick", action="store_true", help="skip the extra sizes and the PPO metric")
+    ap.add_argument("--ppo-envs", type=int, default=4000, help="envs per GPU for the PPO samples/s metric")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
