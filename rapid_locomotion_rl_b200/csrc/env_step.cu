@@ -25,112 +25,9 @@
 // op-by-op eager reference; integer results (cell indices, resets, counters) are exact.
 #include <stdlib.h>
 
-#include "rl_common.cuh"
+#include "env_common.cuh"
 
 namespace rl {
-
-constexpr int ND = RL_NUM_DOF;
-
-struct StepArgs {
-  RlEnvCfg cfg;
-  RlEnvBuffers b;
-  uint64_t seed;
-  uint64_t step;
-};
-
-// ---------------------------------------------------------------------------------------
-// cooperative tile copies
-// ---------------------------------------------------------------------------------------
-// (fallback path for ragged tail tiles / unaligned tensors; full tiles use cp.async.bulk)
-template <int TILE>
-__device__ inline void stage_in(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
-  if ((((uintptr_t)src) & 15) == 0) {
-    const int n4 = n_floats >> 2;
-    // batches of 4 independent 128-bit loads per thread before the first store
-    for (int i = threadIdx.x; i < n4; i += 4 * TILE) {
-      float4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (i + k * TILE < n4) v[k] = ldg_stream4(src + 4 * (i + k * TILE));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (i + k * TILE < n4) reinterpret_cast<float4*>(dst)[i + k * TILE] = v[k];
-    }
-#pragma unroll 1
-    for (int i = (n4 << 2) + threadIdx.x; i < n_floats; i += TILE) dst[i] = __ldg(src + i);
-  } else {
-#pragma unroll 1
-    for (int i = threadIdx.x; i < n_floats; i += TILE) dst[i] = __ldg(src + i);
-  }
-}
-
-template <int TILE>
-__device__ inline void stage_out(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
-  if ((((uintptr_t)dst) & 15) == 0) {
-    const int n4 = n_floats >> 2;
-#pragma unroll 2
-    for (int i = threadIdx.x; i < n4; i += TILE)
-      stg_stream4(dst + 4 * i, reinterpret_cast<const float4*>(src)[i]);
-#pragma unroll 1
-    for (int i = (n4 << 2) + threadIdx.x; i < n_floats; i += TILE) dst[i] = src[i];
-  } else {
-#pragma unroll 1
-    for (int i = threadIdx.x; i < n_floats; i += TILE) dst[i] = src[i];
-  }
-}
-
-// rows of `width` floats in smem (dense) -> global rows with pitch `pitch`
-template <int TILE>
-__device__ inline void stage_out_rows(float* __restrict__ dst, const float* __restrict__ src, int rows,
-                                      int width, int pitch) {
-  const int total = rows * width;
-#pragma unroll 1
-  for (int i = threadIdx.x; i < total; i += TILE) {
-    const int r = i / width, c = i - r * width;
-    dst[(size_t)r * pitch + c] = src[i];
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// small math, written in the reference's operation order
-// ---------------------------------------------------------------------------------------
-struct V3 { float x, y, z; };
-
-// isaacgym.torch_utils.quat_rotate_inverse (xyzw): a - b + c with
-// a = v*(2w^2-1), b = cross(qv,v)*w*2, c = qv*dot(qv,v)*2
-__device__ inline V3 quat_rotate_inverse(float qx, float qy, float qz, float qw, V3 v) {
-  const float s = 2.0f * (qw * qw) - 1.0f;
-  V3 a = {v.x * s, v.y * s, v.z * s};
-  V3 cr = {qy * v.z - qz * v.y, qz * v.x - qx * v.z, qx * v.y - qy * v.x};
-  V3 b = {cr.x * qw * 2.0f, cr.y * qw * 2.0f, cr.z * qw * 2.0f};
-  const float d = (qx * v.x + qy * v.y) + qz * v.z;
-  V3 c = {qx * d * 2.0f, qy * d * 2.0f, qz * d * 2.0f};
-  return {a.x - b.x + c.x, a.y - b.y + c.y, a.z - b.z + c.z};
-}
-
-// isaacgym.torch_utils.quat_apply: v + w*t + cross(qv,t), t = 2*cross(qv,v)
-__device__ inline V3 quat_apply(float qx, float qy, float qz, float qw, V3 v) {
-  V3 t = {(qy * v.z - qz * v.y) * 2.0f, (qz * v.x - qx * v.z) * 2.0f, (qx * v.y - qy * v.x) * 2.0f};
-  V3 c = {qy * t.z - qz * t.y, qz * t.x - qx * t.z, qx * t.y - qy * t.x};
-  return {v.x + qw * t.x + c.x, v.y + qw * t.y + c.y, v.z + qw * t.z + c.z};
-}
-
-__device__ inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-__device__ inline float sq(float x) { return x * x; }
-
-// torch.remainder for floats (sign follows the divisor) - math_utils.py:20 `angles %= 2*pi`
-__device__ inline float py_mod(float a, float b) {
-  float m = fmodf(a, b);
-  if (m != 0.0f && ((b < 0.0f) != (m < 0.0f))) m += b;
-  return m;
-}
-
-// ---------------------------------------------------------------------------------------
-// the fused kernel
-// ---------------------------------------------------------------------------------------
-// 16-bit uniform lane k (0..7) of a Philox block -> (u - 0.5) in (-0.5, 0.5), symmetric, never +-0.5
-__device__ inline float centered_u16(const uint32_t (&r)[4], int k) {
-  const uint32_t x = (r[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-  return __fmaf_rn((float)x, 1.0f / 65536.0f, 0.5f / 65536.0f - 0.5f);
-}
 
 // Observation noise (:392): obs += (2*u - 1) * scale.  Test mode reads u from the injected
 // tensor and keeps the reference's arithmetic exactly; product mode draws 8 sixteen-bit uniforms
@@ -175,7 +72,6 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   const int tid = threadIdx.x;
   const int e = tile0 + tid;
   const bool valid = tid < n_valid;
-  const size_t Ns = (size_t)N;
 
   const int P = cfg.measure_heights ? cfg.num_height_points : 0;
   const int W = STD_OBS ? 42 : cfg.num_obs - P;  // width of the non-height part of the observation
@@ -846,6 +742,19 @@ template <bool FUSE>
 static int launch_step(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed, uint64_t step, void* stream) {
   int rc = validate(cfg, b, !FUSE);
   if (rc != RL_OK) return rc;
+  StepArgs qargs;
+  qargs.cfg = *cfg; qargs.b = *b; qargs.seed = seed; qargs.step = step;
+  {
+    // standard observation layout -> one-warp-per-leg kernel (env_step_quad.cu); RL_ENV_MODE=thread forces
+    // the one-thread-per-env kernel below (also the path of every other observe_* combination)
+    static int force_thread = -1;
+    if (force_thread < 0) { const char* m = getenv("RL_ENV_MODE"); force_thread = (m && m[0] == 't') ? 1 : 0; }
+    const RlEnvCfg& c = *cfg;
+    const int core = c.num_obs - (c.measure_heights ? c.num_height_points : 0);
+    const bool std_obs = c.observe_command && !c.observe_vel && !c.observe_only_ang_vel && !c.observe_only_lin_vel &&
+                         !c.observe_yaw && core == 42;
+    if (std_obs && !force_thread) return launch_step_quad(qargs, FUSE, (cudaStream_t)stream);
+  }
   const int tile = env_tile();
   const size_t smem = step_smem_bytes(*cfg, tile);
   RL_REQUIRE(smem <= 227 * 1024, RL_ERR_UNSUPPORTED, "env step: tile needs %zu B of shared memory", smem);
