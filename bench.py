@@ -164,6 +164,12 @@ def run_ours(args):
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     pk, pk_kind = peaks()
     bpe = BYTES_PER_ENV_STEP["mini_cheetah"]
+    if args.only_ppo:      # development aid: just the learner metric
+        if rank == 0:
+            print(json.dumps(ppo_bench(args.ppo_envs, 24, device, world, pk)))
+        else:
+            ppo_bench(args.ppo_envs, 24, device, world, pk)
+        return
 
     def measure(envs, steps, warmup, sample_clocks):
         n_rep = max(2, math.ceil(2.0 * L2_BYTES / (envs * bpe)))
@@ -414,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=32768, help="envs per GPU")
     ap.add_argument("--quick", action="store_true", help="skip the extra sizes and the PPO metric")
+    ap.add_argument("--only-ppo", action="store_true", help="development aid: print only the PPO metric object")
     ap.add_argument("--ppo-envs", type=int, default=4000, help="envs per GPU for the PPO samples/s metric")
     args = ap.parse_args()
     if args.impl == "reference":

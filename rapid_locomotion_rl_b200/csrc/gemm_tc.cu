@@ -22,7 +22,6 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 
 enum Epilogue : int {
@@ -37,6 +36,9 @@ enum Epilogue : int {
 
 struct GemmArgs {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmC;         // bf16 output tile store (valid when tma_store)
+  CUtensorMap tmAux;       // bf16 aux tile load (valid when epi == EPI_DELU_BF16 and tma_aux)
+  int tma_store, tma_aux;
   void* C;
   const float* bias;
   const __nv_bfloat16* aux;
@@ -47,30 +49,40 @@ struct GemmArgs {
   int epi;
 };
 
-template <int BN, bool TN>
+template <int BN, bool TN, int STAGES>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;          // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ONES_BYTES = TN ? 16 * 128 : 0; // 16 k-rows of 128 B filled with bf16 1.0
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BOXES = (BN + 63) / 64;         // 64-column bf16 boxes per output tile
+  static constexpr int AUX_BYTES = TN ? 0 : BOXES * 128 * 128;   // aux tile for the dgrad epilogue (NT only)
+  static constexpr int F32_PITCH = BN + 4;             // fp32 staging pitch (floats) for the coalesced atomics
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static_assert(BOXES * 128 * 128 <= RING_BYTES, "bf16 staging tile must fit in the stage ring");
+  static_assert(!TN || BM * F32_PITCH * 4 <= RING_BYTES, "fp32 staging tile must fit in the stage ring");
+  static constexpr int TOTAL = RING_BYTES + AUX_BYTES + ONES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : (__expf(x) - 1.f); }
 
-template <int BN, bool TN>
+// STAGES = 2 for short reductions (<= 2 k-blocks per CTA: 48-64 KB of smem, 3 CTAs per SM so that the
+// epilogue of one tile overlaps the loads / MMAs of its neighbours), 4 otherwise.
+template <int BN, bool TN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
-  using S = Smem<BN, TN>;
+  using S = Smem<BN, TN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint8_t* ones = smem + STAGES * S::STAGE_BYTES;
+  uint8_t* aux_tile = smem + S::RING_BYTES;
+  uint8_t* ones = aux_tile + S::AUX_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + S::ONES_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* aux_bar = acc_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -85,6 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(acc_bar, 1);
+    mbar_init(aux_bar, 1);
     mbar_fence_init();
     tma_prefetch_desc(&args.tmA);
     tma_prefetch_desc(&args.tmB);
@@ -103,6 +116,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      if (!TN && args.tma_aux) {          // aux tile of the dgrad epilogue: lands while the main loop runs
+        mbar_expect_tx(aux_bar, S::BOXES * 128 * 128);
+#pragma unroll
+        for (int bx = 0; bx < S::BOXES; ++bx) tma_load_2d(aux_tile + bx * 16384, &args.tmAux, n0 + 64 * bx, m0, aux_bar);
+      }
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES, it = i / STAGES;
         if (it > 0) mbar_wait(&empty_bar[s], (it - 1) & 1);
@@ -157,13 +175,25 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
     }
   } else {
     // ===== epilogue warps (TMEM lane group = warp % 4) =====
+    // Thread = one accumulator row.  Global traffic is made coalesced by staging the tile in shared
+    // memory (the stage ring is free once the accumulators are complete): bf16 tiles leave through TMA
+    // tensor stores from the 128 B-swizzled layout, fp32 split-K tiles through row-contiguous atomics.
     const int g = warp & 3;
-    const int r = m0 + 32 * g + lane;
+    const int lr = 32 * g + lane;               // row within the tile
+    const int r = m0 + lr;
+    const int et = threadIdx.x - 64;            // 0..127 within the epilogue group
     if (num_kb > 0) {
       mbar_wait(acc_bar, 0);
       tc_fence_after();
     }
+    const int epi = args.epi;
+    const bool bf16_out = !(epi == EPI_F32 || epi == EPI_BIAS_F32 || epi == EPI_F32_ATOMIC);
+    const bool staged_bf16 = bf16_out && args.tma_store;
+    const bool staged_f32 = TN && epi == EPI_F32_ATOMIC;
+    const bool aux_smem = !TN && epi == EPI_DELU_BF16 && args.tma_aux;
+    if (aux_smem) mbar_wait(aux_bar, 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * g) << 16);
+    float* stage_f32 = reinterpret_cast<float*>(tiles);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
@@ -173,21 +203,42 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
       const int nb = n0 + c * 32;
-      if (r < args.M && nb < args.N) {
-        const int nvalid = min(32, args.N - nb);
-        float f[32];
+      const int nvalid = max(0, min(32, args.N - nb));
+      float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const int epi = args.epi;
-        if (epi == EPI_BIAS_ELU_BF16 || epi == EPI_BIAS_F32 || epi == EPI_BIAS_BF16) {
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (epi == EPI_BIAS_ELU_BF16 || epi == EPI_BIAS_F32 || epi == EPI_BIAS_BF16) {
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(args.bias + nb) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias + nb + j));
+            f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+          }
+        } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __ldg(args.bias + nb + j);
         }
-        if (epi == EPI_BIAS_ELU_BF16) {
+      }
+      if (epi == EPI_BIAS_ELU_BF16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = elu_f(f[j]);
-        }
-        if (epi == EPI_DELU_BF16) {
+        for (int j = 0; j < 32; ++j) f[j] = elu_f(f[j]);
+      }
+      if (epi == EPI_DELU_BF16) {
+        if (aux_smem) {
+          // 16 B chunks of this row from the swizzled aux tile: box (c>>1), chunk ((c&1)*4 + t) ^ (row & 7)
+          const uint8_t* row = aux_tile + (c >> 1) * 16384 + lr * 128;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(row + ((((c & 1) * 4 + t) ^ (lr & 7)) << 4));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 y = __bfloat1622float2(h[q]);
+              f[t * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
+              f[t * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+            }
+          }
+        } else if (r < args.M) {
           const __nv_bfloat16* ax = args.aux + (size_t)r * args.ld_aux + nb;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -197,6 +248,24 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
             }
           }
         }
+      }
+      if (staged_bf16) {
+        uint8_t* row = tiles + (c >> 1) * 16384 + lr * 128;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(f[t * 8], f[t * 8 + 1]), p1 = __floats2bfloat162_rn(f[t * 8 + 2], f[t * 8 + 3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(f[t * 8 + 4], f[t * 8 + 5]), p3 = __floats2bfloat162_rn(f[t * 8 + 6], f[t * 8 + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(row + ((((c & 1) * 4 + t) ^ (lr & 7)) << 4)) = pk;
+        }
+      } else if (staged_f32) {
+        float* row = stage_f32 + lr * S::F32_PITCH + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else if (r < args.M && nvalid > 0) {
+        // direct path: fp32 outputs of the narrow output layers, unaligned bf16 destinations
         if (epi == EPI_F32 || epi == EPI_BIAS_F32) {
           float* dst = reinterpret_cast<float*>(args.C) + (size_t)r * args.ldc + nb;
           if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -212,20 +281,33 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
           for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(dst + j, f[j]);
         } else {
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.C) + (size_t)r * args.ldc + nb;
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]), p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
-          } else {
+          for (int j = 0; j < 32; ++j) if (j < nvalid) dst[j] = __float2bfloat16(f[j]);
+        }
+      }
+    }
+    if (staged_bf16) {
+      fence_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nvalid) dst[j] = __float2bfloat16(f[j]);
-          }
+        for (int bx = 0; bx < S::BOXES; ++bx)
+          if (n0 + 64 * bx < args.N) tma_store_2d(&args.tmC, tiles + bx * 16384, n0 + 64 * bx, m0);
+        bulk_commit();
+        bulk_wait_read0();
+      }
+    } else if (staged_f32) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // warp g drains rows g, g+4, ...: each atomic instruction covers 32 consecutive columns of one row
+      float* Cf = reinterpret_cast<float*>(args.C);
+#pragma unroll 1
+      for (int rr = g; rr < BM; rr += 4) {
+        const int row = m0 + rr;
+        if (row >= args.M) break;
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          const int n = n0 + cc * 32 + lane;
+          if (n < args.N) atomicAdd(Cf + (size_t)row * args.ldc + n, stage_f32[rr * S::F32_PITCH + cc * 32 + lane]);
         }
       }
     }
@@ -276,17 +358,26 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   return RL_OK;
 }
 
-template <int BN, bool TN>
-static int launch_gemm(const GemmArgs& a, dim3 grid, cudaStream_t st) {
-  using S = Smem<BN, TN>;
+template <int BN, bool TN, int STAGES>
+static int launch_gemm_st(const GemmArgs& a, dim3 grid, cudaStream_t st) {
+  using S = Smem<BN, TN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_bf16_kernel<BN, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t err = cudaFuncSetAttribute(gemm_bf16_kernel<BN, TN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(err));
     configured = true;
   }
-  gemm_bf16_kernel<BN, TN><<<grid, GEMM_THREADS, S::TOTAL, st>>>(a);
+  gemm_bf16_kernel<BN, TN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(a);
   return check_launch("gemm_bf16_kernel");
+}
+
+template <int BN, bool TN>
+static int launch_gemm(const GemmArgs& a, dim3 grid, cudaStream_t st) {
+  if constexpr (TN) {
+    return launch_gemm_st<BN, TN, 4>(a, grid, st);    // the fp32 staging tile needs the 4-stage ring
+  } else {
+    return a.kblocks_per_split <= 2 ? launch_gemm_st<BN, TN, 2>(a, grid, st) : launch_gemm_st<BN, TN, 4>(a, grid, st);
+  }
 }
 
 }  // namespace tc
@@ -323,6 +414,16 @@ extern "C" int rl_gemm_bf16(const void* A, const void* B, void* C, const float* 
   } else {
     if ((rc = make_tmap_bf16(&a.tmA, A, K, M, lda, 64)) != RL_OK) return rc;
     if ((rc = make_tmap_bf16(&a.tmB, B, K, N, ldb, 64)) != RL_OK) return rc;
+  }
+  a.tma_store = 0; a.tma_aux = 0;
+  const bool bf16_out = !(epilogue == EPI_F32 || epilogue == EPI_BIAS_F32 || epilogue == EPI_F32_ATOMIC);
+  if (!transposed && bf16_out && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 8) == 0) {
+    if ((rc = make_tmap_bf16(&a.tmC, C, M, N, ldc, BM)) != RL_OK) return rc;
+    a.tma_store = 1;
+  }
+  if (!transposed && epilogue == EPI_DELU_BF16 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && (ld_aux % 8) == 0) {
+    if ((rc = make_tmap_bf16(&a.tmAux, aux, M, N, ld_aux, BM)) != RL_OK) return rc;
+    a.tma_aux = 1;
   }
   dim3 grid((M + BM - 1) / BM, (N + bn - 1) / bn, splits);
   cudaStream_t st = (cudaStream_t)stream;

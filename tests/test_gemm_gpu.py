@@ -59,6 +59,29 @@ def test_nt_bias_elu_bf16_and_bias_f32():
     torch.testing.assert_close(C2, ref, rtol=2e-3, atol=2e-2)
 
 
+def test_nt_misaligned_bias_and_offset_views():
+    """Bias pointers are 4 B-aligned views of the flat parameter buffer; outputs may be column slices."""
+    M, N, K = 700, 256, 128
+    A, B = rnd(M, K), rnd(N, K, scale=0.2)
+    bias = torch.randn(N + 3, device="cuda")[3:]          # 12 B offset
+    big = torch.zeros(M, 1024, device="cuda", dtype=torch.bfloat16)
+    C = big[:, 512:512 + N]                                # column slice, pitch 1024
+    gemm(A, B, C, bias=bias, M=M, N=N, K=K, epilogue=EPI_BIAS_ELU_BF16)
+    ref = torch.nn.functional.elu(A.float() @ B.float().t() + bias)
+    torch.testing.assert_close(C.float(), ref, rtol=1e-2, atol=2e-2)
+    assert (big[:, :512] == 0).all() and (big[:, 512 + N:] == 0).all()
+    # unaligned bf16 destination (direct epilogue path): 42-column offset, N = 18
+    dst = torch.zeros(M, 64, device="cuda", dtype=torch.bfloat16)
+    B18 = rnd(18, K, scale=0.2)
+    from rapid_locomotion_rl_b200 import _lib
+    lib = _lib.lib()
+    _lib.check(lib.rl_gemm_bf16(A.data_ptr(), B18.data_ptr(), dst.data_ptr() + 42 * 2, bias.data_ptr(), None, None, M, 18, K,
+                                K, K, 64, 0, 0, 6, 1, _lib.current_stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dst[:, 42:60].float(), A.float() @ B18.float().t() + bias[:18], rtol=1e-2, atol=2e-2)
+    assert (dst[:, :42] == 0).all() and (dst[:, 60:] == 0).all()
+
+
 def test_nt_delu_epilogue():
     """dgrad through an ELU: dX = (dY W) * elu'(x) with elu' taken from the stored ELU output."""
     M, N, K = 2000, 256, 128      # dX [M,N] = dY [M,K] * Wt [N,K]^T
