@@ -372,6 +372,9 @@ int rl_gae(const float* rewards, const float* values, const uint8_t* dones,
  * db (transposed form only, may be NULL): db[m] += sum_k A[k,m], the bias gradient, from an extra
  * ones-vector MMA.  All pitches in elements; bf16 operands need 16 B aligned bases and pitches that
  * are multiples of 8. */
+/* one-time per-device set-up of the GEMM kernels (shared-memory limits, tensor-map encoder); required
+ * before GEMM launches are captured into a CUDA graph, harmless otherwise */
+int rl_gemm_init(void);
 int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const void* aux, float* db,
                  int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ld_aux,
                  int32_t transposed, int32_t epilogue, int32_t split_k, void* stream);
@@ -415,7 +418,11 @@ int rl_grad_finalize(const float* grad, int64_t n, const double* stats, float* c
 /* torch.optim.Adam step (ppo.py:44-46,150,168) fused with gradient scaling and zero_grad.
  * use_ctrl: lr = ctrl[0], grad scaled by ctrl[1]; else lr_fixed.  grad_scale: extra factor. */
 int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,
-            int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+            int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+            int32_t* step_dev, void* stream);
+/* step_dev (may be NULL): device int32[2] {optimiser step count, CTA ticket}.  When given, the bias
+ * corrections use step_dev[0] + 1 and the kernel advances the counter itself, so the launch can be captured
+ * in a CUDA graph and replayed; `step` is then ignored. */
 /* bf16 shadow copies of the fp32 master weights: wb [out, ld_wb] and its transpose wbt [in, ld_wbt]
  * (host arrays of n_layers device pointers / dims) */
 int rl_refresh_shadows(const void* const* w, void* const* wb, void* const* wbt, const int32_t* out_dim,

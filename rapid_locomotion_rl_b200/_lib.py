@@ -104,7 +104,8 @@ SIGNATURES = {
     "rl_adapt_loss": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
     "rl_grad_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P]),
     "rl_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
-                          C.c_float, _P]),
+                          C.c_float, _P, _P]),
+    "rl_gemm_init": (C.c_int, []),
     "rl_refresh_shadows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "rl_policy_sample": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

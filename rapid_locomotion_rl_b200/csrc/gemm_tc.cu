@@ -15,6 +15,8 @@
 //   warps 2-5 epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
 // Operands stay in the TMA-written swizzled layout; the UMMA shared-memory descriptors address them
 // in place (K-major for NT, MN-major for TN), so no transposed copies of activations are ever made.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace rl {
@@ -359,12 +361,20 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
 }
 
 template <int BN, bool TN, int STAGES>
+static int configure_one() {
+  cudaError_t err = cudaFuncSetAttribute(gemm_bf16_kernel<BN, TN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Smem<BN, TN, STAGES>::TOTAL);
+  RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(err));
+  return RL_OK;
+}
+
+template <int BN, bool TN, int STAGES>
 static int launch_gemm_st(const GemmArgs& a, dim3 grid, cudaStream_t st) {
   using S = Smem<BN, TN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_bf16_kernel<BN, TN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(err));
+    int rc = configure_one<BN, TN, STAGES>();
+    if (rc != RL_OK) return rc;
     configured = true;
   }
   gemm_bf16_kernel<BN, TN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(a);
@@ -376,7 +386,9 @@ static int launch_gemm(const GemmArgs& a, dim3 grid, cudaStream_t st) {
   if constexpr (TN) {
     return launch_gemm_st<BN, TN, 4>(a, grid, st);    // the fp32 staging tile needs the 4-stage ring
   } else {
-    return a.kblocks_per_split <= 2 ? launch_gemm_st<BN, TN, 2>(a, grid, st) : launch_gemm_st<BN, TN, 4>(a, grid, st);
+    static int max_kb2 = -1;     // k-blocks up to which the 2-stage / multi-CTA-per-SM variant is used
+    if (max_kb2 < 0) { const char* e = getenv("RL_GEMM_STAGE2_MAXKB"); max_kb2 = e ? atoi(e) : 16; }
+    return a.kblocks_per_split <= max_kb2 ? launch_gemm_st<BN, TN, 2>(a, grid, st) : launch_gemm_st<BN, TN, 4>(a, grid, st);
   }
 }
 
@@ -385,6 +397,18 @@ static int launch_gemm(const GemmArgs& a, dim3 grid, cudaStream_t st) {
 
 using namespace rl;
 using namespace rl::tc;
+
+// Sets the dynamic shared-memory limits of every GEMM instantiation and resolves the tensor-map encoder.
+// Call once per device before capturing GEMM launches into a CUDA graph.
+extern "C" int rl_gemm_init(void) {
+  int rc;
+  if ((rc = configure_one<32, false, 2>()) || (rc = configure_one<32, false, 4>()) || (rc = configure_one<64, false, 2>()) ||
+      (rc = configure_one<64, false, 4>()) || (rc = configure_one<128, false, 2>()) || (rc = configure_one<128, false, 4>()) ||
+      (rc = configure_one<64, true, 4>()) || (rc = configure_one<128, true, 4>()))
+    return rc;
+  RL_REQUIRE(encode_fn() != nullptr, RL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  return RL_OK;
+}
 
 // C-ABI.  transposed = 0: C[M,N] = A[M,K] B[N,K]^T (lda, ldb = K pitches);
 //         transposed = 1: C[M,N] = A[K,M]^T B[K,N] (lda = pitch of the [K,M] matrix, ldb of [K,N]).

@@ -252,10 +252,17 @@ grad_finalize_kernel(const float* __restrict__ grad, size_t n, const double* __r
 }
 
 // ---- fused Adam (torch.optim.Adam, eps 1e-8, no weight decay), gradient scaled by the clip coefficient
+// step_dev (optional): device-resident optimiser step counter {count, ticket}; the bias corrections are then
+// derived on the device and the last CTA advances the counter, so the launch can live in a CUDA graph.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
             const float* __restrict__ ctrl, float lr_fixed, int use_ctrl, float beta1, float beta2, float eps,
-            float bc1, float bc2_sqrt, float grad_scale) {
+            float bc1, float bc2_sqrt, float grad_scale, int* step_dev) {
+  if (step_dev) {
+    const float t = (float)(step_dev[0] + 1);
+    bc1 = 1.f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  }
   const float lr = use_ctrl ? ctrl[0] : lr_fixed;
   const float coef = (use_ctrl ? ctrl[1] : 1.f) * grad_scale;
   const float step_size = lr / bc1;
@@ -267,6 +274,13 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] -= step_size * (mi / denom);
     g[i] = 0.f;      // zero_grad for the next minibatch
+  }
+  if (step_dev) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int done = atomicAdd(step_dev + 1, 1);
+      if (done == (int)gridDim.x - 1) { step_dev[1] = 0; atomicAdd(step_dev, 1); }
+    }
   }
 }
 
@@ -408,14 +422,15 @@ extern "C" int rl_grad_finalize(const float* grad, int64_t n, const double* stat
 }
 
 extern "C" int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,
-                       int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
-  RL_REQUIRE(p && g && m && v && n > 0 && step >= 1 && (!use_ctrl || ctrl), RL_ERR_BAD_ARG, "rl_adam: bad arguments");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+                       int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                       int32_t* step_dev, void* stream) {
+  RL_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || step_dev) && (!use_ctrl || ctrl), RL_ERR_BAD_ARG, "rl_adam: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)(step > 0 ? step : 1));
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)(step > 0 ? step : 1)));
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, ctrl, lr_fixed, use_ctrl, beta1, beta2, eps, bc1,
-                                                      bc2_sqrt, grad_scale);
+                                                      bc2_sqrt, grad_scale, step_dev);
   return check_launch("adam_kernel");
 }
 

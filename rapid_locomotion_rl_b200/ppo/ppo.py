@@ -56,8 +56,12 @@ class PPO:
         self._fin_ws = torch.zeros(2, dtype=torch.float64, device=dev)
         self._loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self._stats_ad = torch.zeros(4, dtype=torch.float64, device=dev)
-        self._step_main = 0
-        self._step_adapt = 0
+        self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
+        self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
+        self._graph_B = 0
+        self._idx_buf = None
+        self.use_cuda_graph = True
+        _lib.check(self._lib.rl_gemm_init())
         ac = actor_critic
         self._main_layers = ac.L_enc + [ac.L_cat] + ac.L_act + ac.L_cri
 
@@ -184,9 +188,8 @@ class PPO:
         _lib.check(self._lib.rl_grad_finalize(P(g_main), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws),
                                               float(B * world), float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive,
                                               stream))
-        self._step_main += 1
         _lib.check(self._lib.rl_adam(P(ac.flat), P(ac.flat_grad), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
-                                     0.9, 0.999, 1e-8, self._step_main, 1.0, stream))
+                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
         ac.refresh_shadows(self._main_layers)
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
         for _ in range(A.num_adaptation_module_substeps):
@@ -206,12 +209,11 @@ class PPO:
                 allreduce(stats_ad)
             if getattr(self, "debug_keep_grad", False):
                 self.debug_grad[ac.n_main:] = g_adapt
-            self._step_adapt += 1
             n_ad = ac.n_total - ac.n_main
             off = ac.n_main * 4
             _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, ac.flat_grad.data_ptr() + off, ac.flat_m.data_ptr() + off,
                                          ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
-                                         0.9, 0.999, 1e-8, self._step_adapt, 1.0, stream))
+                                         0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, stream))
             ac.refresh_shadows(ac.L_ada)
             self._stats[3] += stats_ad[3]
         if getattr(self, "debug_keep_grad", False):
@@ -228,9 +230,30 @@ class PPO:
         mb = batch // A.num_mini_batches
         indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)
         self._loss_acc.zero_()
+        # Single GPU: the ~70 launches of a minibatch step are captured ONCE in a CUDA graph that reads its
+        # row indices from a fixed buffer; each of the 20 steps is then one index copy + one graph replay.
+        use_graph = self.use_cuda_graph and world == 1 and not getattr(self, "debug_keep_grad", False)
+        if use_graph and (self._graph is None or self._graph_B != mb):
+            self.actor_critic.workspace(mb, backward=True)        # allocate outside the capture
+            self._idx_buf = torch.zeros(mb, dtype=torch.long, device=self.device)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            snap = [t.clone() for t in (self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
+                                        self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc)]
+            with torch.cuda.graph(g):
+                self.minibatch_step(self._idx_buf, 1, None)
+            # capture does not execute, but keep the state bit-identical in any case
+            for t, s0 in zip((self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
+                              self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc), snap):
+                t.copy_(s0)
+            self._graph, self._graph_B = g, mb
         for _ in range(A.num_learning_epochs):
             for i in range(A.num_mini_batches):
-                self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
+                if use_graph:
+                    self._idx_buf.copy_(indices[i * mb:(i + 1) * mb])
+                    self._graph.replay()
+                else:
+                    self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
         n_upd = A.num_learning_epochs * A.num_mini_batches
         acc = (self._loss_acc / (mb * world)).tolist()          # the only device->host read of the update
         self.learning_rate = float(self._ctrl[0])
