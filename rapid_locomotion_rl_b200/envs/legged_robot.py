@@ -483,10 +483,8 @@ class LeggedRobot:
     def _gac_allreduce(self):
         """Multi-GPU hook: sum the int32 incidence counters over ranks so every rank applies the
         identical saturating update."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.curriculum.hit_count)
-            dist.all_reduce(self.curriculum.own_flag)
+        from ..sharding import all_reduce_sum_
+        all_reduce_sum_(self.curriculum.hit_count, self.curriculum.own_flag)
 
     # ---- reward plugin surface: names resolve like the reference (:1079-1093); the built-in
     # terms are evaluated inside the fused kernel, these methods return the last per-term value ----

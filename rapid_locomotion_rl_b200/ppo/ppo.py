@@ -222,10 +222,10 @@ class PPO:
 
     def update(self):
         """ppo.py:94-178."""
-        import torch.distributed as dist
+        from ..sharding import all_reduce_sum_, world_size
         A, st = PPO_Args, self.storage
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+        world = world_size()
+        allreduce = all_reduce_sum_ if world > 1 else None
         batch = st.num_envs * st.num_transitions_per_env
         mb = batch // A.num_mini_batches
         indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)

@@ -83,15 +83,14 @@ class RolloutStorage:
         """rollout_storage.py:76-90 - reverse-time GAE scan + unbiased-std normalisation, on device.
         With torch.distributed initialised the (sum, sumsq, count) statistics are all-reduced between
         the two phases, so the normalisation spans the env shards of every rank."""
-        import torch.distributed as dist
+        from ..sharding import all_reduce_sum_
         T, N = self.num_transitions_per_env, self.num_envs
         last_values = last_values.to(self.device, torch.float).contiguous()
         P, st = _lib.ptr, _lib.current_stream()
         _lib.check(self._lib.rl_gae_scan(P(self.rewards), P(self.values), P(self.dones), P(last_values),
                                          P(self.returns), P(self.advantages), T, N, float(gamma), float(lam),
                                          P(self._gae_ws), P(self._gae_stats), st))
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self._gae_stats)
+        all_reduce_sum_(self._gae_stats)
         _lib.check(self._lib.rl_gae_normalize(P(self.advantages), T, N, P(self._gae_stats), st))
 
     def mini_batch_generator(self, num_mini_batches, num_epochs=8):
