@@ -379,6 +379,111 @@ int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const
                  int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ld_aux,
                  int32_t transposed, int32_t epilogue, int32_t split_k, void* stream);
 
+/* ---- Fused MLP chains on the tensor cores ----------------------------------------------------
+ * The learner's networks (actor_critic.py:38-100: encoder 18-256-128-18, actor / critic 60-512-256-128-{12,1},
+ * adaptation module 630-256-32-18) are chains of Linear(+ELU) layers.  rl_gemm_bf16 runs one layer per
+ * launch and round-trips every activation through HBM; a CHAIN runs a whole forward (or the dgrad half of
+ * the backward) of one or more networks for a 128-row tile inside one persistent CTA:
+ *   - activations live in shared memory as 16 KB "boxes" ([128 rows x 64 bf16 columns], the 128 B-swizzled
+ *     K-major layout TMA writes and tcgen05.mma reads), weights stream from L2 through a ring of 16 KB
+ *     stages, accumulators live in the 512 tensor-memory columns;
+ *   - three warp roles execute three host-built op lists in order, synchronised only by mbarriers:
+ *       LOAD ops (1 thread): one TMA box each (input rows, weight blocks, saved activations for ELU');
+ *       MMA ops  (1 thread): up to four tcgen05.mma K16 steps of [128 x n] += A box * B box^T;
+ *       EPI ops  (4 warps): tcgen05.ld of <= 64 accumulator columns -> bias / ELU / ELU' -> bf16 box for
+ *                           the next layer (and a TMA store of the box for the backward / wgrad) or fp32 rows.
+ *   The schedule (which layer's k-block meets which box when) is data: the op lists.  They are built and
+ *   checked (deadlock freedom, buffer hazards, numerics on an emulator) on the host:
+ *   rapid_locomotion_rl_b200/ppo/chain.py.
+ * A wait is encoded in 16 bits: bits 0-7 barrier id (0xFF = none), bit 8 = parity to wait for in the
+ * CTA's first tile, bit 9 = 1 if that parity flips with every further tile of the persistent loop. */
+#define RL_CHAIN_MAX_TENSORS 24
+#define RL_CHAIN_MAX_BARRIERS 64
+#define RL_CHAIN_MAX_UNITS 14                    /* 16 KB shared-memory units (boxes + ring stages) */
+#define RL_CHAIN_MAX_OUTPUTS 4
+#define RL_CHAIN_NONE 255
+
+typedef struct RlChainTensor {      /* row-major bf16 [rows, cols], `ld` elements between rows */
+  void* base;
+  int64_t rows;
+  int32_t cols, ld;
+  int32_t box_rows;                 /* TMA box = [box_rows, 64 columns]; out-of-range elements read as 0 */
+  int32_t reserved;
+} RlChainTensor;
+
+typedef struct RlChainLoadOp {
+  uint16_t wait;                    /* destination unit free */
+  uint8_t full_bar;                 /* completes (with the byte count) when the box has landed */
+  uint8_t tensor;
+  uint32_t smem_off;                /* destination, multiple of 1024 */
+  int32_t col0, row0;               /* box origin (elements); row0 is relative to the tile when tile_rows */
+  uint32_t expect_bytes;            /* box bytes (box_rows * 128) */
+  uint8_t tile_rows;
+  uint8_t pad0, pad1, pad2;
+  uint32_t pad3, pad4;
+} RlChainLoadOp;
+
+typedef struct RlChainMmaOp {
+  uint32_t a_off, b_off;            /* A: [128 x 64] box, B: [n x 64] box (both K-major, 128 B swizzle) */
+  uint16_t n;                       /* 16..256, multiple of 16 */
+  uint16_t tmem_col;
+  uint8_t k_steps;                  /* 1..4 K16 steps of the 64-wide k-block */
+  uint8_t accumulate;               /* 0: the first step overwrites the accumulator */
+  uint16_t wait0, wait1, wait2;
+  uint8_t commit0, commit1, commit2;   /* mbarriers that tcgen05.commit arrives on after these MMAs */
+  uint8_t pad0;
+  uint32_t pad1, pad2;
+} RlChainMmaOp;
+
+enum RlChainEpiMode {
+  RL_CHAIN_EPI_BIAS_ELU = 0,        /* box = bf16(elu(acc + bias)) */
+  RL_CHAIN_EPI_BIAS = 1,            /* box = bf16(acc + bias) */
+  RL_CHAIN_EPI_BIAS_F32 = 2,        /* out[row, 0:ncols] = acc + bias (fp32 rows in global memory) */
+  RL_CHAIN_EPI_DELU = 3,            /* box = bf16(acc * elu'(aux)), aux = saved ELU output box */
+  RL_CHAIN_EPI_PLAIN = 4            /* box = bf16(acc) */
+};
+
+typedef struct RlChainEpiOp {
+  uint16_t wait_acc, wait_dst, wait_aux;
+  uint8_t arrive_acc_free;          /* after the accumulator columns are in registers (count 4: one per warp) */
+  uint8_t arrive_dst_ready;         /* after the box is written (count 4) */
+  uint8_t release_aux;              /* after every thread has read the aux box (count 1) */
+  uint8_t mode;
+  uint8_t ncols;                    /* accumulator columns handled: 1..64 */
+  uint8_t dst_col0;                 /* first box column written (0 except when merging into a loaded box) */
+  uint16_t tmem_col;
+  uint8_t store_tensor;             /* TMA store of the whole destination box after writing, or NONE */
+  int8_t store_wait_pending;        /* >= 0: cp.async.bulk.wait_group.read <n> before writing (box reuse) */
+  uint8_t release_after_store;      /* barrier to arrive on once the store has read the box, or NONE */
+  uint8_t out_id;                   /* RL_CHAIN_EPI_BIAS_F32: index into outputs[] */
+  uint16_t out_ld;
+  uint32_t bias_off;                /* float offset into `params` of this op's first column bias */
+  uint32_t dst_off, aux_off;
+  int32_t store_col0;
+  uint32_t pad0, pad1, pad2;
+} RlChainEpiOp;
+
+typedef struct RlChainDesc {
+  RlChainTensor tensors[RL_CHAIN_MAX_TENSORS];
+  int32_t n_tensors;
+  int32_t n_units;                  /* 16 KB shared-memory units used (boxes + stages) */
+  int32_t n_barriers;
+  int32_t n_loads, n_mmas, n_epis;
+  uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
+  const RlChainLoadOp* loads_host;  /* HOST arrays; copied to the device by rl_chain_create */
+  const RlChainMmaOp* mmas_host;
+  const RlChainEpiOp* epis_host;
+  const float* params;              /* DEVICE: flat fp32 parameter buffer the bias offsets index */
+  float* outputs[RL_CHAIN_MAX_OUTPUTS];   /* DEVICE fp32 outputs */
+} RlChainDesc;
+
+/* Compiles a chain: encodes the tensor maps, uploads the op lists.  `*handle` is owned by the library
+ * until rl_chain_destroy.  The tensors' base pointers are baked in (workspace buffers must stay put). */
+int rl_chain_create(const RlChainDesc* desc_host, void** handle);
+/* Runs the chain over rows [0, rows) (tiles of 128; rows may be any value up to the tensors' extent). */
+int rl_chain_run(void* handle, int32_t rows, void* stream);
+int rl_chain_destroy(void* handle);
+
 /* ---- PPO update support (mini_gym_learn/ppo/ppo.py:94-178) ---------------------------------- */
 
 /* rollout_storage.py:121-137: the twelve per-minibatch advanced-index gathers, fused with the bf16

@@ -14,7 +14,8 @@ _HEADER = os.path.join(_build.INCLUDE, "rl_b200.h")
 
 _SCALARS = {
     "int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "uint8_t": C.c_uint8,
-    "float": C.c_float, "double": C.c_double, "int": C.c_int,
+    "float": C.c_float, "double": C.c_double, "int": C.c_int, "uint16_t": C.c_uint16, "int16_t": C.c_int16,
+    "int8_t": C.c_int8,
 }
 
 
@@ -52,17 +53,15 @@ def _parse_header(path):
                 is_ptr = base_ptr or d.startswith("*")
                 d = d.lstrip("* ")
                 am = re.match(r"(\w+)\[(\w+)\]$", d)
-                if is_ptr:
-                    ctype = C.c_void_p
-                    name = d
-                elif am:
+                elem = C.c_void_p if is_ptr else (structs[base] if base in structs else _SCALARS[base])
+                if am:
                     name = am.group(1)
                     dim = am.group(2)
                     n = int(dim) if dim.isdigit() else defines[dim]
-                    ctype = _SCALARS[base] * n
+                    ctype = elem * n
                 else:
                     name = d
-                    ctype = _SCALARS[base]
+                    ctype = elem
                 fields.append((name, ctype))
         structs[m.group(3)] = type(m.group(3), (C.Structure,), {"_fields_": fields})
     return defines, enums, structs
@@ -75,6 +74,11 @@ RlResetCfg = STRUCTS["RlResetCfg"]
 RlResetBuffers = STRUCTS["RlResetBuffers"]
 RlGacCfg = STRUCTS["RlGacCfg"]
 RlGacBuffers = STRUCTS["RlGacBuffers"]
+RlChainTensor = STRUCTS["RlChainTensor"]
+RlChainLoadOp = STRUCTS["RlChainLoadOp"]
+RlChainMmaOp = STRUCTS["RlChainMmaOp"]
+RlChainEpiOp = STRUCTS["RlChainEpiOp"]
+RlChainDesc = STRUCTS["RlChainDesc"]
 
 RL_OK = DEFINES["RL_OK"]
 REWARD_TERM_IDS = {k[len("RL_REW_"):].lower(): v for k, v in ENUMS.items() if k.startswith("RL_REW_") and k != "RL_REW_COUNT"}
@@ -106,6 +110,9 @@ SIGNATURES = {
     "rl_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
                           C.c_float, _P, _P]),
     "rl_gemm_init": (C.c_int, []),
+    "rl_chain_create": (C.c_int, [_P, _P]),
+    "rl_chain_run": (C.c_int, [_P, C.c_int32, _P]),
+    "rl_chain_destroy": (C.c_int, [_P]),
     "rl_refresh_shadows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "rl_policy_sample": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

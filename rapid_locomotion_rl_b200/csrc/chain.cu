@@ -1,0 +1,415 @@
+// Fused MLP chains on the 5th-generation tensor cores: a whole forward (or dgrad) pass of the learner's
+// networks (mini_gym_learn/ppo/actor_critic.py:38-100; the autograd backward behind ppo.py:146-168) for
+// a 128-row tile inside ONE persistent CTA.  The reference runs each nn.Linear / nn.ELU as its own cuBLAS
+// + elementwise launch with every activation going through HBM; rl_gemm_bf16 (gemm_tc.cu) fuses the
+// epilogue but still launches per layer.  Here activations stay in shared memory between layers, weights
+// stream from L2 through a TMA ring and accumulators stay in tensor memory.
+//
+// Execution model (see include/rl_b200.h "Fused MLP chains"): three warp roles interpret three host-built
+// op lists, in order, once per tile of the persistent loop; every dependency is an mbarrier:
+//   warp 0 lane 0     LOAD ops: mbarrier wait (unit free) -> expect_tx -> cp.async.bulk.tensor.2d
+//   warp 1 lane 0     MMA ops : waits (stage full / box ready / accumulator free) -> <= 4 tcgen05.mma
+//                               (M128 x n x K16, kind::f16, fp32 in TMEM) -> tcgen05.commit on <= 3 barriers
+//   warps 2-5         EPI ops : wait (accumulator full) -> tcgen05.ld -> bias / ELU / ELU' -> swizzled bf16
+//                               box in shared memory (the next layer's A operand) -> TMA store of the box
+//                               (saved activation / gradient for wgrad) or fp32 output rows
+// Shared memory = n_units x 16 KB (activation boxes and ring stages, all [rows x 64 bf16] tiles in the
+// 128 B-swizzled K-major layout shared by TMA and the UMMA descriptors) + 64 mbarriers.
+// The host side (ppo/chain.py) builds the op lists and proves them on an emulator (deadlock freedom,
+// buffer hazards, parity bookkeeping, numerics) before anything reaches the GPU.
+#include <stdlib.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace rl {
+namespace tc {
+
+constexpr int CHAIN_THREADS = 192;
+constexpr int UNIT_BYTES = 16384;
+
+struct ChainParams {
+  CUtensorMap tmaps[RL_CHAIN_MAX_TENSORS];
+  const RlChainLoadOp* loads;
+  const RlChainMmaOp* mmas;
+  const RlChainEpiOp* epis;
+  const float* params;
+  float* outputs[RL_CHAIN_MAX_OUTPUTS];
+  int n_loads, n_mmas, n_epis;
+  int n_units, n_barriers;
+  int num_tiles, rows;
+  uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
+};
+
+// mbarrier wait with a watchdog: a schedule bug must surface as a launch error, never as a hung GPU
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void chain_wait(uint64_t* bars, uint32_t spec, int it) {
+  const uint32_t id = spec & 0xFFu;
+  if (id == RL_CHAIN_NONE) return;
+  const uint32_t parity = ((spec >> 8) ^ ((spec >> 9) & (uint32_t)it)) & 1u;
+  uint32_t spins = 0;
+  while (!mbar_try(&bars[id], parity)) {
+    if (++spins > (1u << 24)) {
+      printf("mlp_chain_kernel: wait on barrier %u (parity %u, tile iteration %d) timed out, block %d thread %d\n", id, parity, it,
+             (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : (__expf(x) - 1.f); }
+
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_read_dyn(int n) {
+  switch (n) {
+    case 0: bulk_wait_read_n<0>(); break;
+    case 1: bulk_wait_read_n<1>(); break;
+    case 2: bulk_wait_read_n<2>(); break;
+    case 3: bulk_wait_read_n<3>(); break;
+    case 4: bulk_wait_read_n<4>(); break;
+    case 5: bulk_wait_read_n<5>(); break;
+    case 6: bulk_wait_read_n<6>(); break;
+    default: bulk_wait_read_n<7>(); break;
+  }
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// byte offset of the 16 B chunk holding columns [8c, 8c+8) of row r inside a 128 B-swizzled [rows x 64] box
+__device__ __forceinline__ uint32_t sw_chunk(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+mlp_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_units * UNIT_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + RL_CHAIN_MAX_BARRIERS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < p.n_barriers; ++b) mbar_init(&bars[b], p.barrier_count[b]);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ===================================== LOAD role =====================================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int m0 = tile * 128;
+        for (int i = 0; i < p.n_loads; ++i) {
+          const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p.loads + i));
+          const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p.loads + i) + 1);
+          const uint32_t wait = w0.x & 0xFFFFu, full_bar = (w0.x >> 16) & 0xFFu, tensor = w0.x >> 24;
+          const uint32_t smem_off = w0.y;
+          const int col0 = (int)w0.z, row0 = (int)w0.w;
+          const uint32_t expect = w1.x;
+          const bool tile_rows = (w1.y & 0xFFu) != 0;
+          chain_wait(bars, wait, it);
+          mbar_expect_tx(&bars[full_bar], expect);
+          tma_load_2d(smem + smem_off, &p.tmaps[tensor], col0, row0 + (tile_rows ? m0 : 0), &bars[full_bar]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA role ======================================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int i = 0; i < p.n_mmas; ++i) {
+          const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p.mmas + i));
+          const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p.mmas + i) + 1);
+          const uint32_t a_off = w0.x, b_off = w0.y;
+          const uint32_t n = w0.z & 0xFFFFu, tmem_col = w0.z >> 16;
+          const uint32_t k_steps = w0.w & 0xFFu, accumulate = (w0.w >> 8) & 0xFFu, wait0 = w0.w >> 16;
+          const uint32_t wait1 = w1.x & 0xFFFFu, wait2 = w1.x >> 16;
+          const uint32_t c0 = w1.y & 0xFFu, c1 = (w1.y >> 8) & 0xFFu, c2 = (w1.y >> 16) & 0xFFu;
+          chain_wait(bars, wait0, it);
+          chain_wait(bars, wait1, it);
+          chain_wait(bars, wait2, it);
+          tc_fence_after();
+          const uint32_t idesc = instr_desc_bf16(128, (int)n, false, false);
+          const uint32_t a_addr = smem_base + a_off, b_addr = smem_base + b_off;
+          for (uint32_t kk = 0; kk < k_steps; ++kk) {
+            const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+            const uint64_t db = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
+            mma_bf16_ss(tmem_base + tmem_col, da, db, idesc, (accumulate | kk) != 0);
+          }
+          if (c0 != RL_CHAIN_NONE) mma_commit(&bars[c0]);
+          if (c1 != RL_CHAIN_NONE) mma_commit(&bars[c1]);
+          if (c2 != RL_CHAIN_NONE) mma_commit(&bars[c2]);
+        }
+      }
+    }
+  } else {
+    // ===================================== EPILOGUE role =================================
+    const int g = warp & 3;                      // TMEM lane quarter this warp may read
+    const int lr = 32 * g + lane;                // row within the tile
+    const int et = threadIdx.x - 64;             // 0..127
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * g) << 16);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = tile * 128;
+      const int r = m0 + lr;
+#pragma unroll 1
+      for (int i = 0; i < p.n_epis; ++i) {
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p.epis + i));
+        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p.epis + i) + 1);
+        const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(p.epis + i) + 2);
+        const uint32_t wait_acc = w0.x & 0xFFFFu, wait_dst = w0.x >> 16, wait_aux = w0.y & 0xFFFFu;
+        const uint32_t arrive_acc_free = (w0.y >> 16) & 0xFFu, arrive_dst_ready = w0.y >> 24;
+        const uint32_t release_aux = w0.z & 0xFFu, mode = (w0.z >> 8) & 0xFFu;
+        const int ncols = (int)((w0.z >> 16) & 0xFFu), dst_col0 = (int)(w0.z >> 24);
+        const uint32_t tmem_col = w0.w & 0xFFFFu, store_tensor = (w0.w >> 16) & 0xFFu;
+        const int store_wait_pending = (int)(int8_t)(w0.w >> 24);
+        const uint32_t release_after_store = w1.x & 0xFFu, out_id = (w1.x >> 8) & 0xFFu, out_ld = w1.x >> 16;
+        const uint32_t bias_off = w1.y, dst_off = w1.z, aux_off = w1.w;
+        const int store_col0 = (int)w2.x;
+
+        // ---- accumulator columns -> registers ----
+        chain_wait(bars, wait_acc, it);
+        tc_fence_after();
+        float f[64];
+        {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + tmem_col, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (ncols > 32) {
+            tmem_ld32(lane_addr + tmem_col + 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[32 + j] = 0.f;
+          }
+        }
+        if (arrive_acc_free != RL_CHAIN_NONE) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[arrive_acc_free]);
+        }
+
+        // ---- elementwise ----
+        if (mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32) {
+          const float* bias = p.params + bias_off;
+          if (ncols == 64 && (bias_off & 3u) == 0) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
+              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) if (j < ncols) f[j] += __ldg(bias + j);
+          }
+          if (mode == RL_CHAIN_EPI_BIAS_ELU) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) f[j] = elu1(f[j]);
+          }
+        } else if (mode == RL_CHAIN_EPI_DELU) {
+          chain_wait(bars, wait_aux, it);
+          const uint8_t* aux = smem + aux_off;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(aux + sw_chunk(lr, c));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 y = __bfloat1622float2(h[q]);
+              f[c * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
+              f[c * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+            }
+          }
+        }
+
+        if (mode == RL_CHAIN_EPI_BIAS_F32) {
+          // ---- fp32 output rows (network outputs: 12 / 1 / 18 columns) ----
+          if (r < p.rows) {
+            float* dst = p.outputs[out_id] + (size_t)r * out_ld;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) if (j < ncols) dst[j] = f[j];
+          }
+          continue;
+        }
+
+        // ---- bf16 box for the next layer ----
+        if (store_wait_pending >= 0) {          // a TMA store issued earlier may still be reading this box
+          if (et == 0) bulk_wait_read_dyn(store_wait_pending);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        chain_wait(bars, wait_dst, it);
+        uint8_t* box = smem + dst_off;
+        if (dst_col0 == 0 && ncols == 64) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[c * 8], f[c * 8 + 1]), p1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]), p3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(box + sw_chunk(lr, c)) = pk;
+          }
+        } else {
+          // partial box: `ncols` columns starting at dst_col0 (latent merged next to the observations,
+          // or a narrow gradient); columns outside the range keep their content
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (j < ncols) {
+              const int col = dst_col0 + j;
+              *reinterpret_cast<__nv_bfloat16*>(box + sw_chunk(lr, col >> 3) + (col & 7) * 2) = __float2bfloat16(f[j]);
+            }
+          }
+        }
+        fence_async_smem();                      // generic-proxy writes -> visible to tcgen05.mma / TMA
+        if (arrive_dst_ready != RL_CHAIN_NONE) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[arrive_dst_ready]);
+        }
+        if (store_tensor != RL_CHAIN_NONE || release_aux != RL_CHAIN_NONE) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            if (release_aux != RL_CHAIN_NONE) mbar_arrive(&bars[release_aux]);
+            if (store_tensor != RL_CHAIN_NONE) {
+              tma_store_2d(&p.tmaps[store_tensor], box, store_col0, m0);
+              bulk_commit();
+              if (release_after_store != RL_CHAIN_NONE) {
+                bulk_wait_read_n<0>();
+                mbar_arrive(&bars[release_after_store]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (et == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+struct ChainHandle {
+  ChainParams params;
+  void* dev_ops;
+  size_t smem_bytes;
+};
+
+}  // namespace tc
+}  // namespace rl
+
+using namespace rl;
+using namespace rl::tc;
+
+extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
+  RL_REQUIRE(d && handle, RL_ERR_BAD_ARG, "rl_chain_create: null argument");
+  RL_REQUIRE(d->n_tensors >= 0 && d->n_tensors <= RL_CHAIN_MAX_TENSORS, RL_ERR_BAD_ARG, "rl_chain_create: n_tensors=%d", d->n_tensors);
+  RL_REQUIRE(d->n_units > 0 && d->n_units <= RL_CHAIN_MAX_UNITS, RL_ERR_BAD_ARG, "rl_chain_create: n_units=%d", d->n_units);
+  RL_REQUIRE(d->n_barriers > 0 && d->n_barriers <= RL_CHAIN_MAX_BARRIERS, RL_ERR_BAD_ARG, "rl_chain_create: n_barriers=%d", d->n_barriers);
+  RL_REQUIRE(d->n_loads >= 0 && d->n_mmas >= 0 && d->n_epis >= 0 && d->loads_host && d->mmas_host && d->epis_host,
+             RL_ERR_BAD_ARG, "rl_chain_create: op lists missing");
+  static_assert(sizeof(RlChainLoadOp) == 32 && sizeof(RlChainMmaOp) == 32 && sizeof(RlChainEpiOp) == 48, "op layouts");
+  const uint32_t limit = (uint32_t)d->n_units * UNIT_BYTES;
+  for (int i = 0; i < d->n_loads; ++i) {
+    const RlChainLoadOp& o = d->loads_host[i];
+    RL_REQUIRE(o.tensor < d->n_tensors && o.full_bar < d->n_barriers && (o.smem_off & 1023u) == 0 &&
+               o.smem_off + o.expect_bytes <= limit && o.expect_bytes > 0 && o.expect_bytes <= 2 * UNIT_BYTES,
+               RL_ERR_BAD_ARG, "rl_chain_create: load op %d malformed", i);
+  }
+  for (int i = 0; i < d->n_mmas; ++i) {
+    const RlChainMmaOp& o = d->mmas_host[i];
+    RL_REQUIRE(o.n >= 16 && o.n <= 256 && (o.n % 16) == 0 && o.tmem_col + o.n <= 512 && o.k_steps >= 1 && o.k_steps <= 4 &&
+               (o.a_off & 1023u) == 0 && (o.b_off & 1023u) == 0 && o.a_off + UNIT_BYTES <= limit && o.b_off + (uint32_t)o.n * 128 <= limit,
+               RL_ERR_BAD_ARG, "rl_chain_create: mma op %d malformed", i);
+  }
+  for (int i = 0; i < d->n_epis; ++i) {
+    const RlChainEpiOp& o = d->epis_host[i];
+    RL_REQUIRE(o.ncols >= 1 && o.ncols <= 64 && o.tmem_col + (o.ncols > 32 ? 64 : 32) <= 512 && o.mode <= RL_CHAIN_EPI_PLAIN, RL_ERR_BAD_ARG,
+               "rl_chain_create: epilogue op %d malformed", i);
+    if (o.mode == RL_CHAIN_EPI_BIAS_F32)
+      RL_REQUIRE(o.out_id < RL_CHAIN_MAX_OUTPUTS && d->outputs[o.out_id] != nullptr, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d output", i);
+    else
+      RL_REQUIRE((o.dst_off & 1023u) == 0 && o.dst_off + UNIT_BYTES <= limit && o.dst_col0 + o.ncols <= 64, RL_ERR_BAD_ARG,
+                 "rl_chain_create: epilogue op %d destination", i);
+    RL_REQUIRE(o.store_tensor == RL_CHAIN_NONE || o.store_tensor < d->n_tensors, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d store", i);
+  }
+  ChainHandle* h = new ChainHandle();
+  memset(&h->params, 0, sizeof(h->params));
+  int rc;
+  for (int t = 0; t < d->n_tensors; ++t) {
+    const RlChainTensor& T = d->tensors[t];
+    if ((rc = make_tmap_bf16(&h->params.tmaps[t], T.base, (uint64_t)T.rows, (uint64_t)T.cols, (uint64_t)T.ld, (uint32_t)T.box_rows)) != RL_OK) {
+      delete h;
+      return rc;
+    }
+  }
+  const size_t nl = (size_t)d->n_loads * sizeof(RlChainLoadOp), nm = (size_t)d->n_mmas * sizeof(RlChainMmaOp),
+               ne = (size_t)d->n_epis * sizeof(RlChainEpiOp);
+  cudaError_t err = cudaMalloc(&h->dev_ops, nl + nm + ne + 48);
+  if (err != cudaSuccess) { delete h; set_error("rl_chain_create: cudaMalloc: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
+  uint8_t* base = reinterpret_cast<uint8_t*>(h->dev_ops);
+  err = cudaMemcpy(base, d->loads_host, nl, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(base + nl, d->mmas_host, nm, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(base + nl + nm, d->epis_host, ne, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: cudaMemcpy: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
+  h->params.loads = reinterpret_cast<const RlChainLoadOp*>(base);
+  h->params.mmas = reinterpret_cast<const RlChainMmaOp*>(base + nl);
+  h->params.epis = reinterpret_cast<const RlChainEpiOp*>(base + nl + nm);
+  h->params.params = d->params;
+  for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->params.outputs[i] = d->outputs[i];
+  h->params.n_loads = d->n_loads; h->params.n_mmas = d->n_mmas; h->params.n_epis = d->n_epis;
+  h->params.n_units = d->n_units; h->params.n_barriers = d->n_barriers;
+  memcpy(h->params.barrier_count, d->barrier_count, RL_CHAIN_MAX_BARRIERS);
+  h->smem_bytes = (size_t)d->n_units * UNIT_BYTES + RL_CHAIN_MAX_BARRIERS * 8 + 16 + 1024;
+  static size_t configured = 0;
+  if (h->smem_bytes > configured) {
+    err = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: smem %zu B: %s", h->smem_bytes, cudaGetErrorString(err)); return RL_ERR_CUDA; }
+    configured = h->smem_bytes;
+  }
+  *handle = h;
+  return RL_OK;
+}
+
+extern "C" int rl_chain_run(void* handle, int32_t rows, void* stream) {
+  RL_REQUIRE(handle && rows > 0, RL_ERR_BAD_ARG, "rl_chain_run: handle=%p rows=%d", handle, rows);
+  ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  ChainParams p = h->params;
+  p.rows = rows;
+  p.num_tiles = (rows + 127) / 128;
+  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  mlp_chain_kernel<<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
+  return check_launch("mlp_chain_kernel");
+}
+
+extern "C" int rl_chain_destroy(void* handle) {
+  if (!handle) return RL_OK;
+  ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
+  cudaFree(h->dev_ops);
+  delete h;
+  return RL_OK;
+}

@@ -13,6 +13,7 @@ concatenated [1024 x 60] GEMM; the encoder is evaluated once per batch, not twic
 10: `act` and `evaluate` both call it).  There is no eager fallback.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -88,6 +89,9 @@ class ActorCritic(nn.Module):
         self._cache_key = None
         self._act_step = 0
         self.seed = 0
+        # fused MLP chains (csrc/chain.cu): one persistent kernel per network pass instead of one GEMM per layer
+        self.use_chain = os.environ.get("RL_USE_CHAIN", "1") != "0"
+        self._chains = {}
 
     # ------------------------------------------------------------------------------------------------
     def _linears(self, seq):
@@ -197,7 +201,35 @@ class ActorCritic(nn.Module):
                 self._ws_bwd = True
             self._ws, self._ws_rows = w, R
             self._cache_key = None
+            self._chains = {}          # chain programs bake the workspace pointers in
         return self._ws
+
+    # ------------------------------------------------------------------------------------------------
+    # fused chains
+    # ------------------------------------------------------------------------------------------------
+    def _chain_tensors(self):
+        """Workspace buffers, bf16 shadow weights and bias offsets (floats into self.flat) by the names
+        ppo/chain.py uses."""
+        w = self._ws
+        off = lambda L: (L.b.data_ptr() - self.flat.data_ptr()) // 4
+        e, a, c, d = self.L_enc, self.L_act, self.L_cri, self.L_ada
+        T = {k: w[k] for k in w}
+        T.update(params=self.flat, num_obs=self.num_obs,
+                 We1=e[0].wb, We2=e[1].wb, We3=e[2].wb, Wcat=self.L_cat.wb, Wa2=a[0].wb, Wa3=a[1].wb, Wa4=a[2].wb,
+                 Wc2=c[0].wb, Wc3=c[1].wb, Wc4=c[2].wb, Wd1=d[0].wb, Wd2=d[1].wb, Wd3=d[2].wb,
+                 We2t=e[1].wbt, We3t=e[2].wbt, Wcat_t=self.L_cat.wbt, Wa2t=a[0].wbt, Wa3t=a[1].wbt, Wa4t=a[2].wbt,
+                 Wc2t=c[0].wbt, Wc3t=c[1].wbt, Wc4t=c[2].wbt, Wd2t=d[1].wbt, Wd3t=d[2].wbt,
+                 b_e1=off(e[0]), b_e2=off(e[1]), b_e3=off(e[2]), b_cat=off(self.L_cat), b_a2=off(a[0]), b_a3=off(a[1]),
+                 b_a4=off(a[2]), b_c2=off(c[0]), b_c3=off(c[1]), b_c4=off(c[2]), b_d1=off(d[0]), b_d2=off(d[1]),
+                 b_d3=off(d[2]))
+        return T
+
+    def _chain(self, key, build):
+        prog = self._chains.get(key)
+        if prog is None:
+            prog = build(self._chain_tensors()).compile()
+            self._chains[key] = prog
+        return prog
 
     # ------------------------------------------------------------------------------------------------
     # GEMM plumbing
@@ -223,6 +255,12 @@ class ActorCritic(nn.Module):
 
     def forward_teacher(self, rows, want_value=True, want_mean=True):
         """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace."""
+        if self.use_chain:
+            from . import chain
+            save = bool(getattr(self, "_ws_bwd", False))
+            self._chain(("teacher", save, want_mean, want_value),
+                        lambda T: chain.teacher_forward_program(T, save=save, want_mean=want_mean, want_value=want_value)).run(rows)
+            return
         self.forward_encoder(rows)
         self._trunk(rows, want_value, want_mean)
 

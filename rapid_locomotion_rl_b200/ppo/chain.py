@@ -1,0 +1,738 @@
+"""Host side of the fused MLP chains (csrc/chain.cu, include/rl_b200.h "Fused MLP chains").
+
+A chain program is three op lists (LOAD / MMA / EPI) that the three warp roles of one persistent CTA
+execute in order for every 128-row tile.  This module
+  * builds the programs for the learner's networks (mini_gym_learn/ppo/actor_critic.py:38-100 forward,
+    and the dgrad half of the autograd backward behind ppo.py:146-168) with a small resource-tracking
+    builder (shared-memory units, ring stages, tensor-memory regions, mbarrier phase bookkeeping), and
+  * EMULATES a program on the CPU: the three roles and the asynchronous agents (TMA loads / stores, the
+    tensor-core pipe) run under a randomised scheduler with the exact mbarrier semantics of the device
+    (parity waits, arrival counts, transaction bytes), checking deadlock freedom, phase-parity
+    soundness and shared-memory hazards, and computing the numerical result in bf16 / fp32.
+The emulator is how a schedule is proved before it ever reaches the GPU; the product path only uses
+`ChainProgram.compile()` + `run()`.
+"""
+import ctypes as C
+import random
+
+import torch
+
+from .. import _lib
+
+UNIT = 16384
+NONE = 255
+EPI_BIAS_ELU, EPI_BIAS, EPI_BIAS_F32, EPI_DELU, EPI_PLAIN = range(5)
+
+
+class _Wait:
+    __slots__ = ("bar", "need")
+
+    def __init__(self, bar, need):
+        self.bar, self.need = bar, need
+
+    def key(self):
+        return (self.bar, self.need)
+
+
+class StageUse:
+    """One landing of a TMA box in a ring stage."""
+    __slots__ = ("stage", "off", "full", "empty_bar", "released")
+
+    def __init__(self, stage, off, full, empty_bar):
+        self.stage, self.off, self.full, self.empty_bar, self.released = stage, off, full, empty_bar, False
+
+
+class BoxUse:
+    """One content of an activation unit (written by the epilogue, or loaded by TMA for inputs)."""
+    __slots__ = ("unit", "off", "ready", "free_bar", "released", "has_reader")
+
+    def __init__(self, unit, off, ready, free_bar):
+        self.unit, self.off, self.ready, self.free_bar = unit, off, ready, free_bar
+        self.released, self.has_reader = False, True
+
+
+class AccUse:
+    __slots__ = ("region", "col", "full", "free_bar", "wait_free", "started", "closed")
+
+    def __init__(self, region, col, free_bar, wait_free):
+        self.region, self.col, self.free_bar, self.wait_free = region, col, free_bar, wait_free
+        self.full, self.started, self.closed = None, False, False
+
+
+class ChainProgram:
+    """Builder + container of one chain program."""
+
+    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain"):
+        """Shared-memory units: [inputs | pool | stages]; `regions`: {name: (first tmem column, width)}."""
+        self.name = name
+        self.n_inputs, self.n_pool, self.n_stages = n_inputs, n_pool, n_stages
+        self.n_units = n_inputs + n_pool + n_stages
+        assert self.n_units <= _lib.DEFINES["RL_CHAIN_MAX_UNITS"]
+        self.tensors = []                # (torch tensor 2-D view, box_rows)
+        self.bar_count = []
+        self.bar_phases = []             # completions per tile
+        self.bar_name = []
+        self.loads, self.mmas, self.epis = [], [], []
+        self.outputs = [None] * _lib.DEFINES["RL_CHAIN_MAX_OUTPUTS"]
+        self.params = None
+        self.regions = dict(regions)
+        # resources
+        self.pool_units = [n_inputs + i for i in range(n_pool)]
+        self.stage_units = [n_inputs + n_pool + i for i in range(n_stages)]
+        self.stage_full = [self._bar(1, "stage%d.full" % i) for i in range(n_stages)]
+        self.stage_empty = [self._bar(1, "stage%d.empty" % i) for i in range(n_stages)]
+        self.stage_uses = [0] * n_stages
+        self.ring_pos = 0
+        self.pool_ready = [self._bar(4, "pool%d.ready" % i) for i in range(n_pool)]
+        self.pool_free = [self._bar(1, "pool%d.free" % i) for i in range(n_pool)]
+        self.pool_pos = 0
+        self.pool_last = [None] * n_pool           # last BoxUse per pool unit
+        self.acc_full = {r: self._bar(1, "acc_%s.full" % r) for r in regions}
+        self.acc_free = {r: self._bar(4, "acc_%s.free" % r) for r in regions}
+        self.acc_uses = {r: 0 for r in regions}
+        self.acc_open = {r: None for r in regions}
+        self.input_full, self.input_free, self.input_loads = {}, {}, {}
+        self.waited = {"load": set(), "mma": set(), "epi": set()}
+        # TMA-store bookkeeping (epilogue thread 0 commits one bulk group per store)
+        self.n_stores = 0
+        self.unit_last_store = {}        # unit -> store index within the tile
+        self._finalized = False
+
+    # ---------------------------------------------------------------------------------------------
+    def _bar(self, count, name):
+        self.bar_count.append(count)
+        self.bar_phases.append(0)
+        self.bar_name.append(name)
+        assert len(self.bar_count) <= _lib.DEFINES["RL_CHAIN_MAX_BARRIERS"]
+        return len(self.bar_count) - 1
+
+    def _signal(self, bar):
+        """One more phase completion of `bar` per tile; returns its ordinal (1-based)."""
+        self.bar_phases[bar] += 1
+        return self.bar_phases[bar]
+
+    def tensor(self, t, box_rows):
+        assert t.dim() == 2 and t.dtype == torch.bfloat16 and t.stride(1) == 1
+        assert (t.stride(0) * 2) % 16 == 0 and t.data_ptr() % 16 == 0, "TMA operand alignment"
+        assert 8 <= box_rows <= 256 and box_rows * 128 <= UNIT
+        self.tensors.append((t, box_rows))
+        assert len(self.tensors) <= _lib.DEFINES["RL_CHAIN_MAX_TENSORS"]
+        return len(self.tensors) - 1
+
+    def output(self, idx, t):
+        assert t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1
+        self.outputs[idx] = t
+        return idx
+
+    def _w(self, role, wait):
+        """Drop waits this role has already performed (same barrier, same completion)."""
+        if wait is None:
+            return None
+        if wait.key() in self.waited[role]:
+            return None
+        self.waited[role].add(wait.key())
+        return wait
+
+    # ---- inputs: TMA-loaded [128 x 64] boxes in dedicated units ------------------------------------
+    def load_input(self, slot, tensor, col0, extra_free_arrivals=0):
+        """Loads the tile's rows of `tensor` (64 columns from col0) into input unit `slot`."""
+        assert slot < self.n_inputs and slot not in self.input_loads
+        full = self._bar(1, "in%d.full" % slot)
+        free = self._bar(1 + extra_free_arrivals, "in%d.free" % slot)
+        self.input_full[slot], self.input_free[slot] = full, free
+        ordn = self._signal(full)
+        self.loads.append(dict(wait=_Wait(free, 0), full_bar=full, tensor=tensor, smem_off=slot * UNIT, col0=col0, row0=0,
+                               bytes=UNIT, tile_rows=1))
+        use = BoxUse(slot, slot * UNIT, _Wait(full, ordn), free)
+        self.input_loads[slot] = use
+        return use
+
+    # ---- ring stages ------------------------------------------------------------------------------
+    def load_stage(self, tensor, col0, row0, tile_rows=False):
+        t, box_rows = self.tensors[tensor]
+        s = self.ring_pos % self.n_stages
+        self.ring_pos += 1
+        wait = _Wait(self.stage_empty[s], self.stage_uses[s])
+        self.stage_uses[s] += 1
+        ordn = self._signal(self.stage_full[s])
+        off = self.stage_units[s] * UNIT
+        self.loads.append(dict(wait=wait, full_bar=self.stage_full[s], tensor=tensor, smem_off=off, col0=col0, row0=row0,
+                               bytes=box_rows * 128, tile_rows=int(tile_rows)))
+        return StageUse(s, off, _Wait(self.stage_full[s], ordn), self.stage_empty[s])
+
+    # ---- tensor-memory accumulators -----------------------------------------------------------------
+    def acc(self, region):
+        assert self.acc_open[region] is None or self.acc_open[region].closed, "accumulator %s still open" % region
+        col, width = self.regions[region]
+        a = AccUse(region, col, self.acc_free[region], _Wait(self.acc_free[region], self.acc_uses[region]))
+        self.acc_uses[region] += 1
+        self.acc_open[region] = a
+        return a
+
+    # ---- MMA ------------------------------------------------------------------------------------------
+    def mma(self, a, b, n, acc, col_off=0, k_steps=4, accumulate=True, acc_last=False, a_release=False, b_release=True):
+        """acc[:, col_off : col_off + n] (+)= A box * B box^T over k_steps K16 steps."""
+        waits, commits = [], []
+        for w in (a.full if isinstance(a, StageUse) else a.ready, b.full, None if acc.started else acc.wait_free):
+            w = self._w("mma", w)
+            if w is not None:
+                waits.append(w)
+        acc.started = True
+        if b_release:
+            assert not b.released
+            b.released = True
+            commits.append(b.empty_bar)
+            self._signal(b.empty_bar)
+        if a_release:
+            assert not a.released
+            a.released = True
+            bar = a.empty_bar if isinstance(a, StageUse) else a.free_bar
+            commits.append(bar)
+            self._signal(bar)
+        if acc_last:
+            acc.full = _Wait(self.acc_full[acc.region], self._signal(self.acc_full[acc.region]))
+            commits.append(self.acc_full[acc.region])
+        width = self.regions[acc.region][1]
+        assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 128
+        assert len(waits) <= 3 and len(commits) <= 3
+        self.mmas.append(dict(a_off=a.off, b_off=b.off, n=n, tmem_col=acc.col + col_off, k_steps=k_steps,
+                              accumulate=int(accumulate), waits=waits, commits=commits))
+
+    # ---- epilogue ---------------------------------------------------------------------------------------
+    def _epi_common(self, acc, col, ncols, mode, bias_off, first, last):
+        assert acc.full is not None, "accumulator has no closing MMA yet"
+        op = dict(wait_acc=self._w("epi", acc.full) if first else None, wait_dst=None, wait_aux=None, arrive_acc_free=NONE,
+                  arrive_dst_ready=NONE, release_aux=NONE, mode=mode, ncols=ncols, dst_col0=0, tmem_col=acc.col + col,
+                  store_tensor=NONE, store_wait_pending=-1, release_after_store=NONE, out_id=NONE, out_ld=0,
+                  bias_off=bias_off, dst_off=0, aux_off=0, store_col0=0)
+        if last:
+            op["arrive_acc_free"] = acc.free_bar
+            self._signal(acc.free_bar)
+            acc.closed = True
+        return op
+
+    def epi_box(self, acc, col, mode, bias_off=0, ncols=64, aux=None, store=None, first=False, last=False, has_reader=True):
+        """Accumulator columns [col, col+ncols) -> bf16 box in the next pool unit (round robin)."""
+        op = self._epi_common(acc, col, ncols, mode, bias_off, first, last)
+        i = self.pool_pos % self.n_pool
+        self.pool_pos += 1
+        unit = self.pool_units[i]
+        prev = self.pool_last[i]
+        if prev is not None:
+            assert prev.released or not prev.has_reader, "pool unit %d reused before its content got a releasing reader" % i
+        # frees emitted so far for this unit == completions the writer must have seen
+        op["wait_dst"] = self._w("epi", _Wait(self.pool_free[i], self.bar_phases[self.pool_free[i]]))
+        ordn = self._signal(self.pool_ready[i])
+        op["arrive_dst_ready"] = self.pool_ready[i]
+        op["dst_off"] = unit * UNIT
+        self._store_hazard(op, unit)
+        if mode == EPI_DELU:
+            assert aux is not None and not aux.released
+            op["wait_aux"] = self._w("epi", aux.full)
+            op["aux_off"] = aux.off
+            op["release_aux"] = aux.empty_bar
+            aux.released = True
+            self._signal(aux.empty_bar)
+        if store is not None:
+            op["store_tensor"], op["store_col0"] = store
+            self.unit_last_store[unit] = self.n_stores
+            self.n_stores += 1
+        use = BoxUse(unit, unit * UNIT, _Wait(self.pool_ready[i], ordn), self.pool_free[i])
+        use.has_reader = has_reader
+        self.pool_last[i] = use
+        self.epis.append(op)
+        return use
+
+    def _store_hazard(self, op, unit):
+        """The unit may still be read by a TMA store issued earlier (this tile or the previous one)."""
+        if unit in self.unit_last_store:
+            op["_store_dep"] = ("same", self.unit_last_store[unit], self.n_stores)
+        else:
+            op["_store_dep"] = ("prev", None, self.n_stores)     # resolved in finalize (needs stores per tile)
+        op["_unit"] = unit
+
+    def epi_merge(self, acc, col, ncols, mode, bias_off, box, dst_col0, ready_bar_count4, store=None, release_after_store=NONE,
+                  first=True, last=True):
+        """Accumulator columns -> `ncols` columns at dst_col0 of an already loaded input box (the encoder latent
+        next to the observations).  Waits for the box's TMA load, signals `ready_bar_count4`."""
+        op = self._epi_common(acc, col, ncols, mode, bias_off, first, last)
+        op["wait_dst"] = self._w("epi", box.ready)
+        op["dst_off"], op["dst_col0"] = box.off, dst_col0
+        ordn = self._signal(ready_bar_count4)
+        op["arrive_dst_ready"] = ready_bar_count4
+        if store is not None:
+            op["store_tensor"], op["store_col0"] = store
+            self.n_stores += 1
+            op["release_after_store"] = release_after_store
+        self.epis.append(op)
+        merged = BoxUse(box.unit, box.off, _Wait(ready_bar_count4, ordn), box.free_bar)
+        return merged
+
+    def epi_out(self, acc, col, ncols, bias_off, out_id, first=True, last=True):
+        op = self._epi_common(acc, col, ncols, EPI_BIAS_F32, bias_off, first, last)
+        op["out_id"], op["out_ld"] = out_id, self.outputs[out_id].stride(0)
+        self.epis.append(op)
+
+    # ---------------------------------------------------------------------------------------------
+    def finalize(self):
+        if self._finalized:
+            return self
+        for s in range(self.n_stages):
+            assert self.bar_phases[self.stage_empty[s]] == self.stage_uses[s], "stage %d: uses and releases differ" % s
+        for slot, use in self.input_loads.items():
+            assert self.bar_phases[self.input_free[slot]] == 1, "input %d is never released (or more than once)" % slot
+        S = self.n_stores
+        for op in self.epis:
+            dep = op.pop("_store_dep", None)
+            unit = op.pop("_unit", None)
+            if dep is None:
+                continue
+            kind, k, m = dep
+            if kind == "same":
+                pend = m - 1 - k
+            elif unit in self.unit_last_store:       # last stored in the previous tile
+                pend = m - 1 - (self.unit_last_store[unit] - S)
+            else:
+                pend = None
+            op["store_wait_pending"] = -1 if pend is None else max(0, min(7, pend))
+        self._finalized = True
+        return self
+
+    def _spec(self, w):
+        if w is None:
+            return NONE
+        flip = self.bar_phases[w.bar] & 1
+        return w.bar | (((w.need - 1) & 1) << 8) | (flip << 9)
+
+    def pack(self):
+        """ctypes arrays + RlChainDesc (keeps references alive on self)."""
+        self.finalize()
+        L = (_lib.RlChainLoadOp * max(1, len(self.loads)))()
+        for i, o in enumerate(self.loads):
+            x = L[i]
+            x.wait, x.full_bar, x.tensor, x.smem_off = self._spec(o["wait"]), o["full_bar"], o["tensor"], o["smem_off"]
+            x.col0, x.row0, x.expect_bytes, x.tile_rows = o["col0"], o["row0"], o["bytes"], o["tile_rows"]
+        M = (_lib.RlChainMmaOp * max(1, len(self.mmas)))()
+        for i, o in enumerate(self.mmas):
+            x = M[i]
+            x.a_off, x.b_off, x.n, x.tmem_col, x.k_steps, x.accumulate = o["a_off"], o["b_off"], o["n"], o["tmem_col"], o["k_steps"], o["accumulate"]
+            ws = [self._spec(w) for w in o["waits"]] + [NONE] * 3
+            x.wait0, x.wait1, x.wait2 = ws[:3]
+            cs = list(o["commits"]) + [NONE] * 3
+            x.commit0, x.commit1, x.commit2 = cs[:3]
+        E = (_lib.RlChainEpiOp * max(1, len(self.epis)))()
+        for i, o in enumerate(self.epis):
+            x = E[i]
+            x.wait_acc, x.wait_dst, x.wait_aux = self._spec(o["wait_acc"]), self._spec(o["wait_dst"]), self._spec(o["wait_aux"])
+            for k in ("arrive_acc_free", "arrive_dst_ready", "release_aux", "mode", "ncols", "dst_col0", "tmem_col", "store_tensor",
+                      "store_wait_pending", "release_after_store", "out_id", "out_ld", "bias_off", "dst_off", "aux_off", "store_col0"):
+                setattr(x, k, o[k])
+        d = _lib.RlChainDesc()
+        for i, (t, box_rows) in enumerate(self.tensors):
+            T = d.tensors[i]
+            T.base, T.rows, T.cols, T.ld, T.box_rows = t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), box_rows
+        d.n_tensors, d.n_units, d.n_barriers = len(self.tensors), self.n_units, len(self.bar_count)
+        d.n_loads, d.n_mmas, d.n_epis = len(self.loads), len(self.mmas), len(self.epis)
+        for i, c in enumerate(self.bar_count):
+            d.barrier_count[i] = c
+        d.loads_host, d.mmas_host, d.epis_host = C.cast(L, C.c_void_p), C.cast(M, C.c_void_p), C.cast(E, C.c_void_p)
+        d.params = self.params.data_ptr() if self.params is not None else None
+        for i, t in enumerate(self.outputs):
+            d.outputs[i] = t.data_ptr() if t is not None else None
+        self._packed = (L, M, E, d)
+        return d
+
+    # ---- product path -----------------------------------------------------------------------------------
+    def compile(self):
+        lib = _lib.lib()
+        d = self.pack()
+        h = C.c_void_p()
+        _lib.check(lib.rl_chain_create(C.byref(d), C.byref(h)))
+        self._handle, self._libref = h, lib
+        return self
+
+    def run(self, rows, stream=None):
+        _lib.check(self._libref.rl_chain_run(self._handle, int(rows), _lib.current_stream() if stream is None else stream))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and getattr(self, "_libref", None) is not None:
+            try:
+                self._libref.rl_chain_destroy(h)
+            except Exception:
+                pass
+
+
+# =====================================================================================================
+# Emulator
+# =====================================================================================================
+class ChainHazard(AssertionError):
+    pass
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class Emulator:
+    """Executes a ChainProgram on CPU tensors with the device's synchronisation semantics."""
+
+    def __init__(self, prog, rows, n_ctas=1, seed=0):
+        prog.finalize()
+        self.p, self.rows, self.rng = prog, rows, random.Random(seed)
+        self.num_tiles = (rows + 127) // 128
+        self.n_ctas = n_ctas
+
+    # ---- mbarrier -------------------------------------------------------------------------------------
+    class Bar:
+        def __init__(self, count):
+            self.count, self.pending, self.tx, self.n = count, count, 0, 0
+
+        def _check(self):
+            if self.pending == 0 and self.tx == 0:
+                self.n += 1
+                self.pending = self.count
+
+        def arrive(self):
+            if self.pending <= 0:
+                raise ChainHazard("mbarrier over-arrival")
+            self.pending -= 1
+            self._check()
+
+        def arrive_expect(self, nbytes):
+            self.tx += nbytes
+            self.arrive()
+
+        def complete_tx(self, nbytes):
+            self.tx -= nbytes
+            self._check()
+
+    def run(self):
+        for cta in range(min(self.n_ctas, self.num_tiles)):
+            self._run_cta(cta)
+
+    def _run_cta(self, cta):
+        p = self.p
+        tiles = list(range(cta, self.num_tiles, self.n_ctas))
+        bars = [Emulator.Bar(c) for c in p.bar_count]
+        units = [torch.zeros(128, 64) for _ in range(p.n_units)]
+        unit_readers = [0] * p.n_units       # issued, not yet executed async reads (MMA operands, TMA stores)
+        unit_loading = [0] * p.n_units       # TMA loads in flight into the unit
+        tmem = torch.zeros(128, 512)
+        mma_queue = []                       # issued MMAs / commits, executed in order by the tensor pipe
+        loads_inflight, stores_inflight = [], []
+        store_groups = {"issued": 0, "read": 0}
+        state = {"done": 0}
+
+        def spec_wait(w, it, role):
+            """Generator step: block until the hardware parity test passes; checks phase soundness."""
+            if w is None:
+                return
+            need = w.need + it * p.bar_phases[w.bar]
+            parity = (need - 1) & 1
+            b = bars[w.bar]
+            while True:
+                if b.n > need:
+                    raise ChainHazard("%s: barrier %s overran: %d completions, waiter needs %d (tile it %d)" %
+                                      (role, p.bar_name[w.bar], b.n, need, it))
+                if (b.n & 1) != parity:
+                    if b.n != need:
+                        raise ChainHazard("%s: parity alias on %s" % (role, p.bar_name[w.bar]))
+                    return
+                if b.n != need - 1:
+                    raise ChainHazard("%s: barrier %s is %d phases behind" % (role, p.bar_name[w.bar], need - b.n))
+                yield
+
+        def touches(off, nbytes):
+            return range(off // UNIT, (off + nbytes - 1) // UNIT + 1)
+
+        # ---------------- roles as generators ----------------
+        def load_role():
+            for it, tile in enumerate(tiles):
+                m0 = tile * 128
+                for o in p.loads:
+                    yield from spec_wait(o["wait"], it, "load")
+                    u = o["smem_off"] // UNIT
+                    if unit_readers[u] or unit_loading[u]:
+                        raise ChainHazard("TMA load into unit %d while it is still read / loaded (%s)" % (u, p.name))
+                    unit_loading[u] += 1
+                    bars[o["full_bar"]].arrive_expect(o["bytes"])
+                    loads_inflight.append((o, m0))
+                    yield
+            state["done"] += 1
+
+        def land(o, m0):
+            t, box_rows = p.tensors[o["tensor"]]
+            u = o["smem_off"] // UNIT
+            r0 = o["row0"] + (m0 if o["tile_rows"] else 0)
+            box = torch.zeros(box_rows, 64)
+            rr = max(0, min(box_rows, t.shape[0] - r0))
+            cc = max(0, min(64, t.shape[1] - o["col0"]))
+            if rr > 0 and cc > 0:
+                box[:rr, :cc] = t[r0:r0 + rr, o["col0"]:o["col0"] + cc].float()
+            if unit_readers[u]:
+                raise ChainHazard("TMA load landed in unit %d under a reader" % u)
+            units[u][:box_rows] = box
+            unit_loading[u] -= 1
+            bars[o["full_bar"]].complete_tx(o["bytes"])
+
+        def mma_role():
+            for it, tile in enumerate(tiles):
+                for o in p.mmas:
+                    for w in o["waits"]:
+                        yield from spec_wait(w, it, "mma")
+                    ua, ub = o["a_off"] // UNIT, o["b_off"] // UNIT
+                    for u in (ua, ub):
+                        if unit_loading[u]:
+                            raise ChainHazard("MMA reads unit %d while a TMA load is in flight" % u)
+                        unit_readers[u] += 1
+                    mma_queue.append(("mma", o))
+                    for c in o["commits"]:
+                        mma_queue.append(("commit", c))
+                    yield
+            state["done"] += 1
+
+        def exec_mma(o):
+            ua, ub = o["a_off"] // UNIT, o["b_off"] // UNIT
+            n, c0 = o["n"], o["tmem_col"]
+            k = 16 * o["k_steps"]
+            A, B = units[ua][:, :k], units[ub][:n, :k]
+            d = A @ B.t()
+            if o["accumulate"]:
+                tmem[:, c0:c0 + n] += d
+            else:
+                tmem[:, c0:c0 + n] = d
+            unit_readers[ua] -= 1
+            unit_readers[ub] -= 1
+
+        def epi_role():
+            for it, tile in enumerate(tiles):
+                m0 = tile * 128
+                for o in p.epis:
+                    yield from spec_wait(o["wait_acc"], it, "epi")
+                    nc = o["ncols"]
+                    f = tmem[:, o["tmem_col"]:o["tmem_col"] + nc].clone()
+                    if o["arrive_acc_free"] != NONE:
+                        for _ in range(4):
+                            bars[o["arrive_acc_free"]].arrive()
+                    mode = o["mode"]
+                    if mode in (EPI_BIAS_ELU, EPI_BIAS, EPI_BIAS_F32):
+                        f = f + p.params[o["bias_off"]:o["bias_off"] + nc].float()
+                        if mode == EPI_BIAS_ELU:
+                            f = torch.where(f > 0, f, torch.exp(f) - 1)
+                    elif mode == EPI_DELU:
+                        yield from spec_wait(o["wait_aux"], it, "epi")
+                        ua = o["aux_off"] // UNIT
+                        if unit_loading[ua]:
+                            raise ChainHazard("epilogue reads aux unit %d while a TMA load is in flight" % ua)
+                        y = units[ua][:, :nc]
+                        f = f * torch.where(y > 0, torch.ones_like(y), y + 1)
+                    if mode == EPI_BIAS_F32:
+                        out = p.outputs[o["out_id"]]
+                        rr = max(0, min(128, self.rows - m0))
+                        out[m0:m0 + rr, :nc] = f[:rr]
+                        continue
+                    if o["store_wait_pending"] >= 0:
+                        while store_groups["issued"] - store_groups["read"] > o["store_wait_pending"]:
+                            yield
+                    yield from spec_wait(o["wait_dst"], it, "epi")
+                    u = o["dst_off"] // UNIT
+                    if unit_readers[u] or unit_loading[u]:
+                        raise ChainHazard("epilogue overwrites unit %d under a reader (%s, epi op tmem_col %d)" %
+                                          (u, p.name, o["tmem_col"]))
+                    units[u][:, o["dst_col0"]:o["dst_col0"] + nc] = _bf16(f)
+                    if o["arrive_dst_ready"] != NONE:
+                        for _ in range(4):
+                            bars[o["arrive_dst_ready"]].arrive()
+                    if o["release_aux"] != NONE:
+                        bars[o["release_aux"]].arrive()
+                    if o["store_tensor"] != NONE:
+                        unit_readers[u] += 1
+                        store_groups["issued"] += 1
+                        stores_inflight.append((o, m0, u))
+                        if o["release_after_store"] != NONE:
+                            while store_groups["issued"] != store_groups["read"]:
+                                yield
+                            bars[o["release_after_store"]].arrive()
+                    yield
+            state["done"] += 1
+
+        def do_store(o, m0, u):
+            t, _ = p.tensors[o["store_tensor"]]
+            rr = max(0, min(128, t.shape[0] - m0))
+            cc = max(0, min(64, t.shape[1] - o["store_col0"]))
+            if rr > 0 and cc > 0:
+                t[m0:m0 + rr, o["store_col0"]:o["store_col0"] + cc] = units[u][:rr, :cc].to(t.dtype)
+            unit_readers[u] -= 1
+            store_groups["read"] += 1
+
+        roles = [load_role(), mma_role(), epi_role()]
+        alive = [True, True, True]
+        blocked_rounds = 0
+        # adversarial speeds: every agent (3 roles, TMA loads, tensor pipe, TMA stores) gets its own firing
+        # probability per round, re-drawn now and then, so slow-consumer / slow-producer races are exercised
+        speeds = [1.0] * 6
+        rounds = 0
+        while True:
+            progressed = False
+            if rounds % 400 == 0:
+                speeds = [self.rng.choice((0.03, 0.3, 1.0)) for _ in range(6)]
+            rounds += 1
+            order = [0, 1, 2, 3, 4, 5]
+            self.rng.shuffle(order)
+            for a in order:
+                if self.rng.random() > speeds[a]:
+                    continue
+                if a < 3:
+                    if not alive[a]:
+                        continue
+                    before = (len(loads_inflight), len(mma_queue), len(stores_inflight), tuple(b.n for b in bars),
+                              tuple(b.pending for b in bars), store_groups["issued"])
+                    try:
+                        next(roles[a])
+                    except StopIteration:
+                        alive[a] = False
+                        progressed = True
+                        continue
+                    after = (len(loads_inflight), len(mma_queue), len(stores_inflight), tuple(b.n for b in bars),
+                             tuple(b.pending for b in bars), store_groups["issued"])
+                    progressed |= before != after
+                elif a == 3 and loads_inflight:
+                    i = self.rng.randrange(len(loads_inflight))      # TMA completes out of order
+                    land(*loads_inflight.pop(i))
+                    progressed = True
+                elif a == 4 and mma_queue:
+                    kind, x = mma_queue.pop(0)                        # the tensor pipe executes in order
+                    if kind == "mma":
+                        exec_mma(x)
+                    else:
+                        bars[x].arrive()
+                    progressed = True
+                elif a == 5 and stores_inflight:
+                    do_store(*stores_inflight.pop(0))                 # bulk groups complete in order
+                    progressed = True
+            if not any(alive) and not loads_inflight and not mma_queue and not stores_inflight:
+                break
+            if progressed:
+                blocked_rounds = 0
+            else:
+                blocked_rounds += 1
+                if blocked_rounds > 5000 and not loads_inflight and not mma_queue and not stores_inflight:
+                    raise ChainHazard("deadlock in %s: roles alive %s, barrier completions %s" %
+                                      (p.name, alive, {p.bar_name[i]: b.n for i, b in enumerate(bars)}))
+
+
+# =====================================================================================================
+# Programs for the learner's networks
+# =====================================================================================================
+REGIONS = {"C0": (0, 64), "C1": (64, 64), "BIG": (128, 256), "MID": (384, 128)}
+
+
+def _dense(p, a_boxes, w_tensor, n_out, acc, k_last_steps=4, release_a=True, w_row0=0):
+    """acc[:, :n_out] = sum_j A box j * W[w_row0 : w_row0 + n_out, 64 j : 64 j + 64]^T in halves of <= 128 output
+    columns (one ring stage per weight box).  Closes the accumulator."""
+    nk = len(a_boxes)
+    halves = [(h, min(128, n_out - h)) for h in range(0, n_out, 128)]
+    for j, a in enumerate(a_boxes):
+        for hi, (h0, hn) in enumerate(halves):
+            st = p.load_stage(w_tensor, col0=64 * j, row0=w_row0 + h0)
+            p.mma(a, st, n=hn, acc=acc, col_off=h0, k_steps=k_last_steps if j == nk - 1 else 4, accumulate=j > 0,
+                  acc_last=(j == nk - 1 and hi == len(halves) - 1), a_release=release_a and hi == len(halves) - 1)
+
+
+def _boxes(p, acc, width, mode, bias_off, store_tensor=None, store_col0=0, aux_tensor=None, aux_col0=0, has_reader=True):
+    """Epilogue of a `width`-column accumulator into width/64 pool boxes (the last may be narrower)."""
+    out = []
+    n = (width + 63) // 64
+    for c in range(n):
+        nc = min(64, width - 64 * c)
+        aux = p.load_stage(aux_tensor, col0=aux_col0 + 64 * c, row0=0, tile_rows=True) if aux_tensor is not None else None
+        out.append(p.epi_box(acc, 64 * c, mode, bias_off=bias_off + 64 * c, ncols=nc, aux=aux,
+                             store=None if store_tensor is None else (store_tensor, store_col0 + 64 * c),
+                             first=(c == 0), last=(c == n - 1), has_reader=has_reader))
+    return out
+
+
+def _round16(n):
+    return (n + 15) // 16 * 16
+
+
+def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=6):
+    """encoder(priv) -> latent merged into the [obs | latent] box -> actor mean / critic value
+    (actor_critic.py:124-173 `act` / `evaluate` on one batch; ppo.py:102-107 inside the update).
+    T: tensors + parameter offsets (see ActorCritic._chain_tensors).  save: also store every hidden
+    activation (the backward needs them).  trunk=False: only refresh the latent slot of Xac."""
+    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=REGIONS, name="teacher_forward")
+    p.params = T["params"]
+    tXp, tXac = p.tensor(T["Xp"], 128), p.tensor(T["Xac"], 128)
+    tWe1, tWe2 = p.tensor(T["We1"], 128), p.tensor(T["We2"], 128)
+    lat = T["We3"].shape[0]
+    tWe3 = p.tensor(T["We3"], _round16(lat))
+    st = lambda name: p.tensor(T[name], 128) if save else None
+    tH1, tH2 = st("H1"), st("H2")
+    xp = p.load_input(0, tXp, 0)
+    xac = p.load_input(1, tXac, 0, extra_free_arrivals=1)
+    # ---- encoder ----
+    kp = T["Xp"].shape[1]
+    acc = p.acc("BIG")
+    _dense(p, [xp], tWe1, T["We1"].shape[0], acc, k_last_steps=(kp + 15) // 16)
+    h1 = _boxes(p, acc, T["We1"].shape[0], EPI_BIAS_ELU, T["b_e1"], tH1)
+    acc = p.acc("MID")
+    _dense(p, h1, tWe2, T["We2"].shape[0], acc)
+    h2 = _boxes(p, acc, T["We2"].shape[0], EPI_BIAS_ELU, T["b_e2"], tH2)
+    acc = p.acc("C0")
+    _dense(p, h2, tWe3, _round16(lat), acc)
+    merged_ready = p._bar(4, "xac.merged")
+    xacm = p.epi_merge(acc, 0, lat, EPI_BIAS, T["b_e3"], xac, T["num_obs"], merged_ready, store=(tXac, 0),
+                       release_after_store=xac.free_bar)
+    if not trunk:
+        # nobody multiplies the merged box: release it from the tensor-pipe side with a 1-step dummy?  No -
+        # simply give the free barrier its second arrival from the epilogue store alone.
+        p.bar_count[xac.free_bar] = 1
+        p._signal(xac.free_bar)
+        return p.finalize()
+    # ---- actor / critic: first layer streamed in 64-column chunks straight into the second layer ----
+    tWcat = p.tensor(T["Wcat"], 64)
+    tY1 = st("Y1")
+    H = T["Wcat"].shape[0] // 2
+    nets = []
+    if want_mean:
+        nets.append(("a", 0, T["Wa2"], T["Wa3"], T["Wa4"], "A2", "A3", T["b_a2"], T["b_a3"], T["b_a4"], 0))
+    if want_value:
+        nets.append(("c", H, T["Wc2"], T["Wc3"], T["Wc4"], "C2", "C3", T["b_c2"], T["b_c3"], T["b_c4"], 1))
+    for ni, (tag, off, W2, W3, W4, n2, n3, b2, b3, b4, out_id) in enumerate(nets):
+        tW2, tW3 = p.tensor(W2, 128), p.tensor(W3, 128)
+        n_out = W4.shape[0]
+        tW4 = p.tensor(W4, _round16(n_out))
+        t2, t3 = st(n2), st(n3)
+        nch = H // 64
+        acc2 = p.acc("BIG")
+        chunk_box = [None] * nch
+
+        def l1(j):
+            a1 = p.acc("C%d" % (j % 2))
+            s = p.load_stage(tWcat, col0=0, row0=off + 64 * j)
+            p.mma(xacm, s, n=64, acc=a1, k_steps=4, accumulate=False, acc_last=True,
+                  a_release=(ni == len(nets) - 1 and j == nch - 1))
+            chunk_box[j] = p.epi_box(a1, 0, EPI_BIAS_ELU, bias_off=T["b_cat"] + off + 64 * j,
+                                     store=None if tY1 is None else (tY1, off + 64 * j), first=True, last=True)
+
+        def l2(j):
+            for h in range(0, W2.shape[0], 128):
+                s = p.load_stage(tW2, col0=64 * j, row0=h)
+                p.mma(chunk_box[j], s, n=128, acc=acc2, col_off=h, k_steps=4, accumulate=j > 0,
+                      acc_last=(j == nch - 1 and h + 128 >= W2.shape[0]), a_release=(h + 128 >= W2.shape[0]))
+        l1(0)
+        for j in range(1, nch):
+            l1(j)
+            l2(j - 1)
+        l2(nch - 1)
+        a2 = _boxes(p, acc2, W2.shape[0], EPI_BIAS_ELU, b2, t2)
+        acc3 = p.acc("MID")
+        _dense(p, a2, tW3, W3.shape[0], acc3)
+        a3 = _boxes(p, acc3, W3.shape[0], EPI_BIAS_ELU, b3, t3)
+        acc4 = p.acc("C%d" % (ni % 2))
+        _dense(p, a3, tW4, _round16(n_out), acc4)
+        p.output(out_id, T["mean"] if tag == "a" else T["value"])
+        p.epi_out(acc4, 0, n_out, b4, out_id)
+    return p.finalize()
