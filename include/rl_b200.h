@@ -397,7 +397,7 @@ int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const
  *   rapid_locomotion_rl_b200/ppo/chain.py.
  * A wait is encoded in 16 bits: bits 0-7 barrier id (0xFF = none), bit 8 = parity to wait for in the
  * CTA's first tile, bit 9 = 1 if that parity flips with every further tile of the persistent loop. */
-#define RL_CHAIN_MAX_TENSORS 24
+#define RL_CHAIN_MAX_TENSORS 32
 #define RL_CHAIN_MAX_BARRIERS 64
 #define RL_CHAIN_MAX_UNITS 14                    /* 16 KB shared-memory units (boxes + ring stages) */
 #define RL_CHAIN_MAX_OUTPUTS 4

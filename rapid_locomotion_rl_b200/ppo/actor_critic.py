@@ -248,16 +248,19 @@ class ActorCritic(nn.Module):
 
     def forward_encoder(self, rows):
         """env_factor_encoder(priv) -> bf16 latent written straight into the latent slot of Xac."""
+        if self.use_chain:
+            from . import chain
+            self._chain(("encoder",), lambda T: chain.teacher_forward_program(T, save=False, trunk=False)).run(rows)
+            return
         w, e = self._ws, self.L_enc
         self._fwd(e[0], w["Xp"], 0, w["Xp"].shape[1], w["H1"], 0, w["H1"].shape[1], rows, EPI_BIAS_ELU_BF16)
         self._fwd(e[1], w["H1"], 0, w["H1"].shape[1], w["H2"], 0, w["H2"].shape[1], rows, EPI_BIAS_ELU_BF16)
         self._fwd(e[2], w["H2"], 0, w["H2"].shape[1], w["Xac"], self.num_obs, w["Xac"].shape[1], rows, EPI_BIAS_BF16)
 
-    def forward_teacher(self, rows, want_value=True, want_mean=True):
+    def forward_teacher(self, rows, want_value=True, want_mean=True, save=False):
         """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace."""
         if self.use_chain:
             from . import chain
-            save = bool(getattr(self, "_ws_bwd", False))
             self._chain(("teacher", save, want_mean, want_value),
                         lambda T: chain.teacher_forward_program(T, save=save, want_mean=want_mean, want_value=want_value)).run(rows)
             return
@@ -280,8 +283,12 @@ class ActorCritic(nn.Module):
             self._fwd(c[1], w["C2"], 0, w["C2"].shape[1], w["C3"], 0, w["C3"].shape[1], rows, EPI_BIAS_ELU_BF16)
             self._fwd(c[2], w["C3"], 0, w["C3"].shape[1], w["value"], 0, 1, rows, EPI_BIAS_F32)
 
-    def forward_adaptation(self, rows, into_latent_slot=False):
+    def forward_adaptation(self, rows, into_latent_slot=False, save=False):
         """adaptation_module(obs_history) -> pred (fp32) or, for the student policy, the latent slot of Xac."""
+        if self.use_chain and not into_latent_slot:
+            from . import chain
+            self._chain(("adaptation", save), lambda T: chain.adaptation_forward_program(T, save=save)).run(rows)
+            return
         w, a = self._ws, self.L_ada
         self._fwd(a[0], w["Xh"], 0, w["Xh"].shape[1], w["D1"], 0, w["D1"].shape[1], rows, EPI_BIAS_ELU_BF16)
         self._fwd(a[1], w["D1"], 0, w["D1"].shape[1], w["D2"], 0, w["D2"].shape[1], rows, EPI_BIAS_ELU_BF16)

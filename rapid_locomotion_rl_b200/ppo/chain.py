@@ -214,12 +214,16 @@ class ChainProgram:
     def epi_box(self, acc, col, mode, bias_off=0, ncols=64, aux=None, store=None, first=False, last=False, has_reader=True):
         """Accumulator columns [col, col+ncols) -> bf16 box in the next pool unit (round robin)."""
         op = self._epi_common(acc, col, ncols, mode, bias_off, first, last)
-        i = self.pool_pos % self.n_pool
-        self.pool_pos += 1
+        # next unit, in round-robin order, whose content already has its releasing reader in the program
+        for probe in range(self.n_pool):
+            i = (self.pool_pos + probe) % self.n_pool
+            prev = self.pool_last[i]
+            if prev is None or prev.released or not prev.has_reader:
+                break
+        else:
+            raise AssertionError("%s: all %d pool units hold live boxes" % (self.name, self.n_pool))
+        self.pool_pos = i + 1
         unit = self.pool_units[i]
-        prev = self.pool_last[i]
-        if prev is not None:
-            assert prev.released or not prev.has_reader, "pool unit %d reused before its content got a releasing reader" % i
         # frees emitted so far for this unit == completions the writer must have seen
         op["wait_dst"] = self._w("epi", _Wait(self.pool_free[i], self.bar_phases[self.pool_free[i]]))
         ordn = self._signal(self.pool_ready[i])
@@ -735,4 +739,112 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
         _dense(p, a3, tW4, _round16(n_out), acc4)
         p.output(out_id, T["mean"] if tag == "a" else T["value"])
         p.epi_out(acc4, 0, n_out, b4, out_id)
+    return p.finalize()
+
+
+def trunk_backward_program(T, n_stages=6):
+    """dgrad half of the backward of actor + critic + encoder (what autograd does behind ppo.py:146-148 for
+    the layer inputs): from d(loss)/d(mean) and d(loss)/d(value) down to the encoder's first hidden layer,
+    multiplying by ELU' of the saved activations, storing every layer-output gradient for the wgrad GEMMs.
+    The two first-layer gradient streams (actor, critic) also accumulate d(latent)."""
+    regions = {"C0": (0, 64), "C1": (64, 64), "BIG": (128, 256), "LAT": (384, 32)}
+    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=regions, name="trunk_backward")
+    H = T["Wcat_t"].shape[1] // 2
+    num_obs = T["num_obs"]
+    tY1, tdY1 = p.tensor(T["Y1"], 128), p.tensor(T["dY1"], 128)
+    tWcat_t = p.tensor(T["Wcat_t"], 32)
+    acc_lat = p.acc("LAT")
+    nets = [("a", T["dmean"], 0, "Wa4t", "Wa3t", "Wa2t", "A3", "A2", "dA3", "dA2"),
+            ("c", T["dvalue"], H, "Wc4t", "Wc3t", "Wc2t", "C3", "C2", "dC3", "dC2")]
+    lat_ops = {"n": 0, "total": 2 * (H // 64)}
+    for ni, (tag, d_out, off, w4, w3, w2, s3, s2, g3, g2) in enumerate(nets):
+        d_in = p.load_input(ni, p.tensor(d_out, 128), 0)
+        tW4, tW3, tW2 = p.tensor(T[w4], 128), p.tensor(T[w3], 128), p.tensor(T[w2], 64)
+        tS3, tS2, tG3, tG2 = p.tensor(T[s3], 128), p.tensor(T[s2], 128), p.tensor(T[g3], 128), p.tensor(T[g2], 128)
+        n3, n2 = T[w4].shape[0], T[w3].shape[0]
+        acc = p.acc("BIG")
+        _dense(p, [d_in], tW4, n3, acc, k_last_steps=(d_out.shape[1] + 15) // 16)
+        d3 = _boxes(p, acc, n3, EPI_DELU, 0, tG3, aux_tensor=tS3)
+        acc = p.acc("BIG")
+        _dense(p, d3, tW3, n2, acc)
+        d2 = _boxes(p, acc, n2, EPI_DELU, 0, tG2, aux_tensor=tS2)
+        nch = H // 64
+        boxes = [None] * nch
+
+        def chunk(c):
+            a1 = p.acc("C%d" % (c % 2))
+            for j, a in enumerate(d2):
+                s = p.load_stage(tW2, col0=64 * j, row0=64 * c)
+                p.mma(a, s, n=64, acc=a1, k_steps=4, accumulate=j > 0, acc_last=(j == len(d2) - 1), a_release=(c == nch - 1))
+            aux = p.load_stage(tY1, col0=off + 64 * c, row0=0, tile_rows=True)
+            boxes[c] = p.epi_box(a1, 0, EPI_DELU, aux=aux, store=(tdY1, off + 64 * c), first=True, last=True)
+
+        def lat(c):
+            s = p.load_stage(tWcat_t, col0=off + 64 * c, row0=num_obs)
+            lat_ops["n"] += 1
+            p.mma(boxes[c], s, n=32, acc=acc_lat, k_steps=4, accumulate=lat_ops["n"] > 1,
+                  acc_last=(lat_ops["n"] == lat_ops["total"]), a_release=True)
+        chunk(0)
+        for c in range(1, nch):
+            chunk(c)
+            lat(c - 1)
+        lat(nch - 1)
+    # ---- encoder ----
+    tdLat = p.tensor(T["dLat"], 128)
+    dlat = _boxes(p, acc_lat, 32, EPI_PLAIN, 0, tdLat)
+    tWe3t, tWe2t = p.tensor(T["We3t"], 128), p.tensor(T["We2t"], 128)
+    tH2, tH1, tdH2, tdH1 = p.tensor(T["H2"], 128), p.tensor(T["H1"], 128), p.tensor(T["dH2"], 128), p.tensor(T["dH1"], 128)
+    acc = p.acc("BIG")
+    _dense(p, dlat, tWe3t, T["We3t"].shape[0], acc, k_last_steps=2)
+    dh2 = _boxes(p, acc, T["We3t"].shape[0], EPI_DELU, 0, tdH2, aux_tensor=tH2)
+    acc = p.acc("BIG")
+    _dense(p, dh2, tWe2t, T["We2t"].shape[0], acc)
+    _boxes(p, acc, T["We2t"].shape[0], EPI_DELU, 0, tdH1, aux_tensor=tH1, has_reader=False)
+    return p.finalize()
+
+
+def adaptation_forward_program(T, save=True):
+    """adaptation_module(obs_history) (actor_critic.py:158-162; ppo.py:157): the 630-wide input streams
+    through the ring next to the first layer's weights, the two small layers stay on chip."""
+    p = ChainProgram(n_pool=6, n_stages=8, n_inputs=0, regions=REGIONS, name="adaptation_forward")
+    p.params = T["params"]
+    tXh, tWd1 = p.tensor(T["Xh"], 128), p.tensor(T["Wd1"], 128)
+    n1, n2, n3 = T["Wd1"].shape[0], T["Wd2"].shape[0], T["Wd3"].shape[0]
+    tWd2, tWd3 = p.tensor(T["Wd2"], _round16(n2)), p.tensor(T["Wd3"], _round16(n3))
+    st = lambda name: p.tensor(T[name], 128) if save else None
+    tD1, tD2 = st("D1"), st("D2")
+    K = T["Xh"].shape[1]
+    nk = (K + 63) // 64
+    acc = p.acc("BIG")
+    for j in range(nk):
+        a = p.load_stage(tXh, col0=64 * j, row0=0, tile_rows=True)
+        halves = list(range(0, n1, 128))
+        for hi, h in enumerate(halves):
+            b = p.load_stage(tWd1, col0=64 * j, row0=h)
+            p.mma(a, b, n=min(128, n1 - h), acc=acc, col_off=h, k_steps=min(4, (K - 64 * j + 15) // 16), accumulate=j > 0,
+                  acc_last=(j == nk - 1 and hi == len(halves) - 1), a_release=(hi == len(halves) - 1))
+    d1 = _boxes(p, acc, n1, EPI_BIAS_ELU, T["b_d1"], tD1)
+    acc = p.acc("C0")
+    _dense(p, d1, tWd2, _round16(n2), acc)
+    d2 = _boxes(p, acc, n2, EPI_BIAS_ELU, T["b_d2"], tD2)
+    acc = p.acc("C1")
+    _dense(p, d2, tWd3, _round16(n3), acc, k_last_steps=(n2 + 15) // 16)
+    p.output(0, T["pred"])
+    p.epi_out(acc, 0, n3, T["b_d3"], 0)
+    return p.finalize()
+
+
+def adaptation_backward_program(T):
+    """dgrad of the adaptation-module regression (ppo.py:164-166): d(pred) -> d(D2) -> d(D1)."""
+    p = ChainProgram(n_pool=6, n_stages=6, n_inputs=1, regions=REGIONS, name="adaptation_backward")
+    dp = p.load_input(0, p.tensor(T["dpred"], 128), 0)
+    n2, n1 = T["Wd3t"].shape[0], T["Wd2t"].shape[0]
+    tW3, tW2 = p.tensor(T["Wd3t"], _round16(n2)), p.tensor(T["Wd2t"], 128)
+    tD2, tD1, tdD2, tdD1 = p.tensor(T["D2"], 128), p.tensor(T["D1"], 128), p.tensor(T["dD2"], 128), p.tensor(T["dD1"], 128)
+    acc = p.acc("C0")
+    _dense(p, [dp], tW3, _round16(n2), acc, k_last_steps=(T["dpred"].shape[1] + 15) // 16)
+    dd2 = _boxes(p, acc, n2, EPI_DELU, 0, tdD2, aux_tensor=tD2)
+    acc = p.acc("BIG")
+    _dense(p, dd2, tW2, n1, acc, k_last_steps=(n2 + 15) // 16)
+    _boxes(p, acc, n1, EPI_DELU, 0, tdD1, aux_tensor=tD1, has_reader=False)
     return p.finalize()

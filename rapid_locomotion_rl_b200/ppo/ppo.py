@@ -16,6 +16,7 @@ import ctypes as C
 import torch
 
 from .. import _lib
+from . import chain
 from .actor_critic import (AC_Args, ActorCritic, EPI_ATOMIC, EPI_BF16, EPI_DELU_BF16)
 from .rollout_storage import RolloutStorage
 
@@ -143,7 +144,7 @@ class PPO:
             P(flat(st.advantages)), P(flat(st.mu)), P(flat(st.sigma)), P(idx), B, ac.num_obs, ac.num_priv, ac.num_hist,
             P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
         # ---- forward ----
-        ac.forward_teacher(B)
+        ac.forward_teacher(B, save=True)
         # ---- loss + output gradients ----
         self._stats.zero_()
         inv_gb = 1.0 / (B * world)
@@ -151,30 +152,32 @@ class PPO:
             P(w["mean"]), P(w["value"]), None, P(w["Xac"]), ld("Xac"), ac.num_obs, P(w["Lrow"]), P(ac.std.data), B,
             A.clip_param, A.value_loss_coef, A.entropy_coef, int(A.use_clipped_value_loss), inv_gb, P(w["dmean"]),
             P(w["dvalue"]), P(w["dpred"]), P(ac.std_grad), P(self._stats), stream))
-        # ---- backward: actor ----
+        # ---- backward ----
         H = AC_Args.actor_hidden_dims[0]
         a, c, e, d = ac.L_act, ac.L_cri, ac.L_enc, ac.L_ada
+        if ac.use_chain:
+            # dgrad of actor + critic + encoder in ONE persistent kernel (csrc/chain.cu)
+            ac._chain(("trunk_backward",), chain.trunk_backward_program).run(B)
+        else:
+            self._dgrad(a[2], w["dmean"], 0, 16, w["dA3"], 0, ld("dA3"), B, aux=w["A3"], ld_aux=ld("A3"))
+            self._dgrad(a[1], w["dA3"], 0, ld("dA3"), w["dA2"], 0, ld("dA2"), B, aux=w["A2"], ld_aux=ld("A2"))
+            self._dgrad(a[0], w["dA2"], 0, ld("dA2"), w["dY1"], 0, ld("dY1"), B, aux=w["Y1"], ld_aux=ld("Y1"))
+            self._dgrad(c[2], w["dvalue"], 0, 8, w["dC3"], 0, ld("dC3"), B, aux=w["C3"], ld_aux=ld("C3"))
+            self._dgrad(c[1], w["dC3"], 0, ld("dC3"), w["dC2"], 0, ld("dC2"), B, aux=w["C2"], ld_aux=ld("C2"))
+            self._dgrad(c[0], w["dC2"], 0, ld("dC2"), w["dY1"], H, ld("dY1"), B, aux=w["Y1"], aux_off=H, ld_aux=ld("Y1"))
+            self._dgrad(ac.L_cat, w["dY1"], 0, ld("dY1"), w["dLat"], 0, ld("dLat"), B, col0=ac.num_obs, ncols=ac.latent_dim)
+            self._dgrad(e[2], w["dLat"], 0, ld("dLat"), w["dH2"], 0, ld("dH2"), B, aux=w["H2"], ld_aux=ld("H2"))
+            self._dgrad(e[1], w["dH2"], 0, ld("dH2"), w["dH1"], 0, ld("dH1"), B, aux=w["H1"], ld_aux=ld("H1"))
+        # weight / bias gradients: split-K TN GEMMs over the batch rows
         self._wgrad(a[2], w["dmean"], 0, 16, w["A3"], 0, ld("A3"), B)
-        self._dgrad(a[2], w["dmean"], 0, 16, w["dA3"], 0, ld("dA3"), B, aux=w["A3"], ld_aux=ld("A3"))
         self._wgrad(a[1], w["dA3"], 0, ld("dA3"), w["A2"], 0, ld("A2"), B)
-        self._dgrad(a[1], w["dA3"], 0, ld("dA3"), w["dA2"], 0, ld("dA2"), B, aux=w["A2"], ld_aux=ld("A2"))
         self._wgrad(a[0], w["dA2"], 0, ld("dA2"), w["Y1"], 0, ld("Y1"), B)
-        self._dgrad(a[0], w["dA2"], 0, ld("dA2"), w["dY1"], 0, ld("dY1"), B, aux=w["Y1"], ld_aux=ld("Y1"))
-        # ---- backward: critic ----
         self._wgrad(c[2], w["dvalue"], 0, 8, w["C3"], 0, ld("C3"), B)
-        self._dgrad(c[2], w["dvalue"], 0, 8, w["dC3"], 0, ld("dC3"), B, aux=w["C3"], ld_aux=ld("C3"))
         self._wgrad(c[1], w["dC3"], 0, ld("dC3"), w["C2"], 0, ld("C2"), B)
-        self._dgrad(c[1], w["dC3"], 0, ld("dC3"), w["dC2"], 0, ld("dC2"), B, aux=w["C2"], ld_aux=ld("C2"))
         self._wgrad(c[0], w["dC2"], 0, ld("dC2"), w["Y1"], H, ld("Y1"), B)
-        self._dgrad(c[0], w["dC2"], 0, ld("dC2"), w["dY1"], H, ld("dY1"), B, aux=w["Y1"], aux_off=H, ld_aux=ld("Y1"))
-        # ---- shared first layer (actor | critic) and the latent gradient ----
         self._wgrad(ac.L_cat, w["dY1"], 0, ld("dY1"), w["Xac"], 0, ld("Xac"), B)
-        self._dgrad(ac.L_cat, w["dY1"], 0, ld("dY1"), w["dLat"], 0, ld("dLat"), B, col0=ac.num_obs, ncols=ac.latent_dim)
-        # ---- backward: encoder ----
         self._wgrad(e[2], w["dLat"], 0, ld("dLat"), w["H2"], 0, ld("H2"), B)
-        self._dgrad(e[2], w["dLat"], 0, ld("dLat"), w["dH2"], 0, ld("dH2"), B, aux=w["H2"], ld_aux=ld("H2"))
         self._wgrad(e[1], w["dH2"], 0, ld("dH2"), w["H1"], 0, ld("H1"), B)
-        self._dgrad(e[1], w["dH2"], 0, ld("dH2"), w["dH1"], 0, ld("dH1"), B, aux=w["H1"], ld_aux=ld("H1"))
         self._wgrad(e[0], w["dH1"], 0, ld("dH1"), w["Xp"], 0, ld("Xp"), B)
         # ---- data-parallel reduction of the policy gradients and loss statistics ----
         g_main, g_adapt = ac.flat_grad[:ac.n_main], ac.flat_grad[ac.n_main:]
@@ -194,15 +197,18 @@ class PPO:
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
         for _ in range(A.num_adaptation_module_substeps):
             ac.forward_encoder(B)
-            ac.forward_adaptation(B)
+            ac.forward_adaptation(B, save=True)
             stats_ad = self._stats_ad
             stats_ad.zero_()
             _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(w["Xac"]), ld("Xac"), ac.num_obs, B, inv_gb, P(w["dpred"]),
                                                P(stats_ad), stream))
+            if ac.use_chain:
+                ac._chain(("adaptation_backward",), chain.adaptation_backward_program).run(B)
+            else:
+                self._dgrad(d[2], w["dpred"], 0, 24, w["dD2"], 0, ld("dD2"), B, aux=w["D2"], ld_aux=ld("D2"))
+                self._dgrad(d[1], w["dD2"], 0, ld("dD2"), w["dD1"], 0, ld("dD1"), B, aux=w["D1"], ld_aux=ld("D1"))
             self._wgrad(d[2], w["dpred"], 0, 24, w["D2"], 0, ld("D2"), B)
-            self._dgrad(d[2], w["dpred"], 0, 24, w["dD2"], 0, ld("dD2"), B, aux=w["D2"], ld_aux=ld("D2"))
             self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
-            self._dgrad(d[1], w["dD2"], 0, ld("dD2"), w["dD1"], 0, ld("dD1"), B, aux=w["D1"], ld_aux=ld("D1"))
             self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
             if allreduce is not None:
                 allreduce(g_adapt)

@@ -18,6 +18,14 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=["chain", "layers"], autouse=True)
+def learner_path(request, monkeypatch):
+    """Every test runs on both learner paths: fused MLP chains (csrc/chain.cu, the default) and one
+    tcgen05 GEMM per layer (csrc/gemm_tc.cu)."""
+    monkeypatch.setenv("RL_USE_CHAIN", "1" if request.param == "chain" else "0")
+    return request.param
+
+
 def make_ac():
     from cases import learner_weights
     from rapid_locomotion_rl_b200.ppo import ActorCritic
