@@ -483,6 +483,12 @@ int rl_chain_create(const RlChainDesc* desc_host, void** handle);
 /* Runs the chain over rows [0, rows) (tiles of 128; rows may be any value up to the tensors' extent). */
 int rl_chain_run(void* handle, int32_t rows, void* stream);
 int rl_chain_destroy(void* handle);
+/* Profiling aid: record per-op clock64 stamps of CTA 0 during its tile iteration `tile_iteration` (< 0: off):
+ * 1 stamp per LOAD op, 2 per MMA op (waits passed, commits issued), 5 per EPI op (start, accumulator ready,
+ * registers loaded, elementwise done, end), in that order.  rl_chain_read_trace copies them to the host
+ * (synchronising) and returns how many stamps it wrote. */
+int rl_chain_trace(void* handle, int32_t tile_iteration);
+int64_t rl_chain_read_trace(void* handle, uint64_t* out_host, int64_t capacity);
 
 /* ---- PPO update support (mini_gym_learn/ppo/ppo.py:94-178) ---------------------------------- */
 

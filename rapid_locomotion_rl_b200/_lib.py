@@ -113,6 +113,8 @@ SIGNATURES = {
     "rl_chain_create": (C.c_int, [_P, _P]),
     "rl_chain_run": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_destroy": (C.c_int, [_P]),
+    "rl_chain_trace": (C.c_int, [_P, C.c_int32]),
+    "rl_chain_read_trace": (C.c_int64, [_P, _P, C.c_int64]),
     "rl_refresh_shadows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "rl_policy_sample": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

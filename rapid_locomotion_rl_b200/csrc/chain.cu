@@ -38,8 +38,11 @@ struct ChainParams {
   int n_loads, n_mmas, n_epis;
   int n_units, n_barriers;
   int num_tiles, rows;
+  unsigned long long* trace;      // profiling aid: clock64 stamps of CTA 0 in tile iteration trace_it (or null)
+  int trace_it;
   uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
 };
+constexpr int TRACE_MMA = 2, TRACE_EPI = 5;     // stamps per op (loads: 1)
 
 // mbarrier wait with a watchdog: a schedule bug must surface as a launch error, never as a hung GPU
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
@@ -123,6 +126,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           chain_wait(bars, wait, it);
           mbar_expect_tx(&bars[full_bar], expect);
           tma_load_2d(smem + smem_off, &p.tmaps[tensor], col0, row0 + (tile_rows ? m0 : 0), &bars[full_bar]);
+          if (p.trace && blockIdx.x == 0 && it == p.trace_it) p.trace[i] = clock64();
         }
       }
     }
@@ -142,6 +146,8 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           chain_wait(bars, wait0, it);
           chain_wait(bars, wait1, it);
           chain_wait(bars, wait2, it);
+          const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it;
+          if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
           tc_fence_after();
           const uint32_t idesc = instr_desc_bf16(128, (int)n, false, false);
           const uint32_t a_addr = smem_base + a_off, b_addr = smem_base + b_off;
@@ -153,6 +159,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (c0 != RL_CHAIN_NONE) mma_commit(&bars[c0]);
           if (c1 != RL_CHAIN_NONE) mma_commit(&bars[c1]);
           if (c2 != RL_CHAIN_NONE) mma_commit(&bars[c2]);
+          if (tr) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
         }
       }
     }
@@ -182,8 +189,12 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         const int store_col0 = (int)w2.x;
 
         // ---- accumulator columns -> registers ----
+        const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it && et == 0;
+        unsigned long long* tp = p.trace + p.n_loads + TRACE_MMA * p.n_mmas + TRACE_EPI * i;
+        if (tr) tp[0] = clock64();
         chain_wait(bars, wait_acc, it);
         tc_fence_after();
+        if (tr) tp[1] = clock64();
         float f[64];
         {
           uint32_t v[32];
@@ -207,6 +218,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (lane == 0) mbar_arrive(&bars[arrive_acc_free]);
         }
 
+        if (tr) tp[2] = clock64();
         // ---- elementwise ----
         if (mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32) {
           const float* bias = p.params + bias_off;
@@ -247,8 +259,10 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) if (j < ncols) dst[j] = f[j];
           }
+          if (tr) tp[3] = tp[4] = clock64();
           continue;
         }
+        if (tr) tp[3] = clock64();
 
         // ---- bf16 box for the next layer ----
         if (store_wait_pending >= 0) {          // a TMA store issued earlier may still be reading this box
@@ -297,6 +311,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
             }
           }
         }
+        if (tr) tp[4] = clock64();
       }
     }
     if (et == 0) bulk_wait_all();
@@ -310,6 +325,8 @@ struct ChainHandle {
   ChainParams params;
   void* dev_ops;
   size_t smem_bytes;
+  unsigned long long* trace;
+  size_t trace_len;
 };
 
 }  // namespace tc
@@ -384,8 +401,36 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
     if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: smem %zu B: %s", h->smem_bytes, cudaGetErrorString(err)); return RL_ERR_CUDA; }
     configured = h->smem_bytes;
   }
+  h->trace = nullptr;
+  h->trace_len = (size_t)d->n_loads + TRACE_MMA * (size_t)d->n_mmas + TRACE_EPI * (size_t)d->n_epis;
   *handle = h;
   return RL_OK;
+}
+
+// Profiling aid: per-op clock64 stamps of CTA 0 in tile iteration `tile_iteration` of the next runs
+// (1 stamp per LOAD op, 2 per MMA op: after the waits / after the commits, 5 per EPI op: start, accumulator
+// ready, registers loaded, elementwise done, end).  tile_iteration < 0 switches tracing off.
+extern "C" int rl_chain_trace(void* handle, int32_t tile_iteration) {
+  RL_REQUIRE(handle, RL_ERR_BAD_ARG, "rl_chain_trace: null handle");
+  ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
+  if (tile_iteration >= 0 && !h->trace) {
+    cudaError_t err = cudaMalloc(&h->trace, h->trace_len * 8);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "rl_chain_trace: cudaMalloc: %s", cudaGetErrorString(err));
+    cudaMemset(h->trace, 0, h->trace_len * 8);
+  }
+  h->params.trace = tile_iteration >= 0 ? h->trace : nullptr;
+  h->params.trace_it = tile_iteration;
+  return RL_OK;
+}
+// copies the stamps to `out_host` (capacity in stamps); returns the number of stamps or a negative error
+extern "C" int64_t rl_chain_read_trace(void* handle, uint64_t* out_host, int64_t capacity) {
+  RL_REQUIRE(handle && out_host, RL_ERR_BAD_ARG, "rl_chain_read_trace: null argument");
+  ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
+  RL_REQUIRE(h->trace, RL_ERR_BAD_ARG, "rl_chain_read_trace: tracing was never enabled");
+  const size_t n = (size_t)capacity < h->trace_len ? (size_t)capacity : h->trace_len;
+  cudaError_t err = cudaMemcpy(out_host, h->trace, n * 8, cudaMemcpyDeviceToHost);
+  RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "rl_chain_read_trace: %s", cudaGetErrorString(err));
+  return (int64_t)n;
 }
 
 extern "C" int rl_chain_run(void* handle, int32_t rows, void* stream) {
@@ -410,6 +455,7 @@ extern "C" int rl_chain_destroy(void* handle) {
   if (!handle) return RL_OK;
   ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
   cudaFree(h->dev_ops);
+  if (h->trace) cudaFree(h->trace);
   delete h;
   return RL_OK;
 }

@@ -224,6 +224,18 @@ class ActorCritic(nn.Module):
                  b_d3=off(d[2]))
         return T
 
+    def prepare_update_chains(self):
+        """Compiles every chain PPO.minibatch_step launches (rl_chain_create allocates and copies, which is
+        not allowed while a CUDA graph is being captured)."""
+        if not self.use_chain:
+            return
+        from . import chain
+        self._chain(("teacher", True, True, True), lambda T: chain.teacher_forward_program(T, save=True))
+        self._chain(("trunk_backward",), chain.trunk_backward_program)
+        self._chain(("encoder",), lambda T: chain.teacher_forward_program(T, save=False, trunk=False))
+        self._chain(("adaptation", True), lambda T: chain.adaptation_forward_program(T, save=True))
+        self._chain(("adaptation_backward",), chain.adaptation_backward_program)
+
     def _chain(self, key, build):
         prog = self._chains.get(key)
         if prog is None:

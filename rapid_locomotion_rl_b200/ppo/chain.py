@@ -358,6 +358,24 @@ class ChainProgram:
     def run(self, rows, stream=None):
         _lib.check(self._libref.rl_chain_run(self._handle, int(rows), _lib.current_stream() if stream is None else stream))
 
+    def trace(self, tile_iteration):
+        _lib.check(self._libref.rl_chain_trace(self._handle, int(tile_iteration)))
+
+    def read_trace(self):
+        """{"load": [t], "mma": [(t_waited, t_committed)], "epi": [(start, acc ready, regs, math, end)]} in
+        SM clock cycles relative to the first stamp (profiling aid)."""
+        n = len(self.loads) + 2 * len(self.mmas) + 5 * len(self.epis)
+        buf = (C.c_uint64 * n)()
+        got = self._libref.rl_chain_read_trace(self._handle, buf, n)
+        if got < 0:
+            _lib.check(int(got))
+        v = list(buf)
+        t0 = min(x for x in v if x)
+        v = [x - t0 if x else None for x in v]
+        nl, nm = len(self.loads), len(self.mmas)
+        return {"load": v[:nl], "mma": [tuple(v[nl + 2 * i: nl + 2 * i + 2]) for i in range(nm)],
+                "epi": [tuple(v[nl + 2 * nm + 5 * i: nl + 2 * nm + 5 * i + 5]) for i in range(len(self.epis))]}
+
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and getattr(self, "_libref", None) is not None:

@@ -241,6 +241,7 @@ class PPO:
         use_graph = self.use_cuda_graph and world == 1 and not getattr(self, "debug_keep_grad", False)
         if use_graph and (self._graph is None or self._graph_B != mb):
             self.actor_critic.workspace(mb, backward=True)        # allocate outside the capture
+            self.actor_critic.prepare_update_chains()
             self._idx_buf = torch.zeros(mb, dtype=torch.long, device=self.device)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
