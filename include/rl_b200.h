@@ -390,8 +390,9 @@ int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const
  *   - three warp roles execute three host-built op lists in order, synchronised only by mbarriers:
  *       LOAD ops (1 thread): one TMA box each (input rows, weight blocks, saved activations for ELU');
  *       MMA ops  (1 thread): up to four tcgen05.mma K16 steps of [128 x n] += A box * B box^T;
- *       EPI ops  (4 warps): tcgen05.ld of <= 64 accumulator columns -> bias / ELU / ELU' -> bf16 box for
- *                           the next layer (and a TMA store of the box for the backward / wgrad) or fp32 rows.
+ *       EPI ops  (2 x 4 warps): tcgen05.ld of <= 64 accumulator columns -> bias / ELU / ELU' -> bf16 box for
+ *                           the next layer (and a TMA store of the box for the backward / wgrad) or fp32 rows;
+ *                           two workers, each runs the ops tagged with its index, in order.
  *   The schedule (which layer's k-block meets which box when) is data: the op lists.  They are built and
  *   checked (deadlock freedom, buffer hazards, numerics on an emulator) on the host:
  *   rapid_locomotion_rl_b200/ppo/chain.py.
@@ -460,7 +461,9 @@ typedef struct RlChainEpiOp {
   uint32_t bias_off;                /* float offset into `params` of this op's first column bias */
   uint32_t dst_off, aux_off;
   int32_t store_col0;
-  uint32_t pad0, pad1, pad2;
+  uint8_t worker;                   /* which of the two epilogue warp groups executes this op */
+  uint8_t padb0, padb1, padb2;
+  uint32_t pad1, pad2;
 } RlChainEpiOp;
 
 typedef struct RlChainDesc {

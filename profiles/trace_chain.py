@@ -29,13 +29,14 @@ allv = [x for x in ld if x is not None] + [x for t in mm for x in t if x is not 
 print("span %d cycles" % (max(allv) - min(allv)))
 print("LOAD issue times:", " ".join(str(x) for x in ld))
 print("MMA  (waited, committed):")
-for i, (a, b) in enumerate(mm):
+for i, t in enumerate(mm):
     o = prog.mmas[i]
-    print("  %3d n=%3d col=%3d k=%d acc=%d waits=%s  %7d %7d" % (i, o["n"], o["tmem_col"], o["k_steps"], o["accumulate"],
-          [prog.bar_name[x.bar] for x in o["waits"]], a, b))
+    print("  %3d n=%3d col=%3d k=%d acc=%d waits=%s  %s" % (i, o["n"], o["tmem_col"], o["k_steps"], o["accumulate"],
+          [prog.bar_name[x.bar] for x in o["waits"]], " ".join("%7s" % x for x in t)))
 print("EPI  (start, acc ready, regs, math, end):")
+ordered = [o for o in prog.epis if o["worker"] == 0] + [o for o in prog.epis if o["worker"] == 1]
 for i, t in enumerate(ep):
-    o = prog.epis[i]
-    print("  %3d mode=%d ncols=%2d col=%3d store=%s  %s   [wait %d ld %d math %d write %d]" % (
-        i, o["mode"], o["ncols"], o["tmem_col"], o["store_tensor"] != 255, " ".join("%7d" % x for x in t),
+    o = ordered[i]
+    print("  %3d w%d mode=%d ncols=%2d col=%3d store=%s  %s   [wait %d ld %d math %d write %d]" % (
+        i, o["worker"], o["mode"], o["ncols"], o["tmem_col"], o["store_tensor"] != 255, " ".join("%7d" % x for x in t),
         t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3]))

@@ -10,39 +10,56 @@
 //   warp 0 lane 0     LOAD ops: mbarrier wait (unit free) -> expect_tx -> cp.async.bulk.tensor.2d
 //   warp 1 lane 0     MMA ops : waits (stage full / box ready / accumulator free) -> <= 4 tcgen05.mma
 //                               (M128 x n x K16, kind::f16, fp32 in TMEM) -> tcgen05.commit on <= 3 barriers
-//   warps 2-5         EPI ops : wait (accumulator full) -> tcgen05.ld -> bias / ELU / ELU' -> swizzled bf16
+//   warps 2-5, 6-9    EPI ops : two workers, each runs its own list: wait (accumulator full) -> tcgen05.ld -> bias / ELU / ELU' -> swizzled bf16
 //                               box in shared memory (the next layer's A operand) -> TMA store of the box
 //                               (saved activation / gradient for wgrad) or fp32 output rows
-// Shared memory = n_units x 16 KB (activation boxes and ring stages, all [rows x 64 bf16] tiles in the
-// 128 B-swizzled K-major layout shared by TMA and the UMMA descriptors) + 64 mbarriers.
+// Shared memory = n_units x 16 KB dynamic (activation boxes and ring stages, all [rows x 64 bf16] tiles in the
+// 128 B-swizzled K-major layout shared by TMA and the UMMA descriptors) + 3 KB static (64 mbarriers, the
+// per-warp bias staging rows): 14 units use exactly the 227 KB a CTA can have.
 // The host side (ppo/chain.py) builds the op lists and proves them on an emulator (deadlock freedom,
 // buffer hazards, parity bookkeeping, numerics) before anything reaches the GPU.
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "tc_common.cuh"
 
 namespace rl {
 namespace tc {
 
-constexpr int CHAIN_THREADS = 192;
+constexpr int CHAIN_THREADS = 320;          // warp 0 LOAD, warp 1 MMA, warps 2-5 / 6-9 the two epilogue workers
 constexpr int UNIT_BYTES = 16384;
+constexpr int FIXED_SMEM = 3072;            // static: 64 mbarriers | tmem slot | per-warp bias staging (8 x 256 B)
+constexpr int TRACE_MMA = 8, TRACE_EPI = 5; // stamps per op (loads: 1)
+
+// device-side op formats (built by rl_chain_create from the ABI structs)
+struct DevMmaOp {            // 32 B
+  uint32_t a_lo, b_lo;       // low descriptor words without the shared-memory window base: (off >> 4) | LBO field
+  uint32_t idesc;
+  uint16_t tmem_col;
+  uint8_t k_steps, accumulate;
+  uint16_t wait0, wait1, wait2;
+  uint8_t commit0, commit1, commit2, pad0;
+  uint16_t pad1;
+  uint32_t pad2;
+};
+static_assert(sizeof(DevMmaOp) == 32, "DevMmaOp layout");
 
 struct ChainParams {
   CUtensorMap tmaps[RL_CHAIN_MAX_TENSORS];
   const RlChainLoadOp* loads;
-  const RlChainMmaOp* mmas;
-  const RlChainEpiOp* epis;
+  const DevMmaOp* mmas;
+  const RlChainEpiOp* epis[2];    // per epilogue worker
   const float* params;
   float* outputs[RL_CHAIN_MAX_OUTPUTS];
-  int n_loads, n_mmas, n_epis;
+  int n_loads, n_mmas, n_epis[2];
   int n_units, n_barriers;
   int num_tiles, rows;
   unsigned long long* trace;      // profiling aid: clock64 stamps of CTA 0 in tile iteration trace_it (or null)
   int trace_it;
   uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
 };
-constexpr int TRACE_MMA = 2, TRACE_EPI = 5;     // stamps per op (loads: 1)
 
 // mbarrier wait with a watchdog: a schedule bug must surface as a launch error, never as a hung GPU
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
@@ -55,21 +72,27 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __noinline__ void chain_timeout(uint32_t id, uint32_t parity, int it) {
+  printf("mlp_chain_kernel: wait on barrier %u (parity %u, tile iteration %d) timed out, block %d thread %d\n", id, parity, it,
+         (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void chain_wait(uint64_t* bars, uint32_t spec, int it) {
   const uint32_t id = spec & 0xFFu;
   if (id == RL_CHAIN_NONE) return;
   const uint32_t parity = ((spec >> 8) ^ ((spec >> 9) & (uint32_t)it)) & 1u;
   uint32_t spins = 0;
   while (!mbar_try(&bars[id], parity)) {
-    if (++spins > (1u << 24)) {
-      printf("mlp_chain_kernel: wait on barrier %u (parity %u, tile iteration %d) timed out, block %d thread %d\n", id, parity, it,
-             (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 24)) chain_timeout(id, parity, it);
   }
 }
 
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : (__expf(x) - 1.f); }
+// ELU on the fp32 accumulator: exp through ex2.approx.ftz (MUFU), 4 instructions per element
+__device__ __forceinline__ float elu1(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.f;
+}
 
 template <int N>
 __device__ __forceinline__ void bulk_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -90,15 +113,28 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // byte offset of the 16 B chunk holding columns [8c, 8c+8) of row r inside a 128 B-swizzled [rows x 64] box
 __device__ __forceinline__ uint32_t sw_chunk(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+__device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  // descriptor high word: SBO = 1024 B (8-row group pitch), version 1, SWIZZLE_128B
+  constexpr uint32_t HI = 64u | (1u << 14) | (2u << 29);
+  const uint64_t da = ((uint64_t)HI << 32) | a_lo, db = ((uint64_t)HI << 32) | b_lo;
+  mma_bf16_ss(tmem_d, da, db, idesc, accumulate != 0);
+}
+
 __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 mlp_chain_kernel(const __grid_constant__ ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_units * UNIT_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + RL_CHAIN_MAX_BARRIERS);
+  __shared__ __align__(1024) uint8_t s_fixed[FIXED_SMEM];
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_fixed);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_fixed + 512);
+  float* s_bias = reinterpret_cast<float*>(s_fixed + 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
 
   if (threadIdx.x == 0) {
+    if (smem_base & 1023u) {
+      printf("mlp_chain_kernel: dynamic shared memory is not 1024 B aligned (0x%x)\n", smem_base);
+      __trap();
+    }
     for (int b = 0; b < p.n_barriers; ++b) mbar_init(&bars[b], p.barrier_count[b]);
     mbar_fence_init();
   }
@@ -107,17 +143,18 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
     // ===================================== LOAD role =====================================
-    if (lane == 0) {
+    if (lane == 0 && p.n_loads > 0) {
+      const uint4* ops = reinterpret_cast<const uint4*>(p.loads);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int m0 = tile * 128;
+        uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1);
         for (int i = 0; i < p.n_loads; ++i) {
-          const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p.loads + i));
-          const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p.loads + i) + 1);
+          const uint4 w0 = n0, w1 = n1;
+          if (i + 1 < p.n_loads) { n0 = __ldg(ops + 2 * (i + 1)); n1 = __ldg(ops + 2 * (i + 1) + 1); }
           const uint32_t wait = w0.x & 0xFFFFu, full_bar = (w0.x >> 16) & 0xFFu, tensor = w0.x >> 24;
           const uint32_t smem_off = w0.y;
           const int col0 = (int)w0.z, row0 = (int)w0.w;
@@ -132,52 +169,60 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     }
   } else if (warp == 1) {
     // ===================================== MMA role ======================================
-    if (lane == 0) {
+    if (lane == 0 && p.n_mmas > 0) {
+      const uint4* ops = reinterpret_cast<const uint4*>(p.mmas);
+      const uint32_t base16 = smem_base >> 4;
+      const uint32_t bar0 = smem_u32(bars);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1);
         for (int i = 0; i < p.n_mmas; ++i) {
-          const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p.mmas + i));
-          const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p.mmas + i) + 1);
-          const uint32_t a_off = w0.x, b_off = w0.y;
-          const uint32_t n = w0.z & 0xFFFFu, tmem_col = w0.z >> 16;
-          const uint32_t k_steps = w0.w & 0xFFu, accumulate = (w0.w >> 8) & 0xFFu, wait0 = w0.w >> 16;
-          const uint32_t wait1 = w1.x & 0xFFFFu, wait2 = w1.x >> 16;
-          const uint32_t c0 = w1.y & 0xFFu, c1 = (w1.y >> 8) & 0xFFu, c2 = (w1.y >> 16) & 0xFFu;
+          const uint4 w0 = n0, w1 = n1;
+          if (i + 1 < p.n_mmas) { n0 = __ldg(ops + 2 * (i + 1)); n1 = __ldg(ops + 2 * (i + 1) + 1); }
+          const uint32_t a_lo = w0.x + base16, b_lo = w0.y + base16, idesc = w0.z;
+          const uint32_t tmem_d = tmem_base + (w0.w & 0xFFFFu);
+          const uint32_t k_steps = (w0.w >> 16) & 0xFFu, accumulate = w0.w >> 24;
+          const uint32_t wait0 = w1.x & 0xFFFFu, wait1 = w1.x >> 16, wait2 = w1.y & 0xFFFFu;
+          const uint32_t c0 = (w1.y >> 16) & 0xFFu, c1 = w1.y >> 24, c2 = w1.z & 0xFFu;
           chain_wait(bars, wait0, it);
           chain_wait(bars, wait1, it);
           chain_wait(bars, wait2, it);
           const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it;
           if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
           tc_fence_after();
-          const uint32_t idesc = instr_desc_bf16(128, (int)n, false, false);
-          const uint32_t a_addr = smem_base + a_off, b_addr = smem_base + b_off;
-          for (uint32_t kk = 0; kk < k_steps; ++kk) {
-            const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t db = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            mma_bf16_ss(tmem_base + tmem_col, da, db, idesc, (accumulate | kk) != 0);
-          }
-          if (c0 != RL_CHAIN_NONE) mma_commit(&bars[c0]);
-          if (c1 != RL_CHAIN_NONE) mma_commit(&bars[c1]);
-          if (c2 != RL_CHAIN_NONE) mma_commit(&bars[c2]);
-          if (tr) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
+          mma_issue(tmem_d, a_lo, b_lo, idesc, accumulate);                     // K16 step 0
+          if (k_steps > 1) mma_issue(tmem_d, a_lo + 2, b_lo + 2, idesc, 1);     // +32 B per step
+          if (k_steps > 2) mma_issue(tmem_d, a_lo + 4, b_lo + 4, idesc, 1);
+          if (k_steps > 3) mma_issue(tmem_d, a_lo + 6, b_lo + 6, idesc, 1);
+          if (tr) p.trace[p.n_loads + TRACE_MMA * i + 4] = clock64();
+          if (c0 != RL_CHAIN_NONE) mma_commit(reinterpret_cast<uint64_t*>(0) + 0, bar0 + 8 * c0);
+          if (c1 != RL_CHAIN_NONE) mma_commit(reinterpret_cast<uint64_t*>(0) + 0, bar0 + 8 * c1);
+          if (c2 != RL_CHAIN_NONE) mma_commit(reinterpret_cast<uint64_t*>(0) + 0, bar0 + 8 * c2);
+          if (tr) p.trace[p.n_loads + TRACE_MMA * i + 7] = clock64();
         }
       }
     }
   } else {
-    // ===================================== EPILOGUE role =================================
+    // ===================================== EPILOGUE workers ==============================
+    const int worker = (warp - 2) >> 2;          // warps 2-5: worker 0, warps 6-9: worker 1
     const int g = warp & 3;                      // TMEM lane quarter this warp may read
     const int lr = 32 * g + lane;                // row within the tile
-    const int et = threadIdx.x - 64;             // 0..127
+    const int et = threadIdx.x - 64 - 128 * worker;     // 0..127 within the worker
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * g) << 16);
+    float* my_bias = s_bias + (warp - 2) * 64;
+    const int n_ops = p.n_epis[worker];
+    const uint4* ops = reinterpret_cast<const uint4*>(p.epis[worker]);
+    const int bar_id = 1 + worker;
+    const int trace_base = p.n_loads + TRACE_MMA * p.n_mmas + (worker ? TRACE_EPI * p.n_epis[0] : 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.num_tiles && n_ops > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
       const int r = m0 + lr;
+      uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1), n2 = __ldg(ops + 2);
 #pragma unroll 1
-      for (int i = 0; i < p.n_epis; ++i) {
-        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(p.epis + i));
-        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(p.epis + i) + 1);
-        const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(p.epis + i) + 2);
+      for (int i = 0; i < n_ops; ++i) {
+        const uint4 w0 = n0, w1 = n1, w2 = n2;
+        if (i + 1 < n_ops) { n0 = __ldg(ops + 3 * (i + 1)); n1 = __ldg(ops + 3 * (i + 1) + 1); n2 = __ldg(ops + 3 * (i + 1) + 2); }
         const uint32_t wait_acc = w0.x & 0xFFFFu, wait_dst = w0.x >> 16, wait_aux = w0.y & 0xFFFFu;
         const uint32_t arrive_acc_free = (w0.y >> 16) & 0xFFu, arrive_dst_ready = w0.y >> 24;
         const uint32_t release_aux = w0.z & 0xFFu, mode = (w0.z >> 8) & 0xFFu;
@@ -187,11 +232,19 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         const uint32_t release_after_store = w1.x & 0xFFu, out_id = (w1.x >> 8) & 0xFFu, out_ld = w1.x >> 16;
         const uint32_t bias_off = w1.y, dst_off = w1.z, aux_off = w1.w;
         const int store_col0 = (int)w2.x;
+        const bool has_bias = mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32;
 
-        // ---- accumulator columns -> registers ----
         const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it && et == 0;
-        unsigned long long* tp = p.trace + p.n_loads + TRACE_MMA * p.n_mmas + TRACE_EPI * i;
+        unsigned long long* tp = p.trace + trace_base + TRACE_EPI * i;
         if (tr) tp[0] = clock64();
+        // bias of this op's columns: two coalesced loads per warp, issued before the accumulator wait
+        float b_lo = 0.f, b_hi = 0.f;
+        if (has_bias) {
+          const float* bias = p.params + bias_off;
+          if (lane < ncols) b_lo = __ldg(bias + lane);
+          if (lane + 32 < ncols) b_hi = __ldg(bias + 32 + lane);
+        }
+        // ---- accumulator columns -> registers ----
         chain_wait(bars, wait_acc, it);
         tc_fence_after();
         if (tr) tp[1] = clock64();
@@ -217,20 +270,18 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[arrive_acc_free]);
         }
-
         if (tr) tp[2] = clock64();
+
         // ---- elementwise ----
-        if (mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32) {
-          const float* bias = p.params + bias_off;
-          if (ncols == 64 && (bias_off & 3u) == 0) {
+        if (has_bias) {
+          __syncwarp();                            // the previous op's broadcast reads are done
+          my_bias[lane] = b_lo;
+          my_bias[32 + lane] = b_hi;
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
-              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) if (j < ncols) f[j] += __ldg(bias + j);
+          for (int j = 0; j < 64; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(my_bias + j);
+            f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
           }
           if (mode == RL_CHAIN_EPI_BIAS_ELU) {
 #pragma unroll
@@ -257,7 +308,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (r < p.rows) {
             float* dst = p.outputs[out_id] + (size_t)r * out_ld;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) if (j < ncols) dst[j] = f[j];
+            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = f[j];
           }
           if (tr) tp[3] = tp[4] = clock64();
           continue;
@@ -267,7 +318,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         // ---- bf16 box for the next layer ----
         if (store_wait_pending >= 0) {          // a TMA store issued earlier may still be reading this box
           if (et == 0) bulk_wait_read_dyn(store_wait_pending);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
         chain_wait(bars, wait_dst, it);
         uint8_t* box = smem + dst_off;
@@ -282,10 +333,10 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
             *reinterpret_cast<uint4*>(box + sw_chunk(lr, c)) = pk;
           }
         } else {
-          // partial box: `ncols` columns starting at dst_col0 (latent merged next to the observations,
-          // or a narrow gradient); columns outside the range keep their content
+          // partial box: `ncols` (<= 32) columns starting at dst_col0 (latent merged next to the observations,
+          // or a narrow layer); columns outside the range keep their content
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
+          for (int j = 0; j < 32; ++j) {
             if (j < ncols) {
               const int col = dst_col0 + j;
               *reinterpret_cast<__nv_bfloat16*>(box + sw_chunk(lr, col >> 3) + (col & 7) * 2) = __float2bfloat16(f[j]);
@@ -298,7 +349,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (lane == 0) mbar_arrive(&bars[arrive_dst_ready]);
         }
         if (store_tensor != RL_CHAIN_NONE || release_aux != RL_CHAIN_NONE) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (et == 0) {
             if (release_aux != RL_CHAIN_NONE) mbar_arrive(&bars[release_aux]);
             if (store_tensor != RL_CHAIN_NONE) {
@@ -356,8 +407,14 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
                (o.a_off & 1023u) == 0 && (o.b_off & 1023u) == 0 && o.a_off + UNIT_BYTES <= limit && o.b_off + (uint32_t)o.n * 128 <= limit,
                RL_ERR_BAD_ARG, "rl_chain_create: mma op %d malformed", i);
   }
+  int n_epi_w[2] = {0, 0};
   for (int i = 0; i < d->n_epis; ++i) {
     const RlChainEpiOp& o = d->epis_host[i];
+    RL_REQUIRE(o.worker < 2, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d worker", i);
+    RL_REQUIRE(o.ncols <= 32 || (o.dst_col0 == 0 && o.ncols == 64) || o.mode == RL_CHAIN_EPI_BIAS_F32, RL_ERR_BAD_ARG,
+               "rl_chain_create: epilogue op %d: partial boxes hold <= 32 columns", i);
+    RL_REQUIRE(o.mode != RL_CHAIN_EPI_BIAS_F32 || o.ncols <= 32, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d: <= 32 output columns", i);
+    ++n_epi_w[o.worker];
     RL_REQUIRE(o.ncols >= 1 && o.ncols <= 64 && o.tmem_col + (o.ncols > 32 ? 64 : 32) <= 512 && o.mode <= RL_CHAIN_EPI_PLAIN, RL_ERR_BAD_ARG,
                "rl_chain_create: epilogue op %d malformed", i);
     if (o.mode == RL_CHAIN_EPI_BIAS_F32)
@@ -377,24 +434,43 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
       return rc;
     }
   }
-  const size_t nl = (size_t)d->n_loads * sizeof(RlChainLoadOp), nm = (size_t)d->n_mmas * sizeof(RlChainMmaOp),
+  // device formats: MMA ops with precomputed descriptor words, epilogue ops split per worker
+  const size_t nl = (size_t)d->n_loads * sizeof(RlChainLoadOp), nm = (size_t)d->n_mmas * sizeof(DevMmaOp),
                ne = (size_t)d->n_epis * sizeof(RlChainEpiOp);
-  cudaError_t err = cudaMalloc(&h->dev_ops, nl + nm + ne + 48);
+  std::vector<uint8_t> blob(nl + nm + ne + 64, 0);
+  if (nl) memcpy(blob.data(), d->loads_host, nl);
+  DevMmaOp* dm = reinterpret_cast<DevMmaOp*>(blob.data() + nl);
+  for (int i = 0; i < d->n_mmas; ++i) {
+    const RlChainMmaOp& o = d->mmas_host[i];
+    DevMmaOp& x = dm[i];
+    x.a_lo = (o.a_off >> 4) | (1u << 16);        // LBO field = 1 (unused for swizzled K-major)
+    x.b_lo = (o.b_off >> 4) | (1u << 16);
+    x.idesc = instr_desc_bf16(128, o.n, false, false);
+    x.tmem_col = o.tmem_col; x.k_steps = o.k_steps; x.accumulate = o.accumulate;
+    x.wait0 = o.wait0; x.wait1 = o.wait1; x.wait2 = o.wait2;
+    x.commit0 = o.commit0; x.commit1 = o.commit1; x.commit2 = o.commit2;
+  }
+  RlChainEpiOp* de = reinterpret_cast<RlChainEpiOp*>(blob.data() + nl + nm);
+  {
+    int pos[2] = {0, n_epi_w[0]};
+    for (int i = 0; i < d->n_epis; ++i) de[pos[d->epis_host[i].worker]++] = d->epis_host[i];
+  }
+  cudaError_t err = cudaMalloc(&h->dev_ops, blob.size());
   if (err != cudaSuccess) { delete h; set_error("rl_chain_create: cudaMalloc: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
   uint8_t* base = reinterpret_cast<uint8_t*>(h->dev_ops);
-  err = cudaMemcpy(base, d->loads_host, nl, cudaMemcpyHostToDevice);
-  if (err == cudaSuccess) err = cudaMemcpy(base + nl, d->mmas_host, nm, cudaMemcpyHostToDevice);
-  if (err == cudaSuccess) err = cudaMemcpy(base + nl + nm, d->epis_host, ne, cudaMemcpyHostToDevice);
+  err = cudaMemcpy(base, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: cudaMemcpy: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
   h->params.loads = reinterpret_cast<const RlChainLoadOp*>(base);
-  h->params.mmas = reinterpret_cast<const RlChainMmaOp*>(base + nl);
-  h->params.epis = reinterpret_cast<const RlChainEpiOp*>(base + nl + nm);
+  h->params.mmas = reinterpret_cast<const DevMmaOp*>(base + nl);
+  h->params.epis[0] = reinterpret_cast<const RlChainEpiOp*>(base + nl + nm);
+  h->params.epis[1] = h->params.epis[0] + n_epi_w[0];
   h->params.params = d->params;
   for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->params.outputs[i] = d->outputs[i];
-  h->params.n_loads = d->n_loads; h->params.n_mmas = d->n_mmas; h->params.n_epis = d->n_epis;
+  h->params.n_loads = d->n_loads; h->params.n_mmas = d->n_mmas;
+  h->params.n_epis[0] = n_epi_w[0]; h->params.n_epis[1] = n_epi_w[1];
   h->params.n_units = d->n_units; h->params.n_barriers = d->n_barriers;
   memcpy(h->params.barrier_count, d->barrier_count, RL_CHAIN_MAX_BARRIERS);
-  h->smem_bytes = (size_t)d->n_units * UNIT_BYTES + RL_CHAIN_MAX_BARRIERS * 8 + 16 + 1024;
+  h->smem_bytes = (size_t)d->n_units * UNIT_BYTES;      // dynamic part; FIXED_SMEM bytes are static
   static size_t configured = 0;
   if (h->smem_bytes > configured) {
     err = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
@@ -408,7 +484,7 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
 }
 
 // Profiling aid: per-op clock64 stamps of CTA 0 in tile iteration `tile_iteration` of the next runs
-// (1 stamp per LOAD op, 2 per MMA op: after the waits / after the commits, 5 per EPI op: start, accumulator
+// (1 stamp per LOAD op, 8 per MMA op: waits passed, after each K16 step (4), after each commit (3), 5 per EPI op: start, accumulator
 // ready, registers loaded, elementwise done, end).  tile_iteration < 0 switches tracing off.
 extern "C" int rl_chain_trace(void* handle, int32_t tile_iteration) {
   RL_REQUIRE(handle, RL_ERR_BAD_ARG, "rl_chain_trace: null handle");

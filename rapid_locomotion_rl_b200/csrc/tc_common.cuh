@@ -60,6 +60,9 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mma_commit(uint64_t*, uint32_t bar_smem_addr) {      // barrier given by its shared address
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
+}
 // 32 lanes x 32 columns of 32-bit: thread i of the warp gets row (lane base + i), columns c..c+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

@@ -52,18 +52,22 @@ class BoxUse:
 
 
 class AccUse:
-    __slots__ = ("region", "col", "full", "free_bar", "wait_free", "started", "closed")
+    __slots__ = ("region", "col", "full", "free_bar", "wait_free", "started", "closed", "last_op")
 
     def __init__(self, region, col, free_bar, wait_free):
         self.region, self.col, self.free_bar, self.wait_free = region, col, free_bar, wait_free
         self.full, self.started, self.closed = None, False, False
+        self.last_op = {}               # epilogue worker -> its last op on this accumulator use
 
 
 class ChainProgram:
     """Builder + container of one chain program."""
 
-    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain"):
-        """Shared-memory units: [inputs | pool | stages]; `regions`: {name: (first tmem column, width)}."""
+    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None):
+        """Shared-memory units: [inputs | pool | stages]; `regions`: {name: (first tmem column, width)};
+        `region_worker`: regions whose accumulator uses are read by ONE epilogue op -> the worker that owns
+        them (a waiter must see every phase of a barrier, so such a region cannot change hands); the other
+        regions are read by both workers, chunk c by worker c % 2."""
         self.name = name
         self.n_inputs, self.n_pool, self.n_stages = n_inputs, n_pool, n_stages
         self.n_units = n_inputs + n_pool + n_stages
@@ -79,7 +83,10 @@ class ChainProgram:
         # resources
         self.pool_units = [n_inputs + i for i in range(n_pool)]
         self.stage_units = [n_inputs + n_pool + i for i in range(n_stages)]
-        self.stage_full = [self._bar(1, "stage%d.full" % i) for i in range(n_stages)]
+        # a barrier must have ONE waiting agent that sees every phase (waits name a phase only by its parity):
+        # each stage has one "full" barrier per consumer role and the producer signals the one of the role
+        # that will read this particular landing
+        self.stage_full = {"mma": [self._bar(1, "stage%d.full.mma" % i) for i in range(n_stages)]}
         self.stage_empty = [self._bar(1, "stage%d.empty" % i) for i in range(n_stages)]
         self.stage_uses = [0] * n_stages
         self.ring_pos = 0
@@ -92,10 +99,14 @@ class ChainProgram:
         self.acc_uses = {r: 0 for r in regions}
         self.acc_open = {r: None for r in regions}
         self.input_full, self.input_free, self.input_loads = {}, {}, {}
-        self.waited = {"load": set(), "mma": set(), "epi": set()}
-        # TMA-store bookkeeping (epilogue thread 0 commits one bulk group per store)
-        self.n_stores = 0
-        self.unit_last_store = {}        # unit -> store index within the tile
+        self.waited = {"load": set(), "mma": set(), "epi0": set(), "epi1": set()}
+        # two epilogue workers (4 warps each) take the EPI ops alternately; a pool unit always belongs to the
+        # worker of its parity, so the TMA-store bookkeeping (one bulk group per store, committed by the
+        # worker's first thread) stays within one thread
+        self.region_worker = dict(region_worker or {"C0": 0, "C1": 1})
+        self.n_stores = [0, 0]
+        self.unit_last_store = {}        # unit -> store index within the tile (of the unit's worker)
+        self.acc_participants = {r: set() for r in regions}
         self._finalized = False
 
     # ---------------------------------------------------------------------------------------------
@@ -148,17 +159,25 @@ class ChainProgram:
         return use
 
     # ---- ring stages ------------------------------------------------------------------------------
-    def load_stage(self, tensor, col0, row0, tile_rows=False):
+    def load_stage(self, tensor, col0, row0, tile_rows=False, consumer="mma"):
+        """One TMA box into the next ring stage; `consumer`: the role that will wait for it ("mma", "epi0", "epi1")."""
         t, box_rows = self.tensors[tensor]
         s = self.ring_pos % self.n_stages
         self.ring_pos += 1
         wait = _Wait(self.stage_empty[s], self.stage_uses[s])
         self.stage_uses[s] += 1
-        ordn = self._signal(self.stage_full[s])
+        if consumer not in self.stage_full:
+            self.stage_full[consumer] = [self._bar(1, "stage%d.full.%s" % (i, consumer)) for i in range(self.n_stages)]
+        full = self.stage_full[consumer][s]
+        ordn = self._signal(full)
         off = self.stage_units[s] * UNIT
-        self.loads.append(dict(wait=wait, full_bar=self.stage_full[s], tensor=tensor, smem_off=off, col0=col0, row0=row0,
+        self.loads.append(dict(wait=wait, full_bar=full, tensor=tensor, smem_off=off, col0=col0, row0=row0,
                                bytes=box_rows * 128, tile_rows=int(tile_rows)))
-        return StageUse(s, off, _Wait(self.stage_full[s], ordn), self.stage_empty[s])
+        return StageUse(s, off, _Wait(full, ordn), self.stage_empty[s])
+
+    def worker_for(self, acc, col):
+        """Epilogue worker that reads accumulator columns [col, col + 64) of this use."""
+        return self.region_worker[acc.region] if acc.region in self.region_worker else (col // 64) % 2
 
     # ---- tensor-memory accumulators -----------------------------------------------------------------
     def acc(self, region):
@@ -199,81 +218,84 @@ class ChainProgram:
                               accumulate=int(accumulate), waits=waits, commits=commits))
 
     # ---- epilogue ---------------------------------------------------------------------------------------
-    def _epi_common(self, acc, col, ncols, mode, bias_off, first, last):
+    def _epi_common(self, acc, col, ncols, mode, bias_off, last):
         assert acc.full is not None, "accumulator has no closing MMA yet"
-        op = dict(wait_acc=self._w("epi", acc.full) if first else None, wait_dst=None, wait_aux=None, arrive_acc_free=NONE,
+        w = self.worker_for(acc, col)
+        assert acc.region not in self.region_worker or not acc.last_op, "region %s is single-op" % acc.region
+        op = dict(worker=w, wait_acc=self._w("epi%d" % w, acc.full), wait_dst=None, wait_aux=None, arrive_acc_free=NONE,
                   arrive_dst_ready=NONE, release_aux=NONE, mode=mode, ncols=ncols, dst_col0=0, tmem_col=acc.col + col,
                   store_tensor=NONE, store_wait_pending=-1, release_after_store=NONE, out_id=NONE, out_ld=0,
                   bias_off=bias_off, dst_off=0, aux_off=0, store_col0=0)
+        acc.last_op[w] = op
         if last:
-            op["arrive_acc_free"] = acc.free_bar
+            # every participating worker arrives (4 warps each) after ITS last read of this accumulator use
+            for o in acc.last_op.values():
+                o["arrive_acc_free"] = acc.free_bar
+            self.acc_participants[acc.region].add(len(acc.last_op))
             self._signal(acc.free_bar)
             acc.closed = True
         return op
 
-    def epi_box(self, acc, col, mode, bias_off=0, ncols=64, aux=None, store=None, first=False, last=False, has_reader=True):
-        """Accumulator columns [col, col+ncols) -> bf16 box in the next pool unit (round robin)."""
-        op = self._epi_common(acc, col, ncols, mode, bias_off, first, last)
+    def epi_box(self, acc, col, mode, bias_off=0, ncols=64, aux=None, store=None, last=False, has_reader=True):
+        """Accumulator columns [col, col+ncols) -> bf16 box in the next free pool unit of the worker's parity."""
+        op = self._epi_common(acc, col, ncols, mode, bias_off, last)
+        w = op["worker"]
         # next unit, in round-robin order, whose content already has its releasing reader in the program
         for probe in range(self.n_pool):
             i = (self.pool_pos + probe) % self.n_pool
             prev = self.pool_last[i]
-            if prev is None or prev.released or not prev.has_reader:
+            if i % 2 == w and (prev is None or prev.released or not prev.has_reader):
                 break
         else:
-            raise AssertionError("%s: all %d pool units hold live boxes" % (self.name, self.n_pool))
+            raise AssertionError("%s: every pool unit of worker %d holds a live box" % (self.name, w))
         self.pool_pos = i + 1
         unit = self.pool_units[i]
         # frees emitted so far for this unit == completions the writer must have seen
-        op["wait_dst"] = self._w("epi", _Wait(self.pool_free[i], self.bar_phases[self.pool_free[i]]))
+        op["wait_dst"] = self._w("epi%d" % w, _Wait(self.pool_free[i], self.bar_phases[self.pool_free[i]]))
         ordn = self._signal(self.pool_ready[i])
         op["arrive_dst_ready"] = self.pool_ready[i]
         op["dst_off"] = unit * UNIT
-        self._store_hazard(op, unit)
+        # the unit may still be read by a TMA store this worker issued earlier (this tile or the previous one)
+        op["_store_dep"] = (self.unit_last_store.get(unit), self.n_stores[w])
+        op["_unit"] = unit
         if mode == EPI_DELU:
             assert aux is not None and not aux.released
-            op["wait_aux"] = self._w("epi", aux.full)
+            assert "epi%d" % w in self.bar_name[aux.full.bar], "aux box was loaded for another consumer"
+            op["wait_aux"] = self._w("epi%d" % w, aux.full)
             op["aux_off"] = aux.off
             op["release_aux"] = aux.empty_bar
             aux.released = True
             self._signal(aux.empty_bar)
         if store is not None:
             op["store_tensor"], op["store_col0"] = store
-            self.unit_last_store[unit] = self.n_stores
-            self.n_stores += 1
+            self.unit_last_store[unit] = self.n_stores[w]
+            self.n_stores[w] += 1
         use = BoxUse(unit, unit * UNIT, _Wait(self.pool_ready[i], ordn), self.pool_free[i])
         use.has_reader = has_reader
         self.pool_last[i] = use
         self.epis.append(op)
         return use
 
-    def _store_hazard(self, op, unit):
-        """The unit may still be read by a TMA store issued earlier (this tile or the previous one)."""
-        if unit in self.unit_last_store:
-            op["_store_dep"] = ("same", self.unit_last_store[unit], self.n_stores)
-        else:
-            op["_store_dep"] = ("prev", None, self.n_stores)     # resolved in finalize (needs stores per tile)
-        op["_unit"] = unit
-
     def epi_merge(self, acc, col, ncols, mode, bias_off, box, dst_col0, ready_bar_count4, store=None, release_after_store=NONE,
-                  first=True, last=True):
+                  last=True):
         """Accumulator columns -> `ncols` columns at dst_col0 of an already loaded input box (the encoder latent
         next to the observations).  Waits for the box's TMA load, signals `ready_bar_count4`."""
-        op = self._epi_common(acc, col, ncols, mode, bias_off, first, last)
-        op["wait_dst"] = self._w("epi", box.ready)
+        op = self._epi_common(acc, col, ncols, mode, bias_off, last)
+        w = op["worker"]
+        op["wait_dst"] = self._w("epi%d" % w, box.ready)
         op["dst_off"], op["dst_col0"] = box.off, dst_col0
         ordn = self._signal(ready_bar_count4)
         op["arrive_dst_ready"] = ready_bar_count4
         if store is not None:
             op["store_tensor"], op["store_col0"] = store
-            self.n_stores += 1
+            self.n_stores[w] += 1
             op["release_after_store"] = release_after_store
         self.epis.append(op)
         merged = BoxUse(box.unit, box.off, _Wait(ready_bar_count4, ordn), box.free_bar)
         return merged
 
-    def epi_out(self, acc, col, ncols, bias_off, out_id, first=True, last=True):
-        op = self._epi_common(acc, col, ncols, EPI_BIAS_F32, bias_off, first, last)
+    def epi_out(self, acc, col, ncols, bias_off, out_id, last=True):
+        op = self._epi_common(acc, col, ncols, EPI_BIAS_F32, bias_off, last)
         op["out_id"], op["out_ld"] = out_id, self.outputs[out_id].stride(0)
         self.epis.append(op)
 
@@ -285,17 +307,20 @@ class ChainProgram:
             assert self.bar_phases[self.stage_empty[s]] == self.stage_uses[s], "stage %d: uses and releases differ" % s
         for slot, use in self.input_loads.items():
             assert self.bar_phases[self.input_free[slot]] == 1, "input %d is never released (or more than once)" % slot
-        S = self.n_stores
+        for r, parts in self.acc_participants.items():
+            assert len(parts) <= 1, "region %s is read by %s epilogue workers in different uses" % (r, sorted(parts))
+            if parts:
+                self.bar_count[self.acc_free[r]] = 4 * next(iter(parts))
         for op in self.epis:
             dep = op.pop("_store_dep", None)
             unit = op.pop("_unit", None)
             if dep is None:
                 continue
-            kind, k, m = dep
-            if kind == "same":
+            k, m = dep                                # the unit's last store / stores this worker issued so far
+            if k is not None:
                 pend = m - 1 - k
-            elif unit in self.unit_last_store:       # last stored in the previous tile
-                pend = m - 1 - (self.unit_last_store[unit] - S)
+            elif unit in self.unit_last_store:        # last stored in the previous tile
+                pend = m - 1 - (self.unit_last_store[unit] - self.n_stores[op["worker"]])
             else:
                 pend = None
             op["store_wait_pending"] = -1 if pend is None else max(0, min(7, pend))
@@ -328,7 +353,7 @@ class ChainProgram:
         for i, o in enumerate(self.epis):
             x = E[i]
             x.wait_acc, x.wait_dst, x.wait_aux = self._spec(o["wait_acc"]), self._spec(o["wait_dst"]), self._spec(o["wait_aux"])
-            for k in ("arrive_acc_free", "arrive_dst_ready", "release_aux", "mode", "ncols", "dst_col0", "tmem_col", "store_tensor",
+            for k in ("worker", "arrive_acc_free", "arrive_dst_ready", "release_aux", "mode", "ncols", "dst_col0", "tmem_col", "store_tensor",
                       "store_wait_pending", "release_after_store", "out_id", "out_ld", "bias_off", "dst_off", "aux_off", "store_col0"):
                 setattr(x, k, o[k])
         d = _lib.RlChainDesc()
@@ -364,7 +389,7 @@ class ChainProgram:
     def read_trace(self):
         """{"load": [t], "mma": [(t_waited, t_committed)], "epi": [(start, acc ready, regs, math, end)]} in
         SM clock cycles relative to the first stamp (profiling aid)."""
-        n = len(self.loads) + 2 * len(self.mmas) + 5 * len(self.epis)
+        n = len(self.loads) + 8 * len(self.mmas) + 5 * len(self.epis)
         buf = (C.c_uint64 * n)()
         got = self._libref.rl_chain_read_trace(self._handle, buf, n)
         if got < 0:
@@ -373,8 +398,8 @@ class ChainProgram:
         t0 = min(x for x in v if x)
         v = [x - t0 if x else None for x in v]
         nl, nm = len(self.loads), len(self.mmas)
-        return {"load": v[:nl], "mma": [tuple(v[nl + 2 * i: nl + 2 * i + 2]) for i in range(nm)],
-                "epi": [tuple(v[nl + 2 * nm + 5 * i: nl + 2 * nm + 5 * i + 5]) for i in range(len(self.epis))]}
+        return {"load": v[:nl], "mma": [tuple(v[nl + 8 * i: nl + 8 * i + 8]) for i in range(nm)],
+                "epi": [tuple(v[nl + 8 * nm + 5 * i: nl + 8 * nm + 5 * i + 5]) for i in range(len(self.epis))]}
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -442,8 +467,9 @@ class Emulator:
         unit_loading = [0] * p.n_units       # TMA loads in flight into the unit
         tmem = torch.zeros(128, 512)
         mma_queue = []                       # issued MMAs / commits, executed in order by the tensor pipe
-        loads_inflight, stores_inflight = [], []
-        store_groups = {"issued": 0, "read": 0}
+        loads_inflight = []
+        stores_inflight = [[], []]           # per epilogue worker: bulk groups complete in order
+        store_groups = [{"issued": 0, "read": 0}, {"issued": 0, "read": 0}]
         state = {"done": 0}
 
         def spec_wait(w, it, role):
@@ -527,10 +553,13 @@ class Emulator:
             unit_readers[ua] -= 1
             unit_readers[ub] -= 1
 
-        def epi_role():
+        def epi_role(wk):
+            sg = store_groups[wk]
             for it, tile in enumerate(tiles):
                 m0 = tile * 128
                 for o in p.epis:
+                    if o["worker"] != wk:
+                        continue
                     yield from spec_wait(o["wait_acc"], it, "epi")
                     nc = o["ncols"]
                     f = tmem[:, o["tmem_col"]:o["tmem_col"] + nc].clone()
@@ -555,7 +584,7 @@ class Emulator:
                         out[m0:m0 + rr, :nc] = f[:rr]
                         continue
                     if o["store_wait_pending"] >= 0:
-                        while store_groups["issued"] - store_groups["read"] > o["store_wait_pending"]:
+                        while sg["issued"] - sg["read"] > o["store_wait_pending"]:
                             yield
                     yield from spec_wait(o["wait_dst"], it, "epi")
                     u = o["dst_off"] // UNIT
@@ -570,10 +599,10 @@ class Emulator:
                         bars[o["release_aux"]].arrive()
                     if o["store_tensor"] != NONE:
                         unit_readers[u] += 1
-                        store_groups["issued"] += 1
-                        stores_inflight.append((o, m0, u))
+                        sg["issued"] += 1
+                        stores_inflight[wk].append((o, m0, u))
                         if o["release_after_store"] != NONE:
-                            while store_groups["issued"] != store_groups["read"]:
+                            while sg["issued"] != sg["read"]:
                                 yield
                             bars[o["release_after_store"]].arrive()
                     yield
@@ -586,60 +615,62 @@ class Emulator:
             if rr > 0 and cc > 0:
                 t[m0:m0 + rr, o["store_col0"]:o["store_col0"] + cc] = units[u][:rr, :cc].to(t.dtype)
             unit_readers[u] -= 1
-            store_groups["read"] += 1
+            store_groups[o["worker"]]["read"] += 1
 
-        roles = [load_role(), mma_role(), epi_role()]
-        alive = [True, True, True]
+        roles = [load_role(), mma_role(), epi_role(0), epi_role(1)]
+        alive = [True, True, True, True]
+        NR = 4
         blocked_rounds = 0
         # adversarial speeds: every agent (3 roles, TMA loads, tensor pipe, TMA stores) gets its own firing
         # probability per round, re-drawn now and then, so slow-consumer / slow-producer races are exercised
-        speeds = [1.0] * 6
+        speeds = [1.0] * (NR + 4)
         rounds = 0
         while True:
             progressed = False
             if rounds % 400 == 0:
-                speeds = [self.rng.choice((0.03, 0.3, 1.0)) for _ in range(6)]
+                speeds = [self.rng.choice((0.03, 0.3, 1.0)) for _ in range(NR + 4)]
             rounds += 1
-            order = [0, 1, 2, 3, 4, 5]
+            order = list(range(NR + 4))
             self.rng.shuffle(order)
             for a in order:
                 if self.rng.random() > speeds[a]:
                     continue
-                if a < 3:
+                if a < NR:
                     if not alive[a]:
                         continue
-                    before = (len(loads_inflight), len(mma_queue), len(stores_inflight), tuple(b.n for b in bars),
-                              tuple(b.pending for b in bars), store_groups["issued"])
+                    before = (len(loads_inflight), len(mma_queue), len(stores_inflight[0]), len(stores_inflight[1]),
+                              tuple(b.n for b in bars), tuple(b.pending for b in bars))
                     try:
                         next(roles[a])
                     except StopIteration:
                         alive[a] = False
                         progressed = True
                         continue
-                    after = (len(loads_inflight), len(mma_queue), len(stores_inflight), tuple(b.n for b in bars),
-                             tuple(b.pending for b in bars), store_groups["issued"])
+                    after = (len(loads_inflight), len(mma_queue), len(stores_inflight[0]), len(stores_inflight[1]),
+                             tuple(b.n for b in bars), tuple(b.pending for b in bars))
                     progressed |= before != after
-                elif a == 3 and loads_inflight:
+                elif a == NR and loads_inflight:
                     i = self.rng.randrange(len(loads_inflight))      # TMA completes out of order
                     land(*loads_inflight.pop(i))
                     progressed = True
-                elif a == 4 and mma_queue:
+                elif a == NR + 1 and mma_queue:
                     kind, x = mma_queue.pop(0)                        # the tensor pipe executes in order
                     if kind == "mma":
                         exec_mma(x)
                     else:
                         bars[x].arrive()
                     progressed = True
-                elif a == 5 and stores_inflight:
-                    do_store(*stores_inflight.pop(0))                 # bulk groups complete in order
+                elif a >= NR + 2 and stores_inflight[a - NR - 2]:
+                    do_store(*stores_inflight[a - NR - 2].pop(0))     # bulk groups complete in order
                     progressed = True
-            if not any(alive) and not loads_inflight and not mma_queue and not stores_inflight:
+            inflight = loads_inflight or mma_queue or stores_inflight[0] or stores_inflight[1]
+            if not any(alive) and not inflight:
                 break
             if progressed:
                 blocked_rounds = 0
             else:
                 blocked_rounds += 1
-                if blocked_rounds > 5000 and not loads_inflight and not mma_queue and not stores_inflight:
+                if blocked_rounds > 5000 and not inflight:
                     raise ChainHazard("deadlock in %s: roles alive %s, barrier completions %s" %
                                       (p.name, alive, {p.bar_name[i]: b.n for i, b in enumerate(bars)}))
 
@@ -668,10 +699,12 @@ def _boxes(p, acc, width, mode, bias_off, store_tensor=None, store_col0=0, aux_t
     n = (width + 63) // 64
     for c in range(n):
         nc = min(64, width - 64 * c)
-        aux = p.load_stage(aux_tensor, col0=aux_col0 + 64 * c, row0=0, tile_rows=True) if aux_tensor is not None else None
+        aux = None
+        if aux_tensor is not None:
+            aux = p.load_stage(aux_tensor, col0=aux_col0 + 64 * c, row0=0, tile_rows=True, consumer="epi%d" % p.worker_for(acc, 64 * c))
         out.append(p.epi_box(acc, 64 * c, mode, bias_off=bias_off + 64 * c, ncols=nc, aux=aux,
                              store=None if store_tensor is None else (store_tensor, store_col0 + 64 * c),
-                             first=(c == 0), last=(c == n - 1), has_reader=has_reader))
+                             last=(c == n - 1), has_reader=has_reader))
     return out
 
 
@@ -737,7 +770,7 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
             p.mma(xacm, s, n=64, acc=a1, k_steps=4, accumulate=False, acc_last=True,
                   a_release=(ni == len(nets) - 1 and j == nch - 1))
             chunk_box[j] = p.epi_box(a1, 0, EPI_BIAS_ELU, bias_off=T["b_cat"] + off + 64 * j,
-                                     store=None if tY1 is None else (tY1, off + 64 * j), first=True, last=True)
+                                     store=None if tY1 is None else (tY1, off + 64 * j), last=True)
 
         def l2(j):
             for h in range(0, W2.shape[0], 128):
@@ -766,7 +799,8 @@ def trunk_backward_program(T, n_stages=6):
     multiplying by ELU' of the saved activations, storing every layer-output gradient for the wgrad GEMMs.
     The two first-layer gradient streams (actor, critic) also accumulate d(latent)."""
     regions = {"C0": (0, 64), "C1": (64, 64), "BIG": (128, 256), "LAT": (384, 32)}
-    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=regions, name="trunk_backward")
+    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=regions, name="trunk_backward",
+                     region_worker={"C0": 0, "C1": 1, "LAT": 0})
     H = T["Wcat_t"].shape[1] // 2
     num_obs = T["num_obs"]
     tY1, tdY1 = p.tensor(T["Y1"], 128), p.tensor(T["dY1"], 128)
@@ -794,8 +828,8 @@ def trunk_backward_program(T, n_stages=6):
             for j, a in enumerate(d2):
                 s = p.load_stage(tW2, col0=64 * j, row0=64 * c)
                 p.mma(a, s, n=64, acc=a1, k_steps=4, accumulate=j > 0, acc_last=(j == len(d2) - 1), a_release=(c == nch - 1))
-            aux = p.load_stage(tY1, col0=off + 64 * c, row0=0, tile_rows=True)
-            boxes[c] = p.epi_box(a1, 0, EPI_DELU, aux=aux, store=(tdY1, off + 64 * c), first=True, last=True)
+            aux = p.load_stage(tY1, col0=off + 64 * c, row0=0, tile_rows=True, consumer="epi%d" % p.worker_for(a1, 0))
+            boxes[c] = p.epi_box(a1, 0, EPI_DELU, aux=aux, store=(tdY1, off + 64 * c), last=True)
 
         def lat(c):
             s = p.load_stage(tWcat_t, col0=off + 64 * c, row0=num_obs)
