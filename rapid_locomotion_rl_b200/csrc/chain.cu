@@ -7,8 +7,8 @@
 //
 // Execution model (see include/rl_b200.h "Fused MLP chains"): three warp roles interpret three host-built
 // op lists, in order, once per tile of the persistent loop; every dependency is an mbarrier:
-//   warp 0 lane 0     LOAD ops: mbarrier wait (unit free) -> expect_tx -> cp.async.bulk.tensor.2d
-//   warp 1 lane 0     MMA ops : waits (stage full / box ready / accumulator free) -> <= 4 tcgen05.mma
+//   warp 0 (1 elected lane)  LOAD ops: mbarrier wait (unit free) -> expect_tx -> cp.async.bulk.tensor.2d
+//   warp 1 (1 elected lane)  MMA ops : waits (stage full / box ready / accumulator free) -> <= 4 tcgen05.mma
 //                               (M128 x n x K16, kind::f16, fp32 in TMEM) -> tcgen05.commit on <= 3 barriers
 //   warps 2-5, 6-9    EPI ops : two workers, each runs its own list: wait (accumulator full) -> tcgen05.ld -> bias / ELU / ELU' -> swizzled bf16
 //                               box in shared memory (the next layer's A operand) -> TMA store of the box
@@ -46,11 +46,16 @@ struct DevMmaOp {            // 32 B
 };
 static_assert(sizeof(DevMmaOp) == 32, "DevMmaOp layout");
 
+// The LOAD and MMA op lists travel in the kernel parameters (constant bank): indexed by the loop counter
+// they are read with uniform loads, so the TMA / tcgen05 instructions get their operands in uniform
+// registers directly.  (Ops fetched from global memory are per-thread values: every UTCHMMA then sits in
+// an ELECT / 7x R2UR.BROADCAST waterfall loop, ~90 cycles per instruction - measured.)
+constexpr int MAX_LOADS = 192, MAX_MMAS = 160;
 struct ChainParams {
   CUtensorMap tmaps[RL_CHAIN_MAX_TENSORS];
-  const RlChainLoadOp* loads;
-  const DevMmaOp* mmas;
-  const RlChainEpiOp* epis[2];    // per epilogue worker
+  RlChainLoadOp loads[MAX_LOADS];
+  DevMmaOp mmas[MAX_MMAS];
+  const RlChainEpiOp* epis[2];    // per epilogue worker (global memory)
   const float* params;
   float* outputs[RL_CHAIN_MAX_OUTPUTS];
   int n_loads, n_mmas, n_epis[2];
@@ -113,6 +118,18 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // byte offset of the 16 B chunk holding columns [8c, 8c+8) of row r inside a 128 B-swizzled [rows x 64] box
 __device__ __forceinline__ uint32_t sw_chunk(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+// one lane of a converged warp (CUTLASS elect_one_sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   // descriptor high word: SBO = 1024 B (8-row group pitch), version 1, SWIZZLE_128B
   constexpr uint32_t HI = 64u | (1u << 14) | (2u << 29);
@@ -146,60 +163,49 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 
   if (warp == 0) {
     // ===================================== LOAD role =====================================
-    if (lane == 0 && p.n_loads > 0) {
-      const uint4* ops = reinterpret_cast<const uint4*>(p.loads);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int m0 = tile * 128;
-        uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1);
-        for (int i = 0; i < p.n_loads; ++i) {
-          const uint4 w0 = n0, w1 = n1;
-          if (i + 1 < p.n_loads) { n0 = __ldg(ops + 2 * (i + 1)); n1 = __ldg(ops + 2 * (i + 1) + 1); }
-          const uint32_t wait = w0.x & 0xFFFFu, full_bar = (w0.x >> 16) & 0xFFu, tensor = w0.x >> 24;
-          const uint32_t smem_off = w0.y;
-          const int col0 = (int)w0.z, row0 = (int)w0.w;
-          const uint32_t expect = w1.x;
-          const bool tile_rows = (w1.y & 0xFFu) != 0;
-          chain_wait(bars, wait, it);
-          mbar_expect_tx(&bars[full_bar], expect);
-          tma_load_2d(smem + smem_off, &p.tmaps[tensor], col0, row0 + (tile_rows ? m0 : 0), &bars[full_bar]);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = tile * 128;
+      for (int i = 0; i < p.n_loads; ++i) {
+        const RlChainLoadOp& o = p.loads[i];
+        chain_wait(bars, o.wait, it);
+        if (elect_one()) {
+          mbar_expect_tx(&bars[o.full_bar], o.expect_bytes);
+          tma_load_2d(smem + o.smem_off, &p.tmaps[o.tensor], o.col0, o.row0 + (o.tile_rows ? m0 : 0), &bars[o.full_bar]);
           if (p.trace && blockIdx.x == 0 && it == p.trace_it) p.trace[i] = clock64();
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA role ======================================
-    if (lane == 0 && p.n_mmas > 0) {
-      const uint4* ops = reinterpret_cast<const uint4*>(p.mmas);
-      const uint32_t base16 = smem_base >> 4;
-      const uint32_t bar0 = smem_u32(bars);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1);
-        for (int i = 0; i < p.n_mmas; ++i) {
-          const uint4 w0 = n0, w1 = n1;
-          if (i + 1 < p.n_mmas) { n0 = __ldg(ops + 2 * (i + 1)); n1 = __ldg(ops + 2 * (i + 1) + 1); }
-          const uint32_t a_lo = w0.x + base16, b_lo = w0.y + base16, idesc = w0.z;
-          const uint32_t tmem_d = tmem_base + (w0.w & 0xFFFFu);
-          const uint32_t k_steps = (w0.w >> 16) & 0xFFu, accumulate = w0.w >> 24;
-          const uint32_t wait0 = w1.x & 0xFFFFu, wait1 = w1.x >> 16, wait2 = w1.y & 0xFFFFu;
-          const uint32_t c0 = (w1.y >> 16) & 0xFFu, c1 = w1.y >> 24, c2 = w1.z & 0xFFu;
-          chain_wait(bars, wait0, it);
-          chain_wait(bars, wait1, it);
-          chain_wait(bars, wait2, it);
+    const uint32_t base16 = smem_base >> 4;
+    const uint32_t bar0 = smem_u32(bars);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int i = 0; i < p.n_mmas; ++i) {
+        const DevMmaOp& o = p.mmas[i];
+        chain_wait(bars, o.wait0, it);
+        chain_wait(bars, o.wait1, it);
+        chain_wait(bars, o.wait2, it);
+        tc_fence_after();
+        if (elect_one()) {
           const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it;
           if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
-          tc_fence_after();
-          mma_issue(tmem_d, a_lo, b_lo, idesc, accumulate);                     // K16 step 0
+          const uint32_t a_lo = o.a_lo + base16, b_lo = o.b_lo + base16, idesc = o.idesc;
+          const uint32_t tmem_d = tmem_base + o.tmem_col;
+          const uint32_t k_steps = o.k_steps;
+          mma_issue(tmem_d, a_lo, b_lo, idesc, o.accumulate);                   // K16 step 0
           if (k_steps > 1) mma_issue(tmem_d, a_lo + 2, b_lo + 2, idesc, 1);     // +32 B per step
           if (k_steps > 2) mma_issue(tmem_d, a_lo + 4, b_lo + 4, idesc, 1);
           if (k_steps > 3) mma_issue(tmem_d, a_lo + 6, b_lo + 6, idesc, 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 4] = clock64();
-          if (c0 != RL_CHAIN_NONE) mma_commit(reinterpret_cast<uint64_t*>(0) + 0, bar0 + 8 * c0);
-          if (c1 != RL_CHAIN_NONE) mma_commit(reinterpret_cast<uint64_t*>(0) + 0, bar0 + 8 * c1);
-          if (c2 != RL_CHAIN_NONE) mma_commit(reinterpret_cast<uint64_t*>(0) + 0, bar0 + 8 * c2);
+          if (o.commit0 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * o.commit0);
+          if (o.commit1 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * o.commit1);
+          if (o.commit2 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * o.commit2);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 7] = clock64();
         }
+        __syncwarp();
       }
     }
   } else {
@@ -393,6 +399,9 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   RL_REQUIRE(d->n_barriers > 0 && d->n_barriers <= RL_CHAIN_MAX_BARRIERS, RL_ERR_BAD_ARG, "rl_chain_create: n_barriers=%d", d->n_barriers);
   RL_REQUIRE(d->n_loads >= 0 && d->n_mmas >= 0 && d->n_epis >= 0 && d->loads_host && d->mmas_host && d->epis_host,
              RL_ERR_BAD_ARG, "rl_chain_create: op lists missing");
+  RL_REQUIRE(d->n_loads <= MAX_LOADS && d->n_mmas <= MAX_MMAS, RL_ERR_BAD_ARG,
+             "rl_chain_create: %d load / %d mma ops exceed the %d / %d that fit in the kernel parameters", d->n_loads, d->n_mmas,
+             MAX_LOADS, MAX_MMAS);
   static_assert(sizeof(RlChainLoadOp) == 32 && sizeof(RlChainMmaOp) == 32 && sizeof(RlChainEpiOp) == 48, "op layouts");
   const uint32_t limit = (uint32_t)d->n_units * UNIT_BYTES;
   for (int i = 0; i < d->n_loads; ++i) {
@@ -435,11 +444,10 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
     }
   }
   // device formats: MMA ops with precomputed descriptor words, epilogue ops split per worker
-  const size_t nl = (size_t)d->n_loads * sizeof(RlChainLoadOp), nm = (size_t)d->n_mmas * sizeof(DevMmaOp),
-               ne = (size_t)d->n_epis * sizeof(RlChainEpiOp);
-  std::vector<uint8_t> blob(nl + nm + ne + 64, 0);
-  if (nl) memcpy(blob.data(), d->loads_host, nl);
-  DevMmaOp* dm = reinterpret_cast<DevMmaOp*>(blob.data() + nl);
+  const size_t ne = (size_t)d->n_epis * sizeof(RlChainEpiOp);
+  std::vector<uint8_t> blob(ne + 64, 0);
+  for (int i = 0; i < d->n_loads; ++i) h->params.loads[i] = d->loads_host[i];
+  DevMmaOp* dm = h->params.mmas;
   for (int i = 0; i < d->n_mmas; ++i) {
     const RlChainMmaOp& o = d->mmas_host[i];
     DevMmaOp& x = dm[i];
@@ -450,7 +458,7 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
     x.wait0 = o.wait0; x.wait1 = o.wait1; x.wait2 = o.wait2;
     x.commit0 = o.commit0; x.commit1 = o.commit1; x.commit2 = o.commit2;
   }
-  RlChainEpiOp* de = reinterpret_cast<RlChainEpiOp*>(blob.data() + nl + nm);
+  RlChainEpiOp* de = reinterpret_cast<RlChainEpiOp*>(blob.data());
   {
     int pos[2] = {0, n_epi_w[0]};
     for (int i = 0; i < d->n_epis; ++i) de[pos[d->epis_host[i].worker]++] = d->epis_host[i];
@@ -460,9 +468,7 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   uint8_t* base = reinterpret_cast<uint8_t*>(h->dev_ops);
   err = cudaMemcpy(base, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: cudaMemcpy: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
-  h->params.loads = reinterpret_cast<const RlChainLoadOp*>(base);
-  h->params.mmas = reinterpret_cast<const DevMmaOp*>(base + nl);
-  h->params.epis[0] = reinterpret_cast<const RlChainEpiOp*>(base + nl + nm);
+  h->params.epis[0] = reinterpret_cast<const RlChainEpiOp*>(base);
   h->params.epis[1] = h->params.epis[0] + n_epi_w[0];
   h->params.params = d->params;
   for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->params.outputs[i] = d->outputs[i];
