@@ -92,6 +92,23 @@ __device__ __forceinline__ void chain_wait(uint64_t* bars, uint32_t spec, int it
   }
 }
 
+// up to three waits at once: the try_waits are issued back to back (independent), only failed ones are retried
+__device__ __forceinline__ void chain_wait3(uint64_t* bars, uint32_t s0, uint32_t s1, uint32_t s2, int it) {
+  const uint32_t i0 = s0 & 0xFFu, i1 = s1 & 0xFFu, i2 = s2 & 0xFFu;
+  const uint32_t p0 = ((s0 >> 8) ^ ((s0 >> 9) & (uint32_t)it)) & 1u, p1 = ((s1 >> 8) ^ ((s1 >> 9) & (uint32_t)it)) & 1u,
+                 p2 = ((s2 >> 8) ^ ((s2 >> 9) & (uint32_t)it)) & 1u;
+  bool ok0 = i0 == RL_CHAIN_NONE || mbar_try(&bars[i0], p0);
+  bool ok1 = i1 == RL_CHAIN_NONE || mbar_try(&bars[i1], p1);
+  bool ok2 = i2 == RL_CHAIN_NONE || mbar_try(&bars[i2], p2);
+  uint32_t spins = 0;
+  while (!(ok0 && ok1 && ok2)) {
+    if (!ok0) ok0 = mbar_try(&bars[i0], p0);
+    if (!ok1) ok1 = mbar_try(&bars[i1], p1);
+    if (!ok2) ok2 = mbar_try(&bars[i2], p2);
+    if (++spins > (1u << 24)) chain_timeout(!ok0 ? i0 : (!ok1 ? i1 : i2), 2, it);
+  }
+}
+
 // ELU on the fp32 accumulator: exp through ex2.approx.ftz (MUFU), 4 instructions per element
 __device__ __forceinline__ float elu1(float x) {
   float e;
@@ -163,18 +180,21 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 
   if (warp == 0) {
     // ===================================== LOAD role =====================================
+    // (the next op's fields are fetched - uniform constant loads - before this op's wait, off the critical path)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.num_tiles && p.n_loads > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
+      RlChainLoadOp cur = p.loads[0];
       for (int i = 0; i < p.n_loads; ++i) {
-        const RlChainLoadOp& o = p.loads[i];
-        chain_wait(bars, o.wait, it);
+        const RlChainLoadOp nxt = p.loads[i + 1 < p.n_loads ? i + 1 : i];
+        chain_wait(bars, cur.wait, it);
         if (elect_one()) {
-          mbar_expect_tx(&bars[o.full_bar], o.expect_bytes);
-          tma_load_2d(smem + o.smem_off, &p.tmaps[o.tensor], o.col0, o.row0 + (o.tile_rows ? m0 : 0), &bars[o.full_bar]);
+          mbar_expect_tx(&bars[cur.full_bar], cur.expect_bytes);
+          tma_load_2d(smem + cur.smem_off, &p.tmaps[cur.tensor], cur.col0, cur.row0 + (cur.tile_rows ? m0 : 0), &bars[cur.full_bar]);
           if (p.trace && blockIdx.x == 0 && it == p.trace_it) p.trace[i] = clock64();
         }
         __syncwarp();
+        cur = nxt;
       }
     }
   } else if (warp == 1) {
@@ -182,30 +202,31 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     const uint32_t base16 = smem_base >> 4;
     const uint32_t bar0 = smem_u32(bars);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.num_tiles && p.n_mmas > 0; tile += gridDim.x, ++it) {
+      DevMmaOp cur = p.mmas[0];
+      const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it;
       for (int i = 0; i < p.n_mmas; ++i) {
-        const DevMmaOp& o = p.mmas[i];
-        chain_wait(bars, o.wait0, it);
-        chain_wait(bars, o.wait1, it);
-        chain_wait(bars, o.wait2, it);
+        const DevMmaOp nxt = p.mmas[i + 1 < p.n_mmas ? i + 1 : i];
+        if (tr && lane == 0) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
+        chain_wait3(bars, cur.wait0, cur.wait1, cur.wait2, it);
         tc_fence_after();
         if (elect_one()) {
-          const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it;
           if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
-          const uint32_t a_lo = o.a_lo + base16, b_lo = o.b_lo + base16, idesc = o.idesc;
-          const uint32_t tmem_d = tmem_base + o.tmem_col;
-          const uint32_t k_steps = o.k_steps;
-          mma_issue(tmem_d, a_lo, b_lo, idesc, o.accumulate);                   // K16 step 0
+          const uint32_t a_lo = cur.a_lo + base16, b_lo = cur.b_lo + base16, idesc = cur.idesc;
+          const uint32_t tmem_d = tmem_base + cur.tmem_col;
+          const uint32_t k_steps = cur.k_steps;
+          mma_issue(tmem_d, a_lo, b_lo, idesc, cur.accumulate);                 // K16 step 0
           if (k_steps > 1) mma_issue(tmem_d, a_lo + 2, b_lo + 2, idesc, 1);     // +32 B per step
           if (k_steps > 2) mma_issue(tmem_d, a_lo + 4, b_lo + 4, idesc, 1);
           if (k_steps > 3) mma_issue(tmem_d, a_lo + 6, b_lo + 6, idesc, 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 4] = clock64();
-          if (o.commit0 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * o.commit0);
-          if (o.commit1 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * o.commit1);
-          if (o.commit2 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * o.commit2);
+          if (cur.commit0 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * cur.commit0);
+          if (cur.commit1 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * cur.commit1);
+          if (cur.commit2 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * cur.commit2);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 7] = clock64();
         }
         __syncwarp();
+        cur = nxt;
       }
     }
   } else {
