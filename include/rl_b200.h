@@ -379,6 +379,21 @@ int rl_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const
                  int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ld_aux,
                  int32_t transposed, int32_t epilogue, int32_t split_k, void* stream);
 
+/* Weight / bias gradients of several layers in one launch (the autograd wgrad behind ppo.py:146-148,166):
+ * dW[M,N] += dY[K,M]^T X[K,N] (fp32 atomics, split-K over the K batch rows), db[m] += sum_k dY[k,m].
+ * dY, X: row-major bf16 with pitches ld_dy / ld_x (multiples of 8, 16 B aligned bases); dW fp32 pitch ld_dw. */
+typedef struct RlWgradProblem {
+  const void* dY;
+  const void* X;
+  float* dW;
+  float* db;                        /* may be NULL */
+  int32_t M, N, K;
+  int32_t ld_dy, ld_x, ld_dw;
+  int32_t split_k;
+  int32_t reserved;
+} RlWgradProblem;
+int rl_wgrad_grouped(const RlWgradProblem* problems_host, int32_t n, void* stream);
+
 /* ---- Fused MLP chains on the tensor cores ----------------------------------------------------
  * The learner's networks (actor_critic.py:38-100: encoder 18-256-128-18, actor / critic 60-512-256-128-{12,1},
  * adaptation module 630-256-32-18) are chains of Linear(+ELU) layers.  rl_gemm_bf16 runs one layer per

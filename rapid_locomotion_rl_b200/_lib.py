@@ -74,6 +74,7 @@ RlResetCfg = STRUCTS["RlResetCfg"]
 RlResetBuffers = STRUCTS["RlResetBuffers"]
 RlGacCfg = STRUCTS["RlGacCfg"]
 RlGacBuffers = STRUCTS["RlGacBuffers"]
+RlWgradProblem = STRUCTS["RlWgradProblem"]
 RlChainTensor = STRUCTS["RlChainTensor"]
 RlChainLoadOp = STRUCTS["RlChainLoadOp"]
 RlChainMmaOp = STRUCTS["RlChainMmaOp"]
@@ -110,6 +111,7 @@ SIGNATURES = {
     "rl_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
                           C.c_float, _P, _P]),
     "rl_gemm_init": (C.c_int, []),
+    "rl_wgrad_grouped": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_create": (C.c_int, [_P, _P]),
     "rl_chain_run": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_destroy": (C.c_int, [_P]),

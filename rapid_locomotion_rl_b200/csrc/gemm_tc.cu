@@ -71,8 +71,7 @@ __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : (__expf(x
 // STAGES = 2 for short reductions (<= 2 k-blocks per CTA: 48-64 KB of smem, 3 CTAs per SM so that the
 // epilogue of one tile overlaps the loads / MMAs of its neighbours), 4 otherwise.
 template <int BN, bool TN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
+__device__ __forceinline__ void gemm_tile(const GemmArgs& args, const int bx, const int by, const int bz) {
   using S = Smem<BN, TN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
@@ -87,12 +86,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = bx * BM, n0 = by * BN;
   const int total_kblocks = (args.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * args.kblocks_per_split;
+  const int kb_begin = bz * args.kblocks_per_split;
   const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
-  const bool want_db = TN && args.db != nullptr && blockIdx.y == 0;
+  const bool want_db = TN && args.db != nullptr && by == 0;
   constexpr uint32_t TMEM_COLS = (BN + (TN ? 32 : 0)) <= 32 ? 32 : (BN + (TN ? 32 : 0)) <= 64 ? 64 :
                                  (BN + (TN ? 32 : 0)) <= 128 ? 128 : (BN + (TN ? 32 : 0)) <= 256 ? 256 : 512;
 
@@ -326,6 +325,37 @@ gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+template <int BN, bool TN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ GemmArgs args) {
+  gemm_tile<BN, TN, STAGES>(args, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Grouped wgrad: the weight / bias gradients of SEVERAL layers (dW_l = dY_l^T X_l, split-K over the batch
+// rows, fp32 atomics into the flat gradient) in ONE launch.  The 13 wgrad GEMMs of a PPO minibatch are
+// independent and individually too small to fill 148 SMs (128 x 16 ... 512 x 256 outputs); one grid whose
+// CTAs are dealt over (problem, m tile, n tile, k split) keeps every SM busy and pays one launch.
+constexpr int MAX_GROUP = 12;
+struct GroupedArgs {
+  GemmArgs g[MAX_GROUP];
+  int first_cta[MAX_GROUP + 1];   // prefix sums of CTAs per problem
+  int grid_x[MAX_GROUP], grid_y[MAX_GROUP];
+  int n;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+wgrad_grouped_kernel(const __grid_constant__ GroupedArgs G) {
+  int p = 0;
+  const int cta = blockIdx.x;
+  while (p + 1 < G.n && cta >= G.first_cta[p + 1]) ++p;
+  const int local = cta - G.first_cta[p];
+  // k split slowest: consecutive CTAs share the same K range of dY / X (L2 reuse across the m / n tiles)
+  const int gx = G.grid_x[p], gy = G.grid_y[p];
+  const int bx = local % gx, by = (local / gx) % gy, bz = local / (gx * gy);
+  gemm_tile<BN, true, 4>(G.g[p], bx, by, bz);
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -406,7 +436,78 @@ extern "C" int rl_gemm_init(void) {
       (rc = configure_one<64, false, 4>()) || (rc = configure_one<128, false, 2>()) || (rc = configure_one<128, false, 4>()) ||
       (rc = configure_one<64, true, 4>()) || (rc = configure_one<128, true, 4>()))
     return rc;
+  {
+    cudaError_t e1 = cudaFuncSetAttribute(wgrad_grouped_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, true, 4>::TOTAL);
+    cudaError_t e2 = cudaFuncSetAttribute(wgrad_grouped_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, true, 4>::TOTAL);
+    RL_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute(wgrad_grouped)");
+  }
   RL_REQUIRE(encode_fn() != nullptr, RL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  return RL_OK;
+}
+
+// fills GemmArgs for the transposed (wgrad) form; returns the grid of that problem
+static int build_wgrad_args(GemmArgs& a, const void* A, const void* B, float* C, float* db, int M, int N, int K, int lda, int ldb,
+                            int ldc, int split_k, dim3* grid) {
+  a.C = C; a.bias = nullptr; a.aux = nullptr; a.db = db;
+  a.ldc = ldc; a.ld_aux = 0; a.M = M; a.N = N; a.K = K; a.epi = EPI_F32_ATOMIC;
+  const int total_kb = (K + BK - 1) / BK;
+  a.kblocks_per_split = (total_kb + split_k - 1) / split_k;
+  const int splits = (total_kb + a.kblocks_per_split - 1) / a.kblocks_per_split;
+  const int bn = N <= 64 ? 64 : 128;
+  int rc;
+  if ((rc = make_tmap_bf16(&a.tmA, A, K, M, lda, 64)) != RL_OK) return rc;
+  if ((rc = make_tmap_bf16(&a.tmB, B, K, N, ldb, 64)) != RL_OK) return rc;
+  a.tma_store = 0; a.tma_aux = 0;
+  *grid = dim3((M + BM - 1) / BM, (N + bn - 1) / bn, splits);
+  return RL_OK;
+}
+
+template <int BN>
+static int launch_grouped(const GroupedArgs& G, int total, cudaStream_t st) {
+  using S = Smem<BN, true, 4>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(wgrad_grouped_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute(wgrad_grouped): %s", cudaGetErrorString(err));
+    configured = true;
+  }
+  wgrad_grouped_kernel<BN><<<total, GEMM_THREADS, S::TOTAL, st>>>(G);
+  return check_launch("wgrad_grouped_kernel");
+}
+
+// C-ABI: n weight-gradient problems dW_i[M_i, N_i] += dY_i[K, M_i]^T X_i[K, N_i] (+ db_i[m] += sum_k dY_i[k, m])
+// in at most two launches (one per tile width).  split_k_i: see rl_gemm_bf16.
+extern "C" int rl_wgrad_grouped(const RlWgradProblem* pr, int32_t n, void* stream) {
+  RL_REQUIRE(pr && n > 0, RL_ERR_BAD_ARG, "rl_wgrad_grouped: no problems");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int width = 0; width < 2; ++width) {          // 0: outputs with N <= 64 (BN = 64), 1: the rest (BN = 128)
+    GroupedArgs G;
+    G.n = 0;
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+      const RlWgradProblem& q = pr[i];
+      RL_REQUIRE(q.dY && q.X && q.dW && q.M > 0 && q.N > 0 && q.K > 0 && q.split_k >= 1, RL_ERR_BAD_ARG, "rl_wgrad_grouped: problem %d", i);
+      if ((q.N <= 64) != (width == 0)) continue;
+      if (G.n == MAX_GROUP) {                         // flush a full group
+        G.first_cta[G.n] = total;
+        int rc = width == 0 ? launch_grouped<64>(G, total, st) : launch_grouped<128>(G, total, st);
+        if (rc != RL_OK) return rc;
+        G.n = 0; total = 0;
+      }
+      dim3 grid;
+      int rc = build_wgrad_args(G.g[G.n], q.dY, q.X, q.dW, q.db, q.M, q.N, q.K, q.ld_dy, q.ld_x, q.ld_dw, q.split_k, &grid);
+      if (rc != RL_OK) return rc;
+      G.first_cta[G.n] = total;
+      G.grid_x[G.n] = grid.x; G.grid_y[G.n] = grid.y;
+      total += grid.x * grid.y * grid.z;
+      ++G.n;
+    }
+    if (G.n > 0) {
+      G.first_cta[G.n] = total;
+      int rc = width == 0 ? launch_grouped<64>(G, total, st) : launch_grouped<128>(G, total, st);
+      if (rc != RL_OK) return rc;
+    }
+  }
   return RL_OK;
 }
 

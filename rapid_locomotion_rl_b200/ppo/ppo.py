@@ -12,6 +12,7 @@ module) -> bf16 shadow refresh.  No host synchronisation happens inside update()
 means are read back once at the end (the reference syncs >= 5 times per minibatch).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -62,6 +63,8 @@ class PPO:
         self._graph_B = 0
         self._idx_buf = None
         self.use_cuda_graph = True
+        self.group_wgrads = os.environ.get("RL_GROUP_WGRADS", "1") != "0"
+        self._wq = []
         _lib.check(self._lib.rl_gemm_init())
         ac = actor_critic
         self._main_layers = ac.L_enc + [ac.L_cat] + ac.L_act + ac.L_cri
@@ -115,11 +118,35 @@ class PPO:
         return max(1, min(total_kb, (296 + tiles - 1) // tiles))
 
     def _wgrad(self, L, dY, dy_off, ld_dy, X, x_off, ld_x, rows):
-        """dW[out,in] += dY^T X (split-K, atomics into the flat gradient) and db from the ones-MMA."""
+        """dW[out,in] += dY^T X (split-K, atomics into the flat gradient) and db from the ones-MMA.
+        Problems are queued and launched together by _wgrad_flush (one grid for all layers)."""
         ac = self.actor_critic
+        if self.group_wgrads:
+            q = _lib.RlWgradProblem()
+            q.dY, q.X, q.dW, q.db = ac._p(dY, dy_off), ac._p(X, x_off), L.gw.data_ptr(), L.gb.data_ptr()
+            q.M, q.N, q.K, q.ld_dy, q.ld_x, q.ld_dw = L.out, L.inp, rows, ld_dy, ld_x, L.inp
+            self._wq.append(q)
+            return
         split = self._split(L.out, L.inp, 64, rows)
         ac._gemm(ac._p(dY, dy_off), ld_dy, ac._p(X, x_off), ld_x, L.gw.data_ptr(), L.inp, L.out, L.inp, rows,
                  EPI_ATOMIC, transposed=1, db=L.gb.data_ptr(), split_k=split)
+
+    def _wgrad_flush(self):
+        """Launches the queued weight-gradient problems as one grouped grid (csrc/gemm_tc.cu): largest first,
+        split-K sized so that the whole group is ~4 CTAs per SM."""
+        if not self._wq:
+            return
+        qs = sorted(self._wq, key=lambda q: -(q.M * q.N))
+        self._wq = []
+        tiles = [((q.M + 127) // 128) * ((q.N + (127 if q.N > 64 else 63)) // (128 if q.N > 64 else 64)) for q in qs]
+        work = [t * max(q.N, 64) for t, q in zip(tiles, qs)]            # ~ MMA time per k-block of the problem
+        total_kb = (qs[0].K + 63) // 64
+        budget = 4 * 148
+        for q, t, wk in zip(qs, tiles, work):
+            share = max(1.0, budget * wk / float(sum(work)))
+            q.split_k = int(max(1, min(total_kb, round(share / t))))
+        arr = (_lib.RlWgradProblem * len(qs))(*qs)
+        _lib.check(self._lib.rl_wgrad_grouped(arr, len(qs), _lib.current_stream()))
 
     def _dgrad(self, L, dY, dy_off, ld_dy, dX, dx_off, ld_dx, rows, aux=None, aux_off=0, ld_aux=0, col0=0, ncols=None):
         """dX = (dY W[:, col0:col0+ncols]) (* elu'(aux)): B operand = the transposed shadow, rows col0.."""
@@ -179,6 +206,7 @@ class PPO:
         self._wgrad(e[2], w["dLat"], 0, ld("dLat"), w["H2"], 0, ld("H2"), B)
         self._wgrad(e[1], w["dH2"], 0, ld("dH2"), w["H1"], 0, ld("H1"), B)
         self._wgrad(e[0], w["dH1"], 0, ld("dH1"), w["Xp"], 0, ld("Xp"), B)
+        self._wgrad_flush()
         # ---- data-parallel reduction of the policy gradients and loss statistics ----
         g_main, g_adapt = ac.flat_grad[:ac.n_main], ac.flat_grad[ac.n_main:]
         if allreduce is not None:
@@ -210,6 +238,7 @@ class PPO:
             self._wgrad(d[2], w["dpred"], 0, 24, w["D2"], 0, ld("D2"), B)
             self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
             self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
+            self._wgrad_flush()
             if allreduce is not None:
                 allreduce(g_adapt)
                 allreduce(stats_ad)
