@@ -154,6 +154,7 @@ __device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint32_t a_lo, uint32
   mma_bf16_ss(tmem_d, da, db, idesc, accumulate != 0);
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   __shared__ __align__(1024) uint8_t s_fixed[FIXED_SMEM];
@@ -191,7 +192,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         if (elect_one()) {
           mbar_expect_tx(&bars[cur.full_bar], cur.expect_bytes);
           tma_load_2d(smem + cur.smem_off, &p.tmaps[cur.tensor], cur.col0, cur.row0 + (cur.tile_rows ? m0 : 0), &bars[cur.full_bar]);
-          if (p.trace && blockIdx.x == 0 && it == p.trace_it) p.trace[i] = clock64();
+          if (TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it) p.trace[i] = clock64();
         }
         __syncwarp();
         cur = nxt;
@@ -204,7 +205,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles && p.n_mmas > 0; tile += gridDim.x, ++it) {
       DevMmaOp cur = p.mmas[0];
-      const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it;
+      const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it;
       for (int i = 0; i < p.n_mmas; ++i) {
         const DevMmaOp nxt = p.mmas[i + 1 < p.n_mmas ? i + 1 : i];
         if (tr && lane == 0) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
@@ -261,7 +262,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         const int store_col0 = (int)w2.x;
         const bool has_bias = mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32;
 
-        const bool tr = p.trace && blockIdx.x == 0 && it == p.trace_it && et == 0;
+        const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it && et == 0;
         unsigned long long* tp = p.trace + trace_base + TRACE_EPI * i;
         if (tr) tp[0] = clock64();
         // bias of this op's columns: two coalesced loads per warp, issued before the accumulator wait
@@ -500,7 +501,8 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   h->smem_bytes = (size_t)d->n_units * UNIT_BYTES;      // dynamic part; FIXED_SMEM bytes are static
   static size_t configured = 0;
   if (h->smem_bytes > configured) {
-    err = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    err = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: smem %zu B: %s", h->smem_bytes, cudaGetErrorString(err)); return RL_ERR_CUDA; }
     configured = h->smem_bytes;
   }
@@ -550,7 +552,8 @@ extern "C" int rl_chain_run(void* handle, int32_t rows, void* stream) {
   p.rows = rows;
   p.num_tiles = (rows + 127) / 128;
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  mlp_chain_kernel<<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
+  if (p.trace) mlp_chain_kernel<true><<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
+  else mlp_chain_kernel<false><<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
   return check_launch("mlp_chain_kernel");
 }
 

@@ -63,14 +63,15 @@ class AccUse:
 class ChainProgram:
     """Builder + container of one chain program."""
 
-    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None):
+    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1):
         """Shared-memory units: [inputs | pool | stages]; `regions`: {name: (first tmem column, width)};
         `region_worker`: regions whose accumulator uses are read by ONE epilogue op -> the worker that owns
         them (a waiter must see every phase of a barrier, so such a region cannot change hands); the other
         regions are read by both workers, chunk c by worker c % 2."""
         self.name = name
         self.n_inputs, self.n_pool, self.n_stages = n_inputs, n_pool, n_stages
-        self.n_units = n_inputs + n_pool + n_stages
+        self.stage_units = stage_units      # 16 KB units per ring stage (2: boxes of up to 256 rows, N = 256 MMAs)
+        self.n_units = n_inputs + n_pool + n_stages * stage_units
         assert self.n_units <= _lib.DEFINES["RL_CHAIN_MAX_UNITS"]
         self.tensors = []                # (torch tensor 2-D view, box_rows)
         self.bar_count = []
@@ -82,7 +83,7 @@ class ChainProgram:
         self.regions = dict(regions)
         # resources
         self.pool_units = [n_inputs + i for i in range(n_pool)]
-        self.stage_units = [n_inputs + n_pool + i for i in range(n_stages)]
+        self.stage_unit0 = [n_inputs + n_pool + i * stage_units for i in range(n_stages)]
         # a barrier must have ONE waiting agent that sees every phase (waits name a phase only by its parity):
         # each stage has one "full" barrier per consumer role and the producer signals the one of the role
         # that will read this particular landing
@@ -125,7 +126,7 @@ class ChainProgram:
     def tensor(self, t, box_rows):
         assert t.dim() == 2 and t.dtype == torch.bfloat16 and t.stride(1) == 1
         assert (t.stride(0) * 2) % 16 == 0 and t.data_ptr() % 16 == 0, "TMA operand alignment"
-        assert 8 <= box_rows <= 256 and box_rows * 128 <= UNIT
+        assert 8 <= box_rows <= 256 and box_rows * 128 <= UNIT * self.stage_units
         self.tensors.append((t, box_rows))
         assert len(self.tensors) <= _lib.DEFINES["RL_CHAIN_MAX_TENSORS"]
         return len(self.tensors) - 1
@@ -170,7 +171,7 @@ class ChainProgram:
             self.stage_full[consumer] = [self._bar(1, "stage%d.full.%s" % (i, consumer)) for i in range(self.n_stages)]
         full = self.stage_full[consumer][s]
         ordn = self._signal(full)
-        off = self.stage_units[s] * UNIT
+        off = self.stage_unit0[s] * UNIT
         self.loads.append(dict(wait=wait, full_bar=full, tensor=tensor, smem_off=off, col0=col0, row0=row0,
                                bytes=box_rows * 128, tile_rows=int(tile_rows)))
         return StageUse(s, off, _Wait(full, ordn), self.stage_empty[s])
@@ -212,7 +213,7 @@ class ChainProgram:
             acc.full = _Wait(self.acc_full[acc.region], self._signal(self.acc_full[acc.region]))
             commits.append(self.acc_full[acc.region])
         width = self.regions[acc.region][1]
-        assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 128
+        assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 128 * self.stage_units
         assert len(waits) <= 3 and len(commits) <= 3
         self.mmas.append(dict(a_off=a.off, b_off=b.off, n=n, tmem_col=acc.col + col_off, k_steps=k_steps,
                               accumulate=int(accumulate), waits=waits, commits=commits))
@@ -462,7 +463,9 @@ class Emulator:
         p = self.p
         tiles = list(range(cta, self.num_tiles, self.n_ctas))
         bars = [Emulator.Bar(c) for c in p.bar_count]
-        units = [torch.zeros(128, 64) for _ in range(p.n_units)]
+        flat_smem = torch.zeros(128 * p.n_units, 64)       # unit u = rows [128 u, 128 u + 128)
+        units = [flat_smem[128 * u:128 * u + 128] for u in range(p.n_units)]
+        nun = lambda off, rows: range(off // UNIT, (off + rows * 128 - 1) // UNIT + 1)
         unit_readers = [0] * p.n_units       # issued, not yet executed async reads (MMA operands, TMA stores)
         unit_loading = [0] * p.n_units       # TMA loads in flight into the unit
         tmem = torch.zeros(128, 512)
@@ -500,10 +503,10 @@ class Emulator:
                 m0 = tile * 128
                 for o in p.loads:
                     yield from spec_wait(o["wait"], it, "load")
-                    u = o["smem_off"] // UNIT
-                    if unit_readers[u] or unit_loading[u]:
-                        raise ChainHazard("TMA load into unit %d while it is still read / loaded (%s)" % (u, p.name))
-                    unit_loading[u] += 1
+                    for u in nun(o["smem_off"], o["bytes"] // 128):
+                        if unit_readers[u] or unit_loading[u]:
+                            raise ChainHazard("TMA load into unit %d while it is still read / loaded (%s)" % (u, p.name))
+                        unit_loading[u] += 1
                     bars[o["full_bar"]].arrive_expect(o["bytes"])
                     loads_inflight.append((o, m0))
                     yield
@@ -518,10 +521,11 @@ class Emulator:
             cc = max(0, min(64, t.shape[1] - o["col0"]))
             if rr > 0 and cc > 0:
                 box[:rr, :cc] = t[r0:r0 + rr, o["col0"]:o["col0"] + cc].float()
-            if unit_readers[u]:
-                raise ChainHazard("TMA load landed in unit %d under a reader" % u)
-            units[u][:box_rows] = box
-            unit_loading[u] -= 1
+            for uu in nun(o["smem_off"], box_rows):
+                if unit_readers[uu]:
+                    raise ChainHazard("TMA load landed in unit %d under a reader" % uu)
+                unit_loading[uu] -= 1
+            flat_smem[128 * u:128 * u + box_rows] = box
             bars[o["full_bar"]].complete_tx(o["bytes"])
 
         def mma_role():
@@ -529,8 +533,7 @@ class Emulator:
                 for o in p.mmas:
                     for w in o["waits"]:
                         yield from spec_wait(w, it, "mma")
-                    ua, ub = o["a_off"] // UNIT, o["b_off"] // UNIT
-                    for u in (ua, ub):
+                    for u in [o["a_off"] // UNIT] + list(nun(o["b_off"], o["n"])):
                         if unit_loading[u]:
                             raise ChainHazard("MMA reads unit %d while a TMA load is in flight" % u)
                         unit_readers[u] += 1
@@ -544,14 +547,14 @@ class Emulator:
             ua, ub = o["a_off"] // UNIT, o["b_off"] // UNIT
             n, c0 = o["n"], o["tmem_col"]
             k = 16 * o["k_steps"]
-            A, B = units[ua][:, :k], units[ub][:n, :k]
+            A, B = units[ua][:, :k], flat_smem[128 * ub:128 * ub + n, :k]
             d = A @ B.t()
             if o["accumulate"]:
                 tmem[:, c0:c0 + n] += d
             else:
                 tmem[:, c0:c0 + n] = d
-            unit_readers[ua] -= 1
-            unit_readers[ub] -= 1
+            for u in [ua] + list(nun(o["b_off"], n)):
+                unit_readers[u] -= 1
 
         def epi_role(wk):
             sg = store_groups[wk]
@@ -685,7 +688,8 @@ def _dense(p, a_boxes, w_tensor, n_out, acc, k_last_steps=4, release_a=True, w_r
     """acc[:, :n_out] = sum_j A box j * W[w_row0 : w_row0 + n_out, 64 j : 64 j + 64]^T in halves of <= 128 output
     columns (one ring stage per weight box).  Closes the accumulator."""
     nk = len(a_boxes)
-    halves = [(h, min(128, n_out - h)) for h in range(0, n_out, 128)]
+    wmax = 128 * p.stage_units
+    halves = [(h, min(wmax, n_out - h)) for h in range(0, n_out, wmax)]
     for j, a in enumerate(a_boxes):
         for hi, (h0, hn) in enumerate(halves):
             st = p.load_stage(w_tensor, col0=64 * j, row0=w_row0 + h0)
@@ -712,15 +716,16 @@ def _round16(n):
     return (n + 15) // 16 * 16
 
 
-def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=6):
+def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=3, stage_units=2):
     """encoder(priv) -> latent merged into the [obs | latent] box -> actor mean / critic value
     (actor_critic.py:124-173 `act` / `evaluate` on one batch; ppo.py:102-107 inside the update).
     T: tensors + parameter offsets (see ActorCritic._chain_tensors).  save: also store every hidden
     activation (the backward needs them).  trunk=False: only refresh the latent slot of Xac."""
-    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=REGIONS, name="teacher_forward")
+    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=REGIONS, name="teacher_forward", stage_units=stage_units)
     p.params = T["params"]
+    wbox = lambda w: min(128 * stage_units, _round16(w.shape[0]))      # weight box rows
     tXp, tXac = p.tensor(T["Xp"], 128), p.tensor(T["Xac"], 128)
-    tWe1, tWe2 = p.tensor(T["We1"], 128), p.tensor(T["We2"], 128)
+    tWe1, tWe2 = p.tensor(T["We1"], wbox(T["We1"])), p.tensor(T["We2"], wbox(T["We2"]))
     lat = T["We3"].shape[0]
     tWe3 = p.tensor(T["We3"], _round16(lat))
     st = lambda name: p.tensor(T[name], 128) if save else None
@@ -756,7 +761,7 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
     if want_value:
         nets.append(("c", H, T["Wc2"], T["Wc3"], T["Wc4"], "C2", "C3", T["b_c2"], T["b_c3"], T["b_c4"], 1))
     for ni, (tag, off, W2, W3, W4, n2, n3, b2, b3, b4, out_id) in enumerate(nets):
-        tW2, tW3 = p.tensor(W2, 128), p.tensor(W3, 128)
+        tW2, tW3 = p.tensor(W2, wbox(W2)), p.tensor(W3, wbox(W3))
         n_out = W4.shape[0]
         tW4 = p.tensor(W4, _round16(n_out))
         t2, t3 = st(n2), st(n3)
@@ -773,10 +778,11 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
                                      store=None if tY1 is None else (tY1, off + 64 * j), last=True)
 
         def l2(j):
-            for h in range(0, W2.shape[0], 128):
+            wmax = 128 * p.stage_units
+            for h in range(0, W2.shape[0], wmax):
                 s = p.load_stage(tW2, col0=64 * j, row0=h)
-                p.mma(chunk_box[j], s, n=128, acc=acc2, col_off=h, k_steps=4, accumulate=j > 0,
-                      acc_last=(j == nch - 1 and h + 128 >= W2.shape[0]), a_release=(h + 128 >= W2.shape[0]))
+                p.mma(chunk_box[j], s, n=min(wmax, W2.shape[0] - h), acc=acc2, col_off=h, k_steps=4, accumulate=j > 0,
+                      acc_last=(j == nch - 1 and h + wmax >= W2.shape[0]), a_release=(h + wmax >= W2.shape[0]))
         l1(0)
         for j in range(1, nch):
             l1(j)
@@ -858,9 +864,9 @@ def trunk_backward_program(T, n_stages=6):
 def adaptation_forward_program(T, save=True):
     """adaptation_module(obs_history) (actor_critic.py:158-162; ppo.py:157): the 630-wide input streams
     through the ring next to the first layer's weights, the two small layers stay on chip."""
-    p = ChainProgram(n_pool=6, n_stages=8, n_inputs=0, regions=REGIONS, name="adaptation_forward")
+    p = ChainProgram(n_pool=6, n_stages=4, n_inputs=0, regions=REGIONS, name="adaptation_forward", stage_units=2)
     p.params = T["params"]
-    tXh, tWd1 = p.tensor(T["Xh"], 128), p.tensor(T["Wd1"], 128)
+    tXh, tWd1 = p.tensor(T["Xh"], 128), p.tensor(T["Wd1"], min(256, _round16(T["Wd1"].shape[0])))
     n1, n2, n3 = T["Wd1"].shape[0], T["Wd2"].shape[0], T["Wd3"].shape[0]
     tWd2, tWd3 = p.tensor(T["Wd2"], _round16(n2)), p.tensor(T["Wd3"], _round16(n3))
     st = lambda name: p.tensor(T[name], 128) if save else None
@@ -870,10 +876,10 @@ def adaptation_forward_program(T, save=True):
     acc = p.acc("BIG")
     for j in range(nk):
         a = p.load_stage(tXh, col0=64 * j, row0=0, tile_rows=True)
-        halves = list(range(0, n1, 128))
+        halves = list(range(0, n1, 256))
         for hi, h in enumerate(halves):
             b = p.load_stage(tWd1, col0=64 * j, row0=h)
-            p.mma(a, b, n=min(128, n1 - h), acc=acc, col_off=h, k_steps=min(4, (K - 64 * j + 15) // 16), accumulate=j > 0,
+            p.mma(a, b, n=min(256, n1 - h), acc=acc, col_off=h, k_steps=min(4, (K - 64 * j + 15) // 16), accumulate=j > 0,
                   acc_last=(j == nk - 1 and hi == len(halves) - 1), a_release=(hi == len(halves) - 1))
     d1 = _boxes(p, acc, n1, EPI_BIAS_ELU, T["b_d1"], tD1)
     acc = p.acc("C0")

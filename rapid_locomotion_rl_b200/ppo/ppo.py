@@ -132,19 +132,18 @@ class PPO:
                  EPI_ATOMIC, transposed=1, db=L.gb.data_ptr(), split_k=split)
 
     def _wgrad_flush(self):
-        """Launches the queued weight-gradient problems as one grouped grid (csrc/gemm_tc.cu): largest first,
-        split-K sized so that the whole group is ~4 CTAs per SM."""
+        """Launches the queued weight-gradient problems as one grouped grid (csrc/gemm_tc.cu), largest first."""
         if not self._wq:
             return
         qs = sorted(self._wq, key=lambda q: -(q.M * q.N))
         self._wq = []
-        tiles = [((q.M + 127) // 128) * ((q.N + (127 if q.N > 64 else 63)) // (128 if q.N > 64 else 64)) for q in qs]
-        work = [t * max(q.N, 64) for t, q in zip(tiles, qs)]            # ~ MMA time per k-block of the problem
+        tiles = sum(((q.M + 127) // 128) * ((q.N + (127 if q.N > 64 else 63)) // (128 if q.N > 64 else 64)) for q in qs)
         total_kb = (qs[0].K + 63) // 64
-        budget = 4 * 148
-        for q, t, wk in zip(qs, tiles, work):
-            share = max(1.0, budget * wk / float(sum(work)))
-            q.split_k = int(max(1, min(total_kb, round(share / t))))
+        # every CTA reduces the same number of 64-row k-blocks (equal durations, no straggler problem):
+        # about six waves of CTAs over the 148 SMs, at most 64 k-blocks each
+        kb_per_cta = int(max(4, min(64, total_kb * tiles / (148.0 * 6))))
+        for q in qs:
+            q.split_k = max(1, (total_kb + kb_per_cta - 1) // kb_per_cta)
         arr = (_lib.RlWgradProblem * len(qs))(*qs)
         _lib.check(self._lib.rl_wgrad_grouped(arr, len(qs), _lib.current_stream()))
 
