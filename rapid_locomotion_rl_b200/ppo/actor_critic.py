@@ -236,6 +236,13 @@ class ActorCritic(nn.Module):
         self._chain(("adaptation", True), lambda T: chain.adaptation_forward_program(T, save=True))
         self._chain(("adaptation_backward",), chain.adaptation_backward_program)
 
+    def prepare_rollout_chains(self, rows):
+        """Workspace + policy chain for `act` / `evaluate` on `rows` envs, compiled ahead of a graph capture."""
+        self.workspace(rows)
+        if self.use_chain:
+            from . import chain
+            self._chain(("teacher", False, True, True), lambda T: chain.teacher_forward_program(T, save=False))
+
     def _chain(self, key, build):
         prog = self._chains.get(key)
         if prog is None:
