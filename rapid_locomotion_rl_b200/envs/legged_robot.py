@@ -264,9 +264,10 @@ class LeggedRobot:
     def use_device_step_counter(self, enable=True):
         """Key the in-kernel RNG with a device-resident step counter so that `step()` can be captured
         in a CUDA graph and replayed (kernel arguments, including the host step number, are frozen
-        inside a graph).  The counter continues from `common_step_counter`."""
+        inside a graph).  The counter continues from `common_step_counter`: the next step() keys its draws
+        with common_step_counter + 1, exactly as the host-counter path does."""
         if enable:
-            self._step_state = torch.tensor([self.common_step_counter, 0], dtype=torch.int64, device=self.device)
+            self._step_state = torch.tensor([self.common_step_counter + 1, 0], dtype=torch.int64, device=self.device)
             self._bufs.step_state = self._step_state.data_ptr()
         else:
             self._bufs.step_state = None
