@@ -298,6 +298,10 @@ def run_ours(args):
         torch.cuda.empty_cache()
         ppo = ppo_bench(args.ppo_envs, 24, device, world, pk)
 
+    runner = None
+    if world == 1 and not args.quick:
+        runner = runner_bench(args.ppo_envs, device)
+
     out = {
         "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -319,6 +323,7 @@ def run_ours(args):
                      "kernel": "env_step_kernel<true>", "algorithmic_bytes_per_launch": args.envs * bpe},
         "also": also,
         "ppo": ppo,
+        "runner": runner,
     }
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(sample_envs=4000, steps=10, warmup=2)
@@ -377,6 +382,30 @@ def ppo_bench(n_envs, T, device, world, pk, iters=3):
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": tf / (pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]), "traffic": None},
             "losses": list(res), "dtype": "bf16 operands, fp32 accumulate / master weights"}
+
+
+def runner_bench(n_envs, device, iters=10):
+    """the whole training iteration through the drop-in Runner - 24 x [policy chain, Normal
+    sample, fused env step, history push, storage writes] replayed from CUDA graphs, then GAE + PPO.update.
+    The simulator is outside the path: its state tensors stay as they are between steps."""
+    import torch
+    from cases import build_case
+    from rapid_locomotion_rl_b200.envs import HistoryWrapper, VelocityTrackingEasyEnv
+    from rapid_locomotion_rl_b200.ppo import Runner
+    cfg, robot, terrain = build_case("mc_flat", n_envs)
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device=device, headless=True, cfg=cfg, terrain=terrain, seed=0))
+    torch.manual_seed(0)
+    res = {}
+    for graph in (True, False):
+        r = Runner(env, device=device, graph_rollout=graph)
+        # one learn() call: the first 7 iterations warm up (eager rollout, then one capture per history-ring
+        # phase); every iteration ends with update()'s device->host read of the losses, so the per-iteration
+        # host times are device-complete
+        hist = r.learn(7 + iters)
+        res["graph" if graph else "eager"] = sum(h["time_iter"] for h in hist[7:]) / iters
+    return {"metric": "training env-steps/s (rollout + GAE + PPO.update, synthetic simulator state)", "envs": n_envs,
+            "steps_per_env": 24, "value": n_envs * 24 / res["graph"], "ms_per_iteration": res["graph"] * 1e3,
+            "ms_per_iteration_eager_rollout": res["eager"] * 1e3}
 
 
 def cpu_env_arm(envs, steps, warmup, threads=None):
