@@ -232,6 +232,10 @@ typedef struct RlEnvBuffers {
   uint64_t* step_state;         /* [2] */
 } RlEnvBuffers;
 
+/* profiling aid: enable / read the globaltimer phase stamps of one CTA of the fused env-step kernel
+ * (entry, SoA loads issued, staged rows landed, phase 1 start / end, barrier, outputs written, barrier,
+ * stores issued); out_host16 may be NULL */
+int rl_debug_env_trace(int32_t enable, uint64_t* out_host16);
 const char* rl_last_error(void);
 const char* rl_version(void);
 /* sizeof(struct <name>) as compiled into the library (-1 for an unknown name): lets a

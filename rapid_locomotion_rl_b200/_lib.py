@@ -90,6 +90,7 @@ SIGNATURES = {
     "rl_last_error": (C.c_char_p, []),
     "rl_version": (C.c_char_p, []),
     "rl_sizeof": (C.c_int64, [C.c_char_p]),
+    "rl_debug_env_trace": (C.c_int, [C.c_int32, _P]),
     "rl_env_torques": (C.c_int, [_P, _P, _P]),
     "rl_env_post_physics": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "rl_env_step_fused": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),

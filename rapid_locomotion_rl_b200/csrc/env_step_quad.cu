@@ -34,10 +34,41 @@ enum Frame { F_BLV = 0, F_BAV = 3, F_GRAV = 6, F_VWX = 9, F_VWY = 10, F_CMDN = 1
 enum Ct { C_COLL = 0, C_STUMBLE, C_FCF, C_AIR, C_RESET, C_TIMEOUT, NCT = 6 };
 constexpr int NR = RL_MAX_TERMS;
 
-template <bool FUSE, int MINB>
+// profiling aid (RL_ENV_TRACE=1): globaltimer stamps of one CTA's phases, read back by rl_debug_env_trace
+__device__ unsigned long long g_env_trace[16];
+__device__ int g_env_trace_on = 0;
+__device__ __forceinline__ void env_stamp(int i) {
+#ifdef RL_ENV_TRACE      // compiled out by default: even a predicated-off stamp costs a global load per thread
+  if (g_env_trace_on && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_env_trace[i] = t;
+  }
+#endif
+}
+
+// STD = the shipped training configuration (both robots): 'P' control, exactly the 12 default reward terms in
+// their default order, observation noise on, positive-reward clip on, no pushes / heights / time-out resets /
+// terminal body height / termination term / global reference.  Those switches become compile-time constants:
+// the uniform branches, their constant-bank loads and the run-time term dispatch disappear (the kernel is
+// instruction-issue bound: ~1600 warp instructions per 32 envs, 40 % of them integer / branch / constant loads).
+constexpr uint32_t STD_TERM_MASK = 0xFFFu;
+
+template <bool FUSE, int MINB, bool STD>
 __global__ void __launch_bounds__(QTHREADS, MINB)
 env_step_quad_kernel(const __grid_constant__ StepArgs args) {
+  env_stamp(0);
   const RlEnvCfg& cfg = args.cfg;
+  const int c_control = STD ? 0 : cfg.control_type;
+  const bool c_push = STD ? false : cfg.push_robots != 0;
+  const bool c_heights = STD ? false : cfg.measure_heights != 0;
+  const bool c_noise = STD ? true : cfg.add_noise != 0;
+  const bool c_timeout = STD ? false : cfg.timeout_resets != 0;
+  const bool c_tbh = STD ? false : cfg.use_terminal_body_height != 0;
+  const bool c_term = STD ? false : cfg.has_termination != 0;
+  const bool c_pos = STD ? true : cfg.only_positive_rewards != 0;
+  const bool c_global = STD ? false : cfg.global_reference != 0;
+  const int c_n_terms = STD ? 12 : cfg.n_terms;
   const RlEnvBuffers& b = args.b;
   const int N = cfg.num_envs, NB = cfg.num_bodies;
   const int tile0 = blockIdx.x * QT;
@@ -45,10 +76,10 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int e = tile0 + lane;
   const bool valid = lane < n_valid;
-  const int P = cfg.measure_heights ? cfg.num_height_points : 0;
+  const int P = c_heights ? cfg.num_height_points : 0;
   constexpr int W = 42;
   const uint64_t rng_step = args.step + (b.step_state ? b.step_state[0] : 0ull);
-  const uint32_t tmask = cfg.term_mask;
+  const uint32_t tmask = STD ? STD_TERM_MASK : cfg.term_mask;
   const float co = cfg.clip_obs;
 
   extern __shared__ __align__(16) float smem[];
@@ -118,9 +149,9 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
       kp[k] = b.Kp_factors[ix]; kd[k] = b.Kd_factors[ix]; ms[k] = b.motor_strengths[ix];
       la[k] = b.last_actions[ix]; ldv[k] = b.last_dof_vel[ix];
     }
-    if (w < cfg.n_terms) { es0 = pe[w * N]; cs0 = pc[w * N]; }
-    if (w + 4 < cfg.n_terms) { es1 = pe[(w + 4) * N]; cs1 = pc[(w + 4) * N]; }
-    if (w + 8 < cfg.n_terms) { es2 = pe[(w + 8) * N]; cs2 = pc[(w + 8) * N]; }
+    if (w < c_n_terms) { es0 = pe[w * N]; cs0 = pc[w * N]; }
+    if (w + 4 < c_n_terms) { es1 = pe[(w + 4) * N]; cs1 = pc[(w + 4) * N]; }
+    if (w + 8 < c_n_terms) { es2 = pe[(w + 8) * N]; cs2 = pc[(w + 8) * N]; }
     ep = (int)b.episode_length_buf[e];
     cmd = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
     if (w == 1) {
@@ -140,11 +171,13 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
       for (int k = 0; k < 3; ++k) sc6[3 + k] = b.com_displacements[k * N + e];
     } else if (w == 3) {
       ex0 = pe[RL_ROW_TOTAL * N];
-      if (cfg.has_termination) { ex1 = pe[RL_ROW_TERMINATION * N]; ex2 = pc[RL_ROW_TERMINATION * N]; }
+      if (c_term) { ex1 = pe[RL_ROW_TERMINATION * N]; ex2 = pc[RL_ROW_TERMINATION * N]; }
     }
   }
+  env_stamp(1);
   __syncthreads();                      // mbarrier init / cooperative stores visible
   if (bulk_in) mbar_wait(&s_bar, 0);    // all staged bytes have landed
+  env_stamp(2);
   ep += 1;                              // :152
 
   // ---- teleport (:768-791) by warp 0, then the height phase if enabled ---------------------------------
@@ -159,7 +192,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
     if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
   }
-  if (cfg.measure_heights) {
+  if (c_heights) {
     __syncthreads();
     const float hscale = cfg.horizontal_scale, vscale = cfg.vertical_scale;
 #pragma unroll 1
@@ -195,7 +228,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
         mh[p] = h;
         acc += bz - h;
         float o = clampf(bz - 0.5f - h, -1.f, 1.f) * cfg.obs_scale_height;
-        if (cfg.add_noise) {
+        if (c_noise) {
           if (nu) {
             o += (2.0f * nu[W + p] - 1.0f) * cfg.noise_scale_height;
           } else {
@@ -213,6 +246,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     __syncthreads();
   }
 
+  env_stamp(3);
   // =================================== phase 1 ===========================================================
   float tq[3], oq[3], oqd[3], oa[3], pm[3];        // this leg's torques / observation / priv columns
   float g0 = 0.f, g1 = 0.f, g2 = 0.f;              // warp 0: noisy gravity columns
@@ -239,11 +273,11 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
       if (FUSE) {
         float as = a * cfg.action_scale;
         if (k == 0) as *= cfg.hip_scale_reduction;             // dofs 0,3,6,9 (:666)
-        if (cfg.control_type == 0) {
+        if (c_control == 0) {
           const float jpt = as + cfg.default_dof_pos[j];
           b.joint_pos_target[ix] = jpt;
           t = cfg.p_gains[j] * kp[k] * (jpt - q[k]) - cfg.d_gains[j] * kd[k] * qd[k];
-        } else if (cfg.control_type == 1) {
+        } else if (c_control == 1) {
           t = cfg.p_gains[j] * (as - qd[k]) - cfg.d_gains[j] * (qd[k] - ldv[k]) / cfg.sim_dt;
         } else {
           t = as;
@@ -301,7 +335,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     for (int k = 0; k < 3; ++k) pm[k] = clampf((ms[k] - cfg.priv_shift[4]) * cfg.priv_scale[4], -co, co);
 
     // ---- observation noise for this leg's q / qd columns (:392): Philox block w, lanes 0-5 ----
-    if (cfg.add_noise) {
+    if (c_noise) {
       const float* nu = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
       uint32_t r4[4] = {0u, 0u, 0u, 0u};
       if (!nu) Philox::gen(args.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | (uint32_t)w, r4);
@@ -328,7 +362,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
       const V3 blv = quat_rotate_inverse(qx, qy, qz, qw, vw);
       const V3 bav = quat_rotate_inverse(qx, qy, qz, qw, ww);
       const V3 grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
-      if (cfg.push_robots && (ep % cfg.push_interval) == 0) {
+      if (c_push && (ep % cfg.push_interval) == 0) {
         float u0, u1;
         if (b.push_u) { u0 = b.push_u[e]; u1 = b.push_u[N + e]; }
         else { float u4[4]; rng4(args.seed, (uint32_t)e, rng_step, RNG_PUSH, 0, u4); u0 = u4[0]; u1 = u4[1]; }
@@ -348,7 +382,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
       b.last_root_vel[3 * N + e] = ww.x; b.last_root_vel[4 * N + e] = ww.y; b.last_root_vel[5 * N + e] = ww.z;
       // gravity observation columns 0-2 with noise: Philox block 4, lanes 0-2
       g0 = grav.x; g1 = grav.y; g2 = grav.z;
-      if (cfg.add_noise) {
+      if (c_noise) {
         const float* nu = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
         if (nu) {
           g0 += (2.0f * nu[0] - 1.0f) * cfg.noise_scale_core[0];
@@ -366,7 +400,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     } else if (w == 1) {
       // ---- contact terms: termination (:190-202), collision, stumble, contact forces, air time ----
       const float* con = s_con + lane * NB * 3;
-      const float hmean = cfg.measure_heights ? s_hmean[lane] : root[2];
+      const float hmean = c_heights ? s_hmean[lane] : root[2];
       bool reset = false;
 #pragma unroll 1
       for (int k = 0; k < cfg.n_term_bodies; ++k) {
@@ -374,12 +408,12 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
         reset |= sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) > 1.0f;
       }
       bool time_out = false;
-      if (cfg.timeout_resets) {
+      if (c_timeout) {
         time_out = ep > cfg.max_episode_length;
         reset |= time_out;
         b.time_out_buf[e] = time_out ? 1 : 0;
       }
-      if (cfg.use_terminal_body_height) reset |= hmean < cfg.terminal_body_height;
+      if (c_tbh) reset |= hmean < cfg.terminal_body_height;
       b.reset_buf[e] = reset ? 1 : 0;
       b.episode_length_buf[e] = (int64_t)ep;
       float coll = 0.f;
@@ -426,7 +460,9 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
       for (int k = 0; k < 3; ++k) sc6[3 + k] = clampf((sc6[3 + k] - cfg.priv_shift[3]) * cfg.priv_scale[3], -co, co);
     }
   }
+  env_stamp(4);
   __syncthreads();
+  env_stamp(5);
 
   // =================================== phase 2 ===========================================================
   // Every warp evaluates ITS OWN reward terms (i = w, w+4, ...) from the exchanged partial sums, frames and
@@ -443,7 +479,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     auto eval_term = [&](int id) -> float {
       switch (id) {
         case RL_REW_TRACKING_LIN_VEL: {
-          const float vx = cfg.global_reference ? F(F_VWX) : F(F_BLV), vy = cfg.global_reference ? F(F_VWY) : F(F_BLV + 1);
+          const float vx = c_global ? F(F_VWX) : F(F_BLV), vy = c_global ? F(F_VWY) : F(F_BLV + 1);
           return expf(-(sq(cmd.x - vx) + sq(cmd.y - vy)) / cfg.tracking_sigma);
         }
         case RL_REW_TRACKING_ANG_VEL: return expf(-sq(cmd.z - F(F_BAV + 2)) / cfg.tracking_sigma_yaw);
@@ -452,7 +488,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
         case RL_REW_ORIENTATION: return sq(F(F_GRAV)) + sq(F(F_GRAV + 1));
         case RL_REW_TORQUES: return psum(P_TQ2);
         case RL_REW_DOF_ACC: return psum(P_ACC2);
-        case RL_REW_BASE_HEIGHT: return sq((cfg.measure_heights ? s_hmean[lane] : root[2]) - cfg.base_height_target);
+        case RL_REW_BASE_HEIGHT: return sq((c_heights ? s_hmean[lane] : root[2]) - cfg.base_height_target);
         case RL_REW_FEET_AIR_TIME: return CT(C_AIR) * ((cmd_xy_norm > 0.1f) ? 1.f : 0.f);
         case RL_REW_COLLISION: return CT(C_COLL);
         case RL_REW_ACTION_RATE: return psum(P_RATE2);
@@ -471,6 +507,18 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     };
     float* pew = b.episode_sums + e;
     float* pcw = b.command_sums + e;
+    if (STD) {
+      // warp w owns terms w, w + 4, w + 8 - compile-time ids, the dispatch folds away
+      float r0, r1, r2;
+      if (w == 0) { r0 = eval_term(0); r1 = eval_term(4); r2 = eval_term(8); }
+      else if (w == 1) { r0 = eval_term(1); r1 = eval_term(5); r2 = eval_term(9); }
+      else if (w == 2) { r0 = eval_term(2); r1 = eval_term(6); r2 = eval_term(10); }
+      else { r0 = eval_term(3); r1 = eval_term(7); r2 = eval_term(11); }
+      r0 *= cfg.term_scale[w]; r1 *= cfg.term_scale[w + 4]; r2 *= cfg.term_scale[w + 8];
+      pew[w * N] = es0 + r0; pcw[w * N] = cs0 + r0; s_r[w * QT + lane] = r0;
+      pew[(w + 4) * N] = es1 + r1; pcw[(w + 4) * N] = cs1 + r1; s_r[(w + 4) * QT + lane] = r1;
+      pew[(w + 8) * N] = es2 + r2; pcw[(w + 8) * N] = cs2 + r2; s_r[(w + 8) * QT + lane] = r2;
+    } else
 #pragma unroll 1
     for (int k = 0; k < MAXOWN; ++k) {
       const int i = w + 4 * k;
@@ -513,17 +561,24 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     }
   }
   if (dirty) s_root_dirty = 1;
+  env_stamp(6);
   fence_async_smem();
   __syncthreads();
+  env_stamp(7);
 
   // =================================== phase 3: warp 3 closes compute_reward (:314-340) ===================
   if (w == 3 && valid) {
     float rew = 0.f;
+    if (STD) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rew += s_r[i * QT + lane];               // reward_names order
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < cfg.n_terms; ++i) rew += s_r[i * QT + lane];       // reward_names order
-    if (cfg.only_positive_rewards) rew = fmaxf(rew, 0.f);
+      for (int i = 0; i < cfg.n_terms; ++i) rew += s_r[i * QT + lane];
+    }
+    if (c_pos) rew = fmaxf(rew, 0.f);
     b.episode_sums[RL_ROW_TOTAL * N + e] = ex0 + rew;
-    if (cfg.has_termination) {
+    if (c_term) {
       const bool term_flag = s_ct[C_RESET * QT + lane] != 0.f && s_ct[C_TIMEOUT * QT + lane] == 0.f;   // :1554
       const float r = (term_flag ? 1.f : 0.f) * cfg.termination_scale;
       rew += r;
@@ -556,6 +611,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     if (FUSE) stage_out<QTHREADS>(o_tq, s_tq, n_valid * ND);
     if (s_root_dirty) stage_out<QTHREADS>(o_root, s_root, n_valid * 13);
   }
+  env_stamp(8);
   if (b.step_state && tid == 0) {
     // (no fence needed: the counter value read on entry was consumed long ago; this only counts CTAs)
     const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
@@ -573,23 +629,48 @@ static size_t quad_smem_bytes(const RlEnvCfg& cfg) {
   return (size_t)QT * (tile + xchg) * sizeof(float);
 }
 
-template <bool FUSE, int MINB>
+template <bool FUSE, int MINB, bool STD = false>
 static int launch_quad_inst(const StepArgs& args, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(env_step_quad_kernel<FUSE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(env_step_quad_kernel<FUSE, MINB, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     configured = smem;
   }
   const int grid = (args.cfg.num_envs + QT - 1) / QT;
-  env_step_quad_kernel<FUSE, MINB><<<grid, QTHREADS, smem, st>>>(args);
+  env_step_quad_kernel<FUSE, MINB, STD><<<grid, QTHREADS, smem, st>>>(args);
   return check_launch("env_step_quad_kernel");
 }
 
+}  // namespace rl
+extern "C" int rl_debug_env_trace(int32_t enable, uint64_t* out_host16) {
+  int on = enable;
+  cudaMemcpyToSymbol(rl::g_env_trace_on, &on, sizeof(int));
+  if (out_host16) cudaMemcpyFromSymbol(out_host16, rl::g_env_trace, 16 * sizeof(unsigned long long));
+  return RL_OK;
+}
+namespace rl {
 int launch_step_quad(const StepArgs& args, bool fuse_torques, cudaStream_t st) {
   const size_t smem = quad_smem_bytes(args.cfg);
   static int minb = 0;     // RL_QUAD_MINB=6: 85 registers / 6 CTAs per SM instead of 64 / 8 (tuning knob)
   if (!minb) { const char* m = getenv("RL_QUAD_MINB"); minb = (m && atoi(m) == 6) ? 6 : 8; }
+  static int std_ok = -1;   // RL_ENV_STD=0 forces the generic instantiation
+  if (std_ok < 0) { const char* e = getenv("RL_ENV_STD"); std_ok = (e && atoi(e) == 0) ? 0 : 1; }
+  const RlEnvCfg& c = args.cfg;
+  bool is_std = std_ok && c.control_type == 0 && !c.push_robots && !c.measure_heights && c.add_noise && !c.timeout_resets &&
+                !c.use_terminal_body_height && !c.has_termination && c.only_positive_rewards && !c.global_reference &&
+                c.n_terms == 12 && c.term_mask == STD_TERM_MASK;
+  for (int i = 0; is_std && i < 12; ++i) is_std = c.term_id[i] == i;
+  if (is_std) {
+    // small grids (<= 4 CTAs per SM) are pure latency: 80 registers / no spills wins; otherwise 8 CTAs / SM
+    // (64 registers) - measured: 4000 envs 6.9 vs 7.9 us, 32768 envs 16.7 vs 13.9 us, 262144 envs 81.2 vs 80.3 us
+    static int force = -1;
+    if (force < 0) { const char* m = getenv("RL_QUAD_MINB"); force = m ? atoi(m) : 0; }
+    const int n_cta = (c.num_envs + QT - 1) / QT;
+    const bool use6 = force == 6 || (force != 8 && n_cta <= 4 * 148);
+    if (use6) return fuse_torques ? launch_quad_inst<true, 6, true>(args, smem, st) : launch_quad_inst<false, 6, true>(args, smem, st);
+    return fuse_torques ? launch_quad_inst<true, 8, true>(args, smem, st) : launch_quad_inst<false, 8, true>(args, smem, st);
+  }
   if (minb == 6) return fuse_torques ? launch_quad_inst<true, 6>(args, smem, st) : launch_quad_inst<false, 6>(args, smem, st);
   return fuse_torques ? launch_quad_inst<true, 8>(args, smem, st) : launch_quad_inst<false, 8>(args, smem, st);
 }
