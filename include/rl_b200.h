@@ -393,7 +393,7 @@ typedef struct RlWgradProblem {
   float* db;                        /* may be NULL */
   int32_t M, N, K;
   int32_t ld_dy, ld_x, ld_dw;
-  int32_t split_k;
+  int32_t split_k;                  /* k ranges per output tile; 0 = let the library choose */
   int32_t reserved;
 } RlWgradProblem;
 int rl_wgrad_grouped(const RlWgradProblem* problems_host, int32_t n, void* stream);

@@ -477,16 +477,21 @@ static int launch_grouped(const GroupedArgs& G, int total, cudaStream_t st) {
 
 // C-ABI: n weight-gradient problems dW_i[M_i, N_i] += dY_i[K, M_i]^T X_i[K, N_i] (+ db_i[m] += sum_k dY_i[k, m])
 // in at most two launches (one per tile width).  split_k_i: see rl_gemm_bf16.
+int wgrad_persistent_launch(const RlWgradProblem* pr, int n, cudaStream_t st);   // wgrad_persistent.cu
+
 extern "C" int rl_wgrad_grouped(const RlWgradProblem* pr, int32_t n, void* stream) {
   RL_REQUIRE(pr && n > 0, RL_ERR_BAD_ARG, "rl_wgrad_grouped: no problems");
   cudaStream_t st = (cudaStream_t)stream;
+  static int persistent = -1;     // RL_WGRAD_PERSISTENT=0: one split-K CTA per (tile, k range) instead of the persistent kernel
+  if (persistent < 0) { const char* e = getenv("RL_WGRAD_PERSISTENT"); persistent = (e && atoi(e) == 0) ? 0 : 1; }
+  if (persistent) return wgrad_persistent_launch(pr, n, st);
   for (int width = 0; width < 2; ++width) {          // 0: outputs with N <= 64 (BN = 64), 1: the rest (BN = 128)
     GroupedArgs G;
     G.n = 0;
     int total = 0;
     for (int i = 0; i < n; ++i) {
       const RlWgradProblem& q = pr[i];
-      RL_REQUIRE(q.dY && q.X && q.dW && q.M > 0 && q.N > 0 && q.K > 0 && q.split_k >= 1, RL_ERR_BAD_ARG, "rl_wgrad_grouped: problem %d", i);
+      RL_REQUIRE(q.dY && q.X && q.dW && q.M > 0 && q.N > 0 && q.K > 0 && q.split_k >= 0, RL_ERR_BAD_ARG, "rl_wgrad_grouped: problem %d", i);
       if ((q.N <= 64) != (width == 0)) continue;
       if (G.n == MAX_GROUP) {                         // flush a full group
         G.first_cta[G.n] = total;
@@ -495,7 +500,7 @@ extern "C" int rl_wgrad_grouped(const RlWgradProblem* pr, int32_t n, void* strea
         G.n = 0; total = 0;
       }
       dim3 grid;
-      int rc = build_wgrad_args(G.g[G.n], q.dY, q.X, q.dW, q.db, q.M, q.N, q.K, q.ld_dy, q.ld_x, q.ld_dw, q.split_k, &grid);
+      int rc = build_wgrad_args(G.g[G.n], q.dY, q.X, q.dW, q.db, q.M, q.N, q.K, q.ld_dy, q.ld_x, q.ld_dw, q.split_k > 0 ? q.split_k : 16, &grid);
       if (rc != RL_OK) return rc;
       G.first_cta[G.n] = total;
       G.grid_x[G.n] = grid.x; G.grid_y[G.n] = grid.y;

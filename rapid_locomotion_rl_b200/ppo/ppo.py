@@ -137,6 +137,13 @@ class PPO:
             return
         qs = sorted(self._wq, key=lambda q: -(q.M * q.N))
         self._wq = []
+        if os.environ.get("RL_WGRAD_PERSISTENT", "1") != "0":
+            # persistent kernel (csrc/wgrad_persistent.cu): the library sizes the work items itself
+            for q in qs:
+                q.split_k = 0
+            arr = (_lib.RlWgradProblem * len(qs))(*qs)
+            _lib.check(self._lib.rl_wgrad_grouped(arr, len(qs), _lib.current_stream()))
+            return
         tiles = sum(((q.M + 127) // 128) * ((q.N + (127 if q.N > 64 else 63)) // (128 if q.N > 64 else 64)) for q in qs)
         total_kb = (qs[0].K + 63) // 64
         # every CTA reduces the same number of 64-row k-blocks (equal durations, no straggler problem):

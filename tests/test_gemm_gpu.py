@@ -120,3 +120,35 @@ def test_bad_arguments():
         gemm(A[:, 1:], B, C, M=128, N=128, K=63)                            # misaligned base
     with pytest.raises(_lib.RlError):
         gemm(A, B, C, M=128, N=128, K=64, split_k=2)                        # split-K without atomics
+
+
+@pytest.mark.parametrize("K", [64, 1000, 24000])
+def test_wgrad_grouped_vs_torch(K):
+    """rl_wgrad_grouped (persistent kernel: all layers' dW / db in one launch) against fp32 torch on the
+    same bf16 operands: dW += dY^T X, db += column sums of dY; shapes of the learner's layers."""
+    import ctypes as C
+    from rapid_locomotion_rl_b200 import _lib
+    lib = _lib.lib()
+    _lib.check(lib.rl_gemm_init())
+    torch.manual_seed(K)
+    shapes = [(256, 512), (128, 256), (12, 128), (1, 128), (1024, 60), (256, 18), (18, 32), (256, 630)]
+    probs, keep = [], []
+    for M, N in shapes:
+        ldy, ldx = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+        dY = torch.zeros(K, ldy, dtype=torch.bfloat16, device="cuda"); dY[:, :M] = torch.randn(K, M, device="cuda") * 0.1
+        X = torch.zeros(K, ldx, dtype=torch.bfloat16, device="cuda"); X[:, :N] = torch.randn(K, N, device="cuda")
+        dW = torch.randn(M, N, device="cuda") * 0.01          # accumulates on top of existing content
+        db = torch.randn(M, device="cuda") * 0.01
+        ref_w = dW + dY[:, :M].float().t() @ X[:, :N].float()
+        ref_b = db + dY[:, :M].float().sum(0)
+        q = _lib.RlWgradProblem()
+        q.dY, q.X, q.dW, q.db = dY.data_ptr(), X.data_ptr(), dW.data_ptr(), db.data_ptr()
+        q.M, q.N, q.K, q.ld_dy, q.ld_x, q.ld_dw, q.split_k = M, N, K, ldy, ldx, N, 0
+        probs.append(q); keep.append((dY, X, dW, db, ref_w, ref_b))
+    arr = (_lib.RlWgradProblem * len(probs))(*probs)
+    _lib.check(lib.rl_wgrad_grouped(arr, len(probs), _lib.current_stream()))
+    torch.cuda.synchronize()
+    for (M, N), (dY, X, dW, db, ref_w, ref_b) in zip(shapes, keep):
+        tol = 2e-3 * (K ** 0.5)
+        torch.testing.assert_close(dW, ref_w, rtol=2e-3, atol=tol, msg="dW %dx%d" % (M, N))
+        torch.testing.assert_close(db, ref_b, rtol=2e-3, atol=tol, msg="db %d" % M)
