@@ -567,6 +567,38 @@ int rl_policy_sample(const float* mean, const float* std, int32_t N, uint64_t se
                      const float* inj_normal, float* actions, float* logp, float* mu_out, float* sigma_out,
                      void* stream);
 
+/* rollout_storage.py:54-71 RolloutStorage.add_transitions: one launch writes the transition of every env into
+ * the [t] slices of the storage (the reference: eleven copy_ kernels per step).  Sources are [N, dim] rows with
+ * the given pitches (the observation history is a strided view of the ring buffer); destinations are dense. */
+typedef struct RlStorageAdd {
+  const float* obs;
+  const float* priv;
+  const float* hist;
+  const float* actions;
+  const float* mu;
+  const float* sigma;
+  const float* rewards;
+  const float* values;
+  const float* logp;
+  const float* bins;
+  const uint8_t* dones;
+  float* dst_obs;
+  float* dst_priv;
+  float* dst_hist;
+  float* dst_actions;
+  float* dst_mu;
+  float* dst_sigma;
+  float* dst_rewards;
+  float* dst_values;
+  float* dst_logp;
+  float* dst_bins;
+  uint8_t* dst_dones;
+  int64_t ld_obs, ld_priv, ld_hist;
+  int32_t N, obs_dim, priv_dim, hist_dim, act_dim;
+  int32_t reserved;
+} RlStorageAdd;
+int rl_storage_add(const RlStorageAdd* q_host, void* stream);
+
 /* history_wrapper.py:23 - append obs to a 2H-slot ring so that the last H steps are
  * always one contiguous row span: hist [N, 2*H*num_obs], writes slots k and k+H. */
 int rl_history_push(float* hist, const float* obs, int32_t N, int32_t num_obs, int32_t H,

@@ -75,6 +75,7 @@ RlResetBuffers = STRUCTS["RlResetBuffers"]
 RlGacCfg = STRUCTS["RlGacCfg"]
 RlGacBuffers = STRUCTS["RlGacBuffers"]
 RlWgradProblem = STRUCTS["RlWgradProblem"]
+RlStorageAdd = STRUCTS["RlStorageAdd"]
 RlChainTensor = STRUCTS["RlChainTensor"]
 RlChainLoadOp = STRUCTS["RlChainLoadOp"]
 RlChainMmaOp = STRUCTS["RlChainMmaOp"]
@@ -101,6 +102,7 @@ SIGNATURES = {
     "rl_gae_scan": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P]),
     "rl_gae_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "rl_gae": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
+    "rl_storage_add": (C.c_int, [_P, _P]),
     "rl_history_push": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int32] * 10 + [_P]),
     "rl_ppo_gather": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),

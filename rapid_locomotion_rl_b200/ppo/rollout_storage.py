@@ -63,6 +63,9 @@ class RolloutStorage:
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
+        if self._fused_add(transition, s):
+            self.step += 1
+            return
         self.observations[s].copy_(transition.observations)
         self.privileged_observations[s].copy_(transition.privileged_observations)
         self.observation_histories[s].copy_(transition.observation_histories)
@@ -75,6 +78,40 @@ class RolloutStorage:
         self.sigma[s].copy_(transition.action_sigma)
         self.env_bins[s].copy_(transition.env_bins.view(-1, 1))
         self.step += 1
+
+    def _fused_add(self, t, s):
+        """One launch for the eleven per-step copies (csrc/history.cu rl_storage_add).  Falls back to the
+        copy_ sequence (still on the device) only for layouts the kernel does not take: non-fp32 sources,
+        rows that are not unit-stride."""
+        N = self.num_envs
+        f32 = (t.observations, t.privileged_observations, t.observation_histories, t.actions, t.action_mean, t.action_sigma,
+               t.rewards, t.values, t.actions_log_prob, t.env_bins)
+        if any(x.dtype != torch.float32 or x.device != self.device or x.shape[0] != N for x in f32):
+            return False
+        rows = (t.observations, t.privileged_observations, t.observation_histories)
+        if any(x.dim() != 2 or x.stride(1) != 1 for x in rows):
+            return False
+        small = [x if x.is_contiguous() else x.contiguous() for x in f32[3:]]
+        dones = t.dones
+        if dones.dtype == torch.bool:
+            dones = dones.view(torch.uint8)
+        if dones.dtype != torch.uint8 or not dones.is_contiguous() or dones.numel() != N:
+            return False
+        q = _lib.RlStorageAdd()
+        P = lambda x: x.data_ptr()
+        q.obs, q.priv, q.hist = P(rows[0]), P(rows[1]), P(rows[2])
+        q.actions, q.mu, q.sigma, q.rewards, q.values, q.logp, q.bins = (P(x) for x in small)
+        q.dones = P(dones)
+        q.dst_obs, q.dst_priv, q.dst_hist = P(self.observations[s]), P(self.privileged_observations[s]), P(self.observation_histories[s])
+        q.dst_actions, q.dst_mu, q.dst_sigma = P(self.actions[s]), P(self.mu[s]), P(self.sigma[s])
+        q.dst_rewards, q.dst_values, q.dst_logp = P(self.rewards[s]), P(self.values[s]), P(self.actions_log_prob[s])
+        q.dst_bins, q.dst_dones = P(self.env_bins[s]), P(self.dones[s])
+        q.ld_obs, q.ld_priv, q.ld_hist = rows[0].stride(0), rows[1].stride(0), rows[2].stride(0)
+        q.N, q.obs_dim, q.priv_dim, q.hist_dim, q.act_dim = N, rows[0].shape[1], rows[1].shape[1], rows[2].shape[1], small[0].shape[-1]
+        import ctypes as C
+        self._keep = (small, dones)
+        _lib.check(self._lib.rl_storage_add(C.byref(q), _lib.current_stream()))
+        return True
 
     def clear(self):
         self.step = 0

@@ -66,3 +66,38 @@ def test_graph_rollout_writes_what_eager_writes():
         outs[graph] = snap
     for k in outs[False]:
         torch.testing.assert_close(outs[True][k], outs[False][k], rtol=1e-5, atol=1e-6, msg=k)
+
+
+def test_add_transitions_fused_copy():
+    """RolloutStorage.add_transitions (rollout_storage.py:54-71) as one launch: every field of the [t] slice
+    equals the source, including the strided history-ring view and the bool dones."""
+    from rapid_locomotion_rl_b200.ppo import RolloutStorage
+    N, T = 333, 4
+    st = RolloutStorage(N, T, [42], [18], [630], [12], DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    ring = torch.randn(N, 2 * 630, device=DEV, generator=g)
+    for s in range(T):
+        t = RolloutStorage.Transition()
+        t.observations = torch.randn(N + 5, 42, device=DEV, generator=g)[:N]
+        t.critic_observations = t.observations
+        t.privileged_observations = torch.randn(N, 18, device=DEV, generator=g)
+        t.observation_histories = ring[:, 42 * (s + 1):42 * (s + 1) + 630]        # row-strided view, like HistoryWrapper's
+        t.actions = torch.randn(N, 12, device=DEV, generator=g)
+        t.rewards = torch.randn(N, device=DEV, generator=g)
+        t.dones = torch.rand(N, device=DEV, generator=g) < 0.3
+        t.values = torch.randn(N, 1, device=DEV, generator=g)
+        t.actions_log_prob = torch.randn(N, device=DEV, generator=g)
+        t.action_mean = torch.randn(N, 12, device=DEV, generator=g)
+        t.action_sigma = torch.rand(N, 12, device=DEV, generator=g)
+        t.env_bins = torch.randint(0, 5202, (N,), device=DEV, generator=g).float()
+        st.add_transitions(t)
+        torch.cuda.synchronize()
+        assert torch.equal(st.observations[s], t.observations) and torch.equal(st.privileged_observations[s], t.privileged_observations)
+        assert torch.equal(st.observation_histories[s], t.observation_histories)
+        assert torch.equal(st.actions[s], t.actions) and torch.equal(st.mu[s], t.action_mean) and torch.equal(st.sigma[s], t.action_sigma)
+        assert torch.equal(st.rewards[s, :, 0], t.rewards) and torch.equal(st.values[s], t.values)
+        assert torch.equal(st.actions_log_prob[s, :, 0], t.actions_log_prob) and torch.equal(st.env_bins[s, :, 0], t.env_bins)
+        assert torch.equal(st.dones[s, :, 0], t.dones.to(torch.uint8))
+    assert st.step == T
+    with pytest.raises(AssertionError):
+        st.add_transitions(t)
