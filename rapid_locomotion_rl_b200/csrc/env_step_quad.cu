@@ -662,14 +662,16 @@ int launch_step_quad(const StepArgs& args, bool fuse_torques, cudaStream_t st) {
                 c.n_terms == 12 && c.term_mask == STD_TERM_MASK;
   for (int i = 0; is_std && i < 12; ++i) is_std = c.term_id[i] == i;
   if (is_std) {
-    // small grids (<= 4 CTAs per SM) are pure latency: 80 registers / no spills wins; otherwise 8 CTAs / SM
-    // (64 registers) - measured: 4000 envs 6.9 vs 7.9 us, 32768 envs 16.7 vs 13.9 us, 262144 envs 81.2 vs 80.3 us
+    // small grids (<= 4 CTAs per SM) are pure latency: 6 CTAs / SM (80 registers, no spills) wins; otherwise
+    // 7 CTAs / SM (72 registers; 7 x 148 = 1036 CTAs still hold 32768 envs in one wave).  Measured per launch,
+    // 6 / 7 / 8 CTAs per SM: 4000 envs 6.9 / 7.4 / 7.9 us, 32768 envs 16.7 / 13.3 / 14.0 us, 262144 envs 81 / 73 / 80 us
     static int force = -1;
     if (force < 0) { const char* m = getenv("RL_QUAD_MINB"); force = m ? atoi(m) : 0; }
     const int n_cta = (c.num_envs + QT - 1) / QT;
     const bool use6 = force == 6 || (force != 8 && n_cta <= 4 * 148);
     if (use6) return fuse_torques ? launch_quad_inst<true, 6, true>(args, smem, st) : launch_quad_inst<false, 6, true>(args, smem, st);
-    return fuse_torques ? launch_quad_inst<true, 8, true>(args, smem, st) : launch_quad_inst<false, 8, true>(args, smem, st);
+    if (force == 8) return fuse_torques ? launch_quad_inst<true, 8, true>(args, smem, st) : launch_quad_inst<false, 8, true>(args, smem, st);
+    return fuse_torques ? launch_quad_inst<true, 7, true>(args, smem, st) : launch_quad_inst<false, 7, true>(args, smem, st);
   }
   if (minb == 6) return fuse_torques ? launch_quad_inst<true, 6>(args, smem, st) : launch_quad_inst<false, 6>(args, smem, st);
   return fuse_torques ? launch_quad_inst<true, 8>(args, smem, st) : launch_quad_inst<false, 8>(args, smem, st);
