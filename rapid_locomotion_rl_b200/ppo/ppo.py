@@ -271,9 +271,12 @@ class PPO:
         mb = batch // A.num_mini_batches
         indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)
         self._loss_acc.zero_()
-        # Single GPU: the ~70 launches of a minibatch step are captured ONCE in a CUDA graph that reads its
+        # The ~25 launches of a minibatch step are captured ONCE in a CUDA graph that reads its
         # row indices from a fixed buffer; each of the 20 steps is then one index copy + one graph replay.
-        use_graph = self.use_cuda_graph and world == 1 and not getattr(self, "debug_keep_grad", False)
+        # (multi-GPU: the NCCL all-reduces are captured too - every rank captures the same sequence; set
+        # RL_PPO_GRAPH_MULTI=0 to launch eagerly instead)
+        multi_ok = world == 1 or os.environ.get("RL_PPO_GRAPH_MULTI", "1") != "0"
+        use_graph = self.use_cuda_graph and multi_ok and not getattr(self, "debug_keep_grad", False)
         if use_graph and (self._graph is None or self._graph_B != mb):
             self.actor_critic.workspace(mb, backward=True)        # allocate outside the capture
             self.actor_critic.prepare_update_chains()
@@ -283,7 +286,7 @@ class PPO:
             snap = [t.clone() for t in (self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
                                         self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc)]
             with torch.cuda.graph(g):
-                self.minibatch_step(self._idx_buf, 1, None)
+                self.minibatch_step(self._idx_buf, world, allreduce)
             # capture does not execute, but keep the state bit-identical in any case
             for t, s0 in zip((self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
                               self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc), snap):
