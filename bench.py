@@ -297,6 +297,39 @@ def run_ours(args):
             del reps2
             torch.cuda.empty_cache()
 
+    if world == 1 and not args.quick:
+        # the gymapi-shaped sequence - `decimation` x (torque kernel between physics sub-steps) +
+        # one post-physics kernel per step (5 launches instead of the 1 fused launch)
+        k3 = min(args.steps, 300)
+        n_rep = max(2, math.ceil(2.0 * L2_BYTES / (args.envs * bpe)))
+        reps3 = build_replicas("mc_flat", args.envs, n_rep, device, seed0=rank)
+        for env3, a3, _ in reps3:
+            env3.use_device_step_counter(True)
+
+        def seq(i):
+            env3, a3, _ = reps3[i % len(reps3)]
+            for _ in range(env3.cfg.control.decimation):
+                env3._compute_torques(a3)
+            env3.post_physics_step(a3)
+        for i in range(4):
+            seq(i)
+        torch.cuda.synchronize()
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3):
+            for i in range(k3):
+                seq(i)
+        g3.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g3.replay(); e1.record()
+        torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1)
+        also["decimation_sequence"] = {"value": args.envs * k3 / (ms3 * 1e-3), "ms_per_step": ms3 / k3, "steps": k3,
+                                       "launches_per_step": 1 + reps3[0][0].cfg.control.decimation, "envs": args.envs,
+                                       "note": "4 x rl_env_torques + rl_env_post_physics per step (the shape of the real gymapi loop)"}
+        del reps3, g3
+        torch.cuda.empty_cache()
+
     ppo = None
     if not args.quick:
         try:
@@ -416,7 +449,7 @@ def runner_bench(n_envs, device, iters=10):
             "ms_per_iteration_eager_rollout": res["eager"] * 1e3}
 
 
-def cpu_env_arm(envs, steps, warmup, threads=None):
+def cpu_env_arm(envs, steps, warmup, threads=None, device="cpu"):
     """The reference's algorithm for the path on host cores: oracle/env_oracle.py (a torch-CPU
     restatement pinned bit-exactly to the reference; the reference itself is Python and cannot travel
     to the GPU box).  Returns (env-steps/s, threads used, seconds)."""
@@ -429,17 +462,23 @@ def cpu_env_arm(envs, steps, warmup, threads=None):
     if threads:
         torch.set_num_threads(threads)
     cfg, robot, terrain = build_case("mc_flat", envs)
-    o = OracleEnv(cfg, robot, terrain)
-    st = synthetic_state(0, envs, robot.num_bodies, 12, o.default_dof_pos[0].numpy(), o.feet_indices.tolist(),
+    o = OracleEnv(cfg, robot, terrain, device=device)
+    st = synthetic_state(0, envs, robot.num_bodies, 12, o.default_dof_pos[0].cpu().numpy(), o.feet_indices.tolist(),
                          o.termination_contact_indices.tolist())
     statekit.apply_to_oracle(o, st)
-    o.commands[:, :3] = torch.rand(envs, 3) * 2 - 1
-    actions = torch.randn(envs, 12)
+    for d in (o.episode_sums, o.command_sums):
+        for k in d:
+            d[k] = d[k].to(device)
+    o.commands[:, :3] = torch.rand(envs, 3, device=device) * 2 - 1
+    actions = torch.randn(envs, 12, device=device)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
     for _ in range(warmup):
         o.step(actions)
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         o.step(actions)
+    sync()
     dt = time.perf_counter() - t0
     return envs * steps / dt, torch.get_num_threads(), dt
 
@@ -450,9 +489,19 @@ def cpu_baseline(sample_envs, steps, warmup, target_s=12.0):
     _, _, probe = cpu_env_arm(sample_envs, 2, 1)
     steps = int(min(5000, max(steps, target_s / max(probe / 2, 1e-6))))   # ~10-30 s of CPU work
     v, cores, secs = cpu_env_arm(sample_envs, steps, warmup)
-    return {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d envs x %d steps of the same Mini Cheetah flat step through oracle/env_oracle.py (torch CPU fp32, "
-                      "%.1f s)" % (sample_envs, steps, secs)}
+    out = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+           "sample": "%d envs x %d steps of the same Mini Cheetah flat step through oracle/env_oracle.py (torch CPU fp32, "
+                     "%.1f s)" % (sample_envs, steps, secs)}
+    if torch.cuda.is_available():
+        # the reference's torch-eager path ON the B200 (the port issues the reference's ~300 small
+        # ATen kernels per step), as the GPU number the fused kernel replaces
+        try:
+            vg, _, sg = cpu_env_arm(32768, 30, 5, device="cuda:0")
+            out["torch_eager_gpu_port"] = {"value": vg, "unit": "env-steps/s", "sample": "32768 envs x 30 steps, oracle port on "
+                                           "cuda:0 (torch eager fp32, %.2f s)" % sg}
+        except Exception as exc:      # the baseline must never take the bench down
+            out["torch_eager_gpu_port"] = {"error": str(exc)[:200]}
+    return out
 
 
 def run_reference(args):

@@ -335,8 +335,9 @@ class LeggedRobot:
         b.actions_in = self._actions_in.data_ptr()
         inj = self._inject
         b.noise_u = _lib.ptr(inj.get("noise_u")); b.dr_u = _lib.ptr(inj.get("dr_u")); b.push_u = _lib.ptr(inj.get("push_u"))
+        host_step = 0 if b.step_state else self.common_step_counter
         _lib.check(self._lib.rl_env_post_physics(C.byref(self._cfg_struct), C.byref(b), self.seed,
-                                                 self.common_step_counter, _lib.current_stream()))
+                                                 host_step, _lib.current_stream()))
 
     def get_observations(self):
         return self.obs_buf
