@@ -32,6 +32,13 @@ constexpr int CHAIN_THREADS = 320;          // warp 0 LOAD, warp 1 MMA, warps 2-
 constexpr int UNIT_BYTES = 16384;
 constexpr int FIXED_SMEM = 3072;            // static: 64 mbarriers | tmem slot | per-warp bias staging (8 x 256 B)
 constexpr int TRACE_MMA = 8, TRACE_EPI = 5; // stamps per op (loads: 1)
+#ifndef RL_CHAIN_WAIT_NS_LOAD
+#define RL_CHAIN_WAIT_NS_LOAD 0
+#endif
+#ifndef RL_CHAIN_WAIT_NS_EPI
+#define RL_CHAIN_WAIT_NS_EPI 0
+#endif
+constexpr int WAIT_NS_LOAD = RL_CHAIN_WAIT_NS_LOAD, WAIT_NS_EPI = RL_CHAIN_WAIT_NS_EPI;
 
 // device-side op formats (built by rl_chain_create from the ABI structs)
 struct DevMmaOp {            // 32 B
@@ -82,12 +89,17 @@ __device__ __noinline__ void chain_timeout(uint32_t id, uint32_t parity, int it)
          (int)blockIdx.x, (int)threadIdx.x);
   __trap();
 }
+// SLEEP_NS > 0: back off between polls (tried: 64 ns in the LOAD warp, 32 ns in the epilogue workers - no gain,
+// the dgrad chain got slower; kept as a compile-time knob, default off) so that a waiting warp does not take issue slots from the warps that
+// share its scheduler (the LOAD warp and the epilogue workers are not latency critical; the MMA warp is)
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void chain_wait(uint64_t* bars, uint32_t spec, int it) {
   const uint32_t id = spec & 0xFFu;
   if (id == RL_CHAIN_NONE) return;
   const uint32_t parity = ((spec >> 8) ^ ((spec >> 9) & (uint32_t)it)) & 1u;
   uint32_t spins = 0;
   while (!mbar_try(&bars[id], parity)) {
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if (++spins > (1u << 24)) chain_timeout(id, parity, it);
   }
 }
@@ -188,7 +200,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
       RlChainLoadOp cur = p.loads[0];
       for (int i = 0; i < p.n_loads; ++i) {
         const RlChainLoadOp nxt = p.loads[i + 1 < p.n_loads ? i + 1 : i];
-        chain_wait(bars, cur.wait, it);
+        chain_wait<WAIT_NS_LOAD>(bars, cur.wait, it);
         if (elect_one()) {
           mbar_expect_tx(&bars[cur.full_bar], cur.expect_bytes);
           tma_load_2d(smem + cur.smem_off, &p.tmaps[cur.tensor], cur.col0, cur.row0 + (cur.tile_rows ? m0 : 0), &bars[cur.full_bar]);
@@ -273,7 +285,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (lane + 32 < ncols) b_hi = __ldg(bias + 32 + lane);
         }
         // ---- accumulator columns -> registers ----
-        chain_wait(bars, wait_acc, it);
+        chain_wait<WAIT_NS_EPI>(bars, wait_acc, it);
         tc_fence_after();
         if (tr) tp[1] = clock64();
         float f[64];
@@ -316,7 +328,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
             for (int j = 0; j < 64; ++j) f[j] = elu1(f[j]);
           }
         } else if (mode == RL_CHAIN_EPI_DELU) {
-          chain_wait(bars, wait_aux, it);
+          chain_wait<WAIT_NS_EPI>(bars, wait_aux, it);
           const uint8_t* aux = smem + aux_off;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -348,7 +360,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (et == 0) bulk_wait_read_dyn(store_wait_pending);
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
-        chain_wait(bars, wait_dst, it);
+        chain_wait<WAIT_NS_EPI>(bars, wait_dst, it);
         uint8_t* box = smem + dst_off;
         if (dst_col0 == 0 && ncols == 64) {
 #pragma unroll
