@@ -55,24 +55,3 @@ def env_shard(num_envs_global, rank_=None, world=None):
     base, rem = divmod(int(num_envs_global), world)
     start = rank_ * base + min(rank_, rem)
     return start, base + (1 if rank_ < rem else 0)
-
-
-def normalise_from_moments(x, moments):
-    """(x - mean) / (std_unbiased + 1e-8) from float64 (sum, sumsq, count) - the host restatement of what
-    rl_gae_normalize does with the all-reduced statistics (rollout_storage.py:90)."""
-    s, ss, n = (float(v) for v in moments)
-    mean = s / n
-    var = max(0.0, (ss - n * mean * mean) / (n - 1.0))
-    return ((x.double() - mean) / (var ** 0.5 + 1e-8)).to(x.dtype)
-
-
-def saturating_bump_(weights, hit_count, own_flag, step=0.2):
-    """w <- min(1, w + step) applied k = hit_count + (own_flag > 0) times (order independent, so the
-    all-reduced integer counters give the same float64 weights on every rank).  Host restatement of the
-    update in csrc/gac.cu used by the CPU tests; the product path runs rl_gac_update_sample."""
-    k = hit_count.to(torch.int64) + (own_flag > 0).to(torch.int64)
-    for _ in range(int(k.max().item()) if k.numel() else 0):
-        m = k > 0
-        weights[m] = torch.clamp(weights[m] + step, 0.0, 1.0)
-        k = k - m.to(torch.int64)
-    return weights

@@ -25,6 +25,27 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# ---- host restatements of what the kernels do with the all-reduced buffers (checkers, test-only) ----
+def normalise_from_moments(x, moments):
+    """(x - mean) / (std_unbiased + 1e-8) from float64 (sum, sumsq, count) - the host restatement of what
+    rl_gae_normalize does with the all-reduced statistics (rollout_storage.py:90)."""
+    s, ss, n = (float(v) for v in moments)
+    mean = s / n
+    var = max(0.0, (ss - n * mean * mean) / (n - 1.0))
+    return ((x.double() - mean) / (var ** 0.5 + 1e-8)).to(x.dtype)
+
+
+def saturating_bump_(weights, hit_count, own_flag, step=0.2):
+    """w <- min(1, w + step) applied k = hit_count + (own_flag > 0) times (order independent, so the
+    all-reduced integer counters give the same float64 weights on every rank): what rl_gac_update_sample does."""
+    k = hit_count.to(torch.int64) + (own_flag > 0).to(torch.int64)
+    for _ in range(int(k.max().item()) if k.numel() else 0):
+        m = k > 0
+        weights[m] = torch.clamp(weights[m] + step, 0.0, 1.0)
+        k = k - m.to(torch.int64)
+    return weights
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -106,7 +127,7 @@ def _worker(rank, world, port, out):
         raw = ret - val[:, sl]
         mom = torch.tensor([raw.double().sum(), (raw.double() ** 2).sum(), float(raw.numel())], dtype=torch.float64)
         sharding.all_reduce_sum_(mom)
-        res["adv"] = sharding.normalise_from_moments(raw, mom)
+        res["adv"] = normalise_from_moments(raw, mom)
         res["ret"] = ret
 
         # ---- GAC: all-reduced incidence counters -> identical saturating update ---------------------------
@@ -126,7 +147,7 @@ def _worker(rank, world, port, out):
                 near = np.logical_and(cur.grid >= cur.grid[:, [b]] - 0.5, cur.grid <= cur.grid[:, [b]] + 0.5).all(axis=0)
                 hit += torch.from_numpy(near.astype(np.int32))
         sharding.all_reduce_sum_(hit, own)
-        w = sharding.saturating_bump_(torch.from_numpy(cur.weights.copy()), hit, own)
+        w = saturating_bump_(torch.from_numpy(cur.weights.copy()), hit, own)
         res["gac_w"] = w
         out[rank] = res
     finally:
