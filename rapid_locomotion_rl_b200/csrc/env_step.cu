@@ -627,42 +627,46 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
 // standalone PD torques (:653-688) for the real-simulator path: called `decimation` times
 __global__ void __launch_bounds__(128)
 env_torques_kernel(const __grid_constant__ StepArgs args) {
+  // one thread per (env, leg): 4x the threads of a thread-per-env mapping and a quarter of the dependent work
+  // each - this launch runs `decimation` times per step between physics sub-steps, its latency is what counts
   const RlEnvCfg& cfg = args.cfg;
   const RlEnvBuffers& b = args.b;
   const int N = cfg.num_envs;
   const size_t Ns = (size_t)N;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int leg = blockIdx.y;
   if (e >= N) return;
-  // rows are 48 B / 96 B and 16 B aligned: 128-bit row loads (L1 merges neighbouring rows)
-  float act[ND], dof[2 * ND], out[ND];
+  const float* ap = b.actions_in + (size_t)e * ND + 3 * leg;
+  const float2* dp = reinterpret_cast<const float2*>(b.dof_state + (size_t)e * 24 + 6 * leg);     // 8 B aligned
+  float act[3], q[3], qd[3], kp[3], kd[3], ms[3], ldv[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-    *reinterpret_cast<float4*>(act + 4 * k) = *reinterpret_cast<const float4*>(b.actions_in + (size_t)e * ND + 4 * k);
+  for (int k = 0; k < 3; ++k) {
+    const int j = 3 * leg + k;
+    act[k] = ap[k];
+    const float2 d = dp[k];
+    q[k] = d.x; qd[k] = d.y;
+    kp[k] = b.Kp_factors[j * Ns + e]; kd[k] = b.Kd_factors[j * Ns + e]; ms[k] = b.motor_strengths[j * Ns + e];
+    ldv[k] = cfg.control_type == 1 ? b.last_dof_vel[j * Ns + e] : 0.f;
+  }
 #pragma unroll
-  for (int k = 0; k < 6; ++k)
-    *reinterpret_cast<float4*>(dof + 4 * k) = *reinterpret_cast<const float4*>(b.dof_state + (size_t)e * 24 + 4 * k);
-#pragma unroll
-  for (int j = 0; j < ND; ++j) {
-    const float q = dof[2 * j], qd = dof[2 * j + 1];
-    const float a = clampf(act[j], -cfg.clip_actions, cfg.clip_actions);
+  for (int k = 0; k < 3; ++k) {
+    const int j = 3 * leg + k;
+    const float a = clampf(act[k], -cfg.clip_actions, cfg.clip_actions);
     float as = a * cfg.action_scale;
-    if (j % 3 == 0) as *= cfg.hip_scale_reduction;
+    if (k == 0) as *= cfg.hip_scale_reduction;
     float t;
     if (cfg.control_type == 0) {
       const float jpt = as + cfg.default_dof_pos[j];
       b.joint_pos_target[j * Ns + e] = jpt;
-      t = cfg.p_gains[j] * b.Kp_factors[j * Ns + e] * (jpt - q) - cfg.d_gains[j] * b.Kd_factors[j * Ns + e] * qd;
+      t = cfg.p_gains[j] * kp[k] * (jpt - q[k]) - cfg.d_gains[j] * kd[k] * qd[k];
     } else if (cfg.control_type == 1) {
-      t = cfg.p_gains[j] * (as - qd) - cfg.d_gains[j] * (qd - b.last_dof_vel[j * Ns + e]) / cfg.sim_dt;
+      t = cfg.p_gains[j] * (as - qd[k]) - cfg.d_gains[j] * (qd[k] - ldv[k]) / cfg.sim_dt;
     } else {
       t = as;
     }
-    t = t * b.motor_strengths[j * Ns + e];
-    out[j] = clampf(t, -cfg.torque_limits[j], cfg.torque_limits[j]);
+    t = t * ms[k];
+    b.torques[(size_t)e * ND + j] = clampf(t, -cfg.torque_limits[j], cfg.torque_limits[j]);
   }
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    *reinterpret_cast<float4*>(b.torques + (size_t)e * ND + 4 * k) = *reinterpret_cast<float4*>(out + 4 * k);
 }
 
 static size_t step_smem_bytes(const RlEnvCfg& cfg, int tile) {
@@ -786,6 +790,6 @@ extern "C" int rl_env_torques(const RlEnvCfg* cfg, const RlEnvBuffers* b, void* 
   StepArgs args;
   args.cfg = *cfg; args.b = *b; args.seed = 0; args.step = 0;
   const int grid = (cfg->num_envs + 127) / 128;
-  env_torques_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(args);
+  env_torques_kernel<<<dim3(grid, 4), 128, 0, (cudaStream_t)stream>>>(args);
   return check_launch("env_torques_kernel");
 }
