@@ -34,7 +34,21 @@ ppo_gather_kernel(const float* __restrict__ obs, const float* __restrict__ priv,
     if (c < obs_dim) Xac[(size_t)warp * ldac + c] = __float2bfloat16(obs[src * obs_dim + c]);
     else if (c >= obs_dim + LAT) Xac[(size_t)warp * ldac + c] = zero;   // [obs_dim, obs_dim+18) is the latent slot
   }
-  if (Xh) for (int c = lane; c < ldh; c += 32) Xh[(size_t)warp * ldh + c] = c < hist_dim ? __float2bfloat16(hist[src * hist_dim + c]) : zero;
+  if (Xh) {
+    // the 630-float history row is 86 % of the gathered bytes: 8 B loads / 4 B bf16x2 stores when the row is
+    // 8 B aligned (even hist_dim, even pitch), i.e. 256 B read and 128 B written per warp instruction
+    const float* hs = hist + src * hist_dim;
+    __nv_bfloat16* hd = Xh + (size_t)warp * ldh;
+    if (((hist_dim | ldh) & 1) == 0 && ((reinterpret_cast<uintptr_t>(hs) | reinterpret_cast<uintptr_t>(hd)) & 7) == 0) {
+      for (int c = 2 * lane; c < ldh; c += 64) {
+        float2 v = make_float2(0.f, 0.f);
+        if (c < hist_dim) v = *reinterpret_cast<const float2*>(hs + c);
+        *reinterpret_cast<__nv_bfloat162*>(hd + c) = __floats2bfloat162_rn(v.x, v.y);
+      }
+    } else {
+      for (int c = lane; c < ldh; c += 32) hd[c] = c < hist_dim ? __float2bfloat16(hs[c]) : zero;
+    }
+  }
   float* L = Lrow + (size_t)warp * LROW;
   if (lane < ACT) {
     L[lane] = actions[src * ACT + lane];
