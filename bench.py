@@ -281,6 +281,49 @@ def run_ours(args):
     e2e_value = args.envs * world * k_e2e / e2e_s
     e2e_serial = args.envs * world * k_e2e / e2e_serial_s
     assert float(groups[0].h_out[0].abs().sum()) > 0 and float(groups[1].h_out[0].abs().sum()) > 0
+    # ---- zero-copy variant: the kernel reads the pinned host rows and writes the pinned host outputs itself
+    # (LeggedRobot.bind_host_io / step_host: one launch per step, no staging copies); one group with a sync per
+    # step, and two groups on two streams so that one group's PCIe reads overlap the other's writes ----
+    e2e_zero_copy = e2e_zero_copy2 = None
+    try:
+        for gs in groups:
+            e_ = gs.env
+            gs.h_reset_u8 = torch.empty(e_.num_envs, dtype=torch.uint8, pin_memory=True)
+            e_.bind_host_io(gs.h_in[0], gs.h_in[1], gs.h_in[2], gs.h_out[0], gs.h_out[1], gs.h_out[2], gs.h_reset_u8)
+
+        def zc_submit(gs):
+            with torch.cuda.stream(gs.stream):
+                gs.env.step_host(gs.h_in[3])
+                gs.done.record(gs.stream)
+            gs.pending = True
+
+        def zc_run(gl, k):
+            for i in range(k):
+                gs = gl[i % len(gl)]
+                gs.wait()                    # this group's previous outputs are in host memory
+                zc_submit(gs)
+            for gs in gl:
+                gs.wait()
+
+        def zc_time(gl):
+            zc_run(gl, 4)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            zc_run(gl, k_e2e)
+            torch.cuda.synchronize()
+            dtz = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dtz], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtz = float(t.item())
+            return args.envs * world * k_e2e / dtz
+        e2e_zero_copy = zc_time(groups[:1])
+        e2e_zero_copy2 = zc_time(groups)
+        assert float(groups[0].h_out[0].abs().sum()) > 0 and float(groups[1].h_out[0].abs().sum()) > 0
+    except Exception as exc:
+        e2e_zero_copy = "failed: %s" % str(exc)[:160]
     env = None
     del groups
 
@@ -355,7 +398,7 @@ def run_ours(args):
                    "launch": "K steps captured in one CUDA graph, device-side RNG step counter"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
-                "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e, "serial_value": e2e_serial,
+                "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e, "serial_value": e2e_serial, "zero_copy_value": e2e_zero_copy, "zero_copy_two_groups_value": e2e_zero_copy2,
                 "note": "every step: pinned host buffers -> H2D -> LeggedRobot.step -> D2H of obs/priv/rew/reset -> host "
                         "wait; two env groups double-buffered on two streams (serial_value: one group, sync per step)"},
         "gpu_launches": args.steps,

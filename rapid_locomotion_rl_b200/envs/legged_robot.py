@@ -299,6 +299,44 @@ class LeggedRobot:
     # ------------------------------------------------------------------------------------------
     # hot path
     # ------------------------------------------------------------------------------------------
+    def bind_host_io(self, root_states, dof_state, contact_forces, obs, priv, rew, reset_u8):
+        """Zero-copy host boundary (the reference's CPU-pipeline case, `sim.use_gpu_pipeline = False`: the
+        simulator's state tensors live in host memory).  The arguments are PINNED host tensors of the simulator
+        shapes; under unified addressing the kernels read / write them in place over PCIe (TMA bulk loads of
+        the AoS rows, bulk stores of the observation rows), so a step is ONE launch with no staging copies:
+        reads and writes of different CTAs overlap on the two PCIe directions by themselves.  All persistent
+        env state stays in device memory.  Use `step_host` afterwards."""
+        want = {"root_states": (root_states, self.root_states), "dof_state": (dof_state, self.dof_state),
+                "contact_forces": (contact_forces, self.all_contact_forces), "obs": (obs, self.obs_buf),
+                "priv": (priv, self.privileged_obs_buf), "rew": (rew, self.rew_buf), "reset": (reset_u8, self._reset_u8)}
+        for name, (h, d) in want.items():
+            if not (h.is_pinned() and h.is_contiguous() and h.dtype == d.dtype and h.numel() == d.numel()):
+                raise ValueError("bind_host_io: %s must be a pinned, contiguous host tensor of dtype %s with %d elements"
+                                 % (name, d.dtype, d.numel()))
+        self._host_io = dict(root_states=root_states, dof_state=dof_state, contact_forces=contact_forces, obs=obs, priv=priv,
+                             rew=rew, reset=reset_u8)
+        b, P = self._bufs, _lib.ptr
+        b.root_states, b.dof_state, b.contact_forces = P(root_states), P(dof_state), P(contact_forces)
+        b.obs_buf, b.privileged_obs_buf, b.rew_buf, b.reset_buf = P(obs), P(priv), P(rew), P(reset_u8)
+
+    def step_host(self, actions_host):
+        """`step` for an env bound with `bind_host_io`: `actions_host` is a pinned host tensor [N, num_actions].
+        Returns the bound host tensors (obs, priv, rew, reset_u8); they are valid once the stream has been
+        synchronised."""
+        io = self._host_io
+        if not (actions_host.is_pinned() and actions_host.is_contiguous() and actions_host.dtype == torch.float32 and
+                tuple(actions_host.shape) == (self.num_envs, self.num_actions)):
+            raise ValueError("step_host: actions must be a pinned contiguous float32 host tensor [%d, %d]"
+                             % (self.num_envs, self.num_actions))
+        self.common_step_counter += 1
+        b = self._bufs
+        b.actions_in = actions_host.data_ptr()
+        b.noise_u = b.dr_u = b.push_u = None
+        host_step = 0 if b.step_state else self.common_step_counter
+        _lib.check(self._lib.rl_env_step_fused(C.byref(self._cfg_struct), C.byref(b), self.seed, host_step,
+                                               _lib.current_stream()))
+        return io["obs"], io["priv"], io["rew"], io["reset"]
+
     def step(self, actions):
         """legged_robot.py:106-137.  One fused launch: torques + post-physics pipeline."""
         actions = actions.to(self.device, torch.float)

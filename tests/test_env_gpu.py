@@ -310,3 +310,44 @@ def test_api_errors():
         env.step(torch.zeros(15, 12, device=DEV))
     with pytest.raises(_lib.RlError):
         LeggedRobot(cfg, sim_device="cpu", terrain=terrain)
+
+
+def test_host_io_zero_copy_matches_device_step():
+    """bind_host_io / step_host (simulator tensors and outputs in pinned host memory, read and written by
+    the kernel in place) gives exactly what the device-resident step gives."""
+    import numpy as np
+    from cases import build_case
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    n = 4133
+    outs = []
+    for host in (False, True):
+        cfg, robot, terrain = build_case("mc_flat", n)
+        env = LeggedRobot(cfg, sim_device="cuda:0", headless=True, terrain=terrain, seed=11)
+        p = env.params
+        st = synthetic_state(5, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx, p.term_idx[:p.n_term_bodies])
+        actions = torch.from_numpy(np.random.default_rng(1).normal(0, 1, (n, 12)).astype(np.float32))
+        env.commands[:, :3] = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, (n, 3)).astype(np.float32)).cuda()
+        if not host:
+            env.sim.root_states.copy_(torch.from_numpy(st["root_states"]))
+            env.sim.dof_state.copy_(torch.from_numpy(st["dof_state"]).view(-1, 2))
+            env.sim.contact_forces.copy_(torch.from_numpy(st["contact_forces"]).view(-1, 3))
+            for _ in range(3):
+                obs, priv, rew, reset, _x = env.step(actions.cuda())
+            torch.cuda.synchronize()
+            outs.append([t.cpu().clone() for t in (obs, priv, rew, reset.to(torch.uint8), env.torques, env.episode_sums["total"])])
+        else:
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            h_root, h_dof, h_con = pin(st["root_states"]), pin(st["dof_state"].reshape(-1, 2)), pin(st["contact_forces"].reshape(-1, 3))
+            h_obs = torch.zeros(n, env.num_obs).pin_memory(); h_priv = torch.zeros(n, 18).pin_memory()
+            h_rew = torch.zeros(n).pin_memory(); h_reset = torch.zeros(n, dtype=torch.uint8).pin_memory()
+            env.bind_host_io(h_root, h_dof, h_con, h_obs, h_priv, h_rew, h_reset)
+            h_act = actions.pin_memory()
+            for _ in range(3):
+                env.step_host(h_act)
+            torch.cuda.synchronize()
+            outs.append([t.clone() for t in (h_obs, h_priv, h_rew, h_reset)] + [env.torques.cpu(), env.episode_sums["total"].cpu()])
+            with pytest.raises(ValueError):
+                env.step_host(actions)          # not pinned
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
