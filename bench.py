@@ -400,7 +400,10 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
                 "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e, "serial_value": e2e_serial, "zero_copy_value": e2e_zero_copy, "zero_copy_two_groups_value": e2e_zero_copy2,
                 "note": "every step: pinned host buffers -> H2D -> LeggedRobot.step -> D2H of obs/priv/rew/reset -> host "
-                        "wait; two env groups double-buffered on two streams (serial_value: one group, sync per step)"},
+                        "wait; two env groups double-buffered on two streams, H2D of one staggered against the D2H of the other "
+                        "(serial_value: one group, sync per step; zero_copy_value: LeggedRobot.bind_host_io / step_host - the kernel "
+                        "reads the pinned rows and writes the pinned outputs in place, one launch per step, one group; "
+                        "zero_copy_two_groups_value: the same on two streams)"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
