@@ -115,7 +115,9 @@ class ActorCritic(nn.Module):
         n = sum(p.numel() for p in order)
         dev = self.device_
         self.flat = torch.zeros(n, device=dev)
-        self.flat_grad = torch.zeros(n, device=dev)
+        # + 8 tail floats: the loss statistics ride in the same all-reduce as the gradients (multi-GPU)
+        self._grad_store = torch.zeros(n + 8, device=dev)
+        self.flat_grad = self._grad_store[:n]
         self.flat_m = torch.zeros(n, device=dev)
         self.flat_v = torch.zeros(n, device=dev)
         self.n_main, self.n_total = n_main, n

@@ -215,9 +215,13 @@ class PPO:
         self._wgrad_flush()
         # ---- data-parallel reduction of the policy gradients and loss statistics ----
         g_main, g_adapt = ac.flat_grad[:ac.n_main], ac.flat_grad[ac.n_main:]
+        tail = ac._grad_store[ac.n_total:ac.n_total + 4]
         if allreduce is not None:
-            allreduce(g_main)
-            allreduce(self._stats)
+            # ONE all-reduce: [policy gradient | adaptation gradient (all zero here) | 4 loss statistics].  The
+            # per-rank statistics were summed in float64; their fp32 images are summed over the ranks.
+            tail.copy_(self._stats)
+            allreduce(ac._grad_store[:ac.n_total + 4])
+            self._stats.copy_(tail)
         if getattr(self, "debug_keep_grad", False):      # parity tests read the raw gradient / statistics
             self.debug_grad = ac.flat_grad.clone()
         # ---- clip + KL-adaptive lr + Adam, all on the device ----
@@ -246,8 +250,9 @@ class PPO:
             self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
             self._wgrad_flush()
             if allreduce is not None:
-                allreduce(g_adapt)
-                allreduce(stats_ad)
+                tail.copy_(stats_ad)
+                allreduce(ac._grad_store[ac.n_main:ac.n_total + 4])
+                stats_ad.copy_(tail)
             if getattr(self, "debug_keep_grad", False):
                 self.debug_grad[ac.n_main:] = g_adapt
             n_ad = ac.n_total - ac.n_main
