@@ -548,6 +548,30 @@ int rl_adapt_loss(const float* pred, const void* Xac, int32_t ldac, int32_t lat_
  * workspace: 16 zeroed bytes. */
 int rl_grad_finalize(const float* grad, int64_t n, const double* stats, float* ctrl, void* workspace,
                      double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, void* stream);
+/* same, from an already reduced squared gradient norm (device double) */
+int rl_grad_finalize_from_norm(const double* norm2, const double* stats, float* ctrl, double global_B,
+                               float desired_kl, float max_grad_norm, int32_t adaptive, void* stream);
+
+/* ---- multi-GPU: gradient all-reduce over NVLink peer memory, fused with the gradient-norm reduction and
+ * zero_grad (the sum of the env shards' gradients that precedes clip_grad_norm_ / optimizer.step,
+ * ppo.py:146-150).  Every rank owns a gradient buffer, a staging buffer of the same size and a 256 B flag block,
+ * all mapped by every other rank (CUDA IPC); `local_ws` is 16 zeroed bytes of ordinary device memory
+ * (a double accumulator and the call counter).  One launch:
+ * wait until every rank's gradient is complete -> rank r sums slice r of all gradients (rank order, bit-identical
+ * everywhere) into its staging buffer and accumulates its squared norm -> wait -> gather all slices into `out`,
+ * total norm into `norm2_out`, zero the own gradient segment.  `step` is the call ordinal (> 0, equal on all
+ * ranks, strictly increasing), or 0 to use the device-side counter kept at local_ws + 8 (CUDA-graph replay).  offset and n are multiples of 4 floats; the norm covers the first norm_n floats. */
+#define RL_PEER_MAX_RANKS 16
+typedef struct RlPeerComm {
+  void* grad[RL_PEER_MAX_RANKS];    /* rank p's gradient buffer as mapped in THIS process */
+  void* stage[RL_PEER_MAX_RANKS];   /* rank p's staging buffer */
+  void* flags[RL_PEER_MAX_RANKS];   /* rank p's flag block (zero initialised) */
+  void* local_ws;
+  int32_t world, rank;
+} RlPeerComm;
+int rl_peer_allreduce(const RlPeerComm* comm_host, int64_t offset, int64_t n, int64_t norm_n, float* out,
+                      double* norm2_out, uint32_t step, void* stream);
+
 /* torch.optim.Adam step (ppo.py:44-46,150,168) fused with gradient scaling and zero_grad.
  * use_ctrl: lr = ctrl[0], grad scaled by ctrl[1]; else lr_fixed.  grad_scale: extra factor. */
 int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,

@@ -76,6 +76,7 @@ RlGacCfg = STRUCTS["RlGacCfg"]
 RlGacBuffers = STRUCTS["RlGacBuffers"]
 RlWgradProblem = STRUCTS["RlWgradProblem"]
 RlStorageAdd = STRUCTS["RlStorageAdd"]
+RlPeerComm = STRUCTS["RlPeerComm"]
 RlChainTensor = STRUCTS["RlChainTensor"]
 RlChainLoadOp = STRUCTS["RlChainLoadOp"]
 RlChainMmaOp = STRUCTS["RlChainMmaOp"]
@@ -114,6 +115,8 @@ SIGNATURES = {
     "rl_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
                           C.c_float, _P, _P]),
     "rl_gemm_init": (C.c_int, []),
+    "rl_grad_finalize_from_norm": (C.c_int, [_P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P]),
+    "rl_peer_allreduce": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_uint32, _P]),
     "rl_wgrad_grouped": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_create": (C.c_int, [_P, _P]),
     "rl_chain_run": (C.c_int, [_P, C.c_int32, _P]),

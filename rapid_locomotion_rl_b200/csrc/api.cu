@@ -38,6 +38,7 @@ extern "C" int64_t rl_sizeof(const char* name) {
   if (!strcmp(name, "RlResetBuffers")) return sizeof(RlResetBuffers);
   if (!strcmp(name, "RlGacCfg")) return sizeof(RlGacCfg);
   if (!strcmp(name, "RlGacBuffers")) return sizeof(RlGacBuffers);
+  if (!strcmp(name, "RlPeerComm")) return sizeof(RlPeerComm);
   if (!strcmp(name, "RlStorageAdd")) return sizeof(RlStorageAdd);
   if (!strcmp(name, "RlWgradProblem")) return sizeof(RlWgradProblem);
   if (!strcmp(name, "RlChainTensor")) return sizeof(RlChainTensor);

@@ -265,6 +265,24 @@ grad_finalize_kernel(const float* __restrict__ grad, size_t n, const double* __r
   }
 }
 
+// clip coefficient / KL-adaptive learning rate from an already reduced squared gradient norm (multi-GPU: the
+// peer all-reduce kernel computes it while it sums the gradients)
+__global__ void finalize_from_norm_kernel(const double* __restrict__ norm2, const double* __restrict__ stats, float* ctrl,
+                                          double global_B, float desired_kl, float max_norm, int adaptive) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double norm = sqrt(*norm2);
+  const float coef = (float)((double)max_norm / (norm + 1e-6));
+  ctrl[1] = coef < 1.f ? coef : 1.f;
+  const float kl = (float)(stats[2] / global_B);
+  ctrl[2] = kl;
+  if (adaptive) {
+    float lr = ctrl[0];
+    if (kl > desired_kl * 2.0f) lr = fmaxf(1e-5f, lr / 1.5f);
+    else if (kl < desired_kl / 2.0f && kl > 0.0f) lr = fminf(1e-2f, lr * 1.5f);
+    ctrl[0] = lr;
+  }
+}
+
 // ---- fused Adam (torch.optim.Adam, eps 1e-8, no weight decay), gradient scaled by the clip coefficient
 // step_dev (optional): device-resident optimiser step counter {count, ticket}; the bias corrections are then
 // derived on the device and the last CTA advances the counter, so the launch can live in a CUDA graph.
@@ -433,6 +451,13 @@ extern "C" int rl_grad_finalize(const float* grad, int64_t n, const double* stat
   grad_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, (size_t)n, stats, ctrl, (FinalizeWs*)workspace,
                                                                global_B, desired_kl, max_grad_norm, adaptive);
   return check_launch("grad_finalize_kernel");
+}
+
+extern "C" int rl_grad_finalize_from_norm(const double* norm2, const double* stats, float* ctrl, double global_B, float desired_kl,
+                                          float max_grad_norm, int32_t adaptive, void* stream) {
+  RL_REQUIRE(norm2 && stats && ctrl && global_B > 0, RL_ERR_BAD_ARG, "rl_grad_finalize_from_norm: bad arguments");
+  finalize_from_norm_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(norm2, stats, ctrl, global_B, desired_kl, max_grad_norm, adaptive);
+  return check_launch("finalize_from_norm_kernel");
 }
 
 extern "C" int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,

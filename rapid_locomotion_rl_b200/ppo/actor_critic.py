@@ -155,6 +155,25 @@ class ActorCritic(nn.Module):
         self._all_layers = self.L_enc + [self.L_cat] + self.L_act + self.L_cri + self.L_ada
         self.refresh_shadows()
 
+    def rebind_grad_store(self, store):
+        """Moves the flat gradient (and every view of it: per-parameter, per-layer, std) into `store`, a float32
+        device tensor with at least n_total + 8 elements - e.g. memory that the other ranks have mapped."""
+        old = self.flat_grad
+        n = self.n_total
+        assert store.dtype == torch.float32 and store.numel() >= n + 8 and store.is_contiguous()
+        store[:n + 8].copy_(self._grad_store)
+        new_flat = store[:n]
+
+        def move(v):
+            off = (v.data_ptr() - old.data_ptr()) // 4
+            assert 0 <= off and off + v.numel() <= n
+            return new_flat[off:off + v.numel()].view(v.shape)
+        self._grad_view = {k: move(v) for k, v in self._grad_view.items()}
+        for L in self._all_layers:
+            L.gw, L.gb = move(L.gw), move(L.gb)
+        self.std_grad = move(self.std_grad)
+        self._grad_store, self.flat_grad = store[:n + 8], new_flat
+
     def _offset_of(self, p):
         return (p.data.data_ptr() - self.flat.data_ptr()) // 4
 

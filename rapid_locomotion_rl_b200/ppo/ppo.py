@@ -64,10 +64,22 @@ class PPO:
         self._idx_buf = None
         self.use_cuda_graph = True
         self.group_wgrads = os.environ.get("RL_GROUP_WGRADS", "1") != "0"
+        self._peer = None           # sharding.PeerComm once enable_peer_allreduce() has mapped the ranks' buffers
+        self._g_red = None
         self._wq = []
         _lib.check(self._lib.rl_gemm_init())
         ac = actor_critic
         self._main_layers = ac.L_enc + [ac.L_cat] + ac.L_act + ac.L_cri
+
+    def enable_peer_allreduce(self):
+        """Multi-GPU: moves the gradient accumulation buffer into memory every rank has mapped and switches the
+        gradient all-reduce of update() from NCCL to the fused NVLink peer kernel.  Collective: call on every rank."""
+        from ..sharding import PeerComm
+        ac = self.actor_critic
+        self._peer = PeerComm(ac.n_total + 8, self.device)
+        ac.rebind_grad_store(self._peer.grad)
+        self._g_red = torch.zeros(self._peer.n, device=self.device)
+        self._graph = None
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape,
                      action_shape):
@@ -216,20 +228,34 @@ class PPO:
         # ---- data-parallel reduction of the policy gradients and loss statistics ----
         g_main, g_adapt = ac.flat_grad[:ac.n_main], ac.flat_grad[ac.n_main:]
         tail = ac._grad_store[ac.n_total:ac.n_total + 4]
-        if allreduce is not None:
-            # ONE all-reduce: [policy gradient | adaptation gradient (all zero here) | 4 loss statistics].  The
-            # per-rank statistics were summed in float64; their fp32 images are summed over the ranks.
+        adaptive = int(A.desired_kl is not None and A.schedule == "adaptive")
+        peer = self._peer if allreduce == "peer" else None
+        g_used = ac.flat_grad
+        if peer is not None:
+            # ONE kernel over NVLink peer memory (csrc/peer_allreduce.cu): sum of every rank's [policy gradient |
+            # adaptation gradient (all zero here) | 4 loss statistics], the squared norm of the policy part, and
+            # the zeroing of the accumulation buffer
+            tail.copy_(self._stats)
+            peer.all_reduce(self._g_red, norm_n=ac.n_main)
+            self._stats.copy_(self._g_red[ac.n_total:ac.n_total + 4])
+            g_used = self._g_red
+        elif allreduce is not None:
+            # NCCL: ONE all-reduce of the same buffer.  The per-rank statistics were summed in float64; their fp32
+            # images are summed over the ranks.
             tail.copy_(self._stats)
             allreduce(ac._grad_store[:ac.n_total + 4])
             self._stats.copy_(tail)
         if getattr(self, "debug_keep_grad", False):      # parity tests read the raw gradient / statistics
-            self.debug_grad = ac.flat_grad.clone()
+            self.debug_grad = g_used[:ac.n_total].clone()
         # ---- clip + KL-adaptive lr + Adam, all on the device ----
-        adaptive = int(A.desired_kl is not None and A.schedule == "adaptive")
-        _lib.check(self._lib.rl_grad_finalize(P(g_main), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws),
-                                              float(B * world), float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive,
-                                              stream))
-        _lib.check(self._lib.rl_adam(P(ac.flat), P(ac.flat_grad), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
+        if peer is not None:
+            _lib.check(self._lib.rl_grad_finalize_from_norm(P(peer.norm2), P(self._stats), P(self._ctrl), float(B * world),
+                                                            float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive, stream))
+        else:
+            _lib.check(self._lib.rl_grad_finalize(P(g_main), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws),
+                                                  float(B * world), float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive,
+                                                  stream))
+        _lib.check(self._lib.rl_adam(P(ac.flat), P(g_used), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
                                      0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
         ac.refresh_shadows(self._main_layers)
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
@@ -249,15 +275,19 @@ class PPO:
             self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
             self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
             self._wgrad_flush()
-            if allreduce is not None:
+            if peer is not None:
+                tail.copy_(stats_ad)
+                peer.all_reduce(self._g_red, norm_n=0)
+                stats_ad.copy_(self._g_red[ac.n_total:ac.n_total + 4])
+            elif allreduce is not None:
                 tail.copy_(stats_ad)
                 allreduce(ac._grad_store[ac.n_main:ac.n_total + 4])
                 stats_ad.copy_(tail)
             if getattr(self, "debug_keep_grad", False):
-                self.debug_grad[ac.n_main:] = g_adapt
+                self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
             n_ad = ac.n_total - ac.n_main
             off = ac.n_main * 4
-            _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, ac.flat_grad.data_ptr() + off, ac.flat_m.data_ptr() + off,
+            _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_used.data_ptr() + off, ac.flat_m.data_ptr() + off,
                                          ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
                                          0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, stream))
             ac.refresh_shadows(ac.L_ada)
@@ -272,6 +302,10 @@ class PPO:
         A, st = PPO_Args, self.storage
         world = world_size()
         allreduce = all_reduce_sum_ if world > 1 else None
+        if world > 1 and os.environ.get("RL_PEER_ALLREDUCE", "1") != "0":
+            if self._peer is None:
+                self.enable_peer_allreduce()
+            allreduce = "peer"
         batch = st.num_envs * st.num_transitions_per_env
         mb = batch // A.num_mini_batches
         indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)

@@ -55,3 +55,54 @@ def env_shard(num_envs_global, rank_=None, world=None):
     base, rem = divmod(int(num_envs_global), world)
     start = rank_ * base + min(rank_, rem)
     return start, base + (1 if rank_ < rem else 0)
+
+
+class PeerComm:
+    """Every rank's gradient buffer, staging buffer and flag block mapped into every rank (CUDA IPC over NVLink /
+    NVSwitch peer access) for `rl_peer_allreduce` (csrc/peer_allreduce.cu): the gradient all-reduce of PPO.update
+    as ONE kernel that also produces the gradient norm and zeroes the accumulation buffer, instead of an NCCL call
+    followed by separate reduction / zeroing work.  Needs an initialised process group (handles are exchanged with
+    all_gather_object) and all ranks on one node."""
+
+    def __init__(self, n_floats, device):
+        import ctypes as C
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _lib
+        self._lib = _lib.lib()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > _lib.DEFINES["RL_PEER_MAX_RANKS"]:
+            raise _lib.RlError("PeerComm supports at most %d ranks" % _lib.DEFINES["RL_PEER_MAX_RANKS"])
+        self.n = (int(n_floats) + 3) // 4 * 4
+        self.device = torch.device(device)
+        # one allocation per rank: [gradient n | staging n | 64 flag words]
+        self.block = torch.zeros(2 * self.n + 64, dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, reduce_tensor(self.block))
+        self.peers = []
+        for p in range(self.world):
+            if p == self.rank:
+                self.peers.append(self.block)
+            else:
+                rebuild, args = handles[p]
+                self.peers.append(rebuild(*args))          # cudaIpcOpenMemHandle (enables peer access lazily)
+        self.grad = self.block[:self.n]
+        self.local_ws = torch.zeros(4, dtype=torch.float32, device=self.device)      # 16 B: norm accumulator, call counter
+        self.norm2 = torch.zeros(1, dtype=torch.float64, device=self.device)
+        c = _lib.RlPeerComm()
+        for p, t in enumerate(self.peers):
+            base = t.data_ptr()
+            c.grad[p], c.stage[p], c.flags[p] = base, base + 4 * self.n, base + 8 * self.n
+        c.local_ws, c.world, c.rank = self.local_ws.data_ptr(), self.world, self.rank
+        self._c = c
+        dist.barrier()          # nobody starts reducing before every rank has mapped every buffer
+
+    def all_reduce(self, out, norm_n=0):
+        """out[:n] = sum over ranks of their gradient buffers; self.norm2 = squared norm of out[:norm_n]; the own
+        gradient buffer is zeroed.  Uses the device-side call counter, so the launch can live in a CUDA graph."""
+        import ctypes as C
+        from . import _lib
+        assert out.dtype == torch.float32 and out.numel() >= self.n and out.is_contiguous()
+        _lib.check(self._lib.rl_peer_allreduce(C.byref(self._c), 0, self.n, int(norm_n), out.data_ptr(), self.norm2.data_ptr(), 0,
+                                               _lib.current_stream()))

@@ -57,6 +57,25 @@ def main():
     ppo.minibatch_step(idx_local, world, sharding.all_reduce_sum_)
     torch.cuda.synchronize()
     flat = ac.flat.clone()
+
+    # ---- the same steps with the fused NVLink peer all-reduce instead of NCCL (csrc/peer_allreduce.cu) ----
+    acp, ppop = make(N, slice(s0, s0 + cnt))
+    ppop.storage.compute_returns(last_values[s0:s0 + cnt].to(dev), PPO_Args.gamma, PPO_Args.lam)
+    ppop.enable_peer_allreduce()
+    ppop.minibatch_step(idx_local, world, "peer")
+    torch.cuda.synchronize()
+    d1 = (acp.flat - flat).abs().max().item()
+    assert d1 <= 2e-6, "peer all-reduce step differs from the NCCL step: %g" % d1
+    for k in range(1, 4):                                   # more steps: call counters, zeroing, both segments
+        idx_k = perms[rank][k * mb:(k + 1) * mb].to(dev)
+        ppo.minibatch_step(idx_k, world, sharding.all_reduce_sum_)
+        ppop.minibatch_step(idx_k, world, "peer")
+    torch.cuda.synchronize()
+    d4 = (acp.flat - ac.flat).abs().max().item()
+    assert d4 <= 2e-4, "peer and NCCL paths drifted apart after 4 steps: %g" % d4
+    peers_flat = [torch.zeros_like(acp.flat) for _ in range(world)]
+    dist.all_gather(peers_flat, acp.flat)
+    assert all(torch.equal(peers_flat[0], t) for t in peers_flat), "ranks diverged on the peer path"
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     adv_local = ppo.storage.advantages.clone()
@@ -91,7 +110,8 @@ def main():
         assert diff <= 2.5e-3, "sharded step differs from the single-process step: %g" % diff     # |dw| <= lr per Adam step
         cos = torch.nn.functional.cosine_similarity(ac1.flat - ppo1_init(dev), flat - ppo1_init(dev), dim=0).item()
         assert cos > 0.98, cos
-        print("MULTIGPU OK world=%d max|dw diff|=%.3g update cosine=%.4f" % (world, diff, cos))
+        print("MULTIGPU OK world=%d max|dw diff|=%.3g update cosine=%.4f; peer vs NCCL: %.3g after 1 step, %.3g after 4" %
+              (world, diff, cos, d1, d4))
     dist.barrier()
     dist.destroy_process_group()
 
