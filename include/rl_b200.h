@@ -569,6 +569,7 @@ typedef struct RlPeerComm {
   void* local_ws;
   int32_t world, rank;
 } RlPeerComm;
+int rl_enable_peer_access(int32_t peer_device);   /* current device -> peer_device loads / stores */
 int rl_peer_allreduce(const RlPeerComm* comm_host, int64_t offset, int64_t n, int64_t norm_n, float* out,
                       double* norm2_out, uint32_t step, void* stream);
 

@@ -116,6 +116,7 @@ SIGNATURES = {
                           C.c_float, _P, _P]),
     "rl_gemm_init": (C.c_int, []),
     "rl_grad_finalize_from_norm": (C.c_int, [_P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P]),
+    "rl_enable_peer_access": (C.c_int, [C.c_int32]),
     "rl_peer_allreduce": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_uint32, _P]),
     "rl_wgrad_grouped": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_create": (C.c_int, [_P, _P]),

@@ -180,3 +180,16 @@ extern "C" int rl_peer_allreduce(const RlPeerComm* comm, int64_t offset, int64_t
   rl::peer_allreduce_kernel<<<grid, rl::PEER_THREADS, 0, (cudaStream_t)stream>>>(a);
   return rl::check_launch("peer_allreduce_kernel");
 }
+
+// enables direct loads / stores from the current device to `peer_device` (no-op when already enabled)
+extern "C" int rl_enable_peer_access(int32_t peer_device) {
+  int cur = 0, can = 0;
+  cudaGetDevice(&cur);
+  if (cur == peer_device) return RL_OK;
+  cudaDeviceCanAccessPeer(&can, cur, peer_device);
+  RL_REQUIRE(can, RL_ERR_UNSUPPORTED, "rl_enable_peer_access: device %d cannot access device %d", cur, peer_device);
+  cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (err == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); err = cudaSuccess; }
+  RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(err));
+  return RL_OK;
+}

@@ -79,14 +79,20 @@ class PeerComm:
         self.block = torch.zeros(2 * self.n + 64, dtype=torch.float32, device=self.device)
         torch.cuda.synchronize(self.device)
         handles = [None] * self.world
-        dist.all_gather_object(handles, reduce_tensor(self.block))
+        dist.all_gather_object(handles, (self.device.index, reduce_tensor(self.block)))
         self.peers = []
-        for p in range(self.world):
-            if p == self.rank:
-                self.peers.append(self.block)
-            else:
-                rebuild, args = handles[p]
-                self.peers.append(rebuild(*args))          # cudaIpcOpenMemHandle (enables peer access lazily)
+        with torch.cuda.device(self.device):
+            for p in range(self.world):
+                if p == self.rank:
+                    self.peers.append(self.block)
+                    continue
+                src_dev, (rebuild, args) = handles[p]
+                _lib.check(self._lib.rl_enable_peer_access(int(src_dev)))
+                # open the IPC handle with OUR device current (argument 6 of rebuild_cuda_tensor is the device the
+                # storage is opened on): the mapping is then addressable by kernels of this device over NVLink
+                args = list(args)
+                args[6] = self.device.index
+                self.peers.append(rebuild(*args))          # cudaIpcOpenMemHandle, peer access enabled lazily
         self.grad = self.block[:self.n]
         self.local_ws = torch.zeros(4, dtype=torch.float32, device=self.device)      # 16 B: norm accumulator, call counter
         self.norm2 = torch.zeros(1, dtype=torch.float64, device=self.device)
