@@ -277,7 +277,7 @@ class PPO:
             self._wgrad_flush()
             if peer is not None:
                 tail.copy_(stats_ad)
-                peer.all_reduce(self._g_red, norm_n=0)
+                peer.all_reduce(self._g_red, norm_n=0, start=ac.n_main)     # adaptation gradient + statistics only
                 stats_ad.copy_(self._g_red[ac.n_total:ac.n_total + 4])
             elif allreduce is not None:
                 tail.copy_(stats_ad)

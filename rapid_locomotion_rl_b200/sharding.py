@@ -104,11 +104,13 @@ class PeerComm:
         self._c = c
         dist.barrier()          # nobody starts reducing before every rank has mapped every buffer
 
-    def all_reduce(self, out, norm_n=0):
-        """out[:n] = sum over ranks of their gradient buffers; self.norm2 = squared norm of out[:norm_n]; the own
-        gradient buffer is zeroed.  Uses the device-side call counter, so the launch can live in a CUDA graph."""
+    def all_reduce(self, out, norm_n=0, start=0):
+        """out[start:n] = sum over ranks of that range of their gradient buffers (start is rounded down to a multiple
+        of 4); self.norm2 = squared norm of the first norm_n floats of the range; the own range is zeroed.  Uses the
+        device-side call counter, so the launch can live in a CUDA graph."""
         import ctypes as C
         from . import _lib
         assert out.dtype == torch.float32 and out.numel() >= self.n and out.is_contiguous()
-        _lib.check(self._lib.rl_peer_allreduce(C.byref(self._c), 0, self.n, int(norm_n), out.data_ptr(), self.norm2.data_ptr(), 0,
-                                               _lib.current_stream()))
+        start = int(start) // 4 * 4
+        _lib.check(self._lib.rl_peer_allreduce(C.byref(self._c), start, self.n - start, int(norm_n), out.data_ptr() + 4 * start,
+                                               self.norm2.data_ptr(), 0, _lib.current_stream()))
