@@ -41,15 +41,13 @@ constexpr int TRACE_MMA = 8, TRACE_EPI = 5; // stamps per op (loads: 1)
 constexpr int WAIT_NS_LOAD = RL_CHAIN_WAIT_NS_LOAD, WAIT_NS_EPI = RL_CHAIN_WAIT_NS_EPI;
 
 // device-side op formats (built by rl_chain_create from the ABI structs)
-struct DevMmaOp {            // 32 B
+struct DevMmaOp {            // 32 B; everything the issuing warp would otherwise have to decode is precomputed
   uint32_t a_lo, b_lo;       // low descriptor words without the shared-memory window base: (off >> 4) | LBO field
   uint32_t idesc;
-  uint16_t tmem_col;
-  uint8_t k_steps, accumulate;
-  uint16_t wait0, wait1, wait2;
-  uint8_t commit0, commit1, commit2, pad0;
-  uint16_t pad1;
-  uint32_t pad2;
+  uint32_t misc;             // tmem_col | k_steps << 16 | accumulate << 24
+  uint16_t wait_off[3];      // byte offset of the barrier in the barrier block + 1, or 0 for "no wait"
+  uint16_t commit_off[3];    // same for the barriers tcgen05.commit arrives on
+  uint32_t parities;         // bit 2j: parity of wait j when the tile iteration is even, bit 2j+1: when it is odd
 };
 static_assert(sizeof(DevMmaOp) == 32, "DevMmaOp layout");
 
@@ -82,6 +80,16 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_addr(uint32_t bar_smem_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar_smem_addr), "r"(parity) : "memory");
   return ok != 0;
 }
 __device__ __noinline__ void chain_timeout(uint32_t id, uint32_t parity, int it) {
@@ -221,21 +229,35 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
       for (int i = 0; i < p.n_mmas; ++i) {
         const DevMmaOp nxt = p.mmas[i + 1 < p.n_mmas ? i + 1 : i];
         if (tr && lane == 0) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
-        chain_wait3(bars, cur.wait0, cur.wait1, cur.wait2, it);
+        {
+          // fast path: the three try_waits back to back; only what failed is polled again
+          const uint32_t par = cur.parities >> (it & 1);
+          const uint32_t w0 = cur.wait_off[0], w1 = cur.wait_off[1], w2 = cur.wait_off[2];
+          bool ok0 = w0 == 0 || mbar_try_addr(bar0 + w0 - 1, par & 1u);
+          bool ok1 = w1 == 0 || mbar_try_addr(bar0 + w1 - 1, (par >> 2) & 1u);
+          bool ok2 = w2 == 0 || mbar_try_addr(bar0 + w2 - 1, (par >> 4) & 1u);
+          uint32_t spins = 0;
+          while (!(ok0 && ok1 && ok2)) {
+            if (!ok0) ok0 = mbar_try_addr(bar0 + w0 - 1, par & 1u);
+            if (!ok1) ok1 = mbar_try_addr(bar0 + w1 - 1, (par >> 2) & 1u);
+            if (!ok2) ok2 = mbar_try_addr(bar0 + w2 - 1, (par >> 4) & 1u);
+            if (++spins > (1u << 24)) chain_timeout(((!ok0 ? w0 : (!ok1 ? w1 : w2)) - 1) / 8, 2, it);
+          }
+        }
         tc_fence_after();
         if (elect_one()) {
           if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
           const uint32_t a_lo = cur.a_lo + base16, b_lo = cur.b_lo + base16, idesc = cur.idesc;
-          const uint32_t tmem_d = tmem_base + cur.tmem_col;
-          const uint32_t k_steps = cur.k_steps;
-          mma_issue(tmem_d, a_lo, b_lo, idesc, cur.accumulate);                 // K16 step 0
+          const uint32_t tmem_d = tmem_base + (cur.misc & 0xFFFFu);
+          const uint32_t k_steps = (cur.misc >> 16) & 0xFFu;
+          mma_issue(tmem_d, a_lo, b_lo, idesc, cur.misc >> 24);                 // K16 step 0
           if (k_steps > 1) mma_issue(tmem_d, a_lo + 2, b_lo + 2, idesc, 1);     // +32 B per step
           if (k_steps > 2) mma_issue(tmem_d, a_lo + 4, b_lo + 4, idesc, 1);
           if (k_steps > 3) mma_issue(tmem_d, a_lo + 6, b_lo + 6, idesc, 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 4] = clock64();
-          if (cur.commit0 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * cur.commit0);
-          if (cur.commit1 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * cur.commit1);
-          if (cur.commit2 != RL_CHAIN_NONE) mma_commit(nullptr, bar0 + 8 * cur.commit2);
+          if (cur.commit_off[0]) mma_commit(nullptr, bar0 + cur.commit_off[0] - 1);
+          if (cur.commit_off[1]) mma_commit(nullptr, bar0 + cur.commit_off[1] - 1);
+          if (cur.commit_off[2]) mma_commit(nullptr, bar0 + cur.commit_off[2] - 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 7] = clock64();
         }
         __syncwarp();
@@ -488,9 +510,16 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
     x.a_lo = (o.a_off >> 4) | (1u << 16);        // LBO field = 1 (unused for swizzled K-major)
     x.b_lo = (o.b_off >> 4) | (1u << 16);
     x.idesc = instr_desc_bf16(128, o.n, false, false);
-    x.tmem_col = o.tmem_col; x.k_steps = o.k_steps; x.accumulate = o.accumulate;
-    x.wait0 = o.wait0; x.wait1 = o.wait1; x.wait2 = o.wait2;
-    x.commit0 = o.commit0; x.commit1 = o.commit1; x.commit2 = o.commit2;
+    x.misc = (uint32_t)o.tmem_col | ((uint32_t)o.k_steps << 16) | ((uint32_t)(o.accumulate != 0) << 24);
+    const uint16_t ws[3] = {o.wait0, o.wait1, o.wait2};
+    const uint8_t cs[3] = {o.commit0, o.commit1, o.commit2};
+    x.parities = 0;
+    for (int j = 0; j < 3; ++j) {
+      const uint32_t id = ws[j] & 0xFFu, base = (ws[j] >> 8) & 1u, flip = (ws[j] >> 9) & 1u;
+      x.wait_off[j] = id == RL_CHAIN_NONE ? 0 : (uint16_t)(8 * id + 1);
+      x.parities |= (base << (2 * j)) | ((base ^ flip) << (2 * j + 1));
+      x.commit_off[j] = cs[j] == RL_CHAIN_NONE ? 0 : (uint16_t)(8 * cs[j] + 1);
+    }
   }
   RlChainEpiOp* de = reinterpret_cast<RlChainEpiOp*>(blob.data());
   {
