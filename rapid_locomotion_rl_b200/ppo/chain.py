@@ -799,63 +799,87 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
     return p.finalize()
 
 
-def trunk_backward_program(T, n_stages=6):
+def trunk_backward_program(T, n_stages=8):
     """dgrad half of the backward of actor + critic + encoder (what autograd does behind ppo.py:146-148 for
     the layer inputs): from d(loss)/d(mean) and d(loss)/d(value) down to the encoder's first hidden layer,
     multiplying by ELU' of the saved activations, storing every layer-output gradient for the wgrad GEMMs.
-    The two first-layer gradient streams (actor, critic) also accumulate d(latent)."""
-    regions = {"C0": (0, 64), "C1": (64, 64), "BIG": (128, 256), "LAT": (384, 32)}
-    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=regions, name="trunk_backward",
-                     region_worker={"C0": 0, "C1": 1, "LAT": 0})
+    The two first-layer gradient streams (actor, critic) also accumulate d(latent).
+
+    The wide first-layer gradient (2 x 512 columns) is produced in 128-column super-chunks: four N = 128 MMAs
+    each (one per 64-wide k-block of the second layer's gradient) - the MMA warp pays ~900 cycles per op
+    whatever its size, so half as many ops as 64-column chunks is what shortens the tile.
+
+    Tensor-memory map (columns): D2 [0, 256) | SA [256, 384) | LAT [384, 416); SB [0, 128) lies INSIDE D2.
+    The builder tracks each name separately; the overlap is safe because of the MMA warp's program order:
+      * D2 is written again only after the last use of SB has been read - the MMAs that consumed SB's boxes
+        (the d(latent) accumulation) waited for those boxes, i.e. for the epilogue's reads of SB, and come
+        earlier in the program;
+      * SB is first written by super-chunk 1, after super-chunk 0's four MMAs have waited for all four boxes
+        of the 256-wide gradient, i.e. for every read of D2.
+    The emulator's numeric check under adversarial scheduling covers exactly this (an early overwrite of an
+    unread accumulator shows up as a wrong result)."""
+    regions = {"D2": (0, 256), "SB": (0, 128), "SA": (256, 128), "LAT": (384, 32)}
+    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=0, regions=regions, name="trunk_backward",
+                     region_worker={"LAT": 0})
     H = T["Wcat_t"].shape[1] // 2
     num_obs = T["num_obs"]
+    assert H % 128 == 0
     tY1, tdY1 = p.tensor(T["Y1"], 128), p.tensor(T["dY1"], 128)
     tWcat_t = p.tensor(T["Wcat_t"], 32)
     acc_lat = p.acc("LAT")
     nets = [("a", T["dmean"], 0, "Wa4t", "Wa3t", "Wa2t", "A3", "A2", "dA3", "dA2"),
             ("c", T["dvalue"], H, "Wc4t", "Wc3t", "Wc2t", "C3", "C2", "dC3", "dC2")]
+    nsc = H // 128
     lat_ops = {"n": 0, "total": 2 * (H // 64)}
     for ni, (tag, d_out, off, w4, w3, w2, s3, s2, g3, g2) in enumerate(nets):
-        d_in = p.load_input(ni, p.tensor(d_out, 128), 0)
-        tW4, tW3, tW2 = p.tensor(T[w4], 128), p.tensor(T[w3], 128), p.tensor(T[w2], 64)
+        tW4, tW3, tW2 = p.tensor(T[w4], 128), p.tensor(T[w3], 128), p.tensor(T[w2], 128)
         tS3, tS2, tG3, tG2 = p.tensor(T[s3], 128), p.tensor(T[s2], 128), p.tensor(T[g3], 128), p.tensor(T[g2], 128)
         n3, n2 = T[w4].shape[0], T[w3].shape[0]
-        acc = p.acc("BIG")
+        assert n3 <= 128 and n2 <= 256 and n2 % 64 == 0
+        d_in = p.load_stage(p.tensor(d_out, 128), col0=0, row0=0, tile_rows=True)
+        acc = p.acc("SA")
         _dense(p, [d_in], tW4, n3, acc, k_last_steps=(d_out.shape[1] + 15) // 16)
         d3 = _boxes(p, acc, n3, EPI_DELU, 0, tG3, aux_tensor=tS3)
-        acc = p.acc("BIG")
+        acc = p.acc("D2")
         _dense(p, d3, tW3, n2, acc)
         d2 = _boxes(p, acc, n2, EPI_DELU, 0, tG2, aux_tensor=tS2)
-        nch = H // 64
-        boxes = [None] * nch
+        accs, boxes = [None] * nsc, [None] * nsc
 
-        def chunk(c):
-            a1 = p.acc("C%d" % (c % 2))
+        def sc_mma(k):
+            a1 = p.acc("SA" if k % 2 == 0 else "SB")
             for j, a in enumerate(d2):
-                s = p.load_stage(tW2, col0=64 * j, row0=64 * c)
-                p.mma(a, s, n=64, acc=a1, k_steps=4, accumulate=j > 0, acc_last=(j == len(d2) - 1), a_release=(c == nch - 1))
-            aux = p.load_stage(tY1, col0=off + 64 * c, row0=0, tile_rows=True, consumer="epi%d" % p.worker_for(a1, 0))
-            boxes[c] = p.epi_box(a1, 0, EPI_DELU, aux=aux, store=(tdY1, off + 64 * c), last=True)
+                s = p.load_stage(tW2, col0=64 * j, row0=128 * k)
+                p.mma(a, s, n=128, acc=a1, k_steps=4, accumulate=j > 0, acc_last=(j == len(d2) - 1), a_release=(k == nsc - 1))
+            accs[k] = a1
 
-        def lat(c):
-            s = p.load_stage(tWcat_t, col0=off + 64 * c, row0=num_obs)
-            lat_ops["n"] += 1
-            p.mma(boxes[c], s, n=32, acc=acc_lat, k_steps=4, accumulate=lat_ops["n"] > 1,
-                  acc_last=(lat_ops["n"] == lat_ops["total"]), a_release=True)
-        chunk(0)
-        for c in range(1, nch):
-            chunk(c)
-            lat(c - 1)
-        lat(nch - 1)
+        def sc_epi(k):
+            boxes[k] = _boxes(p, accs[k], 128, EPI_DELU, 0, tdY1, store_col0=off + 128 * k, aux_tensor=tY1, aux_col0=off + 128 * k)
+
+        def lat(k):
+            for b, box in enumerate(boxes[k]):
+                s = p.load_stage(tWcat_t, col0=off + 128 * k + 64 * b, row0=num_obs)
+                lat_ops["n"] += 1
+                p.mma(box, s, n=32, acc=acc_lat, k_steps=4, accumulate=lat_ops["n"] > 1,
+                      acc_last=(lat_ops["n"] == lat_ops["total"]), a_release=True)
+        # software pipeline: the MMAs of super-chunk k run while the epilogue workers finish super-chunk k - 1;
+        # the d(latent) MMAs of k - 1 come next (they release the two pool units super-chunk k's boxes go to)
+        sc_mma(0)
+        sc_epi(0)
+        for k in range(1, nsc):
+            sc_mma(k)
+            lat(k - 1)
+            sc_epi(k)
+        lat(nsc - 1)
     # ---- encoder ----
     tdLat = p.tensor(T["dLat"], 128)
     dlat = _boxes(p, acc_lat, 32, EPI_PLAIN, 0, tdLat)
     tWe3t, tWe2t = p.tensor(T["We3t"], 128), p.tensor(T["We2t"], 128)
     tH2, tH1, tdH2, tdH1 = p.tensor(T["H2"], 128), p.tensor(T["H1"], 128), p.tensor(T["dH2"], 128), p.tensor(T["dH1"], 128)
-    acc = p.acc("BIG")
+    assert T["We3t"].shape[0] <= 128 and T["We2t"].shape[0] <= 256
+    acc = p.acc("SA")
     _dense(p, dlat, tWe3t, T["We3t"].shape[0], acc, k_last_steps=2)
     dh2 = _boxes(p, acc, T["We3t"].shape[0], EPI_DELU, 0, tdH2, aux_tensor=tH2)
-    acc = p.acc("BIG")
+    acc = p.acc("D2")
     _dense(p, dh2, tWe2t, T["We2t"].shape[0], acc)
     _boxes(p, acc, T["We2t"].shape[0], EPI_DELU, 0, tdH1, aux_tensor=tH1, has_reader=False)
     return p.finalize()

@@ -98,6 +98,31 @@ def test_emulator_detects_broken_schedules(mutant):
     assert caught >= 1
 
 
+def test_emulator_detects_accumulator_aliasing():
+    """trunk_backward lets two accumulator names share tensor-memory columns (SB inside D2) and relies on program
+    order for safety.  Swapping the ping-pong order makes super-chunk 0 overwrite columns of the 256-wide
+    gradient the epilogue has not read yet: the emulated result must come out wrong."""
+    import inspect
+    code = inspect.getsource(chain.trunk_backward_program)
+    assert '"SA" if k % 2 == 0 else "SB"' in code
+    ns = dict(vars(chain))
+    exec(code.replace('"SA" if k % 2 == 0 else "SB"', '"SB" if k % 2 == 0 else "SA"'), ns)
+    caught = 0
+    for seed in range(3):
+        T = ck.make_tensors(ROWS, seed)
+        fwd = ck.ref_teacher(T)
+        for k in ("H1", "H2", "Y1", "A2", "A3", "C2", "C3"):
+            T[k].copy_(fwd[k].to(torch.bfloat16))
+        ref = ck.ref_trunk_backward(T)
+        try:
+            chain.Emulator(ns["trunk_backward_program"](T), ROWS, seed=seed).run()
+            caught += any((T[k].float()[:, :ref[k].shape[1]] - ref[k]).abs().max().item() > 0.03 * max(1.0, ref[k].abs().max().item())
+                          for k in ("dA2", "dC2", "dY1", "dLat"))
+        except chain.ChainHazard:
+            caught += 1
+    assert caught >= 2
+
+
 def test_packed_program_layout():
     """The ctypes op arrays carry what the builder decided (spot checks) and respect the device limits."""
     T = ck.make_tensors(ROWS, 0)
