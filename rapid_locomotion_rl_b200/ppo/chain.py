@@ -63,16 +63,17 @@ class AccUse:
 class ChainProgram:
     """Builder + container of one chain program."""
 
-    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1):
-        """Shared-memory units: [inputs | pool | stages]; `regions`: {name: (first tmem column, width)};
+    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1, rings=None):
+        """Shared-memory units: [inputs | pool | ring stages]; `regions`: {name: (first tmem column, width)};
         `region_worker`: regions whose accumulator uses are read by ONE epilogue op -> the worker that owns
         them (a waiter must see every phase of a barrier, so such a region cannot change hands); the other
-        regions are read by both workers, chunk c by worker c % 2."""
+        regions are read by both workers, chunk c by worker c % 2.
+        `rings`: [(name, n_stages, units per stage)] - several independent TMA rings (default: one ring "main" of
+        n_stages x stage_units); the LOAD role still issues every load in program order."""
         self.name = name
-        self.n_inputs, self.n_pool, self.n_stages = n_inputs, n_pool, n_stages
-        self.stage_units = stage_units      # 16 KB units per ring stage (2: boxes of up to 256 rows, N = 256 MMAs)
-        self.n_units = n_inputs + n_pool + n_stages * stage_units
-        assert self.n_units <= _lib.DEFINES["RL_CHAIN_MAX_UNITS"]
+        self.n_inputs, self.n_pool = n_inputs, n_pool
+        rings = rings or [("main", n_stages, stage_units)]
+        self.n_stages, self.stage_units = rings[0][1], rings[0][2]      # of the default (first) ring
         self.tensors = []                # (torch tensor 2-D view, box_rows)
         self.bar_count = []
         self.bar_phases = []             # completions per tile
@@ -83,14 +84,20 @@ class ChainProgram:
         self.regions = dict(regions)
         # resources
         self.pool_units = [n_inputs + i for i in range(n_pool)]
-        self.stage_unit0 = [n_inputs + n_pool + i * stage_units for i in range(n_stages)]
         # a barrier must have ONE waiting agent that sees every phase (waits name a phase only by its parity):
         # each stage has one "full" barrier per consumer role and the producer signals the one of the role
         # that will read this particular landing
-        self.stage_full = {"mma": [self._bar(1, "stage%d.full.mma" % i) for i in range(n_stages)]}
-        self.stage_empty = [self._bar(1, "stage%d.empty" % i) for i in range(n_stages)]
-        self.stage_uses = [0] * n_stages
-        self.ring_pos = 0
+        self.rings = {}
+        unit = n_inputs + n_pool
+        for rname, ns, su in rings:
+            tag = "" if rname == "main" else rname + "."
+            self.rings[rname] = dict(n=ns, su=su, unit0=[unit + i * su for i in range(ns)], pos=0, uses=[0] * ns, tag=tag,
+                                     empty=[self._bar(1, "%sstage%d.empty" % (tag, i)) for i in range(ns)],
+                                     full={"mma": [self._bar(1, "%sstage%d.full.mma" % (tag, i)) for i in range(ns)]})
+            unit += ns * su
+        self.default_ring = rings[0][0]
+        self.n_units = unit
+        assert self.n_units <= _lib.DEFINES["RL_CHAIN_MAX_UNITS"]
         self.pool_ready = [self._bar(4, "pool%d.ready" % i) for i in range(n_pool)]
         self.pool_free = [self._bar(1, "pool%d.free" % i) for i in range(n_pool)]
         self.pool_pos = 0
@@ -126,7 +133,7 @@ class ChainProgram:
     def tensor(self, t, box_rows):
         assert t.dim() == 2 and t.dtype == torch.bfloat16 and t.stride(1) == 1
         assert (t.stride(0) * 2) % 16 == 0 and t.data_ptr() % 16 == 0, "TMA operand alignment"
-        assert 8 <= box_rows <= 256 and box_rows * 128 <= UNIT * self.stage_units
+        assert 8 <= box_rows <= 256 and box_rows * 128 <= UNIT * max(r["su"] for r in self.rings.values())
         self.tensors.append((t, box_rows))
         assert len(self.tensors) <= _lib.DEFINES["RL_CHAIN_MAX_TENSORS"]
         return len(self.tensors) - 1
@@ -160,21 +167,23 @@ class ChainProgram:
         return use
 
     # ---- ring stages ------------------------------------------------------------------------------
-    def load_stage(self, tensor, col0, row0, tile_rows=False, consumer="mma"):
-        """One TMA box into the next ring stage; `consumer`: the role that will wait for it ("mma", "epi0", "epi1")."""
+    def load_stage(self, tensor, col0, row0, tile_rows=False, consumer="mma", ring=None):
+        """One TMA box into the next stage of `ring`; `consumer`: the role that will wait for it ("mma", "epi0", "epi1")."""
         t, box_rows = self.tensors[tensor]
-        s = self.ring_pos % self.n_stages
-        self.ring_pos += 1
-        wait = _Wait(self.stage_empty[s], self.stage_uses[s])
-        self.stage_uses[s] += 1
-        if consumer not in self.stage_full:
-            self.stage_full[consumer] = [self._bar(1, "stage%d.full.%s" % (i, consumer)) for i in range(self.n_stages)]
-        full = self.stage_full[consumer][s]
+        R = self.rings[ring or self.default_ring]
+        assert box_rows * 128 <= UNIT * R["su"], "box does not fit a stage of this ring"
+        s = R["pos"] % R["n"]
+        R["pos"] += 1
+        wait = _Wait(R["empty"][s], R["uses"][s])
+        R["uses"][s] += 1
+        if consumer not in R["full"]:
+            R["full"][consumer] = [self._bar(1, "%sstage%d.full.%s" % (R["tag"], i, consumer)) for i in range(R["n"])]
+        full = R["full"][consumer][s]
         ordn = self._signal(full)
-        off = self.stage_unit0[s] * UNIT
+        off = R["unit0"][s] * UNIT
         self.loads.append(dict(wait=wait, full_bar=full, tensor=tensor, smem_off=off, col0=col0, row0=row0,
                                bytes=box_rows * 128, tile_rows=int(tile_rows)))
-        return StageUse(s, off, _Wait(full, ordn), self.stage_empty[s])
+        return StageUse(s, off, _Wait(full, ordn), R["empty"][s])
 
     def worker_for(self, acc, col):
         """Epilogue worker that reads accumulator columns [col, col + 64) of this use."""
@@ -213,7 +222,7 @@ class ChainProgram:
             acc.full = _Wait(self.acc_full[acc.region], self._signal(self.acc_full[acc.region]))
             commits.append(self.acc_full[acc.region])
         width = self.regions[acc.region][1]
-        assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 128 * self.stage_units
+        assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 256
         assert len(waits) <= 3 and len(commits) <= 3
         self.mmas.append(dict(a_off=a.off, b_off=b.off, n=n, tmem_col=acc.col + col_off, k_steps=k_steps,
                               accumulate=int(accumulate), waits=waits, commits=commits))
@@ -304,8 +313,9 @@ class ChainProgram:
     def finalize(self):
         if self._finalized:
             return self
-        for s in range(self.n_stages):
-            assert self.bar_phases[self.stage_empty[s]] == self.stage_uses[s], "stage %d: uses and releases differ" % s
+        for rname, R in self.rings.items():
+            for s in range(R["n"]):
+                assert self.bar_phases[R["empty"][s]] == R["uses"][s], "ring %s stage %d: uses and releases differ" % (rname, s)
         for slot, use in self.input_loads.items():
             assert self.bar_phases[self.input_free[slot]] == 1, "input %d is never released (or more than once)" % slot
         for r, parts in self.acc_participants.items():
@@ -469,6 +479,7 @@ class Emulator:
         unit_readers = [0] * p.n_units       # issued, not yet executed async reads (MMA operands, TMA stores)
         unit_loading = [0] * p.n_units       # TMA loads in flight into the unit
         tmem = torch.zeros(128, 512)
+        tmem_unread = torch.zeros(512, dtype=torch.bool)   # written by an MMA, not yet loaded by an epilogue op
         mma_queue = []                       # issued MMAs / commits, executed in order by the tensor pipe
         loads_inflight = []
         stores_inflight = [[], []]           # per epilogue worker: bulk groups complete in order
@@ -547,6 +558,12 @@ class Emulator:
             ua, ub = o["a_off"] // UNIT, o["b_off"] // UNIT
             n, c0 = o["n"], o["tmem_col"]
             k = 16 * o["k_steps"]
+            if not o["accumulate"] and bool(tmem_unread[c0:c0 + n].any()):
+                # accumulator names may share columns (trunk_backward): a new accumulation must never start on
+                # columns whose previous content the epilogue has not loaded yet
+                raise ChainHazard("%s: MMA (tmem col %d, n %d) overwrites accumulator columns the epilogue has not read" %
+                                  (p.name, c0, n))
+            tmem_unread[c0:c0 + n] = True
             A, B = units[ua][:, :k], flat_smem[128 * ub:128 * ub + n, :k]
             d = A @ B.t()
             if o["accumulate"]:
@@ -566,6 +583,7 @@ class Emulator:
                     yield from spec_wait(o["wait_acc"], it, "epi")
                     nc = o["ncols"]
                     f = tmem[:, o["tmem_col"]:o["tmem_col"] + nc].clone()
+                    tmem_unread[o["tmem_col"]:o["tmem_col"] + (64 if nc > 32 else 32)] = False     # tcgen05.ld width
                     if o["arrive_acc_free"] != NONE:
                         for _ in range(4):
                             bars[o["arrive_acc_free"]].arrive()
@@ -885,26 +903,46 @@ def trunk_backward_program(T, n_stages=8):
     return p.finalize()
 
 
-def adaptation_forward_program(T, save=True):
+def adaptation_forward_program(T, save=True, a_depth=4):
     """adaptation_module(obs_history) (actor_critic.py:158-162; ppo.py:157): the 630-wide input streams
-    through the ring next to the first layer's weights, the two small layers stay on chip."""
-    p = ChainProgram(n_pool=6, n_stages=4, n_inputs=0, regions=REGIONS, name="adaptation_forward", stage_units=2)
+    through its own ring next to the first layer's weights, the two small layers stay on chip.
+
+    Two rings: the input boxes come from HBM (~2 us latency, 158 KB per tile) and need `a_depth` boxes in flight;
+    the weight boxes come from L2 and two 32 KB stages are enough.  The LOAD role issues in program order, so the
+    input loads are emitted `a_depth` k-blocks ahead of the weight loads - a weight load waiting for its stage
+    never holds back an input load that could already be in flight."""
+    n_w = (14 - 6 - a_depth) // 2
+    p = ChainProgram(n_pool=6, n_stages=0, n_inputs=0, regions=REGIONS, name="adaptation_forward",
+                     rings=[("w", n_w, 2), ("x", a_depth, 1)])
     p.params = T["params"]
     tXh, tWd1 = p.tensor(T["Xh"], 128), p.tensor(T["Wd1"], min(256, _round16(T["Wd1"].shape[0])))
     n1, n2, n3 = T["Wd1"].shape[0], T["Wd2"].shape[0], T["Wd3"].shape[0]
+    assert n1 <= 256
     tWd2, tWd3 = p.tensor(T["Wd2"], _round16(n2)), p.tensor(T["Wd3"], _round16(n3))
     st = lambda name: p.tensor(T[name], 128) if save else None
     tD1, tD2 = st("D1"), st("D2")
     K = T["Xh"].shape[1]
     nk = (K + 63) // 64
     acc = p.acc("BIG")
+    xs = {}
+
+    def load_x(j):
+        if j < nk:
+            xs[j] = p.load_stage(tXh, col0=64 * j, row0=0, tile_rows=True, ring="x")
+    ws = {}
+
+    def load_w(j):
+        if j < nk:
+            ws[j] = p.load_stage(tWd1, col0=64 * j, row0=0, ring="w")
+    for j in range(a_depth):
+        load_x(j)
+    for j in range(n_w):
+        load_w(j)
     for j in range(nk):
-        a = p.load_stage(tXh, col0=64 * j, row0=0, tile_rows=True)
-        halves = list(range(0, n1, 256))
-        for hi, h in enumerate(halves):
-            b = p.load_stage(tWd1, col0=64 * j, row0=h)
-            p.mma(a, b, n=min(256, n1 - h), acc=acc, col_off=h, k_steps=min(4, (K - 64 * j + 15) // 16), accumulate=j > 0,
-                  acc_last=(j == nk - 1 and hi == len(halves) - 1), a_release=(hi == len(halves) - 1))
+        p.mma(xs.pop(j), ws.pop(j), n=n1, acc=acc, k_steps=min(4, (K - 64 * j + 15) // 16), accumulate=j > 0,
+              acc_last=(j == nk - 1), a_release=True)
+        load_x(j + a_depth)          # both wait for MMA j (it frees their stages): neither holds the other back
+        load_w(j + n_w)
     d1 = _boxes(p, acc, n1, EPI_BIAS_ELU, T["b_d1"], tD1)
     acc = p.acc("C0")
     _dense(p, d1, tWd2, _round16(n2), acc)
