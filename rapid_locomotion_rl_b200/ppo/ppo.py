@@ -58,6 +58,11 @@ class PPO:
         self._fin_ws = torch.zeros(2, dtype=torch.float64, device=dev)
         self._loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self._stats_ad = torch.zeros(4, dtype=torch.float64, device=dev)
+        # The adaptation module's forward pass depends only on the gathered history rows and its own weights, not
+        # on the policy update: it runs on a side stream (a parallel branch of the captured graph) next to the
+        # teacher path, where its CTAs fill the SMs that a 188-tile minibatch leaves idle in its second wave.
+        self.overlap_adaptation = os.environ.get("RL_PPO_OVERLAP", "1") != "0"
+        self._side = self._ev_fork = self._ev_join = None
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -188,6 +193,16 @@ class PPO:
             P(flat(st.actions)), P(flat(st.values)), P(flat(st.returns)), P(flat(st.actions_log_prob)),
             P(flat(st.advantages)), P(flat(st.mu)), P(flat(st.sigma)), P(idx), B, ac.num_obs, ac.num_priv, ac.num_hist,
             P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
+        hoist = self.overlap_adaptation and ac.use_chain and torch.device(self.device).type == "cuda"
+        if hoist:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_fork.record()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_fork)
+                ac.forward_adaptation(B, save=True)
+                self._ev_join.record()
         # ---- forward ----
         ac.forward_teacher(B, save=True)
         # ---- loss + output gradients ----
@@ -259,9 +274,12 @@ class PPO:
                                      0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
         ac.refresh_shadows(self._main_layers)
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
-        for _ in range(A.num_adaptation_module_substeps):
+        for sub in range(A.num_adaptation_module_substeps):
             ac.forward_encoder(B)
-            ac.forward_adaptation(B, save=True)
+            if hoist and sub == 0:
+                torch.cuda.current_stream().wait_event(self._ev_join)      # computed next to the teacher path
+            else:
+                ac.forward_adaptation(B, save=True)
             stats_ad = self._stats_ad
             stats_ad.zero_()
             _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(w["Xac"]), ld("Xac"), ac.num_obs, B, inv_gb, P(w["dpred"]),
