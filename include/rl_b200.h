@@ -526,6 +526,11 @@ int rl_ppo_gather(const float* obs, const float* priv, const float* hist, const 
                   const float* mu, const float* sigma, const int64_t* idx, int32_t B, int32_t obs_dim,
                   int32_t priv_dim, int32_t hist_dim, void* Xp, int32_t ldp, void* Xac, int32_t ldac, void* Xh,
                   int32_t ldh, float* Lrow, void* stream);
+/* rollout_storage.py:124 (`obs_history_batch = observation_histories[batch_idx]`) alone: Xh [B, ldh] bf16.  The
+ * history is 86 % of a minibatch's gathered bytes and only the adaptation module reads it, so PPO.update issues it
+ * on the stream that runs the adaptation forward, off the policy path (rl_ppo_gather is then called with Xh = NULL). */
+int rl_ppo_gather_history(const float* hist, const int64_t* idx, int32_t B, int32_t hist_dim, void* Xh, int32_t ldh,
+                          void* stream);
 /* fp32 [rows, cols] -> bf16 dst[:, dst_col0 : dst_col0 + pad_to], zero padded beyond cols */
 int rl_cast_bf16(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols,
                  int32_t dst_col0, int32_t pad_to, void* stream);

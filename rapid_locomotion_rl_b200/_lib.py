@@ -107,6 +107,7 @@ SIGNATURES = {
     "rl_history_push": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int32] * 10 + [_P]),
     "rl_ppo_gather": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "rl_ppo_gather_history": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "rl_cast_bf16": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_ppo_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
                               C.c_int32, C.c_float, _P, _P, _P, _P, _P, _P]),

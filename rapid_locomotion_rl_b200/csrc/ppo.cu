@@ -16,6 +16,32 @@ constexpr int ACT = 12;      // num_actions
 constexpr int LAT = 18;      // latent / privileged dim
 constexpr int LROW = 40;     // per-row loss inputs: actions 12, mu_old 12, sigma_old 12, logp_old, adv, ret, v_old
 
+// The 630-float history row is 86 % of the gathered bytes.  8 B loads / 4 B bf16x2 stores when the row is 8 B
+// aligned (even hist_dim, even pitch); five loads are issued before the first conversion so that every warp keeps
+// 1.25 KB in flight (one load at a time left the kernel latency bound at ~45 % of the HBM rate).
+__device__ __forceinline__ void gather_history_row(const float* __restrict__ hs, __nv_bfloat16* __restrict__ hd, int hist_dim, int ldh,
+                                                   int lane) {
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  if (((hist_dim | ldh) & 1) == 0 && ((reinterpret_cast<uintptr_t>(hs) | reinterpret_cast<uintptr_t>(hd)) & 7) == 0) {
+    constexpr int U = 5;
+    for (int c0 = 2 * lane; c0 < ldh; c0 += 64 * U) {
+      float2 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 64 * u;
+        v[u] = c < hist_dim ? __ldg(reinterpret_cast<const float2*>(hs + c)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 64 * u;
+        if (c < ldh) *reinterpret_cast<__nv_bfloat162*>(hd + c) = __floats2bfloat162_rn(v[u].x, v[u].y);
+      }
+    }
+  } else {
+    for (int c = lane; c < ldh; c += 32) hd[c] = c < hist_dim ? __float2bfloat16(hs[c]) : zero;
+  }
+}
+
 // ---- minibatch gather (rollout_storage.py:121-137) + bf16 staging -----------------------------------
 // one warp per minibatch row; every global access is a coalesced run along the row
 __global__ void __launch_bounds__(256)
@@ -34,21 +60,7 @@ ppo_gather_kernel(const float* __restrict__ obs, const float* __restrict__ priv,
     if (c < obs_dim) Xac[(size_t)warp * ldac + c] = __float2bfloat16(obs[src * obs_dim + c]);
     else if (c >= obs_dim + LAT) Xac[(size_t)warp * ldac + c] = zero;   // [obs_dim, obs_dim+18) is the latent slot
   }
-  if (Xh) {
-    // the 630-float history row is 86 % of the gathered bytes: 8 B loads / 4 B bf16x2 stores when the row is
-    // 8 B aligned (even hist_dim, even pitch), i.e. 256 B read and 128 B written per warp instruction
-    const float* hs = hist + src * hist_dim;
-    __nv_bfloat16* hd = Xh + (size_t)warp * ldh;
-    if (((hist_dim | ldh) & 1) == 0 && ((reinterpret_cast<uintptr_t>(hs) | reinterpret_cast<uintptr_t>(hd)) & 7) == 0) {
-      for (int c = 2 * lane; c < ldh; c += 64) {
-        float2 v = make_float2(0.f, 0.f);
-        if (c < hist_dim) v = *reinterpret_cast<const float2*>(hs + c);
-        *reinterpret_cast<__nv_bfloat162*>(hd + c) = __floats2bfloat162_rn(v.x, v.y);
-      }
-    } else {
-      for (int c = lane; c < ldh; c += 32) hd[c] = c < hist_dim ? __float2bfloat16(hs[c]) : zero;
-    }
-  }
+  if (Xh) gather_history_row(hist + src * hist_dim, Xh + (size_t)warp * ldh, hist_dim, ldh, lane);
   float* L = Lrow + (size_t)warp * LROW;
   if (lane < ACT) {
     L[lane] = actions[src * ACT + lane];
@@ -56,6 +68,15 @@ ppo_gather_kernel(const float* __restrict__ obs, const float* __restrict__ priv,
     L[2 * ACT + lane] = sigma[src * ACT + lane];
   }
   if (lane == 0) { L[36] = logp[src]; L[37] = adv[src]; L[38] = returns[src]; L[39] = values[src]; }
+}
+
+// obs_history_batch alone (rollout_storage.py:124): the adaptation module's input, gathered on its own stream
+__global__ void __launch_bounds__(256)
+ppo_gather_history_kernel(const float* __restrict__ hist, const int64_t* __restrict__ idx, int B, int hist_dim,
+                          __nv_bfloat16* __restrict__ Xh, int ldh) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  gather_history_row(hist + (size_t)idx[warp] * hist_dim, Xh + (size_t)warp * ldh, hist_dim, ldh, lane);
 }
 
 // fp32 [rows, cols] (pitch ld_src) -> bf16 [rows, ld_dst], zero padded; optional column offset into dst
@@ -406,6 +427,14 @@ extern "C" int rl_ppo_gather(const float* obs, const float* priv, const float* h
       obs, priv, hist, actions, values, returns, logp, adv, mu, sigma, idx, B, obs_dim, priv_dim, hist_dim,
       (__nv_bfloat16*)Xp, ldp, (__nv_bfloat16*)Xac, ldac, (__nv_bfloat16*)Xh, ldh, Lrow);
   return check_launch("ppo_gather_kernel");
+}
+
+extern "C" int rl_ppo_gather_history(const float* hist, const int64_t* idx, int32_t B, int32_t hist_dim, void* Xh, int32_t ldh,
+                                     void* stream) {
+  RL_REQUIRE(hist && idx && Xh, RL_ERR_BAD_ARG, "rl_ppo_gather_history: null pointer");
+  RL_REQUIRE(B > 0 && hist_dim > 0 && hist_dim <= ldh, RL_ERR_BAD_ARG, "rl_ppo_gather_history: bad dimensions");
+  ppo_gather_history_kernel<<<(B * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hist, idx, B, hist_dim, (__nv_bfloat16*)Xh, ldh);
+  return check_launch("ppo_gather_history_kernel");
 }
 
 extern "C" int rl_cast_bf16(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols,

@@ -62,7 +62,7 @@ class PPO:
         # on the policy update: it runs on a side stream (a parallel branch of the captured graph) next to the
         # teacher path, where its CTAs fill the SMs that a 188-tile minibatch leaves idle in its second wave.
         self.overlap_adaptation = os.environ.get("RL_PPO_OVERLAP", "1") != "0"
-        self._side = self._ev_fork = self._ev_join = None
+        self._side = self._ev_fork = self._ev_join = self._hp = None
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -188,21 +188,24 @@ class PPO:
         stream = _lib.current_stream()
         ld = lambda k: w[k].shape[1]
         flat = lambda t: t.flatten(0, 1)
-        _lib.check(self._lib.rl_ppo_gather(
-            P(flat(st.observations)), P(flat(st.privileged_observations)), P(flat(st.observation_histories)),
-            P(flat(st.actions)), P(flat(st.values)), P(flat(st.returns)), P(flat(st.actions_log_prob)),
-            P(flat(st.advantages)), P(flat(st.mu)), P(flat(st.sigma)), P(idx), B, ac.num_obs, ac.num_priv, ac.num_hist,
-            P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
         hoist = self.overlap_adaptation and ac.use_chain and torch.device(self.device).type == "cuda"
         if hoist:
+            # side branch: history gather (86 % of the gathered bytes) + adaptation forward
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
                 self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
             self._ev_fork.record()
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fork)
+                _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
+                                                           ld("Xh"), _lib.current_stream()))
                 ac.forward_adaptation(B, save=True)
                 self._ev_join.record()
+        _lib.check(self._lib.rl_ppo_gather(
+            P(flat(st.observations)), P(flat(st.privileged_observations)), P(flat(st.observation_histories)),
+            P(flat(st.actions)), P(flat(st.values)), P(flat(st.returns)), P(flat(st.actions_log_prob)),
+            P(flat(st.advantages)), P(flat(st.mu)), P(flat(st.sigma)), P(idx), B, ac.num_obs, ac.num_priv, ac.num_hist,
+            P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), None if hoist else P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
         # ---- forward ----
         ac.forward_teacher(B, save=True)
         # ---- loss + output gradients ----
@@ -345,7 +348,14 @@ class PPO:
             g = torch.cuda.CUDAGraph()
             snap = [t.clone() for t in (self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
                                         self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc)]
-            with torch.cuda.graph(g):
+            # capture on a high-priority stream: kernel nodes keep their stream's priority, so the policy path's CTAs
+            # are placed before those of the side branch (adaptation forward), which only fills what is left
+            kw = {}
+            if self.overlap_adaptation and os.environ.get("RL_PPO_PRIO", "1") != "0":
+                if self._hp is None:
+                    self._hp = torch.cuda.Stream(device=self.device, priority=-1)
+                kw["stream"] = self._hp
+            with torch.cuda.graph(g, **kw):
                 self.minibatch_step(self._idx_buf, world, allreduce)
             # capture does not execute, but keep the state bit-identical in any case
             for t, s0 in zip((self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,

@@ -162,3 +162,21 @@ def test_update_vs_golden(golden_dir):
     L = ac.L_act[0]
     torch.testing.assert_close(L.wb[:, :L.inp].float(), L.w.to(torch.bfloat16).float())
     torch.testing.assert_close(L.wbt[:, :L.out].float(), L.w.t().to(torch.bfloat16).float())
+
+
+def test_gather_history_matches_indexing():
+    """rl_ppo_gather_history == observation_histories[batch_idx] (rollout_storage.py:124) rounded to bf16, zero
+    padded to the workspace pitch; odd dimensions take the scalar path."""
+    import ctypes as C
+    from rapid_locomotion_rl_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(3)
+    for rows, dim, ld, B in ((5000, 630, 632, 3001), (700, 45, 48, 129), (64, 7, 9, 64)):
+        hist = torch.randn(rows, dim, generator=g).to(DEV)
+        idx = torch.randint(0, rows, (B,), generator=g).to(DEV)
+        out = torch.full((B, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.rl_ppo_gather_history(hist.data_ptr(), idx.data_ptr(), B, dim, out.data_ptr(), ld, _lib.current_stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out[:, :dim], hist[idx].to(torch.bfloat16))
+        assert float(out[:, dim:].float().abs().max()) == 0.0
+    assert lib.rl_ppo_gather_history(None, idx.data_ptr(), B, dim, out.data_ptr(), ld, _lib.current_stream()) != 0
