@@ -407,7 +407,7 @@ def run_ours(args):
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
-                     "kernel": "env_step_kernel<true>", "algorithmic_bytes_per_launch": args.envs * bpe},
+                     "kernel": "env_step_quad_kernel<FUSE=true,MINB,STD>", "algorithmic_bytes_per_launch": args.envs * bpe},
         "also": also,
         "ppo": ppo,
         "runner": runner,
