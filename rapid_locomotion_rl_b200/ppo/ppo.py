@@ -57,12 +57,14 @@ class PPO:
         self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self._fin_ws = torch.zeros(2, dtype=torch.float64, device=dev)
         self._loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._loss_acc_ad = torch.zeros(1, dtype=torch.float64, device=dev)    # adaptation statistic of deferred tails
         self._stats_ad = torch.zeros(4, dtype=torch.float64, device=dev)
         # The adaptation module's forward pass depends only on the gathered history rows and its own weights, not
         # on the policy update: it runs on a side stream (a parallel branch of the captured graph) next to the
         # teacher path, where its CTAs fill the SMs that a 188-tile minibatch leaves idle in its second wave.
         self.overlap_adaptation = os.environ.get("RL_PPO_OVERLAP", "1") != "0"
         self._side = self._ev_fork = self._ev_join = self._hp = None
+        self._graph_defer = None
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -179,8 +181,15 @@ class PPO:
                  L.out, EPI_DELU_BF16 if aux is not None else EPI_BF16,
                  aux=None if aux is None else ac._p(aux, aux_off), ld_aux=ld_aux)
 
-    def minibatch_step(self, idx, world=1, allreduce=None):
-        """One PPO minibatch on the rows `idx` (int64 device tensor) of the flattened storage."""
+    def minibatch_step(self, idx, world=1, allreduce=None, defer_tail=False, pending_tail=False):
+        """One PPO minibatch on the rows `idx` (int64 device tensor) of the flattened storage.
+
+        defer_tail: the adaptation module's update of THIS minibatch (loss, dgrad, wgrad, Adam - `_adapt_tail`) is
+        left pending; it runs on the side branch of the NEXT call (pending_tail=True), before that call's adaptation
+        forward, concurrently with the next policy path.  The order of every dependent pair of operations is the
+        reference's (the policy path never reads the adaptation module; its regression target is copied out of the
+        [obs | latent] box before the next minibatch overwrites it), so the results are those of the sequential
+        schedule.  update() flushes the last pending tail."""
         ac, st, A = self.actor_critic, self.storage, PPO_Args
         B = int(idx.numel())
         w = ac.workspace(B, backward=True)
@@ -197,6 +206,8 @@ class PPO:
             self._ev_fork.record()
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fork)
+                if pending_tail:
+                    self._adapt_tail(B, world, None, deferred=True)
                 _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
                                                            ld("Xh"), _lib.current_stream()))
                 ac.forward_adaptation(B, save=True)
@@ -277,45 +288,81 @@ class PPO:
                                      0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
         ac.refresh_shadows(self._main_layers)
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
+        assert not defer_tail or (hoist and A.num_adaptation_module_substeps == 1 and allreduce is None)
         for sub in range(A.num_adaptation_module_substeps):
             ac.forward_encoder(B)
+            if defer_tail:
+                # the next minibatch's teacher forward overwrites the latent slot: keep this one's target
+                self._target(B)[:B, :ac.latent_dim].copy_(w["Xac"][:B, ac.num_obs:ac.num_obs + ac.latent_dim])
+                torch.cuda.current_stream().wait_event(self._ev_join)      # every forked branch rejoins
+                break
             if hoist and sub == 0:
                 torch.cuda.current_stream().wait_event(self._ev_join)      # computed next to the teacher path
             else:
                 ac.forward_adaptation(B, save=True)
-            stats_ad = self._stats_ad
-            stats_ad.zero_()
-            _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(w["Xac"]), ld("Xac"), ac.num_obs, B, inv_gb, P(w["dpred"]),
-                                               P(stats_ad), stream))
-            if ac.use_chain:
-                ac._chain(("adaptation_backward",), chain.adaptation_backward_program).run(B)
-            else:
-                self._dgrad(d[2], w["dpred"], 0, 24, w["dD2"], 0, ld("dD2"), B, aux=w["D2"], ld_aux=ld("D2"))
-                self._dgrad(d[1], w["dD2"], 0, ld("dD2"), w["dD1"], 0, ld("dD1"), B, aux=w["D1"], ld_aux=ld("D1"))
-            self._wgrad(d[2], w["dpred"], 0, 24, w["D2"], 0, ld("D2"), B)
-            self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
-            self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
-            self._wgrad_flush()
-            if peer is not None:
-                tail.copy_(stats_ad)
-                peer.all_reduce(self._g_red, norm_n=0, start=ac.n_main)     # adaptation gradient + statistics only
-                stats_ad.copy_(self._g_red[ac.n_total:ac.n_total + 4])
-            elif allreduce is not None:
-                tail.copy_(stats_ad)
-                allreduce(ac._grad_store[ac.n_main:ac.n_total + 4])
-                stats_ad.copy_(tail)
-            if getattr(self, "debug_keep_grad", False):
-                self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
-            n_ad = ac.n_total - ac.n_main
-            off = ac.n_main * 4
-            _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_used.data_ptr() + off, ac.flat_m.data_ptr() + off,
-                                         ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
-                                         0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, stream))
-            ac.refresh_shadows(ac.L_ada)
-            self._stats[3] += stats_ad[3]
+            self._adapt_tail(B, world, allreduce)
         if getattr(self, "debug_keep_grad", False):
             self.debug_stats = self._stats.clone()
         self._loss_acc += self._stats
+
+    def _target(self, B):
+        """bf16 [B, 24] copy of the adaptation regression target (deferred tail only)."""
+        t = getattr(self, "_tgt", None)
+        if t is None or t.shape[0] < B:
+            self._tgt = t = torch.zeros(B, 24, dtype=torch.bfloat16, device=self.device)
+        return t
+
+    def _adapt_tail(self, B, world, allreduce, deferred=False):
+        """ppo.py:158-170 after the adaptation forward: regression loss against the encoder latent, backward,
+        Adam step of the adaptation module.  deferred: runs one minibatch later on the side stream (target from
+        the saved copy, statistics into their own accumulator)."""
+        ac, A = self.actor_critic, PPO_Args
+        w = ac._ws
+        P = _lib.ptr
+        stream = _lib.current_stream()
+        ld = lambda k: w[k].shape[1]
+        d = ac.L_ada
+        inv_gb = 1.0 / (B * world)
+        peer = self._peer if allreduce == "peer" else None
+        g_used = self._g_red if peer is not None else ac.flat_grad
+        tail = ac._grad_store[ac.n_total:ac.n_total + 4]
+        stats_ad = self._stats_ad
+        stats_ad.zero_()
+        if deferred:
+            tgt = self._target(B)
+            _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(tgt), tgt.shape[1], 0, B, inv_gb, P(w["dpred"]), P(stats_ad), stream))
+        else:
+            _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(w["Xac"]), ld("Xac"), ac.num_obs, B, inv_gb, P(w["dpred"]),
+                                               P(stats_ad), stream))
+        if ac.use_chain:
+            ac._chain(("adaptation_backward",), chain.adaptation_backward_program).run(B)
+        else:
+            self._dgrad(d[2], w["dpred"], 0, 24, w["dD2"], 0, ld("dD2"), B, aux=w["D2"], ld_aux=ld("D2"))
+            self._dgrad(d[1], w["dD2"], 0, ld("dD2"), w["dD1"], 0, ld("dD1"), B, aux=w["D1"], ld_aux=ld("D1"))
+        self._wgrad(d[2], w["dpred"], 0, 24, w["D2"], 0, ld("D2"), B)
+        self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
+        self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
+        self._wgrad_flush()
+        if peer is not None:
+            tail.copy_(stats_ad)
+            peer.all_reduce(self._g_red, norm_n=0, start=ac.n_main)     # adaptation gradient + statistics only
+            stats_ad.copy_(self._g_red[ac.n_total:ac.n_total + 4])
+        elif allreduce is not None:
+            tail.copy_(stats_ad)
+            allreduce(ac._grad_store[ac.n_main:ac.n_total + 4])
+            stats_ad.copy_(tail)
+        if getattr(self, "debug_keep_grad", False):
+            self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
+        n_ad = ac.n_total - ac.n_main
+        off = ac.n_main * 4
+        _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_used.data_ptr() + off, ac.flat_m.data_ptr() + off,
+                                     ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
+                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, stream))
+        ac.refresh_shadows(ac.L_ada)
+        if deferred:
+            self._loss_acc_ad += stats_ad[3:4]
+        else:
+            self._stats[3] += stats_ad[3]
 
     def update(self):
         """ppo.py:94-178."""
@@ -340,35 +387,49 @@ class PPO:
         # RL_PPO_GRAPH_MULTI=0 to launch eagerly instead)
         multi_ok = world == 1 or os.environ.get("RL_PPO_GRAPH_MULTI", "1") != "0"
         use_graph = self.use_cuda_graph and multi_ok and not getattr(self, "debug_keep_grad", False)
-        if use_graph and (self._graph is None or self._graph_B != mb):
+        # Deferred adaptation tail (minibatch_step docstring): single GPU, graph mode.  Two graphs: the first minibatch
+        # of an update has no pending tail, every later one runs its predecessor's tail on the side branch.
+        defer = (use_graph and allreduce is None and self.overlap_adaptation and self.actor_critic.use_chain and
+                 A.num_adaptation_module_substeps == 1 and os.environ.get("RL_PPO_DEFER_TAIL", "1") != "0")
+        if use_graph and (self._graph is None or self._graph_B != mb or self._graph_defer != defer):
             self.actor_critic.workspace(mb, backward=True)        # allocate outside the capture
             self.actor_critic.prepare_update_chains()
+            self._target(mb)
             self._idx_buf = torch.zeros(mb, dtype=torch.long, device=self.device)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            snap = [t.clone() for t in (self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
-                                        self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc)]
+            state = (self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
+                     self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc, self._loss_acc_ad)
+            snap = [t.clone() for t in state]
             # capture on a high-priority stream: kernel nodes keep their stream's priority, so the policy path's CTAs
-            # are placed before those of the side branch (adaptation forward), which only fills what is left
+            # are placed before those of the side branch (adaptation module), which only fills what is left
             kw = {}
             if self.overlap_adaptation and os.environ.get("RL_PPO_PRIO", "1") != "0":
                 if self._hp is None:
                     self._hp = torch.cuda.Stream(device=self.device, priority=-1)
                 kw["stream"] = self._hp
-            with torch.cuda.graph(g, **kw):
-                self.minibatch_step(self._idx_buf, world, allreduce)
+            graphs = []
+            for pending in ((False, True) if defer else (False,)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, **kw):
+                    self.minibatch_step(self._idx_buf, world, allreduce, defer_tail=defer, pending_tail=pending)
+                graphs.append(g)
             # capture does not execute, but keep the state bit-identical in any case
-            for t, s0 in zip((self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
-                              self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc), snap):
+            for t, s0 in zip(state, snap):
                 t.copy_(s0)
-            self._graph, self._graph_B = g, mb
+            self._graph, self._graph_rest, self._graph_B, self._graph_defer = graphs[0], graphs[-1], mb, defer
+        self._loss_acc_ad.zero_()
+        first = True
         for _ in range(A.num_learning_epochs):
             for i in range(A.num_mini_batches):
                 if use_graph:
                     self._idx_buf.copy_(indices[i * mb:(i + 1) * mb])
-                    self._graph.replay()
+                    (self._graph if first else self._graph_rest).replay()
+                    first = False
                 else:
                     self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
+        if use_graph and defer:
+            self._adapt_tail(mb, world, None, deferred=True)       # the last minibatch's adaptation update
+            self._loss_acc[3:4] += self._loss_acc_ad
         n_upd = A.num_learning_epochs * A.num_mini_batches
         acc = (self._loss_acc / (mb * world)).tolist()          # the only device->host read of the update
         self.learning_rate = float(self._ctrl[0])
