@@ -65,7 +65,6 @@ class PPO:
         self.overlap_adaptation = os.environ.get("RL_PPO_OVERLAP", "1") != "0"
         self._side = self._ev_fork = self._ev_join = self._hp = None
         self._graph_defer = self._graph_rest = None
-        self._tail_allreduce = None
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -215,7 +214,7 @@ class PPO:
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fork)
                 if pending_tail:
-                    self._adapt_tail(B, world, self._tail_allreduce, deferred=True)
+                    self._adapt_tail(B, world, None, deferred=True)
                 _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
                                                            ld("Xh"), _lib.current_stream()))
                 ac.forward_adaptation(B, save=True)
@@ -402,7 +401,6 @@ class PPO:
         # (a 2-GPU trial of the deferred tail also hung in the small-batch test) - there the tail stays serial.
         defer = (use_graph and allreduce is None and self.overlap_adaptation and self.actor_critic.use_chain and
                  A.num_adaptation_module_substeps == 1 and os.environ.get("RL_PPO_DEFER_TAIL", "1") != "0")
-        self._tail_allreduce = None
         if use_graph and (self._graph is None or self._graph_B != mb or self._graph_defer != defer):
             self.actor_critic.workspace(mb, backward=True)        # allocate outside the capture
             self.actor_critic.prepare_update_chains()
@@ -440,7 +438,7 @@ class PPO:
                 else:
                     self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
         if use_graph and defer:
-            self._adapt_tail(mb, world, self._tail_allreduce, deferred=True)       # the last minibatch's adaptation update
+            self._adapt_tail(mb, world, None, deferred=True)       # the last minibatch's adaptation update
             self._loss_acc[3:4] += self._loss_acc_ad
         n_upd = A.num_learning_epochs * A.num_mini_batches
         acc = (self._loss_acc / (mb * world)).tolist()          # the only device->host read of the update

@@ -137,3 +137,34 @@ def test_packed_program_layout():
     for i, o in enumerate(prog.loads):
         assert L[i].expect_bytes == o["bytes"] and L[i].smem_off == o["smem_off"]
     assert sum(1 for o in prog.epis if o["store_tensor"] != chain.NONE) == sum(prog.n_stores)
+
+
+@pytest.mark.parametrize("a_depth,n_ctas", [(2, 1), (4, 2), (6, 1)])
+def test_adaptation_forward_ring_depths(a_depth, n_ctas):
+    """Two TMA rings (input boxes `a_depth` deep, weights in what is left): every split of the ring units must run
+    to completion and give the same numbers - the prefetch distance is a performance knob, not a correctness one."""
+    T = ck.make_tensors(ROWS, 11)
+    ref = ck.ref_adaptation(T)
+    prog = chain.adaptation_forward_program(T, a_depth=a_depth)
+    assert set(prog.rings) == {"w", "x"} and prog.rings["x"]["n"] == a_depth and prog.n_units <= 14
+    chain.Emulator(prog, ROWS, n_ctas=n_ctas, seed=a_depth).run()
+    _close(T, ref, ("D1", "D2", "pred"))
+
+
+def test_emulator_detects_load_order_deadlock():
+    """The LOAD role issues in program order.  A load that waits for a ring stage whose release depends on a LATER
+    load can never be issued: the emulator must report the deadlock instead of spinning.  Built by emitting one
+    more input box ahead than the input ring has stages."""
+    T = ck.make_tensors(ROWS, 0)
+    p = chain.ChainProgram(n_pool=2, n_stages=0, n_inputs=0, regions={"BIG": (0, 256)}, name="bad_prefetch",
+                           rings=[("w", 1, 2), ("x", 2, 1)])
+    p.params = T["params"]
+    tX, tW = p.tensor(T["Xh"], 128), p.tensor(T["Wd1"], 256)
+    acc = p.acc("BIG")
+    xs = [p.load_stage(tX, col0=64 * j, row0=0, tile_rows=True, ring="x") for j in range(3)]     # 3 boxes, 2 stages
+    for j in range(3):
+        b = p.load_stage(tW, col0=64 * j, row0=0, ring="w")       # never reached: the third x load blocks the role
+        p.mma(xs[j], b, n=256, acc=acc, k_steps=4, accumulate=j > 0, acc_last=(j == 2), a_release=True)
+    p.epi_box(acc, 0, chain.EPI_BIAS_ELU, bias_off=T["b_d1"], last=True, has_reader=False)
+    with pytest.raises(chain.ChainHazard, match="deadlock"):
+        chain.Emulator(p, 128, seed=0).run()
