@@ -63,15 +63,18 @@ class AccUse:
 class ChainProgram:
     """Builder + container of one chain program."""
 
-    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1, rings=None):
+    def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1, rings=None,
+                 n_workers=2):
         """Shared-memory units: [inputs | pool | ring stages]; `regions`: {name: (first tmem column, width)};
         `region_worker`: regions whose accumulator uses are read by ONE epilogue op -> the worker that owns
         them (a waiter must see every phase of a barrier, so such a region cannot change hands); the other
-        regions are read by both workers, chunk c by worker c % 2.
+        regions are read by all workers, chunk c by worker c % n_workers.
+        `n_workers`: epilogue warp groups.  The kernel (csrc/chain.cu) has two; programs for three can be built,
+        emulated and timed (profiles/chain_model.py) - rl_chain_create rejects them until the kernel grows a third.
         `rings`: [(name, n_stages, units per stage)] - several independent TMA rings (default: one ring "main" of
         n_stages x stage_units); the LOAD role still issues every load in program order."""
         self.name = name
-        self.n_inputs, self.n_pool = n_inputs, n_pool
+        self.n_inputs, self.n_pool, self.n_workers = n_inputs, n_pool, n_workers
         rings = rings or [("main", n_stages, stage_units)]
         self.n_stages, self.stage_units = rings[0][1], rings[0][2]      # of the default (first) ring
         self.tensors = []                # (torch tensor 2-D view, box_rows)
@@ -107,12 +110,13 @@ class ChainProgram:
         self.acc_uses = {r: 0 for r in regions}
         self.acc_open = {r: None for r in regions}
         self.input_full, self.input_free, self.input_loads = {}, {}, {}
-        self.waited = {"load": set(), "mma": set(), "epi0": set(), "epi1": set()}
+        self.waited = {"load": set(), "mma": set()}
+        self.waited.update({"epi%d" % k: set() for k in range(n_workers)})
         # two epilogue workers (4 warps each) take the EPI ops alternately; a pool unit always belongs to the
         # worker of its parity, so the TMA-store bookkeeping (one bulk group per store, committed by the
         # worker's first thread) stays within one thread
         self.region_worker = dict(region_worker or {"C0": 0, "C1": 1})
-        self.n_stores = [0, 0]
+        self.n_stores = [0] * n_workers
         self.unit_last_store = {}        # unit -> store index within the tile (of the unit's worker)
         self.acc_participants = {r: set() for r in regions}
         self._finalized = False
@@ -187,7 +191,7 @@ class ChainProgram:
 
     def worker_for(self, acc, col):
         """Epilogue worker that reads accumulator columns [col, col + 64) of this use."""
-        return self.region_worker[acc.region] if acc.region in self.region_worker else (col // 64) % 2
+        return self.region_worker[acc.region] if acc.region in self.region_worker else (col // 64) % self.n_workers
 
     # ---- tensor-memory accumulators -----------------------------------------------------------------
     def acc(self, region):
@@ -254,7 +258,7 @@ class ChainProgram:
         for probe in range(self.n_pool):
             i = (self.pool_pos + probe) % self.n_pool
             prev = self.pool_last[i]
-            if i % 2 == w and (prev is None or prev.released or not prev.has_reader):
+            if i % self.n_workers == w and (prev is None or prev.released or not prev.has_reader):
                 break
         else:
             raise AssertionError("%s: every pool unit of worker %d holds a live box" % (self.name, w))
@@ -482,8 +486,9 @@ class Emulator:
         tmem_unread = torch.zeros(512, dtype=torch.bool)   # written by an MMA, not yet loaded by an epilogue op
         mma_queue = []                       # issued MMAs / commits, executed in order by the tensor pipe
         loads_inflight = []
-        stores_inflight = [[], []]           # per epilogue worker: bulk groups complete in order
-        store_groups = [{"issued": 0, "read": 0}, {"issued": 0, "read": 0}]
+        NW = p.n_workers
+        stores_inflight = [[] for _ in range(NW)]           # per epilogue worker: bulk groups complete in order
+        store_groups = [{"issued": 0, "read": 0} for _ in range(NW)]
         state = {"done": 0}
 
         def spec_wait(w, it, role):
@@ -638,20 +643,20 @@ class Emulator:
             unit_readers[u] -= 1
             store_groups[o["worker"]]["read"] += 1
 
-        roles = [load_role(), mma_role(), epi_role(0), epi_role(1)]
-        alive = [True, True, True, True]
-        NR = 4
+        roles = [load_role(), mma_role()] + [epi_role(k) for k in range(NW)]
+        NR = 2 + NW
+        alive = [True] * NR
         blocked_rounds = 0
         # adversarial speeds: every agent (3 roles, TMA loads, tensor pipe, TMA stores) gets its own firing
         # probability per round, re-drawn now and then, so slow-consumer / slow-producer races are exercised
-        speeds = [1.0] * (NR + 4)
+        speeds = [1.0] * (NR + 2 + NW)
         rounds = 0
         while True:
             progressed = False
             if rounds % 400 == 0:
-                speeds = [self.rng.choice((0.03, 0.3, 1.0)) for _ in range(NR + 4)]
+                speeds = [self.rng.choice((0.03, 0.3, 1.0)) for _ in range(NR + 2 + NW)]
             rounds += 1
-            order = list(range(NR + 4))
+            order = list(range(NR + 2 + NW))
             self.rng.shuffle(order)
             for a in order:
                 if self.rng.random() > speeds[a]:
@@ -659,7 +664,7 @@ class Emulator:
                 if a < NR:
                     if not alive[a]:
                         continue
-                    before = (len(loads_inflight), len(mma_queue), len(stores_inflight[0]), len(stores_inflight[1]),
+                    before = (len(loads_inflight), len(mma_queue), tuple(len(x) for x in stores_inflight),
                               tuple(b.n for b in bars), tuple(b.pending for b in bars))
                     try:
                         next(roles[a])
@@ -667,7 +672,7 @@ class Emulator:
                         alive[a] = False
                         progressed = True
                         continue
-                    after = (len(loads_inflight), len(mma_queue), len(stores_inflight[0]), len(stores_inflight[1]),
+                    after = (len(loads_inflight), len(mma_queue), tuple(len(x) for x in stores_inflight),
                              tuple(b.n for b in bars), tuple(b.pending for b in bars))
                     progressed |= before != after
                 elif a == NR and loads_inflight:
@@ -684,7 +689,7 @@ class Emulator:
                 elif a >= NR + 2 and stores_inflight[a - NR - 2]:
                     do_store(*stores_inflight[a - NR - 2].pop(0))     # bulk groups complete in order
                     progressed = True
-            inflight = loads_inflight or mma_queue or stores_inflight[0] or stores_inflight[1]
+            inflight = loads_inflight or mma_queue or any(stores_inflight)
             if not any(alive) and not inflight:
                 break
             if progressed:
@@ -734,12 +739,22 @@ def _round16(n):
     return (n + 15) // 16 * 16
 
 
-def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=3, stage_units=2):
+REGIONS3 = {"C0": (0, 64), "C1": (64, 64), "C2": (128, 64), "BIG": (192, 256), "MID": (0, 128)}
+
+
+def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=3, stage_units=2, n_workers=2):
     """encoder(priv) -> latent merged into the [obs | latent] box -> actor mean / critic value
     (actor_critic.py:124-173 `act` / `evaluate` on one batch; ppo.py:102-107 inside the update).
     T: tensors + parameter offsets (see ActorCritic._chain_tensors).  save: also store every hidden
-    activation (the backward needs them).  trunk=False: only refresh the latent slot of Xac."""
-    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=REGIONS, name="teacher_forward", stage_units=stage_units)
+    activation (the backward needs them).  trunk=False: only refresh the latent slot of Xac.
+
+    n_workers=3 (study for the next kernel revision; not runnable on the two-worker kernel): three 64-column chunk
+    accumulators, one per epilogue worker, and the 128-column layer accumulator MID shares the columns of C0 and C1 -
+    safe by program order like SB / D2 in the backward (MID is written only after the MMAs that consumed every
+    chunk box of the stream, and a stream starts only after the MMAs that consumed MID's boxes)."""
+    nw = n_workers
+    p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=REGIONS if nw == 2 else REGIONS3, name="teacher_forward",
+                     stage_units=stage_units, n_workers=nw, region_worker={"C%d" % k: k for k in range(nw)})
     p.params = T["params"]
     wbox = lambda w: min(128 * stage_units, _round16(w.shape[0]))      # weight box rows
     tXp, tXac = p.tensor(T["Xp"], 128), p.tensor(T["Xac"], 128)
@@ -788,7 +803,7 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
         chunk_box = [None] * nch
 
         def l1(j):
-            a1 = p.acc("C%d" % (j % 2))
+            a1 = p.acc("C%d" % (j % nw))
             s = p.load_stage(tWcat, col0=0, row0=off + 64 * j)
             p.mma(xacm, s, n=64, acc=a1, k_steps=4, accumulate=False, acc_last=True,
                   a_release=(ni == len(nets) - 1 and j == nch - 1))
@@ -810,7 +825,9 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
         acc3 = p.acc("MID")
         _dense(p, a2, tW3, W3.shape[0], acc3)
         a3 = _boxes(p, acc3, W3.shape[0], EPI_BIAS_ELU, b3, t3)
-        acc4 = p.acc("C%d" % (ni % 2))
+        # (three workers: MID overlaps C0 / C1, and the head's first MMA waits for the first MID box only - its
+        # accumulator must lie outside MID)
+        acc4 = p.acc("C%d" % (ni % 2) if nw == 2 else "C2")
         _dense(p, a3, tW4, _round16(n_out), acc4)
         p.output(out_id, T["mean"] if tag == "a" else T["value"])
         p.epi_out(acc4, 0, n_out, b4, out_id)

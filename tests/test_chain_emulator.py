@@ -168,3 +168,40 @@ def test_emulator_detects_load_order_deadlock():
     p.epi_box(acc, 0, chain.EPI_BIAS_ELU, bias_off=T["b_d1"], last=True, has_reader=False)
     with pytest.raises(chain.ChainHazard, match="deadlock"):
         chain.Emulator(p, 128, seed=0).run()
+
+
+def test_timing_model_tracks_measured_periods():
+    """profiles/chain_model.py (the cycle model used to explore schedules without a GPU) must run every shipped
+    program to completion and stay within 20 % of the per-tile periods measured on the B200 (196608 rows)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles"))
+    import chain_model as cm
+    T = ck.make_tensors(512, 0)
+    for prog in (chain.teacher_forward_program(T), chain.trunk_backward_program(T), chain.adaptation_forward_program(T),
+                 chain.adaptation_backward_program(T)):
+        m = cm.Model(prog, tiles=5).run()
+        r = m.report()
+        assert all(e > 0 for e in m.tile_end), prog.name                  # every tile finished: no modelled deadlock
+        assert abs(r["period"] / cm.MEASURED[prog.name] - 1) < 0.20, (prog.name, r["period"], cm.MEASURED[prog.name])
+
+
+def test_three_worker_teacher_forward_study():
+    """The builder / emulator / timing model take programs for three epilogue workers (the kernel has two: this is
+    the study that decided NOT to build the third).  The program must be hazard free - its 128-column layer
+    accumulator shares the columns of two chunk accumulators - and numerically right; the model says what it buys."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles"))
+    import chain_model as cm
+    for seed, n_ctas in ((0, 1), (1, 2)):
+        T = ck.make_tensors(ROWS, seed)
+        ref = ck.ref_teacher(T)
+        prog = chain.teacher_forward_program(T, n_workers=3)
+        assert {o["worker"] for o in prog.epis} == {0, 1, 2}
+        chain.Emulator(prog, ROWS, n_ctas=n_ctas, seed=seed).run()
+        _close(T, ref, ("H1", "H2", "Xac", "Y1", "A2", "A3", "C2", "C3", "mean", "value"))
+    T = ck.make_tensors(512, 0)
+    two = cm.Model(chain.teacher_forward_program(T), tiles=5).run().report()["period"]
+    three = cm.Model(chain.teacher_forward_program(T, n_workers=3), tiles=5).run().report()["period"]
+    assert 0.9 < three / two < 1.02, (two, three)          # a few percent at most: the chain is latency bound, not worker bound
