@@ -205,3 +205,7 @@ def test_three_worker_teacher_forward_study():
     two = cm.Model(chain.teacher_forward_program(T), tiles=5).run().report()["period"]
     three = cm.Model(chain.teacher_forward_program(T, n_workers=3), tiles=5).run().report()["period"]
     assert 0.9 < three / two < 1.02, (two, three)          # a few percent at most: the chain is latency bound, not worker bound
+    # the two-worker kernel must refuse the program loudly (argument validation precedes every CUDA call)
+    from rapid_locomotion_rl_b200 import _lib
+    with pytest.raises(_lib.RlError, match="worker"):
+        chain.teacher_forward_program(T, n_workers=3).compile()
