@@ -413,7 +413,7 @@ def run_ours(args):
         "runner": runner,
     }
     if rank == 0 and world == 1:
-        out["cpu_baseline"] = cpu_baseline(sample_envs=4000, steps=10, warmup=2)
+        out["cpu_baseline"] = cpu_baseline(args.envs)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -495,10 +495,46 @@ def runner_bench(n_envs, device, iters=10):
             "ms_per_iteration_eager_rollout": res["eager"] * 1e3}
 
 
+def reference_staged():
+    """True when the unmodified reference is importable here: /root/reference (build container) or the copy staged
+    by oracle/make_ref.py (the GPU box)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
+    import harness
+    return harness.reference_available()
+
+
+def reference_env_arm(envs, steps, warmup, robot="mini_cheetah"):
+    """The UNMODIFIED reference on host cores: HistoryWrapper(VelocityTrackingEasyEnv).step (mini_gym/envs/
+    mini_cheetah/velocity_tracking/velocity_tracking_easy_env.py:42-64, wrappers/history_wrapper.py:18-41, base/
+    legged_robot.py:106-137) driven through the fake-simulator shims on the same synthetic state distribution as
+    our arm.  Returns (env-steps/s, threads, seconds)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
+    import harness
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    env, Cfg = harness.make_reference_env(robot, envs, device="cpu")
+    e = env.env
+    st = synthetic_state(0, envs, e.num_bodies, 12, e.default_dof_pos[0].numpy(), e.feet_indices.tolist(),
+                         e.termination_contact_indices.tolist())
+    T = torch.from_numpy
+    e.all_root_states[:] = T(st["root_states"]); e.all_dof_state[:] = T(st["dof_state"].reshape(-1, 2))
+    e.all_contact_forces[:] = T(st["contact_forces"].reshape(-1, 3))
+    e.commands[:, :3] = torch.rand(envs, 3) * 2 - 1
+    e.episode_length_buf[:] = torch.randint(0, 1001, (envs,))
+    actions = torch.randn(envs, 12)
+    for _ in range(warmup):
+        env.step(actions)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        env.step(actions)
+    dt = time.perf_counter() - t0
+    return envs * steps / dt, torch.get_num_threads(), dt
+
+
 def cpu_env_arm(envs, steps, warmup, threads=None, device="cpu"):
-    """The reference's algorithm for the path on host cores: oracle/env_oracle.py (a torch-CPU
-    restatement pinned bit-exactly to the reference; the reference itself is Python and cannot travel
-    to the GPU box).  Returns (env-steps/s, threads used, seconds)."""
+    """Fallback when the reference is not staged, and the torch-eager-on-GPU leg: oracle/env_oracle.py (a torch
+    restatement pinned bit-exactly to the reference).  Returns (env-steps/s, threads used, seconds)."""
     import numpy as np
     import torch
     import statekit
@@ -529,17 +565,76 @@ def cpu_env_arm(envs, steps, warmup, threads=None, device="cpu"):
     return envs * steps / dt, torch.get_num_threads(), dt
 
 
-def cpu_baseline(sample_envs, steps, warmup, target_s=12.0):
+def reference_ppo_arm(n_envs, T, device, epochs=5, iters=1):
+    """The UNMODIFIED reference learner (mini_gym_learn/ppo/ppo.py:62-178, rollout_storage.py:76-139,
+    actor_critic.py:23-173) on `device` ("cpu": host cores; "cuda:0": torch eager + cuBLAS, the same-box GPU number
+    the fused learner replaces): rollout of synthetic observations through PPO.act / process_env_step, then the timed
+    compute_returns + update.  Returns samples/s and what was run."""
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)
-    _, _, probe = cpu_env_arm(sample_envs, 2, 1)
-    steps = int(min(5000, max(steps, target_s / max(probe / 2, 1e-6))))   # ~10-30 s of CPU work
-    v, cores, secs = cpu_env_arm(sample_envs, steps, warmup)
-    out = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-           "sample": "%d envs x %d steps of the same Mini Cheetah flat step through oracle/env_oracle.py (torch CPU fp32, "
-                     "%.1f s)" % (sample_envs, steps, secs)}
+    sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
+    import harness
+    harness.install()
+    import isaacgym  # noqa: F401  (fake)
+    from mini_gym_learn.ppo import ActorCritic
+    from mini_gym_learn.ppo.ppo import PPO, PPO_Args
+    torch.manual_seed(0)
+    PPO_Args.num_learning_epochs = epochs
+    ac = ActorCritic(42, 18, 630, 12).to(device)
+    ppo = PPO(ac, device=device)
+    ppo.init_storage(n_envs, T, [42], [18], [630], [12])
+    obs = torch.randn(T + 1, n_envs, 42, device=device)
+    priv = torch.rand(T + 1, n_envs, 18, device=device) * 2 - 1
+    hist = torch.randn(n_envs, 630, device=device)
+    bins = torch.zeros(n_envs, device=device)
+    sync = torch.cuda.synchronize if str(device) != "cpu" else (lambda: None)
+    times = []
+    for it in range(iters + (1 if str(device) != "cpu" else 0)):        # the GPU leg gets a warm-up iteration
+        with torch.no_grad():
+            for t in range(T):
+                ppo.act(obs[t], priv[t], hist)
+                ppo.process_env_step(torch.randn(n_envs, device=device) * 0.05, torch.rand(n_envs, device=device) < 0.01,
+                                     {"env_bins": bins})
+        sync()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ppo.compute_returns(obs[T], priv[T])
+        res = ppo.update()
+        sync()
+        times.append(time.perf_counter() - t0)
+    dt = times[-1] if str(device) != "cpu" else sum(times) / len(times)
+    # samples/s of the FULL update (5 epochs): an arm run with fewer epochs is scaled by the epoch count, GAE included
+    full = dt * (5.0 / epochs)
+    return {"value": n_envs * T / full, "unit": "samples/s", "device": str(device), "ms_per_iteration": full * 1e3,
+            "epochs_run": epochs, "threads": torch.get_num_threads(), "envs": n_envs, "steps_per_env": T,
+            "losses": [float(x) for x in res],
+            "what": "unmodified mini_gym_learn PPO.compute_returns + PPO.update (%d of 5 epochs x 4 minibatches timed%s)"
+                    % (epochs, ", scaled to 5" if epochs != 5 else "")}
+
+
+def _subprocess_json(argv, timeout=900):
+    """Runs `python bench.py <argv>` and parses the JSON line it prints (the reference's Cfg / PPO_Args are
+    process-global classes, and its torch thread settings should not leak into our arm)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=timeout)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("no JSON from %s: %s" % (argv, r.stderr[-400:]))
+
+
+def cpu_baseline(envs, target_s=15.0):
+    """The reference arm inside our arm's line: a bounded number of steps of the SAME workload (same env count) through
+    the unmodified reference on the host cores, plus the learner's reference numbers (host cores, and torch eager on the
+    B200) - SURVEY.md 8(d).  Every leg runs in its own process."""
+    import torch
+    try:
+        ref = _subprocess_json(["--impl", "reference", "--envs", str(envs), "--steps", "0", "--target-s", str(target_s)])
+        out = dict(ref["cpu_baseline"])
+    except Exception as exc:
+        out = {"error": str(exc)[:300]}
     if torch.cuda.is_available():
-        # the reference's torch-eager path ON the B200 (the port issues the reference's ~300 small
+        # SURVEY 8(d): the reference's torch-eager algorithm ON the B200 (the port issues the reference's ~300 small
         # ATen kernels per step), as the GPU number the fused kernel replaces
         try:
             vg, _, sg = cpu_env_arm(32768, 30, 5, device="cuda:0")
@@ -550,29 +645,60 @@ def cpu_baseline(sample_envs, steps, warmup, target_s=12.0):
     return out
 
 
+def ppo_reference_block(n_envs):
+    """`ppo.reference`: the unmodified reference learner on identical synthetic rollouts - host cores (1 epoch timed,
+    scaled to 5: an epoch is ~10 s of CPU at 4000 envs) and torch eager on cuda:0 (all 5 epochs)."""
+    out = {}
+    for key, argv in (("cpu", ["--impl", "reference-ppo", "--ppo-envs", str(n_envs), "--ref-device", "cpu", "--ref-epochs", "1"]),
+                      ("torch_eager_gpu", ["--impl", "reference-ppo", "--ppo-envs", str(n_envs), "--ref-device", "cuda:0",
+                                           "--ref-epochs", "5"])):
+        try:
+            out[key] = _subprocess_json(argv)
+        except Exception as exc:
+            out[key] = {"error": str(exc)[:300]}
+    return out
+
+
+def run_reference_ppo(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    import torch
+    if args.ref_device == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    print(json.dumps(reference_ppo_arm(args.ppo_envs, 24, args.ref_device, epochs=args.ref_epochs)))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    # bounded sample per step so that K steps end within a few minutes whatever K the driver picks
-    sample = 4000
-    v1, cores, secs = cpu_env_arm(sample, 1, 1)
-    est = (args.steps + max(3, args.warmup)) * secs
-    while est > 150 and sample > 250:
+    staged = reference_staged()
+    arm = reference_env_arm if staged else cpu_env_arm
+    kind = "reference" if staged else "port"
+    envs = args.envs
+    # one probe step sizes the run: the FULL workload (same env count as our arm) unless K steps of it would not
+    # end within a few minutes - only then is each step a bounded sample of the workload
+    _, _, probe = arm(envs, 1, 1)
+    steps, warm = args.steps, max(3, args.warmup)
+    if steps <= 0:                      # cpu_baseline leg of our arm: ~target_s seconds of CPU work
+        steps, warm = max(5, int(args.target_s / max(probe, 1e-6))), 2
+    sample = envs
+    while (steps + warm) * probe * sample / envs > 240 and sample > 500:
         sample //= 2
-        est /= 2
-    t0 = time.perf_counter()
-    v, cores, secs = cpu_env_arm(sample, args.steps, max(3, args.warmup))
+    v, cores, secs = arm(sample, steps, warm)
+    what = ("unmodified reference HistoryWrapper(VelocityTrackingEasyEnv).step through tests/_ref_shims" if staged else
+            "oracle/env_oracle.py (pinned torch restatement; the reference is not staged here)")
     out = {
         "impl": "reference", "metric": "env_steps_per_s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3,
+        "steps": steps, "warmup": warm, "ms_per_step": secs / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mini_cheetah_flat fused env step, reference algorithm on host cores; each step is a bounded "
-                               "sample of %d envs of the %d-env workload" % (sample, args.envs), "envs_per_gpu": args.envs},
-        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d envs x %d steps, oracle/env_oracle.py (torch CPU fp32)" % (sample, args.steps)},
+        "config": {"workload": "mini_cheetah_flat env step (PD torques + terminations + 12 reward terms + obs/noise/clip + state "
+                               "+ observation history), %d envs per step on host cores" % sample,
+                   "envs_per_gpu": envs, "same_config": sample == envs},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind,
+                         "sample": "%d envs x %d steps, %s (torch CPU fp32, %.1f s)" % (sample, steps, what, secs)},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -584,7 +710,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-ppo"])
+    ap.add_argument("--target-s", type=float, default=15.0, help="reference arm with --steps 0: seconds of CPU work")
+    ap.add_argument("--ref-device", default="cpu", help="--impl reference-ppo: device of the reference learner")
+    ap.add_argument("--ref-epochs", type=int, default=1, help="--impl reference-ppo: epochs timed (scaled to 5)")
     ap.add_argument("--envs", type=int, default=32768, help="envs per GPU")
     ap.add_argument("--quick", action="store_true", help="skip the extra sizes and the PPO metric")
     ap.add_argument("--only-ppo", action="store_true", help="development aid: print only the PPO metric object")
@@ -592,6 +721,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-ppo":
+        run_reference_ppo(args)
     else:
         run_ours(args)
 

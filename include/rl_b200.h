@@ -236,6 +236,10 @@ typedef struct RlEnvBuffers {
  * (entry, SoA loads issued, staged rows landed, phase 1 start / end, barrier, outputs written, barrier,
  * stores issued); out_host16 may be NULL */
 int rl_debug_env_trace(int32_t enable, uint64_t* out_host16);
+/* testing aid: selects the kernel behind rl_env_step_fused / rl_env_post_physics for the shipped configuration on
+ * packed state blocks: 1 = env_step_rows.cu (all tile traffic on TMA; the default), 0 = env_step_quad.cu, -1 = back to
+ * the default (environment variable RL_ENV_ROWS).  Returns the previous setting.  Both kernels produce identical bits. */
+int rl_debug_env_rows(int32_t mode);
 const char* rl_last_error(void);
 const char* rl_version(void);
 /* sizeof(struct <name>) as compiled into the library (-1 for an unknown name): lets a
@@ -538,11 +542,12 @@ int rl_cast_bf16(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, in
  * with the analytic gradients w.r.t. the network outputs written as bf16 GEMM operands:
  * dmean [B,16], dvalue [B,8], dpred [B,24]; dstd[12] and stats[4] (sum surrogate, sum value loss,
  * sum kl, sum adaptation squared error; double) are accumulated atomically.  inv_global_B =
- * 1 / (B * world_size). */
+ * 1 / (B * world_size).  kl_slot (optional): an fp32 word that also receives the KL sum - with several GPUs it is
+ * the word behind the flat gradient, so the KL that drives the learning rate travels in the gradient all-reduce. */
 int rl_ppo_loss(const float* mean, const float* value, const float* pred, const void* Xac, int32_t ldac,
                 int32_t lat_off, const float* Lrow, const float* std, int32_t B, float clip, float value_coef,
                 float entropy_coef, int32_t use_clipped_value, float inv_global_B, void* dmean, void* dvalue,
-                void* dpred, float* dstd, double* stats, void* stream);
+                void* dpred, float* dstd, double* stats, float* kl_slot, void* stream);
 /* ppo.py:157-164 alone: mse(adaptation_module(hist), encoder(priv).detach()) and its gradient dpred
  * [B,24] bf16; adds the squared error to stats[3].  Called after the policy optimiser step, as the
  * reference computes the target with the already updated encoder. */
@@ -550,12 +555,16 @@ int rl_adapt_loss(const float* pred, const void* Xac, int32_t ldac, int32_t lat_
                   float inv_global_B, void* dpred, double* stats, void* stream);
 /* ppo.py:116-124 + :149: gradient 2-norm over `n` floats -> clip coefficient; kl mean -> adaptive
  * learning rate, all on the device.  ctrl[0] = lr (in/out), ctrl[1] = clip coefficient, ctrl[2] = kl.
- * workspace: 16 zeroed bytes. */
-int rl_grad_finalize(const float* grad, int64_t n, const double* stats, float* ctrl, void* workspace,
-                     double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, void* stream);
+ * workspace: 16 zeroed bytes.  kl_slot (optional): the KL sum is read from this fp32 word (the all-reduced one)
+ * instead of stats[2].  loss_acc (optional, double[4]): stats[0..2] are added to loss_acc[0..2] and zeroed
+ * (kl_slot too) - the per-update loss bookkeeping of ppo.py:152-153 without extra launches. */
+int rl_grad_finalize(const float* grad, int64_t n, double* stats, float* ctrl, void* workspace,
+                     double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, double* loss_acc,
+                     float* kl_slot, void* stream);
 /* same, from an already reduced squared gradient norm (device double) */
-int rl_grad_finalize_from_norm(const double* norm2, const double* stats, float* ctrl, double global_B,
-                               float desired_kl, float max_grad_norm, int32_t adaptive, void* stream);
+int rl_grad_finalize_from_norm(const double* norm2, double* stats, float* ctrl, double global_B,
+                               float desired_kl, float max_grad_norm, int32_t adaptive, double* loss_acc, float* kl_slot,
+                               void* stream);
 
 /* ---- multi-GPU: gradient all-reduce over NVLink peer memory, fused with the gradient-norm reduction and
  * zero_grad (the sum of the env shards' gradients that precedes clip_grad_norm_ / optimizer.step,

@@ -93,6 +93,7 @@ SIGNATURES = {
     "rl_version": (C.c_char_p, []),
     "rl_sizeof": (C.c_int64, [C.c_char_p]),
     "rl_debug_env_trace": (C.c_int, [C.c_int32, _P]),
+    "rl_debug_env_rows": (C.c_int, [C.c_int32]),
     "rl_env_torques": (C.c_int, [_P, _P, _P]),
     "rl_env_post_physics": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "rl_env_step_fused": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
@@ -110,13 +111,13 @@ SIGNATURES = {
     "rl_ppo_gather_history": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "rl_cast_bf16": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_ppo_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
-                              C.c_int32, C.c_float, _P, _P, _P, _P, _P, _P]),
+                              C.c_int32, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "rl_adapt_loss": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
-    "rl_grad_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P]),
+    "rl_grad_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P, _P, _P]),
     "rl_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
                           C.c_float, _P, _P]),
     "rl_gemm_init": (C.c_int, []),
-    "rl_grad_finalize_from_norm": (C.c_int, [_P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P]),
+    "rl_grad_finalize_from_norm": (C.c_int, [_P, _P, _P, C.c_double, C.c_float, C.c_float, C.c_int32, _P, _P, _P]),
     "rl_enable_peer_access": (C.c_int, [C.c_int32]),
     "rl_peer_allreduce": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_uint32, _P]),
     "rl_wgrad_grouped": (C.c_int, [_P, C.c_int32, _P]),

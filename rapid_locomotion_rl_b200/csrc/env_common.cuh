@@ -112,5 +112,8 @@ __device__ inline float centered_u16(const uint32_t (&r)[4], int k) {
 
 // launcher of the one-warp-per-leg kernel for the standard observation layout (env_step_quad.cu)
 int launch_step_quad(const StepArgs& args, bool fuse_torques, cudaStream_t st);
+// the same step with all tile traffic on TMA, for the shipped configuration on packed state blocks (env_step_rows.cu)
+bool rows_layout_ok(const StepArgs& args);
+int launch_step_rows(const StepArgs& args, bool fuse_torques, cudaStream_t st);
 
 }  // namespace rl

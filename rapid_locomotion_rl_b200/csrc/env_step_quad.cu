@@ -650,6 +650,14 @@ extern "C" int rl_debug_env_trace(int32_t enable, uint64_t* out_host16) {
   return RL_OK;
 }
 namespace rl {
+static int g_rows_mode = -1;
+}
+extern "C" int rl_debug_env_rows(int32_t mode) {
+  const int prev = rl::g_rows_mode;
+  rl::g_rows_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+  return prev;
+}
+namespace rl {
 int launch_step_quad(const StepArgs& args, bool fuse_torques, cudaStream_t st) {
   const size_t smem = quad_smem_bytes(args.cfg);
   static int minb = 0;     // RL_QUAD_MINB=6: 85 registers / 6 CTAs per SM instead of 64 / 8 (tuning knob)
@@ -662,6 +670,11 @@ int launch_step_quad(const StepArgs& args, bool fuse_torques, cudaStream_t st) {
                 c.n_terms == 12 && c.term_mask == STD_TERM_MASK;
   for (int i = 0; is_std && i < 12; ++i) is_std = c.term_id[i] == i;
   if (is_std) {
+    // packed state blocks + full aligned tiles: every byte of the tile moves on the async proxy (env_step_rows.cu)
+    static int rows_env = -1;   // RL_ENV_ROWS=0 keeps the kernel below
+    if (rows_env < 0) { const char* e = getenv("RL_ENV_ROWS"); rows_env = (e && atoi(e) == 0) ? 0 : 1; }
+    const int rows_on = g_rows_mode < 0 ? rows_env : g_rows_mode;
+    if (rows_on && rows_layout_ok(args)) return launch_step_rows(args, fuse_torques, st);
     // small grids (<= 4 CTAs per SM) are pure latency: 6 CTAs / SM (80 registers, no spills) wins; otherwise
     // 7 CTAs / SM (72 registers; 7 x 148 = 1036 CTAs still hold 32768 envs in one wave).  Measured per launch,
     // 6 / 7 / 8 CTAs per SM: 4000 envs 6.9 / 7.4 / 7.9 us, 32768 envs 16.7 / 13.3 / 14.0 us, 262144 envs 81 / 73 / 80 us

@@ -1,0 +1,536 @@
+// Fused env step, shipped training configuration, ALL tile traffic on the async (TMA) proxy.
+//
+// Same arithmetic and warp roles as env_step_quad.cu (reference: mini_gym/envs/base/legged_robot.py
+// :106-417, :653-688, :1506-1646) - what changes is how the bytes move.  The quad kernel stages only
+// the simulator's AoS rows with cp.async.bulk and reads / writes the env-owned SoA state with ~60
+// per-thread LDG / STG (each with 64-bit address arithmetic): ncu showed every CTA of the single wave
+// spending 4.6 us issuing loads before the first one could start computing, then all of them computing
+// with DRAM idle.  Here the env-owned state lives in three packed row blocks
+//     RO [42][N]  Kp, Kd, motor strength factors (12 each), friction, restitution, payload, com (3)
+//     RW [28][N]  last_actions (12), last_dof_vel (12), feet_air_time (4)
+//     WO [27][N]  joint_pos_target (12), base_lin_vel, base_ang_vel, projected_gravity (3 each), last_root_vel (6)
+// (the Python attributes are views of those blocks) and a CTA fetches its 32-env column of every block
+// with ONE 2-D tensor copy each (box = rows x 32 envs, 128 B inner extent), plus the accumulator rows of
+// episode_sums / command_sums it touches and the four AoS row spans: 11 copies issued by one thread in
+// the first ~100 cycles of the CTA, all landing on one mbarrier.  Per SM the TMA unit serves its CTAs in
+// issue order, so the first CTA computes while the rows of the later ones are still in flight, and the
+// kernel body reads shared memory with immediate offsets (no address arithmetic, no LDG latency).  The
+// results leave the same way: 5 tensor stores + 3 bulk stores issued by one thread.
+// Used when: standard configuration (see launch_step_quad's is_std), num_envs % 32 == 0, the state
+// pointers form the packed blocks; otherwise the caller falls back to env_step_quad.cu.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <map>
+#include <tuple>
+
+#include "env_common.cuh"
+
+namespace rl {
+
+int make_tmap_f32_rows(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n, uint32_t box_rows);
+
+namespace rows {
+
+constexpr int QT = 32, QTHREADS = 128;
+enum RoRow { RO_KP = 0, RO_KD = 12, RO_MS = 24, RO_FRIC = 36, RO_REST = 37, RO_PAYLOAD = 38, RO_COM = 39, RO_ROWS = 42 };
+enum RwRow { RW_LA = 0, RW_LDV = 12, RW_AIR = 24, RW_ROWS = 28 };
+enum WoRow { WO_JPT = 0, WO_BLV = 12, WO_BAV = 15, WO_GRAV = 18, WO_LRV = 21, WO_ROWS = 27 };
+constexpr int ES_ROWS = 13;       // term rows 0-11 | total
+constexpr int CS_ROWS = 17;       // term rows 0-11 | lin_vel_raw, ang_vel_raw, lin_vel_residual, ang_vel_residual, ep_timesteps
+enum Part { P_TQ2 = 0, P_ACC2, P_RATE2, P_LIM, NPART };
+constexpr int ROWB = QT * 4;      // bytes of one 32-env row
+
+struct RowsArgs {
+  StepArgs a;
+  CUtensorMap m_ro, m_rw, m_wo, m_es12, m_es1, m_cs12, m_cs5;
+};
+
+__device__ __forceinline__ void tma_load_rows(void* smem_dst, const CUtensorMap* map, int env0, int row0, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(env0), "r"(row0), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_rows(const CUtensorMap* map, const void* smem_src, int env0, int row0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(env0), "r"(row0) : "memory");
+}
+
+// shared-memory map (bytes from the 128 B aligned base); NB = bodies
+struct Lay {
+  int ro, rw, es, cs, wo, root, dof, con, act, tq_in, x, total;
+  __host__ __device__ Lay(int NB, bool fuse) {
+    ro = 0;
+    rw = ro + RO_ROWS * ROWB;
+    es = rw + RW_ROWS * ROWB;
+    cs = es + ES_ROWS * ROWB;
+    wo = cs + CS_ROWS * ROWB;
+    root = wo + WO_ROWS * ROWB;
+    dof = root + QT * 13 * 4;
+    con = dof + QT * 24 * 4;
+    act = con + QT * NB * 3 * 4;
+    tq_in = act + QT * ND * 4;
+    const int in_end = tq_in + (fuse ? 0 : QT * ND * 4);
+    const int out_end = dof + QT * (42 + RL_PRIV_DIM + ND) * 4;
+    x = ((in_end > out_end ? in_end : out_end) + 127) & ~127;
+    total = x + (NPART * 4 + 2 + 12) * ROWB;      // partial sums | collision, air-time reward | r_i
+  }
+};
+
+template <bool FUSE, int MINB>
+__global__ void __launch_bounds__(QTHREADS, MINB)
+env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
+  const RlEnvCfg& cfg = args.a.cfg;
+  const RlEnvBuffers& b = args.a.b;
+  const int N = cfg.num_envs, NB = cfg.num_bodies;
+  const int tile0 = blockIdx.x * QT;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int e = tile0 + lane;
+  constexpr int W = 42;
+  const float co = cfg.clip_obs;
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_root_dirty;
+  const Lay L(NB, FUSE);
+  float* s_ro = reinterpret_cast<float*>(smem_raw + L.ro);
+  float* s_rw = reinterpret_cast<float*>(smem_raw + L.rw);
+  float* s_es = reinterpret_cast<float*>(smem_raw + L.es);
+  float* s_cs = reinterpret_cast<float*>(smem_raw + L.cs);
+  float* s_wo = reinterpret_cast<float*>(smem_raw + L.wo);
+  float* s_root = reinterpret_cast<float*>(smem_raw + L.root);
+  float* s_dof = reinterpret_cast<float*>(smem_raw + L.dof);
+  float* s_con = reinterpret_cast<float*>(smem_raw + L.con);
+  float* s_act = reinterpret_cast<float*>(smem_raw + L.act);
+  float* s_tq_in = reinterpret_cast<float*>(smem_raw + L.tq_in);
+  float* s_obs = s_dof;                                   // output rows re-use the input tile
+  float* s_priv = s_obs + QT * W;
+  float* s_tq = s_priv + QT * RL_PRIV_DIM;
+  float* s_part = reinterpret_cast<float*>(smem_raw + L.x);        // [NPART][4][32]
+  float* s_coll = s_part + NPART * 4 * QT;                // [32]
+  float* s_air = s_coll + QT;                             // [32]
+  float* s_r = s_air + QT;                                // [12][32]
+
+  // Programmatic dependent launch: let the NEXT kernel of the stream start launching its CTAs now (they run their
+  // prologue and park in griddepcontrol.wait until this grid has completed and flushed), and wait for the PREVIOUS
+  // kernel before the first global access.  Hides the launch latency / CTA ramp between consecutive steps; both
+  // instructions are no-ops when the launch does not carry the programmatic-serialization attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    s_root_dirty = 0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ---- one thread issues every copy of the tile ----------------------------------------------------------
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)((RO_ROWS + RW_ROWS + ES_ROWS + CS_ROWS) * ROWB +
+                                      QT * (13 + 24 + NB * 3 + ND + (FUSE ? 0 : ND)) * 4);
+    mbar_expect_tx(&s_bar, bytes);
+    // simulator rows first: phase 1 starts with them
+    bulk_g2s(s_dof, b.dof_state + (size_t)tile0 * 24, QT * 24 * 4, &s_bar);
+    bulk_g2s(s_act, b.actions_in + (size_t)tile0 * ND, QT * ND * 4, &s_bar);
+    tma_load_rows(s_ro, &args.m_ro, tile0, 0, &s_bar);
+    tma_load_rows(s_rw, &args.m_rw, tile0, 0, &s_bar);
+    bulk_g2s(s_root, b.root_states + (size_t)tile0 * 13, QT * 13 * 4, &s_bar);
+    bulk_g2s(s_con, b.contact_forces + (size_t)tile0 * NB * 3, (uint32_t)(QT * NB * 3 * 4), &s_bar);
+    if (!FUSE) bulk_g2s(s_tq_in, b.torques + (size_t)tile0 * ND, QT * ND * 4, &s_bar);
+    tma_load_rows(s_es, &args.m_es12, tile0, 0, &s_bar);
+    tma_load_rows(s_es + 12 * QT, &args.m_es1, tile0, RL_ROW_TOTAL, &s_bar);
+    tma_load_rows(s_cs, &args.m_cs12, tile0, 0, &s_bar);
+    tma_load_rows(s_cs + 12 * QT, &args.m_cs5, tile0, RL_ROW_EXTRAS, &s_bar);
+  }
+  // small per-env scalars with their own dtypes: plain coalesced loads
+  const uint64_t rng_step = args.a.step + (b.step_state ? b.step_state[0] : 0ull);
+  int ep = (int)b.episode_length_buf[e];
+  const float4 cmd = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
+  uint32_t last_contacts = 0;
+  if (w == 1) last_contacts = *reinterpret_cast<const uint32_t*>(b.last_contacts + (size_t)e * 4);
+  __syncthreads();                      // mbarrier initialised
+  {                                     // every staged byte has landed (bounded: a byte-count bug must trap, not hang)
+    uint32_t spins = 0, ok = 0;
+    const uint32_t bar = smem_u32(&s_bar);
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+      if (!ok && ++spins > (1u << 22)) {
+        if (tid == 0) printf("env_step_rows_kernel: tile %d never landed\n", (int)blockIdx.x);
+        __trap();
+      }
+    }
+  }
+  ep += 1;                              // :152
+
+  // ---- teleport (:768-791) by warp 0 ------------------------------------------------------------------------
+  float* root = s_root + lane * 13;
+  bool dirty = false;
+  if (w == 0 && cfg.teleport_robots) {
+    float x = root[0], y = root[1];
+    const float x0 = x, y0 = y;
+    if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
+    if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
+    if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
+    if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
+    if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
+  }
+
+  // =================================== phase 1 ===========================================================
+  float tq[3], oq[3], oqd[3], oa[3], pm[3], jpt[3];
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  float sc6[6];
+  {
+    // ---- all warps: the three DOFs of leg w (:653-688 and the per-DOF reward sums) ----
+    const float2 d0 = *reinterpret_cast<const float2*>(s_dof + lane * 24 + 6 * w);
+    const float2 d1 = *reinterpret_cast<const float2*>(s_dof + lane * 24 + 6 * w + 2);
+    const float2 d2 = *reinterpret_cast<const float2*>(s_dof + lane * 24 + 6 * w + 4);
+    const float q[3] = {d0.x, d1.x, d2.x}, qd[3] = {d0.y, d1.y, d2.y};
+    float part[NPART];
+#pragma unroll
+    for (int t = 0; t < NPART; ++t) part[t] = 0.f;
+    float ms[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int j = 3 * w + k;
+      const float kp = s_ro[(RO_KP + j) * QT + lane], kd = s_ro[(RO_KD + j) * QT + lane];
+      ms[k] = s_ro[(RO_MS + j) * QT + lane];
+      const float la = s_rw[(RW_LA + j) * QT + lane], ldv = s_rw[(RW_LDV + j) * QT + lane];
+      const float a = clampf(s_act[lane * ND + j], -cfg.clip_actions, cfg.clip_actions);   // :112-113
+      float t;
+      if (FUSE) {
+        float as = a * cfg.action_scale;
+        if (k == 0) as *= cfg.hip_scale_reduction;             // dofs 0,3,6,9 (:666)
+        jpt[k] = as + cfg.default_dof_pos[j];
+        t = cfg.p_gains[j] * kp * (jpt[k] - q[k]) - cfg.d_gains[j] * kd * qd[k];
+        t = t * ms[k];
+        t = clampf(t, -cfg.torque_limits[j], cfg.torque_limits[j]);
+      } else {
+        t = s_tq_in[lane * ND + j];
+      }
+      tq[k] = t;
+      part[P_TQ2] += sq(t);
+      part[P_ACC2] += sq((ldv - qd[k]) / cfg.dt);
+      part[P_RATE2] += sq(la - a);
+      {
+        float ov = -fminf(q[k] - cfg.dof_pos_lo[j], 0.f);
+        ov += fmaxf(q[k] - cfg.dof_pos_hi[j], 0.f);
+        part[P_LIM] += ov;
+      }
+      oq[k] = (q[k] - cfg.default_dof_pos[j]) * cfg.obs_scale_dof_pos;
+      oqd[k] = qd[k] * cfg.obs_scale_dof_vel;
+      oa[k] = a;
+      s_rw[(RW_LA + j) * QT + lane] = a;              // :181-182 (row j, this lane: touched by this thread only)
+      s_rw[(RW_LDV + j) * QT + lane] = qd[k];
+    }
+#pragma unroll
+    for (int t = 0; t < NPART; ++t) s_part[(t * 4 + w) * QT + lane] = part[t];
+
+    // DOF-property re-draw (:591-593, :544-560): rare - written straight to global memory
+    if ((ep % cfg.rand_interval) == 0 &&
+        (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor)) {
+      float u3[4];
+      if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[N + e]; u3[2] = b.dr_u[2 * N + e]; }
+      else rng4(args.a.seed, (uint32_t)e, rng_step, RNG_DR, 0, u3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int ix = (3 * w + k) * N + e;
+        if (cfg.randomize_motor_strength) {
+          ms[k] = u3[0] * cfg.motor_strength_lo_span[1] + cfg.motor_strength_lo_span[0];
+          b.motor_strengths[ix] = ms[k];
+        }
+        if (cfg.randomize_Kp_factor) b.Kp_factors[ix] = u3[1] * cfg.Kp_factor_lo_span[1] + cfg.Kp_factor_lo_span[0];
+        if (cfg.randomize_Kd_factor) b.Kd_factors[ix] = u3[2] * cfg.Kd_factor_lo_span[1] + cfg.Kd_factor_lo_span[0];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pm[k] = clampf((ms[k] - cfg.priv_shift[4]) * cfg.priv_scale[4], -co, co);
+
+    // ---- observation noise for this leg's q / qd columns (:392): Philox block w, lanes 0-5 ----
+    {
+      const float* nu = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
+      uint32_t r4[4] = {0u, 0u, 0u, 0u};
+      if (!nu) Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | (uint32_t)w, r4);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int cq = 6 + 3 * w + k, cqd = 18 + 3 * w + k;
+        if (nu) {
+          oq[k] += (2.0f * nu[cq] - 1.0f) * cfg.noise_scale_core[cq];
+          oqd[k] += (2.0f * nu[cqd] - 1.0f) * cfg.noise_scale_core[cqd];
+        } else {
+          oq[k] = __fmaf_rn(2.0f * centered_u16(r4, k), cfg.noise_scale_core[cq], oq[k]);
+          oqd[k] = __fmaf_rn(2.0f * centered_u16(r4, 3 + k), cfg.noise_scale_core[cqd], oqd[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { oq[k] = clampf(oq[k], -co, co); oqd[k] = clampf(oqd[k], -co, co); oa[k] = clampf(oa[k], -co, co); }
+
+    if (w == 0) {
+      // ---- frames (:159-162) ----
+      const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+      const V3 vw = {root[7], root[8], root[9]};
+      const V3 ww = {root[10], root[11], root[12]};
+      const V3 blv = quat_rotate_inverse(qx, qy, qz, qw, vw);
+      const V3 bav = quat_rotate_inverse(qx, qy, qz, qw, ww);
+      const V3 grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+      s_wo[(WO_BLV + 0) * QT + lane] = blv.x; s_wo[(WO_BLV + 1) * QT + lane] = blv.y; s_wo[(WO_BLV + 2) * QT + lane] = blv.z;
+      s_wo[(WO_BAV + 0) * QT + lane] = bav.x; s_wo[(WO_BAV + 1) * QT + lane] = bav.y; s_wo[(WO_BAV + 2) * QT + lane] = bav.z;
+      s_wo[(WO_GRAV + 0) * QT + lane] = grav.x; s_wo[(WO_GRAV + 1) * QT + lane] = grav.y; s_wo[(WO_GRAV + 2) * QT + lane] = grav.z;
+      s_wo[(WO_LRV + 0) * QT + lane] = vw.x; s_wo[(WO_LRV + 1) * QT + lane] = vw.y; s_wo[(WO_LRV + 2) * QT + lane] = vw.z;
+      s_wo[(WO_LRV + 3) * QT + lane] = ww.x; s_wo[(WO_LRV + 4) * QT + lane] = ww.y; s_wo[(WO_LRV + 5) * QT + lane] = ww.z;
+      // gravity observation columns 0-2 with noise: Philox block 4, lanes 0-2
+      g0 = grav.x; g1 = grav.y; g2 = grav.z;
+      const float* nu = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
+      if (nu) {
+        g0 += (2.0f * nu[0] - 1.0f) * cfg.noise_scale_core[0];
+        g1 += (2.0f * nu[1] - 1.0f) * cfg.noise_scale_core[1];
+        g2 += (2.0f * nu[2] - 1.0f) * cfg.noise_scale_core[2];
+      } else {
+        uint32_t r4[4];
+        Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | 4u, r4);
+        g0 = __fmaf_rn(2.0f * centered_u16(r4, 0), cfg.noise_scale_core[0], g0);
+        g1 = __fmaf_rn(2.0f * centered_u16(r4, 1), cfg.noise_scale_core[1], g1);
+        g2 = __fmaf_rn(2.0f * centered_u16(r4, 2), cfg.noise_scale_core[2], g2);
+      }
+      g0 = clampf(g0, -co, co); g1 = clampf(g1, -co, co); g2 = clampf(g2, -co, co);
+    } else if (w == 1) {
+      // ---- contact terms: termination (:190-202), collision, feet air time (:1619-1631) ----
+      const float* con = s_con + lane * NB * 3;
+      bool reset = false;
+#pragma unroll 1
+      for (int k = 0; k < cfg.n_term_bodies; ++k) {
+        const float* f = con + cfg.term_idx[k] * 3;
+        reset |= sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) > 1.0f;
+      }
+      b.reset_buf[e] = reset ? 1 : 0;
+      b.episode_length_buf[e] = (int64_t)ep;
+      float coll = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < cfg.n_pen_bodies; ++k) {
+        const float* f = con + cfg.pen_idx[k] * 3;
+        coll += (sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) > 0.1f) ? 1.f : 0.f;
+      }
+      float r_air = 0.f;
+      uint32_t nc = 0;
+#pragma unroll
+      for (int k = 0; k < RL_NUM_FEET; ++k) {
+        float air = s_rw[(RW_AIR + k) * QT + lane];
+        const bool contact = con[cfg.feet_idx[k] * 3 + 2] > 1.0f;
+        const bool filt = contact || ((last_contacts >> (8 * k)) & 0xffu);
+        nc |= (contact ? 1u : 0u) << (8 * k);
+        const bool first = (air > 0.f) && filt;
+        air += cfg.dt;
+        r_air += (air - 0.5f) * (first ? 1.f : 0.f);
+        air *= filt ? 0.f : 1.f;
+        s_rw[(RW_AIR + k) * QT + lane] = air;
+      }
+      *reinterpret_cast<uint32_t*>(b.last_contacts + (size_t)e * 4) = nc;
+      s_coll[lane] = coll;
+      s_air[lane] = r_air;
+    } else if (w == 2) {
+      // ---- privileged-observation scalars (:398-417) + clip (:136) ----
+      sc6[0] = clampf((s_ro[RO_FRIC * QT + lane] - cfg.priv_shift[0]) * cfg.priv_scale[0], -co, co);
+      sc6[1] = clampf((s_ro[RO_REST * QT + lane] - cfg.priv_shift[1]) * cfg.priv_scale[1], -co, co);
+      sc6[2] = clampf((s_ro[RO_PAYLOAD * QT + lane] - cfg.priv_shift[2]) * cfg.priv_scale[2], -co, co);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sc6[3 + k] = clampf((s_ro[(RO_COM + k) * QT + lane] - cfg.priv_shift[3]) * cfg.priv_scale[3], -co, co);
+    }
+  }
+  __syncthreads();
+
+  // =================================== phase 2 ===========================================================
+  // warp w evaluates terms w, w + 4, w + 8 (reward_names order of the shipped configuration), adds them to its
+  // accumulator rows (in shared memory) and publishes r_i; it also writes its slices of the output rows.
+  {
+    auto psum = [&](int t) {
+      const float* p = s_part + t * 4 * QT + lane;
+      return (p[0] + p[QT]) + (p[2 * QT] + p[3 * QT]);
+    };
+    auto BLV = [&](int i) { return s_wo[(WO_BLV + i) * QT + lane]; };
+    auto BAV = [&](int i) { return s_wo[(WO_BAV + i) * QT + lane]; };
+    auto GRAV = [&](int i) { return s_wo[(WO_GRAV + i) * QT + lane]; };
+    float r0, r1, r2;
+    if (w == 0) {
+      r0 = expf(-(sq(cmd.x - BLV(0)) + sq(cmd.y - BLV(1))) / cfg.tracking_sigma);        // tracking_lin_vel
+      r1 = sq(GRAV(0)) + sq(GRAV(1));                                                     // orientation
+      const float cmd_xy_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y);
+      r2 = s_air[lane] * ((cmd_xy_norm > 0.1f) ? 1.f : 0.f);                              // feet_air_time
+    } else if (w == 1) {
+      r0 = expf(-sq(cmd.z - BAV(2)) / cfg.tracking_sigma_yaw);                            // tracking_ang_vel
+      r1 = psum(P_TQ2);                                                                   // torques
+      r2 = s_coll[lane];                                                                  // collision
+    } else if (w == 2) {
+      r0 = sq(BLV(2));                                                                    // lin_vel_z
+      r1 = psum(P_ACC2);                                                                  // dof_acc
+      r2 = psum(P_RATE2);                                                                 // action_rate
+    } else {
+      r0 = sq(BAV(0)) + sq(BAV(1));                                                       // ang_vel_xy
+      r1 = sq(root[2] - cfg.base_height_target);                                          // base_height
+      r2 = psum(P_LIM);                                                                   // dof_pos_limits
+    }
+    r0 *= cfg.term_scale[w]; r1 *= cfg.term_scale[w + 4]; r2 *= cfg.term_scale[w + 8];
+    s_es[w * QT + lane] += r0; s_cs[w * QT + lane] += r0; s_r[w * QT + lane] = r0;
+    s_es[(w + 4) * QT + lane] += r1; s_cs[(w + 4) * QT + lane] += r1; s_r[(w + 4) * QT + lane] = r1;
+    s_es[(w + 8) * QT + lane] += r2; s_cs[(w + 8) * QT + lane] += r2; s_r[(w + 8) * QT + lane] = r2;
+    if (w == 1) {
+      const float bx = BLV(0), wz = BAV(2);
+      float* x = s_cs + 12 * QT + lane;
+      x[0 * QT] += bx;                      // lin_vel_raw (:336-340)
+      x[1 * QT] += wz;                      // ang_vel_raw
+      x[2 * QT] += sq(bx - cmd.x);          // lin_vel_residual
+      x[3 * QT] += sq(wz - cmd.z);          // ang_vel_residual
+      x[4 * QT] += 1.0f;                    // ep_timesteps
+    }
+    // output rows (re-using the input tile: every thread passed the barrier above)
+    float* obs = s_obs + lane * W;
+    float* priv = s_priv + lane * RL_PRIV_DIM;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      obs[6 + 3 * w + k] = oq[k];
+      obs[18 + 3 * w + k] = oqd[k];
+      obs[30 + 3 * w + k] = oa[k];
+      priv[6 + 3 * w + k] = pm[k];
+      if (FUSE) {
+        s_tq[lane * ND + 3 * w + k] = tq[k];
+        s_wo[(WO_JPT + 3 * w + k) * QT + lane] = jpt[k];
+      }
+    }
+    if (w == 0) {
+      obs[0] = g0; obs[1] = g1; obs[2] = g2;
+      obs[3] = clampf(cmd.x * cfg.commands_scale[0], -co, co);
+      obs[4] = clampf(cmd.y * cfg.commands_scale[1], -co, co);
+      obs[5] = clampf(cmd.z * cfg.commands_scale[2], -co, co);
+    } else if (w == 2) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) priv[k] = sc6[k];
+    }
+  }
+  if (dirty) s_root_dirty = 1;
+  fence_async_smem();
+  __syncthreads();
+
+  // =================================== stores + phase 3 ==================================================
+  if (tid == 0) {
+    const int wo0 = FUSE ? 0 : WO_BLV;           // post_physics leaves joint_pos_target alone
+    tma_store_rows(&args.m_rw, s_rw, tile0, 0);
+    tma_store_rows(&args.m_wo, s_wo + wo0 * QT, tile0, wo0);
+    tma_store_rows(&args.m_es12, s_es, tile0, 0);
+    tma_store_rows(&args.m_cs12, s_cs, tile0, 0);
+    tma_store_rows(&args.m_cs5, s_cs + 12 * QT, tile0, RL_ROW_EXTRAS);
+    bulk_s2g(b.obs_buf + (size_t)tile0 * W, s_obs, QT * W * 4);
+    bulk_s2g(b.privileged_obs_buf + (size_t)tile0 * RL_PRIV_DIM, s_priv, QT * RL_PRIV_DIM * 4);
+    if (FUSE) bulk_s2g(b.torques + (size_t)tile0 * ND, s_tq, QT * ND * 4);
+    if (s_root_dirty) bulk_s2g(b.root_states + (size_t)tile0 * 13, s_root, QT * 13 * 4);
+    bulk_commit();
+  }
+  if (w == 3) {
+    // warp 3 closes compute_reward (:314-340): sum in reward_names order, positive clip, total row
+    float rew = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) rew += s_r[i * QT + lane];
+    rew = fmaxf(rew, 0.f);
+    b.episode_sums[RL_ROW_TOTAL * N + e] = s_es[12 * QT + lane] + rew;
+    b.rew_buf[e] = rew;
+  }
+  if (tid == 0) {
+    bulk_wait_read0();                 // the stores have read their shared-memory source
+    if (b.step_state) {
+      const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
+      if (done == gridDim.x - 1) {
+        b.step_state[1] = 0;
+        atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
+      }
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+struct MapKey {
+  const void* base; uint64_t rows, n; uint32_t box;
+  bool operator<(const MapKey& o) const { return std::tie(base, rows, n, box) < std::tie(o.base, o.rows, o.n, o.box); }
+};
+
+static int cached_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n, uint32_t box) {
+  // descriptors are pure functions of (base, rows, n, box): build once per env instance
+  static thread_local std::map<MapKey, CUtensorMap> cache;
+  const MapKey k{base, rows, n, box};
+  auto it = cache.find(k);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    const int rc = make_tmap_f32_rows(&m, base, rows, n, box);
+    if (rc != RL_OK) return rc;
+    if (cache.size() > 4096) cache.clear();
+    it = cache.emplace(k, m).first;
+  }
+  *out = it->second;
+  return RL_OK;
+}
+
+template <bool FUSE, int MINB>
+static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(env_step_rows_kernel<FUSE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = smem;
+  }
+  static int pdl = -1;       // RL_ENV_PDL=0: plain stream-ordered launch
+  if (pdl < 0) { const char* e = getenv("RL_ENV_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(ra.a.cfg.num_envs / QT); lc.blockDim = dim3(QTHREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&lc, env_step_rows_kernel<FUSE, MINB>, ra);
+  RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "env_step_rows_kernel launch: %s", cudaGetErrorString(err));
+  return check_launch("env_step_rows_kernel");
+}
+
+}  // namespace rows
+
+// true when the env-owned state pointers form the packed RO / RW / WO blocks and every tile is full and aligned
+bool rows_layout_ok(const StepArgs& a) {
+  const RlEnvCfg& c = a.cfg;
+  const RlEnvBuffers& b = a.b;
+  const size_t N = (size_t)c.num_envs;
+  if (c.num_envs % rows::QT != 0 || c.num_obs != 42 || c.num_actions != ND) return false;
+  if (b.Kd_factors != b.Kp_factors + 12 * N || b.motor_strengths != b.Kp_factors + 24 * N ||
+      b.friction_coeffs != b.Kp_factors + 36 * N || b.restitutions != b.Kp_factors + 37 * N ||
+      b.payloads != b.Kp_factors + 38 * N || b.com_displacements != b.Kp_factors + 39 * N)
+    return false;
+  if (b.last_dof_vel != b.last_actions + 12 * N || b.feet_air_time != b.last_actions + 24 * N) return false;
+  if (b.base_lin_vel != b.joint_pos_target + 12 * N || b.base_ang_vel != b.joint_pos_target + 15 * N ||
+      b.projected_gravity != b.joint_pos_target + 18 * N || b.last_root_vel != b.joint_pos_target + 21 * N)
+    return false;
+  const uintptr_t al = (uintptr_t)b.Kp_factors | (uintptr_t)b.last_actions | (uintptr_t)b.joint_pos_target |
+                       (uintptr_t)b.episode_sums | (uintptr_t)b.command_sums | (uintptr_t)b.root_states | (uintptr_t)b.dof_state |
+                       (uintptr_t)b.contact_forces | (uintptr_t)b.actions_in | (uintptr_t)b.torques | (uintptr_t)b.obs_buf |
+                       (uintptr_t)b.privileged_obs_buf;
+  return (al & 15) == 0;
+}
+
+int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
+  using namespace rows;
+  RowsArgs ra;
+  ra.a = a;
+  const RlEnvBuffers& b = a.b;
+  const uint64_t N = (uint64_t)a.cfg.num_envs;
+  int rc;
+  if ((rc = cached_map(&ra.m_ro, b.Kp_factors, RO_ROWS, N, RO_ROWS)) != RL_OK) return rc;
+  if ((rc = cached_map(&ra.m_rw, b.last_actions, RW_ROWS, N, RW_ROWS)) != RL_OK) return rc;
+  if ((rc = cached_map(&ra.m_wo, b.joint_pos_target, WO_ROWS, N, fuse ? WO_ROWS : WO_ROWS - WO_BLV)) != RL_OK) return rc;
+  if ((rc = cached_map(&ra.m_es12, b.episode_sums, RL_EPISODE_ROWS, N, 12)) != RL_OK) return rc;
+  if ((rc = cached_map(&ra.m_es1, b.episode_sums, RL_EPISODE_ROWS, N, 1)) != RL_OK) return rc;
+  if ((rc = cached_map(&ra.m_cs12, b.command_sums, RL_COMMAND_ROWS, N, 12)) != RL_OK) return rc;
+  if ((rc = cached_map(&ra.m_cs5, b.command_sums, RL_COMMAND_ROWS, N, 5)) != RL_OK) return rc;
+  const Lay L(a.cfg.num_bodies, fuse);
+  const size_t smem = (size_t)L.total;
+  // 7 CTAs / SM when the tile fits (13 bodies), else 6
+  static int force = -1;
+  if (force < 0) { const char* m = getenv("RL_ROWS_MINB"); force = m ? atoi(m) : 0; }
+  const bool seven = force == 7 || (force == 0 && 7 * (smem + 1024 + 128) <= 233472);
+  if (seven) return fuse ? launch_inst<true, 7>(ra, smem, st) : launch_inst<false, 7>(ra, smem, st);
+  return fuse ? launch_inst<true, 6>(ra, smem, st) : launch_inst<false, 6>(ra, smem, st);
+}
+
+}  // namespace rl

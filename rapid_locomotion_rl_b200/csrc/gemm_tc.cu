@@ -390,6 +390,26 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   return RL_OK;
 }
 
+}  // namespace tc
+// host: 2-D fp32 tensor map over an SoA block [rows][n] (n = envs, unit stride), box = [box_rows, 32 envs]
+// (128 B inner extent, no swizzle: shared memory receives dense [box_rows][32] rows), zero fill / clipping out of bounds
+int make_tmap_f32_rows(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n, uint32_t box_rows) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  RL_REQUIRE(fn != nullptr, RL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  RL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (n * 4) % 16 == 0 && box_rows >= 1 && box_rows <= 256, RL_ERR_BAD_ARG,
+             "row-block TMA operand must be 16 B aligned with num_envs %% 4 == 0 (n=%llu, box_rows=%u)", (unsigned long long)n, box_rows);
+  cuuint64_t dims[2] = {n, rows};
+  cuuint64_t strides[1] = {n * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RL_REQUIRE(rc == CUDA_SUCCESS, RL_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 rows) failed (%d)", (int)rc);
+  return RL_OK;
+}
+namespace tc {
+
 template <int BN, bool TN, int STAGES>
 static int configure_one() {
   cudaError_t err = cudaFuncSetAttribute(gemm_bf16_kernel<BN, TN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -109,6 +109,7 @@ struct LossArgs {
   __nv_bfloat16* dpred;   // [B,24]
   float* dstd;            // [12] gradient slot of std (atomic)
   double* stats;          // [4]
+  float* kl_slot;         // optional fp32 KL sum (rides in the gradient all-reduce with several GPUs)
 };
 
 __global__ void __launch_bounds__(128)
@@ -205,7 +206,11 @@ ppo_loss_kernel(const __grid_constant__ LossArgs a) {
     for (int d = 0; d < ACT; ++d) sh_std[warp][d] = g_std[d];
   }
   __syncthreads();
-  if (threadIdx.x < 4) atomicAdd(a.stats + threadIdx.x, sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+  if (threadIdx.x < 4) {
+    const double v = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+    atomicAdd(a.stats + threadIdx.x, v);
+    if (threadIdx.x == 2 && a.kl_slot) atomicAdd(a.kl_slot, (float)v);
+  }
   if (threadIdx.x >= 32 && threadIdx.x < 32 + ACT) {
     const int d = threadIdx.x - 32;
     float g = sh_std[0][d] + sh_std[1][d] + sh_std[2][d] + sh_std[3][d];
@@ -248,9 +253,31 @@ adapt_loss_kernel(const float* __restrict__ pred, const __nv_bfloat16* __restric
 // ctrl (float): [0] learning rate (persistent), [1] clip coefficient, [2] kl mean of this minibatch
 struct FinalizeWs { double sumsq; unsigned int ticket; unsigned int pad; };
 
+// the scalar end of both finalize kernels: clip coefficient (clip_grad_norm_), KL mean -> adaptive learning rate (ppo.py:116-124),
+// and - when loss_acc is given - the bookkeeping PPO.update used to do with separate launches: the minibatch's loss
+// sums are added to the per-update accumulators and the per-minibatch statistics (and the fp32 KL slot) are zeroed.
+__device__ __forceinline__ void finalize_tail(double norm, double* stats, float* ctrl, double global_B, float desired_kl,
+                                              float max_norm, int adaptive, double* loss_acc, float* kl_slot) {
+  const float coef = (float)((double)max_norm / (norm + 1e-6));       // clip_grad_norm_
+  ctrl[1] = coef < 1.f ? coef : 1.f;
+  const float kl = kl_slot ? (float)((double)*kl_slot / global_B) : (float)(stats[2] / global_B);
+  ctrl[2] = kl;
+  if (adaptive) {
+    float lr = ctrl[0];
+    if (kl > desired_kl * 2.0f) lr = fmaxf(1e-5f, lr / 1.5f);
+    else if (kl < desired_kl / 2.0f && kl > 0.0f) lr = fminf(1e-2f, lr * 1.5f);
+    ctrl[0] = lr;
+  }
+  if (loss_acc) {
+    loss_acc[0] += stats[0]; loss_acc[1] += stats[1]; loss_acc[2] += stats[2];
+    stats[0] = 0.0; stats[1] = 0.0; stats[2] = 0.0;
+    if (kl_slot) *kl_slot = 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256)
-grad_finalize_kernel(const float* __restrict__ grad, size_t n, const double* __restrict__ stats, float* ctrl,
-                     FinalizeWs* ws, double global_B, float desired_kl, float max_norm, int adaptive) {
+grad_finalize_kernel(const float* __restrict__ grad, size_t n, double* stats, float* ctrl,
+                     FinalizeWs* ws, double global_B, float desired_kl, float max_norm, int adaptive, double* loss_acc, float* kl_slot) {
   double s = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double g = grad[i];
@@ -271,16 +298,7 @@ grad_finalize_kernel(const float* __restrict__ grad, size_t n, const double* __r
   __syncthreads();
   if (last && threadIdx.x == 0) {
     const double norm = sqrt(*((volatile double*)&ws->sumsq));
-    const float coef = (float)((double)max_norm / (norm + 1e-6));       // clip_grad_norm_
-    ctrl[1] = coef < 1.f ? coef : 1.f;
-    const float kl = (float)(stats[2] / global_B);
-    ctrl[2] = kl;
-    if (adaptive) {
-      float lr = ctrl[0];
-      if (kl > desired_kl * 2.0f) lr = fmaxf(1e-5f, lr / 1.5f);
-      else if (kl < desired_kl / 2.0f && kl > 0.0f) lr = fminf(1e-2f, lr * 1.5f);
-      ctrl[0] = lr;
-    }
+    finalize_tail(norm, stats, ctrl, global_B, desired_kl, max_norm, adaptive, loss_acc, kl_slot);
     ws->sumsq = 0.0;
     ws->ticket = 0;
   }
@@ -288,20 +306,11 @@ grad_finalize_kernel(const float* __restrict__ grad, size_t n, const double* __r
 
 // clip coefficient / KL-adaptive learning rate from an already reduced squared gradient norm (multi-GPU: the
 // peer all-reduce kernel computes it while it sums the gradients)
-__global__ void finalize_from_norm_kernel(const double* __restrict__ norm2, const double* __restrict__ stats, float* ctrl,
-                                          double global_B, float desired_kl, float max_norm, int adaptive) {
+__global__ void finalize_from_norm_kernel(const double* __restrict__ norm2, double* stats, float* ctrl,
+                                          double global_B, float desired_kl, float max_norm, int adaptive, double* loss_acc,
+                                          float* kl_slot) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double norm = sqrt(*norm2);
-  const float coef = (float)((double)max_norm / (norm + 1e-6));
-  ctrl[1] = coef < 1.f ? coef : 1.f;
-  const float kl = (float)(stats[2] / global_B);
-  ctrl[2] = kl;
-  if (adaptive) {
-    float lr = ctrl[0];
-    if (kl > desired_kl * 2.0f) lr = fmaxf(1e-5f, lr / 1.5f);
-    else if (kl < desired_kl / 2.0f && kl > 0.0f) lr = fminf(1e-2f, lr * 1.5f);
-    ctrl[0] = lr;
-  }
+  finalize_tail(sqrt(*norm2), stats, ctrl, global_B, desired_kl, max_norm, adaptive, loss_acc, kl_slot);
 }
 
 // ---- fused Adam (torch.optim.Adam, eps 1e-8, no weight decay), gradient scaled by the clip coefficient
@@ -451,7 +460,7 @@ extern "C" int rl_cast_bf16(const float* src, int32_t ld_src, void* dst, int32_t
 extern "C" int rl_ppo_loss(const float* mean, const float* value, const float* pred, const void* Xac, int32_t ldac,
                            int32_t lat_off, const float* Lrow, const float* std, int32_t B, float clip, float value_coef,
                            float entropy_coef, int32_t use_clipped_value, float inv_global_B, void* dmean, void* dvalue,
-                           void* dpred, float* dstd, double* stats, void* stream) {
+                           void* dpred, float* dstd, double* stats, float* kl_slot, void* stream) {
   RL_REQUIRE(mean && value && Lrow && std && dmean && dvalue && dstd && stats && Xac, RL_ERR_BAD_ARG, "rl_ppo_loss: null pointer");
   RL_REQUIRE(B > 0 && (!pred || dpred), RL_ERR_BAD_ARG, "rl_ppo_loss: bad arguments");
   LossArgs a;
@@ -459,7 +468,7 @@ extern "C" int rl_ppo_loss(const float* mean, const float* value, const float* p
   a.Lrow = Lrow; a.std = std; a.B = B; a.clip = clip; a.value_coef = value_coef; a.entropy_coef = entropy_coef;
   a.use_clipped_value = use_clipped_value; a.inv_global_B = inv_global_B;
   a.dmean = (__nv_bfloat16*)dmean; a.dvalue = (__nv_bfloat16*)dvalue; a.dpred = (__nv_bfloat16*)dpred;
-  a.dstd = dstd; a.stats = stats;
+  a.dstd = dstd; a.stats = stats; a.kl_slot = kl_slot;
   ppo_loss_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
   return check_launch("ppo_loss_kernel");
 }
@@ -472,20 +481,21 @@ extern "C" int rl_adapt_loss(const float* pred, const void* Xac, int32_t ldac, i
   return check_launch("adapt_loss_kernel");
 }
 
-extern "C" int rl_grad_finalize(const float* grad, int64_t n, const double* stats, float* ctrl, void* workspace,
-                                double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, void* stream) {
+extern "C" int rl_grad_finalize(const float* grad, int64_t n, double* stats, float* ctrl, void* workspace,
+                                double global_B, float desired_kl, float max_grad_norm, int32_t adaptive, double* loss_acc,
+                                float* kl_slot, void* stream) {
   RL_REQUIRE(grad && stats && ctrl && workspace && n > 0, RL_ERR_BAD_ARG, "rl_grad_finalize: bad arguments");
   int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
   if (blocks > 148 * 2) blocks = 148 * 2;
   grad_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, (size_t)n, stats, ctrl, (FinalizeWs*)workspace,
-                                                               global_B, desired_kl, max_grad_norm, adaptive);
+                                                               global_B, desired_kl, max_grad_norm, adaptive, loss_acc, kl_slot);
   return check_launch("grad_finalize_kernel");
 }
 
-extern "C" int rl_grad_finalize_from_norm(const double* norm2, const double* stats, float* ctrl, double global_B, float desired_kl,
-                                          float max_grad_norm, int32_t adaptive, void* stream) {
+extern "C" int rl_grad_finalize_from_norm(const double* norm2, double* stats, float* ctrl, double global_B, float desired_kl,
+                                          float max_grad_norm, int32_t adaptive, double* loss_acc, float* kl_slot, void* stream) {
   RL_REQUIRE(norm2 && stats && ctrl && global_B > 0, RL_ERR_BAD_ARG, "rl_grad_finalize_from_norm: bad arguments");
-  finalize_from_norm_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(norm2, stats, ctrl, global_B, desired_kl, max_grad_norm, adaptive);
+  finalize_from_norm_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(norm2, stats, ctrl, global_B, desired_kl, max_grad_norm, adaptive, loss_acc, kl_slot);
   return check_launch("finalize_from_norm_kernel");
 }
 

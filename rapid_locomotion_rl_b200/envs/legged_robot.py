@@ -99,24 +99,30 @@ class LeggedRobot:
         self.extras = {}
 
         # ---- persistent state, SoA storage with [N,K] views ----
+        # Three packed row blocks (csrc/env_step_rows.cu): a CTA of the fused step fetches its 32-env column of each
+        # block with one 2-D TMA copy.  RO = read by the step, RW = read and written, WO = written.
         nd = self.num_dof
-        self._last_actions = z(nd, N); self.last_actions = self._last_actions.t()
+        self._ro = z(42, N)       # Kp 0-11 | Kd 12-23 | motor 24-35 | friction 36 | restitution 37 | payload 38 | com 39-41
+        self._rw = z(28, N)       # last_actions 0-11 | last_dof_vel 12-23 | feet_air_time 24-27
+        self._wo = z(27, N)       # joint_pos_target 0-11 | base_lin_vel | base_ang_vel | projected_gravity | last_root_vel 21-26
+        self._last_actions = self._rw[0:12]; self.last_actions = self._last_actions.t()
         self.actions = self.last_actions  # equal after every step (:181)
-        self._last_dof_vel = z(nd, N); self.last_dof_vel = self._last_dof_vel.t()
-        self._last_root_vel = z(6, N); self.last_root_vel = self._last_root_vel.t()
-        self._joint_pos_target = z(nd, N); self.joint_pos_target = self._joint_pos_target.t()
-        self._base_lin_vel = z(3, N); self.base_lin_vel = self._base_lin_vel.t()
-        self._base_ang_vel = z(3, N); self.base_ang_vel = self._base_ang_vel.t()
-        self._projected_gravity = z(3, N); self.projected_gravity = self._projected_gravity.t()
-        self._Kp = torch.ones(nd, N, device=dev); self.Kp_factors = self._Kp.t()
-        self._Kd = torch.ones(nd, N, device=dev); self.Kd_factors = self._Kd.t()
-        self._motor = torch.ones(nd, N, device=dev); self.motor_strengths = self._motor.t()
+        self._last_dof_vel = self._rw[12:24]; self.last_dof_vel = self._last_dof_vel.t()
+        self._feet_air_time = self._rw[24:28]; self.feet_air_time = self._feet_air_time.t()
+        self._joint_pos_target = self._wo[0:12]; self.joint_pos_target = self._joint_pos_target.t()
+        self._base_lin_vel = self._wo[12:15]; self.base_lin_vel = self._base_lin_vel.t()
+        self._base_ang_vel = self._wo[15:18]; self.base_ang_vel = self._base_ang_vel.t()
+        self._projected_gravity = self._wo[18:21]; self.projected_gravity = self._projected_gravity.t()
+        self._last_root_vel = self._wo[21:27]; self.last_root_vel = self._last_root_vel.t()
+        self._ro[0:36].fill_(1.0)
+        self._Kp = self._ro[0:12]; self.Kp_factors = self._Kp.t()
+        self._Kd = self._ro[12:24]; self.Kd_factors = self._Kd.t()
+        self._motor = self._ro[24:36]; self.motor_strengths = self._motor.t()
         self.default_friction, self.default_restitution = robot.default_friction, robot.default_restitution
-        self.friction_coeffs = self.default_friction * torch.ones(N, device=dev)
-        self.restitutions = self.default_restitution * torch.ones(N, device=dev)
-        self.payloads = z(N)
-        self._com = z(3, N); self.com_displacements = self._com.t()
-        self._feet_air_time = z(4, N); self.feet_air_time = self._feet_air_time.t()
+        self.friction_coeffs = self._ro[36]; self.friction_coeffs.fill_(self.default_friction)
+        self.restitutions = self._ro[37]; self.restitutions.fill_(self.default_restitution)
+        self.payloads = self._ro[38]
+        self._com = self._ro[39:42]; self.com_displacements = self._com.t()
         self._last_contacts_u8 = z(N, 4, dtype=torch.uint8)
         self.last_contacts = self._last_contacts_u8.view(torch.bool)
         self.torques = z(N, nd)

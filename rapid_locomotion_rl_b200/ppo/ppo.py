@@ -57,14 +57,13 @@ class PPO:
         self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self._fin_ws = torch.zeros(2, dtype=torch.float64, device=dev)
         self._loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
-        self._loss_acc_ad = torch.zeros(1, dtype=torch.float64, device=dev)    # adaptation statistic of deferred tails
-        self._stats_ad = torch.zeros(4, dtype=torch.float64, device=dev)
         # The adaptation module's forward pass depends only on the gathered history rows and its own weights, not
         # on the policy update: it runs on a side stream (a parallel branch of the captured graph) next to the
         # teacher path, where its CTAs fill the SMs that a 188-tile minibatch leaves idle in its second wave.
         self.overlap_adaptation = os.environ.get("RL_PPO_OVERLAP", "1") != "0"
-        self._side = self._ev_fork = self._ev_join = self._hp = None
-        self._graph_defer = self._graph_rest = None
+        self._side = self._ev_fork = self._ev_join = self._ev_grads = self._ev_loss = self._hp = None
+        self._graph_lag = self._graph_rest = self._graph_reduce = None
+        self._graph_ws_gen = -1
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -93,7 +92,7 @@ class PPO:
         let the PPO object go out of scope) BEFORE torch.distributed.destroy_process_group(), which otherwise waits
         for the communicator the graphs still reference."""
         self._graph = self._graph_rest = None
-        self._graph_B, self._graph_defer = 0, None
+        self._graph_B, self._graph_lag = 0, None
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape,
                      action_shape):
@@ -188,54 +187,62 @@ class PPO:
                  L.out, EPI_DELU_BF16 if aux is not None else EPI_BF16,
                  aux=None if aux is None else ac._p(aux, aux_off), ld_aux=ld_aux)
 
-    def minibatch_step(self, idx, world=1, allreduce=None, defer_tail=False, pending_tail=False):
+    def minibatch_step(self, idx, world=1, allreduce=None, lag=False, pending=False):
         """One PPO minibatch on the rows `idx` (int64 device tensor) of the flattened storage.
 
-        defer_tail: the adaptation module's update of THIS minibatch (loss, dgrad, wgrad, Adam - `_adapt_tail`) is
-        left pending; it runs on the side branch of the NEXT call (pending_tail=True), before that call's adaptation
-        forward, concurrently with the next policy path.  The order of every dependent pair of operations is the
-        reference's (the policy path never reads the adaptation module; its regression target is copied out of the
-        [obs | latent] box before the next minibatch overwrites it), so the results are those of the sequential
-        schedule.  update() flushes the last pending tail."""
+        lag=False: the reference's order inside one call (ppo.py:99-170): policy forward / loss / backward /
+        [all-reduce] / clip + KL-adaptive lr + Adam, then the adaptation module's regression step against the
+        latent of the UPDATED encoder [+ its own all-reduce].
+        lag=True (update()'s CUDA-graph schedule): the adaptation module runs ONE CALL BEHIND on a side stream.
+        Call i's side branch does the adaptation forward / loss / dgrad / wgrad of minibatch i-1 (`pending`; its
+        history rows were gathered by call i-1, its regression target - the refreshed encoder latent - was copied out
+        of the [obs | latent] box by call i-1) and then gathers the history rows of minibatch i; the main branch joins
+        it before the ONE all-reduce of [policy gradient | adaptation gradient | KL sum], then steps both optimisers.
+        Every dependent pair of operations keeps the reference's order (the policy path never reads the adaptation
+        module; the adaptation forward of minibatch i-1 sees the weights left by the step of minibatch i-2), so the
+        parameters are those of the serial schedule.  update() flushes the last pending minibatch."""
         ac, st, A = self.actor_critic, self.storage, PPO_Args
         B = int(idx.numel())
         w = ac.workspace(B, backward=True)
         P = _lib.ptr
-        stream = _lib.current_stream()
         ld = lambda k: w[k].shape[1]
         flat = lambda t: t.flatten(0, 1)
-        hoist = self.overlap_adaptation and ac.use_chain and torch.device(self.device).type == "cuda"
-        if hoist:
-            # side branch: history gather (86 % of the gathered bytes) + adaptation forward
+        assert not lag or (ac.use_chain and A.num_adaptation_module_substeps == 1)
+        debug = getattr(self, "debug_keep_grad", False)
+        acc0 = self._loss_acc.clone() if debug else None
+        peer = self._peer if allreduce == "peer" else None
+        g_used = self._g_red if peer is not None else ac.flat_grad
+        if lag:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
-                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+                self._ev_fork, self._ev_join, self._ev_grads, self._ev_loss = (torch.cuda.Event() for _ in range(4))
             self._ev_fork.record()
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fork)
-                if pending_tail:
-                    self._adapt_tail(B, world, None, deferred=True)
+                if pending:
+                    self._adapt_grads(B, world, lagged=True, loss_event=self._ev_loss)
+                    self._ev_grads.record()
                 _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
                                                            ld("Xh"), _lib.current_stream()))
-                ac.forward_adaptation(B, save=True)
                 self._ev_join.record()
+        stream = _lib.current_stream()
         _lib.check(self._lib.rl_ppo_gather(
             P(flat(st.observations)), P(flat(st.privileged_observations)), P(flat(st.observation_histories)),
             P(flat(st.actions)), P(flat(st.values)), P(flat(st.returns)), P(flat(st.actions_log_prob)),
             P(flat(st.advantages)), P(flat(st.mu)), P(flat(st.sigma)), P(idx), B, ac.num_obs, ac.num_priv, ac.num_hist,
-            P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), None if hoist else P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
+            P(w["Xp"]), ld("Xp"), P(w["Xac"]), ld("Xac"), None if lag else P(w["Xh"]), ld("Xh"), P(w["Lrow"]), stream))
         # ---- forward ----
         ac.forward_teacher(B, save=True)
-        # ---- loss + output gradients ----
-        self._stats.zero_()
+        # ---- loss + output gradients (the statistics are zeroed by the previous call's finalize kernel) ----
         inv_gb = 1.0 / (B * world)
+        kl_slot = ac._grad_store[ac.n_total:ac.n_total + 1] if allreduce is not None else None
         _lib.check(self._lib.rl_ppo_loss(
             P(w["mean"]), P(w["value"]), None, P(w["Xac"]), ld("Xac"), ac.num_obs, P(w["Lrow"]), P(ac.std.data), B,
             A.clip_param, A.value_loss_coef, A.entropy_coef, int(A.use_clipped_value_loss), inv_gb, P(w["dmean"]),
-            P(w["dvalue"]), P(w["dpred"]), P(ac.std_grad), P(self._stats), stream))
+            P(w["dvalue"]), P(w["dpred"]), P(ac.std_grad), P(self._stats), P(kl_slot), stream))
         # ---- backward ----
         H = AC_Args.actor_hidden_dims[0]
-        a, c, e, d = ac.L_act, ac.L_cri, ac.L_enc, ac.L_ada
+        a, c, e = ac.L_act, ac.L_cri, ac.L_enc
         if ac.use_chain:
             # dgrad of actor + critic + encoder in ONE persistent kernel (csrc/chain.cu)
             ac._chain(("trunk_backward",), chain.trunk_backward_program).run(B)
@@ -261,86 +268,108 @@ class PPO:
         self._wgrad(e[1], w["dH2"], 0, ld("dH2"), w["H1"], 0, ld("H1"), B)
         self._wgrad(e[0], w["dH1"], 0, ld("dH1"), w["Xp"], 0, ld("Xp"), B)
         self._wgrad_flush()
-        # ---- data-parallel reduction of the policy gradients and loss statistics ----
-        g_main, g_adapt = ac.flat_grad[:ac.n_main], ac.flat_grad[ac.n_main:]
-        tail = ac._grad_store[ac.n_total:ac.n_total + 4]
-        adaptive = int(A.desired_kl is not None and A.schedule == "adaptive")
-        peer = self._peer if allreduce == "peer" else None
-        g_used = ac.flat_grad
-        if peer is not None:
-            # ONE kernel over NVLink peer memory (csrc/peer_allreduce.cu): sum of every rank's [policy gradient |
-            # adaptation gradient (all zero here) | 4 loss statistics], the squared norm of the policy part, and
-            # the zeroing of the accumulation buffer
-            tail.copy_(self._stats)
-            peer.all_reduce(self._g_red, norm_n=ac.n_main)
-            self._stats.copy_(self._g_red[ac.n_total:ac.n_total + 4])
-            g_used = self._g_red
-        elif allreduce is not None:
-            # NCCL: ONE all-reduce of the same buffer.  The per-rank statistics were summed in float64; their fp32
-            # images are summed over the ranks.
-            tail.copy_(self._stats)
-            allreduce(ac._grad_store[:ac.n_total + 4])
-            self._stats.copy_(tail)
-        if getattr(self, "debug_keep_grad", False):      # parity tests read the raw gradient / statistics
+        # ---- data-parallel reduction: ONE call over [policy | adaptation | KL sum].  In the lagged
+        # schedule the adaptation range holds minibatch i-1's gradient (joined here); serially it is still zero ----
+        early = lag and pending and allreduce is not None      # several GPUs: the adaptation gradient rides in the ONE call
+        if early:
+            torch.cuda.current_stream().wait_event(self._ev_grads)
+        self._reduce(allreduce, 0, norm_n=ac.n_main)
+        if debug:      # parity tests read the raw gradient / statistics
             self.debug_grad = g_used[:ac.n_total].clone()
         # ---- clip + KL-adaptive lr + Adam, all on the device ----
-        if peer is not None:
-            _lib.check(self._lib.rl_grad_finalize_from_norm(P(peer.norm2), P(self._stats), P(self._ctrl), float(B * world),
-                                                            float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive, stream))
-        else:
-            _lib.check(self._lib.rl_grad_finalize(P(g_main), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws),
-                                                  float(B * world), float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive,
-                                                  stream))
-        _lib.check(self._lib.rl_adam(P(ac.flat), P(g_used), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
-                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
+        self._policy_step(B, world, allreduce)
+        if lag:
+            if early:
+                self._adapt_step(g_used)
+            ac.refresh_shadows(self._main_layers + (ac.L_ada if early else []))
+            # regression target of THIS minibatch (ppo.py:158: the latent of the already updated encoder); the next
+            # call's teacher forward overwrites the latent slot, so it is copied out - after the side branch's loss
+            # kernel has read the previous target
+            ac.forward_encoder(B)
+            if pending:
+                torch.cuda.current_stream().wait_event(self._ev_loss)
+            self._target(B)[:B, :ac.latent_dim].copy_(w["Xac"][:B, ac.num_obs:ac.num_obs + ac.latent_dim])
+            if pending and not early:
+                # one GPU: nothing needs the adaptation gradient before this point, the side branch has the whole
+                # policy path to finish in
+                torch.cuda.current_stream().wait_event(self._ev_grads)
+                self._adapt_step(g_used)
+                ac.refresh_shadows(ac.L_ada)
+            torch.cuda.current_stream().wait_event(self._ev_join)          # every forked branch rejoins
+            return
         ac.refresh_shadows(self._main_layers)
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
-        assert not defer_tail or (hoist and A.num_adaptation_module_substeps == 1 and allreduce is None)
-        for sub in range(A.num_adaptation_module_substeps):
+        for _ in range(A.num_adaptation_module_substeps):
             ac.forward_encoder(B)
-            if defer_tail:
-                # the next minibatch's teacher forward overwrites the latent slot: keep this one's target
-                self._target(B)[:B, :ac.latent_dim].copy_(w["Xac"][:B, ac.num_obs:ac.num_obs + ac.latent_dim])
-                torch.cuda.current_stream().wait_event(self._ev_join)      # every forked branch rejoins
-                break
-            if hoist and sub == 0:
-                torch.cuda.current_stream().wait_event(self._ev_join)      # computed next to the teacher path
-            else:
-                ac.forward_adaptation(B, save=True)
-            self._adapt_tail(B, world, allreduce)
-        if getattr(self, "debug_keep_grad", False):
-            self.debug_stats = self._stats.clone()
-        self._loss_acc += self._stats
+            self._adapt_grads(B, world, lagged=False)
+            self._reduce(allreduce, ac.n_main)
+            if debug:
+                self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
+            self._adapt_step(g_used)
+            ac.refresh_shadows(ac.L_ada)
+        if debug:
+            self.debug_stats = self._loss_acc - acc0
+
+    def _reduce(self, allreduce, start, norm_n=0):
+        """Sum over ranks of the flat gradient buffer from element `start` (0: everything incl. the KL word behind
+        it; n_main: the adaptation module's range).  No-op on one GPU."""
+        ac = self.actor_critic
+        if allreduce is None:
+            return
+        if allreduce == "peer":
+            # ONE kernel over NVLink peer memory (csrc/peer_allreduce.cu): the sum, the squared norm of the policy part
+            # and the zeroing of the accumulation buffer
+            self._peer.all_reduce(self._g_red, norm_n=norm_n, start=start)
+        else:
+            allreduce(ac._grad_store[start:ac.n_total + 4])
+
+    def _policy_step(self, B, world, allreduce):
+        """ppo.py:116-124, 146-150: gradient norm -> clip coefficient, KL mean -> learning rate, Adam on the policy
+        parameters; the finalize kernel also folds this minibatch's loss sums into the per-update accumulators."""
+        ac, A = self.actor_critic, PPO_Args
+        P, stream = _lib.ptr, _lib.current_stream()
+        adaptive = int(A.desired_kl is not None and A.schedule == "adaptive")
+        if allreduce == "peer":
+            g_used = self._g_red
+            _lib.check(self._lib.rl_grad_finalize_from_norm(
+                P(self._peer.norm2), P(self._stats), P(self._ctrl), float(B * world), float(A.desired_kl or 0.0),
+                float(A.max_grad_norm), adaptive, P(self._loss_acc), P(g_used[ac.n_total:ac.n_total + 1]), stream))
+        else:
+            g_used = ac.flat_grad
+            kl_slot = ac._grad_store[ac.n_total:ac.n_total + 1] if allreduce is not None else None
+            _lib.check(self._lib.rl_grad_finalize(
+                P(ac.flat_grad[:ac.n_main]), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws), float(B * world),
+                float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive, P(self._loss_acc), P(kl_slot), stream))
+        _lib.check(self._lib.rl_adam(P(ac.flat), P(g_used), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
+                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
 
     def _target(self, B):
-        """bf16 [B, 24] copy of the adaptation regression target (deferred tail only)."""
+        """bf16 [B, 24] copy of the adaptation regression target (lagged schedule only)."""
         t = getattr(self, "_tgt", None)
         if t is None or t.shape[0] < B:
             self._tgt = t = torch.zeros(B, 24, dtype=torch.bfloat16, device=self.device)
         return t
 
-    def _adapt_tail(self, B, world, allreduce, deferred=False):
-        """ppo.py:158-170 after the adaptation forward: regression loss against the encoder latent, backward,
-        Adam step of the adaptation module.  deferred: runs one minibatch later on the side stream (target from
-        the saved copy, statistics into their own accumulator)."""
-        ac, A = self.actor_critic, PPO_Args
+    def _adapt_grads(self, B, world, lagged, loss_event=None):
+        """ppo.py:157-164: adaptation forward, regression loss against the encoder latent, backward; the gradient lands
+        in the adaptation range of the flat buffer, the squared error in the per-update accumulator.  lagged: the rows
+        are those of the previous call (history already gathered, target in `_tgt`)."""
+        ac = self.actor_critic
         w = ac._ws
         P = _lib.ptr
         stream = _lib.current_stream()
         ld = lambda k: w[k].shape[1]
         d = ac.L_ada
         inv_gb = 1.0 / (B * world)
-        peer = self._peer if allreduce == "peer" else None
-        g_used = self._g_red if peer is not None else ac.flat_grad
-        tail = ac._grad_store[ac.n_total:ac.n_total + 4]
-        stats_ad = self._stats_ad
-        stats_ad.zero_()
-        if deferred:
+        ac.forward_adaptation(B, save=True)
+        if lagged:
             tgt = self._target(B)
-            _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(tgt), tgt.shape[1], 0, B, inv_gb, P(w["dpred"]), P(stats_ad), stream))
+            _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(tgt), tgt.shape[1], 0, B, inv_gb, P(w["dpred"]), P(self._loss_acc), stream))
+            if loss_event is not None:
+                loss_event.record()
         else:
             _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(w["Xac"]), ld("Xac"), ac.num_obs, B, inv_gb, P(w["dpred"]),
-                                               P(stats_ad), stream))
+                                               P(self._loss_acc), stream))
         if ac.use_chain:
             ac._chain(("adaptation_backward",), chain.adaptation_backward_program).run(B)
         else:
@@ -350,36 +379,35 @@ class PPO:
         self._wgrad(d[1], w["dD2"], 0, ld("dD2"), w["D1"], 0, ld("D1"), B)
         self._wgrad(d[0], w["dD1"], 0, ld("dD1"), w["Xh"], 0, ld("Xh"), B)
         self._wgrad_flush()
-        if peer is not None:
-            tail.copy_(stats_ad)
-            peer.all_reduce(self._g_red, norm_n=0, start=ac.n_main)     # adaptation gradient + statistics only
-            stats_ad.copy_(self._g_red[ac.n_total:ac.n_total + 4])
-        elif allreduce is not None:
-            tail.copy_(stats_ad)
-            allreduce(ac._grad_store[ac.n_main:ac.n_total + 4])
-            stats_ad.copy_(tail)
-        if getattr(self, "debug_keep_grad", False):
-            self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
+
+    def _adapt_step(self, g_used):
+        """ppo.py:166-168: Adam on the adaptation module (its own fixed learning rate, no clipping)."""
+        ac, A = self.actor_critic, PPO_Args
         n_ad = ac.n_total - ac.n_main
         off = ac.n_main * 4
         _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_used.data_ptr() + off, ac.flat_m.data_ptr() + off,
                                      ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
-                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, stream))
-        ac.refresh_shadows(ac.L_ada)
-        if deferred:
-            self._loss_acc_ad += stats_ad[3:4]
-        else:
-            self._stats[3] += stats_ad[3]
+                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, _lib.current_stream()))
+
+    def sync_replicas(self):
+        """Data parallelism keeps one replica of the learner per rank and only exchanges gradients, so the replicas
+        must START identical: broadcast the parameters, Adam moments, learning-rate control and step counters from rank
+        0 (collective; update() calls it once).  Without it, ranks that were not seeded identically diverge silently."""
+        from ..sharding import broadcast_
+        ac = self.actor_critic
+        broadcast_(ac.flat, ac.flat_m, ac.flat_v, self._ctrl, self._steps)
+        ac.refresh_shadows()
+        self._replicas_synced = True
 
     def update(self):
         """ppo.py:94-178."""
         from ..sharding import all_reduce_sum_, world_size
-        A, st = PPO_Args, self.storage
+        A, st, ac = PPO_Args, self.storage, self.actor_critic
         world = world_size()
         allreduce = all_reduce_sum_ if world > 1 else None
-        # RL_PEER_ALLREDUCE=1: the fused NVLink peer kernel instead of NCCL.  Measured (PPO iteration, 4000 envs per
-        # GPU): 10.7 vs 10.5 ms at 2 GPUs, 12.1 vs 11.4 ms at 8 GPUs - NCCL (NVLS in-switch reduction) wins; what both
-        # pay is the rank skew at every one of the 40 synchronisation points, so NCCL stays the default.
+        if world > 1 and not getattr(self, "_replicas_synced", False):
+            self.sync_replicas()
+        # RL_PEER_ALLREDUCE=1: the fused NVLink peer kernel instead of NCCL (see DESIGN.md section 8 for the A/B)
         if world > 1 and os.environ.get("RL_PEER_ALLREDUCE", "0") == "1":
             if self._peer is None:
                 self.enable_peer_allreduce()
@@ -388,46 +416,43 @@ class PPO:
         mb = batch // A.num_mini_batches
         indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)
         self._loss_acc.zero_()
-        # The ~25 launches of a minibatch step are captured ONCE in a CUDA graph that reads its
-        # row indices from a fixed buffer; each of the 20 steps is then one index copy + one graph replay.
-        # (multi-GPU: the NCCL all-reduces are captured too - every rank captures the same sequence; set
-        # RL_PPO_GRAPH_MULTI=0 to launch eagerly instead)
+        # The ~25 launches of a minibatch step are captured ONCE in a CUDA graph that reads its row indices from a fixed
+        # buffer; each of the 20 steps is then one index copy + one graph replay (with several GPUs the NCCL all-reduce
+        # is captured too - every rank captures the same sequence; RL_PPO_GRAPH_MULTI=0 launches eagerly instead).
         multi_ok = world == 1 or os.environ.get("RL_PPO_GRAPH_MULTI", "1") != "0"
         use_graph = self.use_cuda_graph and multi_ok and not getattr(self, "debug_keep_grad", False)
-        # Deferred adaptation tail (minibatch_step docstring): single GPU, graph mode.  Two graphs: the first minibatch
-        # of an update has no pending tail, every later one runs its predecessor's tail on the side branch.
-        # Single GPU only: with several GPUs the policy all-reduce covers the whole [policy | adaptation | statistics]
-        # buffer in one call and would race with a tail that accumulates into the adaptation range at the same time
-        # (a 2-GPU trial of the deferred tail also hung in the small-batch test) - there the tail stays serial.
-        defer = (use_graph and allreduce is None and self.overlap_adaptation and self.actor_critic.use_chain and
-                 A.num_adaptation_module_substeps == 1 and os.environ.get("RL_PPO_DEFER_TAIL", "1") != "0")
-        if use_graph and (self._graph is None or self._graph_B != mb or self._graph_defer != defer):
-            self.actor_critic.workspace(mb, backward=True)        # allocate outside the capture
-            self.actor_critic.prepare_update_chains()
+        # Lagged adaptation schedule (minibatch_step docstring): two graphs - the first minibatch of an update has nothing
+        # pending - and one eager flush after the last.  RL_PPO_OVERLAP=0 keeps the serial order.
+        lag = (use_graph and self.overlap_adaptation and ac.use_chain and A.num_adaptation_module_substeps == 1)
+        ws_gen = getattr(ac, "_ws_gen", 0)
+        if use_graph and (self._graph is None or self._graph_B != mb or self._graph_lag != lag or self._graph_ws_gen != ws_gen or
+                          self._graph_reduce != (allreduce if isinstance(allreduce, str) else allreduce is not None)):
+            ac.workspace(mb, backward=True)        # allocate outside the capture
+            ac.prepare_update_chains()
             self._target(mb)
             self._idx_buf = torch.zeros(mb, dtype=torch.long, device=self.device)
             torch.cuda.synchronize()
-            state = (self.actor_critic.flat, self.actor_critic.flat_m, self.actor_critic.flat_v,
-                     self.actor_critic.flat_grad, self._ctrl, self._steps, self._loss_acc, self._loss_acc_ad)
+            state = (ac.flat, ac.flat_m, ac.flat_v, ac._grad_store, self._ctrl, self._steps, self._loss_acc, self._stats)
             snap = [t.clone() for t in state]
             # capture on a high-priority stream: kernel nodes keep their stream's priority, so the policy path's CTAs
             # are placed before those of the side branch (adaptation module), which only fills what is left
             kw = {}
-            if self.overlap_adaptation and os.environ.get("RL_PPO_PRIO", "1") != "0":
+            if lag and os.environ.get("RL_PPO_PRIO", "1") != "0":
                 if self._hp is None:
                     self._hp = torch.cuda.Stream(device=self.device, priority=-1)
                 kw["stream"] = self._hp
             graphs = []
-            for pending in ((False, True) if defer else (False,)):
+            for pending in ((False, True) if lag else (False,)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, **kw):
-                    self.minibatch_step(self._idx_buf, world, allreduce, defer_tail=defer, pending_tail=pending)
+                    self.minibatch_step(self._idx_buf, world, allreduce, lag=lag, pending=pending)
                 graphs.append(g)
             # capture does not execute, but keep the state bit-identical in any case
             for t, s0 in zip(state, snap):
                 t.copy_(s0)
-            self._graph, self._graph_rest, self._graph_B, self._graph_defer = graphs[0], graphs[-1], mb, defer
-        self._loss_acc_ad.zero_()
+            self._graph, self._graph_rest, self._graph_B, self._graph_lag = graphs[0], graphs[-1], mb, lag
+            self._graph_ws_gen = getattr(ac, "_ws_gen", 0)
+            self._graph_reduce = allreduce if isinstance(allreduce, str) else allreduce is not None
         first = True
         for _ in range(A.num_learning_epochs):
             for i in range(A.num_mini_batches):
@@ -437,12 +462,17 @@ class PPO:
                     first = False
                 else:
                     self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
-        if use_graph and defer:
-            self._adapt_tail(mb, world, None, deferred=True)       # the last minibatch's adaptation update
-            self._loss_acc[3:4] += self._loss_acc_ad
+        if use_graph and lag:
+            # the last minibatch's adaptation update
+            self._adapt_grads(mb, world, lagged=True)
+            self._reduce(allreduce, ac.n_main)
+            self._adapt_step(self._g_red if allreduce == "peer" else ac.flat_grad)
+            ac.refresh_shadows(ac.L_ada)
+        if world > 1:
+            all_reduce_sum_(self._loss_acc)        # loss means span the env shards of every rank
         n_upd = A.num_learning_epochs * A.num_mini_batches
         acc = (self._loss_acc / (mb * world)).tolist()          # the only device->host read of the update
         self.learning_rate = float(self._ctrl[0])
         st.clear()
-        lat = self.actor_critic.latent_dim
+        lat = ac.latent_dim
         return acc[1] / n_upd, acc[0] / n_upd, acc[3] / lat / n_upd / A.num_adaptation_module_substeps

@@ -40,6 +40,16 @@ def all_reduce_sum_(*tensors):
         d.all_reduce(t, op=d.ReduceOp.SUM)
 
 
+def broadcast_(*tensors, src=0):
+    """In-place broadcast of each tensor from rank `src` (replica initialisation: PPO.sync_replicas); no-op for a
+    single process."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return
+    for t in tensors:
+        d.broadcast(t, src=src)
+
+
 def all_reduce_max_(t):
     d = _dist()
     if d is not None and d.get_world_size() > 1:

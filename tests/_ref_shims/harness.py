@@ -10,8 +10,23 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("RL_REFERENCE_ROOT", "/root/reference")
 _SHIMS = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(_SHIMS)), "oracle", "_ref")      # oracle/make_ref.py
+
+
+def _reference_root():
+    """RL_REFERENCE_ROOT, else the source tree of the build container, else the copy staged by oracle/make_ref.py
+    (the only one that exists on the GPU box)."""
+    env = os.environ.get("RL_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isdir(os.path.join(cand, "mini_gym")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available():

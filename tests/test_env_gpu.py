@@ -351,3 +351,57 @@ def test_host_io_zero_copy_matches_device_step():
                 env.step_host(actions)          # not pinned
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case,n", [("mc_flat", 4000), ("go1", 4128), ("mc_flat", 32768)])
+def test_rows_kernel_matches_quad_kernel(case, n):
+    """The all-TMA kernel (csrc/env_step_rows.cu, packed state blocks) and the one-warp-per-leg kernel it replaces give
+    identical bits for every output and every piece of state: fused step and post-physics entry, Philox noise (no
+    injection), three consecutive steps (the second re-draws Kp / Kd / motor strength for a third of the envs)."""
+    from rapid_locomotion_rl_b200 import _lib
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    lib = _lib.lib()
+    results = []
+    for mode in (1, 0):
+        prev = lib.rl_debug_env_rows(mode)
+        try:
+            env, cfg, robot, terrain = make_env(case, n)
+            p = env.params
+            rng = np.random.default_rng(7)
+            st = random_persistent_state(rng, n, list(env.episode_sums.keys()))
+            st["episode_length_buf"][::3] = p.rand_interval - 2        # re-draw on the second step
+            for k in env.command_sums:
+                st["command_sums/" + k] = rng.normal(0, 1, n).astype(np.float32)
+            for k in ("env_origins", "terrain_levels", "terrain_types"):
+                st[k] = getattr(env, k).cpu().numpy()
+            st.update(synthetic_state(3, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx,
+                                      p.term_idx[:p.n_term_bodies], z0=0.3, teleport_band_frac=0.05))
+            statekit.apply_to_product(env, st)
+            actions = cu(rng.normal(0, 1, (n, 12)).astype(np.float32))
+            outs = []
+            for s in range(3):
+                if s == 2:                      # the gymapi-shaped entry pair
+                    env._compute_torques(actions)
+                    env.post_physics_step(actions)
+                    o = (env.obs_buf, env.privileged_obs_buf, env.rew_buf, env.reset_buf)
+                else:
+                    o = env.step(actions)[:4]
+                torch.cuda.synchronize()
+                outs.append([t.clone() for t in o] + [env.torques.clone()])
+            state = statekit.state_from_product(env)
+            results.append((outs, state))
+        finally:
+            lib.rl_debug_env_rows(prev)
+    (oa, sa), (ob, sb) = results
+    def where(a, b):
+        a, b = np.asarray(a), np.asarray(b)
+        bad = np.argwhere(a != b)
+        rows = np.unique(bad[:, 0])
+        return "%d elements in %d envs differ; first envs %s (mod 32: %s), first columns %s" % (
+            len(bad), len(rows), rows[:8].tolist(), (rows[:8] % 32).tolist(), bad[:8, 1:].tolist())
+    names = ("obs", "priv", "rew", "reset", "torques")
+    for s, (xa, xb) in enumerate(zip(oa, ob)):
+        for i, (a, b) in enumerate(zip(xa, xb)):
+            assert torch.equal(a, b), "step %d %s: %s" % (s, names[i], where(a.cpu().numpy(), b.cpu().numpy()))
+    for k in sa:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), "state %r: %s" % (k, where(sa[k], sb[k]))

@@ -182,37 +182,36 @@ def test_gather_history_matches_indexing():
     assert lib.rl_ppo_gather_history(None, idx.data_ptr(), B, dim, out.data_ptr(), ld, _lib.current_stream()) != 0
 
 
-def test_side_branch_schedules_match_serial_update(golden_dir, learner_path, monkeypatch):
-    """PPO.update with the adaptation module on the side branch (forward hoisted; loss / dgrad / wgrad / Adam one
-    minibatch behind, two captured graphs + flush) must produce the serial schedule's parameters and statistics:
-    the schedules differ only in WHEN independent kernels run (fp32 atomics order aside)."""
+def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeypatch):
+    """PPO.update with the adaptation module one minibatch behind on the side branch (two captured graphs + flush,
+    ONE gradient reduction point per minibatch) must produce the serial schedule's parameters and statistics: the
+    schedules differ only in WHEN independent kernels run (fp32 atomics order aside)."""
     if learner_path != "chain":
         pytest.skip("the side branch exists on the chain path only")
     from rapid_locomotion_rl_b200.ppo import PPO
     g = np.load(os.path.join(golden_dir, "learner.npz"))
     init, storage, perm = learner_case(g)
     out = {}
-    for name, env in (("serial", dict(RL_PPO_OVERLAP="0")), ("hoisted", dict(RL_PPO_DEFER_TAIL="0")), ("deferred", {})):
-        for k in ("RL_PPO_OVERLAP", "RL_PPO_DEFER_TAIL"):
-            monkeypatch.delenv(k, raising=False)
+    for name, env in (("serial", dict(RL_PPO_OVERLAP="0")), ("lagged", {})):
+        monkeypatch.delenv("RL_PPO_OVERLAP", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ac, _ = make_ac()
         ppo = PPO(ac, device=DEV)
         ppo.init_storage(64, 8, [42], [18], [630], [12])
         _load_storage(ppo, storage, 64, 8)
-        ppo.storage.step = 8
         real = torch.randperm
         torch.randperm = lambda n, **kw: perm.to(DEV)
         try:
-            res = ppo.update()
+            for _ in range(2):               # second update re-uses the captured graphs
+                ppo.storage.step = 8
+                res = ppo.update()
         finally:
             torch.randperm = real
         torch.cuda.synchronize()
-        assert ppo._graph_defer == (name == "deferred")
+        assert ppo._graph_lag == (name == "lagged")
         out[name] = (ac.flat.clone(), res, ppo.learning_rate)
-    for name in ("hoisted", "deferred"):
-        d = (out[name][0] - out["serial"][0]).abs().max().item()
-        assert d <= 2e-4, (name, d)                      # 20 Adam steps of |dw| <= lr = 1e-3 each
-        np.testing.assert_allclose(out[name][1], out["serial"][1], rtol=2e-3, atol=1e-6)
-        assert abs(out[name][2] - out["serial"][2]) <= 1e-12
+    d = (out["lagged"][0] - out["serial"][0]).abs().max().item()
+    assert d <= 4e-4, d                                  # 40 Adam steps of |dw| <= lr = 1e-3 each
+    np.testing.assert_allclose(out["lagged"][1], out["serial"][1], rtol=5e-3, atol=1e-6)
+    assert abs(out["lagged"][2] - out["serial"][2]) <= 1e-12
