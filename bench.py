@@ -31,7 +31,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-BYTES_PER_ENV_STEP = {"mini_cheetah": 1425, "go1": 1473}   # SURVEY.md 8(d) algorithmic bytes
+# SURVEY.md 8(d) algorithmic bytes per env-step: Mini Cheetah flat (780 read + 645 written), Go1 (17 bodies: +48 B of
+# contact rows), Mini Cheetah rough (229-column observations + measured heights; the 9.4 MB height table is L2 resident)
+BYTES_PER_ENV_STEP = {"mc_flat": 1425, "go1": 1473, "mc_rough_full": 2921}
 L2_BYTES = 126 * 1024 * 1024
 H2D_PER_ENV = 48 + 52 + 96 + 156      # actions, root, dof_state, contact rows (Mini Cheetah)
 D2H_PER_ENV = 168 + 72 + 4 + 1        # obs, privileged obs, reward, reset flag
@@ -163,7 +165,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(device))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     pk, pk_kind = peaks()
-    bpe = BYTES_PER_ENV_STEP["mini_cheetah"]
+    bpe = BYTES_PER_ENV_STEP["mc_flat"]
     if args.only_ppo:      # development aid: just the learner metric
         if rank == 0:
             print(json.dumps(ppo_bench(args.ppo_envs, 24, device, world, pk)))
@@ -171,9 +173,9 @@ def run_ours(args):
             ppo_bench(args.ppo_envs, 24, device, world, pk)
         return
 
-    def measure(envs, steps, warmup, sample_clocks):
-        n_rep = max(2, math.ceil(2.0 * L2_BYTES / (envs * bpe)))
-        reps = build_replicas("mc_flat", envs, n_rep, device, seed0=rank)
+    def measure(envs, steps, warmup, sample_clocks, case="mc_flat"):
+        n_rep = max(2, math.ceil(2.0 * L2_BYTES / (envs * BYTES_PER_ENV_STEP[case])))
+        reps = build_replicas(case, envs, n_rep, device, seed0=rank)
         g = time_env_steps(reps, steps, warmup)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(physical_gpu_index(local)) if sample_clocks else None
@@ -341,6 +343,23 @@ def run_ours(args):
             torch.cuda.empty_cache()
 
     if world == 1 and not args.quick:
+        # BASELINE configs[3] (Go1: 17 bodies, 1473 B per env-step) and configs[2] (Mini Cheetah on the full 1800 x 2600
+        # heightfield with measured heights: 2921 B per env-step), at the configs' 4000 envs and at the scale-out size
+        for case in ("go1", "mc_rough_full"):
+            b_case = BYTES_PER_ENV_STEP[case]
+            for envs in (4000, 32768):
+                k2 = min(args.steps, 300)
+                try:
+                    ms2, nr2, reps2, _ = measure(envs, k2, args.warmup, False, case=case)
+                    also["%s_%d" % (case, envs)] = {
+                        "value": envs * k2 / (ms2 * 1e-3), "ms_per_step": ms2 / k2, "steps": k2, "replicas": nr2,
+                        "bytes_per_env_step": b_case, "roofline_frac": envs * b_case / (ms2 * 1e-3 / k2) / 1e9 / pk["hbm_gbs"]}
+                    del reps2
+                except Exception as exc:
+                    also["%s_%d" % (case, envs)] = {"error": str(exc)[:200]}
+                torch.cuda.empty_cache()
+
+    if world == 1 and not args.quick:
         # the gymapi-shaped sequence - `decimation` x (torque kernel between physics sub-steps) +
         # one post-physics kernel per step (5 launches instead of the 1 fused launch)
         k3 = min(args.steps, 300)
@@ -381,6 +400,15 @@ def run_ours(args):
             pass
         torch.cuda.empty_cache()
         ppo = ppo_bench(args.ppo_envs, 24, device, world, pk)
+        # BASELINE configs[4]: the learner at the scale-out size (32768 envs per GPU x 24: 196608-row minibatches)
+        try:
+            torch.cuda.empty_cache()
+            ppo["c5_32768_envs"] = ppo_bench(32768, 24, device, world, pk, iters=2)
+        except Exception as exc:
+            ppo["c5_32768_envs"] = {"error": str(exc)[:200]}
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            ppo["reference"] = ppo_reference_block(args.ppo_envs)
 
     runner = None
     if world == 1 and not args.quick:

@@ -230,6 +230,9 @@ typedef struct RlEnvBuffers {
    * graph): [0] is added to the `step` argument to key the RNG and is incremented once per
    * launch by the last CTA to finish; [1] is that CTA ticket.  NULL => host `step` only. */
   uint64_t* step_state;         /* [2] */
+  /* optional [N]: the sum of the enabled terms BEFORE the positive clip and the termination term (:328-334).  The
+   * Python plugin layer needs it to add user-defined `_reward_<name>` terms exactly where the reference adds them. */
+  float* rew_raw;
 } RlEnvBuffers;
 
 /* profiling aid: enable / read the globaltimer phase stamps of one CTA of the fused env-step kernel
@@ -240,6 +243,10 @@ int rl_debug_env_trace(int32_t enable, uint64_t* out_host16);
  * packed state blocks: 1 = env_step_rows.cu (all tile traffic on TMA; the default), 0 = env_step_quad.cu, -1 = back to
  * the default (environment variable RL_ENV_ROWS).  Returns the previous setting.  Both kernels produce identical bits. */
 int rl_debug_env_rows(int32_t mode);
+/* profiling aid: per-CTA globaltimer stamps of the following env_step_rows launches {entry, loads issued, tile landed,
+ * phase 1 done, phase 2 done, stores issued, stores read, smid}.  enable > 0: number of CTAs to record (switches tracing
+ * on), 0: off.  out_host (optional): receives min(capacity_ctas, recorded) x 8 values of the last traced launch. */
+int rl_debug_env_rows_trace(int32_t enable, uint64_t* out_host, int32_t capacity_ctas);
 const char* rl_last_error(void);
 const char* rl_version(void);
 /* sizeof(struct <name>) as compiled into the library (-1 for an unknown name): lets a
@@ -261,6 +268,12 @@ int rl_env_post_physics(const RlEnvCfg* cfg_host, const RlEnvBuffers* bufs_host,
  * pipeline in ONE kernel.  The benchmark entry (SURVEY 8d metric 1). */
 int rl_env_step_fused(const RlEnvCfg* cfg_host, const RlEnvBuffers* bufs_host, uint64_t seed,
                       uint64_t step, void* stream);
+
+/* legged_robot.py:1469-1503 _get_heights as a launch of its own: out[i, p] = height under measured point p of env
+ * env_ids[i] (NULL: envs 0..n_ids-1), from the current root_states [N,13], the base-frame points [P,2] and the int16
+ * table.  The fused step samples the same values in-kernel; this serves direct callers of the method. */
+int rl_env_heights(const RlEnvCfg* cfg_host, const float* root_states, const float* height_points,
+                   const int16_t* height_samples, const int64_t* env_ids, int32_t n_ids, float* out, void* stream);
 
 /* Reset (legged_robot.py:227-290 reset_idx and the helpers it calls). */
 typedef struct RlResetCfg {
@@ -608,7 +621,8 @@ int rl_policy_sample(const float* mean, const float* std, int32_t N, uint64_t se
 
 /* rollout_storage.py:54-71 RolloutStorage.add_transitions: one launch writes the transition of every env into
  * the [t] slices of the storage (the reference: eleven copy_ kernels per step).  Sources are [N, dim] rows with
- * the given pitches (the observation history is a strided view of the ring buffer); destinations are dense. */
+ * the given pitches (the observation history is a strided view of the ring buffer); destinations are dense.
+ * obs / priv / hist may be NULL (with their destinations): those rows were stored when the action was taken. */
 typedef struct RlStorageAdd {
   const float* obs;
   const float* priv;
@@ -642,6 +656,64 @@ int rl_storage_add(const RlStorageAdd* q_host, void* stream);
  * always one contiguous row span: hist [N, 2*H*num_obs], writes slots k and k+H. */
 int rl_history_push(float* hist, const float* obs, int32_t N, int32_t num_obs, int32_t H,
                     int32_t slot, void* stream);
+
+/* ---- rollout-step glue of Runner.learn (mini_gym_learn/ppo/__init__.py:126-141), two launches per step ----
+ * rl_rollout_boundary runs BETWEEN env step t and the policy pass of step t+1, one warp per env:
+ *   post part (do_post): closes transition t - dst_rewards[n] = rew[n] (+ gamma * values_prev[n] where time_outs[n],
+ *     ppo.py:81-83), dst_dones, dst_bins (rollout_storage.py:63-70) - and pushes the new observation into the history
+ *     ring at `push_slot` (history_wrapper.py:23; ring layout as rl_history_push);
+ *   pre part (do_pre): opens transition t+1 - dst_obs / dst_priv / dst_hist (rollout_storage.py:57-60; the history row is
+ *     the H-slot span starting at ring slot `hist_slot`, whose last slot is the observation just pushed) and the bf16
+ *     staging of the policy inputs: Xac[n, 0:obs_dim] = obs, Xp[n, 0:ld_xp] = priv zero padded. */
+typedef struct RlRolloutBoundary {
+  const float* obs;          /* [N, obs_dim] observation after env step t */
+  const float* priv;         /* [N, priv_dim] */
+  float* ring;               /* [N, 2*H*obs_dim] */
+  const float* rew;          /* [N] */
+  const uint8_t* dones;      /* [N] bool */
+  const uint8_t* time_outs;  /* [N] bool or NULL */
+  const float* values_prev;  /* [N] value estimates of transition t (needed with time_outs) */
+  const float* bins;         /* [N] or NULL (zeros) */
+  float* dst_rewards;        /* storage.rewards[t] [N] */
+  uint8_t* dst_dones;        /* storage.dones[t] [N] */
+  float* dst_bins;           /* storage.env_bins[t] [N] */
+  float* dst_obs;            /* storage.observations[t+1] [N, obs_dim] */
+  float* dst_priv;           /* storage.privileged_observations[t+1] [N, priv_dim] */
+  float* dst_hist;           /* storage.observation_histories[t+1] [N, H*obs_dim] */
+  void* Xac;                 /* bf16 [N, ld_xac] */
+  void* Xp;                  /* bf16 [N, ld_xp] */
+  float gamma;
+  int32_t N, obs_dim, priv_dim, H;
+  int32_t push_slot, hist_slot;
+  int32_t ld_xac, ld_xp;
+  int32_t do_post, do_pre;
+  int32_t reserved;
+} RlRolloutBoundary;
+int rl_rollout_boundary(const RlRolloutBoundary* q_host, void* stream);
+
+/* rl_rollout_act runs AFTER the policy pass, one thread per env: a = mean + std * N(0,1) (actor_critic.py:142-147;
+ * Philox keyed by (seed, env, step + step_state[0]) or the injected normals), its log-probability, and the
+ * transition's slices: actions / mu / sigma / log-prob / value (rollout_storage.py:61-69) next to `actions_out`, the
+ * buffer the env step reads.  step_state (optional, uint64[2]): device-side step counter advanced once per launch, so
+ * the launch replays inside a CUDA graph.  dst_* may all be NULL (plain ActorCritic.act). */
+typedef struct RlRolloutAct {
+  const float* mean;         /* [N, 12] */
+  const float* value;        /* [N] */
+  const float* std;          /* [12] */
+  const float* inj_normal;   /* [N, 12] or NULL */
+  float* actions_out;        /* [N, 12] */
+  float* logp_out;           /* [N] or NULL */
+  float* dst_actions;        /* storage.actions[t] or NULL */
+  float* dst_mu;
+  float* dst_sigma;
+  float* dst_logp;
+  float* dst_values;
+  uint64_t* step_state;      /* [2] or NULL */
+  uint64_t seed, step;
+  int32_t N;
+  int32_t reserved;
+} RlRolloutAct;
+int rl_rollout_act(const RlRolloutAct* q_host, void* stream);
 
 #ifdef __cplusplus
 }

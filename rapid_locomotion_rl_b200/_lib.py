@@ -82,6 +82,8 @@ RlChainLoadOp = STRUCTS["RlChainLoadOp"]
 RlChainMmaOp = STRUCTS["RlChainMmaOp"]
 RlChainEpiOp = STRUCTS["RlChainEpiOp"]
 RlChainDesc = STRUCTS["RlChainDesc"]
+RlRolloutBoundary = STRUCTS["RlRolloutBoundary"]
+RlRolloutAct = STRUCTS["RlRolloutAct"]
 
 RL_OK = DEFINES["RL_OK"]
 REWARD_TERM_IDS = {k[len("RL_REW_"):].lower(): v for k, v in ENUMS.items() if k.startswith("RL_REW_") and k != "RL_REW_COUNT"}
@@ -94,9 +96,11 @@ SIGNATURES = {
     "rl_sizeof": (C.c_int64, [C.c_char_p]),
     "rl_debug_env_trace": (C.c_int, [C.c_int32, _P]),
     "rl_debug_env_rows": (C.c_int, [C.c_int32]),
+    "rl_debug_env_rows_trace": (C.c_int, [C.c_int32, _P, C.c_int32]),
     "rl_env_torques": (C.c_int, [_P, _P, _P]),
     "rl_env_post_physics": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "rl_env_step_fused": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
+    "rl_env_heights": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "rl_env_reset": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "rl_gac_scatter": (C.c_int, [_P, _P, _P]),
     "rl_gac_update_sample": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
@@ -105,6 +109,8 @@ SIGNATURES = {
     "rl_gae_normalize": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "rl_gae": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P]),
     "rl_storage_add": (C.c_int, [_P, _P]),
+    "rl_rollout_boundary": (C.c_int, [_P, _P]),
+    "rl_rollout_act": (C.c_int, [_P, _P]),
     "rl_history_push": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_gemm_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int32] * 10 + [_P]),
     "rl_ppo_gather": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),

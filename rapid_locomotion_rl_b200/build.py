@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
 ]
 # env-path kernels mirror the eager reference op by op: no FMA contraction
-NO_FMA = {"env_step.cu", "env_step_quad.cu", "env_step_rows.cu", "env_reset.cu", "gac.cu", "gae.cu", "history.cu", "api.cu"}
+NO_FMA = {"env_step.cu", "env_step_quad.cu", "env_step_rows.cu", "heights.cu", "env_reset.cu", "gac.cu", "gae.cu", "history.cu", "api.cu"}
 
 
 def _sources():

@@ -370,13 +370,15 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     p.reward_names = [n for n in reward_scales if n != "termination"]
     maxt = _lib.DEFINES["RL_MAX_TERMS"]
     p.term_id, p.term_scale = [], []
+    p.custom_terms = []        # user-defined `_reward_<name>` methods: evaluated by the env class after the fused launch
     for n in p.reward_names:
-        if n not in _lib.REWARD_TERM_IDS:
+        if n not in _lib.REWARD_TERM_IDS or n in custom_reward_names:
             if n in custom_reward_names:
-                raise NotImplementedError(
-                    "reward term %r is a Python-side _reward_ method; only the built-in terms are fused" % n)
+                p.custom_terms.append((n, f32(reward_scales[n])))
+                continue
             raise AttributeError("'LeggedRobot' object has no attribute '_reward_%s'" % n)  # :1093
         p.term_id.append(_lib.REWARD_TERM_IDS[n]); p.term_scale.append(f32(reward_scales[n]))
+    fused_names = [n for n in p.reward_names if n not in dict(p.custom_terms)]
     p.n_terms = len(p.term_id)
     if p.n_terms > maxt:
         raise NotImplementedError("%d enabled reward terms > %d supported by the fused kernel" % (p.n_terms, maxt))
@@ -387,7 +389,7 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     for i in p.term_id[:p.n_terms]:
         p.term_mask |= 1 << i
     # fixed accumulator rows (rl_b200.h): term i -> row i, termination, total / extras
-    p.sum_rows = {n: i for i, n in enumerate(p.reward_names)}
+    p.sum_rows = {n: i for i, n in enumerate(fused_names)}
     if p.has_termination:
         p.sum_rows["termination"] = _lib.DEFINES["RL_MAX_TERMS"]
     p.sum_names = list(p.sum_rows.keys())
@@ -436,7 +438,7 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     p.noise_scale_vec = vec.astype(np.float32)
     ncore = len(p.noise_scale_vec) - p.num_height_points
     maxc = _lib.DEFINES["RL_MAX_CORE_OBS"]
-    if ncore > maxc:
+    if ncore > maxc or p.num_obs - p.num_height_points > maxc:
         raise NotImplementedError("%d non-height observation columns > %d" % (ncore, maxc))
     p.noise_scale_core = [float(x) for x in p.noise_scale_vec[:ncore]] + [0.0] * (maxc - ncore)
     p.noise_scale_height = float(p.noise_scale_vec[-1]) if p.measure_heights else 0.0
@@ -447,7 +449,8 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
         + 3 * p.observe_only_lin_vel + p.observe_yaw + p.num_height_points
     if width != p.num_obs:
         raise ValueError("env.num_observations=%d but the enabled observation groups produce %d columns" % (p.num_obs, width))
-    if len(p.noise_scale_vec) != p.num_obs:
+    p.add_noise = int(bool(cfg.noise.add_noise))
+    if len(p.noise_scale_vec) != p.num_obs and p.add_noise:       # (without noise the reference never uses the vector)
         raise ValueError("noise vector has %d columns for %d observations (reference :882-932 has the same gap)"
                          % (len(p.noise_scale_vec), p.num_obs))
     # privileged observations

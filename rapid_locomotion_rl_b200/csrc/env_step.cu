@@ -479,6 +479,7 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
       if (cfg.has_termination) { e_term = pe[RL_ROW_TERMINATION * N]; c_term = pc[RL_ROW_TERMINATION * N]; }
 #pragma unroll
       for (int x = 0; x < 5; ++x) cx[x] = pc[(RL_ROW_EXTRAS + x) * N];
+      if (b.rew_raw) b.rew_raw[e] = rew;
       if (cfg.only_positive_rewards) rew = fmaxf(rew, 0.f);
       pe[RL_ROW_TOTAL * N] = e_tot + rew;
       if (cfg.has_termination) {

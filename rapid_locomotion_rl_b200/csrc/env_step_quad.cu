@@ -576,6 +576,7 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
 #pragma unroll 1
       for (int i = 0; i < cfg.n_terms; ++i) rew += s_r[i * QT + lane];
     }
+    if (b.rew_raw) b.rew_raw[e] = rew;
     if (c_pos) rew = fmaxf(rew, 0.f);
     b.episode_sums[RL_ROW_TOTAL * N + e] = ex0 + rew;
     if (c_term) {

@@ -16,6 +16,12 @@
 // issue order, so the first CTA computes while the rows of the later ones are still in flight, and the
 // kernel body reads shared memory with immediate offsets (no address arithmetic, no LDG latency).  The
 // results leave the same way: 5 tensor stores + 3 bulk stores issued by one thread.
+// Measured per-CTA timeline at 32768 envs (profiles/r02_env_rows_trace.md): copies issued 0.9 us after entry, tiles land
+// together 4.8 us later (25.6 MB at 5.3 TB/s - all 1024 CTAs are resident at once, so every tile is requested at t = 0),
+// then 5 us of compute and stores.  Two things were tried on top and dropped (A/B in one gpurun call): programmatic
+// dependent launch (4000 envs: 5.9 -> 8.5 us per launch, 32768: 13.2 -> 13.1) and a staggered start in which a CTA of
+// group g issues its copies only when a CTA of group g - 1 has its tile (2 / 3 / 4 groups: 13.7 -> 15.4 / 18.8 / 22.6 us:
+// a group's first byte costs ~1.1 us of latency whatever its size, so serialised groups lose more than overlap wins).
 // Used when: standard configuration (see launch_step_quad's is_std), num_envs % 32 == 0, the state
 // pointers form the packed blocks; otherwise the caller falls back to env_step_quad.cu.
 #include <cuda.h>
@@ -30,6 +36,7 @@ namespace rl {
 
 int make_tmap_f32_rows(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n, uint32_t box_rows);
 
+static bool rows_trace_on = false;
 namespace rows {
 
 constexpr int QT = 32, QTHREADS = 128;
@@ -44,7 +51,16 @@ constexpr int ROWB = QT * 4;      // bytes of one 32-env row
 struct RowsArgs {
   StepArgs a;
   CUtensorMap m_ro, m_rw, m_wo, m_es12, m_es1, m_cs12, m_cs5;
+  unsigned long long* trace;     // profiling aid (rl_debug_env_rows_trace): 8 globaltimer stamps per CTA, or null
 };
+constexpr int TRACE_STAMPS = 8;
+__device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
+  if (trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)blockIdx.x * TRACE_STAMPS + i] = t;
+  }
+}
 
 __device__ __forceinline__ void tma_load_rows(void* smem_dst, const CUtensorMap* map, int env0, int row0, uint64_t* bar) {
   asm volatile(
@@ -116,6 +132,12 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   // kernel before the first global access.  Hides the launch latency / CTA ramp between consecutive steps; both
   // instructions are no-ops when the launch does not carry the programmatic-serialization attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  stamp(args.trace, 0);
+  if (args.trace && tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    args.trace[(size_t)blockIdx.x * TRACE_STAMPS + 7] = smid;
+  }
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
@@ -140,6 +162,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     tma_load_rows(s_cs, &args.m_cs12, tile0, 0, &s_bar);
     tma_load_rows(s_cs + 12 * QT, &args.m_cs5, tile0, RL_ROW_EXTRAS, &s_bar);
   }
+  stamp(args.trace, 1);
   // small per-env scalars with their own dtypes: plain coalesced loads
   const uint64_t rng_step = args.a.step + (b.step_state ? b.step_state[0] : 0ull);
   int ep = (int)b.episode_length_buf[e];
@@ -159,6 +182,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
       }
     }
   }
+  stamp(args.trace, 2);
   ep += 1;                              // :152
 
   // ---- teleport (:768-791) by warp 0 ------------------------------------------------------------------------
@@ -336,6 +360,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     }
   }
   __syncthreads();
+  stamp(args.trace, 3);
 
   // =================================== phase 2 ===========================================================
   // warp w evaluates terms w, w + 4, w + 8 (reward_names order of the shipped configuration), adds them to its
@@ -407,6 +432,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   if (dirty) s_root_dirty = 1;
   fence_async_smem();
   __syncthreads();
+  stamp(args.trace, 4);
 
   // =================================== stores + phase 3 ==================================================
   if (tid == 0) {
@@ -427,12 +453,15 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     float rew = 0.f;
 #pragma unroll
     for (int i = 0; i < 12; ++i) rew += s_r[i * QT + lane];
+    if (b.rew_raw) b.rew_raw[e] = rew;
     rew = fmaxf(rew, 0.f);
     b.episode_sums[RL_ROW_TOTAL * N + e] = s_es[12 * QT + lane] + rew;
     b.rew_buf[e] = rew;
   }
+  stamp(args.trace, 5);
   if (tid == 0) {
     bulk_wait_read0();                 // the stores have read their shared-memory source
+    stamp(args.trace, 6);
     if (b.step_state) {
       const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
       if (done == gridDim.x - 1) {
@@ -473,8 +502,11 @@ static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
     RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     configured = smem;
   }
-  static int pdl = -1;       // RL_ENV_PDL=0: plain stream-ordered launch
-  if (pdl < 0) { const char* e = getenv("RL_ENV_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
+  // RL_ENV_PDL=1: programmatic dependent launch.  Measured inside the K-step CUDA graph (us per launch, PDL off / on):
+  // 4000 envs 5.94 / 8.51, 32768 envs 13.23 / 13.05, 262144 envs 66.05 / 65.89 - programmatic edges cost more than
+  // they hide for small grids, so it stays off by default
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("RL_ENV_PDL"); pdl = (e && atoi(e) == 1) ? 1 : 0; }
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(ra.a.cfg.num_envs / QT); lc.blockDim = dim3(QTHREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
   cudaLaunchAttribute at[1];
@@ -488,6 +520,30 @@ static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
 
 }  // namespace rows
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_ctas = 0;
+}  // namespace rl
+// profiling aid: per-CTA globaltimer stamps of the next env_step_rows launches {entry, loads issued, tile landed, phase 1
+// done, phase 2 done, stores issued, stores read, smid}.  enable > 0: allocate for `enable` CTAs and switch on; 0: off.
+// out_host (optional): receives capacity_ctas x 8 values of the last traced launch.
+extern "C" int rl_debug_env_rows_trace(int32_t enable, uint64_t* out_host, int32_t capacity_ctas) {
+  using namespace rl;
+  if (out_host && g_trace_buf) {
+    const int n = capacity_ctas < g_trace_ctas ? capacity_ctas : g_trace_ctas;
+    cudaError_t err = cudaMemcpy(out_host, g_trace_buf, (size_t)n * rows::TRACE_STAMPS * 8, cudaMemcpyDeviceToHost);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "rl_debug_env_rows_trace: %s", cudaGetErrorString(err));
+  }
+  if (enable > 0 && enable > g_trace_ctas) {
+    if (g_trace_buf) cudaFree(g_trace_buf);
+    cudaError_t err = cudaMalloc(&g_trace_buf, (size_t)enable * rows::TRACE_STAMPS * 8);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "rl_debug_env_rows_trace: %s", cudaGetErrorString(err));
+    g_trace_ctas = enable;
+  }
+  if (enable == 0 && !out_host) g_trace_ctas = g_trace_ctas;   // buffer kept for later read-back
+  rows_trace_on = enable > 0;
+  return RL_OK;
+}
+namespace rl {
 // true when the env-owned state pointers form the packed RO / RW / WO blocks and every tile is full and aligned
 bool rows_layout_ok(const StepArgs& a) {
   const RlEnvCfg& c = a.cfg;
@@ -513,6 +569,7 @@ int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
   using namespace rows;
   RowsArgs ra;
   ra.a = a;
+  ra.trace = (rows_trace_on && g_trace_buf && a.cfg.num_envs / QT <= g_trace_ctas) ? g_trace_buf : nullptr;
   const RlEnvBuffers& b = a.b;
   const uint64_t N = (uint64_t)a.cfg.num_envs;
   int rc;

@@ -42,6 +42,7 @@ storage_add_kernel(const __grid_constant__ StorageAddArgs a) {
   if (warp >= a.N) return;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
+    if (!a.src[t]) continue;              // rows 0-2 (obs / priv / history) may already be in place: PPO.act stores them
     const float* s = a.src[t] + (size_t)warp * a.ld[t];
     float* d = a.dst[t] + (size_t)warp * a.dim[t];
     for (int c = lane; c < a.dim[t]; c += 32) d[c] = s[c];
@@ -62,7 +63,7 @@ extern "C" int rl_storage_add(const RlStorageAdd* q, void* stream) {
   const int dim[9] = {q->obs_dim, q->priv_dim, q->hist_dim, q->act_dim, q->act_dim, q->act_dim, 1, 1, 1};
   const long long ld[9] = {q->ld_obs, q->ld_priv, q->ld_hist, q->act_dim, q->act_dim, q->act_dim, 1, 1, 1};
   for (int i = 0; i < 9; ++i) {
-    RL_REQUIRE(src[i] && dst[i] && dim[i] > 0 && ld[i] >= dim[i], RL_ERR_BAD_ARG, "rl_storage_add: field %d", i);
+    RL_REQUIRE((src[i] || i < 3) && (dst[i] || !src[i]) && dim[i] > 0 && ld[i] >= dim[i], RL_ERR_BAD_ARG, "rl_storage_add: field %d", i);
     a.src[i] = reinterpret_cast<const float*>(src[i]); a.dst[i] = reinterpret_cast<float*>(dst[i]);
     a.dim[i] = dim[i]; a.ld[i] = ld[i];
   }

@@ -50,7 +50,11 @@ class LeggedRobot:
             terrain = TerrainInfo(cfg.terrain)
         self.terrain = terrain
         sim_dt = None if sim_params is None else getattr(sim_params, "dt", None)
-        p = self.params = freeze_env_cfg(cfg, robot, terrain, sim_dt)
+        # reward plugin surface (legged_robot.py:1074-1093): a scale whose name is not one of the fused terms - or whose
+        # `_reward_<name>` a subclass overrides - is served by that Python method after the fused launch
+        custom = [n for n, sc in public_vars(cfg.rewards.scales).items() if sc != 0 and n != "termination" and
+                  self._is_custom_reward(n)]
+        p = self.params = freeze_env_cfg(cfg, robot, terrain, sim_dt, custom_reward_names=custom)
         if cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
             cfg.terrain.curriculum = False
         self.dt = p.dt_double
@@ -58,6 +62,17 @@ class LeggedRobot:
         self.reward_scales = dict(p.reward_scales)
         self.reward_names = list(p.reward_names)
         self.reward_functions = [getattr(self, "_reward_" + n) for n in self.reward_names]
+        self._custom_terms = list(p.custom_terms)
+        base = LeggedRobot
+        self._hook_overrides = [h for h in ("check_termination", "compute_reward", "compute_observations")
+                                if getattr(type(self), h) is not getattr(base, h)]
+        if type(self)._get_heights is not base._get_heights:
+            raise NotImplementedError("_get_heights is overridden: the height samples feed the fused observation / reward "
+                                      "code inside the kernel, a Python replacement cannot reach them")
+        if "check_termination" in self._hook_overrides and (p.has_termination or "survival" in self.reward_names):
+            raise NotImplementedError("check_termination is overridden while the `termination` / `survival` reward terms "
+                                      "are enabled: those terms are evaluated inside the fused launch from the built-in "
+                                      "termination rule")
         cfg.command_ranges = public_vars(cfg.commands)
         cfg.env.max_episode_length = p.max_episode_length_f
         self.max_episode_length = p.max_episode_length_f
@@ -137,6 +152,10 @@ class LeggedRobot:
         self._command_rows = dict(p.sum_rows, **{n: D["RL_MAX_TERMS"] + 1 + i for i, n in enumerate(COMMAND_SUM_EXTRAS)})
         self.episode_sums = {n: self._episode_sums[r] for n, r in self._episode_rows.items()}
         self.command_sums = {n: self._command_sums[r] for n, r in self._command_rows.items()}
+        for name, _ in self._custom_terms:          # plugin terms keep their accumulators outside the packed rows
+            self.episode_sums[name] = z(N)
+            self.command_sums[name] = z(N)
+        self._rew_raw = z(N) if self._custom_terms else None
         self._episode_sum_out = z(D["RL_MAX_TERMS"] + 3, dtype=torch.float64)
         self.common_step_counter = 0
 
@@ -265,6 +284,7 @@ class LeggedRobot:
         b.height_samples = P(self.height_samples) if self.height_samples is not None else None
         b.noise_u = b.dr_u = b.push_u = None
         b.step_state = None
+        b.rew_raw = P(self._rew_raw)
         return b
 
     def use_device_step_counter(self, enable=True):
@@ -359,6 +379,8 @@ class LeggedRobot:
         host_step = 0 if b.step_state else self.common_step_counter
         _lib.check(self._lib.rl_env_step_fused(C.byref(self._cfg_struct), C.byref(b), self.seed,
                                                host_step, _lib.current_stream()))
+        if self._custom_terms or self._hook_overrides:
+            self._run_plugins()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _compute_torques(self, actions):
@@ -382,6 +404,8 @@ class LeggedRobot:
         host_step = 0 if b.step_state else self.common_step_counter
         _lib.check(self._lib.rl_env_post_physics(C.byref(self._cfg_struct), C.byref(b), self.seed,
                                                  host_step, _lib.current_stream()))
+        if self._custom_terms or self._hook_overrides:
+            self._run_plugins()
 
     def get_observations(self):
         return self.obs_buf
@@ -430,10 +454,17 @@ class LeggedRobot:
         sums = self._episode_sum_out
         means = (sums[:-1] / sums[-1]).to(torch.float)
         self.extras["train/episode"] = {"rew_" + n: means[r] for n, r in self._episode_rows.items()}
+        for name, _ in self._custom_terms:          # plugin accumulators (:264-267)
+            self.extras["train/episode"]["rew_" + name] = torch.mean(self.episode_sums[name][env_ids])
+            self.episode_sums[name][env_ids] = 0.
         if cfg.terrain.curriculum:
             self.extras["train/episode"]["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
         if cfg.commands.command_curriculum:
-            self.extras["env_bins"] = self._env_command_bins[:self.num_train_envs].to(torch.float)
+            # (a persistent buffer rewritten in place: captured rollout graphs keep reading this address)
+            if getattr(self, "_env_bins_f", None) is None:
+                self._env_bins_f = torch.zeros(self.num_envs, device=self.device)
+            self._env_bins_f.copy_(self._env_command_bins)
+            self.extras["env_bins"] = self._env_bins_f[:self.num_train_envs]
             self.extras["train/episode"]["command_area"] = (self.curriculum.weights_device.sum() / len(self.curriculum))
         if cfg.commands.yaw_command_curriculum:
             self.extras["train/episode"]["max_command_yaw"] = cfg.command_ranges["ang_vel_yaw"][1]
@@ -532,8 +563,27 @@ class LeggedRobot:
         from ..sharding import all_reduce_sum_
         all_reduce_sum_(self.curriculum.hit_count, self.curriculum.own_flag)
 
-    # ---- reward plugin surface: names resolve like the reference (:1079-1093); the built-in
-    # terms are evaluated inside the fused kernel, these methods return the last per-term value ----
+    # ------------------------------------------------------------------------------------------
+    # plugin surface of the reference class (legged_robot.py:190, :314, :342, :1074-1093, :1469)
+    # ------------------------------------------------------------------------------------------
+    # The fused launch evaluates the reference's default pipeline.  What a subclass can still do, as with the
+    # reference class:
+    #   * define `_reward_<name>(self)` and give `Cfg.rewards.scales.<name>` a non-zero value: the method runs after
+    #     the launch and its term enters rew_buf / episode_sums / command_sums where compute_reward :320-327 adds it
+    #     (before the positive clip; the kernel hands out the unclipped sum for that);
+    #   * override `check_termination`, `compute_reward`, `compute_observations`: the base methods are the results of
+    #     the launch (already in reset_buf / rew_buf / obs_buf), so the usual `super().check_termination();
+    #     self.reset_buf |= ...` idiom works; overrides run after the launch in the reference's order (:164-180).
+    #   * call `_get_heights()` for the terrain heights under any env (a kernel of its own).
+    def _is_custom_reward(self, name):
+        """True when `_reward_<name>` must run as a Python method: not a fused term, or overridden by a subclass."""
+        meth = getattr(type(self), "_reward_" + name, None)
+        if name not in _lib.REWARD_TERM_IDS:
+            if meth is None:
+                raise AttributeError("'%s' object has no attribute '_reward_%s'" % (type(self).__name__, name))   # :1093
+            return True
+        return meth is not None
+
     def __getattr__(self, name):
         if name.startswith("_reward_"):
             term = name[len("_reward_"):]
@@ -544,6 +594,58 @@ class LeggedRobot:
     def _fused_term(self, term):
         raise NotImplementedError("reward term %r is evaluated inside the fused kernel; per-term values are "
                                   "available through episode_sums / command_sums" % term)
+
+    def check_termination(self):
+        """legged_robot.py:190-202: `reset_buf` (and `time_out_buf`) of the last fused launch."""
+        return self.reset_buf
+
+    def compute_reward(self):
+        """legged_robot.py:314-340: `rew_buf` and the accumulators of the last fused launch (plugin terms included)."""
+        return self.rew_buf
+
+    def compute_observations(self):
+        """legged_robot.py:342-417: `obs_buf` / `privileged_obs_buf` of the last fused launch."""
+        return self.obs_buf
+
+    def _get_heights(self, env_ids=None, cfg=None):
+        """legged_robot.py:1469-1503: terrain heights [n, num_height_points] under the robots (min of three truncated
+        samples per point), from the current root states.  The fused step computes the same values in-kernel."""
+        p = self.params
+        if self.cfg.terrain.mesh_type == "plane" or not p.measure_heights:
+            n = self.num_envs if env_ids is None else len(env_ids)
+            return torch.zeros(n, max(1, p.num_height_points), device=self.device)
+        if self.cfg.terrain.mesh_type == "none":
+            raise NameError("Can't measure height with terrain mesh type 'none'")
+        ids = torch.arange(self.num_envs, device=self.device) if env_ids is None else env_ids.to(self.device, torch.long)
+        out = torch.empty(len(ids), p.num_height_points, device=self.device)
+        _lib.check(self._lib.rl_env_heights(C.byref(self._cfg_struct), _lib.ptr(self.root_states), _lib.ptr(self._height_points_xy),
+                                            _lib.ptr(self.height_samples), _lib.ptr(ids.contiguous()), int(len(ids)),
+                                            _lib.ptr(out), _lib.current_stream()))
+        return out
+
+    def _run_plugins(self):
+        """After the fused launch, in the reference's order (:164-180): termination override, reward plugins, reward
+        override, observation override."""
+        p = self.params
+        if "check_termination" in self._hook_overrides:
+            self.check_termination()
+        if self._custom_terms:
+            raw = self._rew_raw                                   # sum of the fused terms before clip / termination
+            clipped = torch.clip(raw, min=0.) if p.only_positive_rewards else raw
+            after_clip = self.rew_buf - clipped                   # the termination term (:330-334), added after the clip
+            total = raw.clone()
+            for name, scale in self._custom_terms:
+                rew = getattr(self, "_reward_" + name)() * scale
+                total += rew
+                self.episode_sums[name] += rew
+                self.command_sums[name] += rew
+            new = torch.clip(total, min=0.) if p.only_positive_rewards else total
+            self.episode_sums["total"] += new - clipped
+            self.rew_buf.copy_(new + after_clip)
+        if "compute_reward" in self._hook_overrides:
+            self.compute_reward()
+        if "compute_observations" in self._hook_overrides:
+            self.compute_observations()
 
     def close(self):
         pass

@@ -86,7 +86,9 @@ class ActorCritic(nn.Module):
         self.to(self.device_)
         self._flatten()
         self._ws_rows = 0
+        self._ws_gen = 0          # bumped whenever the workspace is reallocated: captured graphs hold its addresses
         self._cache_key = None
+        self._split = None        # (stream, fork event, join event) of forward_teacher's two-launch form
         self._act_step = 0
         self.seed = 0
         # fused MLP chains (csrc/chain.cu): one persistent kernel per network pass instead of one GEMM per layer
@@ -221,6 +223,7 @@ class ActorCritic(nn.Module):
                 w["dH2"], w["dH1"], w["dD2"], w["dD1"] = bf(eh[1]), bf(eh[0]), bf(ah[1]), bf(ah[0])
                 self._ws_bwd = True
             self._ws, self._ws_rows = w, R
+            self._ws_gen += 1
             self._cache_key = None
             self._chains = {}          # chain programs bake the workspace pointers in
         return self._ws
@@ -258,11 +261,28 @@ class ActorCritic(nn.Module):
         self._chain(("adaptation_backward",), chain.adaptation_backward_program)
 
     def prepare_rollout_chains(self, rows):
-        """Workspace + policy chain for `act` / `evaluate` on `rows` envs, compiled ahead of a graph capture."""
+        """Workspace + policy chain(s) for `act` / `evaluate` on `rows` envs, compiled ahead of a graph capture."""
         self.workspace(rows)
         if self.use_chain:
             from . import chain
             self._chain(("teacher", False, True, True), lambda T: chain.teacher_forward_program(T, save=False))
+            if self._split_ok(rows):
+                for wm, wv in ((True, False), (False, True)):
+                    self._chain(("teacher", False, wm, wv),
+                                lambda T, wm=wm, wv=wv: chain.teacher_forward_program(T, save=False, want_mean=wm, want_value=wv))
+                self._split_streams()
+
+    @staticmethod
+    def _split_ok(rows):
+        """Small batches leave most SMs idle (one 128-row tile per CTA, and a tile's pass is a serial chain of layers:
+        ~40 us whatever the batch): the actor and the critic then run as TWO concurrent launches, each with its own
+        encoder pass, on disjoint SMs - 23 us instead of 40 us for 4000 envs.  Worth it while both fit in one wave."""
+        return os.environ.get("RL_CHAIN_SPLIT", "1") != "0" and 2 * ((rows + 127) // 128) <= 148
+
+    def _split_streams(self):
+        if self._split is None:
+            self._split = (torch.cuda.Stream(device=self.device_), torch.cuda.Event(), torch.cuda.Event())
+        return self._split
 
     def _chain(self, key, build):
         prog = self._chains.get(key)
@@ -301,8 +321,20 @@ class ActorCritic(nn.Module):
         """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace."""
         if self.use_chain:
             from . import chain
-            self._chain(("teacher", save, want_mean, want_value),
-                        lambda T: chain.teacher_forward_program(T, save=save, want_mean=want_mean, want_value=want_value)).run(rows)
+            prog = lambda wm, wv: self._chain(("teacher", save, wm, wv), lambda T: chain.teacher_forward_program(
+                T, save=save, want_mean=wm, want_value=wv))
+            if want_mean and want_value and not save and self._split_ok(rows):
+                side, fork, join = self._split_streams()
+                critic, actor = prog(False, True), prog(True, False)      # (compiled before the fork: graph-capture safe)
+                fork.record()
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    critic.run(rows)
+                    join.record()
+                actor.run(rows)
+                torch.cuda.current_stream().wait_event(join)
+                return
+            prog(want_mean, want_value).run(rows)
             return
         self.forward_encoder(rows)
         self._trunk(rows, want_value, want_mean)
@@ -405,7 +437,7 @@ class ActorCritic(nn.Module):
         return self._actions
 
     def get_actions_log_prob(self, actions):
-        if actions is self._actions:
+        if actions is self._actions or (actions.data_ptr() == self._actions.data_ptr() and actions.shape == self._actions.shape):
             return self._logp
         var = self.std ** 2
         return (-((actions - self._mean) ** 2) / (2 * var) - torch.log(self.std) - 0.9189385332046727).sum(dim=-1)

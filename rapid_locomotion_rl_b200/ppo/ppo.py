@@ -113,15 +113,21 @@ class PPO:
         t.actions_log_prob = ac.get_actions_log_prob(t.actions).detach()
         t.action_mean = ac._mu
         t.action_sigma = ac._sigma
-        t.observations = obs
-        t.critic_observations = obs
-        t.privileged_observations = privileged_obs
-        t.observation_histories = obs_history
+        # "need to record obs and critic_obs before env.step()" (ppo.py:69): the reference's env returns NEW tensors every
+        # step, so holding references is enough there.  This env rewrites obs_buf / privileged_obs_buf / the history ring
+        # in place, so the three rows go into their [step] slices of the storage NOW; add_transitions finds them stored.
+        if self.storage is not None:
+            self.storage.store_observations(obs, privileged_obs, obs_history)
+            t.observations = t.critic_observations = t.privileged_observations = t.observation_histories = None
+        else:
+            t.observations = t.critic_observations = obs
+            t.privileged_observations, t.observation_histories = privileged_obs, obs_history
         return t.actions
 
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:76-88."""
         t = self.transition
+        self.actor_critic._cache_key = None      # the env buffers behind the cached pass have been rewritten
         t.rewards = rewards.clone()
         t.dones = dones
         t.env_bins = infos["env_bins"]

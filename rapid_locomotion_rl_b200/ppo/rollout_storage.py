@@ -59,16 +59,32 @@ class RolloutStorage:
         self._gae_ws = torch.zeros(int(self._lib.rl_gae_workspace_bytes(N)) // 8 + 1, dtype=torch.float64, device=dev)
         self._gae_stats = torch.zeros(3, dtype=torch.float64, device=dev)
 
+    def store_observations(self, obs, privileged_obs, obs_history):
+        """Rows of rollout_storage.py:57-60 for the CURRENT step, written when the action is taken (PPO.act): the env's
+        observation buffers are rewritten in place by env.step, before add_transitions runs."""
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        s = self.step
+        self.observations[s].copy_(obs)
+        self.privileged_observations[s].copy_(privileged_obs)
+        self.observation_histories[s].copy_(obs_history)
+        self._obs_stored_step = s
+
     def add_transitions(self, transition):
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
-        if self._fused_add(transition, s):
+        stored = transition.observations is None and getattr(self, "_obs_stored_step", -1) == s
+        if transition.observations is None and not stored:
+            raise AssertionError("transition without observations: call PPO.act (store_observations) first")
+        self._obs_stored_step = -1
+        if self._fused_add(transition, s, stored):
             self.step += 1
             return
-        self.observations[s].copy_(transition.observations)
-        self.privileged_observations[s].copy_(transition.privileged_observations)
-        self.observation_histories[s].copy_(transition.observation_histories)
+        if not stored:
+            self.observations[s].copy_(transition.observations)
+            self.privileged_observations[s].copy_(transition.privileged_observations)
+            self.observation_histories[s].copy_(transition.observation_histories)
         self.actions[s].copy_(transition.actions)
         self.rewards[s].copy_(transition.rewards.view(-1, 1))
         self.dones[s].copy_(transition.dones.view(-1, 1))
@@ -79,19 +95,18 @@ class RolloutStorage:
         self.env_bins[s].copy_(transition.env_bins.view(-1, 1))
         self.step += 1
 
-    def _fused_add(self, t, s):
+    def _fused_add(self, t, s, stored=False):
         """One launch for the eleven per-step copies (csrc/history.cu rl_storage_add).  Falls back to the
         copy_ sequence (still on the device) only for layouts the kernel does not take: non-fp32 sources,
         rows that are not unit-stride."""
         N = self.num_envs
-        f32 = (t.observations, t.privileged_observations, t.observation_histories, t.actions, t.action_mean, t.action_sigma,
-               t.rewards, t.values, t.actions_log_prob, t.env_bins)
+        rows = () if stored else (t.observations, t.privileged_observations, t.observation_histories)
+        f32 = rows + (t.actions, t.action_mean, t.action_sigma, t.rewards, t.values, t.actions_log_prob, t.env_bins)
         if any(x.dtype != torch.float32 or x.device != self.device or x.shape[0] != N for x in f32):
             return False
-        rows = (t.observations, t.privileged_observations, t.observation_histories)
         if any(x.dim() != 2 or x.stride(1) != 1 for x in rows):
             return False
-        small = [x if x.is_contiguous() else x.contiguous() for x in f32[3:]]
+        small = [x if x.is_contiguous() else x.contiguous() for x in f32[len(rows):]]
         dones = t.dones
         if dones.dtype == torch.bool:
             dones = dones.view(torch.uint8)
@@ -99,15 +114,20 @@ class RolloutStorage:
             return False
         q = _lib.RlStorageAdd()
         P = lambda x: x.data_ptr()
-        q.obs, q.priv, q.hist = P(rows[0]), P(rows[1]), P(rows[2])
+        if stored:
+            q.obs = q.priv = q.hist = None
+        else:
+            q.obs, q.priv, q.hist = P(rows[0]), P(rows[1]), P(rows[2])
         q.actions, q.mu, q.sigma, q.rewards, q.values, q.logp, q.bins = (P(x) for x in small)
         q.dones = P(dones)
-        q.dst_obs, q.dst_priv, q.dst_hist = P(self.observations[s]), P(self.privileged_observations[s]), P(self.observation_histories[s])
+        q.dst_obs, q.dst_priv, q.dst_hist = (None, None, None) if stored else \
+            (P(self.observations[s]), P(self.privileged_observations[s]), P(self.observation_histories[s]))
         q.dst_actions, q.dst_mu, q.dst_sigma = P(self.actions[s]), P(self.mu[s]), P(self.sigma[s])
         q.dst_rewards, q.dst_values, q.dst_logp = P(self.rewards[s]), P(self.values[s]), P(self.actions_log_prob[s])
         q.dst_bins, q.dst_dones = P(self.env_bins[s]), P(self.dones[s])
-        q.ld_obs, q.ld_priv, q.ld_hist = rows[0].stride(0), rows[1].stride(0), rows[2].stride(0)
-        q.N, q.obs_dim, q.priv_dim, q.hist_dim, q.act_dim = N, rows[0].shape[1], rows[1].shape[1], rows[2].shape[1], small[0].shape[-1]
+        dims = (self.observations.shape[-1], self.privileged_observations.shape[-1], self.observation_histories.shape[-1])
+        q.ld_obs, q.ld_priv, q.ld_hist = dims if stored else (rows[0].stride(0), rows[1].stride(0), rows[2].stride(0))
+        q.N, q.obs_dim, q.priv_dim, q.hist_dim, q.act_dim = N, dims[0], dims[1], dims[2], small[0].shape[-1]
         import ctypes as C
         self._keep = (small, dones)
         _lib.check(self._lib.rl_storage_add(C.byref(q), _lib.current_stream()))

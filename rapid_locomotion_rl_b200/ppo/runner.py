@@ -36,7 +36,7 @@ class RunnerArgs:
 
 
 class Runner:
-    def __init__(self, env, device="cuda:0", graph_rollout=False, physics=None):
+    def __init__(self, env, device="cuda:0", graph_rollout=False, physics=None, fused_rollout=True):
         """env: HistoryWrapper(VelocityTrackingEasyEnv(...)).  physics: optional callable run after every
         env.step (stands in for the simulator advancing its state tensors; synthetic in the tests)."""
         self.device = device
@@ -52,7 +52,14 @@ class Runner:
         self.last_recording_it = 0
         self.graph_rollout = graph_rollout
         self.physics = physics
-        self._graphs, self._warm = {}, False
+        self._graphs, self._warm, self._graphs_ws_gen = {}, False, -1
+        self.fused_rollout = fused_rollout
+        self._act_buf = self._step_state = self._zero_bins = None
+        self._fused_device_steps = False
+        # test hooks (eager rollouts): standard-normal draws to use instead of the generator ([n, 12] tensor), and a
+        # callable(t, action_buffer, storage_slice_or_None) that may overwrite the actions between the policy and env.step
+        self.inject_normal = None
+        self.action_hook = None
         self.env.reset()
 
     # ------------------------------------------------------------------------------------------------
@@ -61,43 +68,140 @@ class Runner:
         n = self.env.num_train_envs
         alg = self.alg
         for _ in range(self.num_steps_per_env):
-            z = torch.randn(n, self.env.num_actions, device=self.device)         # graph-safe Philox stream
+            z = self.inject_normal if self.inject_normal is not None else \
+                torch.randn(n, self.env.num_actions, device=self.device)         # graph-safe Philox stream
             alg.transition.actions = alg.actor_critic.act(obs[:n], privileged_obs[:n], inject_normal=z).detach()
             alg.transition.values = alg.actor_critic.evaluate(obs[:n], privileged_obs[:n]).detach()
             t = alg.transition
             t.actions_log_prob = alg.actor_critic.get_actions_log_prob(t.actions).detach()
             t.action_mean, t.action_sigma = alg.actor_critic._mu, alg.actor_critic._sigma
-            t.observations, t.critic_observations = obs[:n], obs[:n]
-            t.privileged_observations, t.observation_histories = privileged_obs[:n], obs_history[:n]
+            # (stored now: env.step rewrites these buffers in place - see PPO.act)
+            if self.action_hook is not None:
+                self.action_hook(alg.storage.step, t.actions, None)
+            alg.storage.store_observations(obs[:n], privileged_obs[:n], obs_history[:n])
+            t.observations = t.critic_observations = t.privileged_observations = t.observation_histories = None
             obs_dict, rewards, dones, infos = self.env.step(t.actions)
             if self.physics is not None:
                 self.physics(self.env)
             obs, privileged_obs, obs_history = obs_dict["obs"], obs_dict["privileged_obs"], obs_dict["obs_history"]
-            alg.process_env_step(rewards[:n], dones[:n], {"env_bins": infos["env_bins"]} if "env_bins" in infos else
-                                 {"env_bins": torch.zeros(n, device=self.device)})
+            # the reference passes `infos` through (time_outs feeds the gamma * V bootstrap, ppo.py:81-83); only a
+            # missing env_bins is defaulted
+            step_infos = {"env_bins": infos["env_bins"][:n] if "env_bins" in infos else torch.zeros(n, device=self.device)}
+            if "time_outs" in infos:
+                step_infos["time_outs"] = infos["time_outs"][:n]
+            alg.process_env_step(rewards[:n], dones[:n], step_infos)
         return obs, privileged_obs, obs_history
 
+    # ------------------------------------------------------------------------------------------------
+    def _fused_ok(self):
+        """The fused step glue (csrc/rollout.cu) takes the standard stack: HistoryWrapper over a LeggedRobot whose
+        observation row fits a warp pair, the chain learner, no eval split."""
+        env, ac = self.env, self.alg.actor_critic
+        inner = getattr(env, "env", None)
+        return (self.fused_rollout and inner is not None and hasattr(env, "_ring") and hasattr(inner, "_reset_u8") and
+                ac.use_chain and env.num_obs <= 64 and env.num_privileged_obs <= 32 and env.num_actions == 12 and
+                env.num_train_envs == env.num_envs)
+
+    def _rollout_steps_fused(self, obs, privileged_obs, obs_history):
+        """The same loop as `_rollout_steps` with the per-step glue fused: per step ONE boundary kernel (closes
+        transition t-1: reward / bootstrap / done / bin + history push; opens transition t: obs / priv / history rows
+        into the storage + bf16 staging of the policy inputs), the policy pass, ONE act kernel (Normal sample,
+        log-prob, action / mu / sigma / log-prob / value slices) and the fused env step: 4-5 launches instead of ~25.
+        What lands in the storage is what `_rollout_steps` stores (tests/test_runner_gpu.py)."""
+        import ctypes as C
+        from .. import _lib
+        from .ppo import PPO_Args
+        env, alg = self.env, self.alg
+        inner, ac, st = env.env, alg.actor_critic, alg.storage
+        lib, P = _lib.lib(), _lib.ptr
+        n, T, H, W = env.num_train_envs, self.num_steps_per_env, env.obs_history_length, env.num_obs
+        w = ac.workspace(n)
+        if self._act_buf is None or self._act_buf.shape[0] != n:
+            self._act_buf = torch.zeros(n, env.num_actions, device=self.device)
+            self._step_state = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self._zero_bins = torch.zeros(n, device=self.device)
+        if st.step != 0:
+            raise AssertionError("Rollout buffer overflow")
+
+        def boundary(t_close, t_open):
+            q = _lib.RlRolloutBoundary()
+            q.obs, q.priv, q.ring = P(inner.obs_buf), P(inner.privileged_obs_buf), P(env._ring)
+            q.N, q.obs_dim, q.priv_dim, q.H = n, W, env.num_privileged_obs, H
+            q.gamma = PPO_Args.gamma
+            q.do_post, q.do_pre = int(t_close is not None), int(t_open is not None)
+            if t_close is not None:
+                env._slot = (env._slot + 1) % H
+                q.push_slot = env._slot
+                ex = inner.extras
+                tmo = ex["time_outs"] if "time_outs" in ex else None
+                bins = ex["env_bins"] if "env_bins" in ex else None
+                q.rew, q.dones = P(inner.rew_buf), P(inner._reset_u8)
+                q.time_outs = P(tmo.view(torch.uint8)) if tmo is not None else None
+                q.values_prev = P(st.values[t_close])
+                q.bins = P(bins) if bins is not None else None
+                q.dst_rewards, q.dst_dones, q.dst_bins = P(st.rewards[t_close]), P(st.dones[t_close]), P(st.env_bins[t_close])
+                self._keep = (tmo, bins)
+            if t_open is not None:
+                q.hist_slot = env._slot + 1
+                q.dst_obs, q.dst_priv, q.dst_hist = P(st.observations[t_open]), P(st.privileged_observations[t_open]), \
+                    P(st.observation_histories[t_open])
+                q.Xac, q.ld_xac, q.Xp, q.ld_xp = P(w["Xac"]), w["Xac"].shape[1], P(w["Xp"]), w["Xp"].shape[1]
+            _lib.check(lib.rl_rollout_boundary(C.byref(q), _lib.current_stream()))
+
+        for t in range(T):
+            boundary(t - 1 if t > 0 else None, t)
+            ac.forward_teacher(n)                      # encoder -> actor mean / critic value on the staged rows
+            ac._cache_key = None
+            a = _lib.RlRolloutAct()
+            a.mean, a.value, a.std = P(w["mean"]), P(w["value"]), P(ac.std.data)
+            a.inj_normal, a.actions_out, a.logp_out = P(self.inject_normal), P(self._act_buf), None
+            a.dst_actions, a.dst_mu, a.dst_sigma = P(st.actions[t]), P(st.mu[t]), P(st.sigma[t])
+            a.dst_logp, a.dst_values = P(st.actions_log_prob[t]), P(st.values[t])
+            ac._act_step += 1
+            a.step_state = P(self._step_state) if self._fused_device_steps else None
+            a.seed, a.step, a.N = ac.seed, (0 if self._fused_device_steps else ac._act_step), n
+            _lib.check(lib.rl_rollout_act(C.byref(a), _lib.current_stream()))
+            if self.action_hook is not None:
+                self.action_hook(t, self._act_buf, st.actions[t])
+            inner.step(self._act_buf)
+            if self.physics is not None:
+                self.physics(env)
+        boundary(T - 1, None)
+        st.step = T
+        return inner.obs_buf, inner.privileged_obs_buf, env.obs_history
+
     def _rollout(self, obs, privileged_obs, obs_history):
+        steps = self._rollout_steps_fused if self._fused_ok() else self._rollout_steps
         if not self.graph_rollout:
-            return self._rollout_steps(obs, privileged_obs, obs_history)
+            return steps(obs, privileged_obs, obs_history)
         T = self.num_steps_per_env
         inner = getattr(self.env, "env", self.env)
         if not self._warm:
             # first rollout runs eagerly: it compiles the policy chain and makes every lazy allocation
             self._warm = True
             inner.use_device_step_counter(True)
-            return self._rollout_steps(obs, privileged_obs, obs_history)
+            out = steps(obs, privileged_obs, obs_history)
+            if self._fused_ok():
+                # from here on the act kernel keys its Philox draws with a device-side counter (graph replay freezes
+                # kernel arguments); it continues from the host count
+                self._fused_device_steps = True
+                self._step_state[0] = self.alg.actor_critic._act_step + 1
+            return out
         # The history ring advances T mod H slots per rollout, and the `obs_history` view (an address) and the
         # push slots are frozen inside a graph: one graph per distinct start slot (lcm(T, H) / T of them: 5 for
         # T = 24, H = 15), captured on first use, then replayed round robin.
         key = getattr(self.env, "_slot", 0)
+        ws_gen = getattr(self.alg.actor_critic, "_ws_gen", 0)
+        if ws_gen != self._graphs_ws_gen:        # the learner's workspace moved: the captured addresses are stale
+            self._graphs, self._graphs_ws_gen = {}, ws_gen
         if key not in self._graphs:
             host = (key, inner.common_step_counter, self.alg.actor_critic._act_step)
             self.alg.actor_critic.prepare_rollout_chains(self.env.num_train_envs)
+            self._graphs_ws_gen = getattr(self.alg.actor_critic, "_ws_gen", 0)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                out = self._rollout_steps(obs, privileged_obs, obs_history)
+                out = steps(obs, privileged_obs, obs_history)
             slot_after = getattr(self.env, "_slot", 0)
             # capture ran the Python (host counters moved) but no kernel: rewind, the replay below does the work
             if hasattr(self.env, "_slot"):

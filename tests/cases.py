@@ -36,6 +36,13 @@ def case_cfg_hook(case):
             s.stumble = -0.3
             s.stand_still = -0.1
             s.feet_contact_forces = -0.01
+        if case == "mc_only_lin":                     # legged_robot.py:374-376 (+ its noise columns :914-917)
+            Cfg.env.observe_only_lin_vel = True
+            Cfg.env.num_observations = 42 + 3
+        if case == "mc_only_ang":                     # :370-372; _get_noise_scale_vec has no entry for this block, so the
+            Cfg.env.observe_only_ang_vel = True       # reference only runs it with the observation noise off
+            Cfg.env.num_observations = 42 + 3
+            Cfg.noise.add_noise = False
         if case == "mc_rough":
             Cfg.terrain.num_rows = 2
             Cfg.terrain.num_cols = 2
@@ -44,7 +51,9 @@ def case_cfg_hook(case):
     return hook
 
 
-ENV_CASES = ["mc_flat", "go1", "go1_alt", "mc_rough"]
+# mc_rough_full: BASELINE configs[2] at the shipped terrain size (10 x 20 tiles of 8 m, border as configured: the
+# 1800 x 2600 int16 table); mc_rough is the same on a 2 x 2-tile table
+ENV_CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang"]
 
 
 def build_case(case, num_envs):
@@ -57,13 +66,13 @@ def build_case(case, num_envs):
         C.config_go1(cfg)
     else:
         C.config_mini_cheetah(cfg)
-    if case == "mc_rough":
+    if case.startswith("mc_rough"):
         C.config_rough(cfg)
     case_cfg_hook(case)(cfg)
     cfg.env.num_envs = num_envs
     cfg.env.record_video = False
     hs = None
-    if case == "mc_rough":
+    if case.startswith("mc_rough"):
         probe = C.TerrainInfo(cfg.terrain)
         hs = synthetic_heightfield(probe.tot_rows, probe.tot_cols, seed=3)
     terrain = C.TerrainInfo(cfg.terrain, hs)

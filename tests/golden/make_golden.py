@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
 
-CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "learner"]
+CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout"]
 N_ENVS = 48
 N_STEPS = 3
 
@@ -98,17 +98,20 @@ def gen_env_case(case):
     torch.manual_seed(0)
     torch.set_num_threads(1)
     robot = "go1" if case.startswith("go1") else "mini_cheetah"
-    rough = case == "mc_rough"
+    rough = case.startswith("mc_rough")
     hf = (lambda r, c: psim.synthetic_heightfield(r, c, seed=3)) if rough else None
     env, Cfg = harness.make_reference_env(robot, N_ENVS, rough=rough, height_fn=hf, cfg_hook=case_cfg_hook(case))
     e = env.env
     N, NB = e.num_envs, e.num_bodies
-    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31) if False else {"mc_flat": 11, "go1": 12, "go1_alt": 13, "mc_rough": 14}[case])
+    rng = np.random.default_rng(abs(hash(case)) % (2 ** 31) if False else {"mc_flat": 11, "go1": 12, "go1_alt": 13, "mc_rough": 14, "mc_rough_full": 15, "mc_only_lin": 16, "mc_only_ang": 17}[case])
     t = Cfg.terrain
     span_x, span_y = t.terrain_length * t.num_rows, t.terrain_width * t.num_cols
     out = {}
-    if rough:
+    if rough and case != "mc_rough_full":          # (the full table is 9.4 MB: regenerated from its seed by the tests)
         out["heightsamples"] = e.terrain.heightsamples
+    if rough:
+        out["heightsamples_shape"] = np.array(e.terrain.heightsamples.shape)
+        out["heightsamples_sum"] = np.int64(e.terrain.heightsamples.astype(np.int64).sum())
 
     # ---- randomise the persistent state the step reads -------------------------------------------
     def T(a, dtype=torch.float):
@@ -334,6 +337,90 @@ def gen_learner_case():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_rollout_case():
+    """The rollout loop body of Runner.learn (mini_gym_learn/ppo/__init__.py:126-141) with the reference's own env,
+    wrapper, ActorCritic, PPO and RolloutStorage: PPO.act -> HistoryWrapper.step -> PPO.process_env_step for T steps.
+    The actions fed to the env are a FIXED sequence (so the env side of the transitions can be compared tightly while
+    the policy outputs carry their bf16 tolerance); the simulator state is rewritten before every step (scripted
+    physics); a fixed `time_outs` pattern exercises the gamma * V bootstrap of ppo.py:81-83; observation noise is off
+    and no DOF-property re-draw falls into the window, so nothing is random."""
+    import torch
+    import harness
+    import statekit
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+
+    def hook(Cfg):
+        Cfg.noise.add_noise = False
+    env, Cfg = harness.make_reference_env("mini_cheetah", N_ENVS, cfg_hook=hook)
+    e = env.env
+    N, NB, T_ = e.num_envs, e.num_bodies, 6
+    from cases import learner_weights
+    from mini_gym_learn.ppo import ActorCritic
+    from mini_gym_learn.ppo.ppo import PPO
+    ac = ActorCritic(42, 18, 630, 12)
+    ac.load_state_dict({k: torch.from_numpy(v) for k, v in learner_weights().items()})
+    ppo = PPO(ac, device="cpu")
+    ppo.init_storage(N, T_, [42], [18], [630], [12])
+    rng = np.random.default_rng(31)
+    T = lambda a, dt=torch.float: torch.from_numpy(np.asarray(a)).to(dt)
+    out = {}
+    # ---- persistent state, observation buffers and history at the start of the rollout ----
+    e.commands[:, :3] = T(rng.uniform(-1, 1, (N, 3)).astype(np.float32))
+    e.last_actions[:] = T(rng.normal(0, 1, (N, 12)).astype(np.float32))
+    e.last_dof_vel[:] = T(rng.normal(0, 3, (N, 12)).astype(np.float32))
+    e.motor_strengths[:] = T(rng.uniform(0.9, 1.1, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.friction_coeffs[:] = T(rng.uniform(0.05, 4.5, N).astype(np.float32))
+    e.restitutions[:] = T(rng.uniform(0, 1, N).astype(np.float32))
+    e.payloads[:] = T(rng.uniform(-1, 3, N).astype(np.float32))
+    e.com_displacements[:] = T(rng.uniform(-0.1, 0.1, (N, 3)).astype(np.float32))
+    e.feet_air_time[:] = T((rng.uniform(0, 0.6, (N, 4)) * (rng.random((N, 4)) < 0.7)).astype(np.float32))
+    e.last_contacts = T(rng.random((N, 4)) < 0.3, torch.bool)
+    e.episode_length_buf[:] = T(rng.integers(0, 200, N), torch.long)
+    for k in e.episode_sums:
+        e.episode_sums[k][:] = 0.
+    for k in e.command_sums:
+        e.command_sums[k][:] = 0.
+    e.obs_buf[:] = T(rng.normal(0, 1, (N, 42)).astype(np.float32))
+    e.privileged_obs_buf[:] = T(rng.uniform(-1, 1, (N, 18)).astype(np.float32))
+    env.obs_history[:] = 0.
+    for k, v in statekit.state_from_reference(e).items():
+        out["before/" + k] = v
+    out["before/obs_buf"] = e.obs_buf.numpy().copy(); out["before/privileged_obs_buf"] = e.privileged_obs_buf.numpy().copy()
+    time_outs = T(np.arange(N) % 5 == 0, torch.bool)
+    bins = T(rng.integers(0, 5202, N).astype(np.float32))
+    out["time_outs"] = time_outs.numpy(); out["env_bins"] = bins.numpy()
+    t = Cfg.terrain
+    span_x, span_y = t.terrain_length * t.num_rows, t.terrain_width * t.num_cols
+    feet = e.feet_indices.tolist(); term = e.termination_contact_indices.tolist()
+    dflt = e.default_dof_pos[0].numpy()
+    real_normal = torch.normal
+    torch.normal = lambda mean, std, *a, **k: mean.clone() if torch.is_tensor(mean) else real_normal(mean, std, *a, **k)
+    try:
+        od = env.get_observations()
+        for s_ in range(T_):
+            root, dof, con, actions = synth_inputs(rng, e, N, NB, dflt, feet, term, span_x, span_y, 0.30)
+            root[:, 0] = np.clip(root[:, 0], 3.0, span_x - 3.0); root[:, 1] = np.clip(root[:, 1], 3.0, span_y - 3.0)   # no teleport
+            e.all_root_states[:] = T(root); e.all_dof_state[:] = T(dof.reshape(-1, 2)); e.all_contact_forces[:] = T(con.reshape(-1, 3))
+            out["step%d/root_states" % s_] = root; out["step%d/dof_state" % s_] = dof
+            out["step%d/contact_forces" % s_] = con; out["step%d/actions" % s_] = actions
+            with torch.inference_mode():
+                ppo.act(od["obs"], od["privileged_obs"], od["obs_history"])
+                ppo.transition.actions = T(actions)                       # the fixed sequence replaces the sample
+                od, rew, done, infos = env.step(T(actions))
+                ppo.process_env_step(rew, done, {"env_bins": bins, "time_outs": time_outs})
+    finally:
+        torch.normal = real_normal
+    st = ppo.storage
+    for name in ("observations", "privileged_observations", "observation_histories", "actions", "rewards", "dones", "values",
+                 "actions_log_prob", "mu", "sigma", "env_bins"):
+        out["storage/" + name] = getattr(st, name).numpy().copy()
+    out["final/obs"] = od["obs"].numpy().copy(); out["final/obs_history"] = od["obs_history"].numpy().copy()
+    path = os.path.join(HERE, "rollout.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or None
     if which is None:
@@ -343,5 +430,7 @@ if __name__ == "__main__":
         for c in which:
             if c == "learner":
                 gen_learner_case()
+            elif c == "rollout":
+                gen_rollout_case()
             else:
                 gen_env_case(c)

@@ -155,8 +155,35 @@ def test_update_vs_golden(golden_dir):
     assert abs(res[0] - ref[0]) <= 5e-2 * abs(ref[0]) + 1e-3, (res, ref)
     assert abs(res[1] - ref[1]) <= 5e-2 * abs(ref[1]) + 2e-3, (res, ref)
     assert abs(res[2] - ref[2]) <= 5e-2 * abs(ref[2]) + 1e-4, (res, ref)
-    assert abs(ppo.learning_rate - float(g["ppo/final_lr"])) <= 1e-9 + 0.34 * float(g["ppo/final_lr"]), ppo.learning_rate
+    # KL-adaptive learning rate (ppo.py:116-124): the same schedule step for step - every one of the 20 KL tests must
+    # fall on the reference's side, so the final value is the reference's up to fp32 rounding of the 1.5x factors
+    ref_lr = float(g["ppo/final_lr"])
+    assert abs(ppo.learning_rate - ref_lr) <= 1e-6 * ref_lr, (ppo.learning_rate, ref_lr)
     assert ppo.storage.step == 0
+    # final weights against the reference's (ppo/final_digest/*: sum, abs-sum and 64 strided samples per tensor).
+    # Stated tolerance for bf16 operands behind Adam: what is compared is the UPDATE dw = w_final - w_init on the
+    # sampled entries of all tensors together (1565 of them; the reference moves them by up to 1.9e-2) - cosine >= 0.999,
+    # median |dw - dw_ref| <= 5e-5, max <= 6e-3 (an Adam step is lr * m / sqrt(v): where the gradient is near zero its
+    # sign, and with it a full lr-sized step, depends on bf16 rounding); the per-tensor sums must agree as stated below.
+    from cases import learner_weights, tensor_digest
+    init_w = learner_weights()
+    dw, dw_ref = [], []
+    for k, v in ac.state_dict().items():
+        if k.startswith("encoder."):
+            continue
+        ref = g["ppo/final_digest/" + k]
+        got = tensor_digest(v.detach().cpu().numpy())
+        start = tensor_digest(init_w[k])
+        dw.append(got[2:] - start[2:]); dw_ref.append(ref[2:] - start[2:])
+        n = v.numel()
+        assert abs(got[0] - ref[0]) <= 2e-2 * ref[1] / n * n ** 0.5 + 1e-3 * n ** 0.5, (k, got[0], ref[0])
+        assert abs(got[1] - ref[1]) <= 2e-3 * ref[1] + 1e-3, (k, got[1], ref[1])
+    dw, dw_ref = np.concatenate(dw), np.concatenate(dw_ref)
+    cos = float(dw @ dw_ref / (np.linalg.norm(dw) * np.linalg.norm(dw_ref) + 1e-30))
+    print("final-weight update vs reference: cosine %.4f, max |diff| %.2e, |dw_ref| max %.2e" %
+          (cos, np.abs(dw - dw_ref).max(), np.abs(dw_ref).max()))
+    assert cos >= 0.999 and np.abs(dw - dw_ref).max() <= 6e-3 and np.median(np.abs(dw - dw_ref)) <= 5e-5, \
+        (cos, np.abs(dw - dw_ref).max(), np.median(np.abs(dw - dw_ref)))
     # the weights moved, stayed finite, and the bf16 shadows follow the fp32 masters
     assert torch.isfinite(ac.flat).all()
     L = ac.L_act[0]
@@ -215,3 +242,80 @@ def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeyp
     assert d <= 4e-4, d                                  # 40 Adam steps of |dw| <= lr = 1e-3 each
     np.testing.assert_allclose(out["lagged"][1], out["serial"][1], rtol=5e-3, atol=1e-6)
     assert abs(out["lagged"][2] - out["serial"][2]) <= 1e-12
+
+
+def _synthetic_rollout(n_envs, T, seed):
+    """Flattened [T*N, .] storage tensors with the statistics of a real rollout (actions drawn around the old policy)."""
+    g = torch.Generator().manual_seed(seed)
+    B = n_envs * T
+    r = lambda *s: torch.randn(*s, generator=g)
+    st = dict(obs=r(B, 42), priv=torch.rand(B, 18, generator=g) * 2 - 1, hist=r(B, 630) * 0.5, old_mu=r(B, 12) * 0.3,
+              old_sigma=torch.ones(B, 12), values=r(B, 1) * 0.5, returns=r(B, 1) * 0.5, advantages=r(B, 1))
+    st["actions"] = st["old_mu"] + r(B, 12)
+    st["old_logp"] = ppo_oracle.normal_log_prob(st["actions"], st["old_mu"], st["old_sigma"]).sum(-1, keepdim=True)
+    return st
+
+
+def test_minibatch_gradients_vs_oracle_at_c1_size(learner_path):
+    """BASELINE configs[0] size: one minibatch of 24000 rows (4000 envs x 24 / 4) - 188 row tiles, two waves of the
+    persistent chains, multi-item persistent wgrad - against fp32 autograd on the same rows: loss statistics and every
+    gradient tensor, same tolerance as the 256-row case."""
+    from rapid_locomotion_rl_b200.ppo import PPO
+    n_envs, T = 4000, 24
+    storage = _synthetic_rollout(n_envs, T, 11)
+    ac, sd = make_ac()
+    ppo = PPO(ac, device=DEV)
+    ppo.init_storage(n_envs, T, [42], [18], [630], [12])
+    _load_storage(ppo, storage, n_envs, T)
+    idx = torch.randperm(n_envs * T, generator=torch.Generator().manual_seed(3))[:24000]
+    o = ppo_oracle.PPOOracle({k: v.float() for k, v in sd.items()})
+    surr, vloss, aloss, kl = o.step({k: v[idx] for k, v in storage.items()})
+    ppo.debug_keep_grad = True
+    offsets = {k: (v.data_ptr() - ac.flat_grad.data_ptr()) // 4 for k, v in _grad_views(ac).items()}
+    ppo.minibatch_step(idx.to(DEV))
+    torch.cuda.synchronize()
+    stats = (ppo.debug_stats / 24000).tolist()
+    assert abs(stats[0] - surr) <= 3e-2 * abs(surr) + 1e-3, (stats[0], surr)
+    assert abs(stats[1] - vloss) <= 3e-2 * abs(vloss) + 1e-3, (stats[1], vloss)
+    assert abs(stats[2] - kl) <= 5e-2 * abs(kl) + 1e-3, (stats[2], kl)
+    assert abs(stats[3] / 18 - aloss) <= 3e-2 * abs(aloss) + 1e-4, (stats[3] / 18, aloss)
+    flat = ppo.debug_grad.cpu()
+    for k in ppo_oracle.PARAM_ORDER:
+        ref = o.last_adapt_grads[k] if k.startswith("adaptation_module") else o.last_grads[k]
+        got = flat[offsets[k]:offsets[k] + ref.numel()].view(ref.shape)
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+        rel = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+        assert cos >= 0.995 and rel <= 8e-2, "%s: cosine %.5f rel L2 %.4f" % (k, cos, rel)
+
+
+def test_forward_and_loss_vs_oracle_at_c5_size(learner_path):
+    """BASELINE configs[4] size: a 196608-row minibatch (32768 envs x 24 / 4) through the 2.3 GB workspace - network
+    outputs on a strided sample of rows, the loss statistics, and the output-layer gradients against the fp32 oracle
+    evaluated on the same rows (the oracle's forward over all rows takes a few seconds of CPU)."""
+    from rapid_locomotion_rl_b200.ppo import PPO
+    n_envs, T = 32768, 6                          # 196608 rows in the storage = exactly one minibatch of the C5 size
+    storage = _synthetic_rollout(n_envs, T, 12)
+    ac, sd = make_ac()
+    ppo = PPO(ac, device=DEV)
+    ppo.init_storage(n_envs, T, [42], [18], [630], [12])
+    _load_storage(ppo, storage, n_envs, T)
+    B = 196608
+    idx = torch.randperm(n_envs * T, generator=torch.Generator().manual_seed(4))[:B]
+    p = {k: v.float() for k, v in sd.items()}
+    mb = {k: v[idx] for k, v in storage.items()}
+    with torch.no_grad():
+        _, surr, vloss, kl = ppo_oracle.minibatch_losses(p, mb)
+        mean_ref, val_ref = ppo_oracle.actor_mean(p, mb["obs"], mb["priv"]), ppo_oracle.critic_value(p, mb["obs"], mb["priv"])
+    ppo.debug_keep_grad = True
+    ppo.minibatch_step(idx.to(DEV))
+    torch.cuda.synchronize()
+    w = ac._ws
+    sel = torch.arange(0, B, 97)
+    torch.testing.assert_close(w["mean"][:B].cpu()[sel], mean_ref[sel], rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(w["value"][:B].cpu()[sel], val_ref[sel], rtol=2e-2, atol=2e-2)
+    assert torch.nn.functional.cosine_similarity(w["mean"][:B].cpu().flatten(), mean_ref.flatten(), dim=0) > 0.999
+    stats = (ppo.debug_stats / B).tolist()
+    assert abs(stats[0] - surr.item()) <= 3e-2 * abs(surr.item()) + 1e-3, (stats[0], surr.item())
+    assert abs(stats[1] - vloss.item()) <= 3e-2 * abs(vloss.item()) + 1e-3, (stats[1], vloss.item())
+    assert abs(stats[2] - kl.item()) <= 5e-2 * abs(kl.item()) + 1e-3, (stats[2], kl.item())
+    assert torch.isfinite(ppo.debug_grad).all() and float(ppo.debug_grad.abs().max()) > 0
