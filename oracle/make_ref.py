@@ -20,10 +20,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
 SRC = os.environ.get("RL_REFERENCE_ROOT", "/root/reference")
 PACKAGES = ("mini_gym", "mini_gym_learn")
+CHECKPOINT = "runs/rapid-locomotion/example/train/201852.132488/checkpoints/ac_weights_last.pt"
 
 
 def staged():
-    return all(os.path.isdir(os.path.join(DEST, p)) for p in PACKAGES + ("resources",))
+    return all(os.path.isdir(os.path.join(DEST, p)) for p in PACKAGES + ("resources",)) and \
+        os.path.isfile(os.path.join(DEST, CHECKPOINT))
 
 
 def make(force=False):
@@ -44,6 +46,12 @@ def make(force=False):
                 out = os.path.join(DEST, os.path.relpath(dirpath, SRC))
                 os.makedirs(out, exist_ok=True)
                 shutil.copy(os.path.join(dirpath, f), out)
+    # the trained example policy the reference ships (runs/.../checkpoints/ac_weights_last.pt, 2.4 MB of weights): the
+    # checkpoint-compatibility test loads it into the product ActorCritic
+    ck = os.path.join(SRC, CHECKPOINT)
+    if os.path.isfile(ck):
+        os.makedirs(os.path.dirname(os.path.join(DEST, CHECKPOINT)), exist_ok=True)
+        shutil.copy(ck, os.path.join(DEST, CHECKPOINT))
     return DEST
 
 

@@ -364,12 +364,22 @@ class LeggedRobot:
         return io["obs"], io["priv"], io["rew"], io["reset"]
 
     def step(self, actions):
-        """legged_robot.py:106-137.  One fused launch: torques + post-physics pipeline."""
+        """legged_robot.py:106-137.  Synthetic simulator state: one fused launch (torques + post-physics pipeline).
+        Live simulator (`GymApiSim`): the reference's loop - `decimation` x [torque kernel -> physics sub-step] ->
+        refresh -> one post-physics launch."""
         actions = actions.to(self.device, torch.float)
         if not actions.is_contiguous():
             actions = actions.contiguous()
         if actions.shape != (self.num_envs, self.num_actions):
             raise ValueError("actions must be [%d, %d], got %s" % (self.num_envs, self.num_actions, tuple(actions.shape)))
+        if getattr(self.sim, "live", False):
+            for _ in range(self.cfg.control.decimation):                       # :116-126
+                self.sim.apply_torques_and_step(self._compute_torques(actions))
+            self.sim.refresh()                                                 # :143-146, :156, :165-170
+            self.post_physics_step(actions)
+            if self._moved_roots():                                            # teleport / push wrote root rows (:789, :765)
+                self.sim.push_root_state(torch.arange(self.num_envs, device=self.device))
+            return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
         self._actions_in = actions
         self.common_step_counter += 1
         b = self._bufs
@@ -382,6 +392,11 @@ class LeggedRobot:
         if self._custom_terms or self._hook_overrides:
             self._run_plugins()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _moved_roots(self):
+        """True when the step may have rewritten root rows that a live simulator must be told about."""
+        p = self.params
+        return bool(p.teleport_robots or p.push_robots)
 
     def _compute_torques(self, actions):
         """legged_robot.py:653-688 as a standalone launch (the entry a real simulator loop calls
@@ -449,6 +464,10 @@ class LeggedRobot:
         b.dr_u = P(inj.get("reset_dr_u")); b.init_u = P(inj.get("init_u")); b.level_u = P(inj.get("level_u"))
         _lib.check(self._lib.rl_env_reset(C.byref(rc), C.byref(b), self.seed, self.common_step_counter,
                                           _lib.current_stream()))
+        if getattr(self.sim, "live", False):
+            # hand the rewritten rows to the simulator: int32 actor ids of the reset envs (:713-717, :739-741)
+            self.sim.push_dof_state(env_ids)
+            self.sim.push_root_state(env_ids)
         # extras (:261-290): device-side means, no host sync
         p = self.params
         sums = self._episode_sum_out

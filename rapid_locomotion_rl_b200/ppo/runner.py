@@ -21,6 +21,39 @@ from .actor_critic import ActorCritic
 from .ppo import PPO
 
 
+def export_policy(actor_critic, directory, iteration=0):
+    """The files the reference's Runner writes every `save_interval` iterations and at the end of learn()
+    (mini_gym_learn/ppo/__init__.py:222-242, :248-265), under `directory`/checkpoints/:
+        ac_weights_{iteration:06d}.pt, ac_weights_last.pt   the state_dict (35 keys, loadable by the reference class)
+        adaptation_module_latest.jit, body_latest.jit       TorchScript of the adaptation module and the actor body on
+                                                             the CPU - what scripts/play.py and the robot deploy.
+    (The reference uploads them through ml_logger; here they are plain files.)  Returns the paths."""
+    import os
+
+    import torch.nn as nn
+    ck = os.path.join(directory, "checkpoints")
+    os.makedirs(ck, exist_ok=True)
+    sd = {k: v.detach().cpu().clone() for k, v in actor_critic.state_dict().items()}
+    paths = [os.path.join(ck, "ac_weights_%06d.pt" % iteration), os.path.join(ck, "ac_weights_last.pt")]
+    for p_ in paths:
+        torch.save(sd, p_)
+
+    def fresh(prefix, seq):
+        # an ordinary fp32 module with its own storage (the live parameters are views of one flat device buffer)
+        layers = []
+        for m in seq:
+            layers.append(nn.Linear(m.in_features, m.out_features) if isinstance(m, nn.Linear) else nn.ELU())
+        mod = nn.Sequential(*layers)
+        mod.load_state_dict({k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")})
+        return mod.eval()
+    for name, prefix, seq in (("adaptation_module_latest.jit", "adaptation_module", actor_critic.adaptation_module),
+                              ("body_latest.jit", "actor_body", actor_critic.actor_body)):
+        path = os.path.join(ck, name)
+        torch.jit.script(fresh(prefix, seq)).save(path)
+        paths.append(path)
+    return paths
+
+
 class RunnerArgs:
     """mini_gym_learn/ppo/__init__.py:47-62."""
     algorithm_class_name = "PPO"
@@ -218,9 +251,11 @@ class Runner:
         return out
 
     # ------------------------------------------------------------------------------------------------
-    def learn(self, num_learning_iterations, init_at_random_ep_len=False, eval_freq=100, eval_expert=False, log=None):
-        """mini_gym_learn/ppo/__init__.py:92-265 without the logger / checkpoint plumbing.  Returns the list
-        of per-iteration dicts that `log` (if given) also receives."""
+    def learn(self, num_learning_iterations, init_at_random_ep_len=False, eval_freq=100, eval_expert=False, log=None,
+              save_dir=None):
+        """mini_gym_learn/ppo/__init__.py:92-265 without the logger plumbing.  Returns the list of per-iteration dicts
+        that `log` (if given) also receives.  save_dir: write the reference's checkpoint / TorchScript files there every
+        RunnerArgs.save_interval iterations and at the end (export_policy)."""
         env = self.env
         if init_at_random_ep_len:
             env.episode_length_buf.copy_(torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length)))
@@ -243,7 +278,11 @@ class Runner:
             history.append(rec)
             if log is not None:
                 log(rec)
+            if save_dir is not None and it % RunnerArgs.save_interval == 0:
+                export_policy(self.alg.actor_critic, save_dir, it)
         self.current_learning_iteration += num_learning_iterations
+        if save_dir is not None and num_learning_iterations > 0:
+            export_policy(self.alg.actor_critic, save_dir, it)
         return history
 
     def get_inference_policy(self, device=None):

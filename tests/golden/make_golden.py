@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
 
-CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout"]
+CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout", "checkpoint", "curriculum_uniform"]
 N_ENVS = 48
 N_STEPS = 3
 
@@ -421,6 +421,83 @@ def gen_rollout_case():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_checkpoint_case():
+    """The trained policy the reference ships (runs/rapid-locomotion/example/train/201852.132488/checkpoints/
+    ac_weights_last.pt) through the reference's own ActorCritic: teacher / student actions and values on a seeded batch
+    (actor_critic.py:149-173), and the composition scripts/play.py deploys (body(cat(obs, adaptation_module(hist))))."""
+    import torch
+    import harness
+    harness.install()
+    import isaacgym  # noqa: F401  (fake)
+    from mini_gym_learn.ppo import ActorCritic
+    from cases import tensor_digest
+    path = os.path.join(harness.REFERENCE_ROOT, "runs/rapid-locomotion/example/train/201852.132488/checkpoints/ac_weights_last.pt")
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    ac = ActorCritic(42, 18, 630, 12)
+    ac.load_state_dict(sd)
+    ac.eval()
+    g = torch.Generator().manual_seed(5)
+    n = 512
+    obs, priv, hist = torch.randn(n, 42, generator=g), torch.rand(n, 18, generator=g) * 2 - 1, torch.randn(n, 630, generator=g) * 0.5
+    out = {"input_digest": np.concatenate([tensor_digest(x.numpy()) for x in (obs, priv, hist)])}    # inputs come from the seed
+    with torch.no_grad():
+        out["act_teacher"] = ac.act_teacher(obs, priv).numpy()
+        out["act_student"] = ac.act_student(obs, hist).numpy()
+        out["evaluate"] = ac.evaluate(obs, priv).numpy()
+        out["act_inference"] = ac.act_inference({"obs": obs, "obs_history": hist, "privileged_obs": priv}).numpy()
+        out["latent_student"] = ac.adaptation_module(hist).numpy()
+    for k, v in sd.items():
+        out["digest/" + k] = tensor_digest(v.numpy())
+    out["std"] = sd["std"].numpy()
+    path = os.path.join(HERE, "checkpoint.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def gen_curriculum_uniform_case():
+    """_update_command_curriculum_uniform (legged_robot.py:851-880; called from reset_idx :827): the command ranges widen by
+    0.2 per call while the mean tracking reward of the reset envs clears the threshold, only on steps that are multiples
+    of max_episode_length, clipped at the configured maxima.  A scripted sequence of calls; the ranges after every call
+    are the known answers."""
+    import torch
+    import harness
+
+    def hook(Cfg):
+        Cfg.commands.command_curriculum = True
+        Cfg.commands.yaw_command_curriculum = True
+        Cfg.commands.max_forward_curriculum = 1.5
+        Cfg.commands.max_reverse_curriculum = 0.5
+        Cfg.commands.max_yaw_curriculum = 1.3
+    env, Cfg = harness.make_reference_env("mini_cheetah", N_ENVS, cfg_hook=hook, history=False)
+    e = env
+    N = e.num_envs
+    rng = np.random.default_rng(41)
+    L = float(e.cfg.env.max_episode_length)
+    lin_thr = Cfg.commands.forward_curriculum_threshold * e.reward_scales["tracking_lin_vel"]
+    ang_thr = Cfg.commands.yaw_curriculum_threshold * e.reward_scales["tracking_ang_vel"]
+    out = {"max_episode_length": np.float64(L), "lin_threshold": np.float64(lin_thr), "ang_threshold": np.float64(ang_thr)}
+    out["ranges0"] = np.array([Cfg.command_ranges["lin_vel_x"], Cfg.command_ranges["ang_vel_yaw"]], dtype=np.float64)
+    script = []
+    # (step counter multiple?, lin factor of threshold, ang factor): 12 calls
+    plan = [(1, 1.3, 0.7), (0, 1.5, 1.5), (2, 1.2, 1.4), (3, 0.9, 1.2), (4, 1.1, 0.9), (5, 1.4, 1.6), (6, 1.05, 1.05), (7, 2.0, 2.0),
+            (8, 1.5, 1.5), (9, 1.5, 1.5), (10, 1.5, 1.5), (11, 0.5, 1.5)]
+    for i, (mult, lf, af) in enumerate(plan):
+        ids = np.sort(rng.choice(N, N // 2, replace=False))
+        lin = (rng.uniform(0.9, 1.1, N) * lf * lin_thr * L).astype(np.float32)
+        ang = (rng.uniform(0.9, 1.1, N) * af * ang_thr * L).astype(np.float32)
+        e.episode_sums["tracking_lin_vel"][:] = torch.from_numpy(lin)
+        e.episode_sums["tracking_ang_vel"][:] = torch.from_numpy(ang)
+        e.common_step_counter = int(mult * L) if mult else int(3 * L) + 7
+        e._update_command_curriculum_uniform(torch.from_numpy(ids), e.cfg, e.episode_sums)
+        out["call%d/ids" % i] = ids; out["call%d/lin" % i] = lin; out["call%d/ang" % i] = ang
+        out["call%d/step" % i] = np.int64(e.common_step_counter)
+        out["call%d/ranges" % i] = np.array([Cfg.command_ranges["lin_vel_x"], Cfg.command_ranges["ang_vel_yaw"]], dtype=np.float64)
+    out["n_calls"] = np.int64(len(plan))
+    path = os.path.join(HERE, "curriculum_uniform.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), out["ranges0"].tolist(), "->", out["call%d/ranges" % (len(plan) - 1)].tolist())
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or None
     if which is None:
@@ -432,5 +509,9 @@ if __name__ == "__main__":
                 gen_learner_case()
             elif c == "rollout":
                 gen_rollout_case()
+            elif c == "checkpoint":
+                gen_checkpoint_case()
+            elif c == "curriculum_uniform":
+                gen_curriculum_uniform_case()
             else:
                 gen_env_case(c)

@@ -87,7 +87,8 @@ def random_persistent_state(rng, n, sum_names):
     return s
 
 
-@pytest.mark.parametrize("case,n", [("mc_flat", 4000), ("go1", 4133), ("mc_rough", 1000), ("go1_alt", 777)])
+@pytest.mark.parametrize("case,n", [("mc_flat", 4000), ("go1", 4133), ("mc_rough", 1000), ("go1_alt", 777),
+                                    ("mc_rough_full", 4000), ("mc_only_lin", 515)])
 def test_step_vs_oracle_at_size(case, n):
     """Same seeded inputs through the pinned oracle (CPU fp32) and the kernel, two consecutive steps."""
     from oracle.env_oracle import OracleEnv
@@ -119,7 +120,7 @@ def test_step_vs_oracle_at_size(case, n):
         check_step(env, obs, priv, rew, reset, oo.numpy(), op.numpy(), orr.numpy(), ors.numpy(), "%s n=%d step %d" % (case, n, step))
         want = statekit.state_from_oracle(o)
         statekit.assert_state_close(statekit.state_from_product(env), want, RTOL, ATOL, label="%s n=%d" % (case, n))
-        if case == "mc_rough":
+        if case.startswith("mc_rough"):
             assert np.array_equal(env.measured_heights.cpu().numpy(), o.measured_heights.numpy()), "heights are exact"
         st = want  # carry the state into the next step
 
@@ -405,3 +406,25 @@ def test_rows_kernel_matches_quad_kernel(case, n):
             assert torch.equal(a, b), "step %d %s: %s" % (s, names[i], where(a.cpu().numpy(), b.cpu().numpy()))
     for k in sa:
         assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), "state %r: %s" % (k, where(sa[k], sb[k]))
+
+
+def test_uniform_command_curriculum_vs_golden(golden_dir):
+    """_update_command_curriculum_uniform (legged_robot.py:851-880) against the reference's recorded ranges: twelve
+    scripted calls (on / off the max_episode_length step, above / below the thresholds, up to the clip)."""
+    g = np.load(os.path.join(golden_dir, "curriculum_uniform.npz"))
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    cfg, robot, terrain = build_case("mc_flat", 48)
+    c = cfg.commands
+    c.command_curriculum, c.yaw_command_curriculum = True, True
+    c.max_forward_curriculum, c.max_reverse_curriculum, c.max_yaw_curriculum = 1.5, 0.5, 1.3
+    env = LeggedRobot(cfg, sim_device=DEV, headless=True, terrain=terrain)
+    assert env.max_episode_length == float(g["max_episode_length"])
+    r = cfg.command_ranges
+    assert [list(r["lin_vel_x"]), list(r["ang_vel_yaw"])] == g["ranges0"].tolist()
+    for i in range(int(g["n_calls"])):
+        env.episode_sums["tracking_lin_vel"].copy_(cu(g["call%d/lin" % i]))
+        env.episode_sums["tracking_ang_vel"].copy_(cu(g["call%d/ang" % i]))
+        env.common_step_counter = int(g["call%d/step" % i])
+        env._update_command_curriculum_uniform(cu(g["call%d/ids" % i]))
+        got = [[float(x) for x in r["lin_vel_x"]], [float(x) for x in r["ang_vel_yaw"]]]
+        assert np.allclose(got, g["call%d/ranges" % i], rtol=0, atol=1e-12), (i, got, g["call%d/ranges" % i].tolist())
