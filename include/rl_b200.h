@@ -521,6 +521,9 @@ typedef struct RlChainDesc {
 int rl_chain_create(const RlChainDesc* desc_host, void** handle);
 /* Runs the chain over rows [0, rows) (tiles of 128; rows may be any value up to the tensors' extent). */
 int rl_chain_run(void* handle, int32_t rows, void* stream);
+/* the same for the row tiles [tile_begin, tile_end) of the batch only (128 rows per tile): lets the caller pipeline
+ * chunks of a batch through dependent passes on different streams */
+int rl_chain_run_tiles(void* handle, int32_t rows, int32_t tile_begin, int32_t tile_end, void* stream);
 int rl_chain_destroy(void* handle);
 /* Profiling aid: record per-op clock64 stamps of CTA 0 during its tile iteration `tile_iteration` (< 0: off):
  * 1 stamp per LOAD op, 2 per MMA op (waits passed, commits issued), 5 per EPI op (start, accumulator ready,

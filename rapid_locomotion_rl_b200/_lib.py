@@ -129,6 +129,7 @@ SIGNATURES = {
     "rl_wgrad_grouped": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_create": (C.c_int, [_P, _P]),
     "rl_chain_run": (C.c_int, [_P, C.c_int32, _P]),
+    "rl_chain_run_tiles": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_chain_destroy": (C.c_int, [_P]),
     "rl_chain_trace": (C.c_int, [_P, C.c_int32]),
     "rl_chain_read_trace": (C.c_int64, [_P, _P, C.c_int64]),

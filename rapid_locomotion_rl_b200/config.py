@@ -299,7 +299,7 @@ COMMAND_SUM_EXTRAS = ["lin_vel_raw", "ang_vel_raw", "lin_vel_residual", "ang_vel
 
 
 def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, sim_dt=None,
-                   custom_reward_names=()):
+                   custom_reward_names=(), upstream_order=False):
     """Resolve a Cfg tree into EnvParams.
 
     Follows legged_robot.py _parse_cfg :1417-1429 (dt is decimation * float32(sim.dt); the
@@ -497,7 +497,7 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     p.Kd_factor_lo_span = lo_span(dr.Kd_factor_range)
     p.push_robots = int(bool(dr.push_robots))
     p.push_lo_span = [f32(-dr.max_push_vel_xy), f32(dr.max_push_vel_xy - (-dr.max_push_vel_xy))]
-    p.timeout_resets = 0
+    p.timeout_resets = int(bool(upstream_order))      # :197-198, commented out in this fork
     # command curriculum constants (:602-607)
     p.resample_interval = int(cfg.commands.resampling_time / dt)
     return p

@@ -65,7 +65,8 @@ struct ChainParams {
   float* outputs[RL_CHAIN_MAX_OUTPUTS];
   int n_loads, n_mmas, n_epis[2];
   int n_units, n_barriers;
-  int num_tiles, rows;
+  int num_tiles, rows;           // tiles [tile0, num_tiles) of the `rows`-row batch
+  int tile0;
   unsigned long long* trace;      // profiling aid: clock64 stamps of CTA 0 in tile iteration trace_it (or null)
   int trace_it;
   uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
@@ -203,7 +204,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     // ===================================== LOAD role =====================================
     // (the next op's fields are fetched - uniform constant loads - before this op's wait, off the critical path)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles && p.n_loads > 0; tile += gridDim.x, ++it) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && p.n_loads > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
       RlChainLoadOp cur = p.loads[0];
       for (int i = 0; i < p.n_loads; ++i) {
@@ -223,7 +224,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     const uint32_t base16 = smem_base >> 4;
     const uint32_t bar0 = smem_u32(bars);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles && p.n_mmas > 0; tile += gridDim.x, ++it) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && p.n_mmas > 0; tile += gridDim.x, ++it) {
       DevMmaOp cur = p.mmas[0];
       const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it;
       for (int i = 0; i < p.n_mmas; ++i) {
@@ -277,7 +278,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     const int bar_id = 1 + worker;
     const int trace_base = p.n_loads + TRACE_MMA * p.n_mmas + (worker ? TRACE_EPI * p.n_epis[0] : 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles && n_ops > 0; tile += gridDim.x, ++it) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && n_ops > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
       const int r = m0 + lr;
       uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1), n2 = __ldg(ops + 2);
@@ -579,8 +580,20 @@ extern "C" int64_t rl_chain_read_trace(void* handle, uint64_t* out_host, int64_t
   return (int64_t)n;
 }
 
+static int chain_launch(void* handle, int32_t rows, int32_t tile_begin, int32_t tile_end, void* stream);
+
 extern "C" int rl_chain_run(void* handle, int32_t rows, void* stream) {
   RL_REQUIRE(handle && rows > 0, RL_ERR_BAD_ARG, "rl_chain_run: handle=%p rows=%d", handle, rows);
+  return chain_launch(handle, rows, 0, (rows + 127) / 128, stream);
+}
+
+extern "C" int rl_chain_run_tiles(void* handle, int32_t rows, int32_t tile_begin, int32_t tile_end, void* stream) {
+  RL_REQUIRE(handle && rows > 0 && tile_begin >= 0 && tile_begin < tile_end && tile_end <= (rows + 127) / 128, RL_ERR_BAD_ARG,
+             "rl_chain_run_tiles: handle=%p rows=%d tiles [%d, %d)", handle, rows, tile_begin, tile_end);
+  return chain_launch(handle, rows, tile_begin, tile_end, stream);
+}
+
+static int chain_launch(void* handle, int32_t rows, int32_t tile_begin, int32_t tile_end, void* stream) {
   ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
   static int sm_count = 0;
   if (!sm_count) {
@@ -591,8 +604,10 @@ extern "C" int rl_chain_run(void* handle, int32_t rows, void* stream) {
   }
   ChainParams p = h->params;
   p.rows = rows;
-  p.num_tiles = (rows + 127) / 128;
-  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  p.num_tiles = tile_end;
+  p.tile0 = tile_begin;
+  const int n_tiles = tile_end - tile_begin;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   if (p.trace) mlp_chain_kernel<true><<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
   else mlp_chain_kernel<false><<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
   return check_launch("mlp_chain_kernel");

@@ -74,7 +74,7 @@ __device__ __forceinline__ void tma_store_rows(const CUtensorMap* map, const voi
 
 // shared-memory map (bytes from the 128 B aligned base); NB = bodies
 struct Lay {
-  int ro, rw, es, cs, wo, root, dof, con, act, tq_in, x, total;
+  int ro, rw, es, cs, wo, root, dof, con, act, tq_in, x, r, total;
   __host__ __device__ Lay(int NB, bool fuse) {
     ro = 0;
     rw = ro + RO_ROWS * ROWB;
@@ -89,7 +89,11 @@ struct Lay {
     const int in_end = tq_in + (fuse ? 0 : QT * ND * 4);
     const int out_end = dof + QT * (42 + RL_PRIV_DIM + ND) * 4;
     x = ((in_end > out_end ? in_end : out_end) + 127) & ~127;
-    total = x + (NPART * 4 + 2 + 12) * ROWB;      // partial sums | collision, air-time reward | r_i
+    total = x + (NPART * 4 + 2) * ROWB;           // partial sums | collision, air-time reward
+    // r_i [12][32] (written in phase 2, read in phase 3) re-uses the action rows - dead after phase 1, exactly 12 x 32
+    // floats - when the output rows that re-use the input tile end below them (17 bodies: 7 CTAs per SM fit only so)
+    if (act >= out_end) r = act;
+    else { r = total; total += 12 * ROWB; }
   }
 };
 
@@ -125,7 +129,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   float* s_part = reinterpret_cast<float*>(smem_raw + L.x);        // [NPART][4][32]
   float* s_coll = s_part + NPART * 4 * QT;                // [32]
   float* s_air = s_coll + QT;                             // [32]
-  float* s_r = s_air + QT;                                // [12][32]
+  float* s_r = reinterpret_cast<float*>(smem_raw + L.r);    // [12][32] per-term rewards
 
   // Programmatic dependent launch: let the NEXT kernel of the stream start launching its CTAs now (they run their
   // prologue and park in griddepcontrol.wait until this grid has completed and flushed), and wait for the PREVIOUS

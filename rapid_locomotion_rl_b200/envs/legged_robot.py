@@ -26,7 +26,7 @@ from .curriculum import RewardThresholdCurriculum
 class LeggedRobot:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True,
                  eval_cfg=None, initial_dynamics_dict=None, sim=None, terrain=None, seed=0,
-                 gac_rng="philox"):
+                 gac_rng="philox", upstream_order=False):
         if eval_cfg is not None:
             raise NotImplementedError("train/eval env split (eval_cfg) is a 'next' row (SURVEY.md 8f3)")
         self.cfg = cfg
@@ -54,7 +54,13 @@ class LeggedRobot:
         # `_reward_<name>` a subclass overrides - is served by that Python method after the fused launch
         custom = [n for n, sc in public_vars(cfg.rewards.scales).items() if sc != 0 and n != "termination" and
                   self._is_custom_reward(n)]
-        p = self.params = freeze_env_cfg(cfg, robot, terrain, sim_dt, custom_reward_names=custom)
+        # upstream_order: this fork commented the reset / time-out / resampling calls out of the step
+        # (legged_robot.py:177, :197-198, :246, :581); True restores the upstream legged_gym order: resample commands every
+        # resampling_time -> terminations (+ time-outs) -> rewards -> reset_idx of the terminated envs (+ their commands).
+        # Default False = the fork as written = what the goldens pin.
+        self.upstream_order = bool(upstream_order)
+        p = self.params = freeze_env_cfg(cfg, robot, terrain, sim_dt, custom_reward_names=custom,
+                                         upstream_order=self.upstream_order)
         if cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
             cfg.terrain.curriculum = False
         self.dt = p.dt_double
@@ -372,6 +378,8 @@ class LeggedRobot:
             actions = actions.contiguous()
         if actions.shape != (self.num_envs, self.num_actions):
             raise ValueError("actions must be [%d, %d], got %s" % (self.num_envs, self.num_actions, tuple(actions.shape)))
+        if self.upstream_order:
+            self._upstream_resample()
         if getattr(self.sim, "live", False):
             for _ in range(self.cfg.control.decimation):                       # :116-126
                 self.sim.apply_torques_and_step(self._compute_torques(actions))
@@ -379,6 +387,8 @@ class LeggedRobot:
             self.post_physics_step(actions)
             if self._moved_roots():                                            # teleport / push wrote root rows (:789, :765)
                 self.sim.push_root_state(torch.arange(self.num_envs, device=self.device))
+            if self.upstream_order:
+                self._upstream_reset()
             return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
         self._actions_in = actions
         self.common_step_counter += 1
@@ -391,7 +401,27 @@ class LeggedRobot:
                                                host_step, _lib.current_stream()))
         if self._custom_terms or self._hook_overrides:
             self._run_plugins()
+        if self.upstream_order:
+            self._upstream_reset()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _upstream_resample(self):
+        """:578-581 in upstream order: envs whose episode length (after this step's increment) hits the resampling
+        interval draw new commands BEFORE the step's rewards and observations are computed."""
+        interval = self.params.resample_interval
+        ids = ((self.episode_length_buf + 1) % interval == 0).nonzero(as_tuple=False).flatten()
+        if len(ids):
+            self._resample_commands(ids)
+
+    def _upstream_reset(self):
+        """:175-177 in upstream order: reset_idx of the envs that terminated (or timed out) in this step, commands
+        included (:246).  Deviation from upstream, stated: upstream builds the observations AFTER this reset; here the
+        fused launch has already written them, so an env that resets returns its last pre-reset observation (the next
+        step's observation is the first of the new episode)."""
+        ids = self.reset_buf.nonzero(as_tuple=False).flatten()
+        if len(ids):
+            self.reset_idx(ids)
+            self._resample_commands(ids)
 
     def _moved_roots(self):
         """True when the step may have rewritten root rows that a live simulator must be told about."""

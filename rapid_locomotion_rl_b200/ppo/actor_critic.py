@@ -317,12 +317,15 @@ class ActorCritic(nn.Module):
         self._fwd(e[1], w["H1"], 0, w["H1"].shape[1], w["H2"], 0, w["H2"].shape[1], rows, EPI_BIAS_ELU_BF16)
         self._fwd(e[2], w["H2"], 0, w["H2"].shape[1], w["Xac"], self.num_obs, w["Xac"].shape[1], rows, EPI_BIAS_BF16)
 
-    def forward_teacher(self, rows, want_value=True, want_mean=True, save=False):
-        """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace."""
+    def forward_teacher(self, rows, want_value=True, want_mean=True, save=False, tiles=None):
+        """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace (tiles: only these 128-row tiles)."""
         if self.use_chain:
             from . import chain
             prog = lambda wm, wv: self._chain(("teacher", save, wm, wv), lambda T: chain.teacher_forward_program(
                 T, save=save, want_mean=wm, want_value=wv))
+            if tiles is not None:
+                prog(want_mean, want_value).run(rows, tiles=tiles)
+                return
             if want_mean and want_value and not save and self._split_ok(rows):
                 side, fork, join = self._split_streams()
                 critic, actor = prog(False, True), prog(True, False)      # (compiled before the fork: graph-capture safe)

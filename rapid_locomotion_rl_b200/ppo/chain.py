@@ -395,8 +395,13 @@ class ChainProgram:
         self._handle, self._libref = h, lib
         return self
 
-    def run(self, rows, stream=None):
-        _lib.check(self._libref.rl_chain_run(self._handle, int(rows), _lib.current_stream() if stream is None else stream))
+    def run(self, rows, stream=None, tiles=None):
+        """All row tiles of the `rows`-row batch, or only tiles [tiles[0], tiles[1]) (128 rows each)."""
+        st = _lib.current_stream() if stream is None else stream
+        if tiles is None:
+            _lib.check(self._libref.rl_chain_run(self._handle, int(rows), st))
+        else:
+            _lib.check(self._libref.rl_chain_run_tiles(self._handle, int(rows), int(tiles[0]), int(tiles[1]), st))
 
     def trace(self, tile_iteration):
         _lib.check(self._libref.rl_chain_trace(self._handle, int(tile_iteration)))

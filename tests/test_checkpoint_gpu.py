@@ -44,14 +44,22 @@ def test_shipped_checkpoint_loads_and_acts_like_the_reference(golden_dir):
     assert np.allclose(np.concatenate([tensor_digest(x.numpy()) for x in (obs, priv, hist)]), g["input_digest"])
     ac.eval()
     o, p, h = obs.to(DEV), priv.to(DEV), hist.to(DEV)
-    # stated tolerance of the bf16 tensor-core path on trained weights: 2e-2 absolute + 2e-2 relative, cosine > 0.999
+    # Stated tolerance of the bf16 tensor-core path on the TRAINED weights: on these (out-of-distribution, unit-normal)
+    # inputs the policy outputs reach |a| ~ 36 and rounding operands to bf16 alone moves single outputs by up to 0.12
+    # (emulated on the CPU: bf16 inputs / weights / activations, fp32 accumulation), so the bound is on the whole output:
+    # relative L2 error <= 1e-2, cosine > 0.9999, and no element off by more than 0.1 + 5e-2 |ref|.
     for name, got in (("act_teacher", ac.act_teacher(o, p)), ("act_student", ac.act_student(o, h)), ("evaluate", ac.evaluate(o, p)),
                       ("act_inference", ac.act_inference({"obs": o, "obs_history": h, "privileged_obs": p})),
                       ("act_expert_is_teacher", ac.act_expert({"obs": o, "privileged_obs": p}))):
         ref = torch.from_numpy(g["act_teacher" if name == "act_expert_is_teacher" else name])
         got = got.float().cpu()
-        torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2, msg=name)
-        assert torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0) > 0.999, name
+        rel = ((got - ref).norm() / ref.norm()).item()
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+        # (the critic's outputs are ten times smaller than the actor's - mean |V| 0.44 - with the same absolute rounding
+        # noise from its 512-wide first layer: emulated bf16 error 0.057 max, hence the wider relative bound)
+        lim_rel, lim_cos = (5e-2, 0.999) if name == "evaluate" else (1e-2, 0.9999)
+        assert rel <= lim_rel and cos > lim_cos, (name, rel, cos)
+        torch.testing.assert_close(got, ref, rtol=5e-2, atol=1e-1, msg=name)
 
 
 def test_export_matches_reference_runner_files(tmp_path, golden_dir):

@@ -428,3 +428,42 @@ def test_uniform_command_curriculum_vs_golden(golden_dir):
         env._update_command_curriculum_uniform(cu(g["call%d/ids" % i]))
         got = [[float(x) for x in r["lin_vel_x"]], [float(x) for x in r["ang_vel_yaw"]]]
         assert np.allclose(got, g["call%d/ranges" % i], rtol=0, atol=1e-12), (i, got, g["call%d/ranges" % i].tolist())
+
+
+def test_upstream_order_switch():
+    """upstream_order=True restores the call sites this fork commented out: time-outs enter reset_buf
+    (:197-198), terminated envs are reset inside step (:177) and get new commands (:246), commands are resampled every
+    resampling_time (:581).  The default keeps the fork's order: no resets, no time-outs, no resampling inside step."""
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    n = 256
+    envs = {}
+    for up in (False, True):
+        cfg, robot, terrain = build_case("mc_flat", n)
+        env = LeggedRobot(cfg, sim_device=DEV, headless=True, terrain=terrain, seed=4, upstream_order=up)
+        p = env.params
+        assert p.timeout_resets == int(up)
+        st = synthetic_state(2, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx, p.term_idx[:p.n_term_bodies])
+        st["contact_forces"][:, p.term_idx[:p.n_term_bodies]] = 0.0
+        st["contact_forces"][:8, p.term_idx[0], 2] = 50.0                  # envs 0-7 terminate by contact
+        statekit.apply_to_product(env, st)
+        ep = torch.full((n,), 10, dtype=torch.long, device=DEV)
+        ep[8:16] = p.max_episode_length                                     # envs 8-15 time out (ep + 1 > max)
+        ep[16:24] = p.resample_interval - 1                                 # envs 16-23 hit the resampling interval
+        env.episode_length_buf.copy_(ep)
+        env.commands[:, :3] = 7.0                                           # a value no draw produces
+        env.last_actions[:] = 1.0
+        obs, priv, rew, reset, extras = env.step(torch.zeros(n, 12, device=DEV))
+        torch.cuda.synchronize()
+        envs[up] = (env, reset.clone())
+    env, reset = envs[False]
+    assert reset[:8].all() and not reset[8:].any()                          # contact terminations only
+    assert torch.equal(env.episode_length_buf[:8], torch.full((8,), 11, device=DEV))       # nobody was reset
+    assert (env.commands[:, 0] == 7.0).all()
+    env, reset = envs[True]
+    assert reset[:16].all() and not reset[16:].any()                        # + time-outs
+    assert env.time_out_buf[8:16].all() and not env.time_out_buf[:8].any()
+    assert (env.episode_length_buf[:16] == 0).all() and (env.episode_length_buf[24:] == 11).all()
+    assert float(env.last_actions[:16].abs().max()) == 0.0 and float(env.last_actions[24:].min()) == 0.0   # step wrote zeros anyway
+    torch.testing.assert_close(env.dof_pos[:16], env.default_dof_pos.expand(16, 12))
+    assert (env.commands[:24, 0] != 7.0).all() and (env.commands[24:, 0] == 7.0).all()     # reset envs + interval envs resampled

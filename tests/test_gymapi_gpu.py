@@ -91,6 +91,7 @@ def _fill(gym, sim, robot, n, seed=1):
     gym.root[sim.actor_indices] = torch.from_numpy(st["root_states"]).to(DEV)
     gym.dof[sim.dof_indices] = torch.from_numpy(st["dof_state"]).view(-1, 2).to(DEV)
     gym.contact[sim.rb_indices] = torch.from_numpy(st["contact_forces"]).view(-1, 3).to(DEV)
+    sim.refresh()          # the state was written behind the adapter's back: re-gather (a no-op for identity tables)
 
 
 @pytest.mark.parametrize("extra", [0, 2])
