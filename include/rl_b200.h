@@ -426,9 +426,10 @@ int rl_wgrad_grouped(const RlWgradProblem* problems_host, int32_t n, void* strea
  *   - three warp roles execute three host-built op lists in order, synchronised only by mbarriers:
  *       LOAD ops (1 thread): one TMA box each (input rows, weight blocks, saved activations for ELU');
  *       MMA ops  (1 thread): up to four tcgen05.mma K16 steps of [128 x n] += A box * B box^T;
- *       EPI ops  (2 x 4 warps): tcgen05.ld of <= 64 accumulator columns -> bias / ELU / ELU' -> bf16 box for
+ *       EPI ops  (2..4 x 4 warps): tcgen05.ld of <= 64 accumulator columns -> bias / ELU / ELU' -> bf16 box for
  *                           the next layer (and a TMA store of the box for the backward / wgrad) or fp32 rows;
- *                           two workers, each runs the ops tagged with its index, in order.
+ *                           two to four workers (the launch sizes the CTA by the highest worker index the program uses),
+ *                           each runs the ops tagged with its index, in order.
  *   The schedule (which layer's k-block meets which box when) is data: the op lists.  They are built and
  *   checked (deadlock freedom, buffer hazards, numerics on an emulator) on the host:
  *   rapid_locomotion_rl_b200/ppo/chain.py.
@@ -469,7 +470,9 @@ typedef struct RlChainMmaOp {
   uint16_t wait0, wait1, wait2;
   uint8_t commit0, commit1, commit2;   /* mbarriers that tcgen05.commit arrives on after these MMAs */
   uint8_t pad0;
-  uint32_t pad1, pad2;
+  uint16_t wait3;                   /* a fourth wait (0xFF in the low byte = none); zero-initialised structs must set it */
+  uint16_t pad1;
+  uint32_t pad2;
 } RlChainMmaOp;
 
 enum RlChainEpiMode {
@@ -484,7 +487,7 @@ typedef struct RlChainEpiOp {
   uint16_t wait_acc, wait_dst, wait_aux;
   uint8_t arrive_acc_free;          /* after the accumulator columns are in registers (count 4: one per warp) */
   uint8_t arrive_dst_ready;         /* after the box is written (count 4) */
-  uint8_t release_aux;              /* after every thread has read the aux box (count 1) */
+  uint8_t release_aux;              /* after every thread has read the aux box (count 1: the last of the worker's warps arrives) */
   uint8_t mode;
   uint8_t ncols;                    /* accumulator columns handled: 1..64 */
   uint8_t dst_col0;                 /* first box column written (0 except when merging into a loaded box) */
@@ -497,7 +500,7 @@ typedef struct RlChainEpiOp {
   uint32_t bias_off;                /* float offset into `params` of this op's first column bias */
   uint32_t dst_off, aux_off;
   int32_t store_col0;
-  uint8_t worker;                   /* which of the two epilogue warp groups executes this op */
+  uint8_t worker;                   /* which of the (up to four) epilogue warp groups executes this op */
   uint8_t padb0, padb1, padb2;
   uint32_t pad1, pad2;
 } RlChainEpiOp;

@@ -22,9 +22,9 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3     # us
 
 
-for B in (24000, 196608):
+for B in [int(x) for x in os.environ.get('BS', '24000,196608').split(',')]:
     n, T = B * 4 // 24, 24
-    for use_chain in (False, True):
+    for use_chain in ((True,) if os.environ.get('CHAIN_ONLY') else (False, True)):
         torch.manual_seed(0)
         ac = ActorCritic(42, 18, 630, 12, device="cuda:0")
         ac.use_chain = use_chain
@@ -39,11 +39,13 @@ for B in (24000, 196608):
         w = ac._ws
         res = {}
         res["teacher_fwd"] = timeit(lambda: ac.forward_teacher(B, save=True))
+        if use_chain:
+            res["teacher_fwd_nosave"] = timeit(lambda: ac._chain(("teacher", False, True, True), lambda T: chain.teacher_forward(T, save=False)).run(B))
         res["adapt_fwd"] = timeit(lambda: ac.forward_adaptation(B, save=True))
         if use_chain:
-            res["trunk_bwd"] = timeit(lambda: ac._chain(("trunk_backward",), chain.trunk_backward_program).run(B))
+            res["trunk_bwd"] = timeit(lambda: ac._chain(("trunk_backward",), chain.trunk_backward).run(B))
             res["adapt_bwd"] = timeit(lambda: ac._chain(("adaptation_backward",), chain.adaptation_backward_program).run(B))
         res["minibatch_step"] = timeit(lambda: ppo.minibatch_step(idx), 5)
         fl = {"teacher_fwd": 2 * (39680 + 196096 + 194688) * B, "adapt_fwd": 2 * 170048 * B,
-              "trunk_bwd": 2 * (39680 + 196096 + 194688) * B, "adapt_bwd": 2 * 170048 * B, "minibatch_step": 3.603e6 * B}
+              "trunk_bwd": 2 * (39680 + 196096 + 194688) * B, "teacher_fwd_nosave": 2 * (39680 + 196096 + 194688) * B, "adapt_bwd": 2 * 170048 * B, "minibatch_step": 3.603e6 * B}
         print("B=%d chain=%s " % (B, use_chain) + "  ".join("%s %.0f us (%.0f TF/s)" % (k, v, fl[k] / v / 1e6) for k, v in res.items()))

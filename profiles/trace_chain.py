@@ -16,7 +16,7 @@ ac = ActorCritic(42, 18, 630, 12, device="cuda:0")
 w = ac.workspace(B, backward=True)
 for k in ("Xp", "Xac", "Xh", "dmean", "dvalue", "dpred", "H1", "H2", "Y1", "A2", "A3", "C2", "C3", "D1", "D2"):
     w[k].copy_(torch.randn(w[k].shape, device="cuda") * 0.5)
-builders = {"teacher": lambda T: chain.teacher_forward_program(T, save=True), "trunk_backward": chain.trunk_backward_program,
+builders = {"teacher": lambda T: chain.teacher_forward(T, save=True), "trunk_backward": chain.trunk_backward,
             "adaptation": lambda T: chain.adaptation_forward_program(T, save=True), "adaptation_backward": chain.adaptation_backward_program}
 prog = ac._chain((which, "trace"), builders[which])
 prog.run(B); prog.run(B)
@@ -34,7 +34,7 @@ for i, t in enumerate(mm):
     print("  %3d n=%3d col=%3d k=%d acc=%d waits=%s  %s" % (i, o["n"], o["tmem_col"], o["k_steps"], o["accumulate"],
           [prog.bar_name[x.bar] for x in o["waits"]], " ".join("%7s" % x for x in t)))
 print("EPI  (start, acc ready, regs, math, end):")
-ordered = [o for o in prog.epis if o["worker"] == 0] + [o for o in prog.epis if o["worker"] == 1]
+ordered = [o for k in range(4) for o in prog.epis if o["worker"] == k]
 for i, t in enumerate(ep):
     o = ordered[i]
     print("  %3d w%d mode=%d ncols=%2d col=%3d store=%s  %s   [wait %d ld %d math %d write %d]" % (

@@ -18,7 +18,7 @@ STAMP = os.path.join(PKG, ".librl_b200.stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("RL_NVCC_EXTRA", "").split()      # development switches (e.g. -DRL_CHAIN_TRACE_WRITE)
 # env-path kernels mirror the eager reference op by op: no FMA contraction
 NO_FMA = {"env_step.cu", "env_step_quad.cu", "env_step_rows.cu", "heights.cu", "env_reset.cu", "gac.cu", "gae.cu", "history.cu", "api.cu"}
 

@@ -10,9 +10,13 @@
 //   warp 0 (1 elected lane)  LOAD ops: mbarrier wait (unit free) -> expect_tx -> cp.async.bulk.tensor.2d
 //   warp 1 (1 elected lane)  MMA ops : waits (stage full / box ready / accumulator free) -> <= 4 tcgen05.mma
 //                               (M128 x n x K16, kind::f16, fp32 in TMEM) -> tcgen05.commit on <= 3 barriers
-//   warps 2-5, 6-9    EPI ops : two workers, each runs its own list: wait (accumulator full) -> tcgen05.ld -> bias / ELU / ELU' -> swizzled bf16
-//                               box in shared memory (the next layer's A operand) -> TMA store of the box
-//                               (saved activation / gradient for wgrad) or fp32 output rows
+//   warps 2-5, 6-9, .. EPI ops : NW (2..4) workers of four warps, each runs its own list: wait (accumulator full) -> tcgen05.ld ->
+//                               bias / ELU / ELU' -> swizzled bf16 box in shared memory (the next layer's A operand) -> TMA store
+//                               of the box (saved activation / gradient for wgrad) or fp32 output rows.  The four warps of a
+//                               worker never synchronise with each other: warp g owns rows [32 g, 32 g + 32) of every box -
+//                               it writes them, fences them and TMA-stores them (a [32 x 64] sub-box, own bulk groups);
+//                               barriers the program gives ONE arrival per worker are completed by the last of the four
+//                               warps (a shared-memory ticket per barrier)
 // Shared memory = n_units x 16 KB dynamic (activation boxes and ring stages, all [rows x 64 bf16] tiles in the
 // 128 B-swizzled K-major layout shared by TMA and the UMMA descriptors) + 3 KB static (64 mbarriers, the
 // per-warp bias staging rows): 14 units use exactly the 227 KB a CTA can have.
@@ -28,9 +32,11 @@
 namespace rl {
 namespace tc {
 
-constexpr int CHAIN_THREADS = 320;          // warp 0 LOAD, warp 1 MMA, warps 2-5 / 6-9 the two epilogue workers
+constexpr int MAX_WORKERS = 4;
+constexpr int chain_threads(int nw) { return 64 + 128 * nw; }   // warp 0 LOAD, warp 1 MMA, then four warps per epilogue worker
 constexpr int UNIT_BYTES = 16384;
-constexpr int FIXED_SMEM = 3072;            // static: 64 mbarriers | tmem slot | per-warp bias staging (8 x 256 B)
+constexpr int FIXED_SMEM = 3072;            // static: 64 mbarriers | tmem slot, 64 tickets | per-warp bias staging (16 x 128 B)
+constexpr int MAX_STORE_MAPS = 16;
 constexpr int TRACE_MMA = 8, TRACE_EPI = 5; // stamps per op (loads: 1)
 #ifndef RL_CHAIN_WAIT_NS_LOAD
 #define RL_CHAIN_WAIT_NS_LOAD 0
@@ -45,9 +51,9 @@ struct DevMmaOp {            // 32 B; everything the issuing warp would otherwis
   uint32_t a_lo, b_lo;       // low descriptor words without the shared-memory window base: (off >> 4) | LBO field
   uint32_t idesc;
   uint32_t misc;             // tmem_col | k_steps << 16 | accumulate << 24
-  uint16_t wait_off[3];      // byte offset of the barrier in the barrier block + 1, or 0 for "no wait"
+  uint16_t wait_off[4];      // byte offset of the barrier in the barrier block + 1, or 0 for "no wait"
   uint16_t commit_off[3];    // same for the barriers tcgen05.commit arrives on
-  uint32_t parities;         // bit 2j: parity of wait j when the tile iteration is even, bit 2j+1: when it is odd
+  uint16_t parities;         // bit 2j: parity of wait j when the tile iteration is even, bit 2j+1: when it is odd
 };
 static_assert(sizeof(DevMmaOp) == 32, "DevMmaOp layout");
 
@@ -58,12 +64,13 @@ static_assert(sizeof(DevMmaOp) == 32, "DevMmaOp layout");
 constexpr int MAX_LOADS = 192, MAX_MMAS = 160;
 struct ChainParams {
   CUtensorMap tmaps[RL_CHAIN_MAX_TENSORS];
+  CUtensorMap tmaps_st[MAX_STORE_MAPS];   // [32 x 64] boxes over the stored tensors (one warp's rows of a box)
   RlChainLoadOp loads[MAX_LOADS];
   DevMmaOp mmas[MAX_MMAS];
-  const RlChainEpiOp* epis[2];    // per epilogue worker (global memory)
+  const RlChainEpiOp* epis[MAX_WORKERS];    // per epilogue worker (global memory)
   const float* params;
   float* outputs[RL_CHAIN_MAX_OUTPUTS];
-  int n_loads, n_mmas, n_epis[2];
+  int n_loads, n_mmas, n_epis[MAX_WORKERS];
   int n_units, n_barriers;
   int num_tiles, rows;           // tiles [tile0, num_tiles) of the `rows`-row batch
   int tile0;
@@ -175,15 +182,34 @@ __device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint32_t a_lo, uint32
   mma_bf16_ss(tmem_d, da, db, idesc, accumulate != 0);
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+__device__ __forceinline__ void mma_wait(uint32_t bar_addr, uint32_t parity, int it) {
+  if (mbar_try_addr(bar_addr, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_addr(bar_addr, parity)) {
+    if (++spins > (1u << 24)) chain_timeout((bar_addr & 0x1FFu) / 8, parity, it);
+  }
+}
+
+// one arrival per WORKER on a barrier every warp of the worker is done with: the last of the four warps arrives
+// (lane 0 of each warp calls this after its own reads / writes / bulk reads are complete)
+__device__ __forceinline__ void worker_arrive(uint64_t* bars, uint32_t* tickets, uint32_t bar_id) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(tickets + bar_id)) : "memory");
+  if ((old & 3u) == 3u) mbar_arrive(&bars[bar_id]);
+}
+
+template <bool TRACE, int NW>
+__global__ void __launch_bounds__(chain_threads(NW), 1)
 mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   __shared__ __align__(1024) uint8_t s_fixed[FIXED_SMEM];
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_fixed);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_fixed + 512);
-  float* s_bias = reinterpret_cast<float*>(s_fixed + 1024);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* tickets = reinterpret_cast<uint32_t*>(s_fixed + 576);          // 64 x 4 B
+  float* s_bias = reinterpret_cast<float*>(s_fixed + 1024);                // 16 warps x 32 floats
+  // warp-uniform role index (the shuffle tells the compiler so: the LOAD / MMA loops run on the uniform datapath)
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
 
   if (threadIdx.x == 0) {
@@ -194,6 +220,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     for (int b = 0; b < p.n_barriers; ++b) mbar_init(&bars[b], p.barrier_count[b]);
     mbar_fence_init();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) tickets[threadIdx.x - 64] = 0;
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -202,51 +229,43 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 
   if (warp == 0) {
     // ===================================== LOAD role =====================================
-    // (the next op's fields are fetched - uniform constant loads - before this op's wait, off the critical path)
+    const bool leader = elect_one();
     int it = 0;
     for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && p.n_loads > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
-      RlChainLoadOp cur = p.loads[0];
       for (int i = 0; i < p.n_loads; ++i) {
-        const RlChainLoadOp nxt = p.loads[i + 1 < p.n_loads ? i + 1 : i];
+        const RlChainLoadOp& cur = p.loads[i];
         chain_wait<WAIT_NS_LOAD>(bars, cur.wait, it);
-        if (elect_one()) {
+        if (leader) {
           mbar_expect_tx(&bars[cur.full_bar], cur.expect_bytes);
           tma_load_2d(smem + cur.smem_off, &p.tmaps[cur.tensor], cur.col0, cur.row0 + (cur.tile_rows ? m0 : 0), &bars[cur.full_bar]);
           if (TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it) p.trace[i] = clock64();
         }
-        __syncwarp();
-        cur = nxt;
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA role ======================================
+    const bool leader = elect_one();
     const uint32_t base16 = smem_base >> 4;
-    const uint32_t bar0 = smem_u32(bars);
+    uint32_t bar0 = smem_u32(bars);
+    asm volatile("" : "+r"(bar0));      // (opaque: otherwise the address is re-derived - S2R SR_CgaCtaId - at every use)
     int it = 0;
     for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && p.n_mmas > 0; tile += gridDim.x, ++it) {
-      DevMmaOp cur = p.mmas[0];
       const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it;
       for (int i = 0; i < p.n_mmas; ++i) {
-        const DevMmaOp nxt = p.mmas[i + 1 < p.n_mmas ? i + 1 : i];
-        if (tr && lane == 0) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
+        const DevMmaOp& cur = p.mmas[i];
+        if (tr && leader) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
         {
-          // fast path: the three try_waits back to back; only what failed is polled again
-          const uint32_t par = cur.parities >> (it & 1);
-          const uint32_t w0 = cur.wait_off[0], w1 = cur.wait_off[1], w2 = cur.wait_off[2];
-          bool ok0 = w0 == 0 || mbar_try_addr(bar0 + w0 - 1, par & 1u);
-          bool ok1 = w1 == 0 || mbar_try_addr(bar0 + w1 - 1, (par >> 2) & 1u);
-          bool ok2 = w2 == 0 || mbar_try_addr(bar0 + w2 - 1, (par >> 4) & 1u);
-          uint32_t spins = 0;
-          while (!(ok0 && ok1 && ok2)) {
-            if (!ok0) ok0 = mbar_try_addr(bar0 + w0 - 1, par & 1u);
-            if (!ok1) ok1 = mbar_try_addr(bar0 + w1 - 1, (par >> 2) & 1u);
-            if (!ok2) ok2 = mbar_try_addr(bar0 + w2 - 1, (par >> 4) & 1u);
-            if (++spins > (1u << 24)) chain_timeout(((!ok0 ? w0 : (!ok1 ? w1 : w2)) - 1) / 8, 2, it);
-          }
+          // (sequential spins: all three must pass anyway and the later ones are normally complete by then)
+          const uint32_t par = (uint32_t)cur.parities >> (it & 1);
+          const uint32_t w0 = cur.wait_off[0], w1 = cur.wait_off[1], w2 = cur.wait_off[2], w3 = cur.wait_off[3];
+          if (w0) mma_wait(bar0 + w0 - 1, par & 1u, it);
+          if (w1) mma_wait(bar0 + w1 - 1, (par >> 2) & 1u, it);
+          if (w2) mma_wait(bar0 + w2 - 1, (par >> 4) & 1u, it);
+          if (w3) mma_wait(bar0 + w3 - 1, (par >> 6) & 1u, it);
         }
         tc_fence_after();
-        if (elect_one()) {
+        if (leader) {
           if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
           const uint32_t a_lo = cur.a_lo + base16, b_lo = cur.b_lo + base16, idesc = cur.idesc;
           const uint32_t tmem_d = tmem_base + (cur.misc & 0xFFFFu);
@@ -261,22 +280,20 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (cur.commit_off[2]) mma_commit(nullptr, bar0 + cur.commit_off[2] - 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 7] = clock64();
         }
-        __syncwarp();
-        cur = nxt;
       }
     }
   } else {
     // ===================================== EPILOGUE workers ==============================
-    const int worker = (warp - 2) >> 2;          // warps 2-5: worker 0, warps 6-9: worker 1
-    const int g = warp & 3;                      // TMEM lane quarter this warp may read
+    const int worker = (warp - 2) >> 2;          // warps 2-5: worker 0, warps 6-9: worker 1, ...
+    const int g = warp & 3;                      // TMEM lane quarter this warp may read = the box rows it owns
     const int lr = 32 * g + lane;                // row within the tile
-    const int et = threadIdx.x - 64 - 128 * worker;     // 0..127 within the worker
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * g) << 16);
-    float* my_bias = s_bias + (warp - 2) * 64;
+    float* my_bias = s_bias + (warp - 2) * 32;
     const int n_ops = p.n_epis[worker];
     const uint4* ops = reinterpret_cast<const uint4*>(p.epis[worker]);
-    const int bar_id = 1 + worker;
-    const int trace_base = p.n_loads + TRACE_MMA * p.n_mmas + (worker ? TRACE_EPI * p.n_epis[0] : 0);
+    int trace_base = p.n_loads + TRACE_MMA * p.n_mmas;
+    for (int k = 0; k < worker; ++k) trace_base += TRACE_EPI * p.n_epis[k];
+    const bool first = (warp - 2) == 4 * worker && lane == 0;     // the worker's trace stamps come from its first thread
     int it = 0;
     for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && n_ops > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
@@ -297,7 +314,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         const int store_col0 = (int)w2.x;
         const bool has_bias = mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32;
 
-        const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it && et == 0;
+        const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it && first;
         unsigned long long* tp = p.trace + trace_base + TRACE_EPI * i;
         if (tr) tp[0] = clock64();
         // bias of this op's columns: two coalesced loads per warp, issued before the accumulator wait
@@ -337,14 +354,24 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 
         // ---- elementwise ----
         if (has_bias) {
+          // (the per-warp staging row holds 32 columns: two rounds)
           __syncwarp();                            // the previous op's broadcast reads are done
           my_bias[lane] = b_lo;
-          my_bias[32 + lane] = b_hi;
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 64; j += 4) {
+          for (int j = 0; j < 32; j += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(my_bias + j);
             f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+          }
+          if (ncols > 32) {
+            __syncwarp();
+            my_bias[lane] = b_hi;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(my_bias + j);
+              f[32 + j] += bb.x; f[33 + j] += bb.y; f[34 + j] += bb.z; f[35 + j] += bb.w;
+            }
           }
           if (mode == RL_CHAIN_EPI_BIAS_ELU) {
 #pragma unroll
@@ -376,14 +403,22 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (tr) tp[3] = tp[4] = clock64();
           continue;
         }
+#ifndef RL_CHAIN_TRACE_WRITE
         if (tr) tp[3] = clock64();
+#endif
 
-        // ---- bf16 box for the next layer ----
-        if (store_wait_pending >= 0) {          // a TMA store issued earlier may still be reading this box
-          if (et == 0) bulk_wait_read_dyn(store_wait_pending);
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // ---- this warp's 32 rows of the bf16 box for the next layer ----
+        if (store_wait_pending >= 0) {          // a TMA store this warp issued earlier may still be reading its rows
+          if (lane == 0) bulk_wait_read_dyn(store_wait_pending);
+          __syncwarp();
         }
+#ifdef RL_CHAIN_TRACE_WRITE
+        if (tr) tp[0] = clock64();
+#endif
         chain_wait<WAIT_NS_EPI>(bars, wait_dst, it);
+#ifdef RL_CHAIN_TRACE_WRITE
+        if (tr) tp[1] = clock64();
+#endif
         uint8_t* box = smem + dst_off;
         if (dst_col0 == 0 && ncols == 64) {
 #pragma unroll
@@ -406,29 +441,31 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
             }
           }
         }
+#ifdef RL_CHAIN_TRACE_WRITE
+        if (tr) tp[2] = clock64();
+#endif
         fence_async_smem();                      // generic-proxy writes -> visible to tcgen05.mma / TMA
-        if (arrive_dst_ready != RL_CHAIN_NONE) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[arrive_dst_ready]);
-        }
-        if (store_tensor != RL_CHAIN_NONE || release_aux != RL_CHAIN_NONE) {
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (et == 0) {
-            if (release_aux != RL_CHAIN_NONE) mbar_arrive(&bars[release_aux]);
-            if (store_tensor != RL_CHAIN_NONE) {
-              tma_store_2d(&p.tmaps[store_tensor], box, store_col0, m0);
-              bulk_commit();
-              if (release_after_store != RL_CHAIN_NONE) {
-                bulk_wait_read_n<0>();
-                mbar_arrive(&bars[release_after_store]);
-              }
+        __syncwarp();
+#ifdef RL_CHAIN_TRACE_WRITE
+        if (tr) tp[3] = clock64();
+#endif
+        if (lane == 0) {
+          if (arrive_dst_ready != RL_CHAIN_NONE) mbar_arrive(&bars[arrive_dst_ready]);
+          if (release_aux != RL_CHAIN_NONE) worker_arrive(bars, tickets, release_aux);
+          if (store_tensor != RL_CHAIN_NONE) {
+            // (a sub-box that starts below the last row is skipped; the - then empty - group keeps the count)
+            if (m0 + 32 * g < p.rows) tma_store_2d(&p.tmaps_st[store_tensor], box + 4096 * g, store_col0, m0 + 32 * g);
+            bulk_commit();
+            if (release_after_store != RL_CHAIN_NONE) {
+              bulk_wait_read_n<0>();
+              worker_arrive(bars, tickets, release_after_store);
             }
           }
         }
         if (tr) tp[4] = clock64();
       }
     }
-    if (et == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -437,6 +474,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 
 struct ChainHandle {
   ChainParams params;
+  int n_workers;
   void* dev_ops;
   size_t smem_bytes;
   unsigned long long* trace;
@@ -473,10 +511,13 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
                (o.a_off & 1023u) == 0 && (o.b_off & 1023u) == 0 && o.a_off + UNIT_BYTES <= limit && o.b_off + (uint32_t)o.n * 128 <= limit,
                RL_ERR_BAD_ARG, "rl_chain_create: mma op %d malformed", i);
   }
-  int n_epi_w[2] = {0, 0};
+  int n_epi_w[MAX_WORKERS] = {0, 0, 0, 0};
+  int n_workers = 2;
   for (int i = 0; i < d->n_epis; ++i) {
     const RlChainEpiOp& o = d->epis_host[i];
-    RL_REQUIRE(o.worker < 2, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d worker", i);
+    RL_REQUIRE(o.worker < MAX_WORKERS, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d: worker %d (the kernel has at most %d)", i,
+               (int)o.worker, MAX_WORKERS);
+    if (o.worker + 1 > n_workers) n_workers = o.worker + 1;
     RL_REQUIRE(o.ncols <= 32 || (o.dst_col0 == 0 && o.ncols == 64) || o.mode == RL_CHAIN_EPI_BIAS_F32, RL_ERR_BAD_ARG,
                "rl_chain_create: epilogue op %d: partial boxes hold <= 32 columns", i);
     RL_REQUIRE(o.mode != RL_CHAIN_EPI_BIAS_F32 || o.ncols <= 32, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d: <= 32 output columns", i);
@@ -512,20 +553,42 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
     x.b_lo = (o.b_off >> 4) | (1u << 16);
     x.idesc = instr_desc_bf16(128, o.n, false, false);
     x.misc = (uint32_t)o.tmem_col | ((uint32_t)o.k_steps << 16) | ((uint32_t)(o.accumulate != 0) << 24);
-    const uint16_t ws[3] = {o.wait0, o.wait1, o.wait2};
+    const uint16_t ws[4] = {o.wait0, o.wait1, o.wait2, o.wait3};
     const uint8_t cs[3] = {o.commit0, o.commit1, o.commit2};
-    x.parities = 0;
-    for (int j = 0; j < 3; ++j) {
+    uint32_t parities = 0;
+    for (int j = 0; j < 4; ++j) {
       const uint32_t id = ws[j] & 0xFFu, base = (ws[j] >> 8) & 1u, flip = (ws[j] >> 9) & 1u;
       x.wait_off[j] = id == RL_CHAIN_NONE ? 0 : (uint16_t)(8 * id + 1);
-      x.parities |= (base << (2 * j)) | ((base ^ flip) << (2 * j + 1));
-      x.commit_off[j] = cs[j] == RL_CHAIN_NONE ? 0 : (uint16_t)(8 * cs[j] + 1);
+      parities |= (base << (2 * j)) | ((base ^ flip) << (2 * j + 1));
+      if (j < 3) x.commit_off[j] = cs[j] == RL_CHAIN_NONE ? 0 : (uint16_t)(8 * cs[j] + 1);
     }
+    x.parities = (uint16_t)parities;
   }
   RlChainEpiOp* de = reinterpret_cast<RlChainEpiOp*>(blob.data());
   {
-    int pos[2] = {0, n_epi_w[0]};
-    for (int i = 0; i < d->n_epis; ++i) de[pos[d->epis_host[i].worker]++] = d->epis_host[i];
+    int pos[MAX_WORKERS] = {0, 0, 0, 0};
+    for (int k = 1; k < MAX_WORKERS; ++k) pos[k] = pos[k - 1] + n_epi_w[k - 1];
+    // stored tensors get a second map with a [32 x 64] box (each epilogue warp stores its own rows of a box);
+    // the device op names that map
+    int st_of[RL_CHAIN_MAX_TENSORS];
+    for (int t = 0; t < RL_CHAIN_MAX_TENSORS; ++t) st_of[t] = -1;
+    int n_st = 0;
+    for (int i = 0; i < d->n_epis; ++i) {
+      RlChainEpiOp o = d->epis_host[i];
+      if (o.store_tensor != RL_CHAIN_NONE) {
+        if (st_of[o.store_tensor] < 0) {
+          if (n_st >= MAX_STORE_MAPS) { delete h; set_error("rl_chain_create: more than %d stored tensors", MAX_STORE_MAPS); return RL_ERR_BAD_ARG; }
+          const RlChainTensor& T = d->tensors[o.store_tensor];
+          if ((rc = make_tmap_bf16(&h->params.tmaps_st[n_st], T.base, (uint64_t)T.rows, (uint64_t)T.cols, (uint64_t)T.ld, 32)) != RL_OK) {
+            delete h;
+            return rc;
+          }
+          st_of[o.store_tensor] = n_st++;
+        }
+        o.store_tensor = (uint8_t)st_of[o.store_tensor];
+      }
+      de[pos[o.worker]++] = o;
+    }
   }
   cudaError_t err = cudaMalloc(&h->dev_ops, blob.size());
   if (err != cudaSuccess) { delete h; set_error("rl_chain_create: cudaMalloc: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
@@ -533,18 +596,25 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   err = cudaMemcpy(base, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: cudaMemcpy: %s", cudaGetErrorString(err)); return RL_ERR_CUDA; }
   h->params.epis[0] = reinterpret_cast<const RlChainEpiOp*>(base);
-  h->params.epis[1] = h->params.epis[0] + n_epi_w[0];
+  for (int k = 1; k < MAX_WORKERS; ++k) h->params.epis[k] = h->params.epis[k - 1] + n_epi_w[k - 1];
+  h->n_workers = n_workers;
   h->params.params = d->params;
   for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->params.outputs[i] = d->outputs[i];
   h->params.n_loads = d->n_loads; h->params.n_mmas = d->n_mmas;
-  h->params.n_epis[0] = n_epi_w[0]; h->params.n_epis[1] = n_epi_w[1];
+  for (int k = 0; k < MAX_WORKERS; ++k) h->params.n_epis[k] = n_epi_w[k];
   h->params.n_units = d->n_units; h->params.n_barriers = d->n_barriers;
   memcpy(h->params.barrier_count, d->barrier_count, RL_CHAIN_MAX_BARRIERS);
   h->smem_bytes = (size_t)d->n_units * UNIT_BYTES;      // dynamic part; FIXED_SMEM bytes are static
   static size_t configured = 0;
   if (h->smem_bytes > configured) {
-    err = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    const int bytes = (int)h->smem_bytes;
+    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    err = cudaFuncSetAttribute(mlp_chain_kernel<false, 2>, at, bytes);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<true, 2>, at, bytes);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<false, 3>, at, bytes);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<true, 3>, at, bytes);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<false, 4>, at, bytes);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mlp_chain_kernel<true, 4>, at, bytes);
     if (err != cudaSuccess) { cudaFree(h->dev_ops); delete h; set_error("rl_chain_create: smem %zu B: %s", h->smem_bytes, cudaGetErrorString(err)); return RL_ERR_CUDA; }
     configured = h->smem_bytes;
   }
@@ -608,8 +678,16 @@ static int chain_launch(void* handle, int32_t rows, int32_t tile_begin, int32_t 
   p.tile0 = tile_begin;
   const int n_tiles = tile_end - tile_begin;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  if (p.trace) mlp_chain_kernel<true><<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
-  else mlp_chain_kernel<false><<<grid, CHAIN_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RL_CHAIN_LAUNCH(NWK)                                                                                  \
+  do {                                                                                                        \
+    if (p.trace) mlp_chain_kernel<true, NWK><<<grid, chain_threads(NWK), h->smem_bytes, st>>>(p);             \
+    else mlp_chain_kernel<false, NWK><<<grid, chain_threads(NWK), h->smem_bytes, st>>>(p);                    \
+  } while (0)
+  if (h->n_workers <= 2) RL_CHAIN_LAUNCH(2);
+  else if (h->n_workers == 3) RL_CHAIN_LAUNCH(3);
+  else RL_CHAIN_LAUNCH(4);
+#undef RL_CHAIN_LAUNCH
   return check_launch("mlp_chain_kernel");
 }
 

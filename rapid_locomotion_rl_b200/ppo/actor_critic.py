@@ -254,9 +254,9 @@ class ActorCritic(nn.Module):
         if not self.use_chain:
             return
         from . import chain
-        self._chain(("teacher", True, True, True), lambda T: chain.teacher_forward_program(T, save=True))
-        self._chain(("trunk_backward",), chain.trunk_backward_program)
-        self._chain(("encoder",), lambda T: chain.teacher_forward_program(T, save=False, trunk=False))
+        self._chain(("teacher", True, True, True), lambda T: chain.teacher_forward(T, save=True))
+        self._chain(("trunk_backward",), chain.trunk_backward)
+        self._chain(("encoder",), lambda T: chain.teacher_forward(T, save=False, trunk=False))
         self._chain(("adaptation", True), lambda T: chain.adaptation_forward_program(T, save=True))
         self._chain(("adaptation_backward",), chain.adaptation_backward_program)
 
@@ -265,11 +265,11 @@ class ActorCritic(nn.Module):
         self.workspace(rows)
         if self.use_chain:
             from . import chain
-            self._chain(("teacher", False, True, True), lambda T: chain.teacher_forward_program(T, save=False))
+            self._chain(("teacher", False, True, True), lambda T: chain.teacher_forward(T, save=False))
             if self._split_ok(rows):
                 for wm, wv in ((True, False), (False, True)):
                     self._chain(("teacher", False, wm, wv),
-                                lambda T, wm=wm, wv=wv: chain.teacher_forward_program(T, save=False, want_mean=wm, want_value=wv))
+                                lambda T, wm=wm, wv=wv: chain.teacher_forward(T, save=False, want_mean=wm, want_value=wv))
                 self._split_streams()
 
     @staticmethod
@@ -310,7 +310,7 @@ class ActorCritic(nn.Module):
         """env_factor_encoder(priv) -> bf16 latent written straight into the latent slot of Xac."""
         if self.use_chain:
             from . import chain
-            self._chain(("encoder",), lambda T: chain.teacher_forward_program(T, save=False, trunk=False)).run(rows)
+            self._chain(("encoder",), lambda T: chain.teacher_forward(T, save=False, trunk=False)).run(rows)
             return
         w, e = self._ws, self.L_enc
         self._fwd(e[0], w["Xp"], 0, w["Xp"].shape[1], w["H1"], 0, w["H1"].shape[1], rows, EPI_BIAS_ELU_BF16)
@@ -321,7 +321,7 @@ class ActorCritic(nn.Module):
         """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace (tiles: only these 128-row tiles)."""
         if self.use_chain:
             from . import chain
-            prog = lambda wm, wv: self._chain(("teacher", save, wm, wv), lambda T: chain.teacher_forward_program(
+            prog = lambda wm, wv: self._chain(("teacher", save, wm, wv), lambda T: chain.teacher_forward(
                 T, save=save, want_mean=wm, want_value=wv))
             if tiles is not None:
                 prog(want_mean, want_value).run(rows, tiles=tiles)

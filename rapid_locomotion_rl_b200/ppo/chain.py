@@ -52,19 +52,20 @@ class BoxUse:
 
 
 class AccUse:
-    __slots__ = ("region", "col", "full", "free_bar", "wait_free", "started", "closed", "last_op")
+    __slots__ = ("region", "col", "full", "free_bar", "wait_free", "started", "closed", "last_op", "alias_free")
 
     def __init__(self, region, col, free_bar, wait_free):
         self.region, self.col, self.free_bar, self.wait_free = region, col, free_bar, wait_free
         self.full, self.started, self.closed = None, False, False
         self.last_op = {}               # epilogue worker -> its last op on this accumulator use
+        self.alias_free = []            # free waits of overlapping regions (ChainProgram(alias_waits=True))
 
 
 class ChainProgram:
     """Builder + container of one chain program."""
 
     def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1, rings=None,
-                 n_workers=2):
+                 n_workers=2, alias_waits=False):
         """Shared-memory units: [inputs | pool | ring stages]; `regions`: {name: (first tmem column, width)};
         `region_worker`: regions whose accumulator uses are read by ONE epilogue op -> the worker that owns
         them (a waiter must see every phase of a barrier, so such a region cannot change hands); the other
@@ -75,6 +76,10 @@ class ChainProgram:
         n_stages x stage_units); the LOAD role still issues every load in program order."""
         self.name = name
         self.n_inputs, self.n_pool, self.n_workers = n_inputs, n_pool, n_workers
+        # alias_waits: regions may share tensor-memory columns; the first MMA of a use then also waits until the latest
+        # use of every overlapping region has been read by the epilogue (acc(..., implied=) names the ones another
+        # wait of the same op already implies)
+        self.alias_waits = alias_waits
         rings = rings or [("main", n_stages, stage_units)]
         self.n_stages, self.stage_units = rings[0][1], rings[0][2]      # of the default (first) ring
         self.tensors = []                # (torch tensor 2-D view, box_rows)
@@ -194,10 +199,19 @@ class ChainProgram:
         return self.region_worker[acc.region] if acc.region in self.region_worker else (col // 64) % self.n_workers
 
     # ---- tensor-memory accumulators -----------------------------------------------------------------
-    def acc(self, region):
+    def acc(self, region, implied=(), carry=()):
         assert self.acc_open[region] is None or self.acc_open[region].closed, "accumulator %s still open" % region
         col, width = self.regions[region]
         a = AccUse(region, col, self.acc_free[region], _Wait(self.acc_free[region], self.acc_uses[region]))
+        if self.alias_waits:
+            for r2, (c2, w2) in self.regions.items():
+                if r2 != region and r2 not in implied and c2 < col + width and col < c2 + w2:
+                    assert self.acc_open[r2] is None or self.acc_open[r2].closed, "%s opened over the open accumulator %s" % (region, r2)
+                    # a region not used yet in this tile was last used by the PREVIOUS tile: its reads are normally
+                    # implied by that tile's program order; `carry` names the ones that are not (need 0 = the previous
+                    # tile's last completion)
+                    if self.acc_uses[r2] > 0 or r2 in carry:
+                        a.alias_free.append(_Wait(self.acc_free[r2], self.acc_uses[r2]))
         self.acc_uses[region] += 1
         self.acc_open[region] = a
         return a
@@ -206,7 +220,7 @@ class ChainProgram:
     def mma(self, a, b, n, acc, col_off=0, k_steps=4, accumulate=True, acc_last=False, a_release=False, b_release=True):
         """acc[:, col_off : col_off + n] (+)= A box * B box^T over k_steps K16 steps."""
         waits, commits = [], []
-        for w in (a.full if isinstance(a, StageUse) else a.ready, b.full, None if acc.started else acc.wait_free):
+        for w in [a.full if isinstance(a, StageUse) else a.ready, b.full] + ([] if acc.started else [acc.wait_free] + acc.alias_free):
             w = self._w("mma", w)
             if w is not None:
                 waits.append(w)
@@ -227,7 +241,7 @@ class ChainProgram:
             commits.append(self.acc_full[acc.region])
         width = self.regions[acc.region][1]
         assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 256
-        assert len(waits) <= 3 and len(commits) <= 3
+        assert len(waits) <= 4 and len(commits) <= 3, (len(waits), len(commits))
         self.mmas.append(dict(a_off=a.off, b_off=b.off, n=n, tmem_col=acc.col + col_off, k_steps=k_steps,
                               accumulate=int(accumulate), waits=waits, commits=commits))
 
@@ -360,8 +374,8 @@ class ChainProgram:
         for i, o in enumerate(self.mmas):
             x = M[i]
             x.a_off, x.b_off, x.n, x.tmem_col, x.k_steps, x.accumulate = o["a_off"], o["b_off"], o["n"], o["tmem_col"], o["k_steps"], o["accumulate"]
-            ws = [self._spec(w) for w in o["waits"]] + [NONE] * 3
-            x.wait0, x.wait1, x.wait2 = ws[:3]
+            ws = [self._spec(w) for w in o["waits"]] + [NONE] * 4
+            x.wait0, x.wait1, x.wait2, x.wait3 = ws[:4]
             cs = list(o["commits"]) + [NONE] * 3
             x.commit0, x.commit1, x.commit2 = cs[:3]
         E = (_lib.RlChainEpiOp * max(1, len(self.epis)))()
@@ -747,7 +761,8 @@ def _round16(n):
 REGIONS3 = {"C0": (0, 64), "C1": (64, 64), "C2": (128, 64), "BIG": (192, 256), "MID": (0, 128)}
 
 
-def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=3, stage_units=2, n_workers=2):
+def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=3, stage_units=2, n_workers=2,
+                            lookahead=None):
     """encoder(priv) -> latent merged into the [obs | latent] box -> actor mean / critic value
     (actor_critic.py:124-173 `act` / `evaluate` on one batch; ppo.py:102-107 inside the update).
     T: tensors + parameter offsets (see ActorCritic._chain_tensors).  save: also store every hidden
@@ -821,11 +836,16 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
                 s = p.load_stage(tW2, col0=64 * j, row0=h)
                 p.mma(chunk_box[j], s, n=min(wmax, W2.shape[0] - h), acc=acc2, col_off=h, k_steps=4, accumulate=j > 0,
                       acc_last=(j == nch - 1 and h + wmax >= W2.shape[0]), a_release=(h + wmax >= W2.shape[0]))
-        l1(0)
-        for j in range(1, nch):
+        # software pipeline: the first-layer chunk `la` ahead is issued BEFORE the second-layer MMA that waits for chunk
+        # j's box, so a worker finds its next accumulator full the moment it has written a box (la = number of chunk
+        # accumulators: every worker always has one chunk in flight)
+        la = nw if lookahead is None else lookahead
+        for j in range(min(la, nch)):
             l1(j)
-            l2(j - 1)
-        l2(nch - 1)
+        for j in range(nch):
+            if j + la < nch:
+                l1(j + la)
+            l2(j)
         a2 = _boxes(p, acc2, W2.shape[0], EPI_BIAS_ELU, b2, t2)
         acc3 = p.acc("MID")
         _dense(p, a2, tW3, W3.shape[0], acc3)
@@ -833,6 +853,105 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
         # (three workers: MID overlaps C0 / C1, and the head's first MMA waits for the first MID box only - its
         # accumulator must lie outside MID)
         acc4 = p.acc("C%d" % (ni % 2) if nw == 2 else "C2")
+        _dense(p, a3, tW4, _round16(n_out), acc4)
+        p.output(out_id, T["mean"] if tag == "a" else T["value"])
+        p.epi_out(acc4, 0, n_out, b4, out_id)
+    return p.finalize()
+
+
+# Four epilogue workers (16 warps): the wide layers are produced 256 columns at a time - ONE N = 256 MMA op feeds one
+# 64-column chunk to each worker - so the tensor-issuing warp runs far fewer ops (its ~800 cycles per op were what the
+# two-worker stream waited for) and the SM's four schedulers always have a worker in its MUFU-bound ELU phase while
+# another one writes / stores its box.  Tensor-memory map: S [0, 256) (first-layer staging: two uses per network),
+# BIG [256, 512) (second-layer accumulator); the narrow accumulators share S's columns: MID [0, 128) (third layer /
+# encoder hidden 2), O0 / O1 / O2 [128.., 32 each) (mean, value, latent).  alias_waits=True: the first MMA into a region
+# waits until the epilogue has read the latest use of every region it overlaps.
+REGIONS4 = {"S": (0, 256), "BIG": (256, 256), "MID": (0, 128), "O0": (128, 32), "O1": (160, 32), "O2": (192, 32)}
+
+
+def teacher_forward_program4(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=4):
+    """teacher_forward_program for the four-worker kernel (same tensors, same results)."""
+    p = ChainProgram(n_pool=4, n_stages=n_stages, n_inputs=2, regions=REGIONS4, name="teacher_forward4", stage_units=2,
+                     n_workers=4, region_worker={"O0": 2, "O1": 3, "O2": 2}, alias_waits=True)
+    p.params = T["params"]
+    wbox = lambda w: min(256, _round16(w.shape[0]))
+    tXp, tXac = p.tensor(T["Xp"], 128), p.tensor(T["Xac"], 128)
+    tWe1, tWe2 = p.tensor(T["We1"], wbox(T["We1"])), p.tensor(T["We2"], wbox(T["We2"]))
+    lat = T["We3"].shape[0]
+    tWe3 = p.tensor(T["We3"], _round16(lat))
+    st = lambda name: p.tensor(T[name], 128) if save else None
+    tH1, tH2 = st("H1"), st("H2")
+    assert T["We1"].shape[0] <= 256 and T["We2"].shape[0] <= 128 and _round16(lat) <= 32
+    xp = p.load_input(0, tXp, 0)
+    xac = p.load_input(1, tXac, 0, extra_free_arrivals=1)
+    # ---- encoder ----
+    kp = T["Xp"].shape[1]
+    # (the previous tile's last accumulator inside S: its output epilogue may still have to read it)
+    acc = p.acc("S", carry=(("O2",) if not trunk else ("O1",) if want_value else ("O0",)))
+    _dense(p, [xp], tWe1, T["We1"].shape[0], acc, k_last_steps=(kp + 15) // 16)
+    h1 = _boxes(p, acc, T["We1"].shape[0], EPI_BIAS_ELU, T["b_e1"], tH1)
+    acc = p.acc("MID")
+    _dense(p, h1, tWe2, T["We2"].shape[0], acc)
+    h2 = _boxes(p, acc, T["We2"].shape[0], EPI_BIAS_ELU, T["b_e2"], tH2)
+    acc = p.acc("O2")
+    _dense(p, h2, tWe3, _round16(lat), acc)
+    merged_ready = p._bar(4, "xac.merged")
+    xacm = p.epi_merge(acc, 0, lat, EPI_BIAS, T["b_e3"], xac, T["num_obs"], merged_ready, store=(tXac, 0),
+                       release_after_store=xac.free_bar)
+    if not trunk:
+        p.bar_count[xac.free_bar] = 1
+        p._signal(xac.free_bar)
+        return p.finalize()
+    # ---- actor / critic ----
+    tWcat = p.tensor(T["Wcat"], 256)
+    tY1 = st("Y1")
+    H = T["Wcat"].shape[0] // 2
+    assert H % 256 == 0
+    nets = []
+    if want_mean:
+        nets.append(("a", 0, T["Wa2"], T["Wa3"], T["Wa4"], "A2", "A3", T["b_a2"], T["b_a3"], T["b_a4"], 0, "O0"))
+    if want_value:
+        nets.append(("c", H, T["Wc2"], T["Wc3"], T["Wc4"], "C2", "C3", T["b_c2"], T["b_c3"], T["b_c4"], 1, "O1"))
+    for ni, (tag, off, W2, W3, W4, n2, n3, b2, b3, b4, out_id, oreg) in enumerate(nets):
+        assert W2.shape[0] <= 256 and W3.shape[0] <= 128
+        tW2, tW3 = p.tensor(W2, wbox(W2)), p.tensor(W3, wbox(W3))
+        n_out = W4.shape[0]
+        tW4 = p.tensor(W4, _round16(n_out))
+        t2, t3 = st(n2), st(n3)
+        nsc = H // 256
+        acc2 = p.acc("BIG")
+        boxes = [None] * nsc
+        accs = [None] * nsc
+        last_net = ni == len(nets) - 1
+
+        def l1(k):
+            # the latent's read of O2 is implied by the merged box the op waits for
+            a1 = p.acc("S", implied=("O2",))
+            s_ = p.load_stage(tWcat, col0=0, row0=off + 256 * k)
+            p.mma(xacm, s_, n=256, acc=a1, k_steps=4, accumulate=False, acc_last=True, a_release=(last_net and k == nsc - 1))
+            accs[k] = a1
+
+        def l1_epi(k):
+            boxes[k] = _boxes(p, accs[k], 256, EPI_BIAS_ELU, T["b_cat"] + off + 256 * k, tY1, store_col0=off + 256 * k)
+
+        def l2(k):
+            for b, box in enumerate(boxes[k]):
+                j = 4 * k + b
+                s_ = p.load_stage(tW2, col0=64 * j, row0=0)
+                p.mma(box, s_, n=W2.shape[0], acc=acc2, k_steps=4, accumulate=j > 0, acc_last=(j == H // 64 - 1), a_release=True)
+        # software pipeline: super-chunk k + 1's MMA is issued before the second-layer MMAs that wait for the boxes of k
+        l1(0)
+        l1_epi(0)
+        for k in range(1, nsc):
+            l1(k)
+            l2(k - 1)
+            l1_epi(k)
+        l2(nsc - 1)
+        a2 = _boxes(p, acc2, W2.shape[0], EPI_BIAS_ELU, b2, t2)
+        acc3 = p.acc("MID")
+        _dense(p, a2, tW3, W3.shape[0], acc3)
+        a3 = _boxes(p, acc3, W3.shape[0], EPI_BIAS_ELU, b3, t3)
+        acc4 = p.acc(oreg)
         _dense(p, a3, tW4, _round16(n_out), acc4)
         p.output(out_id, T["mean"] if tag == "a" else T["value"])
         p.epi_out(acc4, 0, n_out, b4, out_id)
@@ -990,3 +1109,28 @@ def adaptation_backward_program(T):
     _dense(p, dd2, tW2, n1, acc, k_last_steps=(n2 + 15) // 16)
     _boxes(p, acc, n1, EPI_DELU, 0, tdD1, aux_tensor=tD1, has_reader=False)
     return p.finalize()
+
+
+# =====================================================================================================
+# Which programs the learner runs
+# =====================================================================================================
+def workers():
+    """Epilogue workers of the teacher-forward chain program: RL_CHAIN_WORKERS = 2 | 3 | 4.  Measured at 196608 rows
+    (profiles/r02_chain_ncu.md): 2 workers 438 us (423 with the first-layer chunks issued two ahead), 3 workers with
+    three chunks ahead 411 us, 4 workers (teacher_forward_program4; 96 registers per thread) 549 us."""
+    import os
+    n = int(os.environ.get("RL_CHAIN_WORKERS", "3"))
+    assert n in (2, 3, 4), "RL_CHAIN_WORKERS must be 2, 3 or 4"
+    return n
+
+
+def teacher_forward(T, **kw):
+    import os
+    if workers() == 4:
+        return teacher_forward_program4(T, **kw)
+    la = os.environ.get("RL_CHAIN_LOOKAHEAD")
+    return teacher_forward_program(T, n_workers=workers(), lookahead=int(la) if la else None, **kw)
+
+
+def trunk_backward(T):
+    return trunk_backward_program(T)

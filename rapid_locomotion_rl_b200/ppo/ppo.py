@@ -258,7 +258,7 @@ class PPO:
                 inv_gb, P(w["dmean"][r0:]), P(w["dvalue"][r0:]), P(w["dpred"][r0:]), P(ac.std_grad), P(self._stats),
                 P(kl_slot), _lib.current_stream()))
             # dgrad of actor + critic + encoder in ONE persistent kernel (csrc/chain.cu)
-            ac._chain(("trunk_backward",), chain.trunk_backward_program).run(B, tiles=(t0, t1))
+            ac._chain(("trunk_backward",), chain.trunk_backward).run(B, tiles=(t0, t1))
         chunks = self._chunks(B) if ac.use_chain else None
         if chunks:
             if self._chunk_stream is None:

@@ -186,26 +186,32 @@ def test_timing_model_tracks_measured_periods():
         assert abs(r["period"] / cm.MEASURED[prog.name] - 1) < 0.20, (prog.name, r["period"], cm.MEASURED[prog.name])
 
 
-def test_three_worker_teacher_forward_study():
-    """The builder / emulator / timing model take programs for three epilogue workers (the kernel has two: this is
-    the study that decided NOT to build the third).  The program must be hazard free - its 128-column layer
-    accumulator shares the columns of two chunk accumulators - and numerically right; the model says what it buys."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles"))
-    import chain_model as cm
+def test_three_and_four_worker_teacher_forward():
+    """Programs for three (the shipped teacher forward: three chunk accumulators, the 128-column layer accumulator
+    shares the columns of two of them) and four epilogue workers (teacher_forward_program4: 256-column first-layer
+    staging, every narrow accumulator aliased into it, alias waits) must be hazard free and numerically right, for
+    every variant the product builds."""
     for seed, n_ctas in ((0, 1), (1, 2)):
-        T = ck.make_tensors(ROWS, seed)
-        ref = ck.ref_teacher(T)
-        prog = chain.teacher_forward_program(T, n_workers=3)
-        assert {o["worker"] for o in prog.epis} == {0, 1, 2}
-        chain.Emulator(prog, ROWS, n_ctas=n_ctas, seed=seed).run()
-        _close(T, ref, ("H1", "H2", "Xac", "Y1", "A2", "A3", "C2", "C3", "mean", "value"))
-    T = ck.make_tensors(512, 0)
-    two = cm.Model(chain.teacher_forward_program(T), tiles=5).run().report()["period"]
-    three = cm.Model(chain.teacher_forward_program(T, n_workers=3), tiles=5).run().report()["period"]
-    assert 0.9 < three / two < 1.02, (two, three)          # a few percent at most: the chain is latency bound, not worker bound
-    # the two-worker kernel must refuse the program loudly (argument validation precedes every CUDA call)
+        for nw, build in ((3, lambda T: chain.teacher_forward_program(T, n_workers=3)), (4, chain.teacher_forward_program4)):
+            T = ck.make_tensors(ROWS, seed)
+            ref = ck.ref_teacher(T)
+            prog = build(T)
+            assert {o["worker"] for o in prog.epis} == set(range(nw))
+            chain.Emulator(prog, ROWS, n_ctas=n_ctas, seed=seed).run()
+            _close(T, ref, ("H1", "H2", "Xac", "Y1", "A2", "A3", "C2", "C3", "mean", "value"))
+    for kw in (dict(save=False), dict(trunk=False), dict(want_value=False), dict(want_mean=False, save=False)):
+        for build in (lambda T, **k: chain.teacher_forward_program(T, n_workers=3, **k), chain.teacher_forward_program4):
+            T = ck.make_tensors(ROWS, 3)
+            ref = ck.ref_teacher(T)
+            chain.Emulator(build(T, **kw), ROWS, seed=4).run()
+            keys = ["Xac"]
+            if kw.get("trunk", True):
+                keys += (["mean"] if kw.get("want_mean", True) else []) + (["value"] if kw.get("want_value", True) else [])
+            _close(T, ref, keys)
+    # more than four workers: refused loudly (argument validation precedes every CUDA call)
     from rapid_locomotion_rl_b200 import _lib
+    T = ck.make_tensors(512, 0)
+    prog = chain.teacher_forward_program(T, n_workers=3)
+    prog.epis[0]["worker"] = 4
     with pytest.raises(_lib.RlError, match="worker"):
-        chain.teacher_forward_program(T, n_workers=3).compile()
+        prog.compile()
