@@ -233,6 +233,11 @@ typedef struct RlEnvBuffers {
   /* optional [N]: the sum of the enabled terms BEFORE the positive clip and the termination term (:328-334).  The
    * Python plugin layer needs it to add user-defined `_reward_<name>` terms exactly where the reference adds them. */
   float* rew_raw;
+  /* optional [N] scratch.  When set (and measure_heights is on) the terrain heights (:1469-1503: measured_heights, the
+   * height suffix of obs_buf, mean(z - heights) for the base_height term) are sampled by a launch of their own in front
+   * of the step kernel - one warp per env over the whole GPU - instead of by the four warps of each 32-env CTA.  Same
+   * arithmetic and summation order: identical bits. */
+  float* height_mean;
 } RlEnvBuffers;
 
 /* profiling aid: enable / read the globaltimer phase stamps of one CTA of the fused env-step kernel

@@ -110,6 +110,98 @@ __device__ inline float centered_u16(const uint32_t (&r)[4], int k) {
   return __fmaf_rn((float)x, 1.0f / 65536.0f, 0.5f / 65536.0f - 0.5f);
 }
 
+
+// Terrain heights under ONE env (legged_robot.py:1469-1503), by one warp - lanes over the measured points: writes
+// measured_heights[ge], the height suffix of obs_buf[ge] (:386-389 + noise :392 + clip :134) and returns
+// mean(z - heights) (the base_height term's input) on every lane.  (bx, by, bz, yz, yw): base position (after the
+// teleport) and the z / w components of the base quaternion.  Shared by the step kernels (four warps take the envs of a
+// tile in turn) and by the pre-pass kernel (heights.cu: one warp per env over the whole GPU): same arithmetic, same
+// per-lane summation order, identical bits.
+// Six 32-point chunks at a time (187 points = one pass): pass 1 computes the cell indices and ISSUES the three int16
+// gathers of every chunk (18 independent L2 loads in flight per lane); pass 2 consumes them in per-lane point order.
+__device__ inline float sample_heights_env(const RlEnvCfg& cfg, const RlEnvBuffers& b, uint64_t seed, uint64_t rng_step, int ge,
+                                           float bx, float by, float bz, float yz, float yw, int lane, bool c_noise) {
+  const int P = cfg.num_height_points;
+  const int Wc = cfg.num_obs - P;
+  const float hscale = cfg.horizontal_scale, vscale = cfg.vertical_scale, co = cfg.clip_obs;
+  float nrm = sqrtf(yz * yz + yw * yw);
+  nrm = fmaxf(nrm, 1e-9f);
+  yz = yz / nrm; yw = yw / nrm;
+  float acc = 0.f;
+  float* mh = b.measured_heights + (size_t)ge * P;
+  float* ob = b.obs_buf + (size_t)ge * cfg.num_obs + Wc;
+  const float* nu = b.noise_u ? b.noise_u + (size_t)ge * cfg.num_obs : nullptr;
+  // observation noise: Philox block j serves points [8 j, 8 j + 8); lane L computes the blocks L, L + 32, .. once
+  // (187 points = 24 blocks: one round), the consumers fetch theirs by shuffle
+  const bool philox = c_noise && !nu;
+  constexpr int HU = 6;
+  const int hf_cols = cfg.hf_cols, ix_max = cfg.hf_rows - 2, iy_max = cfg.hf_cols - 2;
+  const int16_t* H = b.height_samples;
+#pragma unroll 1
+  for (int p0 = 0; p0 < P; p0 += 32 * HU) {
+    uint32_t blk[4] = {0u, 0u, 0u, 0u};
+    if (philox && p0 + 8 * lane < P)       // blocks p0 / 8 + lane of this pass (32 * HU / 8 = 24 per pass)
+      Philox::gen(seed, (uint32_t)ge, (uint32_t)rng_step, (uint32_t)(rng_step >> 32),
+                  (RNG_NOISE << 16) | (uint32_t)(64 + (p0 >> 3) + lane), blk);
+    int16_t hs[HU][3];
+#pragma unroll
+    for (int u = 0; u < HU; ++u) {
+      const int p = p0 + 32 * u + lane;
+      hs[u][0] = hs[u][1] = hs[u][2] = 0;
+      if (p < P && !cfg.heights_plane) {
+        const float px = b.height_points[2 * p], py = b.height_points[2 * p + 1];
+        V3 wp = quat_apply(0.f, 0.f, yz, yw, V3{px, py, 0.f});
+        const float fx = (wp.x + bx + cfg.border_size) / hscale;
+        const float fy = (wp.y + by + cfg.border_size) / hscale;
+        // .long() truncates toward zero; the clip to the table makes the saturating 32-bit conversion equivalent
+        const int ix = max(0, min(__float2int_rz(fx), ix_max));
+        const int iy = max(0, min(__float2int_rz(fy), iy_max));
+        const int16_t* h0 = H + ix * hf_cols + iy;
+        hs[u][0] = __ldg(h0);
+        hs[u][1] = __ldg(h0 + hf_cols);
+        hs[u][2] = __ldg(h0 + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < HU; ++u) {
+      const int pbase = p0 + 32 * u;
+      if (pbase >= P) break;                     // warp uniform
+      const int p = pbase + lane;
+      uint32_t r4[4] = {0u, 0u, 0u, 0u};
+      if (philox) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r4[k] = __shfl_sync(0xffffffffu, blk[k], 4 * u + (lane >> 3));
+      }
+      if (p < P) {
+        const float h = cfg.heights_plane ? 0.f : (float)min(min(hs[u][0], hs[u][1]), hs[u][2]) * vscale;
+        mh[p] = h;
+        acc += bz - h;
+        float o = clampf(bz - 0.5f - h, -1.f, 1.f) * cfg.obs_scale_height;
+        if (c_noise) {
+          if (nu) o += (2.0f * nu[Wc + p] - 1.0f) * cfg.noise_scale_height;
+          else o = __fmaf_rn(2.0f * centered_u16(r4, p & 7), cfg.noise_scale_height, o);
+        }
+        ob[p] = clampf(o, -co, co);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  return acc / (float)P;
+}
+
+// legged_robot.py:768-791: the teleport of one env's base position (idempotent: a teleported position lies inside)
+__device__ inline bool teleport_xy(const RlEnvCfg& cfg, float& x, float& y) {
+  const float x0 = x, y0 = y;
+  if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
+  if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
+  if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
+  if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
+  return x != x0 || y != y0;
+}
+
+// heights.cu: the pre-pass launch (b.height_mean set)
+int launch_heights_prepass(const StepArgs& args, cudaStream_t st);
+
 // launcher of the one-warp-per-leg kernel for the standard observation layout (env_step_quad.cu)
 int launch_step_quad(const StepArgs& args, bool fuse_torques, cudaStream_t st);
 // the same step with all tile traffic on TMA, for the shipped configuration on packed state blocks (env_step_rows.cu)

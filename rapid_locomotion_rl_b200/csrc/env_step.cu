@@ -182,56 +182,17 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   // ---- 4. terrain heights (:1469-1503): one warp per env, lanes over points -------------
   if (cfg.measure_heights) {
     const int warp = tid >> 5, lane = tid & 31;
-    const float hscale = cfg.horizontal_scale, vscale = cfg.vertical_scale;
+    if (b.height_mean) {
+      // sampled by the pre-pass launch (heights.cu), which applied the same teleport to its copy of the position
+      if (valid) s_hmean[tid] = b.height_mean[e];
+    } else {
 #pragma unroll 1
-    for (int le = warp; le < n_valid; le += TILE / 32) {
-      const float* r = s_root + le * 13;
-      const int ge = tile0 + le;
-      const float bx = r[0], by = r[1], bz = r[2];
-      // quat_apply_yaw (math_utils.py:12-16): zero x,y then normalize
-      float yz = r[5], yw = r[6];
-      float nrm = sqrtf(yz * yz + yw * yw);
-      nrm = fmaxf(nrm, 1e-9f);
-      yz = yz / nrm; yw = yw / nrm;
-      float acc = 0.f;
-      float* mh = b.measured_heights + (size_t)ge * P;
-      float* ob = b.obs_buf + (size_t)ge * cfg.num_obs + W;
-      const float* nu = b.noise_u ? b.noise_u + (size_t)ge * cfg.num_obs : nullptr;
-#pragma unroll 1
-      for (int p = lane; p < P; p += 32) {
-        float h = 0.f;
-        if (!cfg.heights_plane) {
-          const float px = b.height_points[2 * p], py = b.height_points[2 * p + 1];
-          V3 w = quat_apply(0.f, 0.f, yz, yw, V3{px, py, 0.f});
-          float fx = (w.x + bx + cfg.border_size) / hscale;
-          float fy = (w.y + by + cfg.border_size) / hscale;
-          long long ix = (long long)fx, iy = (long long)fy;  // .long() truncates toward zero
-          ix = max(0ll, min(ix, (long long)cfg.hf_rows - 2));
-          iy = max(0ll, min(iy, (long long)cfg.hf_cols - 2));
-          const int16_t* H = b.height_samples;
-          const int16_t h1 = __ldg(H + ix * cfg.hf_cols + iy);
-          const int16_t h2 = __ldg(H + (ix + 1) * cfg.hf_cols + iy);
-          const int16_t h3 = __ldg(H + ix * cfg.hf_cols + iy + 1);
-          h = (float)min(min(h1, h2), h3) * vscale;
-        }
-        mh[p] = h;
-        acc += bz - h;
-        // observation suffix (:386-389) + noise (:392) + clip (:134)
-        float o = clampf(bz - 0.5f - h, -1.f, 1.f) * cfg.obs_scale_height;
-        if (cfg.add_noise) {
-          if (nu) {
-            o += (2.0f * nu[W + p] - 1.0f) * cfg.noise_scale_height;
-          } else {
-            uint32_t r4[4];   // stream block 64+: disjoint from the core columns' blocks
-            Philox::gen(args.seed, (uint32_t)ge, (uint32_t)rng_step, (uint32_t)(rng_step >> 32),
-                        (RNG_NOISE << 16) | (uint32_t)(64 + (p >> 3)), r4);
-            o = __fmaf_rn(2.0f * centered_u16(r4, p & 7), cfg.noise_scale_height, o);
-          }
-        }
-        ob[p] = clampf(o, -cfg.clip_obs, cfg.clip_obs);
+      for (int le = warp; le < n_valid; le += TILE / 32) {
+        const float* r = s_root + le * 13;
+        const float hm = sample_heights_env(cfg, b, args.seed, rng_step, tile0 + le, r[0], r[1], r[2], r[5], r[6], lane,
+                                            cfg.add_noise != 0);
+        if (lane == 0) s_hmean[le] = hm;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) s_hmean[le] = acc / (float)P;
     }
     __syncthreads();
   }
@@ -706,6 +667,8 @@ static int validate(const RlEnvCfg* cfg, const RlEnvBuffers* b, bool need_torque
   if (cfg->measure_heights) {
     RL_REQUIRE(b->measured_heights && b->height_points, RL_ERR_BAD_ARG, "env step: heights enabled without buffers");
     RL_REQUIRE(cfg->heights_plane || b->height_samples, RL_ERR_BAD_ARG, "env step: height_samples missing");
+    RL_REQUIRE(cfg->heights_plane || (cfg->hf_rows >= 2 && cfg->hf_cols >= 2 && (long long)cfg->hf_rows * cfg->hf_cols < (1ll << 31)),
+               RL_ERR_BAD_CFG, "env step: height table %d x %d (needs >= 2 x 2 and < 2^31 cells)", cfg->hf_rows, cfg->hf_cols);
   }
   if (cfg->timeout_resets) RL_REQUIRE(b->time_out_buf, RL_ERR_BAD_ARG, "env step: time_out_buf missing");
   (void)need_torques_in;
@@ -749,6 +712,11 @@ static int launch_step(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed
   if (rc != RL_OK) return rc;
   StepArgs qargs;
   qargs.cfg = *cfg; qargs.b = *b; qargs.seed = seed; qargs.step = step;
+  if (cfg->measure_heights && b->height_mean) {
+    // terrain heights first, one warp per env over the whole GPU (heights.cu); the step kernel reads the means
+    rc = launch_heights_prepass(qargs, (cudaStream_t)stream);
+    if (rc != RL_OK) return rc;
+  }
   {
     // standard observation layout -> one-warp-per-leg kernel (env_step_quad.cu); RL_ENV_MODE=thread forces
     // the one-thread-per-env kernel below (also the path of every other observe_* combination)

@@ -193,76 +193,17 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
   }
   if (c_heights) {
-    __syncthreads();
-    const float hscale = cfg.horizontal_scale, vscale = cfg.vertical_scale;
+    if (b.height_mean) {
+      // sampled by the pre-pass launch (heights.cu), which applied the same teleport to its copy of the position
+      if (w == 0 && valid) s_hmean[lane] = b.height_mean[e];
+    } else {
+      __syncthreads();
 #pragma unroll 1
-    for (int le = w; le < n_valid; le += 4) {      // one warp per env, lanes over the points (:1469-1503)
-      const float* r = s_root + le * 13;
-      const int ge = tile0 + le;
-      const float bx = r[0], by = r[1], bz = r[2];
-      float yz = r[5], yw = r[6];
-      float nrm = sqrtf(yz * yz + yw * yw);
-      nrm = fmaxf(nrm, 1e-9f);
-      yz = yz / nrm; yw = yw / nrm;
-      float acc = 0.f;
-      float* mh = b.measured_heights + (size_t)ge * P;
-      float* ob = b.obs_buf + (size_t)ge * cfg.num_obs + W;
-      const float* nu = b.noise_u ? b.noise_u + (size_t)ge * cfg.num_obs : nullptr;
-      // Six 32-point chunks at a time (187 points = one pass): pass 1 computes the cell indices and ISSUES the three
-      // int16 gathers of every chunk (18 independent L2 loads in flight per lane - with one chunk per iteration the warp
-      // sat through 6 x 3 dependent-latency round trips per env); pass 2 consumes them in the same per-lane order as
-      // before, so the mean is bit-identical.  The Philox block of 8 consecutive points is computed by one lane of the
-      // group and broadcast (it was computed 8 times).
-      constexpr int HU = 6;
-#pragma unroll 1
-      for (int p0 = 0; p0 < P; p0 += 32 * HU) {
-        int16_t hs[HU][3];
-#pragma unroll
-        for (int u = 0; u < HU; ++u) {
-          const int p = p0 + 32 * u + lane;
-          hs[u][0] = hs[u][1] = hs[u][2] = 0;
-          if (p < P && !cfg.heights_plane) {
-            const float px = b.height_points[2 * p], py = b.height_points[2 * p + 1];
-            V3 wp = quat_apply(0.f, 0.f, yz, yw, V3{px, py, 0.f});
-            float fx = (wp.x + bx + cfg.border_size) / hscale;
-            float fy = (wp.y + by + cfg.border_size) / hscale;
-            long long ix = (long long)fx, iy = (long long)fy;
-            ix = max(0ll, min(ix, (long long)cfg.hf_rows - 2));
-            iy = max(0ll, min(iy, (long long)cfg.hf_cols - 2));
-            const int16_t* H = b.height_samples;
-            hs[u][0] = __ldg(H + ix * cfg.hf_cols + iy);
-            hs[u][1] = __ldg(H + (ix + 1) * cfg.hf_cols + iy);
-            hs[u][2] = __ldg(H + ix * cfg.hf_cols + iy + 1);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < HU; ++u) {
-          const int pbase = p0 + 32 * u;
-          if (pbase >= P) break;                     // warp uniform
-          const int p = pbase + lane;
-          uint32_t r4[4] = {0u, 0u, 0u, 0u};
-          if (c_noise && !nu) {
-            if ((lane & 7) == 0)
-              Philox::gen(args.seed, (uint32_t)ge, (uint32_t)rng_step, (uint32_t)(rng_step >> 32),
-                          (RNG_NOISE << 16) | (uint32_t)(64 + (p >> 3)), r4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) r4[k] = __shfl_sync(0xffffffffu, r4[k], lane & ~7);
-          }
-          if (p < P) {
-            const float h = cfg.heights_plane ? 0.f : (float)min(min(hs[u][0], hs[u][1]), hs[u][2]) * vscale;
-            mh[p] = h;
-            acc += bz - h;
-            float o = clampf(bz - 0.5f - h, -1.f, 1.f) * cfg.obs_scale_height;
-            if (c_noise) {
-              if (nu) o += (2.0f * nu[W + p] - 1.0f) * cfg.noise_scale_height;
-              else o = __fmaf_rn(2.0f * centered_u16(r4, p & 7), cfg.noise_scale_height, o);
-            }
-            ob[p] = clampf(o, -co, co);
-          }
-        }
+      for (int le = w; le < n_valid; le += 4) {      // one warp per env, lanes over the points (:1469-1503)
+        const float* r = s_root + le * 13;
+        const float hm = sample_heights_env(cfg, b, args.seed, rng_step, tile0 + le, r[0], r[1], r[2], r[5], r[6], lane, c_noise);
+        if (lane == 0) s_hmean[le] = hm;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) s_hmean[le] = acc / (float)P;
     }
     __syncthreads();
   }

@@ -35,6 +35,29 @@ env_heights_kernel(const __grid_constant__ RlEnvCfg cfg, const float* __restrict
   }
 }
 
+// The step's height phase as a launch of its own (RlEnvBuffers.height_mean set): one warp per env.  Inside the step kernel
+// the four warps of a 32-env CTA take 8 envs each in turn - at 4000 envs that is 125 CTAs, one warp per scheduler, ~2000
+// dependent instructions per env (51 us per step); here 4000 warps spread over all SMs hide each other's latency.
+__global__ void __launch_bounds__(256)
+env_heights_prepass_kernel(const __grid_constant__ StepArgs args) {
+  const RlEnvCfg& cfg = args.cfg;
+  const RlEnvBuffers& b = args.b;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (e >= cfg.num_envs) return;
+  const uint64_t rng_step = args.step + (b.step_state ? b.step_state[0] : 0ull);
+  const float* r = b.root_states + (size_t)e * 13;
+  float bx = r[0], by = r[1];
+  if (cfg.teleport_robots) teleport_xy(cfg, bx, by);     // the step kernel applies (and stores) the same teleport
+  const float hm = sample_heights_env(cfg, b, args.seed, rng_step, e, bx, by, r[2], r[5], r[6], lane, cfg.add_noise != 0);
+  if (lane == 0) b.height_mean[e] = hm;
+}
+
+int launch_heights_prepass(const StepArgs& args, cudaStream_t st) {
+  const int n = args.cfg.num_envs;
+  env_heights_prepass_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(args);
+  return check_launch("env_heights_prepass_kernel");
+}
+
 }  // namespace rl
 
 extern "C" int rl_env_heights(const RlEnvCfg* cfg, const float* root_states, const float* height_points,

@@ -291,6 +291,14 @@ class LeggedRobot:
         b.noise_u = b.dr_u = b.push_u = None
         b.step_state = None
         b.rew_raw = P(self._rew_raw)
+        # terrain heights in a launch of their own, one warp per env (csrc/heights.cu); RL_ENV_HEIGHTS_PREPASS=0: inside
+        # the step kernel (same bits)
+        import os
+        if self.params.measure_heights and os.environ.get("RL_ENV_HEIGHTS_PREPASS", "1") != "0":
+            self._height_mean = torch.zeros(self.num_envs, device=self.device)
+            b.height_mean = P(self._height_mean)
+        else:
+            b.height_mean = None
         return b
 
     def use_device_step_counter(self, enable=True):

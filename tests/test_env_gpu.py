@@ -408,6 +408,43 @@ def test_rows_kernel_matches_quad_kernel(case, n):
         assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), "state %r: %s" % (k, where(sa[k], sb[k]))
 
 
+@pytest.mark.parametrize("case,n", [("mc_rough", 1000), ("mc_rough_full", 4000)])
+def test_heights_prepass_matches_in_kernel_sampling(case, n, monkeypatch):
+    """The terrain heights sampled by the pre-pass launch (csrc/heights.cu, one warp per env; the default) and inside the
+    step kernel (RL_ENV_HEIGHTS_PREPASS=0) give identical bits: observations (Philox noise, no injection), rewards,
+    measured_heights, every piece of state - over three steps with envs inside the teleport band."""
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    results = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RL_ENV_HEIGHTS_PREPASS", mode)
+        env, cfg, robot, terrain = make_env(case, n)
+        assert (getattr(env, "_height_mean", None) is not None) == (mode == "1")
+        p = env.params
+        rng = np.random.default_rng(11)
+        st = random_persistent_state(rng, n, list(env.episode_sums.keys()))
+        for k in env.command_sums:
+            st["command_sums/" + k] = rng.normal(0, 1, n).astype(np.float32)
+        for k in ("env_origins", "terrain_levels", "terrain_types"):
+            st[k] = getattr(env, k).cpu().numpy()
+        st.update(synthetic_state(5, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx,
+                                  p.term_idx[:p.n_term_bodies], z0=0.3, teleport_band_frac=0.05))
+        statekit.apply_to_product(env, st)
+        actions = cu(rng.normal(0, 1, (n, 12)).astype(np.float32))
+        outs = []
+        for s_ in range(3):
+            o = env.step(actions)[:4]
+            torch.cuda.synchronize()
+            outs.append([t.clone() for t in o] + [env.measured_heights.clone(), env.root_states.clone()])
+        results.append((outs, statekit.state_from_product(env)))
+    (oa, sa), (ob, sb) = results
+    names = ("obs", "priv", "rew", "reset", "measured_heights", "root_states")
+    for s_, (xa, xb) in enumerate(zip(oa, ob)):
+        for i, (a, b) in enumerate(zip(xa, xb)):
+            assert torch.equal(a, b), "step %d %s differs in %d elements" % (s_, names[i], int((a != b).sum()))
+    for k in sa:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), "state %r differs" % k
+
+
 def test_uniform_command_curriculum_vs_golden(golden_dir):
     """_update_command_curriculum_uniform (legged_robot.py:851-880) against the reference's recorded ranges: twelve
     scripted calls (on / off the max_episode_length step, above / below the thresholds, up to the clip)."""
