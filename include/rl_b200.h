@@ -619,6 +619,15 @@ int rl_adam(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl
 /* step_dev (may be NULL): device int32[2] {optimiser step count, CTA ticket}.  When given, the bias
  * corrections use step_dev[0] + 1 and the kernel advances the counter itself, so the launch can be captured
  * in a CUDA graph and replayed; `step` is then ignored. */
+/* rl_adam and rl_refresh_shadows in one launch: the parameters [p, p + n) are stepped and every element that lies
+ * inside one of the `n_layers` weight matrices (w_start[i]: its first element relative to p, [out_dim[i], in_dim[i]]
+ * row-major) is also written to that layer's bf16 operands wb[i] ([out, ld_wb]) and wbt[i] ([in, ld_wbt], transposed).
+ * Pad columns of the operands are left as they are (zero since the first rl_refresh_shadows). */
+int rl_adam_shadows(float* p, float* g, float* m, float* v, int64_t n, const float* ctrl, float lr_fixed,
+                    int32_t use_ctrl, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                    int32_t* step_dev, const int64_t* w_start, void* const* wb, void* const* wbt,
+                    const int32_t* out_dim, const int32_t* in_dim, const int32_t* ld_wb, const int32_t* ld_wbt,
+                    int32_t n_layers, void* stream);
 /* bf16 shadow copies of the fp32 master weights: wb [out, ld_wb] and its transpose wbt [in, ld_wbt]
  * (host arrays of n_layers device pointers / dims) */
 int rl_refresh_shadows(const void* const* w, void* const* wb, void* const* wbt, const int32_t* out_dim,

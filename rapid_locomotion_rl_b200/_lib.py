@@ -133,6 +133,8 @@ SIGNATURES = {
     "rl_chain_destroy": (C.c_int, [_P]),
     "rl_chain_trace": (C.c_int, [_P, C.c_int32]),
     "rl_chain_read_trace": (C.c_int64, [_P, _P, C.c_int64]),
+    "rl_adam_shadows": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                  C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "rl_refresh_shadows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "rl_policy_sample": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

@@ -191,6 +191,29 @@ class ActorCritic(nn.Module):
             arr_i(*[L.ld_wb for L in Ls]), arr_i(*[L.ld_wbt for L in Ls]), n, _lib.current_stream()))
         self._cache_key = None
 
+    def adam_shadows(self, start, n, grad, ctrl, lr_fixed, use_ctrl, step_dev, layers):
+        """One launch: Adam on flat[start : start + n] (rl_adam's arguments) and the bf16 operands of `layers`, whose
+        master weights lie inside that range (csrc/ppo.cu adam_shadows_kernel)."""
+        key = (start, tuple(id(L) for L in layers))
+        tab = self._adam_tabs.get(key) if hasattr(self, "_adam_tabs") else None
+        if tab is None:
+            if not hasattr(self, "_adam_tabs"):
+                self._adam_tabs = {}
+            k = len(layers)
+            arr_p, arr_i, arr_l = (C.c_void_p * k), (C.c_int32 * k), (C.c_int64 * k)
+            tab = (arr_l(*[self._offset_of_data(L.w) - start for L in layers]), arr_p(*[L.wb.data_ptr() for L in layers]),
+                   arr_p(*[L.wbt.data_ptr() for L in layers]), arr_i(*[L.out for L in layers]), arr_i(*[L.inp for L in layers]),
+                   arr_i(*[L.ld_wb for L in layers]), arr_i(*[L.ld_wbt for L in layers]), k)
+            self._adam_tabs[key] = tab
+        off = 4 * start
+        _lib.check(self._lib.rl_adam_shadows(
+            self.flat.data_ptr() + off, grad.data_ptr() + off, self.flat_m.data_ptr() + off, self.flat_v.data_ptr() + off, n,
+            ctrl, float(lr_fixed), int(use_ctrl), 0.9, 0.999, 1e-8, 0, 1.0, step_dev, *tab, _lib.current_stream()))
+        self._cache_key = None
+
+    def _offset_of_data(self, t):
+        return (t.data_ptr() - self.flat.data_ptr()) // 4
+
     def load_state_dict(self, state_dict, strict=True):
         out = super().load_state_dict(state_dict, strict=strict)
         self.refresh_shadows()

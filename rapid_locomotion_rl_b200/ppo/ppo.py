@@ -65,6 +65,7 @@ class PPO:
         self._graph_lag = self._graph_rest = self._graph_reduce = None
         self._graph_ws_gen = -1
         self._chunk_stream = self._ev_chunk_fork = self._ev_chunk_join = None
+        self._fused_adam = os.environ.get("RL_PPO_FUSED_ADAM", "1") != "0"      # Adam + bf16 operands in one launch
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -228,6 +229,10 @@ class PPO:
                 self._side.wait_event(self._ev_fork)
                 if pending:
                     self._adapt_grads(B, world, lagged=True, loss_event=self._ev_loss)
+                    if allreduce is None:
+                        # one GPU: the adaptation module's optimiser step stays on the side branch too (nothing on the
+                        # policy path reads its weights, gradient range or step counter)
+                        self._adapt_step(g_used)
                     self._ev_grads.record()
                 _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
                                                            ld("Xh"), _lib.current_stream()))
@@ -317,7 +322,6 @@ class PPO:
         if lag:
             if early:
                 self._adapt_step(g_used)
-            ac.refresh_shadows(self._main_layers + (ac.L_ada if early else []))
             # regression target of THIS minibatch (ppo.py:158: the latent of the already updated encoder); the next
             # call's teacher forward overwrites the latent slot, so it is copied out - after the side branch's loss
             # kernel has read the previous target
@@ -325,15 +329,8 @@ class PPO:
             if pending:
                 torch.cuda.current_stream().wait_event(self._ev_loss)
             self._target(B)[:B, :ac.latent_dim].copy_(w["Xac"][:B, ac.num_obs:ac.num_obs + ac.latent_dim])
-            if pending and not early:
-                # one GPU: nothing needs the adaptation gradient before this point, the side branch has the whole
-                # policy path to finish in
-                torch.cuda.current_stream().wait_event(self._ev_grads)
-                self._adapt_step(g_used)
-                ac.refresh_shadows(ac.L_ada)
             torch.cuda.current_stream().wait_event(self._ev_join)          # every forked branch rejoins
             return
-        ac.refresh_shadows(self._main_layers)
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
         for _ in range(A.num_adaptation_module_substeps):
             ac.forward_encoder(B)
@@ -342,7 +339,6 @@ class PPO:
             if debug:
                 self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
             self._adapt_step(g_used)
-            ac.refresh_shadows(ac.L_ada)
         if debug:
             self.debug_stats = self._loss_acc - acc0
 
@@ -390,8 +386,13 @@ class PPO:
             _lib.check(self._lib.rl_grad_finalize(
                 P(ac.flat_grad[:ac.n_main]), ac.n_main, P(self._stats), P(self._ctrl), P(self._fin_ws), float(B * world),
                 float(A.desired_kl or 0.0), float(A.max_grad_norm), adaptive, P(self._loss_acc), P(kl_slot), stream))
-        _lib.check(self._lib.rl_adam(P(ac.flat), P(g_used), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
-                                     0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
+        if self._fused_adam and ac.use_chain:
+            # Adam + the bf16 operands of every policy layer in one launch
+            ac.adam_shadows(0, ac.n_main, g_used, P(self._ctrl), 0.0, 1, self._steps.data_ptr(), self._main_layers)
+        else:
+            _lib.check(self._lib.rl_adam(P(ac.flat), P(g_used), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(self._ctrl), 0.0, 1,
+                                         0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr(), stream))
+            ac.refresh_shadows(self._main_layers)
 
     def _target(self, B):
         """bf16 [B, 24] copy of the adaptation regression target (lagged schedule only)."""
@@ -435,9 +436,14 @@ class PPO:
         ac, A = self.actor_critic, PPO_Args
         n_ad = ac.n_total - ac.n_main
         off = ac.n_main * 4
+        if self._fused_adam and ac.use_chain:
+            ac.adam_shadows(ac.n_main, n_ad, g_used, None, float(A.adaptation_module_learning_rate), 0,
+                            self._steps.data_ptr() + 8, ac.L_ada)
+            return
         _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_used.data_ptr() + off, ac.flat_m.data_ptr() + off,
                                      ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
                                      0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, _lib.current_stream()))
+        ac.refresh_shadows(ac.L_ada)
 
     def sync_replicas(self):
         """Data parallelism keeps one replica of the learner per rank and only exchanges gradients, so the replicas
@@ -517,7 +523,6 @@ class PPO:
             self._adapt_grads(mb, world, lagged=True)
             self._reduce(allreduce, ac.n_main)
             self._adapt_step(self._g_red if allreduce == "peer" else ac.flat_grad)
-            ac.refresh_shadows(ac.L_ada)
         if world > 1:
             all_reduce_sum_(self._loss_acc)        # loss means span the env shards of every rank
         n_upd = A.num_learning_epochs * A.num_mini_batches
