@@ -238,6 +238,9 @@ typedef struct RlEnvBuffers {
    * of the step kernel - one warp per env over the whole GPU - instead of by the four warps of each 32-env CTA.  Same
    * arithmetic and summation order: identical bits. */
   float* height_mean;
+  /* optional [2] (zero-initialised, owned by the library between launches): tile queue of the persistent step kernel
+   * (env_step_rows.cu) - {next tile, CTAs done}; without it the tiles are dealt round-robin. */
+  uint32_t* tile_queue;
 } RlEnvBuffers;
 
 /* profiling aid: enable / read the globaltimer phase stamps of one CTA of the fused env-step kernel
@@ -246,7 +249,9 @@ typedef struct RlEnvBuffers {
 int rl_debug_env_trace(int32_t enable, uint64_t* out_host16);
 /* testing aid: selects the kernel behind rl_env_step_fused / rl_env_post_physics for the shipped configuration on
  * packed state blocks: 1 = env_step_rows.cu (all tile traffic on TMA; the default), 0 = env_step_quad.cu, -1 = back to
- * the default (environment variable RL_ENV_ROWS).  Returns the previous setting.  Both kernels produce identical bits. */
+ * the default (environment variable RL_ENV_ROWS); 2 / 3 = env_step_rows.cu with its persistent two-buffer variant forced
+ * on / off (default: off - it measured slower; RL_ENV_PERSIST=1).  Returns the previous setting.  All of
+ * them produce identical bits. */
 int rl_debug_env_rows(int32_t mode);
 /* profiling aid: per-CTA globaltimer stamps of the following env_step_rows launches {entry, loads issued, tile landed,
  * phase 1 done, phase 2 done, stores issued, stores read, smid}.  enable > 0: number of CTAs to record (switches tracing

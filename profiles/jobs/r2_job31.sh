@@ -1,0 +1,24 @@
+python - <<'PY'
+import sys, os, json, math, torch
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import bench
+from rapid_locomotion_rl_b200 import _lib
+lib = _lib.lib()
+lib.rl_debug_env_rows(3)
+for case, envs, steps in (("mc_flat", 8192, 500), ("mc_flat", 16384, 500), ("mc_flat", 32768, 300), ("go1", 32768, 300), ("mc_flat", 65536, 200), ("mc_flat", 262144, 100)):
+    bpe = bench.BYTES_PER_ENV_STEP[case]
+    n_rep = max(2, math.ceil(2.0 * bench.L2_BYTES / (envs * bpe)))
+    reps = bench.build_replicas(case, envs, n_rep, "cuda:0")
+    for cfg in ("0,0,0", "500,148,148", "1000,296,296", "1000,592,0"):
+        os.environ["RL_ENV_STAGGER"] = cfg
+        g = bench.time_env_steps(reps, steps, 5)
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print("%s %d stagger=%s: %.2f us/step frac %.3f" % (case, envs, cfg, best / steps * 1e3, envs * bpe / (best / steps * 1e-3) / 1e9 / 6557.1))
+        del g
+    del reps
+    torch.cuda.empty_cache()
+PY

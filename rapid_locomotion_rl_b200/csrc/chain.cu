@@ -298,11 +298,13 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && n_ops > 0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
       const int r = m0 + lr;
+      // (two / three workers: the next op's words are fetched one op ahead; four workers have no registers to spare)
       uint4 n0 = __ldg(ops), n1 = __ldg(ops + 1), n2 = __ldg(ops + 2);
 #pragma unroll 1
       for (int i = 0; i < n_ops; ++i) {
+        if (NW == 4 && i > 0) { n0 = __ldg(ops + 3 * i); n1 = __ldg(ops + 3 * i + 1); n2 = __ldg(ops + 3 * i + 2); }
         const uint4 w0 = n0, w1 = n1, w2 = n2;
-        if (i + 1 < n_ops) { n0 = __ldg(ops + 3 * (i + 1)); n1 = __ldg(ops + 3 * (i + 1) + 1); n2 = __ldg(ops + 3 * (i + 1) + 2); }
+        if (NW != 4 && i + 1 < n_ops) { n0 = __ldg(ops + 3 * (i + 1)); n1 = __ldg(ops + 3 * (i + 1) + 1); n2 = __ldg(ops + 3 * (i + 1) + 2); }
         const uint32_t wait_acc = w0.x & 0xFFFFu, wait_dst = w0.x >> 16, wait_aux = w0.y & 0xFFFFu;
         const uint32_t arrive_acc_free = (w0.y >> 16) & 0xFFu, arrive_dst_ready = w0.y >> 24;
         const uint32_t release_aux = w0.z & 0xFFu, mode = (w0.z >> 8) & 0xFFu;
@@ -324,6 +326,129 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (lane < ncols) b_lo = __ldg(bias + lane);
           if (lane + 32 < ncols) b_hi = __ldg(bias + 32 + lane);
         }
+        if constexpr (NW == 4) {
+          // ---- four workers: 32 accumulator columns at a time (<= 96 registers per thread without spills) ----
+          chain_wait<WAIT_NS_EPI>(bars, wait_acc, it);
+          tc_fence_after();
+#ifndef RL_CHAIN_TRACE_WRITE
+          if (tr) tp[1] = clock64();
+#endif
+          const int nh = ncols > 32 ? 2 : 1;
+          uint8_t* box = smem + dst_off;
+#pragma unroll 1
+          for (int h = 0; h < nh; ++h) {
+            float f[32];
+            {
+              uint32_t v[32];
+              tmem_ld32(lane_addr + tmem_col + 32 * h, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            }
+            if (h == nh - 1 && arrive_acc_free != RL_CHAIN_NONE) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars[arrive_acc_free]);
+            }
+#ifndef RL_CHAIN_TRACE_WRITE
+            if (tr && h == 0) tp[2] = clock64();
+#endif
+            if (has_bias) {
+              __syncwarp();                            // the previous round's broadcast reads are done
+              my_bias[lane] = h ? b_hi : b_lo;
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(my_bias + j);
+                f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+              }
+              if (mode == RL_CHAIN_EPI_BIAS_ELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = elu1(f[j]);
+              }
+            } else if (mode == RL_CHAIN_EPI_DELU) {
+              if (h == 0) chain_wait<WAIT_NS_EPI>(bars, wait_aux, it);
+              const uint8_t* aux = smem + aux_off;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 pk = *reinterpret_cast<const uint4*>(aux + sw_chunk(lr, 4 * h + c));
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 y = __bfloat1622float2(hh[q]);
+                  f[c * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
+                  f[c * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+                }
+              }
+            }
+            if (mode == RL_CHAIN_EPI_BIAS_F32) {
+              if (r < p.rows) {
+                float* dst = p.outputs[out_id] + (size_t)r * out_ld;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = f[j];
+              }
+              break;
+            }
+            if (h == 0) {
+#ifndef RL_CHAIN_TRACE_WRITE
+              if (tr) tp[3] = clock64();
+#else
+              if (tr) tp[0] = clock64();
+#endif
+              if (store_wait_pending >= 0) {          // a TMA store this warp issued earlier may still be reading its rows
+                if (lane == 0) bulk_wait_read_dyn(store_wait_pending);
+                __syncwarp();
+              }
+#ifdef RL_CHAIN_TRACE_WRITE
+              if (tr) tp[1] = clock64();
+#endif
+              chain_wait<WAIT_NS_EPI>(bars, wait_dst, it);
+#ifdef RL_CHAIN_TRACE_WRITE
+              if (tr) tp[2] = clock64();
+#endif
+            }
+            if (dst_col0 == 0 && ncols == 64) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[c * 8], f[c * 8 + 1]), p1 = __floats2bfloat162_rn(f[c * 8 + 2], f[c * 8 + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[c * 8 + 4], f[c * 8 + 5]), p3 = __floats2bfloat162_rn(f[c * 8 + 6], f[c * 8 + 7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(box + sw_chunk(lr, 4 * h + c)) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                  const int col = dst_col0 + j;
+                  *reinterpret_cast<__nv_bfloat16*>(box + sw_chunk(lr, col >> 3) + (col & 7) * 2) = __float2bfloat16(f[j]);
+                }
+              }
+            }
+          }
+          if (mode == RL_CHAIN_EPI_BIAS_F32) {
+            if (tr) tp[2] = tp[3] = tp[4] = clock64();
+            continue;
+          }
+#ifdef RL_CHAIN_TRACE_WRITE
+          if (tr) tp[3] = clock64();
+#endif
+          fence_async_smem();                      // generic-proxy writes -> visible to tcgen05.mma / TMA
+          __syncwarp();
+          if (lane == 0) {
+            if (arrive_dst_ready != RL_CHAIN_NONE) mbar_arrive(&bars[arrive_dst_ready]);
+            if (release_aux != RL_CHAIN_NONE) worker_arrive(bars, tickets, release_aux);
+            if (store_tensor != RL_CHAIN_NONE) {
+              if (m0 + 32 * g < p.rows) tma_store_2d(&p.tmaps_st[store_tensor], box + 4096 * g, store_col0, m0 + 32 * g);
+              bulk_commit();
+              if (release_after_store != RL_CHAIN_NONE) {
+                bulk_wait_read_n<0>();
+                worker_arrive(bars, tickets, release_after_store);
+              }
+            }
+          }
+        } else {
         // ---- accumulator columns -> registers ----
         chain_wait<WAIT_NS_EPI>(bars, wait_acc, it);
         tc_fence_after();
@@ -461,6 +586,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
               worker_arrive(bars, tickets, release_after_store);
             }
           }
+        }
         }
         if (tr) tp[4] = clock64();
       }

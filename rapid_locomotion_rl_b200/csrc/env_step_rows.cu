@@ -25,6 +25,7 @@
 // Used when: standard configuration (see launch_step_quad's is_std), num_envs % 32 == 0, the state
 // pointers form the packed blocks; otherwise the caller falls back to env_step_quad.cu.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <map>
@@ -35,6 +36,7 @@
 namespace rl {
 
 int make_tmap_f32_rows(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n, uint32_t box_rows);
+extern int g_rows_persist_mode;    // rl_debug_env_rows (env_step_quad.cu)
 
 static bool rows_trace_on = false;
 namespace rows {
@@ -52,6 +54,8 @@ struct RowsArgs {
   StepArgs a;
   CUtensorMap m_ro, m_rw, m_wo, m_es12, m_es1, m_cs12, m_cs5;
   unsigned long long* trace;     // profiling aid (rl_debug_env_rows_trace): 8 globaltimer stamps per CTA, or null
+  int stagger_ns, stagger_from, stagger_group;  // CTAs with blockIdx >= stagger_from issue their copies stagger_ns later (0: off);
+                                                // stagger_group > 0: another stagger_ns for every further `stagger_group` CTAs
 };
 constexpr int TRACE_STAMPS = 8;
 __device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
@@ -97,59 +101,44 @@ struct Lay {
   }
 };
 
-template <bool FUSE, int MINB>
-__global__ void __launch_bounds__(QTHREADS, MINB)
-env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
-  const RlEnvCfg& cfg = args.a.cfg;
-  const RlEnvBuffers& b = args.a.b;
-  const int N = cfg.num_envs, NB = cfg.num_bodies;
-  const int tile0 = blockIdx.x * QT;
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int e = tile0 + lane;
-  constexpr int W = 42;
-  const float co = cfg.clip_obs;
+// shared-memory pointers of one tile buffer + the per-thread constants every part of the step uses
+#define RL_ROWS_TILE_SETUP(BUF)                                                                          \
+  const RlEnvCfg& cfg = args.a.cfg;                                                                      \
+  const RlEnvBuffers& b = args.a.b;                                                                      \
+  const int N = cfg.num_envs, NB = cfg.num_bodies;                                                       \
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;                                            \
+  const int e = tile0 + lane;                                                                            \
+  constexpr int W = 42;                                                                                  \
+  const float co = cfg.clip_obs;                                                                         \
+  uint8_t* const smem_raw = (BUF);                                                                       \
+  const Lay L(NB, FUSE);                                                                                 \
+  float* s_ro = reinterpret_cast<float*>(smem_raw + L.ro);                                               \
+  float* s_rw = reinterpret_cast<float*>(smem_raw + L.rw);                                               \
+  float* s_es = reinterpret_cast<float*>(smem_raw + L.es);                                               \
+  float* s_cs = reinterpret_cast<float*>(smem_raw + L.cs);                                               \
+  float* s_wo = reinterpret_cast<float*>(smem_raw + L.wo);                                               \
+  float* s_root = reinterpret_cast<float*>(smem_raw + L.root);                                           \
+  float* s_dof = reinterpret_cast<float*>(smem_raw + L.dof);                                             \
+  float* s_con = reinterpret_cast<float*>(smem_raw + L.con);                                             \
+  float* s_act = reinterpret_cast<float*>(smem_raw + L.act);                                             \
+  float* s_tq_in = reinterpret_cast<float*>(smem_raw + L.tq_in);                                         \
+  float* s_obs = s_dof;                                   /* output rows re-use the input tile */        \
+  float* s_priv = s_obs + QT * W;                                                                        \
+  float* s_tq = s_priv + QT * RL_PRIV_DIM;                                                               \
+  float* s_part = reinterpret_cast<float*>(smem_raw + L.x);        /* [NPART][4][32] */                  \
+  float* s_coll = s_part + NPART * 4 * QT;                /* [32] */                                     \
+  float* s_air = s_coll + QT;                             /* [32] */                                     \
+  float* s_r = reinterpret_cast<float*>(smem_raw + L.r);    /* [12][32] per-term rewards */              \
+  (void)N; (void)e; (void)co; (void)s_ro; (void)s_rw; (void)s_es; (void)s_cs; (void)s_wo; (void)s_root; \
+  (void)s_con; (void)s_act; (void)s_tq_in; (void)s_obs; (void)s_priv; (void)s_tq; (void)s_part;          \
+  (void)s_coll; (void)s_air; (void)s_r; (void)w; (void)lane; (void)b; (void)tid
 
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_root_dirty;
-  const Lay L(NB, FUSE);
-  float* s_ro = reinterpret_cast<float*>(smem_raw + L.ro);
-  float* s_rw = reinterpret_cast<float*>(smem_raw + L.rw);
-  float* s_es = reinterpret_cast<float*>(smem_raw + L.es);
-  float* s_cs = reinterpret_cast<float*>(smem_raw + L.cs);
-  float* s_wo = reinterpret_cast<float*>(smem_raw + L.wo);
-  float* s_root = reinterpret_cast<float*>(smem_raw + L.root);
-  float* s_dof = reinterpret_cast<float*>(smem_raw + L.dof);
-  float* s_con = reinterpret_cast<float*>(smem_raw + L.con);
-  float* s_act = reinterpret_cast<float*>(smem_raw + L.act);
-  float* s_tq_in = reinterpret_cast<float*>(smem_raw + L.tq_in);
-  float* s_obs = s_dof;                                   // output rows re-use the input tile
-  float* s_priv = s_obs + QT * W;
-  float* s_tq = s_priv + QT * RL_PRIV_DIM;
-  float* s_part = reinterpret_cast<float*>(smem_raw + L.x);        // [NPART][4][32]
-  float* s_coll = s_part + NPART * 4 * QT;                // [32]
-  float* s_air = s_coll + QT;                             // [32]
-  float* s_r = reinterpret_cast<float*>(smem_raw + L.r);    // [12][32] per-term rewards
-
-  // Programmatic dependent launch: let the NEXT kernel of the stream start launching its CTAs now (they run their
-  // prologue and park in griddepcontrol.wait until this grid has completed and flushed), and wait for the PREVIOUS
-  // kernel before the first global access.  Hides the launch latency / CTA ramp between consecutive steps; both
-  // instructions are no-ops when the launch does not carry the programmatic-serialization attribute.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  stamp(args.trace, 0);
-  if (args.trace && tid == 0) {
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    args.trace[(size_t)blockIdx.x * TRACE_STAMPS + 7] = smid;
-  }
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
-    s_root_dirty = 0;
-  }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // ---- one thread issues every copy of the tile ----------------------------------------------------------
-  if (tid == 0) {
+// ---- one thread issues every copy of a tile: 11 requests landing on `bar` ------------------------------------
+template <bool FUSE>
+__device__ __forceinline__ void issue_tile_loads(const RowsArgs& args, uint8_t* buf, uint64_t* bar, int tile0) {
+  RL_ROWS_TILE_SETUP(buf);
+  uint64_t& s_bar = *bar;
+  {
     const uint32_t bytes = (uint32_t)((RO_ROWS + RW_ROWS + ES_ROWS + CS_ROWS) * ROWB +
                                       QT * (13 + 24 + NB * 3 + ND + (FUSE ? 0 : ND)) * 4);
     mbar_expect_tx(&s_bar, bytes);
@@ -166,7 +155,16 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     tma_load_rows(s_cs, &args.m_cs12, tile0, 0, &s_bar);
     tma_load_rows(s_cs + 12 * QT, &args.m_cs5, tile0, RL_ROW_EXTRAS, &s_bar);
   }
-  stamp(args.trace, 1);
+}
+
+// ---- the step of one tile: waits for `bar` (phase `parity`), phases 1 - 3, stores issued (one bulk group) ----
+template <bool FUSE>
+__device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, uint64_t* bar, uint32_t parity, int tile0,
+                                          int* s_root_dirty_p, unsigned long long* trace_p) {
+  RL_ROWS_TILE_SETUP(buf);
+  uint64_t& s_bar = *bar;
+  int& s_root_dirty = *s_root_dirty_p;
+  struct { unsigned long long* trace; } targs{trace_p};
   // small per-env scalars with their own dtypes: plain coalesced loads
   const uint64_t rng_step = args.a.step + (b.step_state ? b.step_state[0] : 0ull);
   int ep = (int)b.episode_length_buf[e];
@@ -179,14 +177,14 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     const uint32_t bar = smem_u32(&s_bar);
     while (!ok) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
       if (!ok && ++spins > (1u << 22)) {
-        if (tid == 0) printf("env_step_rows_kernel: tile %d never landed\n", (int)blockIdx.x);
+        if (tid == 0) printf("env_step_rows_kernel: tile %d never landed\n", tile0 / QT);
         __trap();
       }
     }
   }
-  stamp(args.trace, 2);
+  stamp(targs.trace, 2);
   ep += 1;                              // :152
 
   // ---- teleport (:768-791) by warp 0 ------------------------------------------------------------------------
@@ -364,7 +362,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     }
   }
   __syncthreads();
-  stamp(args.trace, 3);
+  stamp(targs.trace, 3);
 
   // =================================== phase 2 ===========================================================
   // warp w evaluates terms w, w + 4, w + 8 (reward_names order of the shipped configuration), adds them to its
@@ -436,7 +434,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   if (dirty) s_root_dirty = 1;
   fence_async_smem();
   __syncthreads();
-  stamp(args.trace, 4);
+  stamp(targs.trace, 4);
 
   // =================================== stores + phase 3 ==================================================
   if (tid == 0) {
@@ -462,10 +460,115 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     b.episode_sums[RL_ROW_TOTAL * N + e] = s_es[12 * QT + lane] + rew;
     b.rew_buf[e] = rew;
   }
+}
+
+template <bool FUSE, int MINB>
+__global__ void __launch_bounds__(QTHREADS, MINB)
+env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_root_dirty;
+  const int tile0 = blockIdx.x * QT;
+  const int tid = threadIdx.x;
+  const RlEnvBuffers& b = args.a.b;
+
+  // Programmatic dependent launch: let the NEXT kernel of the stream start launching its CTAs now (they run their
+  // prologue and park in griddepcontrol.wait until this grid has completed and flushed), and wait for the PREVIOUS
+  // kernel before the first global access.  Hides the launch latency / CTA ramp between consecutive steps; both
+  // instructions are no-ops when the launch does not carry the programmatic-serialization attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  stamp(args.trace, 0);
+  if (args.trace && tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    args.trace[(size_t)blockIdx.x * TRACE_STAMPS + 7] = smid;
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    s_root_dirty = 0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid == 0) {
+    // time-staggered second group: its requests queue up BEHIND the first group's instead of competing with them, so
+    // the first group's tiles land early and are computed while the second group's bytes stream in
+    if (args.stagger_ns > 0 && (int)blockIdx.x >= args.stagger_from) {
+      const int grp = args.stagger_group > 0 ? 1 + ((int)blockIdx.x - args.stagger_from) / args.stagger_group : 1;
+      __nanosleep((unsigned)(args.stagger_ns * grp));
+    }
+    issue_tile_loads<FUSE>(args, smem_dyn, &s_bar, tile0);
+  }
+  stamp(args.trace, 1);
+  tile_body<FUSE>(args, smem_dyn, &s_bar, 0u, tile0, &s_root_dirty, args.trace);
   stamp(args.trace, 5);
   if (tid == 0) {
     bulk_wait_read0();                 // the stores have read their shared-memory source
     stamp(args.trace, 6);
+    if (b.step_state) {
+      const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
+      if (done == gridDim.x - 1) {
+        b.step_state[1] = 0;
+        atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
+      }
+    }
+  }
+}
+
+// ---- persistent variant: a few CTAs per SM, each with TWO tile buffers ---------------------------------------------
+// With one tile per CTA and the whole grid resident (32768 envs = 1024 CTAs, 7 per SM) every tile is requested in the
+// first microsecond, all of them land together ~5 us later, and only then does anybody compute: load and compute phases
+// are serial (profiles/r02_env_step.md).  Here a CTA keeps one tile loading while it computes the other: while it works
+// on buffer k & 1, the copies of its next tile fly into the other buffer, and the results of the tile before leave
+// through bulk stores.  Tiles are handed out by a queue in global memory (RlEnvBuffers.tile_queue; without it CTA c takes
+// tiles c, c + grid, ...): the CTAs of an SM drift apart, so at any moment some are loading and some computing.
+template <bool FUSE>
+__global__ void __launch_bounds__(QTHREADS, 3)
+env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_bytes) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int s_root_dirty;
+  __shared__ int s_tile[2];
+  const int tid = threadIdx.x;
+  const RlEnvBuffers& b = args.a.b;
+  const int n_tiles = args.a.cfg.num_envs / QT;
+  unsigned int* q = b.tile_queue;
+  auto grab = [&](int cur) -> int {            // thread 0 only
+    const int nx = q ? (int)(gridDim.x + atomicAdd(q, 1u)) : cur + (int)gridDim.x;
+    return nx < n_tiles ? nx : -1;
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    const int t0 = blockIdx.x;
+    s_tile[0] = t0;
+    issue_tile_loads<FUSE>(args, smem_dyn, &s_bar[0], t0 * QT);
+    const int t1 = grab(t0);
+    s_tile[1] = t1;
+    if (t1 >= 0) issue_tile_loads<FUSE>(args, smem_dyn + buf_bytes, &s_bar[1], t1 * QT);
+  }
+  __syncthreads();
+  for (int k = 0;; ++k) {
+    const int bi = k & 1;
+    const int tile = s_tile[bi];
+    if (tile < 0) break;                       // uniform: the queue is empty
+    uint8_t* buf = smem_dyn + bi * buf_bytes;
+    if (tid == 0) s_root_dirty = 0;            // (tile_body's first barrier publishes it)
+    tile_body<FUSE>(args, buf, &s_bar[bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
+    __syncthreads();                           // every thread is done with this buffer (phase 3 read it)
+    if (tid == 0) {
+      bulk_wait_read0();                       // ... and so are its bulk stores: the buffer may be refilled
+      const int tn = grab(tile);
+      s_tile[bi] = tn;                         // read two iterations from now (a barrier lies in between)
+      if (tn >= 0) issue_tile_loads<FUSE>(args, buf, &s_bar[bi], tn * QT);
+    }
+  }
+  if (tid == 0) {
+    bulk_wait_read0();
+    if (q) {
+      const unsigned int done = atomicAdd(q + 1, 1u);
+      if (done == gridDim.x - 1) { q[0] = 0u; q[1] = 0u; __threadfence(); }
+    }
     if (b.step_state) {
       const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
       if (done == gridDim.x - 1) {
@@ -522,6 +625,19 @@ static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
   return check_launch("env_step_rows_kernel");
 }
 
+template <bool FUSE>
+static int launch_persistent(const RowsArgs& ra, int buf_bytes, int grid, cudaStream_t st) {
+  static size_t configured = 0;
+  const size_t smem = 2 * (size_t)buf_bytes;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(env_step_rows_persistent_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = smem;
+  }
+  env_step_rows_persistent_kernel<FUSE><<<grid, QTHREADS, smem, st>>>(ra, buf_bytes);
+  return check_launch("env_step_rows_persistent_kernel");
+}
+
 }  // namespace rows
 
 static unsigned long long* g_trace_buf = nullptr;
@@ -574,6 +690,7 @@ int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
   RowsArgs ra;
   ra.a = a;
   ra.trace = (rows_trace_on && g_trace_buf && a.cfg.num_envs / QT <= g_trace_ctas) ? g_trace_buf : nullptr;
+  ra.stagger_ns = 0; ra.stagger_from = 0; ra.stagger_group = 0;      // set below, once the grid shape is known
   const RlEnvBuffers& b = a.b;
   const uint64_t N = (uint64_t)a.cfg.num_envs;
   int rc;
@@ -586,10 +703,53 @@ int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
   if ((rc = cached_map(&ra.m_cs5, b.command_sums, RL_COMMAND_ROWS, N, 5)) != RL_OK) return rc;
   const Lay L(a.cfg.num_bodies, fuse);
   const size_t smem = (size_t)L.total;
+  {
+    // persistent variant (two tile buffers per CTA, 3 CTAs per SM): opt-in (RL_ENV_PERSIST=1 or rl_debug_env_rows(2)).
+    // Measured against one tile per CTA (us per launch): 32768 envs 18.8 vs 13.6, 262144 envs 79.2 vs 66.7 - a tile takes
+    // ~4.3 us through the 4 warps of one CTA (long dependent chains: Philox, sqrt, exp), so 12 resident warps per SM
+    // compute slower than 28 even though their loads are hidden; kept because it is bit-identical and shows the bound
+    static int persist = -2, sms = 0;
+    if (persist == -2) {
+      const char* e = getenv("RL_ENV_PERSIST");
+      persist = e ? atoi(e) : -1;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    const int n_tiles = a.cfg.num_envs / QT;
+    const int mode = g_rows_persist_mode >= 0 ? g_rows_persist_mode : persist;
+    if (mode == 1) {
+      const int buf_bytes = (L.total + 127) & ~127;
+      const int grid = n_tiles < 3 * sms ? n_tiles : 3 * sms;
+      return fuse ? rows::launch_persistent<true>(ra, buf_bytes, grid, st) : rows::launch_persistent<false>(ra, buf_bytes, grid, st);
+    }
+  }
   // 7 CTAs / SM when the tile fits (13 bodies), else 6
   static int force = -1;
   if (force < 0) { const char* m = getenv("RL_ROWS_MINB"); force = m ? atoi(m) : 0; }
   const bool seven = force == 7 || (force == 0 && 7 * (smem + 1024 + 128) <= 233472);
+  {
+    // Time-staggered copies for a grid that is resident all at once (one wave, several CTAs per SM): with every tile
+    // requested at t = 0 they all land together ~5 us later and nobody computes before that.  The CTAs of the later
+    // "rows" of the wave (blockIdx >= 2 x SMs, then every further 2 x SMs) sleep 1 / 2 / .. us before they issue, so their
+    // requests queue up BEHIND the first ones: the early tiles land sooner and are computed while the rest streams in.
+    // Measured per launch (us, off -> on): 16384 envs 9.95 -> 9.27, 32768 envs 13.63 -> 12.29, Go1 32768 14.79 -> 12.76;
+    // deeper grids (waves start as CTAs retire) and grids of <= 2 CTAs per SM are left alone.  RL_ENV_STAGGER=
+    // "ns,first_cta,ctas_per_group" overrides ("0": off).
+    static int sms = 0, env_ns = -1, env_from = 0, env_group = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+      const char* e = getenv("RL_ENV_STAGGER");
+      if (e) sscanf(e, "%d,%d,%d", &env_ns, &env_from, &env_group);
+    }
+    const int n_tiles = a.cfg.num_envs / QT;
+    if (env_ns >= 0) { ra.stagger_ns = env_ns; ra.stagger_from = env_from; ra.stagger_group = env_group; }
+    else if (n_tiles > 2 * sms && n_tiles <= (seven ? 7 : 6) * sms) { ra.stagger_ns = 1000; ra.stagger_from = 2 * sms; ra.stagger_group = 2 * sms; }
+  }
   if (seven) return fuse ? launch_inst<true, 7>(ra, smem, st) : launch_inst<false, 7>(ra, smem, st);
   return fuse ? launch_inst<true, 6>(ra, smem, st) : launch_inst<false, 6>(ra, smem, st);
 }

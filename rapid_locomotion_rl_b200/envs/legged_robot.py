@@ -299,6 +299,8 @@ class LeggedRobot:
             b.height_mean = P(self._height_mean)
         else:
             b.height_mean = None
+        self._tile_queue = torch.zeros(2, dtype=torch.int32, device=self.device)
+        b.tile_queue = P(self._tile_queue)
         return b
 
     def use_device_step_counter(self, enable=True):

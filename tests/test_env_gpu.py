@@ -354,8 +354,9 @@ def test_host_io_zero_copy_matches_device_step():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("case,n", [("mc_flat", 4000), ("go1", 4128), ("mc_flat", 32768)])
-def test_rows_kernel_matches_quad_kernel(case, n):
+@pytest.mark.parametrize("case,n,rows_mode", [("mc_flat", 4000, 1), ("go1", 4128, 1), ("mc_flat", 32768, 3), ("mc_flat", 32768, 2),
+                                              ("go1", 4128, 2), ("mc_flat", 96, 2), ("mc_flat", 65536, 2)])
+def test_rows_kernel_matches_quad_kernel(case, n, rows_mode):
     """The all-TMA kernel (csrc/env_step_rows.cu, packed state blocks) and the one-warp-per-leg kernel it replaces give
     identical bits for every output and every piece of state: fused step and post-physics entry, Philox noise (no
     injection), three consecutive steps (the second re-draws Kp / Kd / motor strength for a third of the envs)."""
@@ -363,7 +364,8 @@ def test_rows_kernel_matches_quad_kernel(case, n):
     from rapid_locomotion_rl_b200.sim import synthetic_state
     lib = _lib.lib()
     results = []
-    for mode in (1, 0):
+    # rows_mode: 1 = automatic, 2 = persistent two-buffer variant (tile queue), 3 = one tile per CTA
+    for mode in (rows_mode, 0):
         prev = lib.rl_debug_env_rows(mode)
         try:
             env, cfg, robot, terrain = make_env(case, n)
