@@ -191,9 +191,10 @@ class ActorCritic(nn.Module):
             arr_i(*[L.ld_wb for L in Ls]), arr_i(*[L.ld_wbt for L in Ls]), n, _lib.current_stream()))
         self._cache_key = None
 
-    def adam_shadows(self, start, n, grad, ctrl, lr_fixed, use_ctrl, step_dev, layers):
+    def adam_shadows(self, start, n, grad, ctrl, lr_fixed, use_ctrl, step_dev, layers, grad_ptr=None):
         """One launch: Adam on flat[start : start + n] (rl_adam's arguments) and the bf16 operands of `layers`, whose
-        master weights lie inside that range (csrc/ppo.cu adam_shadows_kernel)."""
+        master weights lie inside that range (csrc/ppo.cu adam_shadows_kernel).  grad_ptr: address of the range's
+        gradient when it does not live in `grad` (the flat gradient buffer) at the same offset."""
         key = (start, tuple(id(L) for L in layers))
         tab = self._adam_tabs.get(key) if hasattr(self, "_adam_tabs") else None
         if tab is None:
@@ -207,12 +208,37 @@ class ActorCritic(nn.Module):
             self._adam_tabs[key] = tab
         off = 4 * start
         _lib.check(self._lib.rl_adam_shadows(
-            self.flat.data_ptr() + off, grad.data_ptr() + off, self.flat_m.data_ptr() + off, self.flat_v.data_ptr() + off, n,
+            self.flat.data_ptr() + off, (grad.data_ptr() + off) if grad_ptr is None else grad_ptr,
+            self.flat_m.data_ptr() + off, self.flat_v.data_ptr() + off, n,
             ctrl, float(lr_fixed), int(use_ctrl), 0.9, 0.999, 1e-8, 0, 1.0, step_dev, *tab, _lib.current_stream()))
         self._cache_key = None
 
     def _offset_of_data(self, t):
         return (t.data_ptr() - self.flat.data_ptr()) // 4
+
+    def split_adaptation_grad(self):
+        """Moves the adaptation module's gradient out of the flat buffer into one of its own (returned; same internal
+        layout as flat_grad[n_main : n_total]): with several GPUs it is reduced by a collective of its own, on the side
+        branch, while the policy gradient's all-reduce runs on the main path (PPO.minibatch_step)."""
+        if getattr(self, "ada_grad", None) is not None:
+            return self.ada_grad
+        n_ad = self.n_total - self.n_main
+        g = torch.zeros(n_ad, device=self.device_)
+        base = self.flat_grad.data_ptr() + 4 * self.n_main
+
+        def move(v):
+            off = (v.data_ptr() - base) // 4
+            assert 0 <= off and off + v.numel() <= n_ad
+            return g[off:off + v.numel()].view(v.shape)
+        g.copy_(self.flat_grad[self.n_main:self.n_total])
+        self.flat_grad[self.n_main:self.n_total].zero_()
+        for L in self.L_ada:
+            L.gw, L.gb = move(L.gw), move(L.gb)
+        for k, v in list(self._grad_view.items()):
+            if base <= v.data_ptr() < base + 4 * n_ad:
+                self._grad_view[k] = move(v)
+        self.ada_grad = g
+        return g
 
     def load_state_dict(self, state_dict, strict=True):
         out = super().load_state_dict(state_dict, strict=strict)

@@ -66,6 +66,7 @@ class PPO:
         self._graph_ws_gen = -1
         self._chunk_stream = self._ev_chunk_fork = self._ev_chunk_join = None
         self._fused_adam = os.environ.get("RL_PPO_FUSED_ADAM", "1") != "0"      # Adam + bf16 operands in one launch
+        self._ada_g = None          # several GPUs over NCCL: the adaptation gradient in a buffer of its own (enable_side_comm)
         self._steps = torch.zeros(4, dtype=torch.int32, device=dev)    # {main count, ticket, adaptation count, ticket}
         self._graph = None          # CUDA graph of one minibatch step (single-GPU path)
         self._graph_B = 0
@@ -78,6 +79,21 @@ class PPO:
         _lib.check(self._lib.rl_gemm_init())
         ac = actor_critic
         self._main_layers = ac.L_enc + [ac.L_cat] + ac.L_act + ac.L_cri
+
+    def enable_side_comm(self):
+        """Several GPUs, NCCL (opt-in, RL_PPO_SIDE_COMM=1): the adaptation module's gradient gets a buffer of its own and
+        is summed over a SECOND communicator from the side branch, concurrently with the policy path - so that the one
+        all-reduce per minibatch need not wait for the side branch (adaptation forward / loss / dgrad / wgrad of the
+        previous minibatch, running at low priority in whatever the policy kernels leave free).  Identical results
+        (tests/multigpu_worker.py), but measured slower than the single collective: see update().  Collective (creates
+        the group and warms its communicator up outside any graph capture)."""
+        from ..sharding import side_all_reduce_sum_
+        if self._ada_g is None:
+            assert self._peer is None, "the peer all-reduce keeps the gradient in one mapped buffer"
+            self._ada_g = self.actor_critic.split_adaptation_grad()
+            warm = torch.zeros(8, device=self.device)
+            side_all_reduce_sum_(warm)
+            torch.cuda.synchronize()
 
     def enable_peer_allreduce(self):
         """Multi-GPU: moves the gradient accumulation buffer into memory every rank has mapped and switches the
@@ -229,9 +245,13 @@ class PPO:
                 self._side.wait_event(self._ev_fork)
                 if pending:
                     self._adapt_grads(B, world, lagged=True, loss_event=self._ev_loss)
-                    if allreduce is None:
-                        # one GPU: the adaptation module's optimiser step stays on the side branch too (nothing on the
-                        # policy path reads its weights, gradient range or step counter)
+                    if allreduce is None or self._ada_g is not None:
+                        # the adaptation module's optimiser step stays on the side branch too (nothing on the policy path
+                        # reads its weights, gradient or step counter); several GPUs: its gradient is summed here, over
+                        # the side communicator (enable_side_comm)
+                        if allreduce is not None:
+                            from ..sharding import side_all_reduce_sum_
+                            side_all_reduce_sum_(self._ada_g)
                         self._adapt_step(g_used)
                     self._ev_grads.record()
                 _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
@@ -311,7 +331,8 @@ class PPO:
         self._wgrad_flush()
         # ---- data-parallel reduction: ONE call over [policy | adaptation | KL sum].  In the lagged
         # schedule the adaptation range holds minibatch i-1's gradient (joined here); serially it is still zero ----
-        early = lag and pending and allreduce is not None      # several GPUs: the adaptation gradient rides in the ONE call
+        # several GPUs without the side communicator: the adaptation gradient rides in the ONE call
+        early = lag and pending and allreduce is not None and self._ada_g is None
         if early:
             torch.cuda.current_stream().wait_event(self._ev_grads)
         self._reduce(allreduce, 0, norm_n=ac.n_main)
@@ -337,7 +358,7 @@ class PPO:
             self._adapt_grads(B, world, lagged=False)
             self._reduce(allreduce, ac.n_main)
             if debug:
-                self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total]
+                self.debug_grad[ac.n_main:] = g_used[ac.n_main:ac.n_total] if self._ada_g is None else self._ada_g
             self._adapt_step(g_used)
         if debug:
             self.debug_stats = self._loss_acc - acc0
@@ -366,6 +387,12 @@ class PPO:
             # ONE kernel over NVLink peer memory (csrc/peer_allreduce.cu): the sum, the squared norm of the policy part
             # and the zeroing of the accumulation buffer
             self._peer.all_reduce(self._g_red, norm_n=norm_n, start=start)
+        elif self._ada_g is not None:
+            # (the adaptation gradient lives in its own buffer: the flat buffer's adaptation range stays zero)
+            if start == 0:
+                allreduce(ac._grad_store[:ac.n_total + 4])
+            else:
+                allreduce(self._ada_g)
         else:
             allreduce(ac._grad_store[start:ac.n_total + 4])
 
@@ -436,11 +463,12 @@ class PPO:
         ac, A = self.actor_critic, PPO_Args
         n_ad = ac.n_total - ac.n_main
         off = ac.n_main * 4
+        g_ptr = (g_used.data_ptr() + off) if self._ada_g is None else self._ada_g.data_ptr()
         if self._fused_adam and ac.use_chain:
             ac.adam_shadows(ac.n_main, n_ad, g_used, None, float(A.adaptation_module_learning_rate), 0,
-                            self._steps.data_ptr() + 8, ac.L_ada)
+                            self._steps.data_ptr() + 8, ac.L_ada, grad_ptr=g_ptr)
             return
-        _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_used.data_ptr() + off, ac.flat_m.data_ptr() + off,
+        _lib.check(self._lib.rl_adam(ac.flat.data_ptr() + off, g_ptr, ac.flat_m.data_ptr() + off,
                                      ac.flat_v.data_ptr() + off, n_ad, None, float(A.adaptation_module_learning_rate), 0,
                                      0.9, 0.999, 1e-8, 0, 1.0, self._steps.data_ptr() + 8, _lib.current_stream()))
         ac.refresh_shadows(ac.L_ada)
@@ -468,6 +496,10 @@ class PPO:
             if self._peer is None:
                 self.enable_peer_allreduce()
             allreduce = "peer"
+        elif world > 1 and os.environ.get("RL_PPO_SIDE_COMM", "0") == "1" and self._peer is None:
+            # opt-in: measured SLOWER than the one collective per minibatch (2 GPUs, 4000 envs each: 8.71 vs 8.51 ms per
+            # update - a second latency-bound NCCL launch per step costs more than the join it removes)
+            self.enable_side_comm()
         batch = st.num_envs * st.num_transitions_per_env
         mb = batch // A.num_mini_batches
         indices = torch.randperm(A.num_mini_batches * mb, device=self.device)   # ONE permutation for all epochs (:103)
@@ -488,7 +520,8 @@ class PPO:
             self._target(mb)
             self._idx_buf = torch.zeros(mb, dtype=torch.long, device=self.device)
             torch.cuda.synchronize()
-            state = (ac.flat, ac.flat_m, ac.flat_v, ac._grad_store, self._ctrl, self._steps, self._loss_acc, self._stats)
+            state = (ac.flat, ac.flat_m, ac.flat_v, ac._grad_store, self._ctrl, self._steps, self._loss_acc, self._stats) + \
+                ((self._ada_g,) if self._ada_g is not None else ())
             snap = [t.clone() for t in state]
             # capture on a high-priority stream: kernel nodes keep their stream's priority, so the policy path's CTAs
             # are placed before those of the side branch (adaptation module), which only fills what is left

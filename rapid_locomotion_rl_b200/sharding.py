@@ -40,6 +40,30 @@ def all_reduce_sum_(*tensors):
         d.all_reduce(t, op=d.ReduceOp.SUM)
 
 
+_side_group = None
+
+
+def side_group():
+    """A SECOND process group (its own NCCL communicator) for collectives issued from a side stream concurrently with
+    those of the default group: the adaptation module's gradient all-reduce of PPO.update, which must not be ordered
+    against the policy gradient's.  Collective: every rank must call it at the same point (first use)."""
+    global _side_group
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return None
+    if _side_group is None:
+        _side_group = d.new_group(backend=d.get_backend())
+    return _side_group
+
+
+def side_all_reduce_sum_(t):
+    """In-place SUM all-reduce over the side group (see side_group)."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return
+    d.all_reduce(t, op=d.ReduceOp.SUM, group=side_group())
+
+
 def broadcast_(*tensors, src=0):
     """In-place broadcast of each tensor from rank `src` (replica initialisation: PPO.sync_replicas); no-op for a
     single process."""

@@ -78,6 +78,26 @@ def main():
     assert all(torch.equal(peers_flat[0], t) for t in peers_flat), "ranks diverged on the peer path"
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
+
+    # ---- the whole update() (CUDA-graph replay, adaptation module one call behind on the side branch): its gradient
+    # summed over the side communicator (the default) must give what the single all-reduce per minibatch gives ----
+    def run_update(side):
+        os.environ["RL_PPO_SIDE_COMM"] = "1" if side else "0"
+        acu, ppou = make(N, slice(s0, s0 + cnt))
+        ppou.storage.compute_returns(last_values[s0:s0 + cnt].to(dev), PPO_Args.gamma, PPO_Args.lam)
+        torch.manual_seed(5); torch.cuda.manual_seed(5)
+        ppou.update()
+        torch.cuda.synchronize()
+        assert (ppou._ada_g is not None) == side
+        out = acu.flat.clone()
+        ppou.release_graphs()
+        return out
+    fu_side, fu_one = run_update(True), run_update(False)
+    du = (fu_side - fu_one).abs().max().item()
+    assert du <= 2e-5, "update() over the side communicator differs from the one-collective schedule: %g" % du
+    both = [torch.zeros_like(fu_side) for _ in range(world)]
+    dist.all_gather(both, fu_side)
+    assert all(torch.equal(both[0], t) for t in both), "ranks diverged in update() (side communicator)"
     adv_local = ppo.storage.advantages.clone()
     adv_all = [torch.zeros_like(adv_local) for _ in range(world)]
     dist.all_gather(adv_all, adv_local)
@@ -110,8 +130,8 @@ def main():
         assert diff <= 2.5e-3, "sharded step differs from the single-process step: %g" % diff     # |dw| <= lr per Adam step
         cos = torch.nn.functional.cosine_similarity(ac1.flat - ppo1_init(dev), flat - ppo1_init(dev), dim=0).item()
         assert cos > 0.98, cos
-        print("MULTIGPU OK world=%d max|dw diff|=%.3g update cosine=%.4f; peer vs NCCL: %.3g after 1 step, %.3g after 4" %
-              (world, diff, cos, d1, d4))
+        print("MULTIGPU OK world=%d max|dw diff|=%.3g update cosine=%.4f; peer vs NCCL: %.3g after 1 step, %.3g after 4; "
+              "update() side communicator vs one collective: %.3g" % (world, diff, cos, d1, d4, du))
     dist.barrier()
     dist.destroy_process_group()
 
