@@ -435,7 +435,7 @@ def run_ours(args):
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
-                     "kernel": "env_step_quad_kernel<FUSE=true,MINB,STD>", "algorithmic_bytes_per_launch": args.envs * bpe},
+                     "kernel": "rows::env_step_rows_kernel<FUSE=true,MINB=7> (csrc/env_step_rows.cu)", "algorithmic_bytes_per_launch": args.envs * bpe},
         "also": also,
         "ppo": ppo,
         "runner": runner,
@@ -449,7 +449,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ppo_bench(n_envs, T, device, world, pk, iters=3):
+def ppo_bench(n_envs, T, device, world, pk, iters=5):
     """BASELINE metric 2: PPO samples/s = N*T / (t_compute_returns + t_update), 5 epochs x 4 minibatches,
     ActorCritic 512-256-128 (BASELINE.json configs[0] shape), synthetic rollout produced by the policy itself."""
     import torch
@@ -470,21 +470,28 @@ def ppo_bench(n_envs, T, device, world, pk, iters=3):
             ppo.process_env_step(torch.randn(n_envs, device=device) * 0.05, torch.rand(n_envs, device=device) < 0.01,
                                  {"env_bins": bins})
     times, t_gae = [], []
-    for it in range(iters + 1):
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    sampler = ClockSampler(physical_gpu_index(local))
+    warm = 2             # update() captures its CUDA graphs in the first call and uploads them at their first replay
+    for it in range(iters + warm):
         rollout()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        if it == warm:
+            sampler.__enter__()
         e0.record()
         ppo.compute_returns(obs[T], priv[T])
         e1.record()
         res = ppo.update()
         e2.record()
         torch.cuda.synchronize()
-        if it > 0:       # first iteration is the warm-up
+        if it >= warm:
             times.append(e0.elapsed_time(e2)); t_gae.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
+    sampler.__exit__()
+    # median of the timed iterations (each is one whole compute_returns + update; the mean is reported next to it)
+    ms = sorted(times)[len(times) // 2]
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -496,7 +503,8 @@ def ppo_bench(n_envs, T, device, world, pk, iters=3):
             "ms_gae": sum(t_gae) / len(t_gae), "envs_per_gpu": n_envs, "steps_per_env": T, "epochs": 5, "minibatches": 4,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": tf / (pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]), "traffic": None},
-            "losses": list(res), "dtype": "bf16 operands, fp32 accumulate / master weights"}
+            "losses": list(res), "dtype": "bf16 operands, fp32 accumulate / master weights",
+            "ms_per_iteration_all": [round(t, 3) for t in times], "clocks": sampler.summary()}
 
 
 def runner_bench(n_envs, device, iters=10):

@@ -512,7 +512,9 @@ typedef struct RlChainEpiOp {
   int32_t store_col0;
   uint8_t worker;                   /* which of the (up to four) epilogue warp groups executes this op */
   uint8_t padb0, padb1, padb2;
-  uint32_t pad1, pad2;
+  uint32_t delay_ns;                /* sleep this long before the op (0: none): de-phases workers that would otherwise run
+                                     * their MUFU-bound ELU phases in lock step */
+  uint32_t pad2;
 } RlChainEpiOp;
 
 typedef struct RlChainDesc {

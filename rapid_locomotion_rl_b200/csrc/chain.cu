@@ -22,6 +22,7 @@
 // per-warp bias staging rows): 14 units use exactly the 227 KB a CTA can have.
 // The host side (ppo/chain.py) builds the op lists and proves them on an emulator (deadlock freedom,
 // buffer hazards, parity bookkeeping, numerics) before anything reaches the GPU.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -74,6 +75,7 @@ struct ChainParams {
   int n_units, n_barriers;
   int num_tiles, rows;           // tiles [tile0, num_tiles) of the `rows`-row batch
   int tile0;
+  int dbg_sleep[3];              // sensitivity study (RL_CHAIN_DBG_SLEEP="load,mma,epi" ns per op): where is the critical path?
   unsigned long long* trace;      // profiling aid: clock64 stamps of CTA 0 in tile iteration trace_it (or null)
   int trace_it;
   uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
@@ -235,6 +237,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
       const int m0 = tile * 128;
       for (int i = 0; i < p.n_loads; ++i) {
         const RlChainLoadOp& cur = p.loads[i];
+        if (p.dbg_sleep[0]) __nanosleep(p.dbg_sleep[0]);
         chain_wait<WAIT_NS_LOAD>(bars, cur.wait, it);
         if (leader) {
           mbar_expect_tx(&bars[cur.full_bar], cur.expect_bytes);
@@ -254,6 +257,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
       const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it;
       for (int i = 0; i < p.n_mmas; ++i) {
         const DevMmaOp& cur = p.mmas[i];
+        if (p.dbg_sleep[1]) __nanosleep(p.dbg_sleep[1]);
         if (tr && leader) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
         {
           // (sequential spins: all three must pass anyway and the later ones are normally complete by then)
@@ -314,6 +318,8 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         const uint32_t release_after_store = w1.x & 0xFFu, out_id = (w1.x >> 8) & 0xFFu, out_ld = w1.x >> 16;
         const uint32_t bias_off = w1.y, dst_off = w1.z, aux_off = w1.w;
         const int store_col0 = (int)w2.x;
+        if (w2.z) __nanosleep(w2.z);            // delay_ns
+        if (p.dbg_sleep[2]) __nanosleep(p.dbg_sleep[2]);
         const bool has_bias = mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32;
 
         const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it && first;
@@ -799,6 +805,11 @@ static int chain_launch(void* handle, int32_t rows, int32_t tile_begin, int32_t 
     if (sm_count <= 0) sm_count = 148;
   }
   ChainParams p = h->params;
+  {
+    const char* e = getenv("RL_CHAIN_DBG_SLEEP");
+    p.dbg_sleep[0] = p.dbg_sleep[1] = p.dbg_sleep[2] = 0;
+    if (e) sscanf(e, "%d,%d,%d", &p.dbg_sleep[0], &p.dbg_sleep[1], &p.dbg_sleep[2]);
+  }
   p.rows = rows;
   p.num_tiles = tile_end;
   p.tile0 = tile_begin;

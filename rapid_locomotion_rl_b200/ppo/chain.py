@@ -80,6 +80,8 @@ class ChainProgram:
         # use of every overlapping region has been read by the epilogue (acc(..., implied=) names the ones another
         # wait of the same op already implies)
         self.alias_waits = alias_waits
+        import os
+        self.stagger_ns = int(os.environ.get("RL_CHAIN_STAGGER_NS", "0"))
         rings = rings or [("main", n_stages, stage_units)]
         self.n_stages, self.stage_units = rings[0][1], rings[0][2]      # of the default (first) ring
         self.tensors = []                # (torch tensor 2-D view, box_rows)
@@ -253,7 +255,10 @@ class ChainProgram:
         op = dict(worker=w, wait_acc=self._w("epi%d" % w, acc.full), wait_dst=None, wait_aux=None, arrive_acc_free=NONE,
                   arrive_dst_ready=NONE, release_aux=NONE, mode=mode, ncols=ncols, dst_col0=0, tmem_col=acc.col + col,
                   store_tensor=NONE, store_wait_pending=-1, release_after_store=NONE, out_id=NONE, out_ld=0,
-                  bias_off=bias_off, dst_off=0, aux_off=0, store_col0=0)
+                  bias_off=bias_off, dst_off=0, aux_off=0, store_col0=0, delay_ns=0)
+        # de-phase the workers: the first op of worker w on an accumulator use several workers read starts w x stagger later
+        if self.stagger_ns and acc.region not in self.region_worker and w not in acc.last_op and w > 0:
+            op["delay_ns"] = w * self.stagger_ns
         acc.last_op[w] = op
         if last:
             # every participating worker arrives (4 warps each) after ITS last read of this accumulator use
@@ -383,7 +388,8 @@ class ChainProgram:
             x = E[i]
             x.wait_acc, x.wait_dst, x.wait_aux = self._spec(o["wait_acc"]), self._spec(o["wait_dst"]), self._spec(o["wait_aux"])
             for k in ("worker", "arrive_acc_free", "arrive_dst_ready", "release_aux", "mode", "ncols", "dst_col0", "tmem_col", "store_tensor",
-                      "store_wait_pending", "release_after_store", "out_id", "out_ld", "bias_off", "dst_off", "aux_off", "store_col0"):
+                      "store_wait_pending", "release_after_store", "out_id", "out_ld", "bias_off", "dst_off", "aux_off", "store_col0",
+                      "delay_ns"):
                 setattr(x, k, o[k])
         d = _lib.RlChainDesc()
         for i, (t, box_rows) in enumerate(self.tensors):
@@ -829,6 +835,8 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
                   a_release=(ni == len(nets) - 1 and j == nch - 1))
             chunk_box[j] = p.epi_box(a1, 0, EPI_BIAS_ELU, bias_off=T["b_cat"] + off + 64 * j,
                                      store=None if tY1 is None else (tY1, off + 64 * j), last=True)
+            if p.stagger_ns and 0 < j < nw:          # the stream's first chunk of worker j: de-phase it
+                p.epis[-1]["delay_ns"] = j * p.stagger_ns
 
         def l2(j):
             wmax = 128 * p.stage_units
