@@ -434,8 +434,8 @@ int rl_wgrad_grouped(const RlWgradProblem* problems_host, int32_t n, void* strea
  *     K-major layout TMA writes and tcgen05.mma reads), weights stream from L2 through a ring of 16 KB
  *     stages, accumulators live in the 512 tensor-memory columns;
  *   - three warp roles execute three host-built op lists in order, synchronised only by mbarriers:
- *       LOAD ops (1 thread): one TMA box each (input rows, weight blocks, saved activations for ELU');
- *       MMA ops  (1 thread): up to four tcgen05.mma K16 steps of [128 x n] += A box * B box^T;
+ *       LOAD ops (1 thread each of two issuers): one TMA box each (input rows, weight blocks, saved activations for ELU');
+ *       MMA ops  (1 thread each of two issuers): up to four tcgen05.mma K16 steps of [128 x n] += A box * B box^T;
  *       EPI ops  (2..4 x 4 warps): tcgen05.ld of <= 64 accumulator columns -> bias / ELU / ELU' -> bf16 box for
  *                           the next layer (and a TMA store of the box for the backward / wgrad) or fp32 rows;
  *                           two to four workers (the launch sizes the CTA by the highest worker index the program uses),
@@ -446,7 +446,7 @@ int rl_wgrad_grouped(const RlWgradProblem* problems_host, int32_t n, void* strea
  * A wait is encoded in 16 bits: bits 0-7 barrier id (0xFF = none), bit 8 = parity to wait for in the
  * CTA's first tile, bit 9 = 1 if that parity flips with every further tile of the persistent loop. */
 #define RL_CHAIN_MAX_TENSORS 32
-#define RL_CHAIN_MAX_BARRIERS 64
+#define RL_CHAIN_MAX_BARRIERS 80
 #define RL_CHAIN_MAX_UNITS 14                    /* 16 KB shared-memory units (boxes + ring stages) */
 #define RL_CHAIN_MAX_OUTPUTS 4
 #define RL_CHAIN_NONE 255
@@ -467,7 +467,8 @@ typedef struct RlChainLoadOp {
   int32_t col0, row0;               /* box origin (elements); row0 is relative to the tile when tile_rows */
   uint32_t expect_bytes;            /* box bytes (box_rows * 128) */
   uint8_t tile_rows;
-  uint8_t pad0, pad1, pad2;
+  uint8_t issuer;                   /* 0 / 1: which of the two LOAD warps issues it (the list must be sorted by issuer) */
+  uint8_t pad1, pad2;
   uint32_t pad3, pad4;
 } RlChainLoadOp;
 
@@ -479,7 +480,8 @@ typedef struct RlChainMmaOp {
   uint8_t accumulate;               /* 0: the first step overwrites the accumulator */
   uint16_t wait0, wait1, wait2;
   uint8_t commit0, commit1, commit2;   /* mbarriers that tcgen05.commit arrives on after these MMAs */
-  uint8_t pad0;
+  uint8_t issuer;                   /* 0 / 1: which of the two MMA warps issues it (sorted list; MMAs into one accumulator
+                                     * must share an issuer: tcgen05.mma is ordered only within a thread) */
   uint16_t wait3;                   /* a fourth wait (0xFF in the low byte = none); zero-initialised structs must set it */
   uint16_t pad1;
   uint32_t pad2;

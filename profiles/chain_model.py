@@ -107,8 +107,9 @@ class Model:
 
     # ---- roles ----
     def run(self):
-        self._load(0, 0, 0.0)
-        self._mma(0, 0, 0.0)
+        for k in (0, 1):           # two issuing warps per role, each with its own in-order list
+            self._load(0, 0, 0.0, k)
+            self._mma(0, 0, 0.0, k)
         for wk in self.workers:
             self._epi(wk, 0, 0, 0.0, {"issued": [], })
         while self.heap:
@@ -116,13 +117,14 @@ class Model:
             fn()
         return self
 
-    def _load(self, it, i, now):
+    def _load(self, it, i, now, k=0):
         p, c = self.p, self.c
-        if it >= self.tiles:
+        ops = [o for o in p.loads if o.get("issuer", 0) == k]
+        if it >= self.tiles or not ops:
             return
-        if i >= len(p.loads):
-            return self._load(it + 1, 0, now)
-        o = p.loads[i]
+        if i >= len(ops):
+            return self._load(it + 1, 0, now, k)
+        o = ops[i]
 
         def go(t):
             self.expect(o["full_bar"])
@@ -130,23 +132,25 @@ class Model:
             hbm = bool(o["tile_rows"])
             lat = (c["tma_hbm_base"] + o["bytes"] / c["tma_hbm_bpc"]) if hbm else (c["tma_l2_base"] + o["bytes"] / c["tma_l2_bpc"])
             self.at(t + c["load_issue"] + lat, lambda: self.arrive(o["full_bar"], t + c["load_issue"] + lat, tx_done=True))
-            self.add_busy("load", c["load_issue"] + c["load_loop"])
-            self.at(t + c["load_issue"] + c["load_loop"], lambda: self._load(it, i + 1, t + c["load_issue"] + c["load_loop"]))
-        self.wait("load", o["wait"], it, now, go)
+            self.add_busy("load%d" % k, c["load_issue"] + c["load_loop"])
+            self.at(t + c["load_issue"] + c["load_loop"], lambda: self._load(it, i + 1, t + c["load_issue"] + c["load_loop"], k))
+        self.wait("load%d" % k, o["wait"], it, now, go)
 
-    def _mma(self, it, i, now):
+    def _mma(self, it, i, now, k=0):
         p, c = self.p, self.c
-        if it >= self.tiles:
+        ops = [o for o in p.mmas if o.get("issuer", 0) == k]
+        if it >= self.tiles or not ops:
             return
-        if i >= len(p.mmas):
-            return self._mma(it + 1, 0, now)
-        o = p.mmas[i]
+        if i >= len(ops):
+            return self._mma(it + 1, 0, now, k)
+        o = ops[i]
         waits = list(o["waits"])
+        kk = k
         t0 = now + c["mma_wait"]
 
         def after(k, t):
             if k < len(waits):
-                return self.wait("mma", waits[k], it, t, lambda t2: after(k + 1, t2))
+                return self.wait("mma%d" % kk, waits[k], it, t, lambda t2: after(k + 1, t2))
             stall = c["mma_contend"] if sum(m > t for m in self.math_until) >= 2 else 0.0   # >= 2 workers in their math phase
             t_iss = t + c["mma_issue"] + stall
             start = max(t_iss, self.pipe_free)
@@ -155,8 +159,8 @@ class Model:
             t_end = t_iss + c["mma_commit"]
             for b in o["commits"]:
                 self.at(max(done, t_end), (lambda b=b, d=max(done, t_end): self.arrive(b, d)))
-            self.add_busy("mma", c["mma_wait"] + c["mma_issue"] + stall + c["mma_commit"] + c["mma_loop"])
-            self.at(t_end + c["mma_loop"], lambda: self._mma(it, i + 1, t_end + c["mma_loop"]))
+            self.add_busy("mma%d" % kk, c["mma_wait"] + c["mma_issue"] + stall + c["mma_commit"] + c["mma_loop"])
+            self.at(t_end + c["mma_loop"], lambda: self._mma(it, i + 1, t_end + c["mma_loop"], kk))
         after(0, t0)
 
     def _epi(self, wk, it, i, now, sg):

@@ -34,9 +34,16 @@ namespace rl {
 namespace tc {
 
 constexpr int MAX_WORKERS = 4;
-constexpr int chain_threads(int nw) { return 64 + 128 * nw; }   // warp 0 LOAD, warp 1 MMA, then four warps per epilogue worker
+// warp 0 LOAD, warp 1 MMA, four warps per epilogue worker, then the SECOND issuers: one more LOAD warp and one more MMA
+// warp (they land on other scheduler partitions than warps 0 / 1).  The per-op cost of an issuing warp (~1100 cycles
+// for an MMA op, ~480 for a load, whatever their size: dependent waits, descriptor arithmetic, commits, all on one
+// thread next to two busy epilogue warps) was the critical path of the chains (sensitivity study: profiles/r02_chain_ncu.md),
+// so the op lists are split over two issuers each - by accumulator chain for the MMAs, by ring stage for the loads.
+constexpr int chain_threads(int nw) { return 128 + 128 * nw; }
+constexpr int N_ISSUERS = 2;
 constexpr int UNIT_BYTES = 16384;
-constexpr int FIXED_SMEM = 3072;            // static: 64 mbarriers | tmem slot, 64 tickets | per-warp bias staging (16 x 128 B)
+constexpr int FIXED_SMEM = 3072;            // static: 80 mbarriers [0, 640) | tmem slot 640 | 80 tickets [672, 992) | per-warp bias staging (16 x 128 B) from 1024
+static_assert(RL_CHAIN_MAX_BARRIERS * 8 <= 640 && 672 + RL_CHAIN_MAX_BARRIERS * 4 <= 1024, "fixed shared-memory layout");
 constexpr int MAX_STORE_MAPS = 16;
 constexpr int TRACE_MMA = 8, TRACE_EPI = 5; // stamps per op (loads: 1)
 #ifndef RL_CHAIN_WAIT_NS_LOAD
@@ -57,6 +64,7 @@ struct DevMmaOp {            // 32 B; everything the issuing warp would otherwis
   uint16_t parities;         // bit 2j: parity of wait j when the tile iteration is even, bit 2j+1: when it is odd
 };
 static_assert(sizeof(DevMmaOp) == 32, "DevMmaOp layout");
+constexpr int MAX_OPS_PER_ISSUER = 64;      // an issuing warp keeps its op list in registers: 2 ops per lane
 
 // The LOAD and MMA op lists travel in the kernel parameters (constant bank): indexed by the loop counter
 // they are read with uniform loads, so the TMA / tcgen05 instructions get their operands in uniform
@@ -72,6 +80,7 @@ struct ChainParams {
   const float* params;
   float* outputs[RL_CHAIN_MAX_OUTPUTS];
   int n_loads, n_mmas, n_epis[MAX_WORKERS];
+  int load_begin[N_ISSUERS + 1], mma_begin[N_ISSUERS + 1];     // ops of issuer k: [begin[k], begin[k + 1]) (lists sorted by issuer)
   int n_units, n_barriers;
   int num_tiles, rows;           // tiles [tile0, num_tiles) of the `rows`-row batch
   int tile0;
@@ -188,7 +197,7 @@ __device__ __forceinline__ void mma_wait(uint32_t bar_addr, uint32_t parity, int
   if (mbar_try_addr(bar_addr, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_addr(bar_addr, parity)) {
-    if (++spins > (1u << 24)) chain_timeout((bar_addr & 0x1FFu) / 8, parity, it);
+    if (++spins > (1u << 24)) chain_timeout((bar_addr & 0x3FFu) / 8, parity, it);
   }
 }
 
@@ -206,8 +215,8 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   __shared__ __align__(1024) uint8_t s_fixed[FIXED_SMEM];
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_fixed);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_fixed + 512);
-  uint32_t* tickets = reinterpret_cast<uint32_t*>(s_fixed + 576);          // 64 x 4 B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_fixed + 640);
+  uint32_t* tickets = reinterpret_cast<uint32_t*>(s_fixed + 672);          // one per barrier
   float* s_bias = reinterpret_cast<float*>(s_fixed + 1024);                // 16 warps x 32 floats
   // warp-uniform role index (the shuffle tells the compiler so: the LOAD / MMA loops run on the uniform datapath)
   const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
@@ -222,20 +231,23 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
     for (int b = 0; b < p.n_barriers; ++b) mbar_init(&bars[b], p.barrier_count[b]);
     mbar_fence_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) tickets[threadIdx.x - 64] = 0;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + RL_CHAIN_MAX_BARRIERS) tickets[threadIdx.x - 64] = 0;
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  const int issuer2_warp0 = 2 + 4 * NW;        // warps issuer2_warp0 (LOAD) and issuer2_warp0 + 1 (MMA): the second issuers
+  if (warp == 0 || warp == issuer2_warp0) {
     // ===================================== LOAD role =====================================
+    const int k = warp == 0 ? 0 : 1;
+    const int i0 = p.load_begin[k], i1 = p.load_begin[k + 1];
     const bool leader = elect_one();
     int it = 0;
-    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && p.n_loads > 0; tile += gridDim.x, ++it) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && i1 > i0; tile += gridDim.x, ++it) {
       const int m0 = tile * 128;
-      for (int i = 0; i < p.n_loads; ++i) {
+      for (int i = i0; i < i1; ++i) {
         const RlChainLoadOp& cur = p.loads[i];
         if (p.dbg_sleep[0]) __nanosleep(p.dbg_sleep[0]);
         chain_wait<WAIT_NS_LOAD>(bars, cur.wait, it);
@@ -246,23 +258,40 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == issuer2_warp0 + 1) {
     // ===================================== MMA role ======================================
+    const int k = warp == 1 ? 0 : 1;
+    const int i0 = p.mma_begin[k], i1 = p.mma_begin[k + 1];
     const bool leader = elect_one();
     const uint32_t base16 = smem_base >> 4;
     uint32_t bar0 = smem_u32(bars);
     asm volatile("" : "+r"(bar0));      // (opaque: otherwise the address is re-derived - S2R SR_CgaCtaId - at every use)
+    // The op list lives in the kernel parameters; an indexed constant load costs ~100 cycles and an op needs several
+    // dependent ones.  The list is the same for every tile, so the warp keeps it in registers: lane l holds ops
+    // i0 + l and i0 + 32 + l (8 words each, <= 64 ops per issuer) and hands an op's words out by shuffle.
+    uint32_t mine[2][8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = i0 + 32 * h + lane;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&p.mmas[j < i1 ? j : (i1 > i0 ? i1 - 1 : 0)]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mine[h][q] = (i1 > i0) ? src[q] : 0u;
+    }
     int it = 0;
-    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && p.n_mmas > 0; tile += gridDim.x, ++it) {
+    for (int tile = p.tile0 + blockIdx.x; tile < p.num_tiles && i1 > i0; tile += gridDim.x, ++it) {
       const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it;
-      for (int i = 0; i < p.n_mmas; ++i) {
-        const DevMmaOp& cur = p.mmas[i];
+      for (int i = i0; i < i1; ++i) {
+        const int rel = i - i0, srcl = rel & 31;
+        uint32_t w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[q] = __shfl_sync(0xFFFFFFFFu, rel < 32 ? mine[0][q] : mine[1][q], srcl);
+        // words: a_lo | b_lo | idesc | misc | wait_off 0,1 | wait_off 2,3 | commit_off 0,1 | commit_off 2, parities
         if (p.dbg_sleep[1]) __nanosleep(p.dbg_sleep[1]);
         if (tr && leader) p.trace[p.n_loads + TRACE_MMA * i + 1] = clock64();
         {
-          // (sequential spins: all three must pass anyway and the later ones are normally complete by then)
-          const uint32_t par = (uint32_t)cur.parities >> (it & 1);
-          const uint32_t w0 = cur.wait_off[0], w1 = cur.wait_off[1], w2 = cur.wait_off[2], w3 = cur.wait_off[3];
+          // (sequential spins: all of them must pass anyway and the later ones are normally complete by then)
+          const uint32_t par = (w[7] >> 16) >> (it & 1);
+          const uint32_t w0 = w[4] & 0xFFFFu, w1 = w[4] >> 16, w2 = w[5] & 0xFFFFu, w3 = w[5] >> 16;
           if (w0) mma_wait(bar0 + w0 - 1, par & 1u, it);
           if (w1) mma_wait(bar0 + w1 - 1, (par >> 2) & 1u, it);
           if (w2) mma_wait(bar0 + w2 - 1, (par >> 4) & 1u, it);
@@ -271,17 +300,18 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         tc_fence_after();
         if (leader) {
           if (tr) p.trace[p.n_loads + TRACE_MMA * i] = clock64();
-          const uint32_t a_lo = cur.a_lo + base16, b_lo = cur.b_lo + base16, idesc = cur.idesc;
-          const uint32_t tmem_d = tmem_base + (cur.misc & 0xFFFFu);
-          const uint32_t k_steps = (cur.misc >> 16) & 0xFFu;
-          mma_issue(tmem_d, a_lo, b_lo, idesc, cur.misc >> 24);                 // K16 step 0
+          const uint32_t a_lo = w[0] + base16, b_lo = w[1] + base16, idesc = w[2], misc = w[3];
+          const uint32_t tmem_d = tmem_base + (misc & 0xFFFFu);
+          const uint32_t k_steps = (misc >> 16) & 0xFFu;
+          mma_issue(tmem_d, a_lo, b_lo, idesc, misc >> 24);                     // K16 step 0
           if (k_steps > 1) mma_issue(tmem_d, a_lo + 2, b_lo + 2, idesc, 1);     // +32 B per step
           if (k_steps > 2) mma_issue(tmem_d, a_lo + 4, b_lo + 4, idesc, 1);
           if (k_steps > 3) mma_issue(tmem_d, a_lo + 6, b_lo + 6, idesc, 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 4] = clock64();
-          if (cur.commit_off[0]) mma_commit(nullptr, bar0 + cur.commit_off[0] - 1);
-          if (cur.commit_off[1]) mma_commit(nullptr, bar0 + cur.commit_off[1] - 1);
-          if (cur.commit_off[2]) mma_commit(nullptr, bar0 + cur.commit_off[2] - 1);
+          const uint32_t c0 = w[6] & 0xFFFFu, c1 = w[6] >> 16, c2 = w[7] & 0xFFFFu;
+          if (c0) mma_commit(nullptr, bar0 + c0 - 1);
+          if (c1) mma_commit(nullptr, bar0 + c1 - 1);
+          if (c2) mma_commit(nullptr, bar0 + c2 - 1);
           if (tr) p.trace[p.n_loads + TRACE_MMA * i + 7] = clock64();
         }
       }
@@ -633,15 +663,26 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   const uint32_t limit = (uint32_t)d->n_units * UNIT_BYTES;
   for (int i = 0; i < d->n_loads; ++i) {
     const RlChainLoadOp& o = d->loads_host[i];
+    RL_REQUIRE(o.issuer < N_ISSUERS && (i == 0 || o.issuer >= d->loads_host[i - 1].issuer), RL_ERR_BAD_ARG,
+               "rl_chain_create: load op %d: issuer %d (two issuers, list sorted by issuer)", i, (int)o.issuer);
     RL_REQUIRE(o.tensor < d->n_tensors && o.full_bar < d->n_barriers && (o.smem_off & 1023u) == 0 &&
                o.smem_off + o.expect_bytes <= limit && o.expect_bytes > 0 && o.expect_bytes <= 2 * UNIT_BYTES,
                RL_ERR_BAD_ARG, "rl_chain_create: load op %d malformed", i);
   }
   for (int i = 0; i < d->n_mmas; ++i) {
     const RlChainMmaOp& o = d->mmas_host[i];
+    RL_REQUIRE(o.issuer < N_ISSUERS && (i == 0 || o.issuer >= d->mmas_host[i - 1].issuer), RL_ERR_BAD_ARG,
+               "rl_chain_create: mma op %d: issuer %d (two issuers, list sorted by issuer)", i, (int)o.issuer);
     RL_REQUIRE(o.n >= 16 && o.n <= 256 && (o.n % 16) == 0 && o.tmem_col + o.n <= 512 && o.k_steps >= 1 && o.k_steps <= 4 &&
                (o.a_off & 1023u) == 0 && (o.b_off & 1023u) == 0 && o.a_off + UNIT_BYTES <= limit && o.b_off + (uint32_t)o.n * 128 <= limit,
                RL_ERR_BAD_ARG, "rl_chain_create: mma op %d malformed", i);
+  }
+  {
+    int nm[N_ISSUERS] = {0, 0};
+    for (int i = 0; i < d->n_mmas; ++i) ++nm[d->mmas_host[i].issuer];
+    RL_REQUIRE(nm[0] <= MAX_OPS_PER_ISSUER && nm[1] <= MAX_OPS_PER_ISSUER, RL_ERR_BAD_ARG,
+               "rl_chain_create: %d / %d mma ops per issuer (max %d each: an issuing warp keeps its list in registers)", nm[0], nm[1],
+               MAX_OPS_PER_ISSUER);
   }
   int n_epi_w[MAX_WORKERS] = {0, 0, 0, 0};
   int n_workers = 2;
@@ -733,6 +774,16 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   h->params.params = d->params;
   for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->params.outputs[i] = d->outputs[i];
   h->params.n_loads = d->n_loads; h->params.n_mmas = d->n_mmas;
+  {
+    int nl[N_ISSUERS] = {0, 0}, nm[N_ISSUERS] = {0, 0};
+    for (int i = 0; i < d->n_loads; ++i) ++nl[d->loads_host[i].issuer];
+    for (int i = 0; i < d->n_mmas; ++i) ++nm[d->mmas_host[i].issuer];
+    h->params.load_begin[0] = h->params.mma_begin[0] = 0;
+    for (int k = 0; k < N_ISSUERS; ++k) {
+      h->params.load_begin[k + 1] = h->params.load_begin[k] + nl[k];
+      h->params.mma_begin[k + 1] = h->params.mma_begin[k] + nm[k];
+    }
+  }
   for (int k = 0; k < MAX_WORKERS; ++k) h->params.n_epis[k] = n_epi_w[k];
   h->params.n_units = d->n_units; h->params.n_barriers = d->n_barriers;
   memcpy(h->params.barrier_count, d->barrier_count, RL_CHAIN_MAX_BARRIERS);

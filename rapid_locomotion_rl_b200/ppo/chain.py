@@ -35,20 +35,24 @@ class _Wait:
 
 
 class StageUse:
-    """One landing of a TMA box in a ring stage."""
-    __slots__ = ("stage", "off", "full", "empty_bar", "released")
+    """One landing of a TMA box in a ring stage.  `full` is None until the first MMA that reads the box names its issuer
+    (every issuing warp has its own "full" barrier per stage: a barrier must have a single waiting agent)."""
+    __slots__ = ("stage", "off", "full", "empty_bar", "released", "ring", "load_op")
 
-    def __init__(self, stage, off, full, empty_bar):
+    def __init__(self, stage, off, full, empty_bar, ring=None, load_op=None):
         self.stage, self.off, self.full, self.empty_bar, self.released = stage, off, full, empty_bar, False
+        self.ring, self.load_op = ring, load_op
 
 
 class BoxUse:
-    """One content of an activation unit (written by the epilogue, or loaded by TMA for inputs)."""
-    __slots__ = ("unit", "off", "ready", "free_bar", "released", "has_reader")
+    """One content of an activation unit (written by the epilogue, or loaded by TMA for inputs).  A pool box's `ready`
+    is None until its first reading MMA names the issuer whose "ready" barrier the producing epilogue op arrives on."""
+    __slots__ = ("unit", "off", "ready", "free_bar", "released", "has_reader", "pool_index", "producer_op")
 
-    def __init__(self, unit, off, ready, free_bar):
+    def __init__(self, unit, off, ready, free_bar, pool_index=None, producer_op=None):
         self.unit, self.off, self.ready, self.free_bar = unit, off, ready, free_bar
         self.released, self.has_reader = False, True
+        self.pool_index, self.producer_op = pool_index, producer_op
 
 
 class AccUse:
@@ -65,7 +69,7 @@ class ChainProgram:
     """Builder + container of one chain program."""
 
     def __init__(self, n_pool, n_stages, n_inputs, regions, name="chain", region_worker=None, stage_units=1, rings=None,
-                 n_workers=2, alias_waits=False):
+                 n_workers=2, alias_waits=False, region_issuer=None, n_loaders=1):
         """Shared-memory units: [inputs | pool | ring stages]; `regions`: {name: (first tmem column, width)};
         `region_worker`: regions whose accumulator uses are read by ONE epilogue op -> the worker that owns
         them (a waiter must see every phase of a barrier, so such a region cannot change hands); the other
@@ -82,6 +86,13 @@ class ChainProgram:
         self.alias_waits = alias_waits
         import os
         self.stagger_ns = int(os.environ.get("RL_CHAIN_STAGGER_NS", "0"))
+        # Two issuing warps per role (csrc/chain.cu): MMAs are dealt by accumulator region (`region_issuer`: region -> 0 / 1;
+        # the MMAs into one accumulator must come from one thread), loads by ring stage (stage s -> loader s % n_loaders,
+        # so every stage keeps a single waiting loader).  Nothing orders the two MMA issuers against each other except the
+        # mbarriers, so programs whose regions share columns need alias_waits.
+        self.region_issuer = dict(region_issuer or {})
+        self.n_loaders = n_loaders
+        assert n_loaders in (1, 2) and all(v in (0, 1) for v in self.region_issuer.values())
         rings = rings or [("main", n_stages, stage_units)]
         self.n_stages, self.stage_units = rings[0][1], rings[0][2]      # of the default (first) ring
         self.tensors = []                # (torch tensor 2-D view, box_rows)
@@ -108,7 +119,7 @@ class ChainProgram:
         self.default_ring = rings[0][0]
         self.n_units = unit
         assert self.n_units <= _lib.DEFINES["RL_CHAIN_MAX_UNITS"]
-        self.pool_ready = [self._bar(4, "pool%d.ready" % i) for i in range(n_pool)]
+        self.pool_ready = [{0: self._bar(4, "pool%d.ready" % i)} for i in range(n_pool)]     # per MMA issuer (1: on demand)
         self.pool_free = [self._bar(1, "pool%d.free" % i) for i in range(n_pool)]
         self.pool_pos = 0
         self.pool_last = [None] * n_pool           # last BoxUse per pool unit
@@ -117,7 +128,7 @@ class ChainProgram:
         self.acc_uses = {r: 0 for r in regions}
         self.acc_open = {r: None for r in regions}
         self.input_full, self.input_free, self.input_loads = {}, {}, {}
-        self.waited = {"load": set(), "mma": set()}
+        self.waited = {"load": set(), "mma0": set(), "mma1": set()}
         self.waited.update({"epi%d" % k: set() for k in range(n_workers)})
         # two epilogue workers (4 warps each) take the EPI ops alternately; a pool unit always belongs to the
         # worker of its parity, so the TMA-store bookkeeping (one bulk group per store, committed by the
@@ -172,7 +183,7 @@ class ChainProgram:
         self.input_full[slot], self.input_free[slot] = full, free
         ordn = self._signal(full)
         self.loads.append(dict(wait=_Wait(free, 0), full_bar=full, tensor=tensor, smem_off=slot * UNIT, col0=col0, row0=0,
-                               bytes=UNIT, tile_rows=1))
+                               bytes=UNIT, tile_rows=1, issuer=0))
         use = BoxUse(slot, slot * UNIT, _Wait(full, ordn), free)
         self.input_loads[slot] = use
         return use
@@ -187,14 +198,26 @@ class ChainProgram:
         R["pos"] += 1
         wait = _Wait(R["empty"][s], R["uses"][s])
         R["uses"][s] += 1
+        off = R["unit0"][s] * UNIT
+        op = dict(wait=wait, full_bar=None, tensor=tensor, smem_off=off, col0=col0, row0=row0,
+                  bytes=box_rows * 128, tile_rows=int(tile_rows), issuer=s % self.n_loaders)
+        self.loads.append(op)
+        use = StageUse(s, off, None, R["empty"][s], ring=R, load_op=op)
+        if consumer != "mma":
+            self._resolve_stage(use, consumer)
+        return use
+
+    def _resolve_stage(self, use, consumer):
+        """Names the "full" barrier of a landing once its consumer is known ("mma" / "mma1" / "epiK")."""
+        if use.full is not None:
+            assert consumer in self.bar_name[use.full.bar].split(".")[-1:], "stage box read by two different consumers"
+            return
+        R, s = use.ring, use.stage
         if consumer not in R["full"]:
             R["full"][consumer] = [self._bar(1, "%sstage%d.full.%s" % (R["tag"], i, consumer)) for i in range(R["n"])]
         full = R["full"][consumer][s]
-        ordn = self._signal(full)
-        off = R["unit0"][s] * UNIT
-        self.loads.append(dict(wait=wait, full_bar=full, tensor=tensor, smem_off=off, col0=col0, row0=row0,
-                               bytes=box_rows * 128, tile_rows=int(tile_rows)))
-        return StageUse(s, off, _Wait(full, ordn), R["empty"][s])
+        use.load_op["full_bar"] = full
+        use.full = _Wait(full, self._signal(full))
 
     def worker_for(self, acc, col):
         """Epilogue worker that reads accumulator columns [col, col + 64) of this use."""
@@ -222,8 +245,14 @@ class ChainProgram:
     def mma(self, a, b, n, acc, col_off=0, k_steps=4, accumulate=True, acc_last=False, a_release=False, b_release=True):
         """acc[:, col_off : col_off + n] (+)= A box * B box^T over k_steps K16 steps."""
         waits, commits = [], []
+        issuer = self.region_issuer.get(acc.region, 0)
+        for x in (a, b):
+            if isinstance(x, StageUse):
+                self._resolve_stage(x, "mma" if issuer == 0 else "mma%d" % issuer)
+            elif x.ready is None:
+                self._resolve_box(x, issuer)
         for w in [a.full if isinstance(a, StageUse) else a.ready, b.full] + ([] if acc.started else [acc.wait_free] + acc.alias_free):
-            w = self._w("mma", w)
+            w = self._w("mma%d" % issuer, w)
             if w is not None:
                 waits.append(w)
         acc.started = True
@@ -245,7 +274,16 @@ class ChainProgram:
         assert col_off + n <= width and n % 16 == 0 and 16 <= n <= 256
         assert len(waits) <= 4 and len(commits) <= 3, (len(waits), len(commits))
         self.mmas.append(dict(a_off=a.off, b_off=b.off, n=n, tmem_col=acc.col + col_off, k_steps=k_steps,
-                              accumulate=int(accumulate), waits=waits, commits=commits))
+                              accumulate=int(accumulate), waits=waits, commits=commits, issuer=issuer))
+
+    def _resolve_box(self, box, issuer):
+        """The producing epilogue op arrives on the "ready" barrier of the issuer that reads the box."""
+        i = box.pool_index
+        if issuer not in self.pool_ready[i]:
+            self.pool_ready[i][issuer] = self._bar(4, "pool%d.ready.mma%d" % (i, issuer))
+        bar = self.pool_ready[i][issuer]
+        box.producer_op["arrive_dst_ready"] = bar
+        box.ready = _Wait(bar, self._signal(bar))
 
     # ---- epilogue ---------------------------------------------------------------------------------------
     def _epi_common(self, acc, col, ncols, mode, bias_off, last):
@@ -285,8 +323,7 @@ class ChainProgram:
         unit = self.pool_units[i]
         # frees emitted so far for this unit == completions the writer must have seen
         op["wait_dst"] = self._w("epi%d" % w, _Wait(self.pool_free[i], self.bar_phases[self.pool_free[i]]))
-        ordn = self._signal(self.pool_ready[i])
-        op["arrive_dst_ready"] = self.pool_ready[i]
+        op["arrive_dst_ready"] = None          # named by the first MMA that reads the box (_resolve_box)
         op["dst_off"] = unit * UNIT
         # the unit may still be read by a TMA store this worker issued earlier (this tile or the previous one)
         op["_store_dep"] = (self.unit_last_store.get(unit), self.n_stores[w])
@@ -303,7 +340,7 @@ class ChainProgram:
             op["store_tensor"], op["store_col0"] = store
             self.unit_last_store[unit] = self.n_stores[w]
             self.n_stores[w] += 1
-        use = BoxUse(unit, unit * UNIT, _Wait(self.pool_ready[i], ordn), self.pool_free[i])
+        use = BoxUse(unit, unit * UNIT, None, self.pool_free[i], pool_index=i, producer_op=op)
         use.has_reader = has_reader
         self.pool_last[i] = use
         self.epis.append(op)
@@ -358,6 +395,20 @@ class ChainProgram:
             else:
                 pend = None
             op["store_wait_pending"] = -1 if pend is None else max(0, min(7, pend))
+        for op in self.epis:
+            if op["arrive_dst_ready"] is None:        # a box no MMA reads (stored only)
+                op["arrive_dst_ready"] = NONE
+        for o in self.loads:
+            assert o["full_bar"] is not None, "a stage box nobody reads"
+        # a parity wait names a phase only modulo 2: every barrier an MMA issuer waits on must have that single waiter
+        seen = {}
+        for o in self.mmas:
+            for w in o["waits"]:
+                assert seen.setdefault(w.bar, o["issuer"]) == o["issuer"], \
+                    "%s: barrier %s is waited on by both MMA issuers" % (self.name, self.bar_name[w.bar])
+        # the kernel takes each role's list grouped by issuer (program order kept within an issuer)
+        self.loads.sort(key=lambda o: o["issuer"])
+        self.mmas.sort(key=lambda o: o["issuer"])
         self._finalized = True
         return self
 
@@ -374,11 +425,12 @@ class ChainProgram:
         for i, o in enumerate(self.loads):
             x = L[i]
             x.wait, x.full_bar, x.tensor, x.smem_off = self._spec(o["wait"]), o["full_bar"], o["tensor"], o["smem_off"]
-            x.col0, x.row0, x.expect_bytes, x.tile_rows = o["col0"], o["row0"], o["bytes"], o["tile_rows"]
+            x.col0, x.row0, x.expect_bytes, x.tile_rows, x.issuer = o["col0"], o["row0"], o["bytes"], o["tile_rows"], o["issuer"]
         M = (_lib.RlChainMmaOp * max(1, len(self.mmas)))()
         for i, o in enumerate(self.mmas):
             x = M[i]
             x.a_off, x.b_off, x.n, x.tmem_col, x.k_steps, x.accumulate = o["a_off"], o["b_off"], o["n"], o["tmem_col"], o["k_steps"], o["accumulate"]
+            x.issuer = o["issuer"]
             ws = [self._spec(w) for w in o["waits"]] + [NONE] * 4
             x.wait0, x.wait1, x.wait2, x.wait3 = ws[:4]
             cs = list(o["commits"]) + [NONE] * 3
@@ -509,7 +561,7 @@ class Emulator:
         unit_loading = [0] * p.n_units       # TMA loads in flight into the unit
         tmem = torch.zeros(128, 512)
         tmem_unread = torch.zeros(512, dtype=torch.bool)   # written by an MMA, not yet loaded by an epilogue op
-        mma_queue = []                       # issued MMAs / commits, executed in order by the tensor pipe
+        mma_queues = [[], []]                # per issuing thread: issued MMAs / commits, executed in that thread's order
         loads_inflight = []
         NW = p.n_workers
         stores_inflight = [[] for _ in range(NW)]           # per epilogue worker: bulk groups complete in order
@@ -539,10 +591,12 @@ class Emulator:
             return range(off // UNIT, (off + nbytes - 1) // UNIT + 1)
 
         # ---------------- roles as generators ----------------
-        def load_role():
+        def load_role(k):
             for it, tile in enumerate(tiles):
                 m0 = tile * 128
                 for o in p.loads:
+                    if o["issuer"] != k:
+                        continue
                     yield from spec_wait(o["wait"], it, "load")
                     for u in nun(o["smem_off"], o["bytes"] // 128):
                         if unit_readers[u] or unit_loading[u]:
@@ -569,18 +623,21 @@ class Emulator:
             flat_smem[128 * u:128 * u + box_rows] = box
             bars[o["full_bar"]].complete_tx(o["bytes"])
 
-        def mma_role():
+        def mma_role(k):
             for it, tile in enumerate(tiles):
                 for o in p.mmas:
+                    if o["issuer"] != k:
+                        continue
                     for w in o["waits"]:
                         yield from spec_wait(w, it, "mma")
                     for u in [o["a_off"] // UNIT] + list(nun(o["b_off"], o["n"])):
                         if unit_loading[u]:
                             raise ChainHazard("MMA reads unit %d while a TMA load is in flight" % u)
                         unit_readers[u] += 1
-                    mma_queue.append(("mma", o))
+                    # (one in-order queue per issuing thread; the tensor pipe interleaves the queues arbitrarily)
+                    mma_queues[k].append(("mma", o))
                     for c in o["commits"]:
-                        mma_queue.append(("commit", c))
+                        mma_queues[k].append(("commit", c))
                     yield
             state["done"] += 1
 
@@ -668,8 +725,8 @@ class Emulator:
             unit_readers[u] -= 1
             store_groups[o["worker"]]["read"] += 1
 
-        roles = [load_role(), mma_role()] + [epi_role(k) for k in range(NW)]
-        NR = 2 + NW
+        roles = [load_role(0), load_role(1), mma_role(0), mma_role(1)] + [epi_role(k) for k in range(NW)]
+        NR = 4 + NW
         alive = [True] * NR
         blocked_rounds = 0
         # adversarial speeds: every agent (3 roles, TMA loads, tensor pipe, TMA stores) gets its own firing
@@ -689,7 +746,7 @@ class Emulator:
                 if a < NR:
                     if not alive[a]:
                         continue
-                    before = (len(loads_inflight), len(mma_queue), tuple(len(x) for x in stores_inflight),
+                    before = (len(loads_inflight), len(mma_queues[0]) + len(mma_queues[1]), tuple(len(x) for x in stores_inflight),
                               tuple(b.n for b in bars), tuple(b.pending for b in bars))
                     try:
                         next(roles[a])
@@ -697,15 +754,16 @@ class Emulator:
                         alive[a] = False
                         progressed = True
                         continue
-                    after = (len(loads_inflight), len(mma_queue), tuple(len(x) for x in stores_inflight),
+                    after = (len(loads_inflight), len(mma_queues[0]) + len(mma_queues[1]), tuple(len(x) for x in stores_inflight),
                              tuple(b.n for b in bars), tuple(b.pending for b in bars))
                     progressed |= before != after
                 elif a == NR and loads_inflight:
                     i = self.rng.randrange(len(loads_inflight))      # TMA completes out of order
                     land(*loads_inflight.pop(i))
                     progressed = True
-                elif a == NR + 1 and mma_queue:
-                    kind, x = mma_queue.pop(0)                        # the tensor pipe executes in order
+                elif a == NR + 1 and (mma_queues[0] or mma_queues[1]):
+                    qs = [q for q in mma_queues if q]
+                    kind, x = self.rng.choice(qs).pop(0)              # in order per issuing thread, any interleaving of the two
                     if kind == "mma":
                         exec_mma(x)
                     else:
@@ -714,7 +772,7 @@ class Emulator:
                 elif a >= NR + 2 and stores_inflight[a - NR - 2]:
                     do_store(*stores_inflight[a - NR - 2].pop(0))     # bulk groups complete in order
                     progressed = True
-            inflight = loads_inflight or mma_queue or any(stores_inflight)
+            inflight = loads_inflight or mma_queues[0] or mma_queues[1] or any(stores_inflight)
             if not any(alive) and not inflight:
                 break
             if progressed:
@@ -768,7 +826,7 @@ REGIONS3 = {"C0": (0, 64), "C1": (64, 64), "C2": (128, 64), "BIG": (192, 256), "
 
 
 def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value=True, n_stages=3, stage_units=2, n_workers=2,
-                            lookahead=None):
+                            lookahead=None, two_issuers=False):
     """encoder(priv) -> latent merged into the [obs | latent] box -> actor mean / critic value
     (actor_critic.py:124-173 `act` / `evaluate` on one batch; ppo.py:102-107 inside the update).
     T: tensors + parameter offsets (see ActorCritic._chain_tensors).  save: also store every hidden
@@ -779,8 +837,13 @@ def teacher_forward_program(T, save=True, trunk=True, want_mean=True, want_value
     safe by program order like SB / D2 in the backward (MID is written only after the MMAs that consumed every
     chunk box of the stream, and a stream starts only after the MMAs that consumed MID's boxes)."""
     nw = n_workers
+    # two MMA issuers: the second-layer accumulator (8 of a network's 22 ops, all waiting for epilogue boxes) gets its own
+    # warp; with two workers the third-layer accumulator joins it (with three it shares columns with the chunk
+    # accumulators and stays with them: the overlap is safe by ONE issuer's program order only)
+    issuers = ({"BIG": 1, "MID": 1} if nw == 2 else {"BIG": 1}) if two_issuers else {}
     p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=2, regions=REGIONS if nw == 2 else REGIONS3, name="teacher_forward",
-                     stage_units=stage_units, n_workers=nw, region_worker={"C%d" % k: k for k in range(nw)})
+                     stage_units=stage_units, n_workers=nw, region_worker={"C%d" % k: k for k in range(nw)},
+                     region_issuer=issuers)
     p.params = T["params"]
     wbox = lambda w: min(128 * stage_units, _round16(w.shape[0]))      # weight box rows
     tXp, tXac = p.tensor(T["Xp"], 128), p.tensor(T["Xac"], 128)
@@ -966,7 +1029,7 @@ def teacher_forward_program4(T, save=True, trunk=True, want_mean=True, want_valu
     return p.finalize()
 
 
-def trunk_backward_program(T, n_stages=8):
+def trunk_backward_program(T, n_stages=8, two_issuers=False):
     """dgrad half of the backward of actor + critic + encoder (what autograd does behind ppo.py:146-148 for
     the layer inputs): from d(loss)/d(mean) and d(loss)/d(value) down to the encoder's first hidden layer,
     multiplying by ELU' of the saved activations, storing every layer-output gradient for the wgrad GEMMs.
@@ -986,8 +1049,14 @@ def trunk_backward_program(T, n_stages=8):
     The emulator's numeric check under adversarial scheduling covers exactly this (an early overwrite of an
     unread accumulator shows up as a wrong result)."""
     regions = {"D2": (0, 256), "SB": (0, 128), "SA": (256, 128), "LAT": (384, 32)}
+    # two issuers per role: the d(latent) accumulation (16 of the 63 MMA ops, each waiting for an epilogue box) gets its
+    # own MMA warp - D2 / SB / SA share columns and stay on one issuer - and the 99 loads alternate between two LOAD
+    # warps by ring stage (the sensitivity study put half of this program's time on the LOAD warp's critical path)
     p = ChainProgram(n_pool=6, n_stages=n_stages, n_inputs=0, regions=regions, name="trunk_backward",
-                     region_worker={"LAT": 0})
+                     region_worker={"LAT": 0}, region_issuer={"LAT": 1} if two_issuers else None,
+                     n_loaders=2 if two_issuers else 1, alias_waits=two_issuers)
+    # (alias_waits with two issuers: the program-order argument below ran through the d(latent) MMAs, which now belong
+    # to the other issuer - the first MMA into D2 / SB waits explicitly until the other has been read)
     H = T["Wcat_t"].shape[1] // 2
     num_obs = T["num_obs"]
     assert H % 128 == 0
@@ -1007,7 +1076,7 @@ def trunk_backward_program(T, n_stages=8):
         acc = p.acc("SA")
         _dense(p, [d_in], tW4, n3, acc, k_last_steps=(d_out.shape[1] + 15) // 16)
         d3 = _boxes(p, acc, n3, EPI_DELU, 0, tG3, aux_tensor=tS3)
-        acc = p.acc("D2")
+        acc = p.acc("D2", carry=("SB",) if ni == 0 else ())       # (the previous tile's last super-chunk)
         _dense(p, d3, tW3, n2, acc)
         d2 = _boxes(p, acc, n2, EPI_DELU, 0, tG2, aux_tensor=tS2)
         accs, boxes = [None] * nsc, [None] * nsc
@@ -1132,13 +1201,21 @@ def workers():
     return n
 
 
+def issuers():
+    """MMA / LOAD issuing warps the learner's programs use: RL_CHAIN_ISSUERS = 1 | 2."""
+    import os
+    n = int(os.environ.get("RL_CHAIN_ISSUERS", "2"))
+    assert n in (1, 2)
+    return n
+
+
 def teacher_forward(T, **kw):
     import os
     if workers() == 4:
         return teacher_forward_program4(T, **kw)
     la = os.environ.get("RL_CHAIN_LOOKAHEAD")
-    return teacher_forward_program(T, n_workers=workers(), lookahead=int(la) if la else None, **kw)
+    return teacher_forward_program(T, n_workers=workers(), lookahead=int(la) if la else None, two_issuers=issuers() == 2, **kw)
 
 
 def trunk_backward(T):
-    return trunk_backward_program(T)
+    return trunk_backward_program(T, two_issuers=issuers() == 2)
