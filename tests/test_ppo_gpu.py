@@ -319,3 +319,47 @@ def test_forward_and_loss_vs_oracle_at_c5_size(learner_path):
     assert abs(stats[1] - vloss.item()) <= 3e-2 * abs(vloss.item()) + 1e-3, (stats[1], vloss.item())
     assert abs(stats[2] - kl.item()) <= 5e-2 * abs(kl.item()) + 1e-3, (stats[2], kl.item())
     assert torch.isfinite(ppo.debug_grad).all() and float(ppo.debug_grad.abs().max()) > 0
+
+
+def test_adam_shadows_equals_adam_then_refresh():
+    """rl_adam_shadows (Adam + bf16 operand refresh in one launch) leaves exactly what rl_adam followed by
+    rl_refresh_shadows leaves: parameters, moments, zeroed gradient, both bf16 operands of every layer (bit for bit) -
+    for the policy range (clip coefficient + adaptive lr from the control block) and the adaptation range (fixed lr)."""
+    import ctypes as C
+    from rapid_locomotion_rl_b200 import _lib
+    from rapid_locomotion_rl_b200.ppo import ActorCritic
+    lib = _lib.lib()
+    P = _lib.ptr
+    res = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        ac = ActorCritic(42, 18, 630, 12, device="cuda:0")
+        g = torch.Generator(device="cuda").manual_seed(9)
+        ac.flat_grad.copy_(torch.randn(ac.n_total, device="cuda", generator=g) * 1e-2)
+        ac.flat_m.copy_(torch.randn(ac.n_total, device="cuda", generator=g) * 1e-3)
+        ac.flat_v.copy_(torch.rand(ac.n_total, device="cuda", generator=g) * 1e-4)
+        ctrl = torch.tensor([1e-3, 0.37, 0.0, 0.0], device="cuda")
+        steps = torch.tensor([4, 0, 9, 0], dtype=torch.int32, device="cuda")
+        main = ac.L_enc + [ac.L_cat] + ac.L_act + ac.L_cri
+        n_ad = ac.n_total - ac.n_main
+        if fused:
+            ac.adam_shadows(0, ac.n_main, ac.flat_grad, P(ctrl), 0.0, 1, steps.data_ptr(), main)
+            ac.adam_shadows(ac.n_main, n_ad, ac.flat_grad, None, 2e-3, 0, steps.data_ptr() + 8, ac.L_ada)
+        else:
+            st = _lib.current_stream()
+            _lib.check(lib.rl_adam(P(ac.flat), P(ac.flat_grad), P(ac.flat_m), P(ac.flat_v), ac.n_main, P(ctrl), 0.0, 1,
+                                   0.9, 0.999, 1e-8, 0, 1.0, steps.data_ptr(), st))
+            off = 4 * ac.n_main
+            _lib.check(lib.rl_adam(ac.flat.data_ptr() + off, ac.flat_grad.data_ptr() + off, ac.flat_m.data_ptr() + off,
+                                   ac.flat_v.data_ptr() + off, n_ad, None, 2e-3, 0, 0.9, 0.999, 1e-8, 0, 1.0,
+                                   steps.data_ptr() + 8, st))
+            ac.refresh_shadows()
+        torch.cuda.synchronize()
+        res.append(dict(flat=ac.flat.clone(), m=ac.flat_m.clone(), v=ac.flat_v.clone(), g=ac.flat_grad.clone(), steps=steps.clone(),
+                        wb=[L.wb.clone() for L in ac._all_layers], wbt=[L.wbt.clone() for L in ac._all_layers]))
+    a, b = res
+    for k in ("flat", "m", "v", "g", "steps"):
+        assert torch.equal(a[k], b[k]), k
+    assert float(a["g"].abs().max()) == 0.0 and a["steps"].tolist() == [5, 0, 10, 0]
+    for i, (x, y) in enumerate(zip(a["wb"] + a["wbt"], b["wb"] + b["wbt"])):
+        assert torch.equal(x, y), "bf16 operand %d" % i
