@@ -58,8 +58,9 @@ struct RowsArgs {
                                                 // stagger_group > 0: another stagger_ns for every further `stagger_group` CTAs
 };
 constexpr int TRACE_STAMPS = 8;
+template <bool TRACE>
 __device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
-  if (trace && threadIdx.x == 0) {
+  if (TRACE && trace && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     trace[(size_t)blockIdx.x * TRACE_STAMPS + i] = t;
@@ -158,7 +159,7 @@ __device__ __forceinline__ void issue_tile_loads(const RowsArgs& args, uint8_t* 
 }
 
 // ---- the step of one tile: waits for `bar` (phase `parity`), phases 1 - 3, stores issued (one bulk group) ----
-template <bool FUSE>
+template <bool FUSE, bool TRACE>
 __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, uint64_t* bar, uint32_t parity, int tile0,
                                           int* s_root_dirty_p, unsigned long long* trace_p) {
   RL_ROWS_TILE_SETUP(buf);
@@ -171,6 +172,16 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
   const float4 cmd = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
   uint32_t last_contacts = 0;
   if (w == 1) last_contacts = *reinterpret_cast<const uint32_t*>(b.last_contacts + (size_t)e * 4);
+  // ---- work that does not depend on the tile runs while it is in flight: the Philox blocks of this warp's noise columns
+  // (a ~90-instruction dependent chain each) and the DOF-property re-draw test (an integer remainder) ----
+  const float* const nu_row = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
+  uint32_t rq4[4] = {0u, 0u, 0u, 0u}, rg4[4] = {0u, 0u, 0u, 0u};
+  if (!nu_row) {
+    Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | (uint32_t)w, rq4);
+    if (w == 0) Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | 4u, rg4);
+  }
+  const bool redraw = ((ep + 1) % cfg.rand_interval) == 0 &&
+                      (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor);
   __syncthreads();                      // mbarrier initialised
   {                                     // every staged byte has landed (bounded: a byte-count bug must trap, not hang)
     uint32_t spins = 0, ok = 0;
@@ -184,7 +195,7 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
       }
     }
   }
-  stamp(targs.trace, 2);
+  stamp<TRACE>(targs.trace, 2);
   ep += 1;                              // :152
 
   // ---- teleport (:768-791) by warp 0 ------------------------------------------------------------------------
@@ -251,8 +262,7 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
     for (int t = 0; t < NPART; ++t) s_part[(t * 4 + w) * QT + lane] = part[t];
 
     // DOF-property re-draw (:591-593, :544-560): rare - written straight to global memory
-    if ((ep % cfg.rand_interval) == 0 &&
-        (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor)) {
+    if (redraw) {
       float u3[4];
       if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[N + e]; u3[2] = b.dr_u[2 * N + e]; }
       else rng4(args.a.seed, (uint32_t)e, rng_step, RNG_DR, 0, u3);
@@ -272,9 +282,8 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
 
     // ---- observation noise for this leg's q / qd columns (:392): Philox block w, lanes 0-5 ----
     {
-      const float* nu = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
-      uint32_t r4[4] = {0u, 0u, 0u, 0u};
-      if (!nu) Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | (uint32_t)w, r4);
+      const float* nu = nu_row;
+      const uint32_t (&r4)[4] = rq4;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int cq = 6 + 3 * w + k, cqd = 18 + 3 * w + k;
@@ -305,14 +314,13 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
       s_wo[(WO_LRV + 3) * QT + lane] = ww.x; s_wo[(WO_LRV + 4) * QT + lane] = ww.y; s_wo[(WO_LRV + 5) * QT + lane] = ww.z;
       // gravity observation columns 0-2 with noise: Philox block 4, lanes 0-2
       g0 = grav.x; g1 = grav.y; g2 = grav.z;
-      const float* nu = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
+      const float* nu = nu_row;
       if (nu) {
         g0 += (2.0f * nu[0] - 1.0f) * cfg.noise_scale_core[0];
         g1 += (2.0f * nu[1] - 1.0f) * cfg.noise_scale_core[1];
         g2 += (2.0f * nu[2] - 1.0f) * cfg.noise_scale_core[2];
       } else {
-        uint32_t r4[4];
-        Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32), (RNG_NOISE << 16) | 4u, r4);
+        const uint32_t (&r4)[4] = rg4;
         g0 = __fmaf_rn(2.0f * centered_u16(r4, 0), cfg.noise_scale_core[0], g0);
         g1 = __fmaf_rn(2.0f * centered_u16(r4, 1), cfg.noise_scale_core[1], g1);
         g2 = __fmaf_rn(2.0f * centered_u16(r4, 2), cfg.noise_scale_core[2], g2);
@@ -362,7 +370,7 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
     }
   }
   __syncthreads();
-  stamp(targs.trace, 3);
+  stamp<TRACE>(targs.trace, 3);
 
   // =================================== phase 2 ===========================================================
   // warp w evaluates terms w, w + 4, w + 8 (reward_names order of the shipped configuration), adds them to its
@@ -434,7 +442,7 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
   if (dirty) s_root_dirty = 1;
   fence_async_smem();
   __syncthreads();
-  stamp(targs.trace, 4);
+  stamp<TRACE>(targs.trace, 4);
 
   // =================================== stores + phase 3 ==================================================
   if (tid == 0) {
@@ -462,7 +470,7 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
   }
 }
 
-template <bool FUSE, int MINB>
+template <bool FUSE, int MINB, bool TRACE>
 __global__ void __launch_bounds__(QTHREADS, MINB)
 env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
@@ -477,8 +485,8 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   // kernel before the first global access.  Hides the launch latency / CTA ramp between consecutive steps; both
   // instructions are no-ops when the launch does not carry the programmatic-serialization attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  stamp(args.trace, 0);
-  if (args.trace && tid == 0) {
+  stamp<TRACE>(args.trace, 0);
+  if (TRACE && args.trace && tid == 0) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     args.trace[(size_t)blockIdx.x * TRACE_STAMPS + 7] = smid;
@@ -498,12 +506,12 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     }
     issue_tile_loads<FUSE>(args, smem_dyn, &s_bar, tile0);
   }
-  stamp(args.trace, 1);
-  tile_body<FUSE>(args, smem_dyn, &s_bar, 0u, tile0, &s_root_dirty, args.trace);
-  stamp(args.trace, 5);
+  stamp<TRACE>(args.trace, 1);
+  tile_body<FUSE, TRACE>(args, smem_dyn, &s_bar, 0u, tile0, &s_root_dirty, args.trace);
+  stamp<TRACE>(args.trace, 5);
   if (tid == 0) {
     bulk_wait_read0();                 // the stores have read their shared-memory source
-    stamp(args.trace, 6);
+    stamp<TRACE>(args.trace, 6);
     if (b.step_state) {
       const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
       if (done == gridDim.x - 1) {
@@ -554,7 +562,7 @@ env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_b
     if (tile < 0) break;                       // uniform: the queue is empty
     uint8_t* buf = smem_dyn + bi * buf_bytes;
     if (tid == 0) s_root_dirty = 0;            // (tile_body's first barrier publishes it)
-    tile_body<FUSE>(args, buf, &s_bar[bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
+    tile_body<FUSE, false>(args, buf, &s_bar[bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
     __syncthreads();                           // every thread is done with this buffer (phase 3 read it)
     if (tid == 0) {
       bulk_wait_read0();                       // ... and so are its bulk stores: the buffer may be refilled
@@ -601,11 +609,11 @@ static int cached_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return RL_OK;
 }
 
-template <bool FUSE, int MINB>
-static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
+template <bool FUSE, int MINB, bool TRACE>
+static int launch_inst_t(const RowsArgs& ra, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(env_step_rows_kernel<FUSE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(env_step_rows_kernel<FUSE, MINB, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     configured = smem;
   }
@@ -620,9 +628,15 @@ static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
-  cudaError_t err = cudaLaunchKernelEx(&lc, env_step_rows_kernel<FUSE, MINB>, ra);
+  cudaError_t err = cudaLaunchKernelEx(&lc, env_step_rows_kernel<FUSE, MINB, TRACE>, ra);
   RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "env_step_rows_kernel launch: %s", cudaGetErrorString(err));
   return check_launch("env_step_rows_kernel");
+}
+
+// (the profiling stamps are a template parameter: the shipped instantiation carries none of their instructions)
+template <bool FUSE, int MINB>
+static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
+  return ra.trace ? launch_inst_t<FUSE, MINB, true>(ra, smem, st) : launch_inst_t<FUSE, MINB, false>(ra, smem, st);
 }
 
 template <bool FUSE>
