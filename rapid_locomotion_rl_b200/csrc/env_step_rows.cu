@@ -776,7 +776,12 @@ int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
     }
     const int n_tiles = a.cfg.num_envs / QT;
     if (env_ns >= 0) { ra.h.stagger_ns = env_ns; ra.h.stagger_from = env_from; ra.h.stagger_group = env_group; }
-    else if (n_tiles > 2 * sms && n_tiles <= (seven ? 7 : 6) * sms) { ra.h.stagger_ns = 1000; ra.h.stagger_from = 2 * sms; ra.h.stagger_group = 2 * sms; }
+    else if (n_tiles > 2 * sms && n_tiles <= (seven ? 7 : 6) * sms) {
+      // (re-tuned after the compute phase got shorter: with more than four CTAs per SM the first group is three CTA rows and
+      // the delay 1.1 us - 32768 envs: 11.13 -> 10.79 us per launch; sweep in profiles/r02_env_step.md)
+      const bool deep = n_tiles > 4 * sms;
+      ra.h.stagger_ns = deep ? 1100 : 1000; ra.h.stagger_from = (deep ? 3 : 2) * sms; ra.h.stagger_group = 2 * sms;
+    }
   }
   if (seven) return fuse ? launch_inst<true, 7>(ra, smem, st) : launch_inst<false, 7>(ra, smem, st);
   return fuse ? launch_inst<true, 6>(ra, smem, st) : launch_inst<false, 6>(ra, smem, st);
