@@ -151,22 +151,24 @@ __device__ __forceinline__ void issue_tile_loads(const RowsArgs& args, uint8_t* 
   const IssueHdr& h = args.h;
   const int NB = h.num_bodies;
   const Lay L(NB, FUSE);
-  uint64_t& s_bar = *bar;
-  const uint32_t bytes = (uint32_t)((RO_ROWS + RW_ROWS + ES_ROWS + CS_ROWS) * ROWB +
-                                    QT * (13 + 24 + NB * 3 + ND + (FUSE ? 0 : ND)) * 4);
-  mbar_expect_tx(&s_bar, bytes);
-  // simulator rows first: phase 1 starts with them
-  bulk_g2s(buf + L.dof, h.dof_state + (size_t)tile0 * 24, QT * 24 * 4, &s_bar);
-  bulk_g2s(buf + L.act, h.actions + (size_t)tile0 * ND, QT * ND * 4, &s_bar);
-  tma_load_rows(buf + L.ro, &args.m_ro, tile0, 0, &s_bar);
-  tma_load_rows(buf + L.rw, &args.m_rw, tile0, 0, &s_bar);
-  bulk_g2s(buf + L.root, h.root_states + (size_t)tile0 * 13, QT * 13 * 4, &s_bar);
-  bulk_g2s(buf + L.con, h.contact_forces + (size_t)tile0 * NB * 3, (uint32_t)(QT * NB * 3 * 4), &s_bar);
-  if (!FUSE) bulk_g2s(buf + L.tq_in, h.torques_in + (size_t)tile0 * ND, QT * ND * 4, &s_bar);
-  tma_load_rows(buf + L.es, &args.m_es12, tile0, 0, &s_bar);
-  tma_load_rows(buf + L.es + 12 * ROWB, &args.m_es1, tile0, RL_ROW_TOTAL, &s_bar);
-  tma_load_rows(buf + L.cs, &args.m_cs12, tile0, 0, &s_bar);
-  tma_load_rows(buf + L.cs + 12 * ROWB, &args.m_cs5, tile0, RL_ROW_EXTRAS, &s_bar);
+  // two landing groups: bar[0] = what the per-leg work of phase 1 reads (DOF state, actions, RO / RW blocks), bar[1] = the
+  // rest (root / contact rows for the per-env roles, the accumulator rows of phase 2).  The TMA unit serves a CTA's requests
+  // in issue order, so the leg work starts while the second half of the tile is still in flight.
+  uint64_t& bar_a = bar[0];
+  uint64_t& bar_b = bar[1];
+  mbar_expect_tx(&bar_a, (uint32_t)((RO_ROWS + RW_ROWS) * ROWB + QT * (24 + ND + (FUSE ? 0 : ND)) * 4));
+  mbar_expect_tx(&bar_b, (uint32_t)((ES_ROWS + CS_ROWS) * ROWB + QT * (13 + NB * 3) * 4));
+  bulk_g2s(buf + L.dof, h.dof_state + (size_t)tile0 * 24, QT * 24 * 4, &bar_a);
+  bulk_g2s(buf + L.act, h.actions + (size_t)tile0 * ND, QT * ND * 4, &bar_a);
+  tma_load_rows(buf + L.ro, &args.m_ro, tile0, 0, &bar_a);
+  tma_load_rows(buf + L.rw, &args.m_rw, tile0, 0, &bar_a);
+  if (!FUSE) bulk_g2s(buf + L.tq_in, h.torques_in + (size_t)tile0 * ND, QT * ND * 4, &bar_a);
+  bulk_g2s(buf + L.root, h.root_states + (size_t)tile0 * 13, QT * 13 * 4, &bar_b);
+  bulk_g2s(buf + L.con, h.contact_forces + (size_t)tile0 * NB * 3, (uint32_t)(QT * NB * 3 * 4), &bar_b);
+  tma_load_rows(buf + L.es, &args.m_es12, tile0, 0, &bar_b);
+  tma_load_rows(buf + L.es + 12 * ROWB, &args.m_es1, tile0, RL_ROW_TOTAL, &bar_b);
+  tma_load_rows(buf + L.cs, &args.m_cs12, tile0, 0, &bar_b);
+  tma_load_rows(buf + L.cs + 12 * ROWB, &args.m_cs5, tile0, RL_ROW_EXTRAS, &bar_b);
 }
 
 // ---- the step of one tile: waits for `bar` (phase `parity`), phases 1 - 3, stores issued (one bulk group) ----
@@ -174,7 +176,6 @@ template <bool FUSE, bool TRACE>
 __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, uint64_t* bar, uint32_t parity, int tile0,
                                           int* s_root_dirty_p, unsigned long long* trace_p) {
   RL_ROWS_TILE_SETUP(buf);
-  uint64_t& s_bar = *bar;
   int& s_root_dirty = *s_root_dirty_p;
   struct { unsigned long long* trace; } targs{trace_p};
   // small per-env scalars with their own dtypes: plain coalesced loads
@@ -193,34 +194,25 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
   }
   const bool redraw = ((ep + 1) % cfg.rand_interval) == 0 &&
                       (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor);
-  __syncthreads();                      // mbarrier initialised
-  {                                     // every staged byte has landed (bounded: a byte-count bug must trap, not hang)
+  __syncthreads();                      // mbarriers initialised
+  // a landing group is complete (bounded: a byte-count bug must trap, not hang)
+  auto wait_group = [&](int gidx) {
     uint32_t spins = 0, ok = 0;
-    const uint32_t bar = smem_u32(&s_bar);
+    const uint32_t bar_addr = smem_u32(bar + gidx);
     while (!ok) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                   : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
       if (!ok && ++spins > (1u << 22)) {
-        if (tid == 0) printf("env_step_rows_kernel: tile %d never landed\n", tile0 / QT);
+        if (tid == 0) printf("env_step_rows_kernel: tile %d never landed (group %d)\n", tile0 / QT, gidx);
         __trap();
       }
     }
-  }
+  };
+  wait_group(0);
   stamp<TRACE>(targs.trace, 2);
   ep += 1;                              // :152
-
-  // ---- teleport (:768-791) by warp 0 ------------------------------------------------------------------------
   float* root = s_root + lane * 13;
   bool dirty = false;
-  if (w == 0 && cfg.teleport_robots) {
-    float x = root[0], y = root[1];
-    const float x0 = x, y0 = y;
-    if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
-    if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
-    if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
-    if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
-    if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
-  }
 
   // =================================== phase 1 ===========================================================
   float tq[3], oq[3], oqd[3], oa[3], pm[3], jpt[3];
@@ -310,6 +302,18 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
 #pragma unroll
     for (int k = 0; k < 3; ++k) { oq[k] = clampf(oq[k], -co, co); oqd[k] = clampf(oqd[k], -co, co); oa[k] = clampf(oa[k], -co, co); }
 
+    // ---- the second landing group: root / contact rows, accumulators ----
+    wait_group(1);
+    // teleport (:768-791) by warp 0
+    if (w == 0 && cfg.teleport_robots) {
+      float x = root[0], y = root[1];
+      const float x0 = x, y0 = y;
+      if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
+      if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
+      if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
+      if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
+      if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
+    }
     if (w == 0) {
       // ---- frames (:159-162) ----
       const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
@@ -485,7 +489,7 @@ template <bool FUSE, int MINB, bool TRACE>
 __global__ void __launch_bounds__(QTHREADS, MINB)
 env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar[2];      // the two landing groups of the tile
   __shared__ int s_root_dirty;
   const int tile0 = blockIdx.x * QT;
   const int tid = threadIdx.x;
@@ -503,7 +507,8 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     args.trace[(size_t)blockIdx.x * TRACE_STAMPS + 7] = smid;
   }
   if (tid == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
     mbar_fence_init();
     s_root_dirty = 0;
   }
@@ -515,10 +520,10 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
       const int grp = args.h.stagger_group > 0 ? 1 + ((int)blockIdx.x - args.h.stagger_from) / args.h.stagger_group : 1;
       __nanosleep((unsigned)(args.h.stagger_ns * grp));
     }
-    issue_tile_loads<FUSE>(args, smem_dyn, &s_bar, tile0);
+    issue_tile_loads<FUSE>(args, smem_dyn, s_bar, tile0);
   }
   stamp<TRACE>(args.trace, 1);
-  tile_body<FUSE, TRACE>(args, smem_dyn, &s_bar, 0u, tile0, &s_root_dirty, args.trace);
+  tile_body<FUSE, TRACE>(args, smem_dyn, s_bar, 0u, tile0, &s_root_dirty, args.trace);
   stamp<TRACE>(args.trace, 5);
   if (tid == 0) {
     bulk_wait_read0();                 // the stores have read their shared-memory source
@@ -544,7 +549,7 @@ template <bool FUSE>
 __global__ void __launch_bounds__(QTHREADS, 3)
 env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_bytes) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_bar[4];      // two buffers x two landing groups
   __shared__ int s_root_dirty;
   __shared__ int s_tile[2];
   const int tid = threadIdx.x;
@@ -556,15 +561,14 @@ env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_b
     return nx < n_tiles ? nx : -1;
   };
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&s_bar[i], 1);
     mbar_fence_init();
     const int t0 = blockIdx.x;
     s_tile[0] = t0;
     issue_tile_loads<FUSE>(args, smem_dyn, &s_bar[0], t0 * QT);
     const int t1 = grab(t0);
     s_tile[1] = t1;
-    if (t1 >= 0) issue_tile_loads<FUSE>(args, smem_dyn + buf_bytes, &s_bar[1], t1 * QT);
+    if (t1 >= 0) issue_tile_loads<FUSE>(args, smem_dyn + buf_bytes, &s_bar[2], t1 * QT);
   }
   __syncthreads();
   for (int k = 0;; ++k) {
@@ -573,13 +577,13 @@ env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_b
     if (tile < 0) break;                       // uniform: the queue is empty
     uint8_t* buf = smem_dyn + bi * buf_bytes;
     if (tid == 0) s_root_dirty = 0;            // (tile_body's first barrier publishes it)
-    tile_body<FUSE, false>(args, buf, &s_bar[bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
+    tile_body<FUSE, false>(args, buf, &s_bar[2 * bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
     __syncthreads();                           // every thread is done with this buffer (phase 3 read it)
     if (tid == 0) {
       bulk_wait_read0();                       // ... and so are its bulk stores: the buffer may be refilled
       const int tn = grab(tile);
       s_tile[bi] = tn;                         // read two iterations from now (a barrier lies in between)
-      if (tn >= 0) issue_tile_loads<FUSE>(args, buf, &s_bar[bi], tn * QT);
+      if (tn >= 0) issue_tile_loads<FUSE>(args, buf, &s_bar[2 * bi], tn * QT);
     }
   }
   if (tid == 0) {
