@@ -172,7 +172,7 @@ __device__ __forceinline__ void issue_tile_loads(const RowsArgs& args, uint8_t* 
 }
 
 // ---- the step of one tile: waits for `bar` (phase `parity`), phases 1 - 3, stores issued (one bulk group) ----
-template <bool FUSE, bool TRACE>
+template <bool FUSE, bool TRACE, bool BUMP_STEP>
 __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, uint64_t* bar, uint32_t parity, int tile0,
                                           int* s_root_dirty_p, unsigned long long* trace_p) {
   RL_ROWS_TILE_SETUP(buf);
@@ -195,6 +195,17 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
   const bool redraw = ((ep + 1) % cfg.rand_interval) == 0 &&
                       (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor);
   __syncthreads();                      // mbarriers initialised
+  if (BUMP_STEP && tid == 96 && b.step_state) {     // (a lane of warp 3, whose phase 1 is the shortest)
+    // Device step counter (CUDA-graph replay): every thread of this CTA has read step_state[0] (above the barrier), so the
+    // CTA can be counted NOW - the last CTA to have read the counter advances it for the next launch.  Counting at the end
+    // of the kernel put the atomic's round trip (~0.5 us) after the last store of the last CTA, on the launch's tail; here
+    // it overlaps with the tile's flight.
+    const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
+    if (done == gridDim.x - 1) {
+      b.step_state[1] = 0;
+      atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
+    }
+  }
   // a landing group is complete (bounded: a byte-count bug must trap, not hang)
   auto wait_group = [&](int gidx) {
     uint32_t spins = 0, ok = 0;
@@ -523,18 +534,11 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
     issue_tile_loads<FUSE>(args, smem_dyn, s_bar, tile0);
   }
   stamp<TRACE>(args.trace, 1);
-  tile_body<FUSE, TRACE>(args, smem_dyn, s_bar, 0u, tile0, &s_root_dirty, args.trace);
+  tile_body<FUSE, TRACE, true>(args, smem_dyn, s_bar, 0u, tile0, &s_root_dirty, args.trace);
   stamp<TRACE>(args.trace, 5);
   if (tid == 0) {
     bulk_wait_read0();                 // the stores have read their shared-memory source
     stamp<TRACE>(args.trace, 6);
-    if (b.step_state) {
-      const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
-      if (done == gridDim.x - 1) {
-        b.step_state[1] = 0;
-        atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
-      }
-    }
   }
 }
 
@@ -577,7 +581,7 @@ env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_b
     if (tile < 0) break;                       // uniform: the queue is empty
     uint8_t* buf = smem_dyn + bi * buf_bytes;
     if (tid == 0) s_root_dirty = 0;            // (tile_body's first barrier publishes it)
-    tile_body<FUSE, false>(args, buf, &s_bar[2 * bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
+    tile_body<FUSE, false, false>(args, buf, &s_bar[2 * bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
     __syncthreads();                           // every thread is done with this buffer (phase 3 read it)
     if (tid == 0) {
       bulk_wait_read0();                       // ... and so are its bulk stores: the buffer may be refilled
