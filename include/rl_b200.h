@@ -180,6 +180,28 @@ typedef struct RlEnvCfg {
   /* upstream call order switch: 0 = as written in this fork */
   int32_t timeout_resets;    /* 1: time_out_buf = ep_len > max_episode_length, OR into reset (:197-198) */
   int32_t max_episode_length;
+  /* train / eval env split (legged_robot.py:456-469, base_task.py:43-49): envs [num_train_envs, num_envs) are the
+   * evaluation envs.  The reference hands the EVALUATION Cfg to the functions it calls through _call_train_eval -
+   * inside the step these are _teleport_robots :576, _push_robots :588 and _randomize_dof_props :593 - and its own
+   * Cfg to everything else (rewards, observations, noise, terminations, rand_interval :591).  The eval_* fields are the
+   * evaluation configuration's values of exactly those fields.  num_train_envs == num_envs (or 0): no split. */
+  int32_t num_train_envs;
+  int32_t eval_teleport_robots;
+  float eval_teleport_lo_x;
+  float eval_teleport_hi_x;
+  float eval_teleport_shift_x;
+  float eval_teleport_lo_y;
+  float eval_teleport_hi_y;
+  float eval_teleport_shift_y;
+  int32_t eval_randomize_motor_strength;
+  int32_t eval_randomize_Kp_factor;
+  int32_t eval_randomize_Kd_factor;
+  float eval_motor_strength_lo_span[2];
+  float eval_Kp_factor_lo_span[2];
+  float eval_Kd_factor_lo_span[2];
+  int32_t eval_push_robots;
+  int32_t eval_push_interval;
+  float eval_push_lo_span[2];
 } RlEnvCfg;
 
 /* Buffers of one vectorised env (all device pointers, caller-owned). */

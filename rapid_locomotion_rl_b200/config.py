@@ -247,11 +247,29 @@ def get_scale_shift(rng):
 class TerrainInfo:
     """What the env core reads from the reference's Terrain object (utils/terrain.py:24-70,166-184)."""
 
-    def __init__(self, cfg_terrain, heightsamples=None):
+    def __init__(self, cfg_terrain, heightsamples=None, eval_terrain=None, eval_heightsamples=None):
+        """`eval_terrain`: the evaluation Cfg's terrain namespace (train / eval split, utils/terrain.py:43-57, 166-184):
+        its tiles are appended below the training tiles - `eval_x_offset` rows further (pixels), `eval_rows_offset`
+        tile rows - and `eval_env_origins` carries the shifted platform origins."""
         t = cfg_terrain
         self.mesh_type = t.mesh_type
         self.custom = t.mesh_type in ("heightfield", "trimesh")
         self.x_offset = 0
+        self.eval_x_offset = self.eval_rows_offset = 0
+        self.eval_env_origins = None
+        if self.custom and eval_terrain is not None:
+            train = TerrainInfo(t, heightsamples)
+            ev = TerrainInfo(eval_terrain, eval_heightsamples)
+            self.eval_x_offset, self.eval_rows_offset = train.tot_rows, int(t.num_rows)
+            self.tot_rows, self.tot_cols = train.tot_rows + ev.tot_rows, max(train.tot_cols, ev.tot_cols)
+            hs = np.zeros((self.tot_rows, self.tot_cols), dtype=np.int16)
+            hs[:train.tot_rows, :train.tot_cols] = train.heightsamples
+            hs[train.tot_rows:, :ev.tot_cols] = ev.heightsamples
+            self.heightsamples = hs
+            self.env_origins = train.env_origins
+            self.eval_env_origins = ev.env_origins.copy()
+            self.eval_env_origins[:, :, 0] += self.eval_x_offset * eval_terrain.horizontal_scale      # terrain.py:177
+            return
         if self.custom:
             per_env_w = int(t.terrain_length / t.horizontal_scale)
             per_env_l = int(t.terrain_width / t.horizontal_scale)
@@ -299,7 +317,7 @@ COMMAND_SUM_EXTRAS = ["lin_vel_raw", "ang_vel_raw", "lin_vel_residual", "ang_vel
 
 
 def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, sim_dt=None,
-                   custom_reward_names=(), upstream_order=False):
+                   custom_reward_names=(), upstream_order=False, eval_cfg=None):
     """Resolve a Cfg tree into EnvParams.
 
     Follows legged_robot.py _parse_cfg :1417-1429 (dt is decimation * float32(sim.dt); the
@@ -314,7 +332,10 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     sim_dt = f32(cfg.sim.dt if sim_dt is None else sim_dt)
     dt = cfg.control.decimation * sim_dt  # python double, like the reference's self.dt
     p.dt_double = dt
-    p.num_envs = int(cfg.env.num_envs)
+    # train / eval split (base_task.py:43-49): the evaluation envs follow the training envs
+    p.num_train_envs = int(cfg.env.num_envs)
+    p.num_eval_envs = 0 if eval_cfg is None else int(eval_cfg.env.num_envs)
+    p.num_envs = p.num_train_envs + p.num_eval_envs
     p.num_bodies = robot.num_bodies
     p.num_actions = int(cfg.env.num_actions)
     p.num_obs = int(cfg.env.num_observations)
@@ -497,6 +518,29 @@ def freeze_env_cfg(cfg, robot: RobotSpec = None, terrain: TerrainInfo = None, si
     p.Kd_factor_lo_span = lo_span(dr.Kd_factor_range)
     p.push_robots = int(bool(dr.push_robots))
     p.push_lo_span = [f32(-dr.max_push_vel_xy), f32(dr.max_push_vel_xy - (-dr.max_push_vel_xy))]
+    # the evaluation range's values of the fields the reference reads from the Cfg it hands to _teleport_robots :576,
+    # _push_robots :588 and _randomize_dof_props :593 (everything else in the step comes from the training Cfg)
+    ec = cfg if eval_cfg is None else eval_cfg
+    et, edr = ec.terrain, ec.domain_rand
+    p.eval_teleport_robots = int(bool(et.teleport_robots))
+    if eval_cfg is not None and p.eval_teleport_robots and not terrain.custom:
+        raise AttributeError("x_offset")
+    exo = int((terrain.eval_x_offset if eval_cfg is not None else terrain.x_offset) * et.horizontal_scale)
+    p.eval_teleport_lo_x = f32(et.teleport_thresh + exo)
+    p.eval_teleport_hi_x = f32(et.terrain_length * et.num_rows - et.teleport_thresh + exo)
+    p.eval_teleport_shift_x = f32(et.terrain_length * (et.num_rows - 1))
+    p.eval_teleport_lo_y = f32(et.teleport_thresh)
+    p.eval_teleport_hi_y = f32(et.terrain_width * et.num_cols - et.teleport_thresh)
+    p.eval_teleport_shift_y = f32(et.terrain_width * (et.num_cols - 1))
+    p.eval_randomize_motor_strength = int(bool(edr.randomize_motor_strength))
+    p.eval_randomize_Kp_factor = int(bool(edr.randomize_Kp_factor))
+    p.eval_randomize_Kd_factor = int(bool(edr.randomize_Kd_factor))
+    p.eval_motor_strength_lo_span = lo_span(edr.motor_strength_range)
+    p.eval_Kp_factor_lo_span = lo_span(edr.Kp_factor_range)
+    p.eval_Kd_factor_lo_span = lo_span(edr.Kd_factor_range)
+    p.eval_push_robots = int(bool(edr.push_robots))
+    p.eval_push_interval = int(np.ceil(edr.push_interval_s / dt))
+    p.eval_push_lo_span = [f32(-edr.max_push_vel_xy), f32(edr.max_push_vel_xy - (-edr.max_push_vel_xy))]
     p.timeout_resets = int(bool(upstream_order))      # :197-198, commented out in this fork
     # command curriculum constants (:602-607)
     p.resample_interval = int(cfg.commands.resampling_time / dt)

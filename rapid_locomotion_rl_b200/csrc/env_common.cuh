@@ -189,6 +189,53 @@ __device__ inline float sample_heights_env(const RlEnvCfg& cfg, const RlEnvBuffe
   return acc / (float)P;
 }
 
+// ---- train / eval split (legged_robot.py:456-469): the per-range fields of the configuration -------------------------
+// The reference calls _teleport_robots, _push_robots and _randomize_dof_props once per env range with that range's Cfg;
+// here an env picks its variant by index.  Without a split (num_train_envs == num_envs or 0) every env is a train env.
+struct EnvVariant {
+  int teleport_robots;
+  float teleport_lo_x, teleport_hi_x, teleport_shift_x, teleport_lo_y, teleport_hi_y, teleport_shift_y;
+  int randomize_motor_strength, randomize_Kp_factor, randomize_Kd_factor;
+  float motor_strength_lo_span[2], Kp_factor_lo_span[2], Kd_factor_lo_span[2];
+  int push_robots, push_interval;
+  float push_lo_span[2];
+};
+__device__ __host__ inline bool has_eval_split(const RlEnvCfg& cfg) {
+  return cfg.num_train_envs > 0 && cfg.num_train_envs < cfg.num_envs;
+}
+__device__ inline EnvVariant env_variant(const RlEnvCfg& cfg, int e) {
+  EnvVariant v;
+  const bool ev = has_eval_split(cfg) && e >= cfg.num_train_envs;
+#define RL_PICK(f) v.f = ev ? cfg.eval_##f : cfg.f
+  RL_PICK(teleport_robots);
+  RL_PICK(teleport_lo_x); RL_PICK(teleport_hi_x); RL_PICK(teleport_shift_x);
+  RL_PICK(teleport_lo_y); RL_PICK(teleport_hi_y); RL_PICK(teleport_shift_y);
+  RL_PICK(randomize_motor_strength); RL_PICK(randomize_Kp_factor); RL_PICK(randomize_Kd_factor);
+  RL_PICK(motor_strength_lo_span[0]); RL_PICK(motor_strength_lo_span[1]);
+  RL_PICK(Kp_factor_lo_span[0]); RL_PICK(Kp_factor_lo_span[1]);
+  RL_PICK(Kd_factor_lo_span[0]); RL_PICK(Kd_factor_lo_span[1]);
+  RL_PICK(push_robots); RL_PICK(push_interval);
+  RL_PICK(push_lo_span[0]); RL_PICK(push_lo_span[1]);
+#undef RL_PICK
+  return v;
+}
+
+// legged_robot.py:768-791 for env e of a split population (the range's own thresholds)
+__device__ inline bool teleport_xy_env(const RlEnvCfg& cfg, int e, float& x, float& y) {
+  const bool ev = has_eval_split(cfg) && e >= cfg.num_train_envs;
+  if (!(ev ? cfg.eval_teleport_robots : cfg.teleport_robots)) return false;
+  const float lo_x = ev ? cfg.eval_teleport_lo_x : cfg.teleport_lo_x, hi_x = ev ? cfg.eval_teleport_hi_x : cfg.teleport_hi_x;
+  const float sh_x = ev ? cfg.eval_teleport_shift_x : cfg.teleport_shift_x;
+  const float lo_y = ev ? cfg.eval_teleport_lo_y : cfg.teleport_lo_y, hi_y = ev ? cfg.eval_teleport_hi_y : cfg.teleport_hi_y;
+  const float sh_y = ev ? cfg.eval_teleport_shift_y : cfg.teleport_shift_y;
+  const float x0 = x, y0 = y;
+  if (x < lo_x) x += sh_x;
+  if (x > hi_x) x -= sh_x;
+  if (y < lo_y) y += sh_y;
+  if (y > hi_y) y -= sh_y;
+  return x != x0 || y != y0;
+}
+
 // legged_robot.py:768-791: the teleport of one env's base position (idempotent: a teleported position lies inside)
 __device__ inline bool teleport_xy(const RlEnvCfg& cfg, float& x, float& y) {
   const float x0 = x, y0 = y;

@@ -167,15 +167,9 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
   bool dirty = false;
   if (valid) {
     ep_len += 1;
-    if (cfg.teleport_robots) {
-      float x = root[0], y = root[1];
-      const float x0 = x, y0 = y;
-      if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
-      if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
-      if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
-      if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
-      if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
-    }
+    // (the range's own thresholds under a train / eval split: legged_robot.py:576 through _call_train_eval)
+    float x = root[0], y = root[1];
+    if (teleport_xy_env(cfg, e, x, y)) { root[0] = x; root[1] = y; dirty = true; }
   }
   if (cfg.measure_heights) __syncthreads();  // teleported positions visible to the height warps
 
@@ -229,12 +223,13 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
     grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
 
     // push (:757-766) - after the body-frame velocity was taken (:160 precedes :588)
-    if (cfg.push_robots && (ep_len % cfg.push_interval) == 0) {
+    const EnvVariant var = env_variant(cfg, e);          // train / eval split: this env's range (:588, :593)
+    if (var.push_robots && (ep_len % var.push_interval) == 0) {
       float u0, u1;
       if (b.push_u) { u0 = b.push_u[e]; u1 = b.push_u[N + e]; }
       else { float u4[4]; rng4(args.seed, (uint32_t)e, rng_step, RNG_PUSH, 0, u4); u0 = u4[0]; u1 = u4[1]; }
-      vw.x = cfg.push_lo_span[1] * u0 + cfg.push_lo_span[0];
-      vw.y = cfg.push_lo_span[1] * u1 + cfg.push_lo_span[0];
+      vw.x = var.push_lo_span[1] * u0 + var.push_lo_span[0];
+      vw.y = var.push_lo_span[1] * u1 + var.push_lo_span[0];
       root[7] = vw.x; root[8] = vw.y;
       dirty = true;
     }
@@ -294,22 +289,22 @@ env_step_kernel(const __grid_constant__ StepArgs args) {
 
     // DOF-property re-draw for envs whose episode clock hits the interval (:591-593,:544-560)
     if ((ep_len % cfg.rand_interval) == 0 &&
-        (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor)) {
+        (var.randomize_motor_strength | var.randomize_Kp_factor | var.randomize_Kd_factor)) {
       float u3[4];
       if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[N + e]; u3[2] = b.dr_u[2 * N + e]; }
       else rng4(args.seed, (uint32_t)e, rng_step, RNG_DR, 0, u3);
-      if (cfg.randomize_motor_strength) {
-        const float v = u3[0] * cfg.motor_strength_lo_span[1] + cfg.motor_strength_lo_span[0];
+      if (var.randomize_motor_strength) {
+        const float v = u3[0] * var.motor_strength_lo_span[1] + var.motor_strength_lo_span[0];
 #pragma unroll
         for (int j = 0; j < ND; ++j) { ms[j] = v; b.motor_strengths[j * N + e] = v; }
       }
-      if (cfg.randomize_Kp_factor) {
-        const float v = u3[1] * cfg.Kp_factor_lo_span[1] + cfg.Kp_factor_lo_span[0];
+      if (var.randomize_Kp_factor) {
+        const float v = u3[1] * var.Kp_factor_lo_span[1] + var.Kp_factor_lo_span[0];
 #pragma unroll 1
         for (int j = 0; j < ND; ++j) b.Kp_factors[j * N + e] = v;
       }
-      if (cfg.randomize_Kd_factor) {
-        const float v = u3[2] * cfg.Kd_factor_lo_span[1] + cfg.Kd_factor_lo_span[0];
+      if (var.randomize_Kd_factor) {
+        const float v = u3[2] * var.Kd_factor_lo_span[1] + var.Kd_factor_lo_span[0];
 #pragma unroll 1
         for (int j = 0; j < ND; ++j) b.Kd_factors[j * N + e] = v;
       }
@@ -652,6 +647,10 @@ static int validate(const RlEnvCfg* cfg, const RlEnvBuffers* b, bool need_torque
              "env step: more than %d non-height observation columns", RL_MAX_CORE_OBS);
   RL_REQUIRE(cfg->control_type >= 0 && cfg->control_type <= 2, RL_ERR_BAD_CFG, "env step: control_type=%d", cfg->control_type);
   RL_REQUIRE(cfg->rand_interval > 0 && (!cfg->push_robots || cfg->push_interval > 0), RL_ERR_BAD_CFG, "env step: intervals must be positive");
+  RL_REQUIRE(cfg->num_train_envs >= 0 && cfg->num_train_envs <= cfg->num_envs, RL_ERR_BAD_CFG, "env step: num_train_envs=%d of %d envs",
+             cfg->num_train_envs, cfg->num_envs);
+  RL_REQUIRE(!has_eval_split(*cfg) || !cfg->eval_push_robots || cfg->eval_push_interval > 0, RL_ERR_BAD_CFG,
+             "env step: the evaluation push interval must be positive");
   const int P = cfg->measure_heights ? cfg->num_height_points : 0;
   RL_REQUIRE(cfg->num_obs - P > 0, RL_ERR_BAD_CFG, "env step: num_obs=%d <= height points %d", cfg->num_obs, P);
   RL_REQUIRE(b->root_states && b->dof_state && b->contact_forces && b->actions_in && b->torques &&
@@ -726,7 +725,8 @@ static int launch_step(const RlEnvCfg* cfg, const RlEnvBuffers* b, uint64_t seed
     const int core = c.num_obs - (c.measure_heights ? c.num_height_points : 0);
     const bool std_obs = c.observe_command && !c.observe_vel && !c.observe_only_ang_vel && !c.observe_only_lin_vel &&
                          !c.observe_yaw && core == 42;
-    if (std_obs && !force_thread) return launch_step_quad(qargs, FUSE, (cudaStream_t)stream);
+    // (a train / eval split picks per-env variants of the teleport / push / re-draw fields: the one-thread-per-env kernel)
+    if (std_obs && !force_thread && !has_eval_split(c)) return launch_step_quad(qargs, FUSE, (cudaStream_t)stream);
   }
   const int tile = env_tile();
   const size_t smem = step_smem_bytes(*cfg, tile);

@@ -47,7 +47,7 @@ env_heights_prepass_kernel(const __grid_constant__ StepArgs args) {
   const uint64_t rng_step = args.step + (b.step_state ? b.step_state[0] : 0ull);
   const float* r = b.root_states + (size_t)e * 13;
   float bx = r[0], by = r[1];
-  if (cfg.teleport_robots) teleport_xy(cfg, bx, by);     // the step kernel applies (and stores) the same teleport
+  teleport_xy_env(cfg, e, bx, by);                       // the step kernel applies (and stores) the same teleport
   const float hm = sample_heights_env(cfg, b, args.seed, rng_step, e, bx, by, r[2], r[5], r[6], lane, cfg.add_noise != 0);
   if (lane == 0) b.height_mean[e] = hm;
 }

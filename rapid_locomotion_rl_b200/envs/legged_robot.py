@@ -27,10 +27,12 @@ class LeggedRobot:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True,
                  eval_cfg=None, initial_dynamics_dict=None, sim=None, terrain=None, seed=0,
                  gac_rng="philox", upstream_order=False):
-        if eval_cfg is not None:
-            raise NotImplementedError("train/eval env split (eval_cfg) is a 'next' row (SURVEY.md 8f3)")
+        # train / eval split (legged_robot.py:37-46, base_task.py:43-49): `eval_cfg.env.num_envs` evaluation envs follow the
+        # `cfg.env.num_envs` training envs; the functions the reference calls through _call_train_eval :456-469 see the
+        # evaluation Cfg for that range (teleport / push / DOF re-draw inside the step; curricula, DOF / root reset in reset_idx;
+        # env origins and rigid-body properties at construction), everything else the training Cfg
         self.cfg = cfg
-        self.eval_cfg = None
+        self.eval_cfg = eval_cfg
         self.sim_params = sim_params
         self.physics_engine = physics_engine
         self.sim_device = sim_device
@@ -47,7 +49,7 @@ class LeggedRobot:
         # ---- _parse_cfg (:1417-1429) + asset facts + terrain ----
         robot = robot_for_asset(cfg.asset.file)
         if terrain is None:
-            terrain = TerrainInfo(cfg.terrain)
+            terrain = TerrainInfo(cfg.terrain, eval_terrain=None if eval_cfg is None else eval_cfg.terrain)
         self.terrain = terrain
         sim_dt = None if sim_params is None else getattr(sim_params, "dt", None)
         # reward plugin surface (legged_robot.py:1074-1093): a scale whose name is not one of the fused terms - or whose
@@ -60,7 +62,7 @@ class LeggedRobot:
         # Default False = the fork as written = what the goldens pin.
         self.upstream_order = bool(upstream_order)
         p = self.params = freeze_env_cfg(cfg, robot, terrain, sim_dt, custom_reward_names=custom,
-                                         upstream_order=self.upstream_order)
+                                         upstream_order=self.upstream_order, eval_cfg=eval_cfg)
         if cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
             cfg.terrain.curriculum = False
         self.dt = p.dt_double
@@ -85,9 +87,19 @@ class LeggedRobot:
         cfg.domain_rand.push_interval = float(p.push_interval)
         cfg.domain_rand.rand_interval = float(p.rand_interval)
         cfg.env.num_height_points = len(p.height_points)
+        if eval_cfg is not None:
+            # _parse_cfg(eval_cfg) :1417-1429 (called after the training Cfg's: its episode length is the one left in
+            # self.max_episode_length, :43 / :1425)
+            if eval_cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
+                eval_cfg.terrain.curriculum = False
+            eval_cfg.command_ranges = public_vars(eval_cfg.commands)
+            eval_cfg.env.max_episode_length = float(np.ceil(eval_cfg.env.episode_length_s / self.dt))
+            self.max_episode_length = eval_cfg.env.max_episode_length
+            eval_cfg.domain_rand.push_interval = float(np.ceil(eval_cfg.domain_rand.push_interval_s / self.dt))
+            eval_cfg.domain_rand.rand_interval = float(np.ceil(eval_cfg.domain_rand.rand_interval_s / self.dt))
 
         N = self.num_envs = p.num_envs
-        self.num_train_envs, self.num_eval_envs = N, 0
+        self.num_train_envs, self.num_eval_envs = p.num_train_envs, p.num_eval_envs
         self.num_obs, self.num_privileged_obs, self.num_actions = p.num_obs, p.num_privileged_obs, p.num_actions
         self.num_dof = self.num_dofs = robot.num_dof
         self.num_bodies = robot.num_bodies
@@ -161,6 +173,9 @@ class LeggedRobot:
         for name, _ in self._custom_terms:          # plugin terms keep their accumulators outside the packed rows
             self.episode_sums[name] = z(N)
             self.command_sums[name] = z(N)
+        # (:1101-1105: -1 marks "no finished evaluation episode recorded yet"; the total row starts at 0 in the reference)
+        self.episode_sums_eval = {n: -1 * torch.ones(N, device=dev) for n in self.episode_sums if n != "total"}
+        self.episode_sums_eval["total"] = z(N)
         self._rew_raw = z(N) if self._custom_terms else None
         self._episode_sum_out = z(D["RL_MAX_TERMS"] + 3, dtype=torch.float64)
         self.common_step_counter = 0
@@ -203,7 +218,9 @@ class LeggedRobot:
                 self._set_dynamics(k, v)
         self._gen = torch.Generator(device=dev)
         self._gen.manual_seed(self.seed)
-        self._randomize_rigid_body_props(torch.arange(N, device=dev), cfg)
+        self._randomize_rigid_body_props(torch.arange(self.num_train_envs, device=dev), cfg)          # :1231 per range
+        if self.num_eval_envs:
+            self._randomize_rigid_body_props(torch.arange(self.num_train_envs, N, device=dev), eval_cfg)
 
         # ---- command curriculum (:1056-1072) ----
         self._init_command_distribution()
@@ -211,7 +228,8 @@ class LeggedRobot:
         self._inject = {}     # optional injected uniforms for parity tests
         self._bufs = self._make_buffers()
         self._cfg_struct = p.to_struct()
-        self._reset_cfg = self._make_reset_cfg()
+        self._reset_cfg = self._make_reset_cfg(cfg)
+        self._reset_cfg_eval = self._make_reset_cfg(eval_cfg) if eval_cfg is not None else None
         self.init_done = True
         self.record_now = self.record_eval_now = False
 
@@ -228,28 +246,43 @@ class LeggedRobot:
             target.copy_(value)
 
     def _init_env_origins(self):
-        cfg, N, dev = self.cfg, self.num_envs, self.device
-        if self.terrain.custom:
+        """:1220 `_call_train_eval(self._get_env_origins, arange(num_envs))`: one pass per env range with that range's Cfg."""
+        N, dev = self.num_envs, self.device
+        self.terrain_origins_t = self.terrain_origins_eval_t = None
+        self._origin_gen = torch.Generator(device="cpu"); self._origin_gen.manual_seed(self.seed)
+        self._get_env_origins(torch.arange(self.num_train_envs, device=dev), self.cfg, False)
+        if self.num_eval_envs:
+            self._get_env_origins(torch.arange(self.num_train_envs, N, device=dev), self.eval_cfg, True)
+
+    def _get_env_origins(self, env_ids, cfg, is_eval):
+        """legged_robot.py:1385-1415 for one env range."""
+        dev, n = self.device, len(env_ids)
+        if cfg.terrain.mesh_type in ("heightfield", "trimesh"):
             self.custom_origins = True
             t = cfg.terrain
             max_lvl, min_lvl = t.max_init_terrain_level, t.min_init_terrain_level
             if not t.curriculum:
                 max_lvl, min_lvl = t.num_rows - 1, 0
-            g = torch.Generator(device="cpu"); g.manual_seed(self.seed)
-            self.terrain_levels.copy_(torch.randint(min_lvl, max_lvl + 1, (N,), generator=g))
-            self.terrain_types.copy_(torch.div(torch.arange(N), (N / t.num_cols), rounding_mode="floor").to(torch.long))
+            self.terrain_levels[env_ids] = torch.randint(min_lvl, max_lvl + 1, (n,), generator=self._origin_gen).to(dev)
+            self.terrain_types[env_ids] = torch.div(torch.arange(n), (n / t.num_cols), rounding_mode="floor").to(torch.long).to(dev)
             t.max_terrain_level = t.num_rows
-            self.terrain_origins_t = torch.from_numpy(self.terrain.env_origins).to(dev).to(torch.float).contiguous()
-            t.terrain_origins = self.terrain_origins_t
-            self.env_origins[:] = self.terrain_origins_t[self.terrain_levels, self.terrain_types]
+            table = self.terrain.eval_env_origins if is_eval else self.terrain.env_origins
+            table_t = torch.from_numpy(table).to(dev).to(torch.float).contiguous()
+            if is_eval:
+                self.terrain_origins_eval_t = table_t
+            else:
+                self.terrain_origins_t = table_t
+            t.terrain_origins = table_t
+            self.env_origins[env_ids] = table_t[self.terrain_levels[env_ids], self.terrain_types[env_ids]]
         else:
             self.custom_origins = False
-            num_cols = np.floor(np.sqrt(N))
-            num_rows = np.ceil(N / num_cols)
+            num_cols = np.floor(np.sqrt(n))
+            num_rows = np.ceil(self.num_envs / num_cols)           # (:1408: the TOTAL env count, as written)
             xx, yy = torch.meshgrid(torch.arange(num_rows), torch.arange(num_cols), indexing="ij")
             sp = cfg.env.env_spacing
-            self.env_origins[:, 0] = (sp * xx.flatten()[:N]).to(dev)
-            self.env_origins[:, 1] = (sp * yy.flatten()[:N]).to(dev)
+            self.env_origins[env_ids, 0] = (sp * xx.flatten()[:n]).to(dev)
+            self.env_origins[env_ids, 1] = (sp * yy.flatten()[:n]).to(dev)
+            self.env_origins[env_ids, 2] = 0.
 
     def _init_command_distribution(self):
         c = self.cfg.commands
@@ -315,8 +348,10 @@ class LeggedRobot:
             self._bufs.step_state = None
         self._device_steps = bool(enable)
 
-    def _make_reset_cfg(self):
-        p, cfg = self.params, self.cfg
+    def _make_reset_cfg(self, cfg):
+        """The constants of reset_idx for one env range (the functions behind _call_train_eval :242-251 read them from the
+        range's Cfg)."""
+        p = self.params
         r = _lib.RlResetCfg()
         r.num_envs, r.n_terms, r.has_termination = p.num_envs, p.n_terms, p.has_termination
         r.custom_origins = int(self.custom_origins)
@@ -331,11 +366,13 @@ class LeggedRobot:
         r.x_init_offset, r.y_init_offset = f32(cfg.terrain.x_init_offset), f32(cfg.terrain.y_init_offset)
         for i, v in enumerate(p.default_dof_pos):
             r.default_dof_pos[i] = v
+        dr = cfg.domain_rand
         r.randomize_motor_strength, r.randomize_Kp_factor, r.randomize_Kd_factor = \
-            p.randomize_motor_strength, p.randomize_Kp_factor, p.randomize_Kd_factor
-        for name in ("motor_strength_lo_span", "Kp_factor_lo_span", "Kd_factor_lo_span"):
+            int(bool(dr.randomize_motor_strength)), int(bool(dr.randomize_Kp_factor)), int(bool(dr.randomize_Kd_factor))
+        for name, rng in (("motor_strength_lo_span", dr.motor_strength_range), ("Kp_factor_lo_span", dr.Kp_factor_range),
+                          ("Kd_factor_lo_span", dr.Kd_factor_range)):
             arr = getattr(r, name)
-            arr[0], arr[1] = getattr(p, name)
+            arr[0], arr[1] = lo_span(rng)
         return r
 
     # ------------------------------------------------------------------------------------------
@@ -478,20 +515,64 @@ class LeggedRobot:
         return obs, privileged_obs
 
     def reset_idx(self, env_ids, obs_history=None):
-        """legged_robot.py:227-290 in one launch (+ the host-side uniform command curriculum)."""
+        """legged_robot.py:227-290: one launch per env range (+ the host-side uniform command curriculum)."""
         if len(env_ids) == 0:
             return
         env_ids = env_ids.to(self.device, torch.long).contiguous()
         cfg = self.cfg
-        self._update_command_curriculum_uniform(env_ids)
-        rc = self._reset_cfg
+        if self.num_eval_envs == 0:
+            self._update_command_curriculum_uniform(env_ids, cfg)
+            self._reset_launch(env_ids, cfg, self._reset_cfg, self.terrain_origins_t, obs_history)
+            self._fill_train_extras(env_ids)
+        else:
+            # _call_train_eval :456-469: every per-range function runs on the training ids with the training Cfg, then on
+            # the evaluation ids with the evaluation Cfg
+            train_ids = env_ids[env_ids < self.num_train_envs].contiguous()
+            eval_ids = env_ids[env_ids >= self.num_train_envs].contiguous()
+            if len(train_ids):
+                self._update_command_curriculum_uniform(train_ids, cfg)
+            if len(eval_ids):
+                self._update_command_curriculum_uniform(eval_ids, self.eval_cfg)
+                # :268-276 - the evaluation rollout result is saved once per env before its accumulators are cleared (the
+                # launch below clears them)
+                self.extras["eval/episode"] = {}
+                for key in self.episode_sums:
+                    saved = self.episode_sums_eval[key]
+                    unset = eval_ids[saved[eval_ids] == -1]
+                    saved[unset] = self.episode_sums[key][unset]
+            if len(train_ids):
+                self._reset_launch(train_ids, cfg, self._reset_cfg, self.terrain_origins_t, obs_history)
+                self._fill_train_extras(train_ids)
+            if len(eval_ids):
+                self._reset_launch(eval_ids, self.eval_cfg, self._reset_cfg_eval, self.terrain_origins_eval_t, obs_history)
+                for name, _ in self._custom_terms:
+                    self.episode_sums[name][eval_ids] = 0.
+        # (:279-290: curriculum info and time-outs are written whatever the ids were)
+        if cfg.terrain.curriculum:
+            self.extras.setdefault("train/episode", {})["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
+        if cfg.commands.command_curriculum:
+            # (a persistent buffer rewritten in place: captured rollout graphs keep reading this address)
+            if getattr(self, "_env_bins_f", None) is None:
+                self._env_bins_f = torch.zeros(self.num_envs, device=self.device)
+            self._env_bins_f.copy_(self._env_command_bins)
+            self.extras["env_bins"] = self._env_bins_f[:self.num_train_envs]
+            self.extras.setdefault("train/episode", {})["command_area"] = (self.curriculum.weights_device.sum() / len(self.curriculum))
+        if cfg.commands.yaw_command_curriculum:
+            self.extras.setdefault("train/episode", {})["max_command_yaw"] = cfg.command_ranges["ang_vel_yaw"][1]
+            if self.eval_cfg is not None:
+                self.extras.setdefault("eval/episode", {})["max_command_yaw"] = self.eval_cfg.command_ranges["ang_vel_yaw"][1]
+        if cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf[:self.num_train_envs]
+
+    def _reset_launch(self, env_ids, cfg, rc, terrain_origins, obs_history):
+        """The reset kernel on `env_ids` with the constants of their range (`rc`) and that range's terrain-origin table."""
         rc.terrain_curriculum = int(bool(cfg.terrain.curriculum) and self.init_done)
         b = _lib.RlResetBuffers()
         P = _lib.ptr
         b.mask = None; b.ids = P(env_ids); b.n_ids = int(env_ids.numel())
         b.root_states = P(self.root_states); b.dof_state = P(self.dof_state); b.env_origins = P(self.env_origins)
         b.terrain_levels = P(self.terrain_levels); b.terrain_types = P(self.terrain_types)
-        b.terrain_origins = P(self.terrain_origins_t); b.commands = P(self.commands)
+        b.terrain_origins = P(terrain_origins); b.commands = P(self.commands)
         b.last_actions = P(self._last_actions); b.last_dof_vel = P(self._last_dof_vel)
         b.feet_air_time = P(self._feet_air_time); b.episode_length_buf = P(self.episode_length_buf)
         b.reset_buf = P(self._reset_u8)
@@ -508,47 +589,55 @@ class LeggedRobot:
             # hand the rewritten rows to the simulator: int32 actor ids of the reset envs (:713-717, :739-741)
             self.sim.push_dof_state(env_ids)
             self.sim.push_root_state(env_ids)
-        # extras (:261-290): device-side means, no host sync
-        p = self.params
+
+    def _fill_train_extras(self, train_ids):
+        """:261-267: mean episode sums of the training envs that were just reset (device-side, no host sync)."""
         sums = self._episode_sum_out
         means = (sums[:-1] / sums[-1]).to(torch.float)
         self.extras["train/episode"] = {"rew_" + n: means[r] for n, r in self._episode_rows.items()}
         for name, _ in self._custom_terms:          # plugin accumulators (:264-267)
-            self.extras["train/episode"]["rew_" + name] = torch.mean(self.episode_sums[name][env_ids])
-            self.episode_sums[name][env_ids] = 0.
-        if cfg.terrain.curriculum:
-            self.extras["train/episode"]["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
-        if cfg.commands.command_curriculum:
-            # (a persistent buffer rewritten in place: captured rollout graphs keep reading this address)
-            if getattr(self, "_env_bins_f", None) is None:
-                self._env_bins_f = torch.zeros(self.num_envs, device=self.device)
-            self._env_bins_f.copy_(self._env_command_bins)
-            self.extras["env_bins"] = self._env_bins_f[:self.num_train_envs]
-            self.extras["train/episode"]["command_area"] = (self.curriculum.weights_device.sum() / len(self.curriculum))
-        if cfg.commands.yaw_command_curriculum:
-            self.extras["train/episode"]["max_command_yaw"] = cfg.command_ranges["ang_vel_yaw"][1]
-        if cfg.env.send_timeouts:
-            self.extras["time_outs"] = self.time_out_buf[:self.num_train_envs]
+            self.extras["train/episode"]["rew_" + name] = torch.mean(self.episode_sums[name][train_ids])
+            self.episode_sums[name][train_ids] = 0.
 
-    def _update_command_curriculum_uniform(self, env_ids):
-        """legged_robot.py:851-880: rare (every max_episode_length steps) host-side range widening."""
-        cfg = self.cfg
-        if self.common_step_counter % self.max_episode_length != 0:
+    def reset_evaluation_envs(self):
+        """legged_robot.py:204-225: log the finished evaluation batch, widen the evaluation command ranges, reset every
+        evaluation env and clear the saved results."""
+        if self.eval_cfg is None:
+            return
+        env_ids_eval = torch.arange(self.num_train_envs, self.num_envs, device=self.device)
+        # (as in the reference, extras["eval/episode"] must exist - it does once an evaluation env went through reset_idx)
+        for key, saved in self.episode_sums_eval.items():
+            unset = env_ids_eval[saved[env_ids_eval] == -1]
+            saved[unset] = self.episode_sums[key][unset]
+            self.extras["eval/episode"]["rew_" + key] = torch.mean(saved[saved != -1])
+        self._update_command_curriculum_uniform(env_ids_eval, self.eval_cfg)       # :218
+        self.reset_idx(env_ids_eval)
+        for key in self.episode_sums_eval:
+            self.episode_sums_eval[key] = -1 * torch.ones(self.num_envs, device=self.device)
+
+    def _update_command_curriculum_uniform(self, env_ids, cfg=None):
+        """legged_robot.py:851-880: rare (every max_episode_length steps) host-side range widening.  `cfg` is the Cfg of the
+        env range (its command_ranges are widened; its curriculum switches and clip limits apply); the episode length and the
+        thresholds come from the training Cfg, the accumulators are always `self.episode_sums` (:849)."""
+        cfg = self.cfg if cfg is None else cfg
+        max_len = self.cfg.env.max_episode_length
+        if self.common_step_counter % max_len != 0:
             return
         rs = self.reward_scales
+        tc = self.cfg.commands
 
         def widen(key, sum_name, thr, lo_clip, hi_clip):
-            mean = torch.mean(self.episode_sums[sum_name][env_ids]) / self.max_episode_length
+            mean = torch.mean(self.episode_sums[sum_name][env_ids]) / max_len
             if mean > thr * rs[sum_name]:
                 r = cfg.command_ranges[key]
                 r[0] = np.clip(r[0] - 0.2, -lo_clip, 0.0)
                 r[1] = np.clip(r[1] + 0.2, 0.0, hi_clip)
         c = cfg.commands
         if c.command_curriculum and rs.get("tracking_lin_vel", 0) > 0:
-            widen("lin_vel_x", "tracking_lin_vel", c.forward_curriculum_threshold, c.max_reverse_curriculum,
+            widen("lin_vel_x", "tracking_lin_vel", tc.forward_curriculum_threshold, c.max_reverse_curriculum,
                   c.max_forward_curriculum)
         if c.yaw_command_curriculum and rs.get("tracking_ang_vel", 0) > 0:
-            widen("ang_vel_yaw", "tracking_ang_vel", c.yaw_curriculum_threshold, c.max_yaw_curriculum,
+            widen("ang_vel_yaw", "tracking_ang_vel", tc.yaw_curriculum_threshold, c.max_yaw_curriculum,
                   c.max_yaw_curriculum)
 
     def _randomize_rigid_body_props(self, env_ids, cfg):

@@ -93,14 +93,22 @@ class Runner:
         # callable(t, action_buffer, storage_slice_or_None) that may overwrite the actions between the policy and env.step
         self.inject_normal = None
         self.action_hook = None
+        self.eval_expert = False          # learn(eval_expert=...): evaluation envs act with the teacher instead of the student
         self.env.reset()
 
     # ------------------------------------------------------------------------------------------------
     def _rollout_steps(self, obs, privileged_obs, obs_history):
-        """mini_gym_learn/ppo/__init__.py:127-141 for the training envs (the eval split is 8(f3) 'next')."""
-        n = self.env.num_train_envs
+        """mini_gym_learn/ppo/__init__.py:127-141: the training envs act through PPO.act and fill the storage; evaluation envs
+        (train / eval split) act with the student - or, `eval_expert`, the teacher - policy and are only stepped."""
+        n, n_all = self.env.num_train_envs, self.env.num_envs
         alg = self.alg
         for _ in range(self.num_steps_per_env):
+            actions_eval = None
+            if n_all > n:
+                # (:130-135; evaluated first and copied: the training pass below re-uses the learner's workspace)
+                ac = alg.actor_critic
+                actions_eval = (ac.act_teacher(obs[n:], privileged_obs[n:]) if self.eval_expert
+                                else ac.act_student(obs[n:], obs_history[n:])).detach().clone()
             z = self.inject_normal if self.inject_normal is not None else \
                 torch.randn(n, self.env.num_actions, device=self.device)         # graph-safe Philox stream
             alg.transition.actions = alg.actor_critic.act(obs[:n], privileged_obs[:n], inject_normal=z).detach()
@@ -113,7 +121,8 @@ class Runner:
                 self.action_hook(alg.storage.step, t.actions, None)
             alg.storage.store_observations(obs[:n], privileged_obs[:n], obs_history[:n])
             t.observations = t.critic_observations = t.privileged_observations = t.observation_histories = None
-            obs_dict, rewards, dones, infos = self.env.step(t.actions)
+            obs_dict, rewards, dones, infos = self.env.step(t.actions if actions_eval is None else
+                                                            torch.cat((t.actions, actions_eval), dim=0))      # :136
             if self.physics is not None:
                 self.physics(self.env)
             obs, privileged_obs, obs_history = obs_dict["obs"], obs_dict["privileged_obs"], obs_dict["obs_history"]
@@ -268,7 +277,10 @@ class Runner:
         for it in range(self.current_learning_iteration, tot_iter):
             start = time.time()
             with torch.inference_mode():
+                self.eval_expert = bool(eval_expert)
                 obs, privileged_obs, obs_history = self._rollout(obs, privileged_obs, obs_history)
+                if it % eval_freq == 0:
+                    self.env.reset_evaluation_envs()                     # :194-195 (no-op without evaluation envs)
                 self.alg.compute_returns(obs[:n], privileged_obs[:n])
             mean_value_loss, mean_surrogate_loss, mean_adaptation_module_loss = self.alg.update()
             self.tot_timesteps += self.num_steps_per_env * env.num_envs

@@ -78,10 +78,33 @@ class SyntheticTerrain:
         cfg.env_origins = origins
         self.vertices = np.zeros((3, 3), dtype=np.float32)
         self.triangles = np.zeros((1, 3), dtype=np.uint32)
+        self.eval_cfg = eval_cfg
+        if eval_cfg is not None:
+            # utils/terrain.py:49-57, 166-184: the evaluation tiles are appended below the training tiles
+            ev = SyntheticTerrain(eval_cfg, num_eval_robots)
+            eval_cfg.x_offset = self.tot_rows
+            eval_cfg.rows_offset = cfg.num_rows
+            eval_cfg.env_origins[:, :, 0] += eval_cfg.x_offset * eval_cfg.horizontal_scale
+            hs = np.zeros((self.tot_rows + ev.tot_rows, max(self.tot_cols, ev.tot_cols)), dtype=np.int16)
+            hs[:self.tot_rows, :self.tot_cols] = self.heightsamples
+            hs[self.tot_rows:, :ev.tot_cols] = ev.heightsamples
+            self.heightsamples = self.height_field_raw = hs
+            self.tot_rows, self.tot_cols = hs.shape
+
+
+def clone_cfg(c, name=None):
+    """A second, independent Cfg class tree (the reference's Cfg is one process-global class): what a caller passes as
+    `eval_cfg`."""
+    import copy
+    from params_proto.neo_proto import Meta, PrefixProto
+    ns = {}
+    for k, v in vars(c).items():
+        ns[k] = clone_cfg(v, k) if isinstance(v, Meta) else copy.deepcopy(v)
+    return Meta(name or c.__name__, (PrefixProto,), ns, cli=False)
 
 
 def make_reference_env(robot="mini_cheetah", num_envs=64, device="cpu", rough=False, height_fn=None,
-                       cfg_hook=None, history=True):
+                       cfg_hook=None, history=True, eval_hook=None):
     """Build VelocityTrackingEasyEnv (+HistoryWrapper) of the reference on the fake backend.
 
     NOTE: the reference's `Cfg` is a process-global class mutated by config_*();
@@ -112,7 +135,13 @@ def make_reference_env(robot="mini_cheetah", num_envs=64, device="cpu", rough=Fa
     if cfg_hook is not None:
         cfg_hook(Cfg)
     from mini_gym.envs.mini_cheetah.velocity_tracking import VelocityTrackingEasyEnv
-    env = VelocityTrackingEasyEnv(sim_device=device, headless=True, cfg=Cfg)
+    eval_cfg = None
+    if eval_hook is not None:          # train / eval split: `eval_hook` edits a copy of the finished training Cfg
+        eval_cfg = clone_cfg(Cfg)
+        eval_hook(eval_cfg)
+    env = VelocityTrackingEasyEnv(sim_device=device, headless=True, cfg=Cfg, eval_cfg=eval_cfg)
+    if eval_cfg is not None:
+        env.eval_cfg_used = eval_cfg
     if history:
         from mini_gym.envs.wrappers.history_wrapper import HistoryWrapper
         env = HistoryWrapper(env)

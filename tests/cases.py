@@ -51,6 +51,44 @@ def case_cfg_hook(case):
     return hook
 
 
+def eval_cfg_hook(ev):
+    """The evaluation Cfg of the train / eval split case ("mc_eval": `ev` starts as a copy of the training Cfg, the
+    shipped Mini Cheetah flat-trimesh preset).  Every field the reference reads from the evaluation Cfg differs from the
+    training one: terrain extent / teleport band, pushes, DOF-property ranges, initial-position ranges."""
+    ev.env.num_envs = 16
+    ev.terrain.num_rows = 3
+    ev.terrain.num_cols = 4
+    ev.terrain.teleport_thresh = 1.5
+    ev.terrain.x_init_range = 0.4
+    ev.terrain.y_init_range = 0.7
+    ev.terrain.x_init_offset = 0.3
+    ev.terrain.y_init_offset = -0.2
+    ev.domain_rand.push_robots = True
+    ev.domain_rand.push_interval_s = 0.1
+    ev.domain_rand.max_push_vel_xy = 0.7
+    ev.domain_rand.randomize_motor_strength = False
+    ev.domain_rand.randomize_Kp_factor = True
+    ev.domain_rand.Kp_factor_range = [0.7, 1.1]
+    ev.domain_rand.randomize_Kd_factor = True
+    ev.domain_rand.Kd_factor_range = [0.6, 1.2]
+    ev.domain_rand.added_mass_range = [0.0, 1.0]
+    ev.commands.max_forward_curriculum = 2.0
+
+
+def build_eval_case(num_train):
+    """(cfg, eval_cfg, robot, terrain) of the train / eval split case for our side."""
+    from rapid_locomotion_rl_b200 import config as C
+    from rapid_locomotion_rl_b200.robots import robot_for_asset
+    cfg, ev = C.new_cfg(), C.new_cfg()
+    for c in (cfg, ev):
+        C.config_mini_cheetah(c)
+        c.env.record_video = False
+    cfg.env.num_envs = num_train
+    eval_cfg_hook(ev)
+    terrain = C.TerrainInfo(cfg.terrain, eval_terrain=ev.terrain)
+    return cfg, ev, robot_for_asset(cfg.asset.file), terrain
+
+
 # mc_rough_full: BASELINE configs[2] at the shipped terrain size (10 x 20 tiles of 8 m, border as configured: the
 # 1800 x 2600 int16 table); mc_rough is the same on a 2 x 2-tile table
 ENV_CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang"]

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
 
-CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout", "checkpoint", "curriculum_uniform"]
+CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout", "checkpoint", "curriculum_uniform", "eval_split"]
 N_ENVS = 48
 N_STEPS = 3
 
@@ -275,6 +275,175 @@ def gen_env_case(case):
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_eval_split_case():
+    """Train / eval env split (legged_robot.py:37-46, :204-225, :456-469; base_task.py:43-49): 40 training envs with the
+    shipped Mini Cheetah Cfg + 16 evaluation envs with cases.eval_cfg_hook's Cfg, through three steps (teleport, pushes and
+    DOF-property re-draws per range), a reset_idx over ids of both ranges and reset_evaluation_envs."""
+    import torch
+    import harness
+    import statekit
+    from cases import eval_cfg_hook
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    N_TRAIN = 40
+    env, Cfg = harness.make_reference_env("mini_cheetah", N_TRAIN, eval_hook=eval_cfg_hook)
+    e = env.env
+    ev = env.eval_cfg_used
+    N, NB, NT = e.num_envs, e.num_bodies, e.num_train_envs
+    assert NT == N_TRAIN and N == N_TRAIN + 16
+    rng = np.random.default_rng(31)
+    out = {}
+
+    def T(a, dtype=torch.float):
+        return torch.from_numpy(np.asarray(a)).to(dtype)
+    out["init/env_origins"] = e.env_origins.numpy().copy()
+    out["init/terrain_types"] = e.terrain_types.numpy().copy()
+    out["init/eval_terrain_origins"] = ev.terrain.terrain_origins.numpy().copy()
+    out["init/train_terrain_origins"] = Cfg.terrain.terrain_origins.numpy().copy()
+    e.commands[:, :3] = T(rng.uniform(-1, 1, (N, 3)).astype(np.float32))
+    e.last_actions[:] = T(rng.normal(0, 1, (N, 12)).astype(np.float32))
+    e.last_dof_vel[:] = T(rng.normal(0, 3, (N, 12)).astype(np.float32))
+    e.motor_strengths[:] = T(rng.uniform(0.9, 1.1, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.Kp_factors[:] = T(rng.uniform(0.8, 1.3, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.Kd_factors[:] = T(rng.uniform(0.5, 1.5, (N, 1)).astype(np.float32)).repeat(1, 12)
+    e.friction_coeffs[:] = T(rng.uniform(0.05, 4.5, N).astype(np.float32))
+    e.restitutions[:] = T(rng.uniform(0, 1, N).astype(np.float32))
+    e.payloads[:] = T(rng.uniform(-1, 3, N).astype(np.float32))
+    e.com_displacements[:] = T(rng.uniform(-0.1, 0.1, (N, 3)).astype(np.float32))
+    e.feet_air_time[:] = T((rng.uniform(0, 0.6, (N, 4)) * (rng.random((N, 4)) < 0.7)).astype(np.float32))
+    e.last_contacts = T(rng.random((N, 4)) < 0.3, torch.bool)
+    ri = int(Cfg.domain_rand.rand_interval)
+    pi_eval = int(ev.domain_rand.push_interval)
+    ep = rng.integers(0, 1001, N)
+    ep[::5] = ri * rng.integers(1, 3, len(ep[::5])) - 1          # DOF-property re-draw on step 1 (both ranges)
+    ep[NT + 1::3] = pi_eval * rng.integers(1, 50, len(ep[NT + 1::3])) - 2   # evaluation envs pushed on step 2
+    e.episode_length_buf[:] = T(ep, torch.long)
+    for k in e.episode_sums:
+        e.episode_sums[k][:] = T(rng.normal(0, 1, N).astype(np.float32))
+    for k in e.command_sums:
+        e.command_sums[k][:] = T(rng.normal(0, 1, N).astype(np.float32))
+    feet = e.feet_indices.tolist(); term = e.termination_contact_indices.tolist()
+    dflt = e.default_dof_pos[0].numpy()
+    tt, te = Cfg.terrain, ev.terrain
+    xo_eval = int(te.x_offset * te.horizontal_scale)
+    for s in range(N_STEPS):
+        root, dof, con, actions = synth_inputs(rng, e, N, NB, dflt, feet, term, tt.terrain_length * tt.num_rows,
+                                               tt.terrain_width * tt.num_cols, 0.30)
+        # evaluation robots live on the evaluation tiles (x shifted by the training rows)
+        root[NT:, 0] = xo_eval + rng.uniform(0.5, te.terrain_length * te.num_rows - 0.5, N - NT)
+        root[NT:, 1] = rng.uniform(0.5, te.terrain_width * te.num_cols - 0.5, N - NT)
+        # robots inside the teleport bands of either range
+        root[0, 0] = 0.7; root[1, 0] = tt.terrain_length * tt.num_rows - 1.2; root[2, 1] = 1.1
+        root[NT, 0] = xo_eval + 0.9; root[NT + 1, 0] = xo_eval + te.terrain_length * te.num_rows - 0.4
+        root[NT + 2, 1] = 1.2; root[NT + 3, 1] = te.terrain_width * te.num_cols - 0.8
+        root[NT + 4, 0] = xo_eval + 1.8          # inside the TRAINING threshold (2.0) but not the evaluation one (1.5)
+        e.all_root_states[:] = T(root); e.all_dof_state[:] = T(dof.reshape(-1, 2)); e.all_contact_forces[:] = T(con.reshape(-1, 3))
+        noise_u = rng.random((N, e.num_obs)).astype(np.float32)
+        dr_u = rng.random((3, N)).astype(np.float32)
+        push_u = rng.random((2, N)).astype(np.float32)
+        before = statekit.state_from_reference(e)
+        before["root_states"], before["dof_state"], before["contact_forces"] = root, dof, con
+        epn = e.episode_length_buf.numpy() + 1
+        queue = []
+        # :588 pushes per range (training Cfg: off), :593 re-draws per range, :392 noise
+        for lo, hi, c in ((0, NT, Cfg), (NT, N, ev)):
+            if c.domain_rand.push_robots:
+                ids = lo + np.nonzero(epn[lo:hi] % int(c.domain_rand.push_interval) == 0)[0]
+                queue.append(T(push_u[:, ids].T.copy()))
+        ids_all = np.nonzero(epn % ri == 0)[0]
+        for lo, hi, c in ((0, NT, Cfg), (NT, N, ev)):
+            ids = ids_all[(ids_all >= lo) & (ids_all < hi)]
+            if len(ids) == 0:
+                continue
+            for k, flag in enumerate((c.domain_rand.randomize_motor_strength, c.domain_rand.randomize_Kp_factor,
+                                      c.domain_rand.randomize_Kd_factor)):
+                if flag:
+                    queue.append(T(dr_u[k, ids].copy()))
+        queue.append(T(noise_u))
+        with ScriptedRand(torch, queue):
+            obs, priv, rew, reset, _ = type(e).__mro__[1].step(e, T(actions))
+        after = statekit.state_from_reference(e)
+        pre = "step%d/" % s
+        for k, v in before.items():
+            out[pre + "before/" + k] = v
+        for k, v in after.items():
+            out[pre + "after/" + k] = v
+        out[pre + "actions"] = actions; out[pre + "noise_u"] = noise_u; out[pre + "dr_u"] = dr_u; out[pre + "push_u"] = push_u
+        out[pre + "obs"] = obs.numpy().copy(); out[pre + "priv"] = priv.numpy().copy()
+        out[pre + "rew"] = rew.numpy().copy(); out[pre + "reset"] = reset.numpy().copy()
+
+    # ---- reset_idx over ids of both ranges (:227-290 through _call_train_eval) ----
+    ids = np.sort(np.concatenate([rng.choice(NT, NT // 3, replace=False), NT + rng.choice(N - NT, (N - NT) // 2, replace=False)]))
+    before = statekit.state_from_reference(e)
+    reset_dr_u = rng.random((3, N)).astype(np.float32)
+    init_u = rng.random((2, N)).astype(np.float32)
+    queue = []
+    for lo, hi, c in ((0, NT, Cfg), (NT, N, ev)):                     # :247 per range
+        sel = ids[(ids >= lo) & (ids < hi)]
+        for k, flag in enumerate((c.domain_rand.randomize_motor_strength, c.domain_rand.randomize_Kp_factor,
+                                  c.domain_rand.randomize_Kd_factor)):
+            if flag:
+                queue.append(T(reset_dr_u[k, sel].copy()))
+    for lo, hi in ((0, NT), (NT, N)):                                  # :251 per range (custom origins: xy offset draw)
+        sel = ids[(ids >= lo) & (ids < hi)]
+        queue.append(T(init_u[:, sel].T.copy()))
+    e.extras = {}
+    with ScriptedRand(torch, queue):
+        e.reset_idx(T(ids, torch.long))
+    after = statekit.state_from_reference(e)
+    after["dof_state"] = e.all_dof_state.numpy().reshape(N, 12, 2).copy()
+    for k, v in before.items():
+        out["reset/before/" + k] = v
+    for k, v in after.items():
+        out["reset/after/" + k] = v
+    out["reset/ids"] = ids; out["reset/dr_u"] = reset_dr_u; out["reset/init_u"] = init_u
+    out["reset/reset_buf"] = e.reset_buf.numpy().copy()
+    for k, v in e.extras["train/episode"].items():
+        if k.startswith("rew_"):
+            out["reset/extras/" + k] = np.float32(v)
+    out["reset/eval_extras_keys"] = np.array(sorted(e.extras["eval/episode"].keys()))
+    for k, v in e.episode_sums_eval.items():
+        out["reset/episode_sums_eval/" + k] = v.numpy().copy()
+
+    # ---- reset_evaluation_envs (:204-225) ----
+    for k in e.episode_sums:
+        e.episode_sums[k][:] = T(rng.normal(0, 1, N).astype(np.float32))
+    before = statekit.state_from_reference(e)
+    saved_before = {k: v.numpy().copy() for k, v in e.episode_sums_eval.items()}
+    n_eval = N - NT
+    ev_dr_u = rng.random((3, N)).astype(np.float32)
+    ev_init_u = rng.random((2, N)).astype(np.float32)
+    sel = np.arange(NT, N)
+    queue = []
+    for k, flag in enumerate((ev.domain_rand.randomize_motor_strength, ev.domain_rand.randomize_Kp_factor,
+                              ev.domain_rand.randomize_Kd_factor)):
+        if flag:
+            queue.append(T(ev_dr_u[k, sel].copy()))
+    queue.append(T(ev_init_u[:, sel].T.copy()))
+    # (extras still holds "eval/episode" from the reset above: reset_evaluation_envs :215 writes into it and raises
+    # KeyError when no evaluation env was ever reset through reset_idx)
+    with ScriptedRand(torch, queue):
+        e.reset_evaluation_envs()
+    after = statekit.state_from_reference(e)
+    after["dof_state"] = e.all_dof_state.numpy().reshape(N, 12, 2).copy()
+    for k, v in before.items():
+        out["evalreset/before/" + k] = v
+    for k, v in saved_before.items():
+        out["evalreset/before/episode_sums_eval/" + k] = v
+    for k, v in after.items():
+        out["evalreset/after/" + k] = v
+    out["evalreset/dr_u"] = ev_dr_u; out["evalreset/init_u"] = ev_init_u
+    for k, v in e.episode_sums_eval.items():
+        out["evalreset/after/episode_sums_eval/" + k] = v.numpy().copy()
+    out["evalreset/eval_extras_keys"] = np.array(sorted(e.extras.get("eval/episode", {}).keys()))
+    out["const/max_episode_length_attr"] = np.float64(e.max_episode_length)
+    out["const/eval_push_interval"] = np.float64(ev.domain_rand.push_interval)
+    out["const/eval_x_offset"] = np.int64(te.x_offset)
+    path = os.path.join(HERE, "env_mc_eval.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def gen_learner_case():
     """GAE (rollout_storage.py:76-90) and the PPO update (ppo.py:94-178) of the reference."""
     import torch
@@ -513,5 +682,7 @@ if __name__ == "__main__":
                 gen_checkpoint_case()
             elif c == "curriculum_uniform":
                 gen_curriculum_uniform_case()
+            elif c == "eval_split":
+                gen_eval_split_case()
             else:
                 gen_env_case(c)

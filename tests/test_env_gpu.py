@@ -506,3 +506,107 @@ def test_upstream_order_switch():
     assert float(env.last_actions[:16].abs().max()) == 0.0 and float(env.last_actions[24:].min()) == 0.0   # step wrote zeros anyway
     torch.testing.assert_close(env.dof_pos[:16], env.default_dof_pos.expand(16, 12))
     assert (env.commands[:24, 0] != 7.0).all() and (env.commands[24:, 0] == 7.0).all()     # reset envs + interval envs resampled
+
+
+# ---- train / eval env split (legged_robot.py:37-46, :204-225, :456-469) ---------------------------------------------------
+def make_eval_env(n_train=40, **kw):
+    from cases import build_eval_case
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    cfg, ev, robot, terrain = build_eval_case(n_train)
+    return LeggedRobot(cfg, sim_device=DEV, headless=True, eval_cfg=ev, terrain=terrain, **kw), cfg, ev
+
+
+def test_eval_split_construction_vs_golden(golden_dir):
+    """Env counts, per-range env origins / terrain-origin tables (the evaluation tiles lie below the training tiles), the
+    episode length left by the second _parse_cfg call, the evaluation push interval."""
+    g = load(golden_dir, "mc_eval")
+    env, cfg, ev = make_eval_env()
+    assert (env.num_envs, env.num_train_envs, env.num_eval_envs) == (56, 40, 16)
+    np.testing.assert_array_equal(env.terrain_types.cpu().numpy(), g["init/terrain_types"])
+    np.testing.assert_allclose(env.terrain_origins_t.cpu().numpy(), g["init/train_terrain_origins"], rtol=0, atol=0)
+    np.testing.assert_allclose(env.terrain_origins_eval_t.cpu().numpy(), g["init/eval_terrain_origins"], rtol=0, atol=0)
+    # (terrain levels are random draws; with the same levels the origins are table look-ups)
+    lv, ty = env.terrain_levels.cpu().numpy(), env.terrain_types.cpu().numpy()
+    want = np.concatenate([g["init/train_terrain_origins"][lv[:40], ty[:40]], g["init/eval_terrain_origins"][lv[40:], ty[40:]]])
+    np.testing.assert_allclose(env.env_origins.cpu().numpy(), want, rtol=0, atol=0)
+    assert float(env.max_episode_length) == float(g["const/max_episode_length_attr"])
+    assert float(ev.domain_rand.push_interval) == float(g["const/eval_push_interval"])
+    assert env.terrain.eval_x_offset == int(g["const/eval_x_offset"])
+
+
+def test_eval_split_step_vs_golden(golden_dir):
+    """Three steps of 40 training + 16 evaluation envs: teleport bands, pushes and DOF-property re-draws follow each
+    range's own Cfg, everything else the training Cfg - against the unmodified reference run with `eval_cfg`."""
+    g = load(golden_dir, "mc_eval")
+    env, cfg, ev = make_eval_env()
+    for s in range(3):
+        pre = "step%d/" % s
+        statekit.apply_to_product(env, sub(g, pre + "before/"))
+        env._inject = dict(noise_u=cu(g[pre + "noise_u"]), dr_u=cu(g[pre + "dr_u"]), push_u=cu(g[pre + "push_u"]))
+        obs, priv, rew, reset, _ = env.step(cu(g[pre + "actions"]))
+        check_step(env, obs, priv, rew, reset, g[pre + "obs"], g[pre + "priv"], g[pre + "rew"], g[pre + "reset"],
+                   "mc_eval step %d" % s)
+        got = statekit.state_from_product(env)
+        statekit.assert_state_close(got, sub(g, pre + "after/"), RTOL, ATOL, skip=("contact_forces",),
+                                    label="mc_eval step %d" % s)
+    # the golden inputs do exercise the split: evaluation envs were pushed, teleported with their own band, re-drawn
+    a, b = g["step1/before/root_states"], g["step1/after/root_states"]
+    assert (a[40:, 7:9] != b[40:, 7:9]).any() and (a[:40, 7:9] == b[:40, 7:9]).all()
+    a, b = g["step0/before/root_states"], g["step0/after/root_states"]
+    assert (a[40:44, :2] != b[40:44, :2]).any() and (a[44, :2] == b[44, :2]).all()
+    assert (g["step0/before/Kp_factors"][40:] != g["step0/after/Kp_factors"][40:]).any()
+
+
+def test_eval_split_reset_vs_golden(golden_dir):
+    """reset_idx over ids of both ranges (each range's DOF-property ranges and initial-position ranges; the evaluation
+    rollout results saved once into episode_sums_eval), then reset_evaluation_envs."""
+    g = load(golden_dir, "mc_eval")
+    env, cfg, ev = make_eval_env()
+    statekit.apply_to_product(env, sub(g, "reset/before/"))
+    env._inject = dict(reset_dr_u=cu(g["reset/dr_u"]), init_u=cu(g["reset/init_u"]))
+    env._reset_u8.copy_(cu(g["step2/reset"].astype(np.uint8)))
+    env.extras = {}
+    env.reset_idx(cu(g["reset/ids"], torch.long))
+    torch.cuda.synchronize()
+    got = statekit.state_from_product(env)
+    statekit.assert_state_close(got, sub(g, "reset/after/"), RTOL, ATOL, skip=("contact_forces", "torques", "joint_pos_target",
+                                "base_lin_vel", "base_ang_vel", "projected_gravity", "last_root_vel"), label="mc_eval reset")
+    assert np.array_equal(env.reset_buf.cpu().numpy(), g["reset/reset_buf"])
+    for k, v in sub(g, "reset/extras/").items():
+        np.testing.assert_allclose(float(env.extras["train/episode"][k]), float(v), rtol=1e-5, atol=2e-6, err_msg=k)
+    assert sorted(env.extras["eval/episode"].keys()) == list(g["reset/eval_extras_keys"])
+    for k, v in sub(g, "reset/episode_sums_eval/").items():
+        np.testing.assert_allclose(env.episode_sums_eval[k].cpu().numpy(), v, rtol=RTOL, atol=ATOL, err_msg=k)
+
+    # ---- reset_evaluation_envs ----
+    st = sub(g, "evalreset/before/")
+    statekit.apply_to_product(env, st)
+    for k, v in sub(g, "evalreset/before/episode_sums_eval/").items():
+        env.episode_sums_eval[k].copy_(cu(v))
+    env._inject = dict(reset_dr_u=cu(g["evalreset/dr_u"]), init_u=cu(g["evalreset/init_u"]))
+    env.reset_evaluation_envs()
+    torch.cuda.synchronize()
+    got = statekit.state_from_product(env)
+    statekit.assert_state_close(got, sub(g, "evalreset/after/"), RTOL, ATOL, skip=("contact_forces", "torques", "joint_pos_target",
+                                "base_lin_vel", "base_ang_vel", "projected_gravity", "last_root_vel"), label="mc_eval eval reset")
+    for k, v in sub(g, "evalreset/after/episode_sums_eval/").items():
+        np.testing.assert_allclose(env.episode_sums_eval[k].cpu().numpy(), v, rtol=0, atol=0, err_msg=k)
+    assert sorted(env.extras.get("eval/episode", {}).keys()) == list(g["evalreset/eval_extras_keys"])
+
+
+def test_eval_split_runner_iteration():
+    """One Runner iteration with evaluation envs: the storage holds the training envs only, evaluation envs are stepped with
+    the student policy and reset every eval_freq iterations."""
+    from cases import build_eval_case
+    from rapid_locomotion_rl_b200.envs import VelocityTrackingEasyEnv, HistoryWrapper
+    from rapid_locomotion_rl_b200.ppo import Runner
+    cfg, ev, robot, terrain = build_eval_case(64)
+    ev.env.num_envs = 32
+    from rapid_locomotion_rl_b200 import config as C
+    terrain = C.TerrainInfo(cfg.terrain, eval_terrain=ev.terrain)
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device=DEV, headless=True, cfg=cfg, eval_cfg=ev, terrain=terrain))
+    runner = Runner(env, device=DEV)
+    hist = runner.learn(2, eval_freq=1)
+    assert len(hist) == 2 and all(np.isfinite(h["mean_value_loss"]) for h in hist)
+    assert runner.alg.storage.observations.shape[1] == 64
+    assert int(env.episode_length_buf[64:].max()) <= runner.num_steps_per_env      # evaluation envs were reset
