@@ -514,7 +514,10 @@ enum RlChainEpiMode {
   RL_CHAIN_EPI_BIAS = 1,            /* box = bf16(acc + bias) */
   RL_CHAIN_EPI_BIAS_F32 = 2,        /* out[row, 0:ncols] = acc + bias (fp32 rows in global memory) */
   RL_CHAIN_EPI_DELU = 3,            /* box = bf16(acc * elu'(aux)), aux = saved ELU output box */
-  RL_CHAIN_EPI_PLAIN = 4            /* box = bf16(acc) */
+  RL_CHAIN_EPI_PLAIN = 4,           /* box = bf16(acc) */
+  /* the tanh networks of the reference's high_level_policy learner (high_level_policy/ppo/actor_critic.py:15, :196-213) */
+  RL_CHAIN_EPI_BIAS_TANH = 5,       /* box = bf16(tanh(acc + bias)) */
+  RL_CHAIN_EPI_DTANH = 6            /* box = bf16(acc * (1 - aux^2)), aux = saved tanh output box */
 };
 
 typedef struct RlChainEpiOp {

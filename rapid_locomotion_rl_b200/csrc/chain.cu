@@ -155,6 +155,13 @@ __device__ __forceinline__ float elu1(float x) {
   return x > 0.f ? x : e - 1.f;
 }
 
+// tanh on the fp32 accumulator: one MUFU.TANH (high_level_policy networks)
+__device__ __forceinline__ float tanh1(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int N>
 __device__ __forceinline__ void bulk_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_read_dyn(int n) {
@@ -350,7 +357,8 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
         const int store_col0 = (int)w2.x;
         if (w2.z) __nanosleep(w2.z);            // delay_ns
         if (p.dbg_sleep[2]) __nanosleep(p.dbg_sleep[2]);
-        const bool has_bias = mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32;
+        const bool has_bias = mode == RL_CHAIN_EPI_BIAS_ELU || mode == RL_CHAIN_EPI_BIAS || mode == RL_CHAIN_EPI_BIAS_F32 ||
+                              mode == RL_CHAIN_EPI_BIAS_TANH;
 
         const bool tr = TRACE && p.trace && blockIdx.x == 0 && it == p.trace_it && first;
         unsigned long long* tp = p.trace + trace_base + TRACE_EPI * i;
@@ -401,8 +409,11 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
               if (mode == RL_CHAIN_EPI_BIAS_ELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = elu1(f[j]);
+              } else if (mode == RL_CHAIN_EPI_BIAS_TANH) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = tanh1(f[j]);
               }
-            } else if (mode == RL_CHAIN_EPI_DELU) {
+            } else if (mode == RL_CHAIN_EPI_DELU || mode == RL_CHAIN_EPI_DTANH) {
               if (h == 0) chain_wait<WAIT_NS_EPI>(bars, wait_aux, it);
               const uint8_t* aux = smem + aux_off;
 #pragma unroll
@@ -412,8 +423,13 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float2 y = __bfloat1622float2(hh[q]);
-                  f[c * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
-                  f[c * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+                  if (mode == RL_CHAIN_EPI_DTANH) {
+                    f[c * 8 + 2 * q] *= 1.f - y.x * y.x;
+                    f[c * 8 + 2 * q + 1] *= 1.f - y.y * y.y;
+                  } else {
+                    f[c * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
+                    f[c * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+                  }
                 }
               }
             }
@@ -537,8 +553,11 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
           if (mode == RL_CHAIN_EPI_BIAS_ELU) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) f[j] = elu1(f[j]);
+          } else if (mode == RL_CHAIN_EPI_BIAS_TANH) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) f[j] = tanh1(f[j]);
           }
-        } else if (mode == RL_CHAIN_EPI_DELU) {
+        } else if (mode == RL_CHAIN_EPI_DELU || mode == RL_CHAIN_EPI_DTANH) {
           chain_wait<WAIT_NS_EPI>(bars, wait_aux, it);
           const uint8_t* aux = smem + aux_off;
 #pragma unroll
@@ -548,8 +567,13 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 y = __bfloat1622float2(h[q]);
-              f[c * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
-              f[c * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+              if (mode == RL_CHAIN_EPI_DTANH) {
+                f[c * 8 + 2 * q] *= 1.f - y.x * y.x;
+                f[c * 8 + 2 * q + 1] *= 1.f - y.y * y.y;
+              } else {
+                f[c * 8 + 2 * q] *= (y.x > 0.f) ? 1.f : (y.x + 1.f);
+                f[c * 8 + 2 * q + 1] *= (y.y > 0.f) ? 1.f : (y.y + 1.f);
+              }
             }
           }
         }
@@ -695,7 +719,7 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
                "rl_chain_create: epilogue op %d: partial boxes hold <= 32 columns", i);
     RL_REQUIRE(o.mode != RL_CHAIN_EPI_BIAS_F32 || o.ncols <= 32, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d: <= 32 output columns", i);
     ++n_epi_w[o.worker];
-    RL_REQUIRE(o.ncols >= 1 && o.ncols <= 64 && o.tmem_col + (o.ncols > 32 ? 64 : 32) <= 512 && o.mode <= RL_CHAIN_EPI_PLAIN, RL_ERR_BAD_ARG,
+    RL_REQUIRE(o.ncols >= 1 && o.ncols <= 64 && o.tmem_col + (o.ncols > 32 ? 64 : 32) <= 512 && o.mode <= RL_CHAIN_EPI_DTANH, RL_ERR_BAD_ARG,
                "rl_chain_create: epilogue op %d malformed", i);
     if (o.mode == RL_CHAIN_EPI_BIAS_F32)
       RL_REQUIRE(o.out_id < RL_CHAIN_MAX_OUTPUTS && d->outputs[o.out_id] != nullptr, RL_ERR_BAD_ARG, "rl_chain_create: epilogue op %d output", i);

@@ -39,12 +39,12 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
-def _mlp(dims):
+def _mlp(dims, activation="elu"):
     layers = []
     for i in range(len(dims) - 1):
         layers.append(nn.Linear(dims[i], dims[i + 1]))
         if i < len(dims) - 2:
-            layers.append(nn.ELU())
+            layers.append(nn.ELU() if activation == "elu" else nn.Tanh())
     return nn.Sequential(*layers)
 
 
@@ -56,12 +56,19 @@ class _Layer:
 class ActorCritic(nn.Module):
     is_recurrent = False
 
+    # the configuration namespace and the latent switch of this learner family: the high_level_policy variant
+    # (rapid_locomotion_rl_b200/high_level_policy: tanh networks, USE_LATENT = False) overrides both in a subclass
+    ac_args = AC_Args
+    use_latent = True
+
     def __init__(self, num_obs, num_privileged_obs, num_obs_history, num_actions, device="cuda:0", **kwargs):
         if kwargs:
             print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs.keys())))
         super().__init__()
-        if AC_Args.activation != "elu":
-            raise NotImplementedError("only the ELU activation is fused (AC_Args.activation=%r)" % AC_Args.activation)
+        AC_Args = self.ac_args          # noqa: N806 (shadows the module-level namespace on purpose)
+        self.activation = AC_Args.activation
+        if self.activation not in ("elu", "tanh"):
+            raise NotImplementedError("the fused epilogues cover ELU and tanh (AC_Args.activation=%r)" % AC_Args.activation)
         if num_actions != 12 or num_privileged_obs != 18 or AC_Args.env_factor_encoder_branch_latent_dims != [18]:
             raise NotImplementedError("the fused loss kernel is specialised for 12 actions and an 18-d latent")
         if len(AC_Args.actor_hidden_dims) != 3 or len(AC_Args.critic_hidden_dims) != 3 or \
@@ -76,13 +83,29 @@ class ActorCritic(nn.Module):
         self.latent_dim = lat
         eh = AC_Args.env_factor_encoder_branch_hidden_dims[0]
         ah = AC_Args.adaptation_module_branch_hidden_dims[0]
-        self.env_factor_encoder = _mlp([AC_Args.env_factor_encoder_branch_input_dims[0]] + eh + [lat])
+        act_fn = self.activation
+        self.env_factor_encoder = _mlp([AC_Args.env_factor_encoder_branch_input_dims[0]] + eh + [lat], act_fn)
         self.add_module("encoder", self.env_factor_encoder)           # alias, as in the reference (:56)
-        self.adaptation_module = _mlp([num_obs_history] + ah + [lat])
-        self.actor_body = _mlp([lat + num_obs] + AC_Args.actor_hidden_dims + [num_actions])
-        self.critic_body = _mlp([lat + num_obs] + AC_Args.critic_hidden_dims + [1])
+        self.adaptation_module = _mlp([num_obs_history] + ah + [lat], act_fn)
+        self.actor_body = _mlp([lat + num_obs] + AC_Args.actor_hidden_dims + [num_actions], act_fn)
+        self.critic_body = _mlp([lat + num_obs] + AC_Args.critic_hidden_dims + [1], act_fn)
         self.std = nn.Parameter(AC_Args.init_noise_std * torch.ones(num_actions))
         self.distribution = None
+        if not self.use_latent:
+            # high_level_policy with USE_LATENT = False (high_level_policy/ppo/actor_critic.py:39, :146-150, :188-192): the
+            # bodies see the observations only.  The fused passes keep their [obs | latent] input box; the latent is pinned to
+            # exactly zero instead - the encoder's last layer and the latent columns of both first layers start at zero, and
+            # zero they stay: the latent columns' weight gradient is dY^T * latent = 0, the encoder's gradient comes through
+            # those zero columns, and Adam leaves a parameter whose gradient was always zero untouched.  The observation
+            # columns are drawn like nn.Linear(num_obs, .) draws them (bound 1 / sqrt(num_obs)).
+            with torch.no_grad():
+                last = [m for m in self.env_factor_encoder if isinstance(m, nn.Linear)][-1]
+                last.weight.zero_(); last.bias.zero_()
+                bound = 1.0 / float(num_obs) ** 0.5
+                for body in (self.actor_body, self.critic_body):
+                    body[0].weight[:, :num_obs].uniform_(-bound, bound)
+                    body[0].bias.uniform_(-bound, bound)
+                    body[0].weight[:, num_obs:].zero_()
         self.to(self.device_)
         self._flatten()
         self._ws_rows = 0
@@ -241,9 +264,32 @@ class ActorCritic(nn.Module):
         return g
 
     def load_state_dict(self, state_dict, strict=True):
+        if not self.use_latent:
+            # the reference's no-latent class has `actor_body` / `critic_body` / `std` only, first layers [., num_obs]
+            # (high_level_policy/ppo/actor_critic.py:86-110): pad them with the (zero) latent columns
+            sd = dict(super().state_dict())
+            for k, v in state_dict.items():
+                if k in ("actor_body.0.weight", "critic_body.0.weight") and v.shape[1] == self.num_obs:
+                    full = torch.zeros_like(sd[k])
+                    full[:, :self.num_obs] = v
+                    v = full
+                sd[k] = v
+            state_dict = sd
         out = super().load_state_dict(state_dict, strict=strict)
         self.refresh_shadows()
         return out
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        if not self.use_latent:
+            keep = type(sd)()
+            for k, v in sd.items():
+                if k.startswith(("actor_body.", "critic_body.")) or k == "std":
+                    keep[k] = v[:, :self.num_obs] if k in ("actor_body.0.weight", "critic_body.0.weight") else v
+            if hasattr(sd, "_metadata"):
+                keep._metadata = sd._metadata
+            return keep
+        return sd
 
     # ------------------------------------------------------------------------------------------------
     # workspace
@@ -336,7 +382,9 @@ class ActorCritic(nn.Module):
     def _chain(self, key, build):
         prog = self._chains.get(key)
         if prog is None:
-            prog = build(self._chain_tensors()).compile()
+            prog = build(self._chain_tensors())
+            prog.activation = self.activation          # "tanh": hidden-layer epilogues packed as the tanh modes
+            prog = prog.compile()
             self._chains[key] = prog
         return prog
 
@@ -344,6 +392,8 @@ class ActorCritic(nn.Module):
     # GEMM plumbing
     # ------------------------------------------------------------------------------------------------
     def _gemm(self, A, lda, B, ldb, Cp, ldc, M, N, K, epi, transposed=0, bias=None, aux=None, ld_aux=0, db=None, split_k=1):
+        if self.activation != "elu" and epi in (EPI_BIAS_ELU_BF16, EPI_DELU_BF16):
+            raise NotImplementedError("the per-layer path (RL_USE_CHAIN=0) fuses ELU only; tanh networks run on the chain kernels")
         _lib.check(self._lib.rl_gemm_bf16(A, B, Cp, bias, aux, db, M, N, K, lda, ldb, ldc, ld_aux, transposed, epi,
                                           split_k, _lib.current_stream()))
 
@@ -461,14 +511,17 @@ class ActorCritic(nn.Module):
         """encoder + actor + critic in one pass.  `reuse=True` (only `evaluate` right after `act` on the
         same tensors, the PPO.act pattern ppo.py:64-65) consumes the cached pass instead of repeating it;
         the cache is single-use because env buffers are rewritten in place by kernels torch cannot see."""
-        key = (observations.data_ptr(), privileged_observations.data_ptr(), observations.shape[0])
+        key = (observations.data_ptr(), 0 if privileged_observations is None else privileged_observations.data_ptr(),
+               observations.shape[0])
         if reuse and key == self._cache_key:
             self._cache_key = None
             return
         rows = observations.shape[0]
         w = self.workspace(rows)
         self._stage_obs(observations, rows)
-        self._stage(privileged_observations, w["Xp"], self.num_priv, 0, w["Xp"].shape[1])
+        if privileged_observations is not None and self.use_latent:
+            self._stage(privileged_observations, w["Xp"], self.num_priv, 0, w["Xp"].shape[1])
+        # (no-latent family: the encoder's input box stays at its zeros and its output is pinned to zero anyway)
         self.forward_teacher(rows)
         self._mean = w["mean"][:rows]
         self._value = w["value"][:rows]
@@ -503,6 +556,9 @@ class ActorCritic(nn.Module):
         return self._mean.clone()
 
     def act_student(self, observations, observation_history, policy_info={}):
+        if not self.use_latent:        # high_level_policy/ppo/actor_critic.py:175: actor_body(observations)
+            self.update_distribution(observations, None)
+            return self._mean.clone()
         rows = observations.shape[0]
         w = self.workspace(rows)
         self._stage_obs(observations, rows)

@@ -22,6 +22,10 @@ from .. import _lib
 UNIT = 16384
 NONE = 255
 EPI_BIAS_ELU, EPI_BIAS, EPI_BIAS_F32, EPI_DELU, EPI_PLAIN = range(5)
+# The programs name the hidden-layer epilogues EPI_BIAS_ELU / EPI_DELU; a program whose `activation` is "tanh" (the
+# reference's high_level_policy learner, high_level_policy/ppo/actor_critic.py:15) is packed with these kernel modes instead
+EPI_BIAS_TANH, EPI_DTANH = 5, 6
+ACTIVATIONS = ("elu", "tanh")
 
 
 class _Wait:
@@ -443,6 +447,8 @@ class ChainProgram:
                       "store_wait_pending", "release_after_store", "out_id", "out_ld", "bias_off", "dst_off", "aux_off", "store_col0",
                       "delay_ns"):
                 setattr(x, k, o[k])
+            if getattr(self, "activation", "elu") == "tanh":
+                x.mode = {EPI_BIAS_ELU: EPI_BIAS_TANH, EPI_DELU: EPI_DTANH}.get(o["mode"], o["mode"])
         d = _lib.RlChainDesc()
         for i, (t, box_rows) in enumerate(self.tensors):
             T = d.tensors[i]
@@ -678,14 +684,14 @@ class Emulator:
                     if mode in (EPI_BIAS_ELU, EPI_BIAS, EPI_BIAS_F32):
                         f = f + p.params[o["bias_off"]:o["bias_off"] + nc].float()
                         if mode == EPI_BIAS_ELU:
-                            f = torch.where(f > 0, f, torch.exp(f) - 1)
+                            f = torch.tanh(f) if getattr(p, "activation", "elu") == "tanh" else torch.where(f > 0, f, torch.exp(f) - 1)
                     elif mode == EPI_DELU:
                         yield from spec_wait(o["wait_aux"], it, "epi")
                         ua = o["aux_off"] // UNIT
                         if unit_loading[ua]:
                             raise ChainHazard("epilogue reads aux unit %d while a TMA load is in flight" % ua)
                         y = units[ua][:, :nc]
-                        f = f * torch.where(y > 0, torch.ones_like(y), y + 1)
+                        f = f * ((1 - y * y) if getattr(p, "activation", "elu") == "tanh" else torch.where(y > 0, torch.ones_like(y), y + 1))
                     if mode == EPI_BIAS_F32:
                         out = p.outputs[o["out_id"]]
                         rr = max(0, min(128, self.rows - m0))

@@ -148,7 +148,8 @@ class PPO:
         self.actor_critic._cache_key = None      # the env buffers behind the cached pass have been rewritten
         t.rewards = rewards.clone()
         t.dones = dones
-        t.env_bins = infos["env_bins"]
+        # (the high_level_policy learner stores no bins: high_level_policy/ppo/ppo.py:81)
+        t.env_bins = infos["env_bins"] if "env_bins" in infos else torch.zeros_like(t.rewards)
         if "time_outs" in infos:
             t.rewards += PPO_Args.gamma * torch.squeeze(t.values * infos["time_outs"].unsqueeze(1).to(self.device), 1)
         self.storage.add_transitions(t)
@@ -353,7 +354,8 @@ class PPO:
             torch.cuda.current_stream().wait_event(self._ev_join)          # every forked branch rejoins
             return
         # ---- adaptation module (ppo.py:156-170): target latent from the UPDATED encoder ----
-        for _ in range(A.num_adaptation_module_substeps):
+        # (high_level_policy with USE_LATENT = False has no adaptation module to train: high_level_policy/ppo/ppo.py:157)
+        for _ in range(A.num_adaptation_module_substeps if ac.use_latent else 0):
             ac.forward_encoder(B)
             self._adapt_grads(B, world, lagged=False)
             self._reduce(allreduce, ac.n_main)
@@ -511,7 +513,8 @@ class PPO:
         use_graph = self.use_cuda_graph and multi_ok and not getattr(self, "debug_keep_grad", False)
         # Lagged adaptation schedule (minibatch_step docstring): two graphs - the first minibatch of an update has nothing
         # pending - and one eager flush after the last.  RL_PPO_OVERLAP=0 keeps the serial order.
-        lag = (use_graph and self.overlap_adaptation and ac.use_chain and A.num_adaptation_module_substeps == 1)
+        lag = (use_graph and self.overlap_adaptation and ac.use_chain and A.num_adaptation_module_substeps == 1 and
+               ac.use_latent)
         ws_gen = getattr(ac, "_ws_gen", 0)
         if use_graph and (self._graph is None or self._graph_B != mb or self._graph_lag != lag or self._graph_ws_gen != ws_gen or
                           self._graph_reduce != (allreduce if isinstance(allreduce, str) else allreduce is not None)):

@@ -42,12 +42,18 @@ def export_policy(actor_critic, directory, iteration=0):
         # an ordinary fp32 module with its own storage (the live parameters are views of one flat device buffer)
         layers = []
         for m in seq:
-            layers.append(nn.Linear(m.in_features, m.out_features) if isinstance(m, nn.Linear) else nn.ELU())
+            if isinstance(m, nn.Linear):
+                width = sd[prefix + ".%d.weight" % len(layers)].shape[1]       # (no-latent family: first layer [., num_obs])
+                layers.append(nn.Linear(width, m.out_features))
+            else:
+                layers.append(nn.ELU() if actor_critic.activation == "elu" else nn.Tanh())
         mod = nn.Sequential(*layers)
         mod.load_state_dict({k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")})
         return mod.eval()
-    for name, prefix, seq in (("adaptation_module_latest.jit", "adaptation_module", actor_critic.adaptation_module),
-                              ("body_latest.jit", "actor_body", actor_critic.actor_body)):
+    exports = [("body_latest.jit", "actor_body", actor_critic.actor_body)]
+    if actor_critic.use_latent:        # (high_level_policy/ppo/__init__.py:237-242: only with USE_LATENT)
+        exports.insert(0, ("adaptation_module_latest.jit", "adaptation_module", actor_critic.adaptation_module))
+    for name, prefix, seq in exports:
         path = os.path.join(ck, name)
         torch.jit.script(fresh(prefix, seq)).save(path)
         paths.append(path)
@@ -69,14 +75,20 @@ class RunnerArgs:
 
 
 class Runner:
+    # the learner family (overridden by rapid_locomotion_rl_b200.high_level_policy.ppo.Runner)
+    runner_args = RunnerArgs
+    actor_critic_class = ActorCritic
+    ppo_class = PPO
+
     def __init__(self, env, device="cuda:0", graph_rollout=False, physics=None, fused_rollout=True):
         """env: HistoryWrapper(VelocityTrackingEasyEnv(...)).  physics: optional callable run after every
         env.step (stands in for the simulator advancing its state tensors; synthetic in the tests)."""
         self.device = device
         self.env = env
-        actor_critic = ActorCritic(env.num_obs, env.num_privileged_obs, env.num_obs_history, env.num_actions, device=device)
-        self.alg = PPO(actor_critic, device=device)
-        self.num_steps_per_env = RunnerArgs.num_steps_per_env
+        actor_critic = self.actor_critic_class(env.num_obs, env.num_privileged_obs, env.num_obs_history, env.num_actions,
+                                               device=device)
+        self.alg = self.ppo_class(actor_critic, device=device)
+        self.num_steps_per_env = self.runner_args.num_steps_per_env
         self.alg.init_storage(env.num_train_envs, self.num_steps_per_env, [env.num_obs], [env.num_privileged_obs],
                               [env.num_obs_history], [env.num_actions])
         self.tot_timesteps = 0
@@ -142,7 +154,7 @@ class Runner:
         inner = getattr(env, "env", None)
         return (self.fused_rollout and inner is not None and hasattr(env, "_ring") and hasattr(inner, "_reset_u8") and
                 ac.use_chain and env.num_obs <= 64 and env.num_privileged_obs <= 32 and env.num_actions == 12 and
-                env.num_train_envs == env.num_envs)
+                env.num_train_envs == env.num_envs and ac.use_latent)
 
     def _rollout_steps_fused(self, obs, privileged_obs, obs_history):
         """The same loop as `_rollout_steps` with the per-step glue fused: per step ONE boundary kernel (closes
@@ -290,7 +302,7 @@ class Runner:
             history.append(rec)
             if log is not None:
                 log(rec)
-            if save_dir is not None and it % RunnerArgs.save_interval == 0:
+            if save_dir is not None and it % self.runner_args.save_interval == 0:
                 export_policy(self.alg.actor_critic, save_dir, it)
         self.current_learning_iteration += num_learning_iterations
         if save_dir is not None and num_learning_iterations > 0:

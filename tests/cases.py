@@ -162,3 +162,19 @@ def tensor_digest(a):
     a = np.asarray(a, dtype=np.float32).reshape(-1)
     idx = np.linspace(0, a.size - 1, min(64, a.size)).astype(np.int64)
     return np.concatenate([[a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()], a[idx].astype(np.float64)])
+
+
+def hlp_weights(seed=17):
+    """state_dict of the reference's high_level_policy ActorCritic with USE_LATENT = False: bodies + std only, first layers
+    [512, 42] (high_level_policy/ppo/actor_critic.py:86-110)."""
+    rng = np.random.RandomState(seed)
+    sd = {"std": np.ones(12, np.float32)}
+    for name, shape in LEARNER_SHAPES.items():
+        if not name.startswith(("actor_body", "critic_body")):
+            continue
+        if name.endswith(".0"):
+            shape = (shape[0], 42)
+        bound = 1.0 / np.sqrt(shape[1])
+        sd[name + ".weight"] = rng.uniform(-bound, bound, shape).astype(np.float32)
+        sd[name + ".bias"] = rng.uniform(-bound, bound, shape[0]).astype(np.float32)
+    return sd

@@ -49,10 +49,19 @@ elu = lambda y: torch.where(y > 0, y, torch.exp(y) - 1)
 delu = lambda y: torch.where(y > 0, torch.ones_like(y), y + 1)        # ELU' from the ELU OUTPUT
 
 
+ACT = {"elu": (elu, delu), "tanh": (torch.tanh, lambda y: 1 - y * y)}      # (activation, derivative from the OUTPUT)
+_act = ["elu"]
+
+
+def set_activation(name):
+    """The hidden-layer activation of the ref_* functions below ("elu" | "tanh": the high_level_policy networks)."""
+    _act[0] = name
+
+
 def lin(T, x, name, act=True):
     W = f32(T["W" + name])[:, :x.shape[1]]
     y = x @ W.t() + T["params"][T["b_" + name]:T["b_" + name] + W.shape[0]]
-    return elu(y) if act else y
+    return ACT[_act[0]][0](y) if act else y
 
 
 def ref_teacher(T):
@@ -80,22 +89,22 @@ def ref_trunk_backward(T):
     for tag, d_out, off, n_out in (("a", "dmean", 0, 12), ("c", "dvalue", 512, 1)):
         g = f32(T[d_out])[:, :n_out]
         s3, s2 = ("A3", "A2") if tag == "a" else ("C3", "C2")
-        d3 = bfr((g @ W(tag + "4")[:, :128]) * delu(f32(T[s3])))
-        d2 = bfr((d3 @ W(tag + "3")[:, :256]) * delu(f32(T[s2])))
-        d1 = bfr((d2 @ W(tag + "2")[:, :512]) * delu(f32(T["Y1"])[:, off:off + 512]))
+        d3 = bfr((g @ W(tag + "4")[:, :128]) * ACT[_act[0]][1](f32(T[s3])))
+        d2 = bfr((d3 @ W(tag + "3")[:, :256]) * ACT[_act[0]][1](f32(T[s2])))
+        d1 = bfr((d2 @ W(tag + "2")[:, :512]) * ACT[_act[0]][1](f32(T["Y1"])[:, off:off + 512]))
         dy1[:, off:off + 512] = d1
         out["d" + s3], out["d" + s2] = d3, d2
     out["dY1"] = dy1
     dlat = bfr(dy1 @ W("cat")[:, 42:60])
     out["dLat"] = dlat
-    dh2 = bfr((dlat @ W("e3")[:, :128]) * delu(f32(T["H2"])))
+    dh2 = bfr((dlat @ W("e3")[:, :128]) * ACT[_act[0]][1](f32(T["H2"])))
     out["dH2"] = dh2
-    out["dH1"] = bfr((dh2 @ W("e2")[:, :256]) * delu(f32(T["H1"])))
+    out["dH1"] = bfr((dh2 @ W("e2")[:, :256]) * ACT[_act[0]][1](f32(T["H1"])))
     return out
 
 
 def ref_adaptation_backward(T):
     g = f32(T["dpred"])[:, :18]
-    dd2 = bfr((g @ f32(T["Wd3"])[:, :32]) * delu(f32(T["D2"])))
-    dd1 = bfr((dd2 @ f32(T["Wd2"])[:, :256]) * delu(f32(T["D1"])))
+    dd2 = bfr((g @ f32(T["Wd3"])[:, :32]) * ACT[_act[0]][1](f32(T["D2"])))
+    dd1 = bfr((dd2 @ f32(T["Wd2"])[:, :256]) * ACT[_act[0]][1](f32(T["D1"])))
     return dict(dD2=dd2, dD1=dd1)

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_shims"))
 
-CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout", "checkpoint", "curriculum_uniform", "eval_split"]
+CASES = ["mc_flat", "go1", "go1_alt", "mc_rough", "mc_rough_full", "mc_only_lin", "mc_only_ang", "learner", "rollout", "checkpoint", "curriculum_uniform", "eval_split", "hlp"]
 N_ENVS = 48
 N_STEPS = 3
 
@@ -506,6 +506,57 @@ def gen_learner_case():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_hlp_case():
+    """The reference's second learner, high_level_policy/ppo (tanh networks, USE_LATENT = False): forward passes and one
+    full PPO.update of the UNMODIFIED classes on the seeded rollout of the learner case."""
+    import torch
+    import harness
+    harness.install()
+    import isaacgym  # noqa: F401  (fake)
+    import high_level_policy
+    assert high_level_policy.USE_LATENT is False
+    from high_level_policy.ppo import ActorCritic
+    from high_level_policy.ppo.ppo import PPO
+    from cases import hlp_weights, learner_rollout_inputs, tensor_digest
+    torch.manual_seed(1)
+    torch.set_num_threads(1)
+    out = {}
+    N2, T2 = 64, 8
+    ac = ActorCritic(42, 18, 630, 12)
+    out["keys"] = np.array(sorted(ac.state_dict().keys()))
+    ac.load_state_dict({k: torch.from_numpy(v) for k, v in hlp_weights().items()})
+    T = torch.from_numpy
+    steps, last, perm = learner_rollout_inputs(N2, T2)
+    with torch.no_grad():
+        out["fwd/mean"] = ac.act_teacher(T(steps[0]["obs"]), T(steps[0]["priv"])).numpy().copy()
+        out["fwd/student"] = ac.act_student(T(steps[0]["obs"]), T(steps[0]["hist"])).numpy().copy()
+        out["fwd/value"] = ac.evaluate(T(steps[0]["obs"]), T(steps[0]["priv"])).numpy().copy()
+    ppo = PPO(ac, device="cpu")
+    ppo.init_storage(N2, T2, [42], [18], [630], [12])
+    for sd in steps:
+        ppo.act(T(sd["obs"]), T(sd["priv"]), T(sd["hist"]))
+        ppo.process_env_step(T(sd["rew"]), T(sd["done"]), {})
+    ppo.compute_returns(T(last["obs"]), T(last["priv"]))
+    st = ppo.storage
+    flat = lambda x: x.flatten(0, 1).numpy().copy()
+    for name, tns in (("actions", st.actions), ("values", st.values), ("returns", st.returns), ("old_logp", st.actions_log_prob),
+                      ("advantages", st.advantages), ("old_mu", st.mu), ("old_sigma", st.sigma)):
+        out["ppo/storage/" + name] = flat(tns)
+    real_randperm = torch.randperm
+    torch.randperm = lambda n, **kw: T(perm).clone()
+    try:
+        res = ppo.update()
+    finally:
+        torch.randperm = real_randperm
+    out["ppo/result"] = np.array(res, dtype=np.float64)
+    out["ppo/final_lr"] = np.float64(ppo.learning_rate)
+    for k, v in ac.state_dict().items():
+        out["ppo/final_digest/" + k] = tensor_digest(v.detach().numpy())
+    path = os.path.join(HERE, "hlp.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def gen_rollout_case():
     """The rollout loop body of Runner.learn (mini_gym_learn/ppo/__init__.py:126-141) with the reference's own env,
     wrapper, ActorCritic, PPO and RolloutStorage: PPO.act -> HistoryWrapper.step -> PPO.process_env_step for T steps.
@@ -684,5 +735,7 @@ if __name__ == "__main__":
                 gen_curriculum_uniform_case()
             elif c == "eval_split":
                 gen_eval_split_case()
+            elif c == "hlp":
+                gen_hlp_case()
             else:
                 gen_env_case(c)

@@ -215,3 +215,34 @@ def test_three_and_four_worker_teacher_forward():
     prog.epis[0]["worker"] = 4
     with pytest.raises(_lib.RlError, match="worker"):
         prog.compile()
+
+
+def test_tanh_programs():
+    """The high_level_policy networks (high_level_policy/ppo/actor_critic.py:15): the same programs with `activation = "tanh"`
+    - the emulator evaluates tanh / (1 - y^2) in the hidden-layer epilogues and the packed ops carry the kernel's tanh modes."""
+    ck.set_activation("tanh")
+    try:
+        T = ck.make_tensors(ROWS, 7)
+        ref = ck.ref_teacher(T)
+        prog = chain.teacher_forward_program(T)
+        prog.activation = "tanh"
+        chain.Emulator(prog, ROWS, seed=7).run()
+        _close(T, ref, ("H1", "H2", "Xac", "Y1", "A2", "A3", "C2", "C3", "mean", "value"))
+        prog.pack()
+        E = prog._packed[2]
+        modes = {E[i].mode for i in range(len(prog.epis))}
+        assert chain.EPI_BIAS_TANH in modes and chain.EPI_BIAS_ELU not in modes
+        T = ck.make_tensors(ROWS, 8)
+        fwd = ck.ref_teacher(T)
+        for k in ("H1", "H2", "Y1", "A2", "A3", "C2", "C3"):
+            T[k].copy_(fwd[k].to(torch.bfloat16))
+        ref = ck.ref_trunk_backward(T)
+        prog = chain.trunk_backward_program(T)
+        prog.activation = "tanh"
+        chain.Emulator(prog, ROWS, seed=8).run()
+        _close(T, ref, ("dA3", "dA2", "dC3", "dC2", "dY1", "dLat", "dH2", "dH1"))
+        prog.pack()
+        E = prog._packed[2]
+        assert chain.EPI_DTANH in {E[i].mode for i in range(len(prog.epis))}
+    finally:
+        ck.set_activation("elu")
