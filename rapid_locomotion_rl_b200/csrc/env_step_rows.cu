@@ -271,6 +271,7 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
       oa[k] = a;
       s_rw[(RW_LA + j) * QT + lane] = a;              // :181-182 (row j, this lane: touched by this thread only)
       s_rw[(RW_LDV + j) * QT + lane] = qd[k];
+      if (FUSE) s_wo[(WO_JPT + j) * QT + lane] = jpt[k];
     }
 #pragma unroll
     for (int t = 0; t < NPART; ++t) s_part[(t * 4 + w) * QT + lane] = part[t];
@@ -395,7 +396,16 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
       for (int k = 0; k < 3; ++k) sc6[3 + k] = clampf((s_ro[(RO_COM + k) * QT + lane] - cfg.priv_shift[3]) * cfg.priv_scale[3], -co, co);
     }
   }
+  // the RW and WO blocks are final after phase 1 (phase 2 only reads them): they leave now, under phase 2, issued by a lane
+  // of warp 3 (the shortest phase 2) as a bulk group of its own
+  fence_async_smem();
   __syncthreads();
+  if (tid == 96) {
+    const int wo0 = FUSE ? 0 : WO_BLV;           // post_physics leaves joint_pos_target alone
+    tma_store_rows(&args.m_rw, s_rw, tile0, 0);
+    tma_store_rows(&args.m_wo, s_wo + wo0 * QT, tile0, wo0);
+    bulk_commit();
+  }
   stamp<TRACE>(targs.trace, 3);
 
   // =================================== phase 2 ===========================================================
@@ -452,7 +462,6 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
       priv[6 + 3 * w + k] = pm[k];
       if (FUSE) {
         s_tq[lane * ND + 3 * w + k] = tq[k];
-        s_wo[(WO_JPT + 3 * w + k) * QT + lane] = jpt[k];
       }
     }
     if (w == 0) {
@@ -472,9 +481,6 @@ __device__ __forceinline__ void tile_body(const RowsArgs& args, uint8_t* buf, ui
 
   // =================================== stores + phase 3 ==================================================
   if (tid == 0) {
-    const int wo0 = FUSE ? 0 : WO_BLV;           // post_physics leaves joint_pos_target alone
-    tma_store_rows(&args.m_rw, s_rw, tile0, 0);
-    tma_store_rows(&args.m_wo, s_wo + wo0 * QT, tile0, wo0);
     tma_store_rows(&args.m_es12, s_es, tile0, 0);
     tma_store_rows(&args.m_cs12, s_cs, tile0, 0);
     tma_store_rows(&args.m_cs5, s_cs + 12 * QT, tile0, RL_ROW_EXTRAS);
@@ -536,6 +542,7 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   stamp<TRACE>(args.trace, 1);
   tile_body<FUSE, TRACE, true>(args, smem_dyn, s_bar, 0u, tile0, &s_root_dirty, args.trace);
   stamp<TRACE>(args.trace, 5);
+  if (tid == 96) bulk_wait_read0();    // (the early group of the RW / WO blocks)
   if (tid == 0) {
     bulk_wait_read0();                 // the stores have read their shared-memory source
     stamp<TRACE>(args.trace, 6);
@@ -582,6 +589,7 @@ env_step_rows_persistent_kernel(const __grid_constant__ RowsArgs args, int buf_b
     uint8_t* buf = smem_dyn + bi * buf_bytes;
     if (tid == 0) s_root_dirty = 0;            // (tile_body's first barrier publishes it)
     tile_body<FUSE, false, false>(args, buf, &s_bar[2 * bi], (uint32_t)((k >> 1) & 1), tile * QT, &s_root_dirty, nullptr);
+    if (tid == 96) bulk_wait_read0();          // (the early store group of the RW / WO blocks)
     __syncthreads();                           // every thread is done with this buffer (phase 3 read it)
     if (tid == 0) {
       bulk_wait_read0();                       // ... and so are its bulk stores: the buffer may be refilled
