@@ -176,6 +176,15 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
   }
   env_stamp(1);
   __syncthreads();                      // mbarrier init / cooperative stores visible
+  if (b.step_state && tid == 96) {
+    // device step counter: every thread of this CTA has read it (above the barrier), so the CTA is counted NOW and the
+    // atomic's round trip overlaps with the tile's flight instead of ending the kernel (env_step_rows.cu, profiles/r02_env_step.md)
+    const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
+    if (done == gridDim.x - 1) {
+      b.step_state[1] = 0;
+      atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
+    }
+  }
   if (bulk_in) mbar_wait(&s_bar, 0);    // all staged bytes have landed
   env_stamp(2);
   ep += 1;                              // :152
@@ -575,14 +584,6 @@ env_step_quad_kernel(const __grid_constant__ StepArgs args) {
     if (s_root_dirty) stage_out<QTHREADS>(o_root, s_root, n_valid * 13);
   }
   env_stamp(8);
-  if (b.step_state && tid == 0) {
-    // (no fence needed: the counter value read on entry was consumed long ago; this only counts CTAs)
-    const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
-    if (done == gridDim.x - 1) {
-      b.step_state[1] = 0;
-      atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
-    }
-  }
 }
 
 static size_t quad_smem_bytes(const RlEnvCfg& cfg) {
