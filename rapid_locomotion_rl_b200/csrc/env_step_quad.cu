@@ -618,9 +618,9 @@ static int g_rows_mode = -1;
 int g_rows_persist_mode = -1;      // env_step_rows.cu: -1 automatic, 0 one tile per CTA, 1 persistent
 }
 extern "C" int rl_debug_env_rows(int32_t mode) {
-  const int prev = rl::g_rows_mode < 0 ? -1 : (rl::g_rows_mode == 0 ? 0 : (rl::g_rows_persist_mode == 1 ? 2 : (rl::g_rows_persist_mode == 0 ? 3 : 1)));
+  const int prev = rl::g_rows_mode < 0 ? -1 : (rl::g_rows_mode == 0 ? 0 : (rl::g_rows_persist_mode == 1 ? 2 : (rl::g_rows_persist_mode == 0 ? 3 : (rl::g_rows_persist_mode == 2 ? 4 : 1))));
   rl::g_rows_mode = mode < 0 ? -1 : (mode ? 1 : 0);
-  rl::g_rows_persist_mode = mode == 2 ? 1 : (mode == 3 ? 0 : -1);
+  rl::g_rows_persist_mode = mode == 2 ? 1 : (mode == 3 ? 0 : (mode == 4 ? 2 : -1));    // 4: the 16-warp wide variant
   return prev;
 }
 namespace rl {

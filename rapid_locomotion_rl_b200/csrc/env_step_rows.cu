@@ -549,6 +549,328 @@ env_step_rows_kernel(const __grid_constant__ RowsArgs args) {
   }
 }
 
+// ---- wide variant for grids of at most two CTAs per SM: 16 warps per 32-env tile ---------------------------------------
+// With one or two CTAs per SM (4000 envs = 125 CTAs) nothing hides a warp's latency: the four warps of env_step_rows_kernel
+// run ~700 dependent instructions each after the tile has landed (2.0 - 2.3 us of the 5.0 us a launch takes, r02_env_step.md).
+// Here the same arithmetic is dealt to 16 warps - warp j < 12 owns DOF j (torque, its four reward partials, its observation /
+// privileged columns), warps 12 - 15 the per-env roles; in phase 2 warp i < 12 evaluates reward term i - so the dependent chain
+// of a warp is about a third as long.  Every value is computed by the same operations in the same order (the per-leg partial
+// sums are re-associated exactly as the four-warp kernel forms them: ((0 + x0) + x1) + x2 per leg, (l0 + l1) + (l2 + l3) over
+// legs), so the results are bit-identical (tests/test_env_gpu.py::test_rows_kernel_matches_quad_kernel, mode 4).
+constexpr int WIDE_THREADS = 512;
+template <bool FUSE>
+__global__ void __launch_bounds__(WIDE_THREADS, 1)
+env_step_rows_wide_kernel(const __grid_constant__ RowsArgs args) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int s_root_dirty;
+  const int tile0 = blockIdx.x * QT;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // (one issuing thread: four threads issuing a part of the copies each onto four barriers measured SLOWER - 4000 envs 4.62 vs
+  // 4.43 us per launch - as did two issuing threads in the four-warp kernel)
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    s_root_dirty = 0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) issue_tile_loads<FUSE>(args, smem_dyn, s_bar, tile0);
+
+  RL_ROWS_TILE_SETUP(smem_dyn);
+  float* s_pd = reinterpret_cast<float*>(smem_raw + L.total);          // [NPART][12][32]: per-DOF reward partials
+  float* s_gn = s_pd + NPART * ND * QT;                                // [3][32]: noise of the gravity columns
+  const uint64_t rng_step = args.a.step + (b.step_state ? b.step_state[0] : 0ull);
+  int ep = (int)b.episode_length_buf[e];
+  const float4 cmd = *reinterpret_cast<const float4*>(b.commands + (size_t)e * 4);
+  uint32_t last_contacts = 0;
+  if (w == 13) last_contacts = *reinterpret_cast<const uint32_t*>(b.last_contacts + (size_t)e * 4);
+  // ---- work that does not need the tile: Philox blocks (DOF warps: the block of their leg; warp 12: the gravity block),
+  // the DOF re-draw test ----
+  const float* const nu_row = b.noise_u ? b.noise_u + (size_t)e * cfg.num_obs : nullptr;
+  uint32_t r4[4] = {0u, 0u, 0u, 0u};
+  if (!nu_row && w <= 12)
+    Philox::gen(args.a.seed, (uint32_t)e, (uint32_t)rng_step, (uint32_t)(rng_step >> 32),
+                (RNG_NOISE << 16) | (uint32_t)(w < 12 ? w / 3 : 4), r4);
+  const bool redraw = w < 12 && ((ep + 1) % cfg.rand_interval) == 0 &&
+                      (cfg.randomize_motor_strength | cfg.randomize_Kp_factor | cfg.randomize_Kd_factor);
+  __syncthreads();                      // mbarriers initialised
+  if (tid == 480 && b.step_state) {     // counted as soon as every thread has read the counter (see tile_body)
+    const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state + 1), 1ull);
+    if (done == gridDim.x - 1) {
+      b.step_state[1] = 0;
+      atomicAdd(reinterpret_cast<unsigned long long*>(b.step_state), 1ull);
+    }
+  }
+  auto wait_group = [&](int gidx) {
+    uint32_t spins = 0, ok = 0;
+    const uint32_t bar_addr = smem_u32(s_bar + gidx);
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_addr), "r"(0u) : "memory");
+      if (!ok && ++spins > (1u << 22)) {
+        if (tid == 0) printf("env_step_rows_wide_kernel: tile %d never landed (group %d)\n", tile0 / QT, gidx);
+        __trap();
+      }
+    }
+  };
+  ep += 1;                              // :152
+  float* root = s_root + lane * 13;
+  bool dirty = false;
+
+  // =================================== phase 1 ===========================================================
+  float tq = 0.f, oq = 0.f, oqd = 0.f, oa = 0.f, pm = 0.f;
+  float sc6[6];
+  if (w < 12) {
+    // ---- DOF j (:653-688 and its reward partials) ----
+    wait_group(0);
+    const int j = w, k = j % 3;
+    const float2 d = *reinterpret_cast<const float2*>(s_dof + lane * 24 + 2 * j);
+    const float q = d.x, qd = d.y;
+    const float kp = s_ro[(RO_KP + j) * QT + lane], kd = s_ro[(RO_KD + j) * QT + lane];
+    float ms = s_ro[(RO_MS + j) * QT + lane];
+    const float la = s_rw[(RW_LA + j) * QT + lane], ldv = s_rw[(RW_LDV + j) * QT + lane];
+    const float a = clampf(s_act[lane * ND + j], -cfg.clip_actions, cfg.clip_actions);   // :112-113
+    float t;
+    if (FUSE) {
+      float as = a * cfg.action_scale;
+      if (k == 0) as *= cfg.hip_scale_reduction;             // dofs 0,3,6,9 (:666)
+      const float jpt = as + cfg.default_dof_pos[j];
+      t = cfg.p_gains[j] * kp * (jpt - q) - cfg.d_gains[j] * kd * qd;
+      t = t * ms;
+      t = clampf(t, -cfg.torque_limits[j], cfg.torque_limits[j]);
+      s_wo[(WO_JPT + j) * QT + lane] = jpt;
+    } else {
+      t = s_tq_in[lane * ND + j];
+    }
+    tq = t;
+    s_pd[(P_TQ2 * ND + j) * QT + lane] = sq(t);
+    s_pd[(P_ACC2 * ND + j) * QT + lane] = sq((ldv - qd) / cfg.dt);
+    s_pd[(P_RATE2 * ND + j) * QT + lane] = sq(la - a);
+    {
+      float ov = -fminf(q - cfg.dof_pos_lo[j], 0.f);
+      ov += fmaxf(q - cfg.dof_pos_hi[j], 0.f);
+      s_pd[(P_LIM * ND + j) * QT + lane] = ov;
+    }
+    oq = (q - cfg.default_dof_pos[j]) * cfg.obs_scale_dof_pos;
+    oqd = qd * cfg.obs_scale_dof_vel;
+    oa = a;
+    s_rw[(RW_LA + j) * QT + lane] = a;              // :181-182
+    s_rw[(RW_LDV + j) * QT + lane] = qd;
+    // DOF-property re-draw (:591-593, :544-560): rare - written straight to global memory
+    if (redraw) {
+      float u3[4];
+      if (b.dr_u) { u3[0] = b.dr_u[e]; u3[1] = b.dr_u[N + e]; u3[2] = b.dr_u[2 * N + e]; }
+      else rng4(args.a.seed, (uint32_t)e, rng_step, RNG_DR, 0, u3);
+      const int ix = j * N + e;
+      if (cfg.randomize_motor_strength) {
+        ms = u3[0] * cfg.motor_strength_lo_span[1] + cfg.motor_strength_lo_span[0];
+        b.motor_strengths[ix] = ms;
+      }
+      if (cfg.randomize_Kp_factor) b.Kp_factors[ix] = u3[1] * cfg.Kp_factor_lo_span[1] + cfg.Kp_factor_lo_span[0];
+      if (cfg.randomize_Kd_factor) b.Kd_factors[ix] = u3[2] * cfg.Kd_factor_lo_span[1] + cfg.Kd_factor_lo_span[0];
+    }
+    pm = clampf((ms - cfg.priv_shift[4]) * cfg.priv_scale[4], -co, co);
+    // observation noise of this DOF's q / qd columns (:392): lanes k and 3 + k of the leg's Philox block
+    {
+      const int cq = 6 + j, cqd = 18 + j;
+      if (nu_row) {
+        oq += (2.0f * nu_row[cq] - 1.0f) * cfg.noise_scale_core[cq];
+        oqd += (2.0f * nu_row[cqd] - 1.0f) * cfg.noise_scale_core[cqd];
+      } else {
+        oq = __fmaf_rn(2.0f * centered_u16(r4, k), cfg.noise_scale_core[cq], oq);
+        oqd = __fmaf_rn(2.0f * centered_u16(r4, 3 + k), cfg.noise_scale_core[cqd], oqd);
+      }
+    }
+    oq = clampf(oq, -co, co); oqd = clampf(oqd, -co, co); oa = clampf(oa, -co, co);
+  } else {
+    // ---- per-env roles ----
+    wait_group(0);
+    wait_group(1);
+    if (w == 12) {
+      // teleport (:768-791), base linear velocity + projected gravity (:159-162), the gravity columns' noise draw
+      if (cfg.teleport_robots) {
+        float x = root[0], y = root[1];
+        const float x0 = x, y0 = y;
+        if (x < cfg.teleport_lo_x) x += cfg.teleport_shift_x;
+        if (x > cfg.teleport_hi_x) x -= cfg.teleport_shift_x;
+        if (y < cfg.teleport_lo_y) y += cfg.teleport_shift_y;
+        if (y > cfg.teleport_hi_y) y -= cfg.teleport_shift_y;
+        if (x != x0 || y != y0) { root[0] = x; root[1] = y; dirty = true; }
+      }
+      const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+      const V3 vw = {root[7], root[8], root[9]};
+      const V3 blv = quat_rotate_inverse(qx, qy, qz, qw, vw);
+      const V3 grav = quat_rotate_inverse(qx, qy, qz, qw, V3{0.f, 0.f, -1.f});
+      s_wo[(WO_BLV + 0) * QT + lane] = blv.x; s_wo[(WO_BLV + 1) * QT + lane] = blv.y; s_wo[(WO_BLV + 2) * QT + lane] = blv.z;
+      s_wo[(WO_GRAV + 0) * QT + lane] = grav.x; s_wo[(WO_GRAV + 1) * QT + lane] = grav.y; s_wo[(WO_GRAV + 2) * QT + lane] = grav.z;
+      s_wo[(WO_LRV + 0) * QT + lane] = vw.x; s_wo[(WO_LRV + 1) * QT + lane] = vw.y; s_wo[(WO_LRV + 2) * QT + lane] = vw.z;
+      if (nu_row) {
+        s_gn[0 * QT + lane] = 2.0f * nu_row[0] - 1.0f; s_gn[1 * QT + lane] = 2.0f * nu_row[1] - 1.0f;
+        s_gn[2 * QT + lane] = 2.0f * nu_row[2] - 1.0f;
+      } else {
+        s_gn[0 * QT + lane] = 2.0f * centered_u16(r4, 0); s_gn[1 * QT + lane] = 2.0f * centered_u16(r4, 1);
+        s_gn[2 * QT + lane] = 2.0f * centered_u16(r4, 2);
+      }
+    } else if (w == 13) {
+      // termination (:190-202), feet air time (:1619-1631), episode length
+      const float* con = s_con + lane * NB * 3;
+      bool reset = false;
+#pragma unroll 1
+      for (int k = 0; k < cfg.n_term_bodies; ++k) {
+        const float* f = con + cfg.term_idx[k] * 3;
+        reset |= sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) > 1.0f;
+      }
+      b.reset_buf[e] = reset ? 1 : 0;
+      b.episode_length_buf[e] = (int64_t)ep;
+      float r_air = 0.f;
+      uint32_t nc = 0;
+#pragma unroll
+      for (int k = 0; k < RL_NUM_FEET; ++k) {
+        float air = s_rw[(RW_AIR + k) * QT + lane];
+        const bool contact = con[cfg.feet_idx[k] * 3 + 2] > 1.0f;
+        const bool filt = contact || ((last_contacts >> (8 * k)) & 0xffu);
+        nc |= (contact ? 1u : 0u) << (8 * k);
+        const bool first = (air > 0.f) && filt;
+        air += cfg.dt;
+        r_air += (air - 0.5f) * (first ? 1.f : 0.f);
+        air *= filt ? 0.f : 1.f;
+        s_rw[(RW_AIR + k) * QT + lane] = air;
+      }
+      *reinterpret_cast<uint32_t*>(b.last_contacts + (size_t)e * 4) = nc;
+      s_air[lane] = r_air;
+    } else if (w == 14) {
+      // base angular velocity, privileged-observation scalars (:398-417)
+      const float qx = root[3], qy = root[4], qz = root[5], qw = root[6];
+      const V3 ww = {root[10], root[11], root[12]};
+      const V3 bav = quat_rotate_inverse(qx, qy, qz, qw, ww);
+      s_wo[(WO_BAV + 0) * QT + lane] = bav.x; s_wo[(WO_BAV + 1) * QT + lane] = bav.y; s_wo[(WO_BAV + 2) * QT + lane] = bav.z;
+      s_wo[(WO_LRV + 3) * QT + lane] = ww.x; s_wo[(WO_LRV + 4) * QT + lane] = ww.y; s_wo[(WO_LRV + 5) * QT + lane] = ww.z;
+      sc6[0] = clampf((s_ro[RO_FRIC * QT + lane] - cfg.priv_shift[0]) * cfg.priv_scale[0], -co, co);
+      sc6[1] = clampf((s_ro[RO_REST * QT + lane] - cfg.priv_shift[1]) * cfg.priv_scale[1], -co, co);
+      sc6[2] = clampf((s_ro[RO_PAYLOAD * QT + lane] - cfg.priv_shift[2]) * cfg.priv_scale[2], -co, co);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sc6[3 + k] = clampf((s_ro[(RO_COM + k) * QT + lane] - cfg.priv_shift[3]) * cfg.priv_scale[3], -co, co);
+    } else {
+      // collision (:1550-1553)
+      const float* con = s_con + lane * NB * 3;
+      float coll = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < cfg.n_pen_bodies; ++k) {
+        const float* f = con + cfg.pen_idx[k] * 3;
+        coll += (sqrtf((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) > 0.1f) ? 1.f : 0.f;
+      }
+      s_coll[lane] = coll;
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 480) {                      // the RW / WO blocks are final: they leave under phase 2
+    const int wo0 = FUSE ? 0 : WO_BLV;
+    tma_store_rows(&args.m_rw, s_rw, tile0, 0);
+    tma_store_rows(&args.m_wo, s_wo + wo0 * QT, tile0, wo0);
+    bulk_commit();
+  }
+
+  // =================================== phase 2 ===========================================================
+  {
+    // the four-warp kernel's partial sums: per leg ((0 + x0) + x1) + x2, over legs (l0 + l1) + (l2 + l3)
+    auto psum = [&](int t) {
+      const float* x = s_pd + t * ND * QT + lane;
+      float l[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) l[g] = ((0.f + x[(3 * g) * QT]) + x[(3 * g + 1) * QT]) + x[(3 * g + 2) * QT];
+      return (l[0] + l[1]) + (l[2] + l[3]);
+    };
+    auto BLV = [&](int i) { return s_wo[(WO_BLV + i) * QT + lane]; };
+    auto BAV = [&](int i) { return s_wo[(WO_BAV + i) * QT + lane]; };
+    auto GRAV = [&](int i) { return s_wo[(WO_GRAV + i) * QT + lane]; };
+    float* obs = s_obs + lane * W;
+    float* priv = s_priv + lane * RL_PRIV_DIM;
+    if (w < 12) {
+      wait_group(1);                     // (root rows for base_height, accumulator rows: landed long ago - this thread's own observation)
+      float r;
+      switch (w) {                       // reward_names order of the shipped configuration
+        case 0: r = expf(-(sq(cmd.x - BLV(0)) + sq(cmd.y - BLV(1))) / cfg.tracking_sigma); break;    // tracking_lin_vel
+        case 1: r = expf(-sq(cmd.z - BAV(2)) / cfg.tracking_sigma_yaw); break;                       // tracking_ang_vel
+        case 2: r = sq(BLV(2)); break;                                                               // lin_vel_z
+        case 3: r = sq(BAV(0)) + sq(BAV(1)); break;                                                  // ang_vel_xy
+        case 4: r = sq(GRAV(0)) + sq(GRAV(1)); break;                                                // orientation
+        case 5: r = psum(P_TQ2); break;                                                              // torques
+        case 6: r = psum(P_ACC2); break;                                                             // dof_acc
+        case 7: r = sq(root[2] - cfg.base_height_target); break;                                     // base_height
+        case 8: {                                                                                    // feet_air_time
+          const float cmd_xy_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y);
+          r = s_air[lane] * ((cmd_xy_norm > 0.1f) ? 1.f : 0.f);
+          break;
+        }
+        case 9: r = s_coll[lane]; break;                                                             // collision
+        case 10: r = psum(P_RATE2); break;                                                           // action_rate
+        default: r = psum(P_LIM); break;                                                             // dof_pos_limits
+      }
+      r *= cfg.term_scale[w];
+      s_es[w * QT + lane] += r; s_cs[w * QT + lane] += r; s_r[w * QT + lane] = r;
+      // this DOF's columns of the output rows (re-using the input tile: every thread passed the barrier above)
+      obs[6 + w] = oq; obs[18 + w] = oqd; obs[30 + w] = oa;
+      priv[6 + w] = pm;
+      if (FUSE) s_tq[lane * ND + w] = tq;
+    } else if (w == 12) {
+      float g0, g1, g2;
+      const float n0 = s_gn[0 * QT + lane], n1 = s_gn[1 * QT + lane], n2 = s_gn[2 * QT + lane];
+      if (nu_row) {
+        g0 = GRAV(0) + n0 * cfg.noise_scale_core[0];
+        g1 = GRAV(1) + n1 * cfg.noise_scale_core[1];
+        g2 = GRAV(2) + n2 * cfg.noise_scale_core[2];
+      } else {
+        g0 = __fmaf_rn(n0, cfg.noise_scale_core[0], GRAV(0));
+        g1 = __fmaf_rn(n1, cfg.noise_scale_core[1], GRAV(1));
+        g2 = __fmaf_rn(n2, cfg.noise_scale_core[2], GRAV(2));
+      }
+      obs[0] = clampf(g0, -co, co); obs[1] = clampf(g1, -co, co); obs[2] = clampf(g2, -co, co);
+      obs[3] = clampf(cmd.x * cfg.commands_scale[0], -co, co);
+      obs[4] = clampf(cmd.y * cfg.commands_scale[1], -co, co);
+      obs[5] = clampf(cmd.z * cfg.commands_scale[2], -co, co);
+      if (dirty) s_root_dirty = 1;
+    } else if (w == 13) {
+      const float bx = BLV(0), wz = BAV(2);
+      float* x = s_cs + 12 * QT + lane;
+      x[0 * QT] += bx;                      // lin_vel_raw (:336-340)
+      x[1 * QT] += wz;                      // ang_vel_raw
+      x[2 * QT] += sq(bx - cmd.x);          // lin_vel_residual
+      x[3 * QT] += sq(wz - cmd.z);          // ang_vel_residual
+      x[4 * QT] += 1.0f;                    // ep_timesteps
+    } else if (w == 14) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) priv[k] = sc6[k];
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+
+  // =================================== stores + phase 3 ==================================================
+  if (tid == 0) {
+    tma_store_rows(&args.m_es12, s_es, tile0, 0);
+    tma_store_rows(&args.m_cs12, s_cs, tile0, 0);
+    tma_store_rows(&args.m_cs5, s_cs + 12 * QT, tile0, RL_ROW_EXTRAS);
+    bulk_s2g(b.obs_buf + (size_t)tile0 * W, s_obs, QT * W * 4);
+    bulk_s2g(b.privileged_obs_buf + (size_t)tile0 * RL_PRIV_DIM, s_priv, QT * RL_PRIV_DIM * 4);
+    if (FUSE) bulk_s2g(b.torques + (size_t)tile0 * ND, s_tq, QT * ND * 4);
+    if (s_root_dirty) bulk_s2g(b.root_states + (size_t)tile0 * 13, s_root, QT * 13 * 4);
+    bulk_commit();
+  }
+  if (w == 15) {
+    // compute_reward's tail (:314-340): sum in reward_names order, positive clip, total row
+    float rew = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) rew += s_r[i * QT + lane];
+    if (b.rew_raw) b.rew_raw[e] = rew;
+    rew = fmaxf(rew, 0.f);
+    b.episode_sums[RL_ROW_TOTAL * N + e] = s_es[12 * QT + lane] + rew;
+    b.rew_buf[e] = rew;
+  }
+  if (tid == 480 || tid == 0) bulk_wait_read0();     // each issuing thread: its stores have read their shared-memory source
+}
+
 // ---- persistent variant: a few CTAs per SM, each with TWO tile buffers ---------------------------------------------
 // With one tile per CTA and the whole grid resident (32768 envs = 1024 CTAs, 7 per SM) every tile is requested in the
 // first microsecond, all of them land together ~5 us later, and only then does anybody compute: load and compute phases
@@ -667,6 +989,18 @@ static int launch_inst(const RowsArgs& ra, size_t smem, cudaStream_t st) {
 }
 
 template <bool FUSE>
+static int launch_wide(const RowsArgs& ra, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(env_step_rows_wide_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = smem;
+  }
+  env_step_rows_wide_kernel<FUSE><<<ra.a.cfg.num_envs / QT, WIDE_THREADS, smem, st>>>(ra);
+  return check_launch("env_step_rows_wide_kernel");
+}
+
+template <bool FUSE>
 static int launch_persistent(const RowsArgs& ra, int buf_bytes, int grid, cudaStream_t st) {
   static size_t configured = 0;
   const size_t smem = 2 * (size_t)buf_bytes;
@@ -763,6 +1097,14 @@ int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
     }
     const int n_tiles = a.cfg.num_envs / QT;
     const int mode = g_rows_persist_mode >= 0 ? g_rows_persist_mode : persist;
+    // wide variant (16 warps per tile) for grids of at most RL_ENV_WIDE_MAX CTAs per SM (default below; 0: never);
+    // rl_debug_env_rows(4) forces it, (3) forces the four-warp kernel
+    static int wide_max = -1;
+    if (wide_max < 0) { const char* e = getenv("RL_ENV_WIDE_MAX"); wide_max = e ? atoi(e) : 2; }
+    if (mode == 2 || (mode < 0 && n_tiles <= wide_max * sms)) {
+      const size_t wsmem = (size_t)L.total + (NPART * ND + 3) * ROWB;
+      return fuse ? rows::launch_wide<true>(ra, wsmem, st) : rows::launch_wide<false>(ra, wsmem, st);
+    }
     if (mode == 1) {
       const int buf_bytes = (L.total + 127) & ~127;
       const int grid = n_tiles < 3 * sms ? n_tiles : 3 * sms;

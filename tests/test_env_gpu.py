@@ -355,7 +355,8 @@ def test_host_io_zero_copy_matches_device_step():
 
 
 @pytest.mark.parametrize("case,n,rows_mode", [("mc_flat", 4000, 1), ("go1", 4128, 1), ("mc_flat", 32768, 3), ("mc_flat", 32768, 2),
-                                              ("go1", 4128, 2), ("mc_flat", 96, 2), ("mc_flat", 65536, 2)])
+                                              ("go1", 4128, 2), ("mc_flat", 96, 2), ("mc_flat", 65536, 2),
+                                              ("mc_flat", 4000, 4), ("go1", 4128, 4), ("mc_flat", 32768, 4), ("mc_flat", 4000, 3)])
 def test_rows_kernel_matches_quad_kernel(case, n, rows_mode):
     """The all-TMA kernel (csrc/env_step_rows.cu, packed state blocks) and the one-warp-per-leg kernel it replaces give
     identical bits for every output and every piece of state: fused step and post-physics entry, Philox noise (no
@@ -364,7 +365,8 @@ def test_rows_kernel_matches_quad_kernel(case, n, rows_mode):
     from rapid_locomotion_rl_b200.sim import synthetic_state
     lib = _lib.lib()
     results = []
-    # rows_mode: 1 = automatic, 2 = persistent two-buffer variant (tile queue), 3 = one tile per CTA
+    # rows_mode: 1 = automatic, 2 = persistent two-buffer variant (tile queue), 3 = one tile per CTA (four warps), 4 = the
+    # 16-warp wide variant (what 'automatic' picks for grids of at most two CTAs per SM)
     for mode in (rows_mode, 0):
         prev = lib.rl_debug_env_rows(mode)
         try:
