@@ -996,7 +996,16 @@ static int launch_wide(const RowsArgs& ra, size_t smem, cudaStream_t st) {
     RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     configured = smem;
   }
-  env_step_rows_wide_kernel<FUSE><<<ra.a.cfg.num_envs / QT, WIDE_THREADS, smem, st>>>(ra);
+  static int pdl = -1;          // RL_ENV_PDL=1: programmatic dependent launch (A/B knob, see launch_inst_t)
+  if (pdl < 0) { const char* e = getenv("RL_ENV_PDL"); pdl = (e && atoi(e) == 1) ? 1 : 0; }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(ra.a.cfg.num_envs / QT); lc.blockDim = dim3(WIDE_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&lc, env_step_rows_wide_kernel<FUSE>, ra);
+  RL_REQUIRE(err == cudaSuccess, RL_ERR_CUDA, "env_step_rows_wide_kernel launch: %s", cudaGetErrorString(err));
   return check_launch("env_step_rows_wide_kernel");
 }
 
