@@ -304,6 +304,44 @@ def run_ours(args):
     e2e_value = args.envs * world * k_e2e / e2e_s
     e2e_serial = args.envs * world * k_e2e / e2e_serial_s
     assert float(groups[0].h_out[0].abs().sum()) > 0 and float(groups[1].h_out[0].abs().sum()) > 0
+    # ---- packed variant (LeggedRobot.pack_io): the simulator's rows + actions are views of ONE pinned block, the outputs of
+    # another, so a step is one H2D copy, one launch, one D2H copy; three env groups in flight (PCIe moves one group's
+    # inputs and another's outputs while the third is being submitted) ----
+    e2e_packed = None
+    if len(reps) >= 5:
+        class PackedSide(HostSide):
+            def __init__(self, rep):
+                self.env, actions, st = rep
+                e = self.env
+                e.use_device_step_counter(False)
+                self.d_in_block, self.d_out_block, lay_in, lay_out = e.pack_io()
+                self.h_in_block = torch.empty(self.d_in_block.numel(), dtype=torch.uint8).pin_memory()
+                self.h_out_block = torch.empty(self.d_out_block.numel(), dtype=torch.uint8).pin_memory()
+                hv = e.host_views(self.h_in_block, lay_in)          # what a host-side simulator fills in place
+                hv["root_states"].copy_(torch.from_numpy(st["root_states"]))
+                hv["dof_state"].copy_(torch.from_numpy(st["dof_state"]).view(-1, 2))
+                hv["contact_forces"].copy_(torch.from_numpy(st["contact_forces"]).view(-1, 3))
+                hv["actions"].copy_(actions.cpu())
+                self.h_out = [e.host_views(self.h_out_block, lay_out)["obs"]]
+                self.stream = torch.cuda.Stream()
+                self.done, self.h2d_done = torch.cuda.Event(), torch.cuda.Event()
+                self.pending, self.other = False, None
+
+            def submit(self):
+                with torch.cuda.stream(self.stream):
+                    if self.other is not None and self.other.pending:
+                        self.stream.wait_event(self.other.h2d_done)
+                    self.d_in_block.copy_(self.h_in_block, non_blocking=True)
+                    self.h2d_done.record(self.stream)
+                    self.env.step(self.env.packed_actions)
+                    self.h_out_block.copy_(self.d_out_block, non_blocking=True)
+                    self.done.record(self.stream)
+                self.pending = True
+        pgroups = [PackedSide(reps[i]) for i in (2, 3, 4)]
+        for i, gp in enumerate(pgroups):
+            gp.other = pgroups[i - 1]
+        e2e_packed = args.envs * world * k_e2e / e2e_time(pgroups)
+        assert all(float(gp.h_out[0].abs().sum()) > 0 for gp in pgroups)
     # ---- zero-copy variant: the kernel reads the pinned host rows and writes the pinned host outputs itself
     # (LeggedRobot.bind_host_io / step_host: one launch per step, no staging copies); one group with a sync per
     # step, and two groups on two streams so that one group's PCIe reads overlap the other's writes ----
@@ -446,9 +484,14 @@ def run_ours(args):
                             (n_rep, n_rep * args.envs * bpe / 1e6),
                    "launch": "K steps captured in one CUDA graph, device-side RNG step counter"},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
+        "e2e": {"value": max(e2e_value, e2e_packed or 0.0), "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
                 "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e, "serial_value": e2e_serial, "zero_copy_value": e2e_zero_copy, "zero_copy_two_groups_value": e2e_zero_copy2,
-                "note": "every step: pinned host buffers -> H2D -> LeggedRobot.step -> D2H of obs/priv/rew/reset -> host "
+                "separate_copies_two_groups_value": e2e_value, "packed_three_groups_value": e2e_packed,
+                "note": "value = the better of two ways through the public API, both with HOST buffers and the host waiting for "
+                        "every step's results: (packed_three_groups_value) LeggedRobot.pack_io - the simulator rows + actions are "
+                        "views of ONE pinned block, the outputs of another: one H2D copy, LeggedRobot.step, one D2H copy per step, "
+                        "three env groups in flight; (separate_copies_two_groups_value) four H2D + four D2H copies per step.  "
+                        "every step: pinned host buffers -> H2D -> LeggedRobot.step -> D2H of obs/priv/rew/reset -> host "
                         "wait; two env groups double-buffered on two streams, H2D of one staggered against the D2H of the other "
                         "(serial_value: one group, sync per step; zero_copy_value: LeggedRobot.bind_host_io / step_host - the kernel "
                         "reads the pinned rows and writes the pinned outputs in place, one launch per step, one group; "

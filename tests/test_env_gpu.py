@@ -354,6 +354,56 @@ def test_host_io_zero_copy_matches_device_step():
         assert torch.equal(a, b)
 
 
+def test_packed_io_matches_device_step():
+    """pack_io (simulator rows + actions as views of one device block, outputs of another: one H2D and one D2H copy
+    per step) gives exactly what the step on separately allocated tensors gives."""
+    import numpy as np
+    from cases import build_case
+    from rapid_locomotion_rl_b200.envs import LeggedRobot
+    from rapid_locomotion_rl_b200.sim import synthetic_state
+    n = 4132
+    outs = []
+    for packed in (False, True):
+        cfg, robot, terrain = build_case("mc_flat", n)
+        env = LeggedRobot(cfg, sim_device="cuda:0", headless=True, terrain=terrain, seed=11)
+        p = env.params
+        st = synthetic_state(5, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx, p.term_idx[:p.n_term_bodies])
+        actions = torch.from_numpy(np.random.default_rng(1).normal(0, 1, (n, 12)).astype(np.float32))
+        env.commands[:, :3] = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, (n, 3)).astype(np.float32)).cuda()
+        if not packed:
+            for _ in range(3):                  # the simulator's rows are re-sent every step in both variants
+                env.sim.root_states.copy_(torch.from_numpy(st["root_states"]))
+                env.sim.dof_state.copy_(torch.from_numpy(st["dof_state"]).view(-1, 2))
+                env.sim.contact_forces.copy_(torch.from_numpy(st["contact_forces"]).view(-1, 3))
+                obs, priv, rew, reset, _x = env.step(actions.cuda())
+            torch.cuda.synchronize()
+            outs.append([t.cpu().clone() for t in (obs, priv, rew, reset.to(torch.uint8), env.torques, env.episode_sums["total"])])
+        else:
+            d_in, d_out, lay_in, lay_out = env.pack_io()
+            assert d_in.numel() == n * (13 + 24 + 3 * robot.num_bodies + 12) * 4
+            h_in = torch.empty(d_in.numel(), dtype=torch.uint8).pin_memory()
+            h_out = torch.empty(d_out.numel(), dtype=torch.uint8).pin_memory()
+            hv = LeggedRobot.host_views(h_in, lay_in)
+            hv["root_states"].copy_(torch.from_numpy(st["root_states"]))
+            hv["dof_state"].copy_(torch.from_numpy(st["dof_state"]).view(-1, 2))
+            hv["contact_forces"].copy_(torch.from_numpy(st["contact_forces"]).view(-1, 3))
+            hv["actions"].copy_(actions)
+            for _ in range(3):
+                d_in.copy_(h_in, non_blocking=True)
+                env.step(env.packed_actions)
+                h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            ho = LeggedRobot.host_views(h_out, lay_out)
+            outs.append([ho["obs"].clone(), ho["priv"].clone(), ho["rew"].clone(), ho["reset"].clone(),
+                         env.torques.cpu(), env.episode_sums["total"].cpu()])
+            cfg2, _r2, terrain2 = build_case("mc_flat", 50)
+            env2 = LeggedRobot(cfg2, sim_device="cuda:0", headless=True, terrain=terrain2, seed=1)
+            with pytest.raises(ValueError):
+                env2.pack_io()                  # sections would not be 16-byte aligned
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("case,n,rows_mode", [("mc_flat", 4000, 1), ("go1", 4128, 1), ("mc_flat", 32768, 3), ("mc_flat", 32768, 2),
                                               ("go1", 4128, 2), ("mc_flat", 96, 2), ("mc_flat", 65536, 2),
                                               ("mc_flat", 4000, 4), ("go1", 4128, 4), ("mc_flat", 32768, 4), ("mc_flat", 4000, 3)])
