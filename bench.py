@@ -109,6 +109,42 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pins this process to the CPU cores NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated, so
+    that the staging buffers of the e2e section are first touched (and therefore placed) on the GPU's own NUMA node: with
+    eight ranks on the default policy every rank's pinned pages can end up on one node and all host<->device traffic
+    shares that node's memory controllers and the inter-socket link.  RL_BENCH_NUMA=0 switches it off.  Returns a
+    description for the JSON line."""
+    if os.environ.get("RL_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(local_rank))
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        if not use or len(use) == len(allowed):
+            return "no-op (%d GPU-local cores of %d allowed)" % (len(use), len(allowed))
+        global _ORIG_AFFINITY
+        _ORIG_AFFINITY = allowed
+        os.sched_setaffinity(0, use)
+        return "bound to %d GPU-local cores (%d..%d) of %d" % (len(use), use[0], use[-1], len(allowed))
+    except Exception as e:      # no NVML / no permission: the default placement stands
+        return "unavailable (%s)" % type(e).__name__
+
+
+_ORIG_AFFINITY = None
+
+
+def restore_affinity():
+    """The reference / CPU-baseline legs (own processes, inheriting this one's mask) get every host core back."""
+    if _ORIG_AFFINITY is not None:
+        os.sched_setaffinity(0, _ORIG_AFFINITY)
+
+
 def build_replicas(case, envs, n_rep, device, seed0=0):
     """n_rep independent env instances with synthetic simulator state."""
     import numpy as np
@@ -180,6 +216,7 @@ def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     device = "cuda:%d" % local
     if world > 1:
@@ -387,6 +424,7 @@ def run_ours(args):
         e2e_zero_copy = "failed: %s" % str(exc)[:160]
     env = None
     del groups
+    restore_affinity()
 
     # ---- other sizes (rank 0 only, N=1): the 4000-env configs[1] point and an HBM-resident one -----
     also = {}
@@ -484,7 +522,7 @@ def run_ours(args):
                             (n_rep, n_rep * args.envs * bpe / 1e6),
                    "launch": "K steps captured in one CUDA graph, device-side RNG step counter"},
         "clocks": sampler.summary(),
-        "e2e": {"value": max(e2e_value, e2e_packed or 0.0), "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
+        "e2e": {"host_numa": numa, "value": max(e2e_value, e2e_packed or 0.0), "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
                 "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e, "serial_value": e2e_serial, "zero_copy_value": e2e_zero_copy, "zero_copy_two_groups_value": e2e_zero_copy2,
                 "separate_copies_two_groups_value": e2e_value, "packed_three_groups_value": e2e_packed,
                 "note": "value = the better of two ways through the public API, both with HOST buffers and the host waiting for "

@@ -567,6 +567,27 @@ int rl_chain_run(void* handle, int32_t rows, void* stream);
  * chunks of a batch through dependent passes on different streams */
 int rl_chain_run_tiles(void* handle, int32_t rows, int32_t tile_begin, int32_t tile_end, void* stream);
 int rl_chain_destroy(void* handle);
+/* PPO loss fused into a teacher-forward chain (ppo.py:110-144): the epilogue thread that writes row r of the critic output
+ * (outputs[value_out]; the same thread wrote row r of outputs[mean_out] earlier in its op list - rl_chain_set_ppo_loss
+ * checks that) evaluates the row's clipped surrogate / clipped value loss / KL and writes the gradients w.r.t. the network
+ * outputs exactly as rl_ppo_loss does: dmean [rows,16] and dvalue [rows,8] bf16, dstd[12] / stats[0..2] / kl_slot
+ * accumulated atomically (one set of atomics per warp).  Removes the loss launch between the forward and the backward chain
+ * of an update.  Row indices are those of the whole batch (pointers are NOT offset by the first tile of a
+ * rl_chain_run_tiles call).  loss_host = NULL switches it off; the setting applies to the launches that follow. */
+typedef struct RlChainPpoLoss {
+  const float* Lrow;                /* [rows, 40] per-row loss inputs (rl_ppo_gather) */
+  const float* std;                 /* [12] */
+  void* dmean;                      /* bf16 [rows, 16] */
+  void* dvalue;                     /* bf16 [rows, 8] */
+  float* dstd;                      /* [12] */
+  double* stats;                    /* [4] */
+  float* kl_slot;                   /* or NULL */
+  float clip, value_coef, entropy_coef, inv_global_B;
+  int32_t use_clipped_value;
+  int32_t mean_out, value_out;      /* indices into the chain's outputs[] */
+  int32_t pad;
+} RlChainPpoLoss;
+int rl_chain_set_ppo_loss(void* handle, const RlChainPpoLoss* loss_host);
 /* Profiling aid: record per-op clock64 stamps of CTA 0 during its tile iteration `tile_iteration` (< 0: off):
  * 1 stamp per LOAD op, 2 per MMA op (waits passed, commits issued), 5 per EPI op (start, accumulator ready,
  * registers loaded, elementwise done, end), in that order.  rl_chain_read_trace copies them to the host

@@ -82,6 +82,7 @@ RlChainLoadOp = STRUCTS["RlChainLoadOp"]
 RlChainMmaOp = STRUCTS["RlChainMmaOp"]
 RlChainEpiOp = STRUCTS["RlChainEpiOp"]
 RlChainDesc = STRUCTS["RlChainDesc"]
+RlChainPpoLoss = STRUCTS["RlChainPpoLoss"]
 RlRolloutBoundary = STRUCTS["RlRolloutBoundary"]
 RlRolloutAct = STRUCTS["RlRolloutAct"]
 
@@ -131,6 +132,7 @@ SIGNATURES = {
     "rl_chain_run": (C.c_int, [_P, C.c_int32, _P]),
     "rl_chain_run_tiles": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rl_chain_destroy": (C.c_int, [_P]),
+    "rl_chain_set_ppo_loss": (C.c_int, [_P, _P]),
     "rl_chain_trace": (C.c_int, [_P, C.c_int32]),
     "rl_chain_read_trace": (C.c_int64, [_P, _P, C.c_int64]),
     "rl_adam_shadows": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,

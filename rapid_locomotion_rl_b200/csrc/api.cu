@@ -46,6 +46,7 @@ extern "C" int64_t rl_sizeof(const char* name) {
   if (!strcmp(name, "RlChainMmaOp")) return sizeof(RlChainMmaOp);
   if (!strcmp(name, "RlChainEpiOp")) return sizeof(RlChainEpiOp);
   if (!strcmp(name, "RlChainDesc")) return sizeof(RlChainDesc);
+  if (!strcmp(name, "RlChainPpoLoss")) return sizeof(RlChainPpoLoss);
   if (!strcmp(name, "RlRolloutBoundary")) return sizeof(RlRolloutBoundary);
   if (!strcmp(name, "RlRolloutAct")) return sizeof(RlRolloutAct);
   return -1;

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "tc_common.cuh"
+#include "ppo_loss.cuh"
 
 namespace rl {
 namespace tc {
@@ -88,6 +89,9 @@ struct ChainParams {
   unsigned long long* trace;      // profiling aid: clock64 stamps of CTA 0 in tile iteration trace_it (or null)
   int trace_it;
   uint8_t barrier_count[RL_CHAIN_MAX_BARRIERS];
+  // PPO loss fused into the value-output epilogue (rl_chain_set_ppo_loss): loss.mean = outputs[mean_out]
+  LossArgs loss;
+  int loss_value_out;             // outputs[] index whose epilogue op evaluates the loss, or -1
 };
 
 // mbarrier wait with a watchdog: a schedule bug must surface as a launch error, never as a hung GPU
@@ -214,6 +218,39 @@ __device__ __forceinline__ void worker_arrive(uint64_t* bars, uint32_t* tickets,
   uint32_t old;
   asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(tickets + bar_id)) : "memory");
   if ((old & 3u) == 3u) mbar_arrive(&bars[bar_id]);
+}
+
+// PPO loss of row r (ppo.py:110-144) by the epilogue thread that has just written value[r] (= v) and, earlier in its op
+// list, mean[r]: dmean / dvalue rows, then one set of atomics per warp for the loss statistics and d loss / d std.
+// Called by whole warps.  (Not inlined: the epilogue's 64 accumulator registers are not live across it.)
+__device__ __noinline__ void chain_ppo_loss(const LossArgs& a, int r, int rows, float v) {
+  double s_surr = 0, s_val = 0, s_kl = 0;
+  float g_std[ACT];
+#pragma unroll
+  for (int d = 0; d < ACT; ++d) g_std[d] = 0.f;
+  const bool valid = r < rows;
+  if (valid) ppo_loss_row(a, r, v, s_surr, s_val, s_kl, g_std);
+  const int lane = threadIdx.x & 31;
+  const int n_valid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+  if (n_valid == 0) return;
+  s_surr = warp_sum(s_surr); s_val = warp_sum(s_val); s_kl = warp_sum(s_kl);
+  float mine = 0.f;
+#pragma unroll
+  for (int d = 0; d < ACT; ++d) {
+    const float t = warp_sum(g_std[d]);
+    if (lane == d) mine = t;
+  }
+  if (lane == 0) {
+    atomicAdd(a.stats + 0, s_surr);
+    atomicAdd(a.stats + 1, s_val);
+    atomicAdd(a.stats + 2, s_kl);
+    if (a.kl_slot) atomicAdd(a.kl_slot, (float)s_kl);
+  }
+  if (lane < ACT) {
+    // entropy (:144): mean over rows of sum_d (0.5 + 0.5 log 2pi + log std_d)  =>  d/dstd_d = 1/std_d per row
+    mine += -a.entropy_coef * (1.f / a.std[lane]) * (a.inv_global_B * (float)n_valid);
+    atomicAdd(a.dstd + lane, mine);
+  }
 }
 
 template <bool TRACE, int NW>
@@ -585,6 +622,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = f[j];
           }
+          if ((int)out_id == p.loss_value_out) chain_ppo_loss(p.loss, r, p.rows, f[0]);
           if (tr) tp[3] = tp[4] = clock64();
           continue;
         }
@@ -661,6 +699,7 @@ mlp_chain_kernel(const __grid_constant__ ChainParams p) {
 struct ChainHandle {
   ChainParams params;
   int n_workers;
+  int out_worker[RL_CHAIN_MAX_OUTPUTS], out_pos[RL_CHAIN_MAX_OUTPUTS], out_ld[RL_CHAIN_MAX_OUTPUTS];   // the epilogue op writing outputs[i]: worker, index in the host list (-1: none)
   void* dev_ops;
   size_t smem_bytes;
   unsigned long long* trace;
@@ -795,6 +834,12 @@ extern "C" int rl_chain_create(const RlChainDesc* d, void** handle) {
   h->params.epis[0] = reinterpret_cast<const RlChainEpiOp*>(base);
   for (int k = 1; k < MAX_WORKERS; ++k) h->params.epis[k] = h->params.epis[k - 1] + n_epi_w[k - 1];
   h->n_workers = n_workers;
+  h->params.loss_value_out = -1;
+  for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->out_worker[i] = h->out_pos[i] = -1;
+  for (int i = 0; i < d->n_epis; ++i) {
+    const RlChainEpiOp& o = d->epis_host[i];
+    if (o.mode == RL_CHAIN_EPI_BIAS_F32) { h->out_worker[o.out_id] = o.worker; h->out_pos[o.out_id] = i; h->out_ld[o.out_id] = o.out_ld; }
+  }
   h->params.params = d->params;
   for (int i = 0; i < RL_CHAIN_MAX_OUTPUTS; ++i) h->params.outputs[i] = d->outputs[i];
   h->params.n_loads = d->n_loads; h->params.n_mmas = d->n_mmas;
@@ -901,6 +946,32 @@ static int chain_launch(void* handle, int32_t rows, int32_t tile_begin, int32_t 
   else RL_CHAIN_LAUNCH(4);
 #undef RL_CHAIN_LAUNCH
   return check_launch("mlp_chain_kernel");
+}
+
+extern "C" int rl_chain_set_ppo_loss(void* handle, const RlChainPpoLoss* L) {
+  RL_REQUIRE(handle, RL_ERR_BAD_ARG, "rl_chain_set_ppo_loss: null handle");
+  ChainHandle* h = reinterpret_cast<ChainHandle*>(handle);
+  if (!L) { h->params.loss_value_out = -1; return RL_OK; }
+  RL_REQUIRE(L->Lrow && L->std && L->dmean && L->dvalue && L->dstd && L->stats && L->inv_global_B > 0.f, RL_ERR_BAD_ARG,
+             "rl_chain_set_ppo_loss: null pointer / inv_global_B");
+  RL_REQUIRE(L->mean_out >= 0 && L->mean_out < RL_CHAIN_MAX_OUTPUTS && L->value_out >= 0 && L->value_out < RL_CHAIN_MAX_OUTPUTS &&
+             L->mean_out != L->value_out && h->out_pos[L->mean_out] >= 0 && h->out_pos[L->value_out] >= 0, RL_ERR_BAD_ARG,
+             "rl_chain_set_ppo_loss: outputs %d / %d are not written by this chain", L->mean_out, L->value_out);
+  // the thread that evaluates row r reads mean[r] back: it must be the thread that wrote it, earlier in program order
+  RL_REQUIRE(h->n_workers <= 3 && h->out_worker[L->mean_out] == h->out_worker[L->value_out] && h->out_pos[L->mean_out] < h->out_pos[L->value_out],
+             RL_ERR_BAD_ARG, "rl_chain_set_ppo_loss: the mean rows must be written by the value op's epilogue worker, before it "
+             "(workers %d / %d, ops %d / %d, %d workers)", h->out_worker[L->mean_out], h->out_worker[L->value_out],
+             h->out_pos[L->mean_out], h->out_pos[L->value_out], h->n_workers);
+  RL_REQUIRE(h->out_ld[L->mean_out] == ACT, RL_ERR_BAD_ARG, "rl_chain_set_ppo_loss: mean rows have pitch %d, the loss reads pitch %d",
+             h->out_ld[L->mean_out], ACT);
+  LossArgs& a = h->params.loss;
+  memset(&a, 0, sizeof(a));
+  a.mean = h->params.outputs[L->mean_out]; a.value = h->params.outputs[L->value_out];
+  a.Lrow = L->Lrow; a.std = L->std; a.clip = L->clip; a.value_coef = L->value_coef; a.entropy_coef = L->entropy_coef;
+  a.use_clipped_value = L->use_clipped_value; a.inv_global_B = L->inv_global_B;
+  a.dmean = (__nv_bfloat16*)L->dmean; a.dvalue = (__nv_bfloat16*)L->dvalue; a.dstd = L->dstd; a.stats = L->stats; a.kl_slot = L->kl_slot;
+  h->params.loss_value_out = L->value_out;
+  return RL_OK;
 }
 
 extern "C" int rl_chain_destroy(void* handle) {

@@ -416,12 +416,18 @@ class ActorCritic(nn.Module):
         self._fwd(e[1], w["H1"], 0, w["H1"].shape[1], w["H2"], 0, w["H2"].shape[1], rows, EPI_BIAS_ELU_BF16)
         self._fwd(e[2], w["H2"], 0, w["H2"].shape[1], w["Xac"], self.num_obs, w["Xac"].shape[1], rows, EPI_BIAS_BF16)
 
-    def forward_teacher(self, rows, want_value=True, want_mean=True, save=False, tiles=None):
-        """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace (tiles: only these 128-row tiles)."""
+    def forward_teacher(self, rows, want_value=True, want_mean=True, save=False, tiles=None, loss=None):
+        """encoder -> [actor | critic] on the staged inputs Xp / Xac of the workspace (tiles: only these 128-row tiles).
+        loss (chain path, save=True): an `_lib.RlChainPpoLoss` - the critic's output epilogue also evaluates the PPO loss of its
+        rows (dmean / dvalue / dstd / statistics as rl_ppo_loss writes them), so no loss launch follows."""
         if self.use_chain:
             from . import chain
             prog = lambda wm, wv: self._chain(("teacher", save, wm, wv), lambda T: chain.teacher_forward(
                 T, save=save, want_mean=wm, want_value=wv))
+            if loss is not None or (save and want_mean and want_value):
+                # (the setting is part of the launch parameters: always (re)stated for the program the update uses)
+                assert loss is None or (save and want_mean and want_value)
+                prog(True, True).set_ppo_loss(loss)
             if tiles is not None:
                 prog(want_mean, want_value).run(rows, tiles=tiles)
                 return

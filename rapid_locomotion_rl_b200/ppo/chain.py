@@ -481,6 +481,12 @@ class ChainProgram:
         else:
             _lib.check(self._libref.rl_chain_run_tiles(self._handle, int(rows), int(tiles[0]), int(tiles[1]), st))
 
+    def set_ppo_loss(self, loss):
+        """loss: an `_lib.RlChainPpoLoss` (the value-output epilogue of the launches that follow also evaluates the PPO
+        loss of its rows: include/rl_b200.h) or None (off)."""
+        self._loss_ref = loss
+        _lib.check(self._libref.rl_chain_set_ppo_loss(self._handle, None if loss is None else C.byref(loss)))
+
     def trace(self, tile_iteration):
         _lib.check(self._libref.rl_chain_trace(self._handle, int(tile_iteration)))
 

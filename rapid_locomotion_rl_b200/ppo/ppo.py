@@ -274,15 +274,31 @@ class PPO:
         H = AC_Args.actor_hidden_dims[0]
         a, c, e = ac.L_act, ac.L_cri, ac.L_enc
 
+        # RL_PPO_FUSED_LOSS=1: the loss rides in the forward chain's last epilogue op (rl_chain_set_ppo_loss) - one launch
+        # and one kernel boundary less between the forward and the backward of a chunk.  Bit-identical output gradients
+        # (tests/test_ppo_gpu.py::test_fused_loss_equals_loss_kernel), but measured SLOWER inside the update's graph (4000
+        # envs: 7.53 - 7.57 vs 7.34 ms per update, A/B in one gpurun call, profiles/jobs/r2_job54.sh): the loss launch was a
+        # scheduling point at which the ragged chunk's forward got its SMs; without it the first chunk's backward takes
+        # every SM the moment its forward ends and the ragged chunk finishes ~25 us later (profiles/r02_ppo_timeline_fused.txt).
+        # Kept as an opt-in.
+        fused_loss = None
+        if ac.use_chain and os.environ.get("RL_PPO_FUSED_LOSS", "0") == "1" and ac.activation == "elu":
+            fl = fused_loss = _lib.RlChainPpoLoss()
+            fl.Lrow, fl.std, fl.dmean, fl.dvalue = P(w["Lrow"]), P(ac.std.data), P(w["dmean"]), P(w["dvalue"])
+            fl.dstd, fl.stats, fl.kl_slot = P(ac.std_grad), P(self._stats), P(kl_slot)
+            fl.clip, fl.value_coef, fl.entropy_coef, fl.inv_global_B = A.clip_param, A.value_loss_coef, A.entropy_coef, inv_gb
+            fl.use_clipped_value, fl.mean_out, fl.value_out = int(A.use_clipped_value_loss), 0, 1
+
         def passes(t0, t1):
             r0, r1 = 128 * t0, min(B, 128 * t1)
-            ac.forward_teacher(B, save=True, tiles=(t0, t1))
+            ac.forward_teacher(B, save=True, tiles=(t0, t1), loss=fused_loss)
             # (the statistics are zeroed by the previous call's finalize kernel)
-            _lib.check(self._lib.rl_ppo_loss(
-                P(w["mean"][r0:]), P(w["value"][r0:]), None, P(w["Xac"][r0:]), ld("Xac"), ac.num_obs, P(w["Lrow"][r0:]),
-                P(ac.std.data), r1 - r0, A.clip_param, A.value_loss_coef, A.entropy_coef, int(A.use_clipped_value_loss),
-                inv_gb, P(w["dmean"][r0:]), P(w["dvalue"][r0:]), P(w["dpred"][r0:]), P(ac.std_grad), P(self._stats),
-                P(kl_slot), _lib.current_stream()))
+            if fused_loss is None:
+                _lib.check(self._lib.rl_ppo_loss(
+                    P(w["mean"][r0:]), P(w["value"][r0:]), None, P(w["Xac"][r0:]), ld("Xac"), ac.num_obs, P(w["Lrow"][r0:]),
+                    P(ac.std.data), r1 - r0, A.clip_param, A.value_loss_coef, A.entropy_coef, int(A.use_clipped_value_loss),
+                    inv_gb, P(w["dmean"][r0:]), P(w["dvalue"][r0:]), P(w["dpred"][r0:]), P(ac.std_grad), P(self._stats),
+                    P(kl_slot), _lib.current_stream()))
             # dgrad of actor + critic + encoder in ONE persistent kernel (csrc/chain.cu)
             ac._chain(("trunk_backward",), chain.trunk_backward).run(B, tiles=(t0, t1))
         chunks = self._chunks(B) if ac.use_chain else None

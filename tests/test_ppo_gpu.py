@@ -321,6 +321,39 @@ def test_forward_and_loss_vs_oracle_at_c5_size(learner_path):
     assert torch.isfinite(ppo.debug_grad).all() and float(ppo.debug_grad.abs().max()) > 0
 
 
+@pytest.mark.parametrize("rows", [24000, 333])
+def test_fused_loss_equals_loss_kernel(rows, monkeypatch):
+    """rl_chain_set_ppo_loss (the PPO loss evaluated by the forward chain's value-output epilogue) writes the bit-identical
+    dmean / dvalue rows the stand-alone rl_ppo_loss launch writes (same per-row code on the same mean / value rows), and
+    the atomically accumulated statistics / std gradient / parameter gradients agree to summation order."""
+    from rapid_locomotion_rl_b200.ppo import PPO
+    n_envs, T = 1000, 24
+    storage = _synthetic_rollout(n_envs, T, 21)
+    idx = torch.randperm(n_envs * T, generator=torch.Generator().manual_seed(5))[:rows]
+    got = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("RL_PPO_FUSED_LOSS", fused)
+        ac, sd = make_ac()
+        if not ac.use_chain:
+            pytest.skip("the fused loss lives in the chain kernels")
+        ppo = PPO(ac, device=DEV)
+        ppo.init_storage(n_envs, T, [42], [18], [630], [12])
+        _load_storage(ppo, storage, n_envs, T)
+        ppo.debug_keep_grad = True
+        ppo.minibatch_step(idx.to(DEV))
+        torch.cuda.synchronize()
+        w = ac._ws
+        got[fused] = dict(dmean=w["dmean"][:rows].float().cpu(), dvalue=w["dvalue"][:rows].float().cpu(),
+                          stats=ppo.debug_stats.cpu().clone(), grad=ppo.debug_grad.cpu().clone(),
+                          mean=w["mean"][:rows].cpu().clone(), value=w["value"][:rows].cpu().clone())
+    a, b = got["0"], got["1"]
+    assert torch.equal(a["mean"], b["mean"]) and torch.equal(a["value"], b["value"])
+    assert torch.equal(a["dmean"], b["dmean"]) and torch.equal(a["dvalue"], b["dvalue"])
+    assert float(a["dmean"].abs().max()) > 0 and float(a["dvalue"].abs().max()) > 0
+    torch.testing.assert_close(a["stats"], b["stats"], rtol=1e-9, atol=1e-9)
+    torch.testing.assert_close(a["grad"], b["grad"], rtol=1e-3, atol=1e-5)
+
+
 def test_adam_shadows_equals_adam_then_refresh():
     """rl_adam_shadows (Adam + bf16 operand refresh in one launch) leaves exactly what rl_adam followed by
     rl_refresh_shadows leaves: parameters, moments, zeroed gradient, both bf16 operands of every layer (bit for bit) -
