@@ -7,6 +7,7 @@
 // The reference synchronises the host >= 5 times per minibatch (kl_mean compare :118-121, .item()
 // :152-153,170, slot_cache :161-162); here nothing leaves the device until update() returns.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "rl_common.cuh"
 #include "ppo_loss.cuh"
@@ -41,7 +42,7 @@ __device__ __forceinline__ void gather_history_row(const float* __restrict__ hs,
 }
 
 // ---- minibatch gather (rollout_storage.py:121-137) + bf16 staging -----------------------------------
-// one warp per minibatch row; every global access is a coalesced run along the row
+// one warp per minibatch row; every global access is a coalesced run along the row (any dimensions)
 __global__ void __launch_bounds__(256)
 ppo_gather_kernel(const float* __restrict__ obs, const float* __restrict__ priv, const float* __restrict__ hist,
                   const float* __restrict__ actions, const float* __restrict__ values, const float* __restrict__ returns,
@@ -66,6 +67,60 @@ ppo_gather_kernel(const float* __restrict__ obs, const float* __restrict__ priv,
     L[2 * ACT + lane] = sigma[src * ACT + lane];
   }
   if (lane == 0) { L[36] = logp[src]; L[37] = adv[src]; L[38] = returns[src]; L[39] = values[src]; }
+}
+
+// The same rows for the learner's usual shapes (priv_dim <= ldp <= 32, obs_dim <= ldac <= 64, no history in this launch):
+// GR rows per warp.  With one row per warp the kernel is a chain of two dependent latencies (the row index, then ~10
+// small loads) and ran at ~1/4 of the HBM rate; here the warp fetches its GR indices with one load, issues the loads of
+// all GR rows (7 per lane and row, the four per-row scalars on lanes 12 - 15) before the first store, and only then
+// converts and stores - the same values to the same places.
+constexpr int GATHER_ROWS = 4;
+__global__ void __launch_bounds__(256)
+ppo_gather_rows_kernel(const float* __restrict__ obs, const float* __restrict__ priv, const float* __restrict__ actions,
+                       const float* __restrict__ values, const float* __restrict__ returns, const float* __restrict__ logp,
+                       const float* __restrict__ adv, const float* __restrict__ mu, const float* __restrict__ sigma,
+                       const int64_t* __restrict__ idx, int B, int obs_dim, int priv_dim, __nv_bfloat16* __restrict__ Xp, int ldp,
+                       __nv_bfloat16* __restrict__ Xac, int ldac, float* __restrict__ Lrow) {
+  constexpr int GR = GATHER_ROWS;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row0 = warp * GR;
+  if (row0 >= B) return;
+  long long mine = 0;
+  if (lane < GR && row0 + lane < B) mine = idx[row0 + lane];
+  float vp[GR], vo0[GR], vo1[GR], va[GR], vm[GR], vs[GR];
+  const float* const scalar_src = lane == 12 ? logp : (lane == 13 ? adv : (lane == 14 ? returns : values));
+#pragma unroll
+  for (int r = 0; r < GR; ++r) {
+    const size_t src = (size_t)__shfl_sync(0xFFFFFFFFu, mine, r);
+    vp[r] = vo0[r] = vo1[r] = va[r] = vm[r] = vs[r] = 0.f;
+    if (row0 + r < B) {
+      if (lane < priv_dim) vp[r] = priv[src * priv_dim + lane];
+      if (lane < obs_dim) vo0[r] = obs[src * obs_dim + lane];
+      if (lane + 32 < obs_dim) vo1[r] = obs[src * obs_dim + 32 + lane];
+      if (lane < ACT) {
+        va[r] = actions[src * ACT + lane];
+        vm[r] = mu[src * ACT + lane];
+        vs[r] = sigma[src * ACT + lane];
+      } else if (lane < 16) {
+        va[r] = scalar_src[src];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < GR; ++r) {
+    const int row = row0 + r;
+    if (row >= B) break;
+    if (lane < ldp) Xp[(size_t)row * ldp + lane] = __float2bfloat16(vp[r]);            // (zero beyond priv_dim)
+    __nv_bfloat16* xa = Xac + (size_t)row * ldac;
+    if (lane < obs_dim) xa[lane] = __float2bfloat16(vo0[r]);
+    else if (lane >= obs_dim + LAT && lane < ldac) xa[lane] = __float2bfloat16(0.f);
+    const int c1 = lane + 32;
+    if (c1 < obs_dim) xa[c1] = __float2bfloat16(vo1[r]);
+    else if (c1 >= obs_dim + LAT && c1 < ldac) xa[c1] = __float2bfloat16(0.f);         // [obs_dim, obs_dim+18) is the latent slot
+    float* L = Lrow + (size_t)row * LROW;
+    if (lane < ACT) { L[lane] = va[r]; L[ACT + lane] = vm[r]; L[2 * ACT + lane] = vs[r]; }
+    else if (lane < 16) L[36 + lane - 12] = va[r];                                     // logp, adv, returns, values
+  }
 }
 
 // obs_history_batch alone (rollout_storage.py:124): the adaptation module's input, gathered on its own stream
@@ -411,6 +466,14 @@ extern "C" int rl_ppo_gather(const float* obs, const float* priv, const float* h
              RL_ERR_BAD_ARG, "rl_ppo_gather: null pointer");
   RL_REQUIRE(B > 0 && priv_dim <= ldp && obs_dim + LAT <= ldac && (!Xh || (hist && hist_dim <= ldh)), RL_ERR_BAD_ARG,
              "rl_ppo_gather: bad dimensions");
+  static const bool rows_off = [] { const char* e = getenv("RL_PPO_GATHER_ROWS"); return e && e[0] == '0'; }();
+  if (!Xh && !rows_off && priv_dim <= 32 && ldp <= 32 && obs_dim <= 64 && ldac <= 64) {
+    const int warps = (B + GATHER_ROWS - 1) / GATHER_ROWS;
+    ppo_gather_rows_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        obs, priv, actions, values, returns, logp, adv, mu, sigma, idx, B, obs_dim, priv_dim, (__nv_bfloat16*)Xp, ldp,
+        (__nv_bfloat16*)Xac, ldac, Lrow);
+    return check_launch("ppo_gather_rows_kernel");
+  }
   const int blocks = (B * 32 + 255) / 256;
   ppo_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       obs, priv, hist, actions, values, returns, logp, adv, mu, sigma, idx, B, obs_dim, priv_dim, hist_dim,

@@ -209,6 +209,36 @@ def test_gather_history_matches_indexing():
     assert lib.rl_ppo_gather_history(None, idx.data_ptr(), B, dim, out.data_ptr(), ld, _lib.current_stream()) != 0
 
 
+@pytest.mark.parametrize("obs_dim,priv_dim,ldp,ldac,B", [(42, 18, 32, 64, 24000), (42, 18, 32, 64, 333), (42, 18, 32, 64, 5),
+                                                       (30, 18, 32, 48, 1001), (70, 40, 64, 96, 777)])
+def test_gather_policy_rows_matches_indexing(obs_dim, priv_dim, ldp, ldac, B):
+    """rl_ppo_gather == the twelve `tensor[batch_idx]` gathers of rollout_storage.py:121-137 staged as the learner reads
+    them: Xp / Xac rounded to bf16 with zero padding (the latent slot [obs_dim, obs_dim + 18) untouched), the per-row loss
+    inputs in Lrow; the learner's shapes take the four-rows-per-warp kernel, larger ones the one-row-per-warp kernel."""
+    from rapid_locomotion_rl_b200 import _lib
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(B)
+    rows = 4000
+    r = lambda *sh: torch.randn(*sh, generator=g).to(DEV)
+    obs, priv, act, mu, sig = r(rows, obs_dim), r(rows, priv_dim), r(rows, 12), r(rows, 12), r(rows, 12)
+    val, ret, logp, adv = r(rows, 1), r(rows, 1), r(rows, 1), r(rows, 1)
+    idx = torch.randint(0, rows, (B,), generator=g).to(DEV)
+    Xp = torch.full((B, ldp), 7.0, dtype=torch.bfloat16, device=DEV)
+    Xac = torch.full((B, ldac), 7.0, dtype=torch.bfloat16, device=DEV)
+    L = torch.full((B, 40), 7.0, device=DEV)
+    P = lambda t: t.data_ptr()
+    _lib.check(lib.rl_ppo_gather(P(obs), P(priv), None, P(act), P(val), P(ret), P(logp), P(adv), P(mu), P(sig), P(idx), B, obs_dim,
+                                 priv_dim, 0, P(Xp), ldp, P(Xac), ldac, None, 0, P(L), _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(Xp[:, :priv_dim], priv[idx].to(torch.bfloat16)) and float(Xp[:, priv_dim:].float().abs().max()) == 0.0
+    assert torch.equal(Xac[:, :obs_dim], obs[idx].to(torch.bfloat16))
+    assert torch.all(Xac[:, obs_dim:obs_dim + 18].float() == 7.0)            # the latent slot belongs to the encoder
+    if ldac > obs_dim + 18:
+        assert float(Xac[:, obs_dim + 18:].float().abs().max()) == 0.0
+    want = torch.cat([act[idx], mu[idx], sig[idx], logp[idx], adv[idx], ret[idx], val[idx]], 1)
+    assert torch.equal(L, want)
+
+
 def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeypatch):
     """PPO.update with the adaptation module one minibatch behind on the side branch (two captured graphs + flush,
     ONE gradient reduction point per minibatch) must produce the serial schedule's parameters and statistics: the
