@@ -6,7 +6,9 @@ import sys, math, torch
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import bench
 envs = int(sys.argv[1]); steps = 500
-reps = bench.build_replicas("mc_flat", envs, max(2, math.ceil(2.0 * bench.L2_BYTES / (envs * 1425))), "cuda:0")
+import os
+case = os.environ.get("CASE", "mc_flat")
+reps = bench.build_replicas(case, envs, max(2, math.ceil(2.0 * bench.L2_BYTES / (envs * bench.BYTES_PER_ENV_STEP[case]))), "cuda:0")
 g = bench.time_env_steps(reps, steps, 5)
 best = 1e9
 for _ in range(5):
@@ -20,4 +22,4 @@ for cfg in sys.argv[2:]:
     if cfg != "default":
         env["RL_ENV_STAGGER"] = cfg
     r = subprocess.run([sys.executable, "-c", code, envs], env=env, capture_output=True, text=True)
-    print("envs %s stagger %-16s %s us/launch" % (envs, cfg, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]))
+    print("%s envs %s stagger %-16s %s us/launch" % (os.environ.get("CASE", "mc_flat"), envs, cfg, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]))

@@ -1146,8 +1146,12 @@ int launch_step_rows(const StepArgs& a, bool fuse, cudaStream_t st) {
     else if (n_tiles > 2 * sms && n_tiles <= (seven ? 7 : 6) * sms) {
       // (re-tuned after the compute phase got shorter: with more than four CTAs per SM the first group is three CTA rows and
       // the delay 1.1 us - 32768 envs: 11.13 -> 10.79 us per launch; sweep in profiles/r02_env_step.md)
+      // (last sweep of round 2, profiles/jobs/r2_job60.sh / r2_job61.sh: with more than six CTAs per SM a first group of
+      // 3.25 - 4 CTA rows is a plateau - 32768 envs 10.18 -> 9.98 us per launch with 3.5 rows; Go1 and 24576 envs unchanged)
       const bool deep = n_tiles > 4 * sms;
-      ra.h.stagger_ns = deep ? 1100 : 1000; ra.h.stagger_from = (deep ? 3 : 2) * sms; ra.h.stagger_group = 2 * sms;
+      ra.h.stagger_ns = deep ? 1100 : 1000;
+      ra.h.stagger_from = n_tiles > 6 * sms ? (7 * sms) / 2 : (deep ? 3 : 2) * sms;
+      ra.h.stagger_group = 2 * sms;
     }
   }
   if (seven) return fuse ? launch_inst<true, 7>(ra, smem, st) : launch_inst<false, 7>(ra, smem, st);
