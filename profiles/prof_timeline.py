@@ -39,7 +39,7 @@ ev.sort(key=lambda e: e["ts"])
 t0 = ev[0]["ts"]
 print("kernels in the update: %d, span %.1f us" % (len(ev), ev[-1]["ts"] + ev[-1]["dur"] - t0))
 # the gather kernel opens a minibatch step on the main path: print steps 8 and 9
-starts = [i for i, e in enumerate(ev) if "ppo_gather_kernel" in e["name"] and "history" not in e["name"]]
+starts = [i for i, e in enumerate(ev) if "ppo_gather" in e["name"] and "history" not in e["name"]]
 print("minibatch steps found:", len(starts))
 a, b = starts[8], starts[10]
 base = ev[a]["ts"]

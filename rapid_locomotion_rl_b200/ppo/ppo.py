@@ -241,11 +241,23 @@ class PPO:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
                 self._ev_fork, self._ev_join, self._ev_grads, self._ev_loss = (torch.cuda.Event() for _ in range(4))
+            # The adaptation FORWARD of minibatch i runs at the END of call i's side branch (behind the history gather that
+            # produces its input and the module's own optimiser step of minibatch i-1), not at the start of call i+1's: there
+            # it overlaps the main path's finalize / Adam / encoder-refresh tail, during which the side branch used to idle,
+            # instead of holding every SM (a 148-CTA chain launch) when the next call's policy forward wants them.  Only where
+            # the module's optimiser step is on the side branch too (one GPU, or the side communicator), and only for batches of
+            # several waves of row tiles: A/B in one gpurun call (profiles/jobs/r2_job63.sh) 32768 envs (1536 tiles) 38.02 ->
+            # 37.34 ms per update, 4000 envs (188 tiles) 7.30 -> 7.44 - there the extra 148-CTA launch lands on the ragged
+            # chunk's backward (timelines gpurun_out/r2_ppo_timeline_adafwd0/1.txt).  RL_PPO_ADA_FWD_EARLY=0 / 1 forces it.
+            knob = os.environ.get("RL_PPO_ADA_FWD_EARLY", "auto")
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self._ada_pre = pre = (allreduce is None or self._ada_g is not None) and \
+                (knob == "1" or (knob != "0" and (B + 127) // 128 > 3 * sms))
             self._ev_fork.record()
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._ev_fork)
                 if pending:
-                    self._adapt_grads(B, world, lagged=True, loss_event=self._ev_loss)
+                    self._adapt_grads(B, world, lagged=True, loss_event=self._ev_loss, forward=not pre)
                     if allreduce is None or self._ada_g is not None:
                         # the adaptation module's optimiser step stays on the side branch too (nothing on the policy path
                         # reads its weights, gradient or step counter); several GPUs: its gradient is summed here, over
@@ -257,6 +269,8 @@ class PPO:
                     self._ev_grads.record()
                 _lib.check(self._lib.rl_ppo_gather_history(P(flat(st.observation_histories)), P(idx), B, ac.num_hist, P(w["Xh"]),
                                                            ld("Xh"), _lib.current_stream()))
+                if pre:
+                    ac.forward_adaptation(B, save=True)
                 self._ev_join.record()
         stream = _lib.current_stream()
         _lib.check(self._lib.rl_ppo_gather(
@@ -446,7 +460,7 @@ class PPO:
             self._tgt = t = torch.zeros(B, 24, dtype=torch.bfloat16, device=self.device)
         return t
 
-    def _adapt_grads(self, B, world, lagged, loss_event=None):
+    def _adapt_grads(self, B, world, lagged, loss_event=None, forward=True):
         """ppo.py:157-164: adaptation forward, regression loss against the encoder latent, backward; the gradient lands
         in the adaptation range of the flat buffer, the squared error in the per-update accumulator.  lagged: the rows
         are those of the previous call (history already gathered, target in `_tgt`)."""
@@ -457,7 +471,8 @@ class PPO:
         ld = lambda k: w[k].shape[1]
         d = ac.L_ada
         inv_gb = 1.0 / (B * world)
-        ac.forward_adaptation(B, save=True)
+        if forward:             # (lagged schedule: the previous call's side branch may have run it already)
+            ac.forward_adaptation(B, save=True)
         if lagged:
             tgt = self._target(B)
             _lib.check(self._lib.rl_adapt_loss(P(w["pred"]), P(tgt), tgt.shape[1], 0, B, inv_gb, P(w["dpred"]), P(self._loss_acc), stream))
@@ -572,7 +587,7 @@ class PPO:
                     self.minibatch_step(indices[i * mb:(i + 1) * mb], world, allreduce)
         if use_graph and lag:
             # the last minibatch's adaptation update
-            self._adapt_grads(mb, world, lagged=True)
+            self._adapt_grads(mb, world, lagged=True, forward=not getattr(self, "_ada_pre", False))
             self._reduce(allreduce, ac.n_main)
             self._adapt_step(self._g_red if allreduce == "peer" else ac.flat_grad)
         if world > 1:
