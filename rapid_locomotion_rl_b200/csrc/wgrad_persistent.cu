@@ -228,7 +228,7 @@ int wgrad_persistent_launch(const RlWgradProblem* pr, int n, cudaStream_t st) {
   }
   WgArgs A;
   memset(&A, 0, sizeof(A));
-  // k-blocks per work item: about three items per CTA, 32..128 k-blocks each (measured at 24000 rows: 16 / 32 /
+  // k-blocks per work item: about three items per CTA, 48..128 k-blocks each (first measured at 24000 rows: 16 / 32 /
   // 64 k-blocks -> 93 / 69 / 81 us for the 10 policy layers, 44 / 40 / 48 us for the adaptation module)
   long tile_kb = 0;
   for (int i = 0; i < n; ++i) {
@@ -237,8 +237,11 @@ int wgrad_persistent_launch(const RlWgradProblem* pr, int n, cudaStream_t st) {
     const int bn = q.N <= 64 ? 64 : 128;
     tile_kb += (long)((q.M + 127) / 128) * ((q.N + bn - 1) / bn) * ((q.K + 63) / 64);
   }
+  // (re-measured on the final update schedule, A/B on two boxes, ms per update at 4000 envs: 24 / 32 / 40 / 48 / 56 / 64 / 75
+  // k-blocks per item -> 7.54 / 7.32 / 7.31 / 7.22 / 7.37 / 7.42 / 7.71: the lower bound is 48 now; 32768 envs: 96 / 128 / 192 /
+  // 256 -> 37.26 / 37.14 / 37.02 / 37.43, the upper bound stays)
   long kb_item = tile_kb / (3L * sm_count);
-  if (kb_item < 32) kb_item = 32;
+  if (kb_item < 48) kb_item = 48;
   if (kb_item > 128) kb_item = 128;
   { const char* e = getenv("RL_WGRAD_KB"); if (e && atoi(e) > 0) kb_item = atoi(e); }      // tuning override
   int items = 0;

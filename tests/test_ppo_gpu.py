@@ -249,8 +249,12 @@ def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeyp
     g = np.load(os.path.join(golden_dir, "learner.npz"))
     init, storage, perm = learner_case(g)
     out = {}
-    for name, env in (("serial", dict(RL_PPO_OVERLAP="0")), ("lagged", {})):
+    # ("lagged_early": the adaptation forward of minibatch i at the end of call i's side branch - the schedule update() picks by
+    # itself for batches of several waves of row tiles - forced here on the small batch)
+    for name, env in (("serial", dict(RL_PPO_OVERLAP="0")), ("lagged", dict(RL_PPO_ADA_FWD_EARLY="0")),
+                      ("lagged_early", dict(RL_PPO_ADA_FWD_EARLY="1"))):
         monkeypatch.delenv("RL_PPO_OVERLAP", raising=False)
+        monkeypatch.delenv("RL_PPO_ADA_FWD_EARLY", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ac, _ = make_ac()
@@ -266,12 +270,15 @@ def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeyp
         finally:
             torch.randperm = real
         torch.cuda.synchronize()
-        assert ppo._graph_lag == (name == "lagged")
+        assert ppo._graph_lag == (name != "serial")
+        if name != "serial":
+            assert ppo._ada_pre == (name == "lagged_early")
         out[name] = (ac.flat.clone(), res, ppo.learning_rate)
-    d = (out["lagged"][0] - out["serial"][0]).abs().max().item()
-    assert d <= 4e-4, d                                  # 40 Adam steps of |dw| <= lr = 1e-3 each
-    np.testing.assert_allclose(out["lagged"][1], out["serial"][1], rtol=5e-3, atol=1e-6)
-    assert abs(out["lagged"][2] - out["serial"][2]) <= 1e-12
+    for name in ("lagged", "lagged_early"):
+        d = (out[name][0] - out["serial"][0]).abs().max().item()
+        assert d <= 4e-4, (name, d)                      # 40 Adam steps of |dw| <= lr = 1e-3 each
+        np.testing.assert_allclose(out[name][1], out["serial"][1], rtol=5e-3, atol=1e-6)
+        assert abs(out[name][2] - out["serial"][2]) <= 1e-12
 
 
 def _synthetic_rollout(n_envs, T, seed):
