@@ -407,6 +407,9 @@ class PPO:
         # work and the extra launches cost as much as they save)
         if full == 0 or tiles == full or (tiles - full) > 0.7 * sms or tiles > 3 * sms:
             return None
+        split = int(os.environ.get("RL_PPO_CHUNK_SPLIT", "0"))      # A/B knob: tiles in the first chunk (0: the full waves)
+        if 0 < split < tiles:
+            full = split
         return [(0, full), (full, tiles)]
 
     def _reduce(self, allreduce, start, norm_n=0):
