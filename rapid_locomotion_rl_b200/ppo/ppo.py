@@ -550,7 +550,15 @@ class PPO:
         lag = (use_graph and self.overlap_adaptation and ac.use_chain and A.num_adaptation_module_substeps == 1 and
                ac.use_latent)
         ws_gen = getattr(ac, "_ws_gen", 0)
+        # RL_PPO_ONE_GRAPH=1: ALL minibatch steps of the update in ONE graph (each step reads its rows from its own slice of a
+        # [steps, mb] index buffer) - one replay per update instead of 20, no graph-launch gap between steps.  Same results
+        # (test_lagged_schedule_matches_serial_update), measured no faster (4000 envs 7.37 / 7.38 vs 7.26 / 7.35 ms, 32768 envs
+        # 37.9 vs 38.1, profiles/jobs/r2_job74.sh): the side branch already filled the gaps.  Opt-in.
+        n_steps = A.num_learning_epochs * A.num_mini_batches
+        one = use_graph and os.environ.get("RL_PPO_ONE_GRAPH", "0") == "1"
+        shape_key = (one, n_steps, A.num_mini_batches)
         if use_graph and (self._graph is None or self._graph_B != mb or self._graph_lag != lag or self._graph_ws_gen != ws_gen or
+                          getattr(self, "_graph_shape", None) != shape_key or
                           self._graph_reduce != (allreduce if isinstance(allreduce, str) else allreduce is not None)):
             ac.workspace(mb, backward=True)        # allocate outside the capture
             ac.prepare_update_chains()
@@ -568,19 +576,32 @@ class PPO:
                     self._hp = torch.cuda.Stream(device=self.device, priority=-1)
                 kw["stream"] = self._hp
             graphs = []
-            for pending in ((False, True) if lag else (False,)):
+            if one:
+                self._idx_all = torch.zeros(n_steps, mb, dtype=torch.long, device=self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, **kw):
-                    self.minibatch_step(self._idx_buf, world, allreduce, lag=lag, pending=pending)
+                    for k in range(n_steps):
+                        self.minibatch_step(self._idx_all[k], world, allreduce, lag=lag, pending=lag and k > 0)
                 graphs.append(g)
+            else:
+                for pending in ((False, True) if lag else (False,)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, **kw):
+                        self.minibatch_step(self._idx_buf, world, allreduce, lag=lag, pending=pending)
+                    graphs.append(g)
             # capture does not execute, but keep the state bit-identical in any case
             for t, s0 in zip(state, snap):
                 t.copy_(s0)
             self._graph, self._graph_rest, self._graph_B, self._graph_lag = graphs[0], graphs[-1], mb, lag
             self._graph_ws_gen = getattr(ac, "_ws_gen", 0)
+            self._graph_shape = shape_key
             self._graph_reduce = allreduce if isinstance(allreduce, str) else allreduce is not None
         first = True
-        for _ in range(A.num_learning_epochs):
+        if one:
+            # the same permutation serves every epoch (:103): step e * num_mini_batches + i takes slice i
+            self._idx_all.copy_(indices.view(A.num_mini_batches, mb).repeat(A.num_learning_epochs, 1))
+            self._graph.replay()
+        for _ in range(0 if one else A.num_learning_epochs):
             for i in range(A.num_mini_batches):
                 if use_graph:
                     self._idx_buf.copy_(indices[i * mb:(i + 1) * mb])

@@ -252,9 +252,11 @@ def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeyp
     # ("lagged_early": the adaptation forward of minibatch i at the end of call i's side branch - the schedule update() picks by
     # itself for batches of several waves of row tiles - forced here on the small batch)
     for name, env in (("serial", dict(RL_PPO_OVERLAP="0")), ("lagged", dict(RL_PPO_ADA_FWD_EARLY="0")),
-                      ("lagged_early", dict(RL_PPO_ADA_FWD_EARLY="1"))):
+                      ("lagged_early", dict(RL_PPO_ADA_FWD_EARLY="1")),
+                      ("lagged_one_graph", dict(RL_PPO_ADA_FWD_EARLY="0", RL_PPO_ONE_GRAPH="1"))):
         monkeypatch.delenv("RL_PPO_OVERLAP", raising=False)
         monkeypatch.delenv("RL_PPO_ADA_FWD_EARLY", raising=False)
+        monkeypatch.delenv("RL_PPO_ONE_GRAPH", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ac, _ = make_ac()
@@ -274,7 +276,7 @@ def test_lagged_schedule_matches_serial_update(golden_dir, learner_path, monkeyp
         if name != "serial":
             assert ppo._ada_pre == (name == "lagged_early")
         out[name] = (ac.flat.clone(), res, ppo.learning_rate)
-    for name in ("lagged", "lagged_early"):
+    for name in ("lagged", "lagged_early", "lagged_one_graph"):
         d = (out[name][0] - out["serial"][0]).abs().max().item()
         assert d <= 4e-4, (name, d)                      # 40 Adam steps of |dw| <= lr = 1e-3 each
         np.testing.assert_allclose(out[name][1], out["serial"][1], rtol=5e-3, atol=1e-6)
