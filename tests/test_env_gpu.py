@@ -354,7 +354,8 @@ def test_host_io_zero_copy_matches_device_step():
         assert torch.equal(a, b)
 
 
-def test_packed_io_matches_device_step():
+@pytest.mark.parametrize("case", ["mc_flat", "go1"])
+def test_packed_io_matches_device_step(case):
     """pack_io (simulator rows + actions as views of one device block, outputs of another: one H2D and one D2H copy
     per step) gives exactly what the step on separately allocated tensors gives."""
     import numpy as np
@@ -364,7 +365,7 @@ def test_packed_io_matches_device_step():
     n = 4132
     outs = []
     for packed in (False, True):
-        cfg, robot, terrain = build_case("mc_flat", n)
+        cfg, robot, terrain = build_case(case, n)
         env = LeggedRobot(cfg, sim_device="cuda:0", headless=True, terrain=terrain, seed=11)
         p = env.params
         st = synthetic_state(5, n, robot.num_bodies, 12, np.float32(p.default_dof_pos), p.feet_idx, p.term_idx[:p.n_term_bodies])
