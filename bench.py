@@ -432,6 +432,14 @@ def run_ours(args):
     env = None
     del groups
     restore_affinity()
+    # the headline e2e figure: the best of the ways through the public API (all of them: pinned HOST buffers in, results in
+    # host memory, the host waiting for every step) - which one wins depends on how the box's PCIe path treats the copy
+    # engines (boxes of this pool: packed copies 1.07e8 - 1.44e8, kernel-driven zero copy 1.0e8 everywhere)
+    cands = {"separate_copies_two_groups": e2e_value, "packed_copies": e2e_packed or 0.0}
+    for name, v in (("zero_copy_one_group", e2e_zero_copy), ("zero_copy_two_groups", e2e_zero_copy2)):
+        if isinstance(v, float):
+            cands[name] = v
+    e2e_best = max(cands.items(), key=lambda kv: kv[1])
 
     # ---- other sizes (rank 0 only, N=1): the 4000-env configs[1] point and an HBM-resident one -----
     also = {}
@@ -529,11 +537,11 @@ def run_ours(args):
                             (n_rep, n_rep * args.envs * bpe / 1e6),
                    "launch": "K steps captured in one CUDA graph, device-side RNG step counter"},
         "clocks": sampler.summary(),
-        "e2e": {"host_numa": numa, "value": max(e2e_value, e2e_packed or 0.0), "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
+        "e2e": {"host_numa": numa, "value": e2e_best[1], "variant": e2e_best[0], "unit": "env-steps/s", "h2d_bytes_per_step": args.envs * H2D_PER_ENV,
                 "d2h_bytes_per_step": args.envs * D2H_PER_ENV, "steps": k_e2e, "serial_value": e2e_serial, "zero_copy_value": e2e_zero_copy, "zero_copy_two_groups_value": e2e_zero_copy2,
                 "separate_copies_two_groups_value": e2e_value, "packed_three_groups_value": (e2e_packed_by_groups or {}).get(3) if e2e_packed else None,
                 "packed_four_groups_value": (e2e_packed_by_groups or {}).get(4) if e2e_packed else None,
-                "note": "value = the better of two ways through the public API, both with HOST buffers and the host waiting for "
+                "note": "value = the best of the ways through the public API (`variant` names it), all with HOST buffers and the host waiting for "
                         "every step's results: (packed_three_groups_value) LeggedRobot.pack_io - the simulator rows + actions are "
                         "views of ONE pinned block, the outputs of another: one H2D copy, LeggedRobot.step, one D2H copy per step, "
                         "three or four env groups in flight, whichever is faster on this box (packed_three_groups_value, "
